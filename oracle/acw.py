@@ -1,0 +1,77 @@
+"""Oracle: the `acw()` front end on (trials, time) data, ACF-based acwtypes only.
+
+Follows /root/reference/src/core/acw.jl:109-307 (dims = last, trial_dims = 1):
+  complete data -> comp_ac_fft, all n lags           :145-146
+  NaN data      -> comp_ac_time_missing[, n_lags]    :147-154
+  average_over_trials                                :156-158
+  acw0_sample (sample-index lags)                    :160-163
+  :acw0 / :acw50 / :acweuler                         :164-191
+  :auc window = floor(Int, acw0_sample[1]) of the FIRST slice   :192-201
+  n_lags = ceil(Int, 1.1 * nanmaximum(acw0_sample)) or n        :203-210
+  :tau on acf[:, 1:n_lags]                           :212-231
+`:knee` (FOOOF) is out of scope.
+"""
+import math
+
+import numpy as np
+
+from . import acwred, summary
+
+ACF_ACWTYPES = ("acw0", "acw50", "acweuler", "auc", "tau")
+
+
+def acw(data, fs, acwtypes=ACF_ACWTYPES, n_lags=None, average_over_trials=False):
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        data = data.reshape(1, -1)                      # acw.jl:122-125
+    if isinstance(acwtypes, str):
+        acwtypes = (acwtypes,)
+    for t in acwtypes:
+        if t not in ACF_ACWTYPES:
+            raise ValueError(f"unsupported acwtype {t!r}")
+    dt = 1.0 / fs
+    n = data.shape[1]
+    iscomplete = not np.isnan(data).any()
+    if iscomplete:
+        acf = summary.comp_ac_fft(data)
+    else:
+        acf = summary.comp_ac_time_missing(data, n_lags)
+    if average_over_trials:
+        acf = acf.mean(axis=0, keepdims=True)
+    n_slices = acf.shape[0]
+    lags = np.arange(n, dtype=np.float64) * dt
+
+    k0 = np.array([acwred.first_crossing_index(a, 0.0) for a in acf])
+    k50 = np.array([acwred.first_crossing_index(a, 0.5) for a in acf])
+    ke = np.array([acwred.first_crossing_index(a, acwred.INV_E) for a in acf])
+
+    def as_lag(k):
+        return np.where(k >= 0, k * dt, np.nan)
+
+    out = {"k0": k0, "k50": k50, "ke": ke}
+    if "acw0" in acwtypes:
+        out["acw0"] = as_lag(k0)
+    if "acw50" in acwtypes:
+        out["acw50"] = as_lag(k50)
+    if "acweuler" in acwtypes:
+        out["acweuler"] = as_lag(ke)
+    if "auc" in acwtypes:
+        if k0[0] < 0:
+            raise ValueError("InexactError: Int64(NaN)")          # floor(Int, NaN)
+        w = int(k0[0])
+        out["auc"] = np.array([acwred.acw_romberg(dt, a[:w]) for a in acf])
+    if n_lags is None:
+        valid = k0[k0 >= 0]
+        if valid.size == 0:
+            n_lags = n
+        else:
+            n_lags = int(math.ceil(1.1 * float(valid.max())))
+    acf = acf[:, :n_lags]
+    lags = lags[:n_lags]
+    if "tau" in acwtypes:
+        out["tau"] = np.array([acwred.fit_expdecay(lags, a) for a in acf])
+    out["n_lags"] = n_lags
+    out["acf"] = acf
+    out["lags"] = lags
+    out["n_slices"] = n_slices
+    return out

@@ -1,0 +1,310 @@
+/*
+ * CPU oracle (C, fp64) for the IntrinsicTimescales.jl aABC hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY - used by tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py.  Never linked or called by the
+ * product library (libitjl_b200.so).
+ *
+ * It restates, in the reference's own arithmetic order (fp64, FFT-based ACF), the body
+ * of the serial loop in /root/reference/src/core/abc.jl:174-195:
+ *   generate_data_and_reduce          src/core/model.jl:146-151
+ *   generate_ou_process(_sciml)       src/utils/ou_process.jl:46-62, 114-148
+ *   generate_ou_with_oscillation      src/utils/ou_process.jl:176-218
+ *   comp_ac_fft                       src/stats/summary.jl:46-63
+ *   comp_ac_time_missing              src/stats/summary.jl:455-484
+ *   comp_psd_adfriendly               src/stats/summary.jl:204-235
+ *   linear_/logarithmic_distance      src/stats/distances.jl:29-31, 51-53
+ * The SDE solve is restated as the exact OU transition (see oracle/ou.py header);
+ * the noise stream is the Philox4x32-10 stream specified in oracle/philox.py.
+ * PARITY: unpinned against Julia itself (not installable here); pinned against the
+ * NumPy oracle, which is pinned against the reference's KATs (tests/).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+#define PI 3.14159265358979323846
+
+/* ------------------------------------------------------------ Philox ---- */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+static inline double u01(uint32_t r) { return ((double)(r >> 8) + 0.5) * (1.0 / 16777216.0); }
+static inline void box_muller(uint32_t ra, uint32_t rb, double* z0, double* z1) {
+    double rad = sqrt(-2.0 * log(u01(ra)));
+    double ang = 2.0 * PI * u01(rb);
+    *z0 = rad * cos(ang); *z1 = rad * sin(ang);
+}
+static inline uint32_t c3_word(uint32_t stream, uint64_t gen) {
+    return ((stream & 0xFu) << 28) | (uint32_t)(gen & 0x0FFFFFFFu);
+}
+
+/* --------------------------------------------------------------- FFT ---- */
+typedef struct { int n; double* wr; double* wi; int* rev; } fft_plan;
+
+static fft_plan* fft_plan_create(int n) {
+    fft_plan* p = (fft_plan*)malloc(sizeof(fft_plan));
+    p->n = n;
+    p->wr = (double*)malloc(sizeof(double) * (n / 2));
+    p->wi = (double*)malloc(sizeof(double) * (n / 2));
+    p->rev = (int*)malloc(sizeof(int) * n);
+    for (int i = 0; i < n / 2; ++i) {
+        p->wr[i] = cos(-2.0 * PI * i / n);
+        p->wi[i] = sin(-2.0 * PI * i / n);
+    }
+    int bits = 0; while ((1 << bits) < n) ++bits;
+    for (int i = 0; i < n; ++i) {
+        int r = 0;
+        for (int b = 0; b < bits; ++b) if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+        p->rev[i] = r;
+    }
+    return p;
+}
+static void fft_plan_destroy(fft_plan* p) { free(p->wr); free(p->wi); free(p->rev); free(p); }
+
+/* in-place forward complex FFT (inverse = conj trick by caller) */
+static void fft_exec(const fft_plan* p, double* re, double* im) {
+    int n = p->n;
+    for (int i = 0; i < n; ++i) {
+        int r = p->rev[i];
+        if (r > i) { double t = re[i]; re[i] = re[r]; re[r] = t; t = im[i]; im[i] = im[r]; im[r] = t; }
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        int half = len >> 1, step = n / len;
+        for (int s = 0; s < n; s += len) {
+            for (int j = 0; j < half; ++j) {
+                double wr = p->wr[j * step], wi = p->wi[j * step];
+                int a = s + j, b = a + half;
+                double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr; im[b] = im[a] - xi;
+                re[a] += xr; im[a] += xi;
+            }
+        }
+    }
+}
+
+static int nextpow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+/* ------------------------------------------------------------ model ----- */
+typedef struct {
+    int32_t kind;        /* 0 plain OU, 1 OU + oscillation */
+    int32_t summary;     /* 0 ACF (comp_ac_fft), 1 ACF missing, 2 PSD hamming */
+    int32_t distance;    /* 0 linear, 1 logarithmic */
+    int32_t update;      /* 0 exact, 1 Euler-Maruyama */
+    int64_t n_trials, n_t;
+    double dt, data_mean, data_sd;
+    int64_t n_stats;
+    const double* target_stats;
+    const uint8_t* missing_mask;   /* column-major (trials x n_t), 1 = missing */
+    const int32_t* freq_bins;      /* 0-based indices into psd[2:n2/2] */
+} oracle_model_desc;
+
+typedef struct {
+    double *x, *re, *im, *acc, *win;
+    fft_plan* plan;
+    int n_fft;
+    double win_ss;
+} workspace;
+
+static workspace* ws_create(const oracle_model_desc* m) {
+    workspace* w = (workspace*)calloc(1, sizeof(workspace));
+    int n = (int)m->n_t;
+    w->n_fft = (m->summary == 2) ? 2 * nextpow2(n) : nextpow2(2 * n - 1);
+    w->plan = fft_plan_create(w->n_fft);
+    w->x = (double*)malloc(sizeof(double) * n);
+    w->re = (double*)malloc(sizeof(double) * w->n_fft);
+    w->im = (double*)malloc(sizeof(double) * w->n_fft);
+    int nacc = (m->summary == 2) ? w->n_fft / 2 : (int)m->n_stats;
+    w->acc = (double*)malloc(sizeof(double) * (nacc > 0 ? nacc : 1));
+    w->win = (double*)malloc(sizeof(double) * n);
+    w->win_ss = 0.0;
+    for (int i = 0; i < n; ++i) {
+        w->win[i] = 0.54 - 0.46 * cos(2.0 * PI * i / (n - 1));
+        w->win_ss += w->win[i] * w->win[i];
+    }
+    return w;
+}
+static void ws_destroy(workspace* w) {
+    fft_plan_destroy(w->plan); free(w->x); free(w->re); free(w->im); free(w->acc); free(w->win); free(w);
+}
+
+/* one particle: returns the distance */
+static double particle_distance(const oracle_model_desc* m, workspace* w, const double* theta,
+                                uint64_t seed, uint64_t gen, uint64_t particle,
+                                const double* u0_in, const double* noise_in, const double* phase_in) {
+    const int n = (int)m->n_t, ntr = (int)m->n_trials;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const double tau = theta[0];
+    double a, s;
+    if (m->update == 0) { a = exp(-m->dt / tau); s = sqrt(tau / 2.0 * (1.0 - a * a)); }
+    else { a = 1.0 - m->dt / tau; s = sqrt(m->dt); }
+    double freq = 0.0, coeff = 1.0;
+    if (m->kind == 1) {
+        freq = theta[1]; coeff = theta[2];
+        if (coeff < 0.0) coeff = 1e-4; else if (coeff > 1.0) coeff = 1.0 - 1e-4;
+    }
+    const int nacc = (m->summary == 2) ? w->n_fft / 2 : (int)m->n_stats;
+    for (int i = 0; i < nacc; ++i) w->acc[i] = 0.0;
+    int bad = 0;
+
+    for (int tr = 0; tr < ntr; ++tr) {
+        double u0, phase;
+        {
+            uint32_t c[4] = {0u, (uint32_t)tr, (uint32_t)particle, c3_word(1, gen)};
+            philox4x32_10(c, k0, k1);
+            double z1;
+            box_muller(c[0], c[1], &u0, &z1);
+            phase = 2.0 * PI * u01(c[2]);
+        }
+        if (u0_in) u0 = u0_in[tr];
+        if (phase_in) phase = phase_in[tr];
+        double prev = u0;
+        for (int j = 0; j < n; j += 4) {
+            double z[4] = {0.0, 0.0, 0.0, 0.0};
+            if (noise_in) {
+                for (int q = 0; q < 4 && j + q < n; ++q) z[q] = noise_in[(size_t)tr * n + j + q];
+            } else {
+                uint32_t c[4] = {(uint32_t)(j >> 2), (uint32_t)tr, (uint32_t)particle, c3_word(0, gen)};
+                philox4x32_10(c, k0, k1);
+                box_muller(c[0], c[1], &z[0], &z[1]);
+                box_muller(c[2], c[3], &z[2], &z[3]);
+            }
+            for (int q = 0; q < 4 && j + q < n; ++q) { prev = a * prev + s * z[q]; w->x[j + q] = prev; }
+        }
+        if (m->kind == 1) {
+            double sc = sqrt(coeff), so = sqrt(1.0 - coeff) * sqrt(2.0);
+            for (int j = 0; j < n; ++j) {
+                double t = m->dt * (double)(j + 1);
+                w->x[j] = so * sin(phase + 2.0 * PI * freq * t) + sc * w->x[j];
+            }
+        }
+        /* standardise: (x - mean) / std(n-1) * scale (+ mean for the osc model) */
+        double mean = 0.0;
+        for (int j = 0; j < n; ++j) mean += w->x[j];
+        mean /= n;
+        double ss = 0.0;
+        for (int j = 0; j < n; ++j) { double d = w->x[j] - mean; ss += d * d; }
+        double sd = sqrt(ss / (n - 1));
+        double scale = m->data_sd / sd;
+        double shift = (m->kind == 1) ? m->data_mean : 0.0;
+        for (int j = 0; j < n; ++j) w->x[j] = (w->x[j] - mean) * scale + shift;
+        for (int j = 0; j < n; ++j) if (!isfinite(w->x[j])) { bad = 1; break; }
+        if (bad) break;
+
+        if (m->summary == 0) {
+            /* comp_ac_fft */
+            double m2 = 0.0;
+            for (int j = 0; j < n; ++j) m2 += w->x[j];
+            m2 /= n;
+            for (int j = 0; j < n; ++j) { w->re[j] = w->x[j] - m2; w->im[j] = 0.0; }
+            for (int j = n; j < w->n_fft; ++j) { w->re[j] = 0.0; w->im[j] = 0.0; }
+            fft_exec(w->plan, w->re, w->im);
+            for (int j = 0; j < w->n_fft; ++j) {
+                w->re[j] = w->re[j] * w->re[j] + w->im[j] * w->im[j]; w->im[j] = 0.0;
+            }
+            fft_exec(w->plan, w->re, w->im);     /* real even input: forward == inverse * n */
+            double inv0 = 1.0 / w->re[0];
+            for (int k = 0; k < (int)m->n_stats; ++k) w->acc[k] += w->re[k] * inv0;
+        } else if (m->summary == 1) {
+            /* comp_ac_time_missing with the model's mask applied (NaN -> 0, then
+               subtract the valid-sample mean from every entry) */
+            double sum = 0.0; int nv = 0;
+            for (int j = 0; j < n; ++j) {
+                int miss = m->missing_mask ? m->missing_mask[(size_t)j * ntr + tr] : 0;
+                if (miss) w->x[j] = 0.0; else { sum += w->x[j]; ++nv; }
+            }
+            double xm = sum / nv;
+            double ssq = 0.0;
+            for (int j = 0; j < n; ++j) { w->x[j] -= xm; ssq += w->x[j] * w->x[j]; }
+            for (int k = 0; k < (int)m->n_stats; ++k) {
+                double acc = 0.0;
+                for (int j = 0; j + k < n; ++j) acc += w->x[j] * w->x[j + k];
+                w->acc[k] += acc / ssq;
+            }
+        } else {
+            /* comp_psd_adfriendly */
+            double m2 = 0.0;
+            for (int j = 0; j < n; ++j) m2 += w->x[j];
+            m2 /= n;
+            for (int j = 0; j < n; ++j) { w->re[j] = (w->x[j] - m2) * w->win[j]; w->im[j] = 0.0; }
+            for (int j = n; j < w->n_fft; ++j) { w->re[j] = 0.0; w->im[j] = 0.0; }
+            fft_exec(w->plan, w->re, w->im);
+            double scl = 1.0 / ((1.0 / m->dt) * w->win_ss);
+            for (int j = 0; j < w->n_fft / 2; ++j)
+                w->acc[j] += (w->re[j] * w->re[j] + w->im[j] * w->im[j]) * scl;
+        }
+    }
+    if (bad) return NAN;
+    double d = 0.0;
+    for (int k = 0; k < (int)m->n_stats; ++k) {
+        double v;
+        if (m->summary == 2) v = w->acc[m->freq_bins[k] + 1] / ntr;   /* +1: DC dropped */
+        else v = w->acc[k] / ntr;
+        double e = (m->distance == 0) ? (v - m->target_stats[k]) : (log(v) - log(m->target_stats[k]));
+        d += e * e;
+    }
+    return d / (double)m->n_stats;
+}
+
+/* theta: column-major (n_particles x p) like a Julia Matrix.  u0/phases: (particle, trial)
+ * row-major; noise: (particle, trial, n_t) row-major; any of them may be NULL (Philox).
+ * Particles are independent; they are spread over n_threads pthreads (dynamic chunks of 1). */
+typedef struct {
+    const oracle_model_desc* m; const double* theta; int64_t n_particles; int32_t n_theta;
+    uint64_t seed, generation; int64_t particle_offset;
+    const double *u0, *noise, *phases; double* dist_out; atomic_llong* next;
+} job_t;
+
+static void* worker(void* arg) {
+    job_t* j = (job_t*)arg;
+    const oracle_model_desc* m = j->m;
+    workspace* w = ws_create(m);
+    for (;;) {
+        int64_t i = (int64_t)atomic_fetch_add(j->next, 1);
+        if (i >= j->n_particles) break;
+        double th[8] = {0.0};
+        for (int q = 0; q < j->n_theta && q < 8; ++q) th[q] = j->theta[(size_t)q * j->n_particles + i];
+        size_t pt = (size_t)i * m->n_trials;
+        j->dist_out[i] = particle_distance(m, w, th, j->seed, j->generation,
+                                           (uint64_t)(j->particle_offset + i),
+                                           j->u0 ? j->u0 + pt : NULL,
+                                           j->noise ? j->noise + pt * m->n_t : NULL,
+                                           j->phases ? j->phases + pt : NULL);
+    }
+    ws_destroy(w);
+    return NULL;
+}
+
+int itjl_oracle_max_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+int itjl_oracle_abc_distances(const oracle_model_desc* m, const double* theta, int64_t n_particles,
+                              int32_t n_theta, uint64_t seed, uint64_t generation,
+                              int64_t particle_offset, const double* u0, const double* noise,
+                              const double* phases, double* dist_out, int32_t n_threads) {
+    if (n_threads <= 0) n_threads = itjl_oracle_max_threads();
+    if (n_threads > 256) n_threads = 256;
+    if ((int64_t)n_threads > n_particles) n_threads = (int32_t)(n_particles > 0 ? n_particles : 1);
+    atomic_llong next = 0;
+    job_t job = {m, theta, n_particles, n_theta, seed, generation, particle_offset,
+                 u0, noise, phases, dist_out, &next};
+    if (n_threads == 1) { worker(&job); return 0; }
+    pthread_t tid[256];
+    for (int t = 0; t < n_threads; ++t)
+        if (pthread_create(&tid[t], NULL, worker, &job) != 0) return -1;
+    for (int t = 0; t < n_threads; ++t) pthread_join(tid[t], NULL);
+    return 0;
+}

@@ -1,0 +1,106 @@
+"""Oracle: summary statistics (ACF / NaN-aware ACF / Hamming periodogram).
+
+Follows /root/reference/src/stats/summary.jl:
+  comp_ac_fft           :46-63 (vector), :79-89 (array)
+  comp_psd_adfriendly   :183-235
+  comp_ac_time_missing  :455-484 (vector), :486-496 (array)
+and /root/reference/src/stats/bat_autocor.jl:21-24 (_ac_next_pow_two).
+Arrays are (trials, time): the reference's default dims=ndims(data).
+"""
+import numpy as np
+
+
+def nextpow2(n):
+    """nextpow(2, n)."""
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+def _ac_next_pow_two(i):
+    """bat_autocor.jl:21-24: smallest power of two >= i (i > 0)."""
+    return nextpow2(i) if i > 0 else 1
+
+
+def comp_ac_fft_vec(x, n_lags=None):
+    """summary.jl:46-63."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    if n_lags is None:
+        n_lags = n
+    xc = x - x.mean()
+    n_pad = nextpow2(2 * n - 1)
+    f = np.fft.fft(xc, n_pad)
+    acov = np.real(np.fft.ifft(np.abs(f) ** 2))[:n] / n
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ac = acov / acov[0]
+    return ac[:n_lags]
+
+
+def comp_ac_fft(data, n_lags=None):
+    """summary.jl:79-89 on (trials, time) -> (trials, n_lags)."""
+    data = np.atleast_2d(np.asarray(data, dtype=np.float64))
+    return np.stack([comp_ac_fft_vec(r, n_lags) for r in data])
+
+
+def comp_ac_direct_vec(x, n_lags):
+    """Time-domain restatement of comp_ac_fft (identical up to fp64 rounding; the
+    reference's own cross-check is test/test_summary_stats.jl:57-74)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    xc = x - x.mean()
+    ac = np.array([np.dot(xc[:n - k], xc[k:]) for k in range(n_lags)])
+    return ac / ac[0]
+
+
+def comp_ac_time_missing_vec(x, n_lags=None):
+    """summary.jl:455-484.  Note the reference's quirk: after NaNs are zeroed the
+    valid-sample mean is subtracted from EVERY entry, so masked samples become
+    -mean rather than 0 (:466-471)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    if n_lags is None:
+        n_lags = n
+    valid = ~np.isnan(x)
+    z = np.where(valid, x, 0.0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        xm = z.sum() / valid.sum()
+        z = z - xm
+        ss = np.sum(z * z) / n
+        ac = np.array([np.dot(z[:n - k], z[k:]) / n for k in range(n_lags)])
+        return ac / ss
+
+
+def comp_ac_time_missing(data, n_lags=None):
+    """summary.jl:486-496."""
+    data = np.atleast_2d(np.asarray(data, dtype=np.float64))
+    return np.stack([comp_ac_time_missing_vec(r, n_lags) for r in data])
+
+
+def hamming_window(n):
+    """summary.jl:214."""
+    return 0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(n) / (n - 1))
+
+
+def comp_psd_adfriendly_vec(x, fs, demean=True):
+    """summary.jl:204-235 -> (psd[2:n2/2], freqs[2:n2/2])."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    n2 = 2 * _ac_next_pow_two(n)
+    xd = x - x.mean() if demean else x
+    w = hamming_window(n)
+    xp = np.zeros(n2)
+    xp[:n] = xd * w
+    scale = 1.0 / (fs * np.sum(w ** 2))
+    xf = np.fft.fft(xp)
+    psd = np.abs(xf[:n2 // 2]) ** 2 * scale
+    freqs = np.fft.fftfreq(n2, 1.0 / fs)[:n2 // 2]
+    return psd[1:], freqs[1:]
+
+
+def comp_psd_adfriendly(data, fs):
+    """summary.jl:183-202 on (trials, time) -> ((trials, n2/2-1), freqs)."""
+    data = np.atleast_2d(np.asarray(data, dtype=np.float64))
+    rows = [comp_psd_adfriendly_vec(r, fs) for r in data]
+    return np.stack([r[0] for r in rows]), rows[0][1]
