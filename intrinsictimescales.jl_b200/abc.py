@@ -1,0 +1,337 @@
+"""ABC / PMC-ABC driver with the per-particle loop body on the GPU.
+
+Mirrors src/core/abc.jl (names, keyword arguments, defaults, return fields):
+  basic_abc               :156-215   serial rejection loop  ->  batched: proposals are drawn
+                                     for a chunk, the fused kernel scores the chunk, K3 applies
+                                     `d <= epsilon` and the sequential stopping rule, and the
+                                     chunk is truncated at the min_accepted-th acceptance, so
+                                     n_total / acceptance rates are distributed as in the serial code
+  draw_theta_pmc          :101-117   vectorised (same resample + MvNormal + redraw-while-negative)
+  pmc_abc                 :287-502
+  calc_weights            :520-567   (Gaussian-mixture denominator; the reference's 1-parameter
+                                      branch :533-544 reads an uninitialised buffer - see DESIGN.md)
+  weighted_covar          :582-613
+  effective_sample_size   :632-642
+  select_epsilon          :700-761
+  compute_adaptive_alpha  :807-837
+  find_MAP                :852-873   (Gaussian KDE on a random grid; KernelDensity.jl's
+                                      bandwidth rule is not restated - not on the hot path)
+  get_param_dict_abc      :932-974
+  ABCResults/abc_results  :34-84
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+def get_param_dict_abc():
+    return dict(epsilon_0=1.0, max_iter=10000, min_accepted=100, steps=30, sample_only=False,
+                minAccRate=0.01, target_acc_rate=0.01, target_epsilon=1e-4, show_progress=True,
+                verbose=True, jitter=1e-6, distance_max=10.0, quantile_lower=25.0,
+                quantile_upper=75.0, quantile_init=50.0, acc_rate_buffer=0.1, alpha_max=0.9,
+                alpha_min=0.1, acc_rate_far=2.0, acc_rate_close=0.2, alpha_far_mult=1.5,
+                alpha_close_mult=0.5, convergence_window=5, theta_rtol=1e-2, theta_atol=1e-3,
+                N=10000)
+
+
+@dataclass
+class ABCResults:
+    theta_history: list
+    epsilon_history: list
+    acc_rate_history: list
+    weights_history: list
+    final_theta: np.ndarray
+    final_weights: np.ndarray
+    MAP: np.ndarray
+
+
+# ------------------------------------------------------------- proposals ----
+def draw_theta_prior(model, rng, n):
+    """n i.i.d. draws of [rand(p) for p in prior] (model.jl:154-156) -> (n, n_theta)."""
+    return np.stack([np.asarray(p.rand(rng, n), dtype=np.float64) for p in model.prior], axis=1)
+
+
+def draw_theta_pmc(model, theta_prev, weights, tau_squared, rng, n=1, jitter=1e-5):
+    """n i.i.d. PMC proposals (abc.jl:101-117): theta* resampled with the weights, then
+    MvNormal(theta*, tau_squared + jitter I), redrawn while any component is negative."""
+    theta_prev = np.atleast_2d(np.asarray(theta_prev, dtype=np.float64))
+    w = np.asarray(weights, dtype=np.float64)
+    p = theta_prev.shape[1]
+    cov = np.atleast_2d(np.asarray(tau_squared, dtype=np.float64)) + jitter * np.eye(p)
+    chol = np.linalg.cholesky(cov)
+    cdf = np.cumsum(w / w.sum())
+    idx = np.minimum(np.searchsorted(cdf, rng.random(n), side="right"), w.size - 1)
+    stars = theta_prev[idx]
+    out = stars + rng.standard_normal((n, p)) @ chol.T
+    bad = np.nonzero(np.any(out < 0, axis=1))[0]
+    while bad.size:                                   # redraw around the SAME theta*
+        out[bad] = stars[bad] + rng.standard_normal((bad.size, p)) @ chol.T
+        bad = bad[np.any(out[bad] < 0, axis=1)]
+    return out
+
+
+# ------------------------------------------------------------- basic_abc ----
+def _first_chunk(max_iter, min_accepted, sm_count):
+    return int(min(max_iter, max(2 * sm_count, 2 * min_accepted)))
+
+
+def basic_abc(model, epsilon, max_iter, min_accepted, pmc_mode=False, weights=None, theta_prev=None,
+              tau_squared=None, show_progress=False, rng=None, seed=0, generation=0, ctx=None,
+              scorer=None, proposals=None):
+    """Returns the reference's NamedTuple as a dict: samples, isaccepted, theta_accepted,
+    distances, n_accepted, n_total, epsilon, weights, tau_squared, eff_sample.
+
+    `scorer(theta_chunk, epsilon, needed, generation, particle_offset)` ->
+    (dist, isaccepted, n_total, n_accepted) defaults to the single-GPU fused kernels; the
+    multi-GPU sharded scorer lives in distributed.py.  `proposals` (max_iter, n_theta)
+    overrides the proposal draws (parity tests)."""
+    rng = rng or np.random.default_rng()
+    n_theta = len(model.prior)
+    if scorer is None:
+        gm = model.gpu_model(ctx)
+        sm = gm.ctx.sm_count
+
+        def scorer(th, eps, needed, gen, off):
+            return gm.generation(th, eps, needed, seed=seed, generation=gen, particle_offset=off)
+    else:
+        sm = 148
+    samples = np.zeros((max_iter, n_theta))
+    distances = np.zeros(max_iter)
+    offset = 0
+    accepted = 0
+    it = 0
+    chunk = _first_chunk(max_iter, min_accepted, sm)
+    while offset < max_iter:
+        n = min(chunk, max_iter - offset)
+        if proposals is not None:
+            th = np.asarray(proposals[offset:offset + n], dtype=np.float64)
+        elif pmc_mode:
+            th = draw_theta_pmc(model, theta_prev, weights, tau_squared, rng, n)
+        else:
+            th = draw_theta_prior(model, rng, n)
+        needed = min_accepted - accepted
+        d, _, n_tot, n_acc = scorer(th, float(epsilon), int(needed), int(generation), int(offset))
+        samples[offset:offset + n_tot] = th[:n_tot]
+        distances[offset:offset + n_tot] = d[:n_tot]
+        accepted += n_acc
+        it = offset + n_tot
+        offset += n
+        if needed > 0 and n_acc >= needed:
+            break                                           # abc.jl:190-194
+        rate = accepted / offset if offset else 0.0
+        if rate > 0.0:
+            want = int(1.25 * (min_accepted - accepted) / rate) + 1
+            chunk = int(min(max(want, 2 * sm), 4 * chunk))
+        else:
+            chunk = 4 * chunk
+    dist = distances[:it].copy()
+    isacc = dist <= epsilon
+    theta_accepted = samples[:it][isacc]
+    return dict(samples=samples, isaccepted=isacc, theta_accepted=theta_accepted, distances=dist,
+                n_accepted=int(isacc.sum()), n_total=int(it), epsilon=float(epsilon),
+                weights=np.ones(theta_accepted.size), tau_squared=np.zeros((theta_accepted.size,) * 2)
+                if theta_accepted.size < 4096 else None, eff_sample=theta_accepted.size)
+
+
+# ------------------------------------------------------ PMC bookkeeping ----
+def percentile(x, p):
+    """StatsBase.percentile (quantile type 7)."""
+    return float(np.percentile(np.asarray(x, dtype=np.float64), p, method="linear"))
+
+
+def compute_adaptive_alpha(iteration, current_acc_rate, target_acc_rate, alpha_max=0.9, alpha_min=0.1,
+                           total_iterations=100, acc_rate_far=2.0, acc_rate_close=0.2,
+                           alpha_far_mult=1.5, alpha_close_mult=0.5):
+    progress = iteration / total_iterations
+    base_alpha = alpha_max * (1 - progress) + alpha_min * progress
+    acc_rate_diff = abs(current_acc_rate - target_acc_rate) / target_acc_rate
+    if acc_rate_diff > acc_rate_far:
+        return min(alpha_max, base_alpha * alpha_far_mult)
+    if acc_rate_diff < acc_rate_close:
+        return max(alpha_min, base_alpha * alpha_close_mult)
+    return base_alpha
+
+
+def select_epsilon(distances, current_epsilon, target_acc_rate=0.01, current_acc_rate=0.0, iteration=1,
+                   total_iterations=100, distance_max=10.0, quantile_lower=25.0, quantile_upper=75.0,
+                   quantile_init=50.0, acc_rate_buffer=0.1, alpha_max=0.9, alpha_min=0.1,
+                   acc_rate_far=2.0, acc_rate_close=0.2, alpha_far_mult=1.5, alpha_close_mult=0.5):
+    d = np.asarray(distances, dtype=np.float64)
+    valid = d[~np.isnan(d)]
+    valid = valid[valid < distance_max]
+    if valid.size == 0:
+        return current_epsilon
+    q_lower = percentile(valid, quantile_lower)
+    q_init = percentile(valid, quantile_init)
+    q_upper = percentile(valid, quantile_upper)
+    alpha = compute_adaptive_alpha(iteration, current_acc_rate, target_acc_rate, alpha_max=alpha_max,
+                                   alpha_min=alpha_min, total_iterations=total_iterations,
+                                   acc_rate_far=acc_rate_far, acc_rate_close=acc_rate_close,
+                                   alpha_far_mult=alpha_far_mult, alpha_close_mult=alpha_close_mult)
+    if iteration == 1:
+        return q_init
+    if current_acc_rate > 0.0:
+        if current_acc_rate > target_acc_rate * (1.0 + acc_rate_buffer):
+            return max(q_lower, current_epsilon * (1.0 - alpha))
+        if current_acc_rate < target_acc_rate * (1.0 - acc_rate_buffer):
+            return min(q_upper, current_epsilon * (1.0 + alpha))
+    return current_epsilon            # reference: UndefVarError when the rate is exactly 0
+
+
+def calc_weights(theta_prev, theta, tau_squared, weights, prior, block=2048):
+    theta_prev = np.atleast_2d(np.asarray(theta_prev, dtype=np.float64))
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    if theta_prev.shape[0] == 1 and theta_prev.shape[1] != len(prior):
+        theta_prev = theta_prev.T
+    if theta.shape[0] == 1 and theta.shape[1] != len(prior):
+        theta = theta.T
+    cov = np.atleast_2d(np.asarray(tau_squared, dtype=np.float64))
+    w = np.asarray(weights, dtype=np.float64)
+    k = theta.shape[1]
+    prec = np.linalg.inv(cov)
+    norm = 1.0 / math.sqrt((2.0 * math.pi) ** k * np.linalg.det(cov))
+    pri = np.ones(theta.shape[0])
+    for j, p in enumerate(prior):
+        pri *= p.pdf(theta[:, j])
+    new = np.empty(theta.shape[0])
+    for s in range(0, theta.shape[0], block):
+        diff = theta[s:s + block, None, :] - theta_prev[None, :, :]
+        quad = np.einsum("ijk,kl,ijl->ij", diff, prec, diff)
+        new[s:s + block] = pri[s:s + block] / ((np.exp(-0.5 * quad) * norm) @ w)
+    return new / new.sum()
+
+
+def weighted_covar(x, w):
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    w_norm = np.asarray(w, dtype=np.float64) / np.sum(w)
+    sumw = w_norm.sum()
+    if not math.isclose(sumw, 1.0, rel_tol=1e-10):
+        return np.zeros((x.shape[1], x.shape[1]))
+    sum2 = np.sum(w_norm ** 2)
+    xbar = (w_norm[:, None] * x).sum(axis=0)
+    xc = x - xbar
+    covar = (xc * w_norm[:, None]).T @ xc
+    return covar * sumw / (sumw * sumw - sum2)
+
+
+def effective_sample_size(w):
+    w = np.asarray(w, dtype=np.float64)
+    return float(w.sum() ** 2 / np.sum(w ** 2))
+
+
+def find_MAP(theta_accepted, N=10000, rng=None):
+    from scipy.stats import gaussian_kde
+    rng = rng or np.random.default_rng()
+    theta_accepted = np.atleast_2d(np.asarray(theta_accepted, dtype=np.float64))
+    out = np.empty(theta_accepted.shape[1])
+    for i in range(theta_accepted.shape[1]):
+        col = theta_accepted[:, i]
+        pos = rng.uniform(col.min(), col.max(), N)
+        if col.size < 2 or col.min() == col.max():
+            out[i] = col[0]
+            continue
+        out[i] = pos[int(np.argmax(gaussian_kde(col, bw_method="silverman")(pos)))]
+    return out
+
+
+def abc_results(output_record, rng=None):
+    final_theta = output_record[-1]["theta_accepted"]
+    return ABCResults([r["theta_accepted"] for r in output_record],
+                      [r["epsilon"] for r in output_record],
+                      [r["n_accepted"] / r["n_total"] for r in output_record],
+                      [r["weights"] for r in output_record],
+                      final_theta, output_record[-1]["weights"],
+                      find_MAP(final_theta, rng=rng) if final_theta.size else np.full(final_theta.shape[1], np.nan))
+
+
+def pmc_abc(model, epsilon_0=1.0, max_iter=10000, min_accepted=100, steps=10, sample_only=False,
+            minAccRate=0.01, target_acc_rate=0.01, target_epsilon=5e-3, show_progress=False,
+            verbose=False, jitter=1e-6, distance_max=10.0, quantile_lower=25.0, quantile_upper=75.0,
+            quantile_init=50.0, acc_rate_buffer=0.1, alpha_max=0.9, alpha_min=0.1, acc_rate_far=2.0,
+            acc_rate_close=0.2, alpha_far_mult=1.5, alpha_close_mult=0.5, convergence_window=3,
+            theta_rtol=1e-2, theta_atol=1e-3, rng=None, seed=0, ctx=None, scorer=None,
+            return_record=False, **_unused):
+    rng = rng or np.random.default_rng(seed)
+    eps_kw = dict(target_acc_rate=target_acc_rate, distance_max=distance_max,
+                  quantile_lower=quantile_lower, quantile_upper=quantile_upper,
+                  quantile_init=quantile_init, acc_rate_buffer=acc_rate_buffer, alpha_max=alpha_max,
+                  alpha_min=alpha_min, acc_rate_far=acc_rate_far, acc_rate_close=acc_rate_close,
+                  alpha_far_mult=alpha_far_mult, alpha_close_mult=alpha_close_mult)
+    record = []
+    epsilon = float(epsilon_0)
+    theta_history = []
+    ndim = len(model.prior)
+
+    def finish():
+        res = abc_results(record, rng=rng)
+        return (res, record) if return_record else res
+
+    for i_step in range(1, steps + 1):
+        if verbose:
+            print(f"Starting step {i_step}\nepsilon = {epsilon}")
+        if i_step == 1:
+            result = basic_abc(model, epsilon, max_iter, min_accepted, pmc_mode=False, rng=rng,
+                               seed=seed, generation=i_step, ctx=ctx, scorer=scorer)
+            epsilon = select_epsilon(result["distances"], epsilon, **eps_kw)
+            theta = result["theta_accepted"]
+            tau_squared = 2.0 * np.atleast_2d(np.cov(theta, rowvar=False)) + jitter * np.eye(ndim)
+            weights = np.full(theta.shape[0], 1.0 / theta.shape[0])
+            eff = effective_sample_size(weights)
+        else:
+            prev = record[-1]
+            result = basic_abc(model, epsilon, max_iter, min_accepted, pmc_mode=True,
+                               weights=prev["weights"], theta_prev=prev["theta_accepted"],
+                               tau_squared=prev["tau_squared"], rng=rng, seed=seed, generation=i_step,
+                               ctx=ctx, scorer=scorer)
+            theta = result["theta_accepted"]
+            eff = effective_sample_size(prev["weights"])
+            if sample_only:
+                weights = np.zeros(0); tau_squared = np.zeros((0, 0))
+            else:
+                weights = calc_weights(prev["theta_accepted"], theta, prev["tau_squared"],
+                                       prev["weights"], model.prior)
+                tau_squared = 2.0 * weighted_covar(theta, weights)
+            current_acc_rate = result["n_accepted"] / result["n_total"]
+            epsilon = select_epsilon(result["distances"], epsilon, current_acc_rate=current_acc_rate,
+                                     iteration=i_step, total_iterations=steps, **eps_kw)
+        record.append(dict(theta_accepted=theta, D_accepted=result["distances"],
+                           n_accepted=result["n_accepted"], n_total=result["n_total"], epsilon=epsilon,
+                           weights=weights, tau_squared=tau_squared, eff_sample=eff))
+        current_theta = theta.mean(axis=0, keepdims=True) if theta.size else np.full((1, ndim), np.nan)
+        accept_rate = result["n_accepted"] / result["n_total"]
+        if verbose:
+            print(f"Acceptance Rate = {accept_rate}\nCurrent theta = {current_theta}\n--------------------")
+        if accept_rate < minAccRate:
+            return finish()
+        theta_history.append(current_theta)
+        if len(theta_history) >= convergence_window:
+            converged = True
+            for dim in range(ndim):
+                recent = [float(h[:, dim].mean()) for h in theta_history[-convergence_window:]]
+                param_range = max(recent) - min(recent)
+                param_mean = float(np.mean(recent))
+                if not (param_range / abs(param_mean) < theta_rtol or param_range < theta_atol):
+                    converged = False
+                    break
+            if converged:
+                if verbose:
+                    print(f"Parameters converged after {i_step} iterations")
+                return finish()
+        if epsilon < target_epsilon:
+            return finish()
+    return finish()
+
+
+def int_fit(model, param_dict=None, **kw):
+    """Models.int_fit(model, param_dict) for fit_method = :abc (one_timescale.jl:352-401)."""
+    if model.fit_method != "abc":
+        raise NotImplementedError("only fit_method=:abc runs on the B200 path")
+    params = get_param_dict_abc()
+    if param_dict:
+        params.update(param_dict)
+    params.update(kw)
+    params.pop("N", None)
+    return pmc_abc(model, **params)

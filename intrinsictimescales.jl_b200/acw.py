@@ -1,0 +1,110 @@
+"""`acw(data, fs; ...)` on the GPU - mirror of src/core/acw.jl:109-307 for the ACF-based
+acwtypes (:acw0, :acw50, :acweuler, :auc, :tau).  `:knee` is outside the accelerated path.
+"""
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+
+possible_acwtypes = ["acw0", "acw50", "acweuler", "auc", "tau"]
+_BITS = {"acw0": _lib.ACW0, "acw50": _lib.ACW50, "acweuler": _lib.ACWEULER,
+         "auc": _lib.AUC, "tau": _lib.TAU}
+
+
+@dataclass
+class ACWResults:
+    """src/core/acw.jl:44-55."""
+    fs: float
+    acw_results: Any
+    acwtypes: Any
+    n_lags: Any
+    freqlims: Any
+    acf: Any
+    psd: Any
+    freqs: Any
+    lags: Any
+    x_dim: Any
+
+
+def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
+        average_over_trials=False, ctx=None):
+    """Compute ACW measures of every trial of `data` ((trials, time), time last).
+
+    Returns ACWResults; `acw_results` is a list in the order of `acwtypes` (a single
+    entry when one type is requested), each entry a vector over trials (scalar for a
+    vector input or average_over_trials=True).  Lags without a crossing give NaN.
+    """
+    if acwtypes is None:
+        acwtypes = list(possible_acwtypes)
+    single = isinstance(acwtypes, str)
+    if single:
+        acwtypes = [acwtypes]
+    acwtypes = [str(t).lstrip(":") for t in acwtypes]
+    if len(acwtypes) == 0:
+        raise ValueError(f"No ACW types specified. Possible ACW types: {possible_acwtypes}")
+    for t in acwtypes:
+        if t not in _BITS:
+            raise ValueError(f"Possible ACW types: {possible_acwtypes}, got {t!r}")
+    data = np.asarray(data, dtype=np.float64)
+    was_vector = data.ndim == 1
+    if was_vector:
+        data = data.reshape(1, -1)                              # acw.jl:122-125
+    if data.ndim != 2 or (dims is not None and dims not in (-1, data.ndim - 1, data.ndim)):
+        raise NotImplementedError("the B200 path handles (trials, time) data with dims = last")
+    d = np.asfortranarray(data)
+    n_slices, n_t = d.shape
+    ctx = ctx or _lib.default_context()
+    mask = 0
+    for t in acwtypes:
+        mask |= _BITS[t]
+    n_out = 1 if average_over_trials else n_slices
+    k0 = np.empty(n_out, dtype=np.int32)
+    k50 = np.empty(n_out, dtype=np.int32)
+    ke = np.empty(n_out, dtype=np.int32)
+    auc = np.empty(n_out, dtype=np.float64)
+    tau = np.empty(n_out, dtype=np.float64)
+    nl = ctypes.c_int64(0 if n_lags is None else int(n_lags))
+    # n_lags is only known after the call: reserve the worst case (np.empty only maps
+    # virtual memory; the library writes the first n_out * n_lags entries)
+    acf_buf = None
+    cap = 0
+    if return_acf:
+        cap = n_out * (int(n_lags) if n_lags is not None else n_t)
+        acf_buf = np.empty(cap, dtype=np.float64)
+    # always request acw0: the AUC window and the default n_lags derive from it
+    rc = _lib.lib().itjl_acw(ctx.handle, _lib.ptr(d), n_slices, n_t, float(fs), mask | _lib.ACW0,
+                             int(bool(average_over_trials)), ctypes.byref(nl), _lib.ptr(k0),
+                             _lib.ptr(k50), _lib.ptr(ke), _lib.ptr(auc), _lib.ptr(tau),
+                             _lib.ptr(acf_buf), cap)
+    ctx.check(rc)
+    n_lags_used = int(nl.value)
+    dt = 1.0 / float(fs)
+
+    def as_lag(k):
+        return np.where(k >= 0, k.astype(np.float64) * dt, np.nan)
+
+    if "auc" in acwtypes:
+        # reference: floor(Int, NaN) -> InexactError; romberg on < 2 points -> ArgumentError
+        if k0[0] < 0:
+            raise ValueError("InexactError: no zero crossing in the first slice (AUC window undefined)")
+        if k0[0] < 2:
+            raise ValueError("ArgumentError: y array must have length > 1 (AUC window of the first slice)")
+    res = {"acw0": as_lag(k0), "acw50": as_lag(k50), "acweuler": as_lag(ke), "auc": auc, "tau": tau}
+    results = []
+    for t in acwtypes:
+        v = res[t]
+        results.append(float(v[0]) if (was_vector or n_out == 1) else v)
+    acf = lags = None
+    if return_acf:
+        acf = acf_buf[: n_out * n_lags_used].reshape((n_out, n_lags_used), order="F")
+        if was_vector:
+            acf = acf[0]
+        lags = np.arange(n_lags_used, dtype=np.float64) * dt
+    x_dim = None if acf is None else acf.ndim
+    return ACWResults(float(fs), results[0] if len(results) == 1 else results,
+                      acwtypes[0] if single else acwtypes, n_lags_used, None, acf, None, None,
+                      lags, x_dim)

@@ -1,0 +1,434 @@
+// K4: acw() on stored data - per-slice autocorrelation (fp64, direct lag sum in shared
+// memory) with the threshold reducers, plus the Romberg-AUC and exp-decay-fit epilogues.
+//
+// Replaces the ACF-based part of acw(data, fs; ...) (reference src/core/acw.jl:141-231):
+//   comp_ac_fft / comp_ac_time_missing     src/stats/summary.jl:46-63, 455-484
+//   acw0 / acw50 / acweuler                src/utils/utils.jl:257-264, 218-226, 294-302
+//   acw_romberg                            src/utils/utils.jl:332-334 (Romberg.jl, see oracle/acwred.py)
+//   fit_expdecay                           src/utils/utils.jl:113-126 (argmin of the LM objective)
+//
+// The reference computes all n lags of every slice by FFT and then keeps
+// n_lags = ceil(1.1 max k0) of them; here each slice is scanned in growing lag blocks
+// (20, 20, 40, 80, ...) only until its own zero crossing, in fp64 so that the crossing
+// indices agree with an fp64 reference bit for bit (up to ties at the 1e-15 level).
+// Lag-sum tiling as in abc_kernels.cu, with doubles: thread = (tile of 10 lags) x (time
+// stream), 100 DFMA per 10 LDS.128.
+#include <math.h>
+
+#include "kernels.h"
+
+namespace itjl {
+
+constexpr int TKD = 10;   // lags per thread
+constexpr int TTD = 10;   // samples per time tile
+
+__device__ __forceinline__ void load5d(const double2* __restrict__ p, double* dst) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const double2 v = p[q];
+        dst[2 * q] = v.x; dst[2 * q + 1] = v.y;
+    }
+}
+
+__device__ __forceinline__ void acf_tiles_f64(const double* __restrict__ xs, double (&acc)[TKD], int k0,
+                                              int tile_begin, int tile_end) {
+    double b[2 * TTD];
+    double a[TTD];
+    const double2* pa = reinterpret_cast<const double2*>(xs + tile_begin * TTD);
+    const double2* pb = reinterpret_cast<const double2*>(xs + tile_begin * TTD + k0);
+    load5d(pb, b);
+    pb += 5;
+    int n = tile_end - tile_begin;
+    while (n > 0) {
+        load5d(pb, b + TTD); pb += 5;
+        load5d(pa, a); pa += 5;
+#pragma unroll
+        for (int i = 0; i < TTD; ++i)
+#pragma unroll
+            for (int j = 0; j < TKD; ++j) acc[j] = fma(a[i], b[i + j], acc[j]);
+        if (--n == 0) break;
+        load5d(pb, b); pb += 5;
+        load5d(pa, a); pa += 5;
+#pragma unroll
+        for (int i = 0; i < TTD; ++i)
+#pragma unroll
+            for (int j = 0; j < TKD; ++j) acc[j] = fma(a[i], b[(TTD + i + j) % (2 * TTD)], acc[j]);
+        --n;
+    }
+}
+
+struct AcfSliceParams {
+    const double* data;     // (n_slices x n_t) column-major
+    int64_t n_slices;
+    int n_t;
+    int missing;            // NaN-aware centring (comp_ac_time_missing)
+    int mode;               // 0 = scan until the zero crossing, 1 = fill lags [n_done, need)
+    int max_lags;           // scan limit
+    int need;               // fill target
+    int xs_len;             // doubles in the staging buffer (>= n_t + max block reach)
+    double* acf_work;       // [slice][cap]
+    int64_t cap;
+    int32_t* n_done;        // [slice] lags available in acf_work
+    int32_t* k0; int32_t* k50; int32_t* ke;
+    int32_t* nan_flag;      // set to 1 when any slice holds a NaN (may be null)
+};
+
+constexpr double kInvE = 0.36787944117144233;   // Julia: 1 / ℯ
+
+__global__ void __launch_bounds__(kThreads, 2) k_acf_slices(const AcfSliceParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* xs = reinterpret_cast<double*>(smem_raw);
+    double* part = xs + P.xs_len;                 // [n_streams][lt*TKD] <= kThreads*TKD doubles
+    __shared__ double red[kWarps];
+    __shared__ int s_first[3];
+    __shared__ double s_ss;
+
+    const int tid = threadIdx.x;
+    const int64_t s = blockIdx.x;
+    const int n_t = P.n_t;
+
+    int start = 0, stop = P.max_lags;
+    if (P.mode == 1) {
+        start = P.n_done[s];
+        stop = P.need;
+        if (start >= stop) return;                // uniform per CTA
+    }
+
+    // ---- load + centre -------------------------------------------------------------
+    double lsum = 0.0;
+    int lcnt = 0;
+    for (int j = tid; j < P.xs_len; j += kThreads) {
+        double v = 0.0;
+        if (j < n_t) {
+            v = P.data[s + (size_t)j * P.n_slices];
+            if (P.missing && isnan(v)) v = 0.0; else lcnt++;
+            lsum += v;
+        }
+        xs[j] = v;
+    }
+    lsum = warp_sum(lsum);
+    double dcnt = warp_sum((double)lcnt);
+    if ((tid & 31) == 0) { red[tid >> 5] = lsum; part[tid >> 5] = dcnt; }
+    __syncthreads();
+    double tot = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { tot += red[w]; cnt += part[w]; }
+    const double mean = tot / cnt;                // cnt == n_t for complete data
+    if (tid == 0 && P.nan_flag && cnt < (double)n_t) *P.nan_flag = 1;
+    __syncthreads();
+    double lss = 0.0;
+    for (int j = tid; j < n_t; j += kThreads) {   // summary.jl:471: every entry (masked too) -= mean
+        const double v = xs[j] - mean;
+        xs[j] = v;
+        lss = fma(v, v, lss);
+    }
+    lss = warp_sum(lss);
+    if ((tid & 31) == 0) red[tid >> 5] = lss;
+    if (tid < 3) s_first[tid] = 0x7fffffff;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[w];
+        s_ss = t;
+    }
+    __syncthreads();
+    const double inv_ss = 1.0 / s_ss;
+    const int n_tiles = (n_t + TTD - 1) / TTD;
+
+    // ---- lag blocks --------------------------------------------------------------------
+    int kb = start;
+    int lb = 2 * TKD;
+    while (kb < stop) {
+        if (P.mode == 0 && kb >= 4 * TKD) lb = kb;            // 20, 20, 40, 80, 160, ...
+        if (P.mode == 1) lb = min(stop - kb, kThreads * TKD);
+        lb = min(lb, stop - kb);
+        lb = min(lb, kThreads * TKD);
+        const int lt = (lb + TKD - 1) / TKD;
+        int n_streams = kThreads / lt;
+        if (n_streams > n_tiles) n_streams = n_tiles;
+        const int tps = (n_tiles + n_streams - 1) / n_streams;
+        const int tile = tid % lt, stream = tid / lt;
+        const int row = lt * TKD;
+        if (stream < n_streams) {
+            double acc[TKD];
+#pragma unroll
+            for (int j = 0; j < TKD; ++j) acc[j] = 0.0;
+            const int tb = stream * tps, te = min(tb + tps, n_tiles);
+            if (tb < te) acf_tiles_f64(xs, acc, kb + tile * TKD, tb, te);
+#pragma unroll
+            for (int j = 0; j < TKD; ++j) part[stream * row + tile * TKD + j] = acc[j];
+        }
+        __syncthreads();
+        for (int k = tid; k < lb; k += kThreads) {
+            double v = 0.0;
+            for (int st = 0; st < n_streams; ++st) v += part[st * row + k];
+            v *= inv_ss;
+            const int lag = kb + k;
+            P.acf_work[(size_t)s * P.cap + lag] = v;
+            if (P.mode == 0) {
+                if (v <= 0.0) atomicMin(&s_first[0], lag);
+                if (v <= 0.5) atomicMin(&s_first[1], lag);
+                if (v <= kInvE) atomicMin(&s_first[2], lag);
+            }
+        }
+        __syncthreads();
+        kb += lb;
+        if (P.mode == 0 && s_first[0] != 0x7fffffff) break;
+    }
+    if (tid == 0) {
+        P.n_done[s] = kb;
+        if (P.mode == 0) {
+            P.k0[s] = (s_first[0] == 0x7fffffff) ? -1 : s_first[0];
+            P.k50[s] = (s_first[1] == 0x7fffffff) ? -1 : s_first[1];
+            P.ke[s] = (s_first[2] == 0x7fffffff) ? -1 : s_first[2];
+        }
+    }
+}
+
+// crossing indices of stored ACF rows (acf[row*ld + k], k < n_lags): one warp per row
+__global__ void k_acf_cross(const double* __restrict__ acf, int64_t n_rows, int64_t ld, int n_lags,
+                            int32_t* k0, int32_t* k50, int32_t* ke) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    int f0 = 0x7fffffff, f50 = 0x7fffffff, fe = 0x7fffffff;
+    for (int base = 0; base < n_lags && f0 == 0x7fffffff; base += 32) {
+        const int k = base + lane;
+        const double v = (k < n_lags) ? acf[row * ld + k] : 2.0;
+        const unsigned b0 = __ballot_sync(0xffffffffu, v <= 0.0);
+        const unsigned b50 = __ballot_sync(0xffffffffu, v <= 0.5);
+        const unsigned be = __ballot_sync(0xffffffffu, v <= kInvE);
+        if (f50 == 0x7fffffff && b50) f50 = base + __ffs(b50) - 1;
+        if (fe == 0x7fffffff && be) fe = base + __ffs(be) - 1;
+        if (b0) f0 = base + __ffs(b0) - 1;
+    }
+    if (lane == 0) {
+        k0[row] = (f0 == 0x7fffffff) ? -1 : f0;
+        k50[row] = (f50 == 0x7fffffff) ? -1 : f50;
+        ke[row] = (fe == 0x7fffffff) ? -1 : fe;
+    }
+}
+
+// column mean over rows: out[k] = mean_row acf[row*ld + k]
+__global__ void k_acf_mean(const double* __restrict__ acf, int64_t n_rows, int64_t ld, int n_lags,
+                           double* __restrict__ out) {
+    __shared__ double red[kWarps];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int64_t r = threadIdx.x; r < n_rows; r += kThreads) s += acf[r * ld + k];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[w];
+        out[k] = t / (double)n_rows;
+    }
+}
+
+// (rows x ld) row-major work buffer -> (rows x n_lags) column-major output
+__global__ void k_acf_export(const double* __restrict__ acf, int64_t n_rows, int64_t ld, int n_lags,
+                             double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * n_lags) return;
+    const int64_t row = i % n_rows, k = i / n_rows;
+    out[i] = acf[row * ld + k];
+}
+
+// ---- Romberg AUC ---------------------------------------------------------------------
+// Romberg.jl romberg(dt, y[0..w)) : trapezoid sums at the strides given by the prime
+// factorisation of w-1 (host-computed, increasing), Richardson extrapolation with power 2,
+// returning the tableau entry with the smallest error estimate (oracle/acwred.py).
+constexpr int kMaxRombergLevels = 40;
+
+__global__ void k_acw_auc(const double* __restrict__ acf, int64_t n_rows, int64_t ld, int w, double dt,
+                          const int* __restrict__ strides, int n_strides, double* __restrict__ auc) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const double* y = acf + row * ld;
+    const double endsum = 0.5 * (y[0] + y[w - 1]);
+    double vals[kMaxRombergLevels], hp[kMaxRombergLevels];
+    // order: coarsest stride first (decreasing h)
+    for (int q = 0; q < n_strides; ++q) {
+        const int step = strides[n_strides - 1 - q];
+        double inner = 0.0;
+        for (int i = step; i < w - 1; i += step) inner += y[i];
+        const double h = (double)step * dt;
+        vals[q] = h * (inner + endsum);
+        hp[q] = h * h;
+    }
+    double f0 = vals[0], err = INFINITY;
+    double nev[kMaxRombergLevels];
+    nev[0] = vals[0];
+    const double rtol = 1.4901161193847656e-08;      // sqrt(eps(Float64))
+    for (int j = 1; j < n_strides; ++j) {
+        nev[j] = vals[j];
+        double minerr = INFINITY;
+        for (int i = j - 1; i >= 0; --i) {
+            const double old = nev[i];
+            nev[i] = nev[i + 1] + (nev[i + 1] - nev[i]) / (hp[i] / hp[j] - 1.0);
+            const double e = fabs(nev[i] - old);
+            minerr = fmin(minerr, e);
+            if (e < err) { f0 = nev[i]; err = e; }
+        }
+        if (minerr > 2.0 * err || !isfinite(minerr)) break;
+        if (err <= rtol * fabs(f0)) break;
+    }
+    auc[row] = f0;
+}
+
+// ---- exp-decay fit -------------------------------------------------------------------
+// argmin_tau mean((exp(-lags/tau) - acf)^2), lags = k*dt, k < n_lags: one warp per row.
+// Same algorithm as oracle/acwred.py fit_expdecay (bracket walk in log tau + Illinois).
+__device__ __forceinline__ double dres_dlogtau(const double* __restrict__ y, int n_lags, double dt, double u,
+                                               int lane) {
+    const double sr = exp(-u);
+    double g = 0.0;
+    for (int k = lane; k < n_lags; k += 32) {
+        const double t = (double)k * dt;
+        const double e = exp(-sr * t);
+        g += (e - y[k]) * e * t;
+    }
+    g = warp_sum(g);
+    return g * sr;
+}
+
+__global__ void k_acw_tau(const double* __restrict__ acf, int64_t n_rows, int64_t ld, int n_lags, double dt,
+                          double* __restrict__ tau) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const double* y = acf + row * ld;
+    // u0 = log(acw50 / ln 2) on the truncated ACF (utils.jl:115-120)
+    int f50 = 0x7fffffff;
+    for (int base = 0; base < n_lags && f50 == 0x7fffffff; base += 32) {
+        const int k = base + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, (k < n_lags) && (y[k] <= 0.5));
+        if (b) f50 = base + __ffs(b) - 1;
+    }
+    double tau0 = (f50 == 0x7fffffff) ? 1.0 : -((double)f50 * dt) / log(0.5);
+    if (!(tau0 > 0.0) || !isfinite(tau0)) tau0 = 1.0;
+    const double u0 = log(tau0);
+    const double g0 = dres_dlogtau(y, n_lags, dt, u0, lane);
+    double result = exp(u0);
+    if (g0 != 0.0) {
+        const double dir = (g0 > 0.0) ? -1.0 : 1.0;
+        double up = u0, gp = g0, lo = u0, glo = g0, hi = u0, ghi = g0;
+        bool found = false, exact = false;
+        for (int it = 0; it < 24; ++it) {
+            const double u = up + dir * 0.5;
+            const double g = dres_dlogtau(y, n_lags, dt, u, lane);
+            if (g == 0.0) { result = exp(u); exact = true; break; }
+            if ((g > 0.0) != (gp > 0.0)) {
+                if (dir < 0.0) { lo = u; glo = g; hi = up; ghi = gp; }
+                else { lo = up; glo = gp; hi = u; ghi = g; }
+                found = true;
+                break;
+            }
+            up = u; gp = g;
+        }
+        if (!exact) {
+            if (!found) result = exp(up);
+            else {
+                double a = lo, ga = glo, b = hi, gb = ghi;
+                int side = 0;
+                double u = 0.5 * (a + b), ulast = a;
+                for (int it = 0; it < 100; ++it) {
+                    u = (a * gb - b * ga) / (gb - ga);
+                    if (!(a < u && u < b)) u = 0.5 * (a + b);
+                    const double g = dres_dlogtau(y, n_lags, dt, u, lane);
+                    if (g == 0.0 || fabs(u - ulast) < 1e-13 * fmax(1.0, fabs(u))) break;
+                    ulast = u;
+                    if ((g > 0.0) == (gb > 0.0)) { b = u; gb = g; if (side == -1) ga *= 0.5; side = -1; }
+                    else { a = u; ga = g; if (side == 1) gb *= 0.5; side = 1; }
+                }
+                result = exp(u);
+            }
+        }
+    }
+    if (lane == 0) tau[row] = result;
+}
+
+// ---- host launchers ------------------------------------------------------------------
+static size_t acf_slices_smem(int n_t, int reach, int* xs_len) {
+    int len = n_t + reach + 4 * TTD;
+    len = (len + 1) & ~1;
+    *xs_len = len;
+    return (size_t)len * sizeof(double) + (size_t)kThreads * TKD * sizeof(double);
+}
+
+// largest lag reach whose staging buffer still fits in shared memory
+int acf_max_reach(int n_t, int max_smem) {
+    const long long avail = (long long)max_smem - (long long)kThreads * TKD * 8 - (long long)(n_t + 4 * TTD + 2) * 8;
+    long long r = avail / 8;
+    if (r > n_t) r = n_t;
+    return (int)(r < 0 ? 0 : r);
+}
+
+static cudaError_t launch_slices(AcfSliceParams& P, int reach, int max_smem, cudaStream_t st) {
+    int xs_len = 0;
+    size_t smem = acf_slices_smem(P.n_t, reach, &xs_len);
+    if ((int64_t)smem > (int64_t)max_smem) return cudaErrorInvalidValue;
+    P.xs_len = xs_len;
+    cudaError_t e = cudaFuncSetAttribute(k_acf_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_acf_slices<<<(unsigned)P.n_slices, kThreads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int missing, int max_lags,
+                            double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
+                            int32_t* ke, int32_t* nan_flag, int max_smem, cudaStream_t st) {
+    AcfSliceParams P{};
+    P.nan_flag = nan_flag;
+    P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.missing = missing; P.mode = 0;
+    P.max_lags = max_lags; P.need = 0; P.acf_work = acf_work; P.cap = cap; P.n_done = n_done;
+    P.k0 = k0; P.k50 = k50; P.ke = ke;
+    return launch_slices(P, max_lags, max_smem, st);
+}
+
+cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
+                            double* acf_work, int64_t cap, int32_t* n_done, int max_smem, cudaStream_t st) {
+    AcfSliceParams P{};
+    P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.missing = missing; P.mode = 1;
+    P.max_lags = need; P.need = need; P.acf_work = acf_work; P.cap = cap; P.n_done = n_done;
+    return launch_slices(P, need, max_smem, st);
+}
+
+cudaError_t acf_cross_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, int32_t* k0,
+                             int32_t* k50, int32_t* ke, cudaStream_t st) {
+    const int wpb = 4;
+    k_acf_cross<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(acf, n_rows, ld, n_lags, k0, k50, ke);
+    return cudaGetLastError();
+}
+
+cudaError_t acf_mean_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double* out,
+                            cudaStream_t st) {
+    k_acf_mean<<<n_lags, kThreads, 0, st>>>(acf, n_rows, ld, n_lags, out);
+    return cudaGetLastError();
+}
+
+cudaError_t acf_export_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double* out,
+                              cudaStream_t st) {
+    const int64_t total = n_rows * n_lags;
+    k_acf_export<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(acf, n_rows, ld, n_lags, out);
+    return cudaGetLastError();
+}
+
+cudaError_t acw_auc_launch(const double* acf, int64_t n_rows, int64_t ld, int w, double dt,
+                           const int* strides, int n_strides, double* auc, cudaStream_t st) {
+    if (n_strides > kMaxRombergLevels) return cudaErrorInvalidValue;
+    k_acw_auc<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(acf, n_rows, ld, w, dt, strides, n_strides, auc);
+    return cudaGetLastError();
+}
+
+cudaError_t acw_tau_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double dt, double* tau,
+                           cudaStream_t st) {
+    const int wpb = 4;
+    k_acw_tau<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(acf, n_rows, ld, n_lags, dt, tau);
+    return cudaGetLastError();
+}
+
+}  // namespace itjl

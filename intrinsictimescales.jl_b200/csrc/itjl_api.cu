@@ -1,0 +1,447 @@
+// C-ABI layer of libitjl_b200.so (see include/itjl_b200.h for the contract and the
+// reference functions each entry point replaces).  Host logic only: argument checks,
+// H2D/D2H staging on the context stream, launch geometry, status codes.
+#include <math.h>
+#include <new>
+#include <vector>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace itjl {
+char g_err[512] = {0};
+}
+
+using namespace itjl;
+
+struct itjl_model {
+    itjl_ctx* ctx = nullptr;
+    itjl_model_desc d{};
+    DevBuf target, mask_bits, n_valid, bins, window, twiddle;
+    int mask_words = 0;
+    AbcAcfGeometry geo{};
+    // PSD
+    int n2 = 0, log2_n2 = 0, psd_chunk = 0, psd_xs_len = 0;
+    size_t psd_smem = 0;
+    double psd_scale = 0.0;
+};
+
+extern "C" {
+
+const char* itjl_version(void) { return "itjl_b200 0.1.0 (sm_100a)"; }
+
+int itjl_device_count(int* n_out) {
+    if (!n_out) return fail(nullptr, ITJL_ERR_ARG, "itjl_device_count: null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *n_out = 0; return fail(nullptr, ITJL_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n_out = n;
+    return ITJL_OK;
+}
+
+int itjl_ctx_create(int device, itjl_ctx** ctx_out) {
+    if (!ctx_out) return fail(nullptr, ITJL_ERR_ARG, "itjl_ctx_create: null output");
+    *ctx_out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, ITJL_ERR_NO_DEVICE, "no CUDA device available: %s",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(nullptr, ITJL_ERR_ARG, "itjl_ctx_create: device index out of range");
+    itjl_ctx* ctx = new (std::nothrow) itjl_ctx();
+    if (!ctx) return fail(nullptr, ITJL_ERR_ALLOC, "out of host memory");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) {
+        fail(nullptr, ITJL_ERR_CUDA, "itjl_ctx_create: %s", cudaGetErrorString(e));
+        delete ctx;
+        return ITJL_ERR_CUDA;
+    }
+    *ctx_out = ctx;
+    return ITJL_OK;
+}
+
+int itjl_ctx_destroy(itjl_ctx* ctx) {
+    if (!ctx) return ITJL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->theta, &ctx->dist, &ctx->stats, &ctx->u0, &ctx->noise, &ctx->phases,
+                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3};
+    for (DevBuf* b : bufs) b->release();
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ITJL_OK;
+}
+
+const char* itjl_last_error(const itjl_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int itjl_ctx_synchronize(itjl_ctx* ctx) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
+uint64_t itjl_ctx_stream(const itjl_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+int64_t itjl_ctx_launch_count(const itjl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int itjl_ctx_sm_count(const itjl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int itjl_ctx_timing_reset(itjl_ctx* ctx) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    ctx->timing = true; ctx->timed_launches = 0; ctx->timed_ms = 0.0;
+    return ITJL_OK;
+}
+int itjl_ctx_timing_get(itjl_ctx* ctx, int64_t* n_launches, double* total_ms) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    if (n_launches) *n_launches = ctx->timed_launches;
+    if (total_ms) *total_ms = ctx->timed_ms;
+    return ITJL_OK;
+}
+
+}  // extern "C"
+
+// ---- helpers ---------------------------------------------------------------------------
+static int upload(itjl_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
+    ITJL_CUDA(ctx, buf.reserve(bytes ? bytes : 1));
+    if (bytes) ITJL_CUDA(ctx, cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ITJL_OK;
+}
+
+static int nextpow2_int(int64_t n) { int64_t p = 1; while (p < n) p <<= 1; return (int)p; }
+
+extern "C" {
+
+int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** model_out) {
+    if (!ctx || !desc || !model_out) return fail(ctx, ITJL_ERR_ARG, "itjl_model_create: null argument");
+    *model_out = nullptr;
+    const itjl_model_desc& d = *desc;
+    if (d.kind != ITJL_KIND_OU && d.kind != ITJL_KIND_OU_OSC) return fail(ctx, ITJL_ERR_ARG, "model kind must be OU or OU_OSC");
+    if (d.summary < ITJL_SUMMARY_ACF || d.summary > ITJL_SUMMARY_PSD) return fail(ctx, ITJL_ERR_ARG, "invalid summary method");
+    if (d.distance != ITJL_DIST_LINEAR && d.distance != ITJL_DIST_LOG) return fail(ctx, ITJL_ERR_ARG, "Distance method must be :linear or :logarithmic");
+    if (d.update != ITJL_UPDATE_EXACT && d.update != ITJL_UPDATE_EM) return fail(ctx, ITJL_ERR_ARG, "invalid update rule");
+    if (d.n_trials < 1 || d.n_t < 4 || d.n_t > (1 << 24)) return fail(ctx, ITJL_ERR_ARG, "n_trials >= 1 and 4 <= n_t <= 2^24 required");
+    if (d.n_stats < 1 || !d.target_stats) return fail(ctx, ITJL_ERR_ARG, "target_stats / n_stats missing");
+    if (!(d.dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "dt must be positive");
+    if (d.summary == ITJL_SUMMARY_ACF_MISSING && !d.missing_mask) return fail(ctx, ITJL_ERR_ARG, "missing_mask required for the missing-data ACF");
+    if (d.summary == ITJL_SUMMARY_PSD && !d.freq_bins) return fail(ctx, ITJL_ERR_ARG, "freq_bins required for the PSD summary");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    itjl_model* m = new (std::nothrow) itjl_model();
+    if (!m) return fail(ctx, ITJL_ERR_ALLOC, "out of host memory");
+    m->ctx = ctx; m->d = d;
+    m->d.target_stats = nullptr; m->d.missing_mask = nullptr; m->d.freq_bins = nullptr;
+    int rc = ITJL_OK;
+    std::vector<float> tgt((size_t)d.n_stats);
+    for (int64_t i = 0; i < d.n_stats; ++i) tgt[i] = (float)d.target_stats[i];
+    rc = upload(ctx, m->target, tgt.data(), tgt.size() * sizeof(float));
+
+    if (rc == ITJL_OK && d.summary != ITJL_SUMMARY_PSD) {
+        if (d.n_stats > d.n_t) { delete m; return fail(ctx, ITJL_ERR_ARG, "n_lags must not exceed n_t"); }
+        int g = abc_acf_geometry((int)d.n_t, (int)d.n_stats, ctx->max_smem_optin, &m->geo);
+        if (g != 0) { delete m; return fail(ctx, ITJL_ERR_ARG, g == -2 ? "n_lags > 5120 is not supported by the fused ACF kernel" : "trial does not fit in shared memory (n_t too large)"); }
+    }
+    if (rc == ITJL_OK && d.missing_mask) {
+        m->mask_words = (int)((d.n_t + 31) / 32);
+        std::vector<uint32_t> bits((size_t)d.n_trials * m->mask_words, 0u);
+        std::vector<int> nvalid((size_t)d.n_trials, 0);
+        for (int64_t t = 0; t < d.n_t; ++t)
+            for (int64_t tr = 0; tr < d.n_trials; ++tr) {
+                if (d.missing_mask[tr + t * d.n_trials]) bits[(size_t)tr * m->mask_words + (t >> 5)] |= 1u << (t & 31);
+                else nvalid[tr]++;
+            }
+        rc = upload(ctx, m->mask_bits, bits.data(), bits.size() * sizeof(uint32_t));
+        if (rc == ITJL_OK) rc = upload(ctx, m->n_valid, nvalid.data(), nvalid.size() * sizeof(int));
+        if (rc == ITJL_OK) rc = (cudaStreamSynchronize(ctx->stream) == cudaSuccess) ? ITJL_OK : ITJL_ERR_CUDA;
+    }
+    if (rc == ITJL_OK && d.summary == ITJL_SUMMARY_PSD) {
+        m->n2 = 2 * nextpow2_int(d.n_t);
+        m->log2_n2 = 0; while ((1 << m->log2_n2) < m->n2) m->log2_n2++;
+        for (int64_t i = 0; i < d.n_stats; ++i)
+            if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { delete m; return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
+        m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, &m->psd_chunk, &m->psd_xs_len)
+                      + (size_t)((d.n_stats + 3) & ~3ll) * sizeof(float) + 512;
+        if ((int64_t)m->psd_smem > ctx->max_smem_optin) { delete m; return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
+        std::vector<float> win((size_t)d.n_t);
+        std::vector<float2> tw((size_t)m->n2 / 2);
+        double win_ss = 0.0;
+        psd_make_tables((int)d.n_t, m->n2, win.data(), tw.data(), &win_ss);
+        m->psd_scale = 1.0 / ((1.0 / d.dt) * win_ss);
+        rc = upload(ctx, m->bins, d.freq_bins, (size_t)d.n_stats * sizeof(int32_t));
+        if (rc == ITJL_OK) rc = upload(ctx, m->window, win.data(), win.size() * sizeof(float));
+        if (rc == ITJL_OK) rc = upload(ctx, m->twiddle, tw.data(), tw.size() * sizeof(float2));
+    }
+    if (rc == ITJL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ITJL_ERR_CUDA, "model upload failed");
+    if (rc != ITJL_OK) { itjl_model_destroy(m); return rc; }
+    *model_out = m;
+    return ITJL_OK;
+}
+
+int itjl_model_destroy(itjl_model* m) {
+    if (!m) return ITJL_OK;
+    if (m->ctx) cudaSetDevice(m->ctx->device);
+    m->target.release(); m->mask_bits.release(); m->n_valid.release();
+    m->bins.release(); m->window.release(); m->twiddle.release();
+    delete m;
+    return ITJL_OK;
+}
+
+int itjl_model_work(const itjl_model* m, double* flops_per_sample, int64_t* samples_per_particle) {
+    if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    if (flops_per_sample) {
+        if (m->d.summary == ITJL_SUMMARY_PSD) {
+            // one n2-point real FFT per trial (2.5 n2 log2 n2) + |.|^2 on the selected bins + window etc.
+            *flops_per_sample = (2.5 * m->n2 * m->log2_n2 + 3.0 * (double)m->d.n_stats) / (double)m->d.n_t + 12.0;
+        } else {
+            *flops_per_sample = 2.0 * (double)m->d.n_stats + 8.0;
+        }
+    }
+    if (samples_per_particle) *samples_per_particle = m->d.n_trials * m->d.n_t;
+    return ITJL_OK;
+}
+
+}  // extern "C"
+
+// Launch the fused kernel for one batch; every pointer is a device pointer (or null).
+static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
+                            uint64_t seed, uint64_t generation, int64_t particle_offset,
+                            const double* u0_dev, const double* noise_dev, const double* phases_dev,
+                            double* dist_dev, double* stats_dev) {
+    itjl_ctx* ctx = m->ctx;
+    const itjl_model_desc& d = m->d;
+    const int need_theta = (d.kind == ITJL_KIND_OU_OSC) ? 3 : 1;
+    if (n_theta < need_theta) return fail(ctx, ITJL_ERR_ARG, "theta has too few columns for this model");
+    if (n_particles < 1 || n_particles > 0x7fffffffll) return fail(ctx, ITJL_ERR_ARG, "n_particles out of range");
+    cudaError_t e;
+    if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
+    if (d.summary == ITJL_SUMMARY_PSD) {
+        AbcPsdParams P{};
+        P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
+        P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_stats = (int)d.n_stats;
+        P.chunk = m->psd_chunk; P.xs_len = m->psd_xs_len; P.n2 = m->n2; P.log2_n2 = m->log2_n2;
+        P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
+        P.update = d.update; P.kind = d.kind; P.distance = d.distance;
+        P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+        P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
+        P.particle_offset = particle_offset;
+        P.target = (const float*)m->target.p; P.bins = (const int32_t*)m->bins.p;
+        P.window = (const float*)m->window.p; P.twiddle = (const float2*)m->twiddle.p;
+        P.psd_scale = m->psd_scale;
+        P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
+        P.dist_out = dist_dev; P.stats_out = stats_dev;
+        e = abc_psd_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
+    } else {
+        AbcAcfParams P{};
+        P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
+        P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_lags = (int)d.n_stats;
+        P.chunk = m->geo.chunk; P.xs_stride = m->geo.xs_stride; P.lt = m->geo.lt;
+        P.n_streams = m->geo.n_streams; P.tiles_per_stream = m->geo.tiles_per_stream; P.n_tiles = m->geo.n_tiles;
+        P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
+        P.update = d.update; P.kind = d.kind; P.distance = d.distance;
+        P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+        P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
+        P.particle_offset = particle_offset;
+        P.target = (const float*)m->target.p;
+        P.mask_bits = (const uint32_t*)m->mask_bits.p; P.n_valid = (const int*)m->n_valid.p;
+        P.mask_words = m->mask_words;
+        P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
+        P.dist_out = dist_dev; P.stats_out = stats_dev;
+        e = abc_acf_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC,
+                           m->geo.smem_bytes, ctx->stream);
+    }
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch fused abc kernel: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    if (ctx->timing) {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->timed_ms += ms; ctx->timed_launches++;
+    }
+    return ITJL_OK;
+}
+
+static int stage_inputs(itjl_model* m, const double* theta, int64_t n_particles, int32_t n_theta,
+                        const double* u0, const double* noise, const double* phases) {
+    itjl_ctx* ctx = m->ctx;
+    const itjl_model_desc& d = m->d;
+    int rc = upload(ctx, ctx->theta, theta, (size_t)n_particles * n_theta * sizeof(double));
+    const size_t pt = (size_t)n_particles * d.n_trials;
+    if (rc == ITJL_OK && u0) rc = upload(ctx, ctx->u0, u0, pt * sizeof(double));
+    if (rc == ITJL_OK && noise) rc = upload(ctx, ctx->noise, noise, pt * d.n_t * sizeof(double));
+    if (rc == ITJL_OK && phases) rc = upload(ctx, ctx->phases, phases, pt * sizeof(double));
+    return rc;
+}
+
+extern "C" {
+
+int itjl_abc_distances(itjl_model* m, const double* theta, int64_t n_particles, int32_t n_theta,
+                       uint64_t seed, uint64_t generation, int64_t particle_offset,
+                       const double* u0, const double* noise, const double* phases,
+                       double* dist_out, double* stats_out) {
+    if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    itjl_ctx* ctx = m->ctx;
+    if (!theta || !dist_out) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances: null theta / dist_out");
+    if (n_particles < 1 || n_theta < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances: empty batch");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_inputs(m, theta, n_particles, n_theta, u0, noise, phases);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->dist.reserve((size_t)n_particles * sizeof(double)));
+    if (stats_out) ITJL_CUDA(ctx, ctx->stats.reserve((size_t)n_particles * m->d.n_stats * sizeof(double)));
+    rc = launch_distances(m, (const double*)ctx->theta.p, n_particles, n_theta, seed, generation, particle_offset,
+                          u0 ? (const double*)ctx->u0.p : nullptr, noise ? (const double*)ctx->noise.p : nullptr,
+                          phases ? (const double*)ctx->phases.p : nullptr, (double*)ctx->dist.p,
+                          stats_out ? (double*)ctx->stats.p : nullptr);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(dist_out, ctx->dist.p, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats_out)
+        ITJL_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats.p, (size_t)n_particles * m->d.n_stats * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
+int itjl_abc_distances_dev(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
+                           uint64_t seed, uint64_t generation, int64_t particle_offset, double* dist_dev) {
+    if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    if (!theta_dev || !dist_dev) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_distances_dev: null device pointer");
+    ITJL_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
+    return launch_distances(m, theta_dev, n_particles, n_theta, seed, generation, particle_offset,
+                            nullptr, nullptr, nullptr, dist_dev, nullptr);
+}
+
+int itjl_abc_generation(itjl_model* m, const double* theta, int64_t n_particles, int32_t n_theta,
+                        uint64_t seed, uint64_t generation, int64_t particle_offset,
+                        double epsilon, int64_t min_accepted, double* dist_out, uint8_t* isaccepted,
+                        int64_t* n_total, int64_t* n_accepted) {
+    if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    itjl_ctx* ctx = m->ctx;
+    if (!theta || !dist_out || !isaccepted || !n_total || !n_accepted) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_generation: null argument");
+    if (n_particles < 1 || n_theta < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_generation: empty batch");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_inputs(m, theta, n_particles, n_theta, nullptr, nullptr, nullptr);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->dist.reserve((size_t)n_particles * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->flags.reserve((size_t)n_particles + 2 * sizeof(int64_t) + 16));
+    rc = launch_distances(m, (const double*)ctx->theta.p, n_particles, n_theta, seed, generation, particle_offset,
+                          nullptr, nullptr, nullptr, (double*)ctx->dist.p, nullptr);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->scratch.reserve(2 * sizeof(int64_t)));
+    cudaError_t e = abc_accept_launch((const double*)ctx->dist.p, n_particles, epsilon, min_accepted,
+                                      (uint8_t*)ctx->flags.p, (int64_t*)ctx->scratch.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_abc_accept: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    int64_t out2[2] = {0, 0};
+    ITJL_CUDA(ctx, cudaMemcpyAsync(dist_out, ctx->dist.p, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(isaccepted, ctx->flags.p, (size_t)n_particles, cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(out2, ctx->scratch.p, sizeof(out2), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_total = out2[0]; *n_accepted = out2[1];
+    return ITJL_OK;
+}
+
+int itjl_abc_accept(itjl_ctx* ctx, const double* dist, int64_t n, double epsilon, int64_t min_accepted,
+                    uint8_t* isaccepted, int64_t* n_total, int64_t* n_accepted) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    if (!dist || !isaccepted || !n_total || !n_accepted || n < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_accept: null / empty argument");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload(ctx, ctx->dist, dist, (size_t)n * sizeof(double));
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->flags.reserve((size_t)n));
+    ITJL_CUDA(ctx, ctx->scratch.reserve(2 * sizeof(int64_t)));
+    cudaError_t e = abc_accept_launch((const double*)ctx->dist.p, n, epsilon, min_accepted,
+                                      (uint8_t*)ctx->flags.p, (int64_t*)ctx->scratch.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_abc_accept: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    int64_t out2[2] = {0, 0};
+    ITJL_CUDA(ctx, cudaMemcpyAsync(isaccepted, ctx->flags.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(out2, ctx->scratch.p, sizeof(out2), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_total = out2[0]; *n_accepted = out2[1];
+    return ITJL_OK;
+}
+
+// ---- OU generator ----------------------------------------------------------------------
+static int generate_common(itjl_ctx* ctx, int kind, double tau, double freq, double coeff, double dt,
+                           int64_t n_t, int64_t n_trials, int mode, double scale, double shift, int32_t update,
+                           uint64_t seed, const double* u0, const double* noise, const double* phases, double* out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    if (!out) return fail(ctx, ITJL_ERR_ARG, "generate_ou: null output");
+    if (n_t < 4 || n_trials < 1 || !(dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "generate_ou: need n_t >= 4, n_trials >= 1, dt > 0");
+    if (update != ITJL_UPDATE_EXACT && update != ITJL_UPDATE_EM) return fail(ctx, ITJL_ERR_ARG, "invalid update rule");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    OuGenParams P{};
+    P.n_t = (int)n_t; P.n_trials = (int)n_trials;
+    int c = (int)((n_t + kThreads - 1) / kThreads);
+    P.chunk = (c + 3) & ~3;
+    const size_t smem = (size_t)P.chunk * kThreads * sizeof(float) + 256;
+    if ((int64_t)smem > ctx->max_smem_optin) return fail(ctx, ITJL_ERR_ARG, "generate_ou: n_t too large for one CTA");
+    P.tau = tau; P.freq = freq; P.coeff = coeff; P.dt = dt;
+    P.update = update; P.kind = kind; P.mode = mode; P.scale = (float)scale; P.shift = (float)shift;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+    P.c3_noise = philox_c3(kStreamNoise, 0); P.c3_init = philox_c3(kStreamInit, 0); P.particle = 0;
+    int rc = ITJL_OK;
+    if (u0) { rc = upload(ctx, ctx->u0, u0, (size_t)n_trials * sizeof(double)); P.u0 = (const double*)ctx->u0.p; }
+    if (rc == ITJL_OK && noise) { rc = upload(ctx, ctx->noise, noise, (size_t)n_trials * n_t * sizeof(double)); P.noise = (const double*)ctx->noise.p; }
+    if (rc == ITJL_OK && phases) { rc = upload(ctx, ctx->phases, phases, (size_t)n_trials * sizeof(double)); P.phases = (const double*)ctx->phases.p; }
+    if (rc != ITJL_OK) return rc;
+    const size_t bytes = (size_t)n_trials * n_t * sizeof(double);
+    ITJL_CUDA(ctx, ctx->out.reserve(bytes));
+    P.out = (double*)ctx->out.p;
+    cudaError_t e = ou_generate_launch(P, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_ou_generate: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // solver-failure contract (ou_process.jl:56-61): any non-finite value -> all-NaN matrix
+    bool bad = false;
+    for (size_t i = 0; i < (size_t)n_trials * n_t; ++i) if (!isfinite(out[i])) { bad = true; break; }
+    if (bad) for (size_t i = 0; i < (size_t)n_trials * n_t; ++i) out[i] = NAN;
+    return ITJL_OK;
+}
+
+int itjl_generate_ou(itjl_ctx* ctx, double tau, double true_D, double dt, int64_t n_t, int64_t n_trials,
+                     int32_t standardize, int32_t update, uint64_t seed, const double* u0, const double* noise,
+                     double* out) {
+    return generate_common(ctx, ITJL_KIND_OU, tau, 0.0, 1.0, dt, n_t, n_trials, standardize ? 1 : 2,
+                           true_D, 0.0, update, seed, u0, noise, nullptr, out);
+}
+
+int itjl_generate_ou_osc(itjl_ctx* ctx, double tau, double freq, double coeff, double dt, int64_t n_t,
+                         int64_t n_trials, double data_mean, double data_sd, int32_t update, uint64_t seed,
+                         const double* u0, const double* noise, const double* phases, double* out) {
+    return generate_common(ctx, ITJL_KIND_OU_OSC, tau, freq, coeff, dt, n_t, n_trials, 1, data_sd, data_mean,
+                           update, seed, u0, noise, phases, out);
+}
+
+// ---- measurement -----------------------------------------------------------------------
+int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
+    if (!ctx || !tflops_out) return fail(ctx, ITJL_ERR_ARG, "itjl_fp32_peak: null argument");
+    if (iters < 1) iters = 1;
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8;
+    const int inner = 4096;
+    ITJL_CUDA(ctx, ctx->scratch.reserve((size_t)blocks * kThreads * sizeof(float)));
+    cudaError_t e = fp32_peak_launch((float*)ctx->scratch.p, blocks, inner, ctx->stream);   // warm-up
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_fp32_peak: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double best = 0.0;
+    for (int i = 0; i < iters; ++i) {
+        ITJL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        e = fp32_peak_launch((float*)ctx->scratch.p, blocks, inner, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_fp32_peak: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        ITJL_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        ITJL_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double tf = fp32_peak_flops_per_launch(blocks, inner) / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    *tflops_out = best;
+    return ITJL_OK;
+}
+
+}  // extern "C"

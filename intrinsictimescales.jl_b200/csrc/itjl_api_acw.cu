@@ -1,0 +1,289 @@
+// C-ABI layer, part 2: summary statistics on stored data and acw()
+// (reference src/stats/summary.jl:46-89, 183-235, 455-496 and src/core/acw.jl:141-231).
+#include <math.h>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace itjl;
+
+static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t) {
+    const size_t bytes = (size_t)n_slices * n_t * sizeof(double);
+    ITJL_CUDA(ctx, ctx->data.reserve(bytes));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->data.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ITJL_OK;
+}
+
+static int check_data_args(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, const char* who) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "%s: null context", who);
+    if (!data) return fail(ctx, ITJL_ERR_ARG, "%s: null data", who);
+    if (n_slices < 1 || n_slices > 0x7fffffffll) return fail(ctx, ITJL_ERR_ARG, "%s: n_slices out of range", who);
+    if (n_t < 2 || n_t > (1 << 24)) return fail(ctx, ITJL_ERR_ARG, "%s: need 2 <= n_t <= 2^24", who);
+    return ITJL_OK;
+}
+
+// Device-side ACF of every slice up to n_lags into ctx->out (row-per-slice, ld = cap).
+static int acf_all(itjl_ctx* ctx, int64_t n_slices, int n_t, int n_lags, int missing, int64_t cap, bool reset) {
+    ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 4 + 4) * sizeof(int32_t)));
+    int32_t* n_done = (int32_t*)ctx->flags.p;
+    if (reset) ITJL_CUDA(ctx, cudaMemsetAsync(n_done, 0, (size_t)n_slices * sizeof(int32_t), ctx->stream));
+    cudaError_t e = acf_fill_launch((const double*)ctx->data.p, n_slices, n_t, missing, n_lags,
+                                    (double*)ctx->out.p, cap, n_done, ctx->max_smem_optin, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return ITJL_OK;
+}
+
+static int acf_entry(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t n_lags,
+                     int missing, double* out, const char* who) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, who);
+    if (rc != ITJL_OK) return rc;
+    if (!out) return fail(ctx, ITJL_ERR_ARG, "%s: null output", who);
+    if (n_lags < 1 || n_lags > n_t) return fail(ctx, ITJL_ERR_ARG, "%s: need 1 <= n_lags <= n_t", who);
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_lags > acf_max_reach((int)n_t, ctx->max_smem_optin))
+        return fail(ctx, ITJL_ERR_ARG, "%s: n_t + n_lags does not fit in shared memory", who);
+    rc = upload_data(ctx, data, n_slices, n_t);
+    if (rc != ITJL_OK) return rc;
+    rc = acf_all(ctx, n_slices, (int)n_t, (int)n_lags, missing, n_lags, true);
+    if (rc != ITJL_OK) return rc;
+    const size_t obytes = (size_t)n_slices * n_lags * sizeof(double);
+    ITJL_CUDA(ctx, ctx->out2.reserve(obytes));
+    cudaError_t e = acf_export_launch((const double*)ctx->out.p, n_slices, n_lags, (int)n_lags, (double*)ctx->out2.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_export: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(out, ctx->out2.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
+static void prime_strides(int w, std::vector<int>& strides) {
+    // Romberg.jl: strides 1, f1, f1 f2, ..., w-1 with f_i the prime factors of w-1 (increasing)
+    strides.clear();
+    strides.push_back(1);
+    int m = w - 1;
+    for (int p = 2; (long long)p * p <= m; ++p)
+        while (m % p == 0) { strides.push_back(strides.back() * p); m /= p; }
+    if (m > 1) strides.push_back(strides.back() * m);
+}
+
+extern "C" {
+
+int itjl_acf(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t n_lags, double* out) {
+    return acf_entry(ctx, data, n_slices, n_t, n_lags, 0, out, "itjl_acf");
+}
+
+int itjl_acf_missing(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t n_lags, double* out) {
+    return acf_entry(ctx, data, n_slices, n_t, n_lags, 1, out, "itjl_acf_missing");
+}
+
+int itjl_psd_hamming(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double* out) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_psd_hamming");
+    if (rc != ITJL_OK) return rc;
+    if (!out || !(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_psd_hamming: null output or fs <= 0");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int n2 = 2; while (n2 < n_t) n2 <<= 1; n2 <<= 1;             // 2 * nextpow2(n_t)
+    int log2_n2 = 0; while ((1 << log2_n2) < n2) log2_n2++;
+    const size_t smem = (size_t)n2 * sizeof(float);
+    if ((int64_t)smem > ctx->max_smem_optin) return fail(ctx, ITJL_ERR_ARG, "itjl_psd_hamming: FFT does not fit in shared memory");
+    std::vector<float> win((size_t)n_t);
+    std::vector<float2> tw((size_t)n2 / 2);
+    double win_ss = 0.0;
+    psd_make_tables((int)n_t, n2, win.data(), tw.data(), &win_ss);
+    const double scale = 1.0 / (fs * win_ss);
+    rc = upload_data(ctx, data, n_slices, n_t);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->scratch.reserve(win.size() * sizeof(float)));
+    ITJL_CUDA(ctx, ctx->out3.reserve(tw.size() * sizeof(float2)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out3.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t nb = n2 / 2 - 1;
+    const size_t obytes = (size_t)n_slices * nb * sizeof(double);
+    ITJL_CUDA(ctx, ctx->out.reserve(obytes));
+    cudaError_t e = psd_data_launch((const double*)ctx->data.p, n_slices, (int)n_t, n2, log2_n2, (const float*)ctx->scratch.p,
+                                    (const float2*)ctx->out3.p, scale, (double*)ctx->out.p, smem, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_psd_data: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // win / tw stay alive until here
+    return ITJL_OK;
+}
+
+int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt, double* tau_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_fit_expdecay: null context");
+    if (!acf || !tau_out || n_rows < 1 || n_lags < 1 || !(dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_fit_expdecay: invalid argument");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // rows are read with stride 1 along lags: transpose the column-major input on the host
+    std::vector<double> rows((size_t)n_rows * n_lags);
+    for (int64_t r = 0; r < n_rows; ++r)
+        for (int64_t k = 0; k < n_lags; ++k) rows[(size_t)r * n_lags + k] = acf[r + k * n_rows];
+    ITJL_CUDA(ctx, ctx->out.reserve(rows.size() * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->out3.reserve((size_t)n_rows * sizeof(double)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out.p, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = acw_tau_launch((const double*)ctx->out.p, n_rows, n_lags, (int)n_lags, dt, (double*)ctx->out3.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_tau: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(tau_out, ctx->out3.p, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
+int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, uint32_t typemask,
+             int32_t average_over_trials, int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke,
+             double* auc, double* tau, double* acf_out, int64_t acf_capacity) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_acw");
+    if (rc != ITJL_OK) return rc;
+    if (!n_lags_io) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags_io is required");
+    if (!(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: fs must be positive");
+    if ((typemask & ~31u) || typemask == 0) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: No ACW types specified / unknown type bit");
+    if (((typemask & ITJL_ACW0) && !k0) || ((typemask & ITJL_ACW50) && !k50) || ((typemask & ITJL_ACWEULER) && !ke) ||
+        ((typemask & ITJL_AUC) && !auc) || ((typemask & ITJL_TAU) && !tau))
+        return fail(ctx, ITJL_ERR_ARG, "itjl_acw: output pointer missing for a requested acwtype");
+    const int64_t user_lags = *n_lags_io;
+    if (user_lags < 0 || user_lags > n_t) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags out of range");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double dt = 1.0 / fs;
+    const int nt = (int)n_t;
+    const int reach = acf_max_reach(nt, ctx->max_smem_optin);
+    if (reach < 40) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_t too large for the shared-memory ACF kernel");
+
+    rc = upload_data(ctx, data, n_slices, n_t);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 4 + 4) * sizeof(int32_t)));
+    int32_t* d_done = (int32_t*)ctx->flags.p;
+    int32_t* d_nan = d_done + 4 * n_slices;
+    int32_t* d_k0 = d_done + n_slices;
+    int32_t* d_k50 = d_k0 + n_slices;
+    int32_t* d_ke = d_k50 + n_slices;
+
+    const int64_t n_out = average_over_trials ? 1 : n_slices;
+    std::vector<int32_t> h_k0((size_t)n_out), h_k50((size_t)n_out), h_ke((size_t)n_out);
+    const double* acf_rows = nullptr;      // device rows used by the epilogues
+    int64_t acf_ld = 0;
+    int64_t lags_avail = 0;
+    int64_t cap = 0;
+    cudaError_t e;
+
+    if (!average_over_trials) {
+        // NaN-aware centring is the identity on complete data, so one code path serves both
+        // comp_ac_fft (acw.jl:146) and comp_ac_time_missing (acw.jl:148-153).
+        cap = reach;
+        ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
+        ITJL_CUDA(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int32_t), ctx->stream));
+        e = acw_scan_launch((const double*)ctx->data.p, n_slices, nt, 1, reach, (double*)ctx->out.p, cap,
+                            d_done, d_k0, d_k50, d_ke, d_nan, ctx->max_smem_optin, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(scan): %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(h_k0.data(), d_k0, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(h_k50.data(), d_k50, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(h_ke.data(), d_ke, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        int32_t has_nan = 0;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(&has_nan, d_nan, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (has_nan && user_lags > 0) {
+            // NaN data + user n_lags: the reference only computes n_lags lags (acw.jl:151-152)
+            for (int64_t i = 0; i < n_slices; ++i) {
+                if (h_k0[i] >= user_lags) h_k0[i] = -1;
+                if (h_k50[i] >= user_lags) h_k50[i] = -1;
+                if (h_ke[i] >= user_lags) h_ke[i] = -1;
+            }
+        }
+        acf_rows = (const double*)ctx->out.p; acf_ld = cap;
+    } else {
+        // acf = mean(acf, dims = trial_dims) over ALL lags (acw.jl:156-158): grow the lag
+        // range until the mean ACF crosses zero.
+        int L = (int)(user_lags > 0 ? user_lags : 64);
+        if (L > reach) L = reach;
+        bool first = true;
+        for (;;) {
+            cap = reach;
+            rc = acf_all(ctx, n_slices, nt, L, 1, cap, first);
+            if (rc != ITJL_OK) return rc;
+            first = false;
+            ITJL_CUDA(ctx, ctx->out2.reserve((size_t)reach * sizeof(double)));
+            e = acf_mean_launch((const double*)ctx->out.p, n_slices, cap, L, (double*)ctx->out2.p, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_mean: %s", cudaGetErrorString(e));
+            ctx->launches++;
+            e = acf_cross_launch((const double*)ctx->out2.p, 1, reach, L, d_k0, d_k50, d_ke, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_cross: %s", cudaGetErrorString(e));
+            ctx->launches++;
+            ITJL_CUDA(ctx, cudaMemcpyAsync(h_k0.data(), d_k0, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            ITJL_CUDA(ctx, cudaMemcpyAsync(h_k50.data(), d_k50, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            ITJL_CUDA(ctx, cudaMemcpyAsync(h_ke.data(), d_ke, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_k0[0] >= 0 || L >= reach) break;
+            L = (L * 4 > reach) ? reach : L * 4;
+        }
+        lags_avail = L;
+        acf_rows = (const double*)ctx->out2.p; acf_ld = reach;
+    }
+
+    // n_lags (acw.jl:203-210)
+    int64_t n_lags = user_lags;
+    if (n_lags == 0) {
+        int32_t mx = -1;
+        for (int64_t i = 0; i < n_out; ++i) if (h_k0[i] > mx) mx = h_k0[i];
+        n_lags = (mx < 0) ? n_t : (int64_t)ceil(1.1 * (double)mx);
+        if (n_lags > n_t) n_lags = n_t;
+    }
+    if (n_lags > reach) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags exceeds the shared-memory reach for this n_t");
+    *n_lags_io = n_lags;
+
+    // make sure every row holds n_lags lags
+    if (!average_over_trials) {
+        e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)n_lags, (double*)ctx->out.p, cap,
+                            d_done, ctx->max_smem_optin, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
+        ctx->launches++;
+    } else if (n_lags > lags_avail) {
+        rc = acf_all(ctx, n_slices, nt, (int)n_lags, 1, cap, false);
+        if (rc != ITJL_OK) return rc;
+        e = acf_mean_launch((const double*)ctx->out.p, n_slices, cap, (int)n_lags, (double*)ctx->out2.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_mean: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    }
+
+    if (typemask & ITJL_ACW0) memcpy(k0, h_k0.data(), (size_t)n_out * 4);
+    if (typemask & ITJL_ACW50) memcpy(k50, h_k50.data(), (size_t)n_out * 4);
+    if (typemask & ITJL_ACWEULER) memcpy(ke, h_ke.data(), (size_t)n_out * 4);
+
+    ITJL_CUDA(ctx, ctx->out3.reserve((size_t)n_out * 2 * sizeof(double) + 64 * sizeof(int)));
+    double* d_auc = (double*)ctx->out3.p;
+    double* d_tau = d_auc + n_out;
+    int* d_strides = (int*)(d_tau + n_out);
+    std::vector<int> strides;                      // must outlive the async copy
+    if (typemask & ITJL_AUC) {
+        // window = floor(Int, acw0_sample[1]) of the FIRST slice (acw.jl:194)
+        const int w = h_k0[0];
+        if (w < 2 || w > n_lags) {
+            for (int64_t i = 0; i < n_out; ++i) auc[i] = NAN;    // reference throws here
+        } else {
+            prime_strides(w, strides);
+            ITJL_CUDA(ctx, cudaMemcpyAsync(d_strides, strides.data(), strides.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            e = acw_auc_launch(acf_rows, n_out, acf_ld, w, dt, d_strides, (int)strides.size(), d_auc, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_auc: %s", cudaGetErrorString(e));
+            ctx->launches++;
+            ITJL_CUDA(ctx, cudaMemcpyAsync(auc, d_auc, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    if (typemask & ITJL_TAU) {
+        e = acw_tau_launch(acf_rows, n_out, acf_ld, (int)n_lags, dt, d_tau, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_tau: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (acf_out) {
+        if (acf_capacity < n_out * n_lags) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: acf_out capacity too small");
+        const size_t obytes = (size_t)n_out * n_lags * sizeof(double);
+        ITJL_CUDA(ctx, ctx->stats.reserve(obytes));
+        e = acf_export_launch(acf_rows, n_out, acf_ld, (int)n_lags, (double*)ctx->stats.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_export: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(acf_out, ctx->stats.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
+}  // extern "C"

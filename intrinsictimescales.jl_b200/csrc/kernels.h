@@ -1,0 +1,106 @@
+// Internal declarations shared between the kernel translation units and the C-ABI layer.
+#pragma once
+#include "common.cuh"
+
+namespace itjl {
+
+// ---- abc_kernels.cu ------------------------------------------------------------------
+struct AbcAcfParams {
+    const double* theta;
+    int64_t n_particles;
+    int n_theta;
+    int n_t, n_trials, n_lags;
+    int chunk, xs_stride;
+    int lt, n_streams, tiles_per_stream, n_tiles;
+    double dt, data_mean, data_sd;
+    int update, kind, distance;
+    uint32_t k0, k1, c3_noise, c3_init;
+    int64_t particle_offset;
+    const float* target;
+    const uint32_t* mask_bits;
+    const int* n_valid;
+    int mask_words;
+    const double* u0;
+    const double* noise;
+    const double* phases;
+    double* dist_out;
+    double* stats_out;
+};
+struct AbcAcfGeometry {
+    int chunk, xs_stride, lt, n_streams, tiles_per_stream, n_tiles;
+    size_t smem_bytes;
+};
+int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g);
+cudaError_t abc_acf_launch(const AbcAcfParams& P, bool missing, bool osc, size_t smem, cudaStream_t st);
+cudaError_t abc_accept_launch(const double* dist, int64_t n, double eps, int64_t min_accepted,
+                              uint8_t* isacc, int64_t* out2, cudaStream_t st);
+
+// ---- psd_kernels.cu ------------------------------------------------------------------
+struct AbcPsdParams {
+    const double* theta;
+    int64_t n_particles;
+    int n_theta;
+    int n_t, n_trials, n_stats;
+    int chunk, xs_len;          // simulate chunk; floats in the staging buffer
+    int n2, log2_n2;            // zero-padded real FFT length 2*nextpow2(n_t)
+    double dt, data_mean, data_sd;
+    int update, kind, distance;
+    uint32_t k0, k1, c3_noise, c3_init;
+    int64_t particle_offset;
+    const float* target;        // n_stats
+    const int32_t* bins;        // n_stats, 0-based into psd[2:n2/2]
+    const float* window;        // n_t Hamming window
+    const float2* twiddle;      // n2/2 complex roots exp(-2 pi i k / (n2/2))... see psd_kernels.cu
+    double psd_scale;           // 1 / (fs * sum(window^2))
+    const double* u0;
+    const double* noise;
+    const double* phases;
+    double* dist_out;
+    double* stats_out;
+};
+size_t abc_psd_smem_bytes(int n_t, int n2, int* chunk_out, int* xs_len_out);
+cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st);
+// standalone: comp_psd_adfriendly on stored data (n_slices x n_t col-major double)
+cudaError_t psd_data_launch(const double* data, int64_t n_slices, int n_t, int n2, int log2_n2,
+                            const float* window, const float2* twiddle, double psd_scale,
+                            double* out, size_t smem, cudaStream_t st);
+void psd_make_tables(int n_t, int n2, float* window_host, float2* twiddle_host, double* win_ss);
+
+// ---- ou_kernels.cu -------------------------------------------------------------------
+struct OuGenParams {
+    int n_t, n_trials, chunk;
+    double tau, freq, coeff, dt;
+    int update, kind, mode;     // mode: kScale*
+    float scale, shift;
+    uint32_t k0, k1, c3_noise, c3_init, particle;
+    const double* u0;
+    const double* noise;
+    const double* phases;
+    double* out;                // (n_trials x n_t) column-major
+};
+cudaError_t ou_generate_launch(const OuGenParams& P, cudaStream_t st);
+
+// ---- acw_kernels.cu ------------------------------------------------------------------
+// acf_work is a row-per-slice work buffer [slice][cap]; n_done[slice] = lags present.
+cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int missing, int max_lags,
+                            double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
+                            int32_t* ke, int32_t* nan_flag, int max_smem, cudaStream_t st);
+cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
+                            double* acf_work, int64_t cap, int32_t* n_done, int max_smem, cudaStream_t st);
+cudaError_t acf_cross_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, int32_t* k0,
+                             int32_t* k50, int32_t* ke, cudaStream_t st);
+cudaError_t acf_mean_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double* out,
+                            cudaStream_t st);
+cudaError_t acf_export_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double* out,
+                              cudaStream_t st);
+cudaError_t acw_auc_launch(const double* acf, int64_t n_rows, int64_t ld, int w, double dt,
+                           const int* strides, int n_strides, double* auc, cudaStream_t st);
+cudaError_t acw_tau_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double dt, double* tau,
+                           cudaStream_t st);
+int acf_max_reach(int n_t, int max_smem);
+
+// ---- peak_kernels.cu -----------------------------------------------------------------
+cudaError_t fp32_peak_launch(float* sink, int blocks, int iters, cudaStream_t st);
+double fp32_peak_flops_per_launch(int blocks, int iters);
+
+}  // namespace itjl

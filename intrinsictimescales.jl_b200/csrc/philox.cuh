@@ -1,0 +1,50 @@
+// Philox4x32-10 counter-based RNG + normal transform, device side.
+// Bit-for-bit the stream specified in oracle/philox.py (counter layout, 23-bit uniforms,
+// Box-Muller with cos/sin ordering).  One Philox block feeds four consecutive samples.
+#pragma once
+#include <stdint.h>
+
+namespace itjl {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+constexpr uint32_t kStreamNoise = 0u;
+constexpr uint32_t kStreamInit = 1u;
+
+__host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t stream, uint64_t generation) {
+    return ((stream & 0xFu) << 28) | (uint32_t)(generation & 0x0FFFFFFFull);
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += kPhiloxW0; k1 += kPhiloxW1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ((r >> 9) + 0.5) * 2^-23 : exact in fp32, in (0, 1)
+__device__ __forceinline__ float u01(uint32_t r) {
+    return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
+    const float u = u01(ra);
+    const float v = u01(rb);
+    const float rad = sqrtf(-2.0f * logf(u));
+    float s, c;
+    sincospif(2.0f * v, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+}  // namespace itjl

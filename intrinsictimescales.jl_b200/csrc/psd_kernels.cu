@@ -1,0 +1,233 @@
+// K2: fused  simulate OU(+oscillation) trials -> Hamming periodogram -> trial mean ->
+// distance, one CTA per particle, with the n2 = 2*nextpow2(n_t) point real FFT held
+// entirely in shared memory (n2/2 complex points, in place).
+//
+// Replaces (reference) generate_data -> generate_ou_with_oscillation
+// (src/utils/ou_process.jl:176-218), summary_stats ->
+// mean(comp_psd_adfriendly(data, 1/dt)[1], dims=1)[:][freq_idx]
+// (src/models/one_timescale_and_osc.jl:293 -> src/stats/summary.jl:204-235) and
+// logarithmic_distance / linear_distance (src/stats/distances.jl:29-53).
+//
+// Real FFT of length n2: pack z[m] = x[2m] + i x[2m+1] (exactly the float layout the
+// simulator writes), run an in-place radix-4 DIF complex FFT of N = n2/2 points (output in
+// digit-reversed order, which is never undone - bins are read through the permutation) and
+// recombine X[k] = E[k] + exp(-2 pi i k/n2) O[k] only for the selected bins.
+#include <math.h>
+
+#include "kernels.h"
+#include "simulate.cuh"
+
+namespace itjl {
+
+// U[k] = exp(-2 pi i k / n2), k in [0, n2/2)
+__device__ __forceinline__ float2 tw_lookup(const float2* __restrict__ U, int idx, int N) {
+    // idx in [0, 2N): exp(-2 pi i idx / (2N)); second half by symmetry
+    if (idx >= N) { const float2 w = __ldg(U + (idx - N)); return make_float2(-w.x, -w.y); }
+    return __ldg(U + idx);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// In-place radix-4 (+ final radix-2) DIF FFT of N complex points in shared memory.
+__device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* __restrict__ U) {
+    const int tid = threadIdx.x;
+    int span = N;
+    while (span >= 4) {
+        const int q = span >> 2;
+        const int tstep = (2 * N) / span;          // W_span^j = U[j * tstep]
+        for (int u = tid; u < (N >> 2); u += kThreads) {
+            const int j = u & (q - 1);
+            const int base = (u / q) * span + j;
+            const float2 x0 = buf[base], x1 = buf[base + q], x2 = buf[base + 2 * q], x3 = buf[base + 3 * q];
+            const float2 a0 = make_float2(x0.x + x2.x, x0.y + x2.y);
+            const float2 a1 = make_float2(x0.x - x2.x, x0.y - x2.y);
+            const float2 a2 = make_float2(x1.x + x3.x, x1.y + x3.y);
+            const float2 a3 = make_float2(x1.x - x3.x, x1.y - x3.y);
+            const float2 y0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+            float2 y1 = make_float2(a1.x + a3.y, a1.y - a3.x);      // a1 - i a3
+            float2 y2 = make_float2(a0.x - a2.x, a0.y - a2.y);
+            float2 y3 = make_float2(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
+            if (j != 0) {
+                const int t1 = j * tstep;
+                y1 = cmul(y1, tw_lookup(U, t1, N));
+                y2 = cmul(y2, tw_lookup(U, 2 * t1, N));
+                y3 = cmul(y3, tw_lookup(U, 3 * t1, N));
+            }
+            buf[base] = y0; buf[base + q] = y1; buf[base + 2 * q] = y2; buf[base + 3 * q] = y3;
+        }
+        __syncthreads();
+        span = q;
+    }
+    if (span == 2) {
+        for (int u = tid; u < (N >> 1); u += kThreads) {
+            const float2 x0 = buf[2 * u], x1 = buf[2 * u + 1];
+            buf[2 * u] = make_float2(x0.x + x1.x, x0.y + x1.y);
+            buf[2 * u + 1] = make_float2(x0.x - x1.x, x0.y - x1.y);
+        }
+        __syncthreads();
+    }
+}
+
+// storage position of frequency k after fft_inplace_dif
+__device__ __forceinline__ int fft_pos(int k, int N) {
+    int p = 0, size = N;
+    while (size >= 4) { size >>= 2; p += (k & 3) * size; k >>= 2; }
+    if (size == 2) p += (k & 1);
+    return p;
+}
+
+// |X[k]|^2 of the length-2N real FFT from the packed complex FFT, 1 <= k <= N-1
+__device__ __forceinline__ float real_fft_power(const float2* __restrict__ buf, int k, int N,
+                                                const float2* __restrict__ U) {
+    const float2 zk = buf[fft_pos(k, N)];
+    const float2 zn = buf[fft_pos(N - k, N)];
+    const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);        // E = (Zk + conj Zn)/2
+    const float dr = 0.5f * (zk.x - zn.x), di = 0.5f * (zk.y + zn.y);        // D = (Zk - conj Zn)/2
+    const float or_ = di, oi = -dr;                                          // O = -i D
+    const float2 w = __ldg(U + k);
+    const float xr = er + (w.x * or_ - w.y * oi);
+    const float xi = ei + (w.x * oi + w.y * or_);
+    return xr * xr + xi * xi;
+}
+
+template <bool OSC>
+__global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats = N float2
+    float2* buf = reinterpret_cast<float2*>(smem_raw);
+    float* accb = xs + P.xs_len;                                    // n_stats
+    SimShared* sh = reinterpret_cast<SimShared*>(accb + ((P.n_stats + 3) & ~3));
+    __shared__ double red[kWarps];
+
+    const int tid = threadIdx.x;
+    const int64_t particle = blockIdx.x;
+    const int N = P.n2 >> 1;
+
+    const double tau = P.theta[particle];
+    double freq = 0.0, coeff = 1.0;
+    if (OSC) {
+        freq = P.theta[particle + P.n_particles];
+        coeff = P.theta[particle + 2 * P.n_particles];
+    }
+    const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
+                                       freq, coeff);
+    SimArgs g;
+    g.n_t = P.n_t; g.chunk = P.chunk;
+    g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
+    g.particle = (uint32_t)(P.particle_offset + particle);
+    const size_t pt = (size_t)particle * P.n_trials;
+    g.u0 = P.u0 ? P.u0 + pt : nullptr;
+    g.noise = P.noise ? P.noise + pt * P.n_t : nullptr;
+    g.phases = P.phases ? P.phases + pt : nullptr;
+    g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;
+
+    for (int b = tid; b < P.n_stats; b += kThreads) accb[b] = 0.f;
+
+    for (int trial = 0; trial < P.n_trials; ++trial) {
+        // standardised series * data_sd; the reference then adds data_mean and
+        // comp_psd_adfriendly removes the mean again (summary.jl:209) - skipped both.
+        simulate_trial<false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, 0.0f);
+        for (int i = P.chunk * kThreads + tid; i < P.xs_len; i += kThreads) xs[i] = 0.f;
+        __syncthreads();
+        for (int j = tid; j < P.n_t; j += kThreads) xs[j] *= __ldg(P.window + j);
+        __syncthreads();
+        fft_inplace_dif(buf, N, P.twiddle);
+        for (int b = tid; b < P.n_stats; b += kThreads)
+            accb[b] += real_fft_power(buf, __ldg(P.bins + b) + 1, N, P.twiddle);
+        __syncthreads();
+    }
+
+    const double sc = P.psd_scale / (double)P.n_trials;
+    double local = 0.0;
+    for (int b = tid; b < P.n_stats; b += kThreads) {
+        const double v = (double)accb[b] * sc;
+        if (P.stats_out) P.stats_out[(size_t)particle * P.n_stats + b] = v;
+        const double tgt = (double)P.target[b];
+        const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
+        local += e * e;
+    }
+    local = warp_sum(local);
+    if ((tid & 31) == 0) red[tid >> 5] = local;
+    __syncthreads();
+    if (tid == 0) {
+        double d = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) d += red[w];
+        P.dist_out[particle] = d / (double)P.n_stats;
+    }
+}
+
+// comp_psd_adfriendly on stored data: one CTA per slice, all n2/2 - 1 bins out.
+__global__ void __launch_bounds__(kThreads, 1) k_psd_data(const double* __restrict__ data, int64_t n_slices,
+                                                          int n_t, int n2, const float* __restrict__ window,
+                                                          const float2* __restrict__ U, double psd_scale,
+                                                          double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float2* buf = reinterpret_cast<float2*>(smem_raw);
+    __shared__ double red[kWarps];
+    const int tid = threadIdx.x;
+    const int64_t s = blockIdx.x;
+    const int N = n2 >> 1;
+    double local = 0.0;
+    for (int j = tid; j < n_t; j += kThreads) local += data[s + (size_t)j * n_slices];
+    local = warp_sum(local);
+    if ((tid & 31) == 0) red[tid >> 5] = local;
+    __syncthreads();
+    double mean = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) mean += red[w];
+    mean /= (double)n_t;
+    for (int j = tid; j < n2; j += kThreads)
+        xs[j] = (j < n_t) ? (float)((data[s + (size_t)j * n_slices] - mean) * (double)__ldg(window + j)) : 0.f;
+    __syncthreads();
+    fft_inplace_dif(buf, N, U);
+    for (int k = 1 + tid; k < N; k += kThreads)
+        out[s + (size_t)(k - 1) * n_slices] = (double)real_fft_power(buf, k, N, U) * psd_scale;
+}
+
+size_t abc_psd_smem_bytes(int n_t, int n2, int* chunk_out, int* xs_len_out) {
+    int c = (n_t + kThreads - 1) / kThreads;
+    c = (c + 3) & ~3;
+    int xs_len = n2;                                   // N float2 = n2 floats
+    if (xs_len < c * kThreads) xs_len = c * kThreads;
+    *chunk_out = c;
+    *xs_len_out = xs_len;
+    return (size_t)xs_len * sizeof(float);            // caller adds accumulators + SimShared
+}
+
+void psd_make_tables(int n_t, int n2, float* window_host, float2* twiddle_host, double* win_ss) {
+    const double PI = 3.14159265358979323846;
+    double ss = 0.0;
+    for (int i = 0; i < n_t; ++i) {
+        const double w = 0.54 - 0.46 * cos(2.0 * PI * (double)i / (double)(n_t - 1));   // summary.jl:214
+        window_host[i] = (float)w;
+        ss += w * w;
+    }
+    *win_ss = ss;
+    for (int k = 0; k < n2 / 2; ++k) {
+        const double ang = -2.0 * PI * (double)k / (double)n2;
+        twiddle_host[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+}
+
+cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st) {
+    void (*kern)(const AbcPsdParams) = osc ? k_abc_psd<true> : k_abc_psd<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)P.n_particles, kThreads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t psd_data_launch(const double* data, int64_t n_slices, int n_t, int n2, int log2_n2,
+                            const float* window, const float2* twiddle, double psd_scale, double* out,
+                            size_t smem, cudaStream_t st) {
+    (void)log2_n2;
+    cudaError_t e = cudaFuncSetAttribute(k_psd_data, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_psd_data<<<(unsigned)n_slices, kThreads, smem, st>>>(data, n_slices, n_t, n2, window, twiddle, psd_scale, out);
+    return cudaGetLastError();
+}
+
+}  // namespace itjl

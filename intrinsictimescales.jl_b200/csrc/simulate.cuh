@@ -1,0 +1,240 @@
+// One OU (+ oscillation) trial simulated by a whole CTA straight into shared memory.
+//
+// Replaces, per trial, generate_ou_process / generate_ou_with_oscillation
+// (reference src/utils/ou_process.jl:114-148, 176-218) followed by the centring /
+// scaling that the summary statistic applies first (summary.jl:48, 466-471, 209-213).
+//
+// The linear recurrence x_{k+1} = a x_k + s xi_k is serial in k, so it is evaluated as a
+// blocked scan: every thread integrates its own chunk of `chunk` consecutive samples from
+// a zero state (Philox noise generated in registers), the chunk-end affine maps
+// (a^chunk, y_end) are combined by a warp-shuffle + shared-memory scan, and the carry-in
+// is added back as p_j * carry with p_j = a^(j+1).  Mean and sum of squares follow
+// analytically from per-thread partial sums (S_y, S_yy, S_yp, S_p, S_pp), so the trial
+// needs exactly two passes over its chunk and three __syncthreads().
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace itjl {
+
+struct OuConsts {
+    float eps;    // 1 - a, a = exp(-dt/tau) (exact) or 1 - dt/tau (Euler-Maruyama)
+    float s;      // innovation scale sqrt(tau/2 (1-a^2)) or sqrt(dt)
+    float sc;     // sqrt(coeff)            (1 for the plain OU model)
+    float so;     // sqrt(1-coeff)*sqrt(2)  (0 for the plain OU model)
+    double fdt;   // freq * dt, in turns per sample
+};
+
+__device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int update, int kind,
+                                                   double freq, double coeff) {
+    OuConsts c;
+    double eps, s;
+    if (update == ITJL_UPDATE_EXACT) {
+        const double x = -dt / tau;
+        eps = -expm1(x);                       // 1 - a without cancellation
+        const double a = 1.0 - eps;
+        s = sqrt(tau * 0.5 * (1.0 - a * a));
+    } else {
+        eps = dt / tau;
+        s = sqrt(dt);
+    }
+    c.eps = (float)eps;
+    c.s = (float)s;
+    c.sc = 1.0f; c.so = 0.0f; c.fdt = 0.0;
+    if (kind == ITJL_KIND_OU_OSC) {
+        // ou_process.jl:189-196: only values outside [0, 1] are moved
+        if (coeff < 0.0) coeff = 1e-4; else if (coeff > 1.0) coeff = 1.0 - 1e-4;
+        c.sc = (float)sqrt(coeff);
+        c.so = (float)(sqrt(1.0 - coeff) * 1.4142135623730951);
+        c.fdt = freq * dt;
+    }
+    return c;
+}
+
+struct SimShared {
+    float scanA[kWarps];
+    float scanB[kWarps];
+    double sums[kWarps][4];
+};
+
+enum : int { kScaleUnitNorm = 0, kScaleStd = 1, kScaleRaw = 2 };
+
+struct SimArgs {
+    int n_t;                  // samples per trial
+    int chunk;                // samples per thread (multiple of 4, chunk * kThreads >= n_t)
+    uint32_t k0, k1;          // Philox key (seed)
+    uint32_t c3_noise, c3_init;
+    uint32_t particle;        // global particle index (low 32 bits)
+    const double* u0;         // [trial] injected initial states of this particle, or null
+    const double* noise;      // [trial][n_t] injected N(0,1) increments, or null
+    const double* phases;     // [trial] injected phases (radians), or null
+    const uint32_t* mask_bits;  // [trial][mask_words] missing-sample bitmap, or null
+    const int* n_valid;         // [trial] number of valid samples
+    int mask_words;
+};
+
+// Simulate trial `trial` into xs[0 .. chunk*kThreads).  On return (after the caller's
+// __syncthreads()) xs holds
+//   kScaleUnitNorm : (x - mean) / sqrt(sum (x-mean)^2)                (ACF kernels)
+//                    with MISSING: the comp_ac_time_missing centring, masked samples = -m2
+//   kScaleStd      : (x - mean) / std_{n-1} * scale + shift            (PSD kernel, generator)
+//   kScaleRaw      : x                                                 (standardize = false)
+// and zeros for j >= n_t.
+template <bool MISSING, bool OSC>
+__device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts& oc, int trial,
+                                               float* __restrict__ xs, SimShared* sh, int mode,
+                                               float scale, float shift) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = tid * g.chunk;
+    const float eps = oc.eps, s = oc.s;
+
+    // per-trial initial state and phase (stream 1, block 0)
+    float x0;
+    double phase_turns;
+    {
+        uint32_t r[4];
+        philox4x32_10(0u, (uint32_t)trial, g.particle, g.c3_init, g.k0, g.k1, r);
+        float z1;
+        box_muller(r[0], r[1], x0, z1);
+        phase_turns = (double)u01(r[2]);
+        if (g.u0) x0 = (float)g.u0[trial];
+        if (OSC && g.phases) phase_turns = g.phases[trial] * 0.15915494309189535;
+    }
+
+    // ---- pass A: local recurrence from a zero state + partial sums -----------------
+    float y = 0.f, p = 1.f;
+    float Sy = 0.f, Syy = 0.f, Syp = 0.f, Sp = 0.f, Spp = 0.f;
+    float Vy = 0.f, Vyy = 0.f, Vyp = 0.f, Vp = 0.f, Vpp = 0.f;   // valid-only sums (MISSING)
+    const double* nz = g.noise ? g.noise + (size_t)trial * g.n_t : nullptr;
+    const uint32_t* mrow = MISSING ? g.mask_bits + (size_t)trial * g.mask_words : nullptr;
+    if (j0 < g.n_t) {
+        for (int q = 0; q < g.chunk; q += 4) {
+            const int j = j0 + q;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t mbits = 0u;
+            if (j < g.n_t) {
+                if (nz) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (j + i < g.n_t) z[i] = (float)nz[j + i];
+                } else {
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise,
+                                  g.k0, g.k1, r);
+                    box_muller(r[0], r[1], z[0], z[1]);
+                    box_muller(r[2], r[3], z[2], z[3]);
+                }
+                if (MISSING) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
+            }
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y = fmaf(-eps, y, y);
+                y = fmaf(s, z[i], y);
+                p = fmaf(-eps, p, p);
+                float val = y, pp = p;
+                if (OSC) {
+                    double turns = fma(oc.fdt, (double)(j + i + 1), phase_turns);
+                    turns -= rint(turns);
+                    val = fmaf(oc.so, sinpif(2.0f * (float)turns), oc.sc * y);
+                    pp = oc.sc * p;
+                }
+                v[i] = val;
+                if (j + i < g.n_t) {
+                    Sy += val; Syy = fmaf(val, val, Syy); Syp = fmaf(val, pp, Syp);
+                    Sp += pp;  Spp = fmaf(pp, pp, Spp);
+                    if (MISSING && !((mbits >> i) & 1u)) {
+                        Vy += val; Vyy = fmaf(val, val, Vyy); Vyp = fmaf(val, pp, Vyp);
+                        Vp += pp;  Vpp = fmaf(pp, pp, Vpp);
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+
+    // ---- scan of the chunk-end affine maps x -> A x + B ----------------------------
+    float A = p, B = y;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+        const float Bp = __shfl_up_sync(0xffffffffu, B, d);
+        if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
+    }
+    if (lane == 31) { sh->scanA[warp] = A; sh->scanB[warp] = B; }
+    __syncthreads();
+    float xw = x0;                                   // state entering this warp's first chunk
+    for (int w = 0; w < warp; ++w) xw = fmaf(sh->scanA[w], xw, sh->scanB[w]);
+    const float Aprev = __shfl_up_sync(0xffffffffu, A, 1);
+    const float Bprev = __shfl_up_sync(0xffffffffu, B, 1);
+    const float c = (lane == 0) ? xw : fmaf(Aprev, xw, Bprev);   // carry into this chunk
+
+    // ---- mean / sum of squares from the partial sums --------------------------------
+    double r0 = (double)fmaf(c, Sp, Sy);
+    double r1 = (double)fmaf(c * c, Spp, fmaf(2.0f * c, Syp, Syy));
+    double r2 = 0.0, r3 = 0.0;
+    if (MISSING) {
+        r2 = (double)fmaf(c, Vp, Vy);
+        r3 = (double)fmaf(c * c, Vpp, fmaf(2.0f * c, Vyp, Vyy));
+    }
+    r0 = warp_sum(r0); r1 = warp_sum(r1);
+    if (MISSING) { r2 = warp_sum(r2); r3 = warp_sum(r3); }
+    if (lane == 0) {
+        sh->sums[warp][0] = r0; sh->sums[warp][1] = r1;
+        sh->sums[warp][2] = r2; sh->sums[warp][3] = r3;
+    }
+    __syncthreads();
+    double SX = 0.0, SXX = 0.0, VX = 0.0, VXX = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        SX += sh->sums[w][0]; SXX += sh->sums[w][1];
+        if (MISSING) { VX += sh->sums[w][2]; VXX += sh->sums[w][3]; }
+    }
+    const double n = (double)g.n_t;
+    double m = SX / n;
+    float mf, rf, miss_val = 0.f;
+    if (!MISSING) {
+        const double ss = SXX - n * m * m;
+        double r;
+        if (mode == kScaleUnitNorm) r = 1.0 / sqrt(ss);
+        else if (mode == kScaleStd) r = (double)scale / sqrt(ss / (n - 1.0));
+        else { r = 1.0; m = 0.0; }
+        mf = (float)m; rf = (float)r;
+    } else {
+        // comp_ac_time_missing (summary.jl:460-471) applied to the standardised, masked
+        // trial: valid z = x - m_all, masked z = 0; m2 = mean of valid z; every entry -= m2.
+        const double nv = (double)g.n_valid[trial];
+        const double m2 = (VX - nv * m) / nv;
+        const double mt = m + m2;
+        const double ss = VXX - 2.0 * mt * VX + nv * mt * mt + (n - nv) * m2 * m2;
+        const double r = 1.0 / sqrt(ss);
+        mf = (float)mt; rf = (float)r; miss_val = (float)(-m2 * r);
+    }
+
+    // ---- pass B: add the carry, centre, scale ---------------------------------------
+    if (j0 < g.n_t) {
+        float pb = 1.f;
+        for (int q = 0; q < g.chunk; q += 4) {
+            const int j = j0 + q;
+            float4 v4 = *reinterpret_cast<const float4*>(xs + j);
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            uint32_t mbits = 0u;
+            if (MISSING && j < g.n_t) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pb = fmaf(-eps, pb, pb);
+                const float pp = OSC ? oc.sc * pb : pb;
+                const float x = fmaf(pp, c, v[i]);
+                float o = fmaf(x - mf, rf, shift);
+                if (MISSING && ((mbits >> i) & 1u)) o = miss_val;
+                v[i] = (j + i < g.n_t) ? o : 0.f;
+            }
+            *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    } else {
+        for (int q = 0; q < g.chunk; q += 4)
+            *reinterpret_cast<float4*>(xs + j0 + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+}  // namespace itjl

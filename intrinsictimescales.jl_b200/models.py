@@ -1,0 +1,350 @@
+"""Model constructors and the model protocol, GPU-backed.
+
+Mirrors (same names, argument meaning, defaults and error behaviour):
+  one_timescale_model               src/models/one_timescale.jl:135-205 (ACF branch)
+  one_timescale_with_missing_model  src/models/one_timescale_with_missing.jl:137-213 (ACF branch)
+  one_timescale_and_osc_model       src/models/one_timescale_and_osc.jl:98-189
+  check_model_inputs                src/core/model.jl:239-292
+  draw_theta / generate_data / summary_stats / distance_function /
+  generate_data_and_reduce          src/core/model.jl:146-156 + the model files
+Every numeric step (data ACF/PSD, exp-decay prior fit, simulation, summary, distance) runs
+through libitjl_b200; the per-particle protocol functions are batch-of-one calls of the same
+kernels `basic_abc` uses.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+from . import _lib, summary, utils
+from .ou import n_time_points
+
+
+# ---------------------------------------------------------------- priors ----
+class Normal:
+    """Distributions.Normal(mu, sigma)."""
+
+    def __init__(self, mu, sigma):
+        self.mu, self.sigma = float(mu), float(sigma)
+
+    def rand(self, rng, size=None):
+        return rng.normal(self.mu, self.sigma, size)
+
+    def pdf(self, x):
+        z = (np.asarray(x, dtype=np.float64) - self.mu) / self.sigma
+        return np.exp(-0.5 * z * z) / (self.sigma * math.sqrt(2.0 * math.pi))
+
+    def __repr__(self):
+        return f"Normal(mu={self.mu}, sigma={self.sigma})"
+
+
+class Uniform:
+    """Distributions.Uniform(a, b)."""
+
+    def __init__(self, a, b):
+        self.a, self.b = float(a), float(b)
+
+    def rand(self, rng, size=None):
+        return rng.uniform(self.a, self.b, size)
+
+    def pdf(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return np.where((x >= self.a) & (x <= self.b), 1.0 / (self.b - self.a), 0.0)
+
+    def __repr__(self):
+        return f"Uniform(a={self.a}, b={self.b})"
+
+
+# ----------------------------------------------------------------- models ----
+@dataclass
+class TimescaleModel:
+    """Field-compatible with OneTimescaleModel / OneTimescaleWithMissingModel /
+    OneTimescaleAndOscModel (one_timescale.jl:61-83 and siblings)."""
+    kind: str
+    data: np.ndarray
+    time: np.ndarray
+    fit_method: str
+    summary_method: str
+    lags_freqs: np.ndarray
+    prior: list
+    distance_method: str
+    data_sum_stats: np.ndarray
+    dt: float
+    T: float
+    numTrials: int
+    data_mean: float
+    data_sd: float
+    freqlims: Any = None
+    n_lags: Any = None
+    freq_idx: Any = None
+    dims: int = 2
+    distance_combined: bool = False
+    missing_mask: Any = None
+    update: str = "exact"
+    _gpu: dict = field(default_factory=dict, repr=False)
+
+    @property
+    def n_t(self):
+        return n_time_points(self.dt, self.T)
+
+    @property
+    def n_theta(self):
+        return len(self.prior)
+
+    # ---- GPU handle (itjl_model), cached per context --------------------------------
+    def gpu_model(self, ctx=None):
+        ctx = ctx or _lib.default_context()
+        key = id(ctx)
+        if key not in self._gpu:
+            self._gpu[key] = GpuModel(self, ctx)
+        return self._gpu[key]
+
+
+class GpuModel:
+    """Owns an itjl_model (device copies of the model constants)."""
+
+    def __init__(self, model, ctx):
+        import ctypes
+        self.ctx = ctx
+        self.model = model
+        d = _lib.ModelDesc()
+        d.kind = _lib.KIND_OU_OSC if model.kind == "one_timescale_and_osc" else _lib.KIND_OU
+        if model.summary_method == "psd":
+            d.summary = _lib.SUMMARY_PSD
+        elif model.kind == "one_timescale_with_missing":
+            d.summary = _lib.SUMMARY_ACF_MISSING
+        else:
+            d.summary = _lib.SUMMARY_ACF
+        d.distance = _lib.DIST_LINEAR if model.distance_method == "linear" else _lib.DIST_LOG
+        d.update = _lib.UPDATE_EXACT if model.update == "exact" else _lib.UPDATE_EM
+        d.n_trials = int(model.numTrials)
+        d.n_t = int(model.n_t)
+        d.dt = float(model.dt)
+        d.data_mean = float(model.data_mean)
+        d.data_sd = float(model.data_sd)
+        self._target = np.ascontiguousarray(model.data_sum_stats, dtype=np.float64)
+        d.n_stats = self._target.shape[0]
+        d.target_stats = self._target.ctypes.data
+        self._mask = self._bins = None
+        if model.missing_mask is not None:
+            self._mask = np.asfortranarray(np.asarray(model.missing_mask).astype(np.uint8))
+            d.missing_mask = self._mask.ctypes.data
+        if model.summary_method == "psd":
+            self._bins = np.ascontiguousarray(np.nonzero(model.freq_idx)[0], dtype=np.int32)
+            d.freq_bins = self._bins.ctypes.data
+        self.n_stats = int(d.n_stats)
+        self._h = ctypes.c_void_p()
+        ctx.check(_lib.lib().itjl_model_create(ctx.handle, ctypes.byref(d), ctypes.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def work(self):
+        """(algorithmic flops per OU sample, samples per particle)."""
+        import ctypes
+        f = ctypes.c_double(0.0)
+        s = ctypes.c_int64(0)
+        self.ctx.check(_lib.lib().itjl_model_work(self._h, ctypes.byref(f), ctypes.byref(s)))
+        return f.value, s.value
+
+    def distances(self, theta, seed=0, generation=0, particle_offset=0, u0=None, noise=None,
+                  phases=None, return_stats=False):
+        """d[i] = generate_data_and_reduce(model, theta[i, :]) for a batch."""
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        n, p = theta.shape
+        th = np.asfortranarray(theta)
+        out = np.empty(n, dtype=np.float64)
+        stats = np.empty((n, self.n_stats), dtype=np.float64) if return_stats else None
+        cast = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        u0, noise, phases = cast(u0), cast(noise), cast(phases)
+        self.ctx.check(_lib.lib().itjl_abc_distances(
+            self._h, _lib.ptr(th), n, p, int(seed), int(generation), int(particle_offset),
+            _lib.ptr(u0), _lib.ptr(noise), _lib.ptr(phases), _lib.ptr(out), _lib.ptr(stats)))
+        return (out, stats) if return_stats else out
+
+    def generation(self, theta, epsilon, min_accepted, seed=0, generation=0, particle_offset=0):
+        """Distances + accept mask + sequential stop for a batch (abc.jl:181-199)."""
+        import ctypes
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        n, p = theta.shape
+        th = np.asfortranarray(theta)
+        dist = np.empty(n, dtype=np.float64)
+        isacc = np.empty(n, dtype=np.uint8)
+        n_total = ctypes.c_int64(0)
+        n_acc = ctypes.c_int64(0)
+        self.ctx.check(_lib.lib().itjl_abc_generation(
+            self._h, _lib.ptr(th), n, p, int(seed), int(generation), int(particle_offset),
+            float(epsilon), int(min_accepted), _lib.ptr(dist), _lib.ptr(isacc),
+            ctypes.byref(n_total), ctypes.byref(n_acc)))
+        return dist, isacc.astype(bool), int(n_total.value), int(n_acc.value)
+
+    def distances_dev(self, theta_dev_ptr, n_particles, n_theta, dist_dev_ptr, seed=0, generation=0,
+                      particle_offset=0):
+        """Device-pointer variant (asynchronous on the context stream)."""
+        import ctypes
+        self.ctx.check(_lib.lib().itjl_abc_distances_dev(
+            self._h, ctypes.c_void_p(theta_dev_ptr), int(n_particles), int(n_theta), int(seed),
+            int(generation), int(particle_offset), ctypes.c_void_p(dist_dev_ptr)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().itjl_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------- constructors ----
+def check_model_inputs(data, time, fit_method, summary_method, prior, distance_method):
+    """src/core/model.jl:239-292."""
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        data = data.reshape(1, -1)
+    time = np.asarray(time, dtype=np.float64)
+    if prior is not None and not isinstance(prior, (list, tuple)) and prior != "informed_prior":
+        prior = [prior]
+    if time.shape[0] != data.shape[-1]:
+        raise ValueError("Time vector length must match data length")
+    if np.any(np.diff(time) < 0):
+        raise ValueError("Time vector must be monotonically increasing")
+    if fit_method not in ("abc", "advi", "acw"):
+        raise ValueError("fit_method must be :abc, :advi, or :acw")
+    if fit_method == "advi":
+        raise NotImplementedError("ADVI is outside the B200 hot path (SURVEY.md section 2)")
+    if summary_method not in ("acf", "psd"):
+        raise ValueError("summary_method must be :acf or :psd")
+    if distance_method is not None and distance_method not in ("linear", "logarithmic"):
+        raise ValueError("distance_method must be :linear or :logarithmic")
+    return data, time, (None if prior in (None, "informed_prior") else list(prior))
+
+
+def _acf_branch(acf_mean, n, dt, n_lags, prior):
+    """one_timescale.jl:151-165."""
+    if n_lags is None:
+        a0 = utils.acw0(np.arange(n, dtype=np.float64), acf_mean)
+        if math.isnan(a0):
+            raise ValueError("InexactError: Int64(NaN) (the data ACF never crosses zero)")
+        n_lags = int(math.floor(a0 * 1.1))
+    lags = (np.arange(n, dtype=np.float64) * dt)[:n_lags]
+    stats = np.ascontiguousarray(acf_mean[:n_lags])
+    if prior is None:
+        prior = [Normal(utils.fit_expdecay(lags, stats), 20.0)]          # informed_prior, :20-23
+    return n_lags, lags, stats, prior
+
+
+def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prior=None,
+                        n_lags=None, distance_method=None, distance_combined=False,
+                        update="exact"):
+    if distance_combined:
+        raise NotImplementedError("distance_combined is outside the B200 hot path")
+    data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
+    if summary_method != "acf":
+        raise NotImplementedError("summary_method=:psd of one_timescale_model (DSP periodogram) "
+                                  "is a 'next' row (SURVEY.md 8f.1)")
+    dt = float(time[1] - time[0]); T = float(time[-1])
+    acf_mean = summary.comp_ac_fft(data).mean(axis=0)
+    n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
+    return TimescaleModel("one_timescale", data, time, fit_method, "acf", lags, prior,
+                          distance_method or "linear", stats, dt, T, data.shape[0],
+                          float(data.mean()), float(data.std(ddof=1)), n_lags=n_lags, update=update)
+
+
+def one_timescale_with_missing_model(data, time, fit_method="abc", summary_method="acf", prior=None,
+                                     n_lags=None, distance_method=None, distance_combined=False,
+                                     update="exact"):
+    if distance_combined:
+        raise NotImplementedError("distance_combined is outside the B200 hot path")
+    data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
+    if summary_method != "acf":
+        raise NotImplementedError("the Lomb-Scargle PSD branch is outside the B200 hot path")
+    dt = float(time[1] - time[0]); T = float(time[-1])
+    mask = np.isnan(data)
+    acf_mean = summary.comp_ac_time_missing(data).mean(axis=0)
+    n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
+    return TimescaleModel("one_timescale_with_missing", data, time, fit_method, "acf", lags, prior,
+                          distance_method or "linear", stats, dt, T, data.shape[0],
+                          float(np.nanmean(data)), float(np.nanstd(data, ddof=1)), n_lags=n_lags,
+                          missing_mask=mask, update=update)
+
+
+def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="psd", prior=None,
+                                n_lags=None, distance_method=None, freqlims=None,
+                                distance_combined=False, update="exact"):
+    if distance_combined:
+        raise NotImplementedError("distance_combined is outside the B200 hot path")
+    data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
+    if prior is None:
+        raise NotImplementedError("the informed prior of the oscillation model needs the Lorentzian "
+                                  "knee fit (outside the B200 hot path): pass prior=[...] explicitly")
+    dt = float(time[1] - time[0]); T = float(time[-1])
+    mean, sd = float(data.mean()), float(data.std(ddof=1))
+    if summary_method == "acf":
+        acf_mean = summary.comp_ac_fft(data).mean(axis=0)
+        n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
+        return TimescaleModel("one_timescale_and_osc", data, time, fit_method, "acf", lags, prior,
+                              distance_method or "linear", stats, dt, T, data.shape[0], mean, sd,
+                              n_lags=n_lags, update=update)
+    psd, freqs = summary.comp_psd_adfriendly(data, 1.0 / dt)
+    mean_psd = psd.mean(axis=0)
+    if freqlims is None:
+        freqlims = (0.5, 100.0)
+    freq_idx = (freqs < freqlims[1]) & (freqs > freqlims[0])
+    return TimescaleModel("one_timescale_and_osc", data, time, fit_method, "psd", freqs[freq_idx], prior,
+                          distance_method or "logarithmic", np.ascontiguousarray(mean_psd[freq_idx]),
+                          dt, T, data.shape[0], mean, sd, freqlims=freqlims, freq_idx=freq_idx,
+                          update=update)
+
+
+# ---------------------------------------------------------------- protocol ----
+def draw_theta(model, rng):
+    """src/core/model.jl:154-156."""
+    return np.array([p.rand(rng) for p in model.prior], dtype=np.float64)
+
+
+def generate_data(model, theta, seed=0, ctx=None):
+    """generate_data(model, theta): one synthetic data set, (numTrials, n_t)."""
+    from . import ou
+    if model.kind == "one_timescale_and_osc":
+        return ou.generate_ou_with_oscillation(theta, model.dt, model.T, model.numTrials,
+                                               model.data_mean, model.data_sd, seed=seed,
+                                               update=model.update, ctx=ctx)
+    data = ou.generate_ou_process(theta[0], model.data_sd, model.dt, model.T, model.numTrials,
+                                  seed=seed, update=model.update, ctx=ctx)
+    if model.kind == "one_timescale_with_missing":
+        data[model.missing_mask] = np.nan
+    return data
+
+
+def summary_stats(model, data, ctx=None):
+    if model.summary_method == "acf":
+        if model.kind == "one_timescale_with_missing":
+            return summary.comp_ac_time_missing(data, model.n_lags, ctx=ctx).mean(axis=0)
+        return summary.comp_ac_fft(data, model.n_lags, ctx=ctx).mean(axis=0)
+    psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt, ctx=ctx)
+    return psd.mean(axis=0)[model.freq_idx]
+
+
+def distance_function(model, sum_stats, data_sum_stats):
+    """linear_distance / logarithmic_distance (src/stats/distances.jl:29-53) on host vectors
+    (O(n_stats); the batched path computes them inside the fused kernel)."""
+    a = np.asarray(sum_stats, dtype=np.float64)
+    b = np.asarray(data_sum_stats, dtype=np.float64)
+    if model.distance_method == "linear":
+        return float(np.mean((a - b) ** 2))
+    if model.distance_method == "logarithmic":
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return float(np.mean((np.log(a) - np.log(b)) ** 2))
+    raise ValueError("Distance method must be :linear or :logarithmic")
+
+
+def generate_data_and_reduce(model, theta, seed=0, generation=0, particle=0, ctx=None):
+    """src/core/model.jl:146-151 for ONE particle (a batch-of-one fused kernel launch)."""
+    return float(model.gpu_model(ctx).distances(np.asarray(theta, dtype=np.float64).reshape(1, -1),
+                                                seed=seed, generation=generation,
+                                                particle_offset=particle)[0])

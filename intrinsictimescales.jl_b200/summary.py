@@ -1,0 +1,69 @@
+"""Summary statistics on stored data, computed on the GPU through the C ABI.
+
+Mirrors the reference functions (same names and argument meaning):
+  comp_ac_fft           src/stats/summary.jl:46-63, 79-89
+  comp_ac_time_missing  src/stats/summary.jl:455-496
+  comp_psd_adfriendly   src/stats/summary.jl:183-235
+Arrays are (trials, time) with `dims` = last, the reference default; a Fortran-ordered
+(column-major) array is passed through without a copy, exactly as a Julia Matrix would be.
+"""
+import numpy as np
+
+from . import _lib
+
+
+def _as_slices(data):
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        data = data.reshape(1, -1)
+    if data.ndim != 2:
+        raise ValueError("data must be a vector or a (trials, time) matrix")
+    return np.asfortranarray(data)
+
+
+def comp_ac_fft(data, n_lags=None, ctx=None):
+    """Autocorrelation of each trial (rows), lags 0..n_lags-1; returns (trials, n_lags)
+    (a vector input returns a vector, as the reference's Vector method does)."""
+    vec = np.ndim(data) == 1
+    d = _as_slices(data)
+    ctx = ctx or _lib.default_context()
+    n_slices, n_t = d.shape
+    n_lags = n_t if n_lags is None else int(n_lags)
+    out = np.empty((n_slices, n_lags), dtype=np.float64, order="F")
+    ctx.check(_lib.lib().itjl_acf(ctx.handle, _lib.ptr(d), n_slices, n_t, n_lags, _lib.ptr(out)))
+    return out[0].copy() if vec else out
+
+
+def comp_ac_time_missing(data, n_lags=None, ctx=None):
+    """NaN-aware autocorrelation (NaN = missing sample)."""
+    vec = np.ndim(data) == 1
+    d = _as_slices(data)
+    ctx = ctx or _lib.default_context()
+    n_slices, n_t = d.shape
+    n_lags = n_t if n_lags is None else int(n_lags)
+    out = np.empty((n_slices, n_lags), dtype=np.float64, order="F")
+    ctx.check(_lib.lib().itjl_acf_missing(ctx.handle, _lib.ptr(d), n_slices, n_t, n_lags, _lib.ptr(out)))
+    return out[0].copy() if vec else out
+
+
+def _ac_next_pow_two(i):
+    """src/stats/bat_autocor.jl:21-24."""
+    p = 1
+    while p < i:
+        p <<= 1
+    return p
+
+
+def comp_psd_adfriendly(data, fs, ctx=None):
+    """Hamming-windowed, zero-padded periodogram; returns (power, freqs) with the DC bin
+    dropped: power is (trials, n2/2 - 1), n2 = 2 * nextpow2(n)."""
+    vec = np.ndim(data) == 1
+    d = _as_slices(data)
+    ctx = ctx or _lib.default_context()
+    n_slices, n_t = d.shape
+    n2 = 2 * _ac_next_pow_two(n_t)
+    nb = n2 // 2 - 1
+    out = np.empty((n_slices, nb), dtype=np.float64, order="F")
+    ctx.check(_lib.lib().itjl_psd_hamming(ctx.handle, _lib.ptr(d), n_slices, n_t, float(fs), _lib.ptr(out)))
+    freqs = np.arange(1, n2 // 2, dtype=np.float64) * (float(fs) / n2)     # fftfreq(n2, fs)[2:n2/2]
+    return (out[0].copy() if vec else out), freqs

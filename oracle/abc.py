@@ -50,16 +50,32 @@ def draw_theta_pmc(rng, theta_prev, weights, tau_squared, jitter=1e-5):
 
 
 def basic_abc(distance_fn, draw_fn, n_theta, epsilon, max_iter, min_accepted,
-              generation=0, proposals=None):
+              generation=0, proposals=None, distance_batch_fn=None, lookahead=64):
     """abc.jl:156-215.  `draw_fn()` -> theta (prior or PMC proposal); if
-    `proposals` (max_iter, n_theta) is given they are consumed in order instead."""
+    `proposals` (max_iter, n_theta) is given they are consumed in order instead.
+    `distance_batch_fn(thetas, first_index, generation)` (optional) scores `lookahead`
+    proposals at a time - proposals are i.i.d., so drawing a few ahead of the serial loop and
+    discarding the unused tail leaves every returned quantity distributed as in the
+    reference; it only lets the C restatement use all host cores."""
     samples = np.zeros((max_iter, n_theta))
     dist = np.zeros(max_iter)
     accepted = 0
     it = 0
+    ahead_theta = ahead_d = None
+    ahead_base = 0
     for i in range(max_iter):
-        theta = proposals[i] if proposals is not None else draw_fn()
-        d = distance_fn(theta, i, generation)
+        if distance_batch_fn is not None:
+            if ahead_theta is None or i - ahead_base >= ahead_theta.shape[0]:
+                nb = min(lookahead, max_iter - i)
+                ahead_theta = (np.asarray(proposals[i:i + nb]) if proposals is not None
+                               else np.stack([draw_fn() for _ in range(nb)]))
+                ahead_d = distance_batch_fn(ahead_theta, i, generation)
+                ahead_base = i
+            theta = ahead_theta[i - ahead_base]
+            d = ahead_d[i - ahead_base]
+        else:
+            theta = proposals[i] if proposals is not None else draw_fn()
+            d = distance_fn(theta, i, generation)
         samples[i] = theta
         dist[i] = d
         it += 1
@@ -183,7 +199,7 @@ def effective_sample_size(w):
     return float(w.sum() ** 2 / np.sum(w ** 2))
 
 
-def pmc_abc(model_prior, distance_fn, rng, n_theta=None, epsilon_0=1.0, max_iter=10000,
+def pmc_abc(model_prior, distance_fn, rng, n_theta=None, distance_batch_fn=None, epsilon_0=1.0, max_iter=10000,
             min_accepted=100, steps=10, sample_only=False, minAccRate=0.01,
             target_acc_rate=0.01, target_epsilon=5e-3, jitter=1e-6, distance_max=10.0,
             quantile_lower=25.0, quantile_upper=75.0, quantile_init=50.0,
@@ -206,7 +222,7 @@ def pmc_abc(model_prior, distance_fn, rng, n_theta=None, epsilon_0=1.0, max_iter
         if i_step == 1:
             draw = lambda: np.array([p.rand(rng) for p in prior])
             res = basic_abc(distance_fn, draw, ndim, epsilon, max_iter, min_accepted,
-                            generation=i_step)
+                            generation=i_step, distance_batch_fn=distance_batch_fn)
             epsilon = select_epsilon(res["distances"], epsilon, **eps_kw)
             theta = res["theta_accepted"]
             tau_squared = 2.0 * np.atleast_2d(np.cov(theta, rowvar=False))
@@ -218,7 +234,7 @@ def pmc_abc(model_prior, distance_fn, rng, n_theta=None, epsilon_0=1.0, max_iter
             draw = lambda: draw_theta_pmc(rng, prev["theta_accepted"], prev["weights"],
                                           prev["tau_squared"])
             res = basic_abc(distance_fn, draw, ndim, epsilon, max_iter, min_accepted,
-                            generation=i_step)
+                            generation=i_step, distance_batch_fn=distance_batch_fn)
             theta = res["theta_accepted"]
             eff = effective_sample_size(prev["weights"])
             if sample_only:

@@ -40,7 +40,7 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
-static inline double u01(uint32_t r) { return ((double)(r >> 8) + 0.5) * (1.0 / 16777216.0); }
+static inline double u01(uint32_t r) { return ((double)(r >> 9) + 0.5) * (1.0 / 8388608.0); }
 static inline void box_muller(uint32_t ra, uint32_t rb, double* z0, double* z1) {
     double rad = sqrt(-2.0 * log(u01(ra)));
     double ang = 2.0 * PI * u01(rb);

@@ -35,8 +35,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()                      # make is a no-op when the .so is up to date
         _lib = ctypes.CDLL(_SO)
         _lib.itjl_oracle_abc_distances.restype = ctypes.c_int
         _lib.itjl_oracle_max_threads.restype = ctypes.c_int

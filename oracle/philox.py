@@ -54,9 +54,9 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def u01(r):
-    """uint32 -> open-interval uniform with 24 significant bits:
-    ((r >> 8) + 0.5) * 2^-24  (exactly representable in fp32)."""
-    return ((np.asarray(r, dtype=np.uint32) >> np.uint32(8)).astype(np.float64) + 0.5) * (2.0 ** -24)
+    """uint32 -> open-interval uniform ((r >> 9) + 0.5) * 2^-23: 24 significant bits,
+    exactly representable in fp32, never 0 or 1."""
+    return ((np.asarray(r, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) + 0.5) * (2.0 ** -23)
 
 
 def box_muller(ra, rb):

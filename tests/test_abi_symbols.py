@@ -1,0 +1,53 @@
+"""The C-ABI library must load on a CPU-only box and export every symbol that
+include/itjl_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "itjl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(itjl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ["itjl_ctx_create", "itjl_model_create", "itjl_abc_distances", "itjl_abc_generation",
+                 "itjl_abc_accept", "itjl_generate_ou", "itjl_generate_ou_osc", "itjl_acf",
+                 "itjl_acf_missing", "itjl_psd_hamming", "itjl_acw", "itjl_fit_expdecay",
+                 "itjl_last_error", "itjl_fp32_peak"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    path = pkg.library_path()
+    assert os.path.exists(path), "libitjl_b200.so not built (python __graft_entry__.py)"
+    lib = ctypes.CDLL(path)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/itjl_b200.h but not exported"
+    assert set(declared_symbols()) == set(pkg._lib.SIGNATURES), "ctypes table out of sync with the header"
+    assert b"sm_100a" in pkg._lib.lib().itjl_version()
+
+
+def test_no_device_is_a_loud_error_not_a_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.ItjlError) as e:
+        pkg.Context(0)
+    assert e.value.code == -3
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "intrinsictimescales.jl_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "itjl_oracle" not in src, f

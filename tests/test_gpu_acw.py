@@ -1,0 +1,108 @@
+"""GPU parity: acw() (ACW-0 / ACW-50 / ACW-e indices bit-exact, AUC, tau, ACF) vs the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import acw as oacw
+from oracle import ou as oou
+
+pytestmark = pytest.mark.gpu
+
+TYPES = ["acw0", "acw50", "acweuler", "auc", "tau"]
+
+
+def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=False):
+    want = oacw.acw(data, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average)
+    got = pkg.acw(data, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average, ctx=ctx)
+    res = dict(zip(types, got.acw_results if len(types) > 1 else [got.acw_results]))
+    assert got.n_lags == want["n_lags"]
+    dt = 1.0 / fs
+    for name, key in [("acw0", "k0"), ("acw50", "k50"), ("acweuler", "ke")]:
+        if name in types:
+            w = np.where(want[key] >= 0, want[key] * dt, np.nan)
+            assert np.array_equal(np.atleast_1d(res[name]), w, equal_nan=True), name   # bit-exact
+    if "auc" in types:
+        assert np.allclose(np.atleast_1d(res["auc"]), want["auc"], rtol=1e-11, atol=1e-14)
+    if "tau" in types:
+        assert np.allclose(np.atleast_1d(res["tau"]), want["tau"], rtol=1e-7, atol=0)
+    assert got.acf.shape == want["acf"].shape or got.acf.shape == want["acf"][0].shape
+    assert np.max(np.abs(np.atleast_2d(got.acf) - want["acf"])) < 1e-12
+    assert np.array_equal(got.lags, want["lags"])
+    return got, want
+
+
+def _data_with_k0_first_ge_2(make, seeds=range(100)):
+    for s in seeds:
+        d = make(s)
+        k0 = oacw.acw(d[:1], 1.0, acwtypes=["acw0"])["k0"][0]
+        if k0 >= 2:
+            return d
+    raise RuntimeError("no seed found")
+
+
+def test_acw_on_white_noise(pkg, ctx):
+    d = _data_with_k0_first_ge_2(lambda s: np.random.default_rng(s).standard_normal((400, 5000)))
+    got, want = check_against_oracle(pkg, ctx, d, 100.0)
+    assert want["n_lags"] < 40                                # short-memory regime (HBM-bound)
+
+
+def test_acw_on_ou_data(pkg, ctx):
+    fs = 100.0
+    d = oou.generate_ou_process(0.5, 1.0, 1 / fs, 50.0, 64, seed=3)
+    got, want = check_against_oracle(pkg, ctx, d, fs)
+    assert want["n_lags"] > 60                                # long-memory regime
+    res = dict(zip(TYPES, got.acw_results))
+    # reference's own sanity checks (test_acw.jl:128-143, 285-345)
+    assert np.nanmean(res["acw50"]) == pytest.approx(0.5 * math.log(2), rel=0.5)
+    assert np.mean(res["tau"]) == pytest.approx(0.5, rel=0.5)
+    assert np.all(res["auc"] > 0) and np.all(res["auc"] < 50.0)
+
+
+def test_acw_with_nans_user_lags_vector_and_average(pkg, ctx):
+    fs = 100.0
+    d = oou.generate_ou_process(0.3, 1.0, 1 / fs, 30.0, 20, seed=4)
+    dn = d.copy()
+    rng = np.random.default_rng(0)
+    for r in range(20):
+        s = rng.integers(0, 2500)
+        dn[r, s:s + 200] = np.nan
+    check_against_oracle(pkg, ctx, dn, fs)
+    check_against_oracle(pkg, ctx, dn, fs, n_lags=150)
+    check_against_oracle(pkg, ctx, d, fs, n_lags=25, types=["acw0", "acw50", "acweuler", "tau"])  # crossings beyond n_lags
+    check_against_oracle(pkg, ctx, d, fs, average=True)
+    check_against_oracle(pkg, ctx, d[0], fs)                     # vector input
+    one = pkg.acw(d, fs, acwtypes="acw50", ctx=ctx)
+    assert one.acwtypes == "acw50" and np.asarray(one.acw_results).shape == (20,)
+
+
+def test_acw_edge_cases(pkg, ctx):
+    # never crosses zero -> NaN + n_lags = n (acw.jl:203-207); AUC then throws like the reference
+    t = np.arange(600, dtype=np.float64)
+    d = np.stack([1.0 + 0.001 * np.sin(0.01 * t), 5.0 + np.cos(0.02 * t)])
+    want = oacw.acw(d, 10.0, acwtypes=["acw0", "acw50"])
+    got = pkg.acw(d, 10.0, acwtypes=["acw0", "acw50"], ctx=ctx)
+    assert np.array_equal(got.acw_results[0], np.where(want["k0"] >= 0, want["k0"] / 10.0, np.nan), equal_nan=True)
+    assert got.n_lags == want["n_lags"]
+    with pytest.raises(ValueError):
+        pkg.acw(np.random.default_rng(1).standard_normal((3, 50)) * 0 + np.arange(50.0), 1.0, acwtypes=["auc"], ctx=ctx)
+    with pytest.raises(pkg.ItjlError):
+        pkg.acw(d, -1.0, ctx=ctx)
+
+
+def test_acw_full_size_c2(pkg, ctx):
+    """BASELINE config C2: randn(10000 x 5000), fs = 100, all ACF-based acwtypes.  The oracle
+    checks a subset of trials; the rest through size-independent properties."""
+    rng = np.random.default_rng(0)
+    d = np.asfortranarray(rng.standard_normal((10000, 5000)))
+    got = pkg.acw(d, 100.0, acwtypes=["acw0", "acw50", "acweuler", "tau"], ctx=ctx)
+    r = dict(zip(["acw0", "acw50", "acweuler", "tau"], got.acw_results))
+    idx = np.arange(0, 10000, 97)
+    want = oacw.acw(d[idx], 100.0, acwtypes=["acw0", "acw50", "acweuler"], n_lags=got.n_lags)
+    for name, key in [("acw0", "k0"), ("acw50", "k50"), ("acweuler", "ke")]:
+        assert np.array_equal(r[name][idx], want[key] / 100.0)
+    assert np.max(np.abs(got.acf[idx] - want["acf"])) < 1e-12
+    assert np.all(got.acf[:, 0] == 1.0)
+    assert np.all(r["acw50"] == 0.01) and np.all(r["acweuler"] == 0.01)     # white noise: lag 1
+    assert np.all(r["acw0"] >= 0.01) and got.n_lags == math.ceil(1.1 * round(r["acw0"].max() * 100))
+    assert np.all(r["acw0"] >= r["acweuler"]) and np.all(r["acweuler"] >= r["acw50"])

