@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_acf_slices(const AcfSliceParams
         for (int k = tid; k < lb; k += kThreads) {
             double v = 0.0;
             for (int st = 0; st < n_streams; ++st) v += part[st * row + k];
-            v *= inv_ss;
             const int lag = kb + k;
+            // lag 0 is acov[0]/acov[0] in the reference: exactly 1 (NaN for a constant slice)
+            v = (lag == 0) ? (s_ss / s_ss) : v * inv_ss;
             P.acf_work[(size_t)s * P.cap + lag] = v;
             if (P.mode == 0) {
                 if (v <= 0.0) atomicMin(&s_first[0], lag);

@@ -171,10 +171,18 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
         cap = reach;
         ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
         ITJL_CUDA(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int32_t), ctx->stream));
+        if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
         e = acw_scan_launch((const double*)ctx->data.p, n_slices, nt, 1, reach, (double*)ctx->out.p, cap,
                             d_done, d_k0, d_k50, d_ke, d_nan, ctx->max_smem_optin, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(scan): %s", cudaGetErrorString(e));
         ctx->launches++;
+        if (ctx->timing) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            cudaEventSynchronize(ctx->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            ctx->timed_ms += ms; ctx->timed_launches++;
+        }
         ITJL_CUDA(ctx, cudaMemcpyAsync(h_k0.data(), d_k0, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
         ITJL_CUDA(ctx, cudaMemcpyAsync(h_k50.data(), d_k50, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
         ITJL_CUDA(ctx, cudaMemcpyAsync(h_ke.data(), d_ke, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -84,8 +84,11 @@ def test_acw_edge_cases(pkg, ctx):
     got = pkg.acw(d, 10.0, acwtypes=["acw0", "acw50"], ctx=ctx)
     assert np.array_equal(got.acw_results[0], np.where(want["k0"] >= 0, want["k0"] / 10.0, np.nan), equal_nan=True)
     assert got.n_lags == want["n_lags"]
+    alt = np.tile(np.array([1.0, -1.0]), 25)                    # first slice crosses zero at lag 1
+    with pytest.raises(ValueError):                              # -> 1-point Romberg window: reference throws
+        pkg.acw(np.stack([alt, np.arange(50.0)]), 1.0, acwtypes=["auc"], ctx=ctx)
     with pytest.raises(ValueError):
-        pkg.acw(np.random.default_rng(1).standard_normal((3, 50)) * 0 + np.arange(50.0), 1.0, acwtypes=["auc"], ctx=ctx)
+        oacw.acw(np.stack([alt, np.arange(50.0)]), 1.0, acwtypes=["auc"])
     with pytest.raises(pkg.ItjlError):
         pkg.acw(d, -1.0, ctx=ctx)
 

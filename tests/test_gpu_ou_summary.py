@@ -47,7 +47,7 @@ def test_generate_ou_nan_contract_and_args(pkg, ctx):
     bad = pkg.generate_ou_process(-1e-4, 1.0, 0.002, 4.0, 2, seed=1, ctx=ctx)   # a = exp(+20) per step
     assert np.isnan(bad).all()
     with pytest.raises(pkg.ItjlError):
-        pkg.generate_ou_process(0.3, 1.0, -0.002, 4.0, 2, ctx=ctx)
+        pkg.generate_ou_process(0.3, 1.0, 0.002, 0.004, 2, ctx=ctx)      # n_t = 2 < 4
 
 
 @pytest.mark.parametrize("coeff", [0.95, 0.3, 1.4, -0.2])
