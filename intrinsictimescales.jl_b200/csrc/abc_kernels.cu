@@ -19,60 +19,22 @@
 // x'[t0+k0 ..], and issues 400 FFMAs for 10 LDS.128.  The window is 2*TT wide so the slide
 // is a two-phase register renaming (no moves).  Lane stride of 20 floats = 5 x 16 B makes
 // the b loads bank-conflict free.
+#include <stdlib.h>
+
 #include "kernels.h"
+#include "lagsum.cuh"
 #include "simulate.cuh"
 
 namespace itjl {
 
-constexpr int TK = 20;   // lags per thread
-constexpr int TT = 20;   // samples per time tile
-
-
-__device__ __forceinline__ void load5(const float4* __restrict__ p, float* dst) {
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const float4 v = p[q];
-        dst[4 * q + 0] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
-    }
-}
-
-// acc[j] += sum over tiles [tile_begin, tile_end) of sum_i x[t0+i] * x[t0+i+k0+j]
-__device__ __forceinline__ void acf_tiles(const float* __restrict__ xs, float (&acc)[TK], int k0,
-                                          int tile_begin, int tile_end) {
-    float b[2 * TT];
-    float a[TT];
-    const float4* pa = reinterpret_cast<const float4*>(xs + tile_begin * TT);
-    const float4* pb = reinterpret_cast<const float4*>(xs + tile_begin * TT + k0);
-    load5(pb, b);
-    pb += 5;
-    int n = tile_end - tile_begin;
-    while (n > 0) {
-        // phase 0: window = b[0..39]
-        load5(pb, b + TT); pb += 5;
-        load5(pa, a); pa += 5;
-#pragma unroll
-        for (int i = 0; i < TT; ++i)
-#pragma unroll
-            for (int j = 0; j < TK; ++j) acc[j] = fmaf(a[i], b[i + j], acc[j]);
-        if (--n == 0) break;
-        // phase 1: window = b[20..39], b[0..19]
-        load5(pb, b); pb += 5;
-        load5(pa, a); pa += 5;
-#pragma unroll
-        for (int i = 0; i < TT; ++i)
-#pragma unroll
-            for (int j = 0; j < TK; ++j) acc[j] = fmaf(a[i], b[(TT + i + j) % (2 * TT)], acc[j]);
-        --n;
-    }
-}
-
-template <bool MISSING, bool OSC>
-__global__ void __launch_bounds__(kThreads, 2) k_abc_acf(const AbcAcfParams P) {
+template <int NT, bool MISSING, bool OSC>
+__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const AbcAcfParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int buf_floats = P.xs_stride;
     float* xs0 = reinterpret_cast<float*>(smem_raw);
-    float* xs1 = xs0 + P.xs_stride;
-    SimShared* sh = reinterpret_cast<SimShared*>(xs1 + P.xs_stride);
-    __shared__ double red[kWarps];
+    float* xs1 = (P.n_bufs == 2) ? xs0 + buf_floats : xs0;
+    SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(xs0 + P.n_bufs * buf_floats);
+    __shared__ double red[NT / 32];
 
     const int tid = threadIdx.x;
     const int64_t particle = blockIdx.x;
@@ -88,6 +50,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_abc_acf(const AbcAcfParams P) {
 
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
+    g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
     g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
     g.particle = (uint32_t)(P.particle_offset + particle);
     const size_t pt = (size_t)particle * P.n_trials;
@@ -96,8 +59,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_abc_acf(const AbcAcfParams P) {
     g.phases = P.phases ? P.phases + pt : nullptr;
     g.mask_bits = P.mask_bits; g.n_valid = P.n_valid; g.mask_words = P.mask_words;
 
-    // zero the tail pads once: everything at or beyond chunk*kThreads stays zero
-    for (int i = P.chunk * kThreads + tid; i < P.xs_stride; i += kThreads) { xs0[i] = 0.f; xs1[i] = 0.f; }
+    // zero everything once: the pads at or beyond chunk*NT (and the shifted copies' ends) stay zero
+    for (int i = tid; i < P.n_bufs * buf_floats; i += NT) xs0[i] = 0.f;
+    __syncthreads();
 
     // lag-sum work assignment
     const int tile = tid % P.lt;
@@ -110,12 +74,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_abc_acf(const AbcAcfParams P) {
     float acc[TK];
 #pragma unroll
     for (int j = 0; j < TK; ++j) acc[j] = 0.f;
+    SimCache sim_cache;
 
     for (int trial = 0; trial < P.n_trials; ++trial) {
         float* xs = (trial & 1) ? xs1 : xs0;
-        simulate_trial<MISSING, OSC>(g, oc, trial, xs, sh, kScaleUnitNorm, 1.0f, 0.0f);
+        if (!(P.debug & 1) || trial < 2)                      // debug bit 0: time the lag sum alone
+            simulate_trial<NT, MISSING, OSC>(g, oc, trial, xs, sh, kScaleUnitNorm, 1.0f, 0.0f, sim_cache);
         __syncthreads();
+        if (P.debug & 2) continue;                            // debug bit 1: time the simulator alone
         if (active && tile_begin < tile_end) acf_tiles(xs, acc, k0, tile_begin, tile_end);
+        if (P.n_bufs == 1) __syncthreads();              // single buffer: lag sum done before it is rewritten
     }
 
     // ---- epilogue: reduce over time streams, trial mean, distance -----------------------
@@ -129,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_abc_acf(const AbcAcfParams P) {
     __syncthreads();
     const double inv_trials = 1.0 / (double)P.n_trials;
     double local = 0.0;
-    for (int k = tid; k < P.n_lags; k += kThreads) {
+    for (int k = tid; k < P.n_lags; k += NT) {
         float s = 0.f;
         for (int st = 0; st < P.n_streams; ++st) s += part[st * row + k];
         const double v = (double)s * inv_trials;
@@ -144,15 +112,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_abc_acf(const AbcAcfParams P) {
     if (tid == 0) {
         double d = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) d += red[w];
+        for (int w = 0; w < NT / 32; ++w) d += red[w];
         P.dist_out[particle] = d / (double)P.n_lags;
     }
 }
 
-template __global__ void k_abc_acf<false, false>(const AbcAcfParams);
-template __global__ void k_abc_acf<true, false>(const AbcAcfParams);
-template __global__ void k_abc_acf<false, true>(const AbcAcfParams);
-template __global__ void k_abc_acf<true, true>(const AbcAcfParams);
 
 // ---------------------------------------------------------------------------------------
 // K3: accept mask + sequential stopping rule (abc.jl:185-199) for one batch, single CTA.
@@ -194,36 +158,57 @@ __global__ void __launch_bounds__(1024) k_abc_accept(const double* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // host-side launch geometry
 
-int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g) {
+static int abc_acf_geometry_cfg(int n_t, int n_lags, int max_smem, int nt, int n_bufs, AbcAcfGeometry* g) {
     if (n_t < 2 || n_lags < 1 || n_lags > n_t) return -1;
+    g->threads = nt; g->n_bufs = n_bufs;
     g->lt = (n_lags + TK - 1) / TK;
-    if (g->lt > kThreads) return -2;
-    g->n_streams = kThreads / g->lt;
+    if (g->lt > nt) return -2;
+    g->n_streams = nt / g->lt;
     g->n_tiles = (n_t + TT - 1) / TT;
     if (g->n_streams > g->n_tiles) g->n_streams = g->n_tiles;
     g->tiles_per_stream = (g->n_tiles + g->n_streams - 1) / g->n_streams;
     g->n_streams = (g->n_tiles + g->tiles_per_stream - 1) / g->tiles_per_stream;
-    int c = (n_t + kThreads - 1) / kThreads;
+    int c = (n_t + nt - 1) / nt;
     g->chunk = (c + 3) & ~3;
     int need = (g->n_tiles + g->lt + 2) * TT;               // furthest window read
-    int stride = g->chunk * kThreads;
+    int stride = g->chunk * nt;
     if (stride < need) stride = need;
     int red = g->n_streams * g->lt * TK;                     // epilogue partials live in xs0
     if (stride < red) stride = red;
     g->xs_stride = (stride + 3) & ~3;
-    g->smem_bytes = (size_t)2 * g->xs_stride * sizeof(float) + sizeof(SimShared);
+    g->smem_bytes = (size_t)n_bufs * g->xs_stride * sizeof(float) + sizeof(SimShared<256>);
     if ((int64_t)g->smem_bytes > (int64_t)max_smem) return -3;
     return 0;
 }
 
-cudaError_t abc_acf_launch(const AbcAcfParams& P, bool missing, bool osc, size_t smem, cudaStream_t st) {
+// Default: 128-thread CTAs (up to 5 per SM: independent simulate / lag-sum phases interleave on
+// every SM sub-partition), one series buffer per CTA; 256 threads when there are more than 128
+// lag tiles.  ITJL_ABC_THREADS / ITJL_ABC_BUFS override for tuning.
+int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g) {
+    int nt = 128, n_bufs = 1;
+    if (const char* e = getenv("ITJL_ABC_THREADS")) nt = (atoi(e) == 256) ? 256 : 128;
+    if (const char* e = getenv("ITJL_ABC_BUFS")) n_bufs = (atoi(e) == 2) ? 2 : 1;
+    if ((n_lags + TK - 1) / TK > nt) nt = 256;
+    int rc = abc_acf_geometry_cfg(n_t, n_lags, max_smem, nt, n_bufs, g);
+    if (rc == -3 && n_bufs == 2) rc = abc_acf_geometry_cfg(n_t, n_lags, max_smem, nt, 1, g);
+    return rc;
+}
+
+template <int NT>
+static cudaError_t abc_acf_launch_nt(const AbcAcfParams& P, bool missing, bool osc, size_t smem, cudaStream_t st) {
     void (*kern)(const AbcAcfParams) =
-        missing ? (osc ? k_abc_acf<true, true> : k_abc_acf<true, false>)
-                : (osc ? k_abc_acf<false, true> : k_abc_acf<false, false>);
+        missing ? (osc ? k_abc_acf<NT, true, true> : k_abc_acf<NT, true, false>)
+                : (osc ? k_abc_acf<NT, false, true> : k_abc_acf<NT, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)P.n_particles, kThreads, smem, st>>>(P);
+    kern<<<(unsigned)P.n_particles, NT, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t abc_acf_launch(const AbcAcfParams& P, int threads, bool missing, bool osc, size_t smem,
+                           cudaStream_t st) {
+    return threads == 128 ? abc_acf_launch_nt<128>(P, missing, osc, smem, st)
+                          : abc_acf_launch_nt<256>(P, missing, osc, smem, st);
 }
 
 cudaError_t abc_accept_launch(const double* dist, int64_t n, double eps, int64_t min_accepted,

@@ -71,6 +71,7 @@ struct AcfSliceParams {
     int32_t* n_done;        // [slice] lags available in acf_work
     int32_t* k0; int32_t* k50; int32_t* ke;
     int32_t* nan_flag;      // set to 1 when any slice holds a NaN (may be null)
+    const int32_t* slice_list;  // optional: CTA b works on slice slice_list[b]
 };
 
 constexpr double kInvE = 0.36787944117144233;   // Julia: 1 / ℯ
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_acf_slices(const AcfSliceParams
     __shared__ double s_ss;
 
     const int tid = threadIdx.x;
-    const int64_t s = blockIdx.x;
+    const int64_t s = P.slice_list ? (int64_t)P.slice_list[blockIdx.x] : (int64_t)blockIdx.x;
     const int n_t = P.n_t;
 
     int start = 0, stop = P.max_lags;
@@ -352,6 +353,166 @@ __global__ void k_acw_tau(const double* __restrict__ acf, int64_t n_rows, int64_
     if (lane == 0) tau[row] = result;
 }
 
+// ---- streaming first pass (short-memory data: HBM-bound) -----------------------------------
+// One pass over the column-major input computes, for every slice, the RAW lagged products
+//   P_k = sum_t x_t x_{t-k}, k < SK = 32,   and S = sum x_t,
+// from which k_acw_finish derives the centred autocorrelation algebraically:
+//   C_k = P_k - m (2S - head_k - tail_k) + (n - k) m^2,  m = S / n,
+// head_k / tail_k = sums of the first / last k samples.  Everything is fp64.
+// Layout: a CTA streams SS = 64 adjacent slices (512 contiguous bytes per time step) of one
+// time segment through a 4-tile shared-memory ring with cp.async (tile = 32 time steps,
+// prefetch distance 2, one __syncthreads() per tile); thread = (slice, half of the lags):
+// 16 accumulators + a 16-deep circular register window, 16 DFMA per 2 LDS.64.
+// A NaN (missing sample) simply propagates into P_k; such slices, slices whose zero crossing
+// lies beyond SK lags, and slices whose mean is so large that the raw-moment form would cancel
+// (n m^2 > 1e6 C_0) are flagged and redone exactly by k_acf_slices.
+constexpr int SK = 32;     // lags of the streaming pass
+constexpr int SS = 64;     // slices per CTA
+constexpr int ST = 32;     // time steps per tile
+constexpr int SR = 128;    // ring rows = 4 tiles: halo, current, two in flight
+constexpr int SPART = SK + 1;   // per (segment, slice): P_0..P_31, S
+constexpr int STREAM_THREADS = 128;
+
+struct AcwStreamParams {
+    const double* data;
+    int64_t n_slices;
+    int n_t;
+    int n_seg, seg_len;          // time segments (seg_len multiple of ST)
+    double* part;                // [seg][slice][SPART]
+};
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStreamParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*ring)[SS] = reinterpret_cast<double (*)[SS]>(smem_raw);      // [SR][SS]
+    const int tid = threadIdx.x;
+    const int sl = tid & (SS - 1);
+    const int half = tid >> 6;                         // warp-uniform
+    const int64_t s0 = (int64_t)blockIdx.x * SS;
+    const int seg = blockIdx.y;
+    const int tb = seg * P.seg_len;
+    const int te = min(tb + P.seg_len, P.n_t);
+    const int n_tiles = (te - tb + ST - 1) / ST;
+
+    // ring tile q (q = 0 is the halo, time steps tb-32..tb-1; q >= 1 is data tile q-1) lives in
+    // rows [(q & 3) * ST, (q & 3) * ST + ST)
+    auto load_tile = [&](int q) {
+        const int t0 = tb + (q - 1) * ST;
+        double* base = &ring[(q & 3) * ST][0];
+        for (int i = tid; i < ST * SS; i += STREAM_THREADS) {
+            const int r = i / SS, c = i - r * SS;
+            const int t = t0 + r;
+            if (t >= 0 && t < P.n_t && s0 + c < P.n_slices) cp_async8(base + i, P.data + (s0 + c) + (size_t)t * P.n_slices);
+            else base[i] = 0.0;
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    load_tile(0);
+    load_tile(1);
+    if (n_tiles > 1) load_tile(2); else asm volatile("cp.async.commit_group;");
+    double acc[16], C[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { acc[j] = 0.0; C[j] = 0.0; }
+    double S = 0.0;
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        asm volatile("cp.async.wait_group 1;");        // halo + tiles <= `tile` have landed
+        __syncthreads();                               // ... for every thread; tile-2's rows are free
+        if (tile + 2 < n_tiles) load_tile(tile + 3); else asm volatile("cp.async.commit_group;");
+        const double* cur = &ring[((tile + 1) & 3) * ST][sl];        // rows of this tile
+        const double* prev = &ring[(tile & 3) * ST][sl];             // rows of the previous tile / halo
+        if (tile == 0) {
+            // circular window C[tau & 15] = x_tau, tau = t - 16 half: preload the 15 older samples
+#pragma unroll
+            for (int j = 1; j < 16; ++j) C[(16 - j) & 15] = prev[(ST - 16 * half - j) * SS];
+        }
+        const int valid_rows = min(ST, te - (tb + tile * ST));       // rows >= te belong to the next segment
+#pragma unroll
+        for (int blk = 0; blk < ST; blk += 16) {
+            const double* dly = half ? (blk ? cur + (blk - 16) * SS : prev + (ST - 16) * SS) : cur + blk * SS;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                double z = cur[(blk + i) * SS];
+                if (blk + i >= valid_rows) z = 0.0;
+                C[i] = half ? dly[i * SS] : z;          // tau & 15 == i (tb and ST are multiples of 16)
+                if (half == 0) S += z;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fma(z, C[(i - j) & 15], acc[j]);
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;");
+    if (s0 + sl < P.n_slices) {
+        double* out = P.part + ((size_t)seg * P.n_slices + (s0 + sl)) * SPART;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[16 * half + j] = acc[j];
+        if (half == 0) out[SK] = S;
+    }
+}
+
+struct AcwFinishParams {
+    const double* data;
+    int64_t n_slices;
+    int n_t, n_seg;
+    const double* part;
+    double* acf_work; int64_t cap;
+    int32_t* n_done; int32_t* k0; int32_t* k50; int32_t* ke;
+    int32_t* redo;               // [n_slices] 1 = needs the general kernel
+};
+
+// one warp per slice, lane = lag
+__global__ void __launch_bounds__(128) k_acw_finish(const AcwFinishParams P) {
+    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= P.n_slices) return;
+    const int k = threadIdx.x & 31;
+    double pk = 0.0, S = 0.0;
+    for (int g = 0; g < P.n_seg; ++g) {
+        const double* in = P.part + ((size_t)g * P.n_slices + s) * SPART;
+        pk += in[k];
+        S += in[SK];
+    }
+    const double n = (double)P.n_t;
+    const double m = S / n;
+    // head_k = sum of the first k samples, tail_k = sum of the last k samples: inclusive warp scans
+    double a = 0.0, b = 0.0;
+    if (k > 0 && k <= P.n_t) {
+        a = P.data[s + (size_t)(k - 1) * P.n_slices];
+        b = P.data[s + (size_t)(P.n_t - k) * P.n_slices];
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double ua = __shfl_up_sync(0xffffffffu, a, d), ub = __shfl_up_sync(0xffffffffu, b, d);
+        if (k >= d) { a += ua; b += ub; }
+    }
+    const double ck = pk - m * (2.0 * S - a - b) + (n - (double)k) * m * m;
+    const double c0 = __shfl_sync(0xffffffffu, ck, 0);
+    const bool in_range = k < P.n_t;
+    const double v = (k == 0) ? (c0 / c0) : ck / c0;
+    if (in_range) P.acf_work[(size_t)s * P.cap + k] = v;
+    const unsigned b0 = __ballot_sync(0xffffffffu, in_range && v <= 0.0);
+    const unsigned b50 = __ballot_sync(0xffffffffu, in_range && v <= 0.5);
+    const unsigned be = __ballot_sync(0xffffffffu, in_range && v <= kInvE);
+    const unsigned bad = __ballot_sync(0xffffffffu, in_range && !(v == v));      // NaN anywhere
+    if (k == 0) {
+        const int kmax = min(SK, P.n_t);
+        const int f0 = b0 ? __ffs(b0) - 1 : -1;
+        // the raw-moment form loses digits when the mean dominates; NaN data and slices that
+        // have not crossed zero within SK lags need the exact / longer kernel
+        const bool ill = !(n * m * m <= 1e6 * c0);
+        const bool redo = ill || bad || (f0 < 0 && kmax < P.n_t);
+        P.redo[s] = redo ? 1 : 0;
+        P.n_done[s] = redo ? 0 : kmax;
+        P.k0[s] = f0;
+        P.k50[s] = b50 ? __ffs(b50) - 1 : -1;
+        P.ke[s] = be ? __ffs(be) - 1 : -1;
+    }
+}
+
 // ---- host launchers ------------------------------------------------------------------
 static size_t acf_slices_smem(int n_t, int reach, int* xs_len) {
     int len = n_t + reach + 4 * TTD;
@@ -368,26 +529,61 @@ int acf_max_reach(int n_t, int max_smem) {
     return (int)(r < 0 ? 0 : r);
 }
 
-static cudaError_t launch_slices(AcfSliceParams& P, int reach, int max_smem, cudaStream_t st) {
+static cudaError_t launch_slices(AcfSliceParams& P, int reach, int max_smem, int64_t n_ctas, cudaStream_t st) {
     int xs_len = 0;
     size_t smem = acf_slices_smem(P.n_t, reach, &xs_len);
     if ((int64_t)smem > (int64_t)max_smem) return cudaErrorInvalidValue;
     P.xs_len = xs_len;
     cudaError_t e = cudaFuncSetAttribute(k_acf_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_acf_slices<<<(unsigned)P.n_slices, kThreads, smem, st>>>(P);
+    k_acf_slices<<<(unsigned)n_ctas, kThreads, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
+                              double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
+                              int32_t* ke, int32_t* redo, cudaStream_t st) {
+    AcwStreamParams S{};
+    S.data = data; S.n_slices = n_slices; S.n_t = n_t; S.n_seg = n_seg; S.seg_len = seg_len; S.part = part;
+    dim3 grid((unsigned)((n_slices + SS - 1) / SS), (unsigned)n_seg);
+    const size_t smem = (size_t)SR * SS * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_acw_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_acw_stream<<<grid, STREAM_THREADS, smem, st>>>(S);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    AcwFinishParams F{};
+    F.data = data; F.n_slices = n_slices; F.n_t = n_t; F.n_seg = n_seg; F.part = part;
+    F.acf_work = acf_work; F.cap = cap; F.n_done = n_done; F.k0 = k0; F.k50 = k50; F.ke = ke;
+    F.redo = redo;
+    k_acw_finish<<<(unsigned)((n_slices + 3) / 4), 128, 0, st>>>(F);
+    return cudaGetLastError();
+}
+int acw_stream_lags() { return SK; }
+size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return (size_t)n_seg * SPART * (size_t)n_slices; }
+void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len) {
+    // enough CTAs for ~2 waves of 3 CTAs/SM; segments are multiples of the tile length
+    const int64_t ctas_per_seg = (n_slices + SS - 1) / SS;
+    int g = (int)((6LL * sm_count + ctas_per_seg - 1) / ctas_per_seg);
+    const int max_g = (n_t + 8 * ST - 1) / (8 * ST);          // keep >= 8 tiles per segment
+    if (g > max_g) g = max_g;
+    if (g < 1) g = 1;
+    int len = (n_t + g - 1) / g;
+    len = ((len + ST - 1) / ST) * ST;
+    *seg_len = len;
+    *n_seg = (n_t + len - 1) / len;
 }
 
 cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int missing, int max_lags,
                             double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                            int32_t* ke, int32_t* nan_flag, int max_smem, cudaStream_t st) {
+                            int32_t* ke, int32_t* nan_flag, const int32_t* slice_list, int64_t n_list,
+                            int max_smem, cudaStream_t st) {
     AcfSliceParams P{};
-    P.nan_flag = nan_flag;
+    P.nan_flag = nan_flag; P.slice_list = slice_list;
     P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.missing = missing; P.mode = 0;
     P.max_lags = max_lags; P.need = 0; P.acf_work = acf_work; P.cap = cap; P.n_done = n_done;
     P.k0 = k0; P.k50 = k50; P.ke = ke;
-    return launch_slices(P, max_lags, max_smem, st);
+    return launch_slices(P, max_lags, max_smem, slice_list ? n_list : n_slices, st);
 }
 
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
@@ -395,7 +591,7 @@ cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int m
     AcfSliceParams P{};
     P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.missing = missing; P.mode = 1;
     P.max_lags = need; P.need = need; P.acf_work = acf_work; P.cap = cap; P.n_done = n_done;
-    return launch_slices(P, need, max_smem, st);
+    return launch_slices(P, need, max_smem, n_slices, st);
 }
 
 cudaError_t acf_cross_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, int32_t* k0,

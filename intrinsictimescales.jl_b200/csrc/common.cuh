@@ -41,7 +41,7 @@ struct itjl_ctx {
     bool timing = false;
     int64_t timed_launches = 0;
     double timed_ms = 0.0;
-    itjl::DevBuf theta, dist, stats, u0, noise, phases, flags, scratch, data, out, out2, out3;
+    itjl::DevBuf theta, dist, stats, u0, noise, phases, flags, scratch, data, out, out2, out3, part;
 };
 
 namespace itjl {

@@ -2,6 +2,7 @@
 // reference functions each entry point replaces).  Host logic only: argument checks,
 // H2D/D2H staging on the context stream, launch geometry, status codes.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -69,7 +70,7 @@ int itjl_ctx_destroy(itjl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->theta, &ctx->dist, &ctx->stats, &ctx->u0, &ctx->noise, &ctx->phases,
-                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3};
+                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3, &ctx->part};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -236,7 +237,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         AbcAcfParams P{};
         P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
         P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_lags = (int)d.n_stats;
-        P.chunk = m->geo.chunk; P.xs_stride = m->geo.xs_stride; P.lt = m->geo.lt;
+        P.chunk = m->geo.chunk; P.xs_stride = m->geo.xs_stride; P.n_bufs = m->geo.n_bufs; P.lt = m->geo.lt;
         P.n_streams = m->geo.n_streams; P.tiles_per_stream = m->geo.tiles_per_stream; P.n_tiles = m->geo.n_tiles;
         P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
         P.update = d.update; P.kind = d.kind; P.distance = d.distance;
@@ -248,7 +249,8 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.mask_words = m->mask_words;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
-        e = abc_acf_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC,
+        { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
+        e = abc_acf_launch(P, m->geo.threads, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC,
                            m->geo.smem_bytes, ctx->stream);
     }
     if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch fused abc kernel: %s", cudaGetErrorString(e));
@@ -418,6 +420,8 @@ int itjl_generate_ou_osc(itjl_ctx* ctx, double tau, double freq, double coeff, d
 // ---- measurement -----------------------------------------------------------------------
 int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
     if (!ctx || !tflops_out) return fail(ctx, ITJL_ERR_ARG, "itjl_fp32_peak: null argument");
+    int micro = 0;                                   // tuning: negative iters select a microbenchmark
+    if (iters < 0) { micro = -iters; iters = 5; }
     if (iters < 1) iters = 1;
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8;
@@ -430,7 +434,8 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
     double best = 0.0;
     for (int i = 0; i < iters; ++i) {
         ITJL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        e = fp32_peak_launch((float*)ctx->scratch.p, blocks, inner, ctx->stream);
+        e = micro ? fp32_micro_launch((float*)ctx->scratch.p, blocks, inner, micro, ctx->stream)
+                  : fp32_peak_launch((float*)ctx->scratch.p, blocks, inner, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_fp32_peak: %s", cudaGetErrorString(e));
         ctx->launches++;
         ITJL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

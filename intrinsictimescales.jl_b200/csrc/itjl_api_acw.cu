@@ -1,6 +1,7 @@
 // C-ABI layer, part 2: summary statistics on stored data and acw()
 // (reference src/stats/summary.jl:46-89, 183-235, 455-496 and src/core/acw.jl:141-231).
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "kernels.h"
@@ -25,7 +26,7 @@ static int check_data_args(itjl_ctx* ctx, const double* data, int64_t n_slices, 
 // Device-side ACF of every slice up to n_lags into ctx->out (row-per-slice, ld = cap).
 static int acf_all(itjl_ctx* ctx, int64_t n_slices, int n_t, int n_lags, int missing, int64_t cap, bool reset) {
     ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
-    ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 4 + 4) * sizeof(int32_t)));
+    ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 6 + 4) * sizeof(int32_t)));
     int32_t* n_done = (int32_t*)ctx->flags.p;
     if (reset) ITJL_CUDA(ctx, cudaMemsetAsync(n_done, 0, (size_t)n_slices * sizeof(int32_t), ctx->stream));
     cudaError_t e = acf_fill_launch((const double*)ctx->data.p, n_slices, n_t, missing, n_lags,
@@ -150,9 +151,11 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
 
     rc = upload_data(ctx, data, n_slices, n_t);
     if (rc != ITJL_OK) return rc;
-    ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 4 + 4) * sizeof(int32_t)));
+    ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 6 + 4) * sizeof(int32_t)));
     int32_t* d_done = (int32_t*)ctx->flags.p;
-    int32_t* d_nan = d_done + 4 * n_slices;
+    int32_t* d_nan = d_done + 6 * n_slices;
+    int32_t* d_redo = d_done + 4 * n_slices;
+    int32_t* d_list = d_done + 5 * n_slices;
     int32_t* d_k0 = d_done + n_slices;
     int32_t* d_k50 = d_k0 + n_slices;
     int32_t* d_ke = d_k50 + n_slices;
@@ -163,6 +166,7 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     int64_t acf_ld = 0;
     int64_t lags_avail = 0;
     int64_t cap = 0;
+    bool all_streamed = false;       // every slice holds the streaming pass's 32 lags
     cudaError_t e;
 
     if (!average_over_trials) {
@@ -172,10 +176,40 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
         ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
         ITJL_CUDA(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int32_t), ctx->stream));
         if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
-        e = acw_scan_launch((const double*)ctx->data.p, n_slices, nt, 1, reach, (double*)ctx->out.p, cap,
-                            d_done, d_k0, d_k50, d_ke, d_nan, ctx->max_smem_optin, ctx->stream);
-        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(scan): %s", cudaGetErrorString(e));
-        ctx->launches++;
+        const char* env_stream = getenv("ITJL_ACW_STREAM");
+        const bool use_stream = !(env_stream && atoi(env_stream) == 0) && nt >= 256 && acw_stream_lags() <= reach;
+        std::vector<int32_t> h_redo;
+        if (use_stream) {
+            // one streaming read of the data: raw lagged products of the first 32 lags
+            int n_seg = 1, seg_len = nt;
+            acw_stream_segments(nt, n_slices, ctx->sm_count, &n_seg, &seg_len);
+            ITJL_CUDA(ctx, ctx->part.reserve(acw_stream_part_doubles(n_slices, n_seg) * sizeof(double)));
+            e = acw_stream_launch((const double*)ctx->data.p, n_slices, nt, (double*)ctx->part.p, n_seg, seg_len,
+                                  (double*)ctx->out.p, cap, d_done, d_k0, d_k50, d_ke, d_redo, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_stream: %s", cudaGetErrorString(e));
+            ctx->launches += 2;
+            h_redo.resize((size_t)n_slices);
+            ITJL_CUDA(ctx, cudaMemcpyAsync(h_redo.data(), d_redo, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::vector<int32_t> list;
+            for (int64_t i = 0; i < n_slices; ++i) if (h_redo[i]) list.push_back((int32_t)i);
+            all_streamed = list.empty();
+            if (!list.empty()) {
+                // slices that need more than 32 lags (or exact centring): shared-memory kernel
+                ITJL_CUDA(ctx, cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                e = acw_scan_launch((const double*)ctx->data.p, n_slices, nt, 1, reach, (double*)ctx->out.p, cap,
+                                    d_done, d_k0, d_k50, d_ke, d_nan, d_list, (int64_t)list.size(),
+                                    ctx->max_smem_optin, ctx->stream);
+                if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(scan list): %s", cudaGetErrorString(e));
+                ctx->launches++;
+                ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // list stays alive until here
+            }
+        } else {
+            e = acw_scan_launch((const double*)ctx->data.p, n_slices, nt, 1, reach, (double*)ctx->out.p, cap,
+                                d_done, d_k0, d_k50, d_ke, d_nan, nullptr, 0, ctx->max_smem_optin, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(scan): %s", cudaGetErrorString(e));
+            ctx->launches++;
+        }
         if (ctx->timing) {
             cudaEventRecord(ctx->ev1, ctx->stream);
             cudaEventSynchronize(ctx->ev1);
@@ -240,10 +274,12 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
 
     // make sure every row holds n_lags lags
     if (!average_over_trials) {
-        e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)n_lags, (double*)ctx->out.p, cap,
-                            d_done, ctx->max_smem_optin, ctx->stream);
-        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
-        ctx->launches++;
+        if (!(all_streamed && n_lags <= acw_stream_lags())) {
+            e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)n_lags, (double*)ctx->out.p, cap,
+                                d_done, ctx->max_smem_optin, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
+            ctx->launches++;
+        }
     } else if (n_lags > lags_avail) {
         rc = acf_all(ctx, n_slices, nt, (int)n_lags, 1, cap, false);
         if (rc != ITJL_OK) return rc;

@@ -10,7 +10,7 @@ struct AbcAcfParams {
     int64_t n_particles;
     int n_theta;
     int n_t, n_trials, n_lags;
-    int chunk, xs_stride;
+    int chunk, xs_stride, n_bufs;
     int lt, n_streams, tiles_per_stream, n_tiles;
     double dt, data_mean, data_sd;
     int update, kind, distance;
@@ -25,13 +25,15 @@ struct AbcAcfParams {
     const double* phases;
     double* dist_out;
     double* stats_out;
+    int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = skip simulate, 2 = skip lag sum
 };
 struct AbcAcfGeometry {
-    int chunk, xs_stride, lt, n_streams, tiles_per_stream, n_tiles;
+    int threads, n_bufs, chunk, xs_stride, lt, n_streams, tiles_per_stream, n_tiles;
     size_t smem_bytes;
 };
 int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g);
-cudaError_t abc_acf_launch(const AbcAcfParams& P, bool missing, bool osc, size_t smem, cudaStream_t st);
+cudaError_t abc_acf_launch(const AbcAcfParams& P, int threads, bool missing, bool osc, size_t smem,
+                           cudaStream_t st);
 cudaError_t abc_accept_launch(const double* dist, int64_t n, double eps, int64_t min_accepted,
                               uint8_t* isacc, int64_t* out2, cudaStream_t st);
 
@@ -84,7 +86,15 @@ cudaError_t ou_generate_launch(const OuGenParams& P, cudaStream_t st);
 // acf_work is a row-per-slice work buffer [slice][cap]; n_done[slice] = lags present.
 cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int missing, int max_lags,
                             double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                            int32_t* ke, int32_t* nan_flag, int max_smem, cudaStream_t st);
+                            int32_t* ke, int32_t* nan_flag, const int32_t* slice_list, int64_t n_list,
+                            int max_smem, cudaStream_t st);
+// streaming first pass (raw lagged products of the first acw_stream_lags() lags, one read of the data)
+cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
+                              double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
+                              int32_t* ke, int32_t* redo, cudaStream_t st);
+int acw_stream_lags();
+size_t acw_stream_part_doubles(int64_t n_slices, int n_seg);
+void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len);
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
                             double* acf_work, int64_t cap, int32_t* n_done, int max_smem, cudaStream_t st);
 cudaError_t acf_cross_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, int32_t* k0,
@@ -102,5 +112,6 @@ int acf_max_reach(int n_t, int max_smem);
 // ---- peak_kernels.cu -----------------------------------------------------------------
 cudaError_t fp32_peak_launch(float* sink, int blocks, int iters, cudaStream_t st);
 double fp32_peak_flops_per_launch(int blocks, int iters);
+cudaError_t fp32_micro_launch(float* sink, int blocks, int iters, int mode, cudaStream_t st);
 
 }  // namespace itjl

@@ -11,24 +11,26 @@ template <bool OSC>
 __global__ void __launch_bounds__(kThreads) k_ou_generate(const OuGenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);
-    SimShared* sh = reinterpret_cast<SimShared*>(xs + (size_t)P.chunk * kThreads);
+    SimShared<kThreads>* sh = reinterpret_cast<SimShared<kThreads>*>(xs + (size_t)P.chunk * kThreads);
     const int trial = blockIdx.x;
     const OuConsts oc = make_ou_consts(P.tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
                                        P.freq, P.coeff);
+    SimCache sim_cache;
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
+    g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
     g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
     g.particle = P.particle;
     g.u0 = P.u0; g.noise = P.noise; g.phases = P.phases;
     g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;
-    simulate_trial<false, OSC>(g, oc, trial, xs, sh, P.mode, P.scale, P.shift);
+    simulate_trial<kThreads, false, OSC>(g, oc, trial, xs, sh, P.mode, P.scale, P.shift, sim_cache);
     __syncthreads();
     for (int j = threadIdx.x; j < P.n_t; j += kThreads)
         P.out[(size_t)j * P.n_trials + trial] = (double)xs[j];
 }
 
 cudaError_t ou_generate_launch(const OuGenParams& P, cudaStream_t st) {
-    const size_t smem = (size_t)P.chunk * kThreads * sizeof(float) + sizeof(SimShared);
+    const size_t smem = (size_t)P.chunk * kThreads * sizeof(float) + sizeof(SimShared<kThreads>);
     void (*kern)(const OuGenParams) = (P.kind == ITJL_KIND_OU_OSC) ? k_ou_generate<true> : k_ou_generate<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
     float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats = N float2
     float2* buf = reinterpret_cast<float2*>(smem_raw);
     float* accb = xs + P.xs_len;                                    // n_stats
-    SimShared* sh = reinterpret_cast<SimShared*>(accb + ((P.n_stats + 3) & ~3));
+    SimShared<kThreads>* sh = reinterpret_cast<SimShared<kThreads>*>(accb + ((P.n_stats + 3) & ~3));
     __shared__ double red[kWarps];
 
     const int tid = threadIdx.x;
@@ -112,8 +112,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
     }
     const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
                                        freq, coeff);
+    SimCache sim_cache;
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
+    g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
     g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
     g.particle = (uint32_t)(P.particle_offset + particle);
     const size_t pt = (size_t)particle * P.n_trials;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
     for (int trial = 0; trial < P.n_trials; ++trial) {
         // standardised series * data_sd; the reference then adds data_mean and
         // comp_psd_adfriendly removes the mean again (summary.jl:209) - skipped both.
-        simulate_trial<false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, 0.0f);
+        simulate_trial<kThreads, false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, 0.0f, sim_cache);
         for (int i = P.chunk * kThreads + tid; i < P.xs_len; i += kThreads) xs[i] = 0.f;
         __syncthreads();
         for (int j = tid; j < P.n_t; j += kThreads) xs[j] *= __ldg(P.window + j);

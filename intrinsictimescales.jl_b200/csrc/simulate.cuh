@@ -51,17 +51,20 @@ __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int up
     return c;
 }
 
+template <int NT>
 struct SimShared {
-    float scanA[kWarps];
-    float scanB[kWarps];
-    double sums[kWarps][4];
+    float scanA[NT / 32];
+    float scanB[NT / 32];
+    double sums[NT / 32][4];
 };
 
 enum : int { kScaleUnitNorm = 0, kScaleStd = 1, kScaleRaw = 2 };
 
 struct SimArgs {
     int n_t;                  // samples per trial
-    int chunk;                // samples per thread (multiple of 4, chunk * kThreads >= n_t)
+    double inv_n;             // 1 / n_t
+    float sqrt_nm1;           // sqrt(n_t - 1)
+    int chunk;                // samples per thread (multiple of 4, chunk * NT >= n_t)
     uint32_t k0, k1;          // Philox key (seed)
     uint32_t c3_noise, c3_init;
     uint32_t particle;        // global particle index (low 32 bits)
@@ -73,17 +76,24 @@ struct SimArgs {
     int mask_words;
 };
 
-// Simulate trial `trial` into xs[0 .. chunk*kThreads).  On return (after the caller's
-// __syncthreads()) xs holds
+// Per-thread values that do not change from trial to trial (filled during the first trial).
+struct SimCache {
+    float Sp = 0.f, Spp = 0.f;     // sum p_j, sum p_j^2 over this thread's valid samples
+    bool valid = false;
+};
+
+// Simulate trial `trial` into xs[0 .. chunk*NT) with a CTA of NT threads.  On return (after the
+// caller's __syncthreads()) xs holds
 //   kScaleUnitNorm : (x - mean) / sqrt(sum (x-mean)^2)                (ACF kernels)
 //                    with MISSING: the comp_ac_time_missing centring, masked samples = -m2
 //   kScaleStd      : (x - mean) / std_{n-1} * scale + shift            (PSD kernel, generator)
 //   kScaleRaw      : x                                                 (standardize = false)
 // and zeros for j >= n_t.
-template <bool MISSING, bool OSC>
+template <int NT, bool MISSING, bool OSC>
 __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts& oc, int trial,
-                                               float* __restrict__ xs, SimShared* sh, int mode,
-                                               float scale, float shift) {
+                                               float* __restrict__ xs, SimShared<NT>* sh, int mode,
+                                               float scale, float shift, SimCache& cache) {
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j0 = tid * g.chunk;
     const float eps = oc.eps, s = oc.s;
@@ -107,11 +117,13 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     float Vy = 0.f, Vyy = 0.f, Vyp = 0.f, Vp = 0.f, Vpp = 0.f;   // valid-only sums (MISSING)
     const double* nz = g.noise ? g.noise + (size_t)trial * g.n_t : nullptr;
     const uint32_t* mrow = MISSING ? g.mask_bits + (size_t)trial * g.mask_words : nullptr;
+    const bool need_p_sums = !cache.valid;
     if (j0 < g.n_t) {
         for (int q = 0; q < g.chunk; q += 4) {
             const int j = j0 + q;
             float z[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t mbits = 0u;
+            const bool full = (j + 3 < g.n_t);
             if (j < g.n_t) {
                 if (nz) {
 #pragma unroll
@@ -126,32 +138,47 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 }
                 if (MISSING) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
             }
-            float v[4];
+            float v[4], pp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 y = fmaf(-eps, y, y);
                 y = fmaf(s, z[i], y);
                 p = fmaf(-eps, p, p);
-                float val = y, pp = p;
+                v[i] = y; pp[i] = p;
                 if (OSC) {
                     double turns = fma(oc.fdt, (double)(j + i + 1), phase_turns);
                     turns -= rint(turns);
-                    val = fmaf(oc.so, sinpif(2.0f * (float)turns), oc.sc * y);
-                    pp = oc.sc * p;
+                    v[i] = fmaf(oc.so, sinpif(2.0f * (float)turns), oc.sc * y);
+                    pp[i] = oc.sc * p;
                 }
-                v[i] = val;
-                if (j + i < g.n_t) {
-                    Sy += val; Syy = fmaf(val, val, Syy); Syp = fmaf(val, pp, Syp);
-                    Sp += pp;  Spp = fmaf(pp, pp, Spp);
-                    if (MISSING && !((mbits >> i) & 1u)) {
-                        Vy += val; Vyy = fmaf(val, val, Vyy); Vyp = fmaf(val, pp, Vyp);
-                        Vp += pp;  Vpp = fmaf(pp, pp, Vpp);
+            }
+            if (full && !MISSING) {                      // common case: no per-sample predicates
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syp = fmaf(v[i], pp[i], Syp);
+                }
+                if (need_p_sums) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { Sp += pp[i]; Spp = fmaf(pp[i], pp[i], Spp); }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (j + i < g.n_t) {
+                        Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syp = fmaf(v[i], pp[i], Syp);
+                        if (need_p_sums) { Sp += pp[i]; Spp = fmaf(pp[i], pp[i], Spp); }
+                        if (MISSING && !((mbits >> i) & 1u)) {
+                            Vy += v[i]; Vyy = fmaf(v[i], v[i], Vyy); Vyp = fmaf(v[i], pp[i], Vyp);
+                            Vp += pp[i]; Vpp = fmaf(pp[i], pp[i], Vpp);
+                        }
                     }
                 }
             }
             *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
+    if (need_p_sums) { cache.Sp = Sp; cache.Spp = Spp; cache.valid = true; }
+    else { Sp = cache.Sp; Spp = cache.Spp; }
 
     // ---- scan of the chunk-end affine maps x -> A x + B ----------------------------
     float A = p, B = y;
@@ -186,48 +213,56 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     __syncthreads();
     double SX = 0.0, SXX = 0.0, VX = 0.0, VXX = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
+    for (int w = 0; w < NW; ++w) {
         SX += sh->sums[w][0]; SXX += sh->sums[w][1];
         if (MISSING) { VX += sh->sums[w][2]; VXX += sh->sums[w][3]; }
     }
     const double n = (double)g.n_t;
-    double m = SX / n;
+    double m = SX * g.inv_n;
     float mf, rf, miss_val = 0.f;
     if (!MISSING) {
-        const double ss = SXX - n * m * m;
-        double r;
-        if (mode == kScaleUnitNorm) r = 1.0 / sqrt(ss);
-        else if (mode == kScaleStd) r = (double)scale / sqrt(ss / (n - 1.0));
-        else { r = 1.0; m = 0.0; }
-        mf = (float)m; rf = (float)r;
+        // sums are combined in fp64 (cancellation in SXX - n m^2); the final reciprocal square
+        // root is an fp32 rsqrt refined by one Newton step (relative error < 1e-7)
+        const float ssf = (float)(SXX - n * m * m);
+        float r = rsqrtf(ssf);
+        r = r * fmaf(-0.5f * ssf * r, r, 1.5f);
+        if (mode == kScaleStd) r *= scale * g.sqrt_nm1;
+        else if (mode == kScaleRaw) { r = 1.0f; m = 0.0; }
+        mf = (float)m; rf = r;
     } else {
         // comp_ac_time_missing (summary.jl:460-471) applied to the standardised, masked
         // trial: valid z = x - m_all, masked z = 0; m2 = mean of valid z; every entry -= m2.
         const double nv = (double)g.n_valid[trial];
-        const double m2 = (VX - nv * m) / nv;
+        const double m2 = (double)((float)(VX - nv * m) / (float)nv);
         const double mt = m + m2;
-        const double ss = VXX - 2.0 * mt * VX + nv * mt * mt + (n - nv) * m2 * m2;
-        const double r = 1.0 / sqrt(ss);
-        mf = (float)mt; rf = (float)r; miss_val = (float)(-m2 * r);
+        const float ssf = (float)(VXX - 2.0 * mt * VX + nv * mt * mt + (n - nv) * m2 * m2);
+        float r = rsqrtf(ssf);
+        r = r * fmaf(-0.5f * ssf * r, r, 1.5f);
+        mf = (float)mt; rf = r; miss_val = (float)(-m2) * r;
     }
 
-    // ---- pass B: add the carry, centre, scale ---------------------------------------
+    // ---- pass B: out = (y + p c - m) r + shift = y r + p (c r) + (shift - m r) -----------
     if (j0 < g.n_t) {
-        float pb = 1.f;
+        float pb = OSC ? oc.sc : 1.f;
+        const float crf = c * rf;
+        const float k0 = fmaf(-mf, rf, shift);
         for (int q = 0; q < g.chunk; q += 4) {
             const int j = j0 + q;
             float4 v4 = *reinterpret_cast<const float4*>(xs + j);
             float v[4] = {v4.x, v4.y, v4.z, v4.w};
-            uint32_t mbits = 0u;
-            if (MISSING && j < g.n_t) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 pb = fmaf(-eps, pb, pb);
-                const float pp = OSC ? oc.sc * pb : pb;
-                const float x = fmaf(pp, c, v[i]);
-                float o = fmaf(x - mf, rf, shift);
-                if (MISSING && ((mbits >> i) & 1u)) o = miss_val;
-                v[i] = (j + i < g.n_t) ? o : 0.f;
+                v[i] = fmaf(v[i], rf, fmaf(pb, crf, k0));
+            }
+            if (MISSING || j + 3 >= g.n_t) {
+                uint32_t mbits = 0u;
+                if (MISSING && j < g.n_t) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (MISSING && ((mbits >> i) & 1u)) v[i] = miss_val;
+                    if (j + i >= g.n_t) v[i] = 0.f;
+                }
             }
             *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
         }
