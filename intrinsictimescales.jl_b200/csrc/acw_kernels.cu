@@ -355,23 +355,30 @@ __global__ void k_acw_tau(const double* __restrict__ acf, int64_t n_rows, int64_
 
 // ---- streaming first pass (short-memory data: HBM-bound) -----------------------------------
 // One pass over the column-major input computes, for every slice, the RAW lagged products
-//   P_k = sum_t x_t x_{t-k}, k < SK = 32,   and S = sum x_t,
+//   P_k = sum_t y_t y_{t-k}, k < SK = 32,   and S = sum y_t,     y = x - ref  (per-slice shift)
 // from which k_acw_finish derives the centred autocorrelation algebraically:
 //   C_k = P_k - m (2S - head_k - tail_k) + (n - k) m^2,  m = S / n,
-// head_k / tail_k = sums of the first / last k samples.  Everything is fp64.
+// head_k / tail_k = sums of the first / last k shifted samples.
+// Precision (north_star: "fp32 accumulate, fp64 check"): the shift is applied in fp64, the
+// products and the 32-step tile sums are fp32, tile sums are accumulated in fp64 - ACF error
+// ~1e-8.  Every crossing decision whose ACF value lies within 1e-6 of a threshold (0, 0.5, 1/e),
+// every slice containing a NaN (it propagates into P_k), every slice that has not crossed zero
+// within SK lags and every slice whose shifted mean is still large (n m^2 > C_0) is redone
+// in fp64 by k_acf_slices, so the crossing indices stay bit-exact against an fp64 reference.
 // Layout: a CTA streams SS = 64 adjacent slices (512 contiguous bytes per time step) of one
-// time segment through a 4-tile shared-memory ring with cp.async (tile = 32 time steps,
-// prefetch distance 2, one __syncthreads() per tile); thread = (slice, half of the lags):
-// 16 accumulators + a 16-deep circular register window, 16 DFMA per 2 LDS.64.
-// A NaN (missing sample) simply propagates into P_k; such slices, slices whose zero crossing
-// lies beyond SK lags, and slices whose mean is so large that the raw-moment form would cancel
-// (n m^2 > 1e6 C_0) are flagged and redone exactly by k_acf_slices.
+// time segment through a 4-tile shared-memory ring of raw doubles filled by cp.async (tile = 32
+// time steps, two tiles in flight, one __syncthreads() per tile); thread = (slice, half of the
+// lags): samples are shifted and narrowed to fp32 as they are read, 16 accumulators + a 16-deep
+// circular register window, 16 FFMA per 2 LDS.64.  The shift is the mean of the slice's first
+// 32 samples (same arithmetic in k_acw_finish).
 constexpr int SK = 32;     // lags of the streaming pass
 constexpr int SS = 64;     // slices per CTA
 constexpr int ST = 32;     // time steps per tile
 constexpr int SR = 128;    // ring rows = 4 tiles: halo, current, two in flight
+constexpr int SREF = 32;   // samples averaged for the per-slice shift
 constexpr int SPART = SK + 1;   // per (segment, slice): P_0..P_31, S
 constexpr int STREAM_THREADS = 128;
+constexpr double kStreamTol = 1e-6;
 
 struct AcwStreamParams {
     const double* data;
@@ -384,6 +391,14 @@ struct AcwStreamParams {
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+
+// per-slice shift: mean of the first min(SREF, n_t) samples, summed in time order
+__device__ __forceinline__ double slice_ref(const double* __restrict__ data, int64_t s, int64_t n_slices, int n_t) {
+    const int m = min(SREF, n_t);
+    double r = 0.0;
+    for (int t = 0; t < m; ++t) r += data[s + (size_t)t * n_slices];
+    return r / (double)m;
 }
 
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStreamParams P) {
@@ -406,6 +421,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStrea
         for (int i = tid; i < ST * SS; i += STREAM_THREADS) {
             const int r = i / SS, c = i - r * SS;
             const int t = t0 + r;
+            // rows outside [0, n_t) are only read as the halo of segment 0 (t < 0) or past te;
+            // both are masked where they are consumed (the shift would make a stored 0 non-zero)
             if (t >= 0 && t < P.n_t && s0 + c < P.n_slices) cp_async8(base + i, P.data + (s0 + c) + (size_t)t * P.n_slices);
             else base[i] = 0.0;
         }
@@ -415,10 +432,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStrea
     load_tile(0);
     load_tile(1);
     if (n_tiles > 1) load_tile(2); else asm volatile("cp.async.commit_group;");
-    double acc[16], C[16];
+    const double ref = (s0 + sl < P.n_slices) ? slice_ref(P.data, s0 + sl, P.n_slices, P.n_t) : 0.0;
+
+    float acc[16], C[16];
+    double acc64[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { acc[j] = 0.0; C[j] = 0.0; }
-    double S = 0.0;
+    for (int j = 0; j < 16; ++j) { acc[j] = 0.f; C[j] = 0.f; acc64[j] = 0.0; }
+    double S64 = 0.0;
 
     for (int tile = 0; tile < n_tiles; ++tile) {
         asm volatile("cp.async.wait_group 1;");        // halo + tiles <= `tile` have landed
@@ -426,32 +446,42 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStrea
         if (tile + 2 < n_tiles) load_tile(tile + 3); else asm volatile("cp.async.commit_group;");
         const double* cur = &ring[((tile + 1) & 3) * ST][sl];        // rows of this tile
         const double* prev = &ring[(tile & 3) * ST][sl];             // rows of the previous tile / halo
+        const int t_tile = tb + tile * ST;
         if (tile == 0) {
-            // circular window C[tau & 15] = x_tau, tau = t - 16 half: preload the 15 older samples
+            // circular window C[tau & 15] = y_tau, tau = t - 16 half: preload the 15 older samples
 #pragma unroll
-            for (int j = 1; j < 16; ++j) C[(16 - j) & 15] = prev[(ST - 16 * half - j) * SS];
-        }
-        const int valid_rows = min(ST, te - (tb + tile * ST));       // rows >= te belong to the next segment
-#pragma unroll
-        for (int blk = 0; blk < ST; blk += 16) {
-            const double* dly = half ? (blk ? cur + (blk - 16) * SS : prev + (ST - 16) * SS) : cur + blk * SS;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                double z = cur[(blk + i) * SS];
-                if (blk + i >= valid_rows) z = 0.0;
-                C[i] = half ? dly[i * SS] : z;          // tau & 15 == i (tb and ST are multiples of 16)
-                if (half == 0) S += z;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fma(z, C[(i - j) & 15], acc[j]);
+            for (int j = 1; j < 16; ++j) {
+                const int tau = t_tile - 16 * half - j;
+                C[(16 - j) & 15] = (tau >= 0) ? (float)(prev[(ST - 16 * half - j) * SS] - ref) : 0.f;
             }
         }
+        const int valid_rows = min(ST, te - t_tile);   // later rows belong to the next segment
+        float S = 0.f;
+#pragma unroll
+        for (int blk = 0; blk < ST; blk += 16) {
+            const double* dly = blk ? cur + (blk - 16) * SS : prev + (ST - 16) * SS;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float z = (float)(cur[(blk + i) * SS] - ref);
+                if (blk + i >= valid_rows) z = 0.f;
+                float d = z;
+                if (half) d = (t_tile + blk + i - 16 >= 0) ? (float)(dly[i * SS] - ref) : 0.f;
+                C[i] = d;                                // tau & 15 == i (tb and ST are multiples of 16)
+                S += z;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fmaf(z, C[(i - j) & 15], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { acc64[j] += (double)acc[j]; acc[j] = 0.f; }
+        S64 += (double)S;
     }
     asm volatile("cp.async.wait_group 0;");
     if (s0 + sl < P.n_slices) {
         double* out = P.part + ((size_t)seg * P.n_slices + (s0 + sl)) * SPART;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[16 * half + j] = acc[j];
-        if (half == 0) out[SK] = S;
+        for (int j = 0; j < 16; ++j) out[16 * half + j] = acc64[j];
+        if (half == 0) out[SK] = S64;
     }
 }
 
@@ -462,7 +492,7 @@ struct AcwFinishParams {
     const double* part;
     double* acf_work; int64_t cap;
     int32_t* n_done; int32_t* k0; int32_t* k50; int32_t* ke;
-    int32_t* redo;               // [n_slices] 1 = needs the general kernel
+    int32_t* redo;               // [n_slices] 1 = needs the fp64 kernel
 };
 
 // one warp per slice, lane = lag
@@ -478,11 +508,12 @@ __global__ void __launch_bounds__(128) k_acw_finish(const AcwFinishParams P) {
     }
     const double n = (double)P.n_t;
     const double m = S / n;
-    // head_k = sum of the first k samples, tail_k = sum of the last k samples: inclusive warp scans
+    const double ref = slice_ref(P.data, s, P.n_slices, P.n_t);
+    // head_k = sum of the first k shifted samples, tail_k = sum of the last k: inclusive warp scans
     double a = 0.0, b = 0.0;
     if (k > 0 && k <= P.n_t) {
-        a = P.data[s + (size_t)(k - 1) * P.n_slices];
-        b = P.data[s + (size_t)(P.n_t - k) * P.n_slices];
+        a = P.data[s + (size_t)(k - 1) * P.n_slices] - ref;
+        b = P.data[s + (size_t)(P.n_t - k) * P.n_slices] - ref;
     }
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -498,13 +529,16 @@ __global__ void __launch_bounds__(128) k_acw_finish(const AcwFinishParams P) {
     const unsigned b50 = __ballot_sync(0xffffffffu, in_range && v <= 0.5);
     const unsigned be = __ballot_sync(0xffffffffu, in_range && v <= kInvE);
     const unsigned bad = __ballot_sync(0xffffffffu, in_range && !(v == v));      // NaN anywhere
+    const int f0 = b0 ? __ffs(b0) - 1 : -1;
+    // fp32 products: a value this close to a threshold, at a lag that matters for a crossing,
+    // is decided in fp64 instead
+    const bool matters = in_range && k > 0 && (f0 < 0 || k <= f0);
+    const bool close = fabs(v) < kStreamTol || fabs(v - 0.5) < kStreamTol || fabs(v - kInvE) < kStreamTol;
+    const unsigned unsure = __ballot_sync(0xffffffffu, matters && close);
     if (k == 0) {
         const int kmax = min(SK, P.n_t);
-        const int f0 = b0 ? __ffs(b0) - 1 : -1;
-        // the raw-moment form loses digits when the mean dominates; NaN data and slices that
-        // have not crossed zero within SK lags need the exact / longer kernel
-        const bool ill = !(n * m * m <= 1e6 * c0);
-        const bool redo = ill || bad || (f0 < 0 && kmax < P.n_t);
+        const bool ill = !(n * m * m <= c0);             // shifted mean still dominates: cancellation
+        const bool redo = ill || bad || unsure || (f0 < 0 && kmax < P.n_t);
         P.redo[s] = redo ? 1 : 0;
         P.n_done[s] = redo ? 0 : kmax;
         P.k0[s] = f0;
@@ -587,11 +621,13 @@ cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int m
 }
 
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
-                            double* acf_work, int64_t cap, int32_t* n_done, int max_smem, cudaStream_t st) {
+                            double* acf_work, int64_t cap, int32_t* n_done, const int32_t* slice_list,
+                            int64_t n_list, int max_smem, cudaStream_t st) {
     AcfSliceParams P{};
+    P.slice_list = slice_list;
     P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.missing = missing; P.mode = 1;
     P.max_lags = need; P.need = need; P.acf_work = acf_work; P.cap = cap; P.n_done = n_done;
-    return launch_slices(P, need, max_smem, n_slices, st);
+    return launch_slices(P, need, max_smem, slice_list ? n_list : n_slices, st);
 }
 
 cudaError_t acf_cross_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, int32_t* k0,

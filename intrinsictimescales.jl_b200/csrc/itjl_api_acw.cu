@@ -30,7 +30,7 @@ static int acf_all(itjl_ctx* ctx, int64_t n_slices, int n_t, int n_lags, int mis
     int32_t* n_done = (int32_t*)ctx->flags.p;
     if (reset) ITJL_CUDA(ctx, cudaMemsetAsync(n_done, 0, (size_t)n_slices * sizeof(int32_t), ctx->stream));
     cudaError_t e = acf_fill_launch((const double*)ctx->data.p, n_slices, n_t, missing, n_lags,
-                                    (double*)ctx->out.p, cap, n_done, ctx->max_smem_optin, ctx->stream);
+                                    (double*)ctx->out.p, cap, n_done, nullptr, 0, ctx->max_smem_optin, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
     ctx->launches++;
     return ITJL_OK;
@@ -167,6 +167,7 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     int64_t lags_avail = 0;
     int64_t cap = 0;
     bool all_streamed = false;       // every slice holds the streaming pass's 32 lags
+    int64_t n_redo = 0;              // slices redone by the fp64 kernel (their indices stay in d_list)
     cudaError_t e;
 
     if (!average_over_trials) {
@@ -194,6 +195,7 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
             std::vector<int32_t> list;
             for (int64_t i = 0; i < n_slices; ++i) if (h_redo[i]) list.push_back((int32_t)i);
             all_streamed = list.empty();
+            n_redo = (int64_t)list.size();
             if (!list.empty()) {
                 // slices that need more than 32 lags (or exact centring): shared-memory kernel
                 ITJL_CUDA(ctx, cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -275,8 +277,11 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     // make sure every row holds n_lags lags
     if (!average_over_trials) {
         if (!(all_streamed && n_lags <= acw_stream_lags())) {
+            // streamed slices already hold 32 lags: when that is enough only the redone ones need filling
+            const bool only_list = n_redo > 0 && n_lags <= acw_stream_lags();
             e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)n_lags, (double*)ctx->out.p, cap,
-                                d_done, ctx->max_smem_optin, ctx->stream);
+                                d_done, only_list ? d_list : nullptr, only_list ? n_redo : 0,
+                                ctx->max_smem_optin, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
             ctx->launches++;
         }

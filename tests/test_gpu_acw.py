@@ -10,9 +10,10 @@ from oracle import ou as oou
 pytestmark = pytest.mark.gpu
 
 TYPES = ["acw0", "acw50", "acweuler", "auc", "tau"]
+ACF_VALUE_TOL = 2e-7
 
 
-def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=False):
+def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=False, tau_rtol=1e-5):
     want = oacw.acw(data, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average)
     got = pkg.acw(data, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average, ctx=ctx)
     res = dict(zip(types, got.acw_results if len(types) > 1 else [got.acw_results]))
@@ -22,12 +23,14 @@ def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=F
         if name in types:
             w = np.where(want[key] >= 0, want[key] * dt, np.nan)
             assert np.array_equal(np.atleast_1d(res[name]), w, equal_nan=True), name   # bit-exact
+    # values: the streaming pass multiplies in fp32 (accumulates in fp64): ACF error ~1e-8, two
+    # orders below the 1e-5 of north_star (1); crossing indices above are exact regardless
     if "auc" in types:
-        assert np.allclose(np.atleast_1d(res["auc"]), want["auc"], rtol=1e-11, atol=1e-14)
+        assert np.allclose(np.atleast_1d(res["auc"]), want["auc"], rtol=1e-6, atol=1e-9)
     if "tau" in types:
-        assert np.allclose(np.atleast_1d(res["tau"]), want["tau"], rtol=1e-7, atol=0)
+        assert np.allclose(np.atleast_1d(res["tau"]), want["tau"], rtol=tau_rtol, atol=0)
     assert got.acf.shape == want["acf"].shape or got.acf.shape == want["acf"][0].shape
-    assert np.max(np.abs(np.atleast_2d(got.acf) - want["acf"])) < 1e-12
+    assert np.max(np.abs(np.atleast_2d(got.acf) - want["acf"])) < ACF_VALUE_TOL
     assert np.array_equal(got.lags, want["lags"])
     return got, want
 
@@ -43,8 +46,16 @@ def _data_with_k0_first_ge_2(make, seeds=range(100)):
 
 def test_acw_on_white_noise(pkg, ctx):
     d = _data_with_k0_first_ge_2(lambda s: np.random.default_rng(s).standard_normal((400, 5000)))
-    got, want = check_against_oracle(pkg, ctx, d, 100.0)
+    # white noise: acf[1] ~ 0, so the exp-decay fit is ill-conditioned (d tau / d acf ~ tau /
+    # (acf ln(1/acf))): compare tau loosely and the fitted objective tightly
+    got, want = check_against_oracle(pkg, ctx, d, 100.0, tau_rtol=5e-3)
     assert want["n_lags"] < 40                                # short-memory regime (HBM-bound)
+    from oracle import acwred
+    tau_g = dict(zip(TYPES, got.acw_results))["tau"]
+    for i in range(0, 400, 7):
+        rg = acwred.expdecay_residual(tau_g[i], want["lags"], want["acf"][i])
+        ro = acwred.expdecay_residual(want["tau"][i], want["lags"], want["acf"][i])
+        assert rg <= ro * (1 + 1e-9) + 1e-15
 
 
 def test_acw_on_ou_data(pkg, ctx):
@@ -104,7 +115,7 @@ def test_acw_full_size_c2(pkg, ctx):
     want = oacw.acw(d[idx], 100.0, acwtypes=["acw0", "acw50", "acweuler"], n_lags=got.n_lags)
     for name, key in [("acw0", "k0"), ("acw50", "k50"), ("acweuler", "ke")]:
         assert np.array_equal(r[name][idx], want[key] / 100.0)
-    assert np.max(np.abs(got.acf[idx] - want["acf"])) < 1e-12
+    assert np.max(np.abs(got.acf[idx] - want["acf"])) < ACF_VALUE_TOL
     assert np.all(got.acf[:, 0] == 1.0)
     assert np.all(r["acw50"] == 0.01) and np.all(r["acweuler"] == 0.01)     # white noise: lag 1
     assert np.all(r["acw0"] >= 0.01) and got.n_lags == math.ceil(1.1 * round(r["acw0"].max() * 100))
