@@ -162,17 +162,23 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         m->log2_n2 = 0; while ((1 << m->log2_n2) < m->n2) m->log2_n2++;
         for (int64_t i = 0; i < d.n_stats; ++i)
             if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { delete m; return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
-        m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, &m->psd_chunk, &m->psd_xs_len)
-                      + (size_t)((d.n_stats + 3) & ~3ll) * sizeof(float) + 512;
+        m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
         if ((int64_t)m->psd_smem > ctx->max_smem_optin) { delete m; return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
         std::vector<float> win((size_t)d.n_t);
         std::vector<float2> tw((size_t)m->n2 / 2);
         double win_ss = 0.0;
         psd_make_tables((int)d.n_t, m->n2, win.data(), tw.data(), &win_ss);
         m->psd_scale = 1.0 / ((1.0 / d.dt) * win_ss);
-        rc = upload(ctx, m->bins, d.freq_bins, (size_t)d.n_stats * sizeof(int32_t));
+        std::vector<int4> binpos((size_t)d.n_stats);
+        for (int64_t i = 0; i < d.n_stats; ++i) {
+            const int k = d.freq_bins[i] + 1, N = m->n2 / 2;
+            binpos[i] = make_int4(psd_fft_pos(k, N), psd_fft_pos(N - k, N), k, 0);
+        }
+        rc = upload(ctx, m->bins, binpos.data(), binpos.size() * sizeof(int4));
         if (rc == ITJL_OK) rc = upload(ctx, m->window, win.data(), win.size() * sizeof(float));
         if (rc == ITJL_OK) rc = upload(ctx, m->twiddle, tw.data(), tw.size() * sizeof(float2));
+        // the host vectors above are block-local: finish the copies before they are destroyed
+        if (rc == ITJL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ITJL_ERR_CUDA, "model upload failed");
     }
     if (rc == ITJL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ITJL_ERR_CUDA, "model upload failed");
     if (rc != ITJL_OK) { itjl_model_destroy(m); return rc; }
@@ -227,7 +233,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
         P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
         P.particle_offset = particle_offset;
-        P.target = (const float*)m->target.p; P.bins = (const int32_t*)m->bins.p;
+        P.target = (const float*)m->target.p; P.binpos = (const int4*)m->bins.p;
         P.window = (const float*)m->window.p; P.twiddle = (const float2*)m->twiddle.p;
         P.psd_scale = m->psd_scale;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;

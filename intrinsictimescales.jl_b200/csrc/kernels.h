@@ -50,7 +50,7 @@ struct AbcPsdParams {
     uint32_t k0, k1, c3_noise, c3_init;
     int64_t particle_offset;
     const float* target;        // n_stats
-    const int32_t* bins;        // n_stats, 0-based into psd[2:n2/2]
+    const int4* binpos;         // n_stats: {storage pos of Z[k], of Z[N-k], k, 0}, k = bin + 1
     const float* window;        // n_t Hamming window
     const float2* twiddle;      // n2/2 complex roots exp(-2 pi i k / (n2/2))... see psd_kernels.cu
     double psd_scale;           // 1 / (fs * sum(window^2))
@@ -60,7 +60,8 @@ struct AbcPsdParams {
     double* dist_out;
     double* stats_out;
 };
-size_t abc_psd_smem_bytes(int n_t, int n2, int* chunk_out, int* xs_len_out);
+size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out);
+int psd_fft_pos(int k, int N);
 cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st);
 // standalone: comp_psd_adfriendly on stored data (n_slices x n_t col-major double)
 cudaError_t psd_data_launch(const double* data, int64_t n_slices, int n_t, int n2, int log2_n2,

@@ -29,14 +29,15 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// In-place radix-4 (+ final radix-2) DIF FFT of N complex points in shared memory.
+// In-place radix-4 (+ final radix-2) DIF FFT of N complex points in shared memory (NT threads).
+template <int NT>
 __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* __restrict__ U) {
     const int tid = threadIdx.x;
     int span = N;
     while (span >= 4) {
         const int q = span >> 2;
         const int tstep = (2 * N) / span;          // W_span^j = U[j * tstep]
-        for (int u = tid; u < (N >> 2); u += kThreads) {
+        for (int u = tid; u < (N >> 2); u += NT) {
             const int j = u & (q - 1);
             const int base = (u / q) * span + j;
             const float2 x0 = buf[base], x1 = buf[base + q], x2 = buf[base + 2 * q], x3 = buf[base + 3 * q];
@@ -49,10 +50,13 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* _
             float2 y2 = make_float2(a0.x - a2.x, a0.y - a2.y);
             float2 y3 = make_float2(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
             if (j != 0) {
-                const int t1 = j * tstep;
-                y1 = cmul(y1, tw_lookup(U, t1, N));
-                y2 = cmul(y2, tw_lookup(U, 2 * t1, N));
-                y3 = cmul(y3, tw_lookup(U, 3 * t1, N));
+                // one table read per butterfly: W^2j and W^3j by complex multiplication
+                const float2 w1 = tw_lookup(U, j * tstep, N);
+                const float2 w2 = cmul(w1, w1);
+                const float2 w3 = cmul(w2, w1);
+                y1 = cmul(y1, w1);
+                y2 = cmul(y2, w2);
+                y3 = cmul(y3, w3);
             }
             buf[base] = y0; buf[base + q] = y1; buf[base + 2 * q] = y2; buf[base + 3 * q] = y3;
         }
@@ -60,7 +64,7 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* _
         span = q;
     }
     if (span == 2) {
-        for (int u = tid; u < (N >> 1); u += kThreads) {
+        for (int u = tid; u < (N >> 1); u += NT) {
             const float2 x0 = buf[2 * u], x1 = buf[2 * u + 1];
             buf[2 * u] = make_float2(x0.x + x1.x, x0.y + x1.y);
             buf[2 * u + 1] = make_float2(x0.x - x1.x, x0.y - x1.y);
@@ -70,7 +74,7 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* _
 }
 
 // storage position of frequency k after fft_inplace_dif
-__device__ __forceinline__ int fft_pos(int k, int N) {
+__host__ __device__ __forceinline__ int fft_pos(int k, int N) {
     int p = 0, size = N;
     while (size >= 4) { size >>= 2; p += (k & 3) * size; k >>= 2; }
     if (size == 2) p += (k & 1);
@@ -91,14 +95,31 @@ __device__ __forceinline__ float real_fft_power(const float2* __restrict__ buf, 
     return xr * xr + xi * xi;
 }
 
+// same with the two storage positions precomputed on the host (AbcPsdParams::binpos)
+__device__ __forceinline__ float real_fft_power_at(const float2* __restrict__ buf, int4 bp,
+                                                   const float2* __restrict__ U) {
+    const float2 zk = buf[bp.x];
+    const float2 zn = buf[bp.y];
+    const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);
+    const float dr = 0.5f * (zk.x - zn.x), di = 0.5f * (zk.y + zn.y);
+    const float or_ = di, oi = -dr;
+    const float2 w = __ldg(U + bp.z);
+    const float xr = er + (w.x * or_ - w.y * oi);
+    const float xi = ei + (w.x * oi + w.y * or_);
+    return xr * xr + xi * xi;
+}
+
+constexpr int kPsdThreads = 512;      // fused PSD kernel: 1 CTA/SM (the FFT buffer fills shared memory)
+
 template <bool OSC>
-__global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
+__global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P) {
+    constexpr int NT = kPsdThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats = N float2
     float2* buf = reinterpret_cast<float2*>(smem_raw);
     float* accb = xs + P.xs_len;                                    // n_stats
-    SimShared<kThreads>* sh = reinterpret_cast<SimShared<kThreads>*>(accb + ((P.n_stats + 3) & ~3));
-    __shared__ double red[kWarps];
+    SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb + ((P.n_stats + 3) & ~3));
+    __shared__ double red[NT / 32];
 
     const int tid = threadIdx.x;
     const int64_t particle = blockIdx.x;
@@ -124,25 +145,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
     g.phases = P.phases ? P.phases + pt : nullptr;
     g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;
 
-    for (int b = tid; b < P.n_stats; b += kThreads) accb[b] = 0.f;
+    for (int b = tid; b < P.n_stats; b += NT) accb[b] = 0.f;
 
     for (int trial = 0; trial < P.n_trials; ++trial) {
         // standardised series * data_sd; the reference then adds data_mean and
         // comp_psd_adfriendly removes the mean again (summary.jl:209) - skipped both.
-        simulate_trial<kThreads, false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, 0.0f, sim_cache);
-        for (int i = P.chunk * kThreads + tid; i < P.xs_len; i += kThreads) xs[i] = 0.f;
+        simulate_trial<NT, false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, 0.0f, sim_cache);
+        for (int i = P.chunk * NT + tid; i < P.xs_len; i += NT) xs[i] = 0.f;
         __syncthreads();
-        for (int j = tid; j < P.n_t; j += kThreads) xs[j] *= __ldg(P.window + j);
+        for (int j = tid; j < P.n_t; j += NT) xs[j] *= __ldg(P.window + j);
         __syncthreads();
-        fft_inplace_dif(buf, N, P.twiddle);
-        for (int b = tid; b < P.n_stats; b += kThreads)
-            accb[b] += real_fft_power(buf, __ldg(P.bins + b) + 1, N, P.twiddle);
+        fft_inplace_dif<NT>(buf, N, P.twiddle);
+        for (int b = tid; b < P.n_stats; b += NT)
+            accb[b] += real_fft_power_at(buf, __ldg(P.binpos + b), P.twiddle);
         __syncthreads();
     }
 
     const double sc = P.psd_scale / (double)P.n_trials;
     double local = 0.0;
-    for (int b = tid; b < P.n_stats; b += kThreads) {
+    for (int b = tid; b < P.n_stats; b += NT) {
         const double v = (double)accb[b] * sc;
         if (P.stats_out) P.stats_out[(size_t)particle * P.n_stats + b] = v;
         const double tgt = (double)P.target[b];
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_abc_psd(const AbcPsdParams P) {
     if (tid == 0) {
         double d = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) d += red[w];
+        for (int w = 0; w < NT / 32; ++w) d += red[w];
         P.dist_out[particle] = d / (double)P.n_stats;
     }
 }
@@ -184,19 +205,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_psd_data(const double* __restri
     for (int j = tid; j < n2; j += kThreads)
         xs[j] = (j < n_t) ? (float)((data[s + (size_t)j * n_slices] - mean) * (double)__ldg(window + j)) : 0.f;
     __syncthreads();
-    fft_inplace_dif(buf, N, U);
+    fft_inplace_dif<kThreads>(buf, N, U);
     for (int k = 1 + tid; k < N; k += kThreads)
         out[s + (size_t)(k - 1) * n_slices] = (double)real_fft_power(buf, k, N, U) * psd_scale;
 }
 
-size_t abc_psd_smem_bytes(int n_t, int n2, int* chunk_out, int* xs_len_out) {
-    int c = (n_t + kThreads - 1) / kThreads;
+int psd_fft_pos(int k, int N) { return fft_pos(k, N); }
+
+size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out) {
+    int c = (n_t + kPsdThreads - 1) / kPsdThreads;
     c = (c + 3) & ~3;
     int xs_len = n2;                                   // N float2 = n2 floats
-    if (xs_len < c * kThreads) xs_len = c * kThreads;
+    if (xs_len < c * kPsdThreads) xs_len = c * kPsdThreads;
     *chunk_out = c;
     *xs_len_out = xs_len;
-    return (size_t)xs_len * sizeof(float);            // caller adds accumulators + SimShared
+    return (size_t)xs_len * sizeof(float) + (size_t)((n_stats + 3) & ~3) * sizeof(float) +
+           sizeof(SimShared<kPsdThreads>);
 }
 
 void psd_make_tables(int n_t, int n2, float* window_host, float2* twiddle_host, double* win_ss) {
@@ -218,7 +242,7 @@ cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStr
     void (*kern)(const AbcPsdParams) = osc ? k_abc_psd<true> : k_abc_psd<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)P.n_particles, kThreads, smem, st>>>(P);
+    kern<<<(unsigned)P.n_particles, kPsdThreads, smem, st>>>(P);
     return cudaGetLastError();
 }
 
