@@ -184,6 +184,13 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out);
  * measured with CUDA events on the context stream around each dominant-kernel launch. */
 int itjl_ctx_timing_reset(itjl_ctx* ctx);
 int itjl_ctx_timing_get(itjl_ctx* ctx, int64_t* n_launches, double* total_ms);
+/* Tensor-core self-test: loads `image` (n_bytes of fp16 data, multiple of 16, <= 200 KiB) into shared
+ * memory, issues `n_ops` tcgen05.mma (M = 128, kind::f16) described by ops[4*i .. 4*i+3] =
+ * {A byte offset, B byte offset, TMEM column of D, accumulate flag} with the given no-swizzle
+ * leading / stride byte offsets and instruction descriptor, and returns the 128 x 512 fp32
+ * accumulator block (row-major).  Pins the operand layout the fused ACF kernel relies on. */
+int itjl_tc_probe(itjl_ctx* ctx, const void* image, int64_t n_bytes, const int32_t* ops, int32_t n_ops,
+                  uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t idesc, float* out);
 
 #ifdef __cplusplus
 }

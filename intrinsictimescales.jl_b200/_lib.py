@@ -71,6 +71,7 @@ SIGNATURES = {
     "itjl_fp32_peak": (ctypes.c_int, [_vp, _i32, _vp]),
     "itjl_ctx_timing_reset": (ctypes.c_int, [_vp]),
     "itjl_ctx_timing_get": (ctypes.c_int, [_vp, _vp, _vp]),
+    "itjl_tc_probe": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i32, _u32, _u32, _u32, _vp]),
 }
 
 

@@ -15,12 +15,16 @@ char g_err[512] = {0};
 
 using namespace itjl;
 
+static const bool kTcDefault = false;     // default path of the fused ACF kernel when ITJL_ABC_TC is unset
+
 struct itjl_model {
     itjl_ctx* ctx = nullptr;
     itjl_model_desc d{};
     DevBuf target, mask_bits, n_valid, bins, window, twiddle;
     int mask_words = 0;
     AbcAcfGeometry geo{};
+    AbcTcGeometry tc{};
+    bool use_tc = false;       // lag sums on the tensor cores (abc_tc_kernels.cu)
     // PSD
     int n2 = 0, log2_n2 = 0, psd_chunk = 0, psd_xs_len = 0;
     size_t psd_smem = 0;
@@ -143,6 +147,14 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         if (d.n_stats > d.n_t) { delete m; return fail(ctx, ITJL_ERR_ARG, "n_lags must not exceed n_t"); }
         int g = abc_acf_geometry((int)d.n_t, (int)d.n_stats, ctx->max_smem_optin, &m->geo);
         if (g != 0) { delete m; return fail(ctx, ITJL_ERR_ARG, g == -2 ? "n_lags > 5120 is not supported by the fused ACF kernel" : "trial does not fit in shared memory (n_t too large)"); }
+        // tensor-core lag sums when the lag window fits the 512 TMEM columns (plus a short FFMA tail);
+        // ITJL_ABC_TC=0 forces the FFMA kernel, =1 the tensor-core kernel (error if unsupported), =2 picks
+        // the tensor-core kernel whenever the shape is supported
+        const char* e_tc = getenv("ITJL_ABC_TC");
+        const int want_tc = e_tc ? atoi(e_tc) : -1;
+        const int tcg = abc_tc_geometry((int)d.n_t, (int)d.n_stats, (int)d.n_trials, ctx->max_smem_optin, ctx->sm_count, &m->tc);
+        if (want_tc == 1 && tcg != 0) { delete m; return fail(ctx, ITJL_ERR_ARG, "ITJL_ABC_TC=1 but the tensor-core kernel does not support this shape"); }
+        m->use_tc = (tcg == 0) && (want_tc != 0) && (want_tc >= 1 || kTcDefault);
     }
     if (rc == ITJL_OK && d.missing_mask) {
         m->mask_words = (int)((d.n_t + 31) / 32);
@@ -239,6 +251,28 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
         e = abc_psd_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
+    } else if (m->use_tc) {
+        AbcTcParams P{};
+        const AbcTcGeometry& t = m->tc;
+        P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
+        P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_lags = (int)d.n_stats;
+        P.dt = d.dt; P.update = d.update; P.kind = d.kind; P.distance = d.distance;
+        P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+        P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
+        P.particle_offset = particle_offset;
+        P.target = (const float*)m->target.p;
+        P.mask_bits = (const uint32_t*)m->mask_bits.p; P.n_valid = (const int*)m->n_valid.p;
+        P.mask_words = m->mask_words;
+        P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
+        P.dist_out = dist_dev; P.stats_out = stats_dev;
+        P.groups = t.groups; P.chunk = t.chunk; P.xs_stride = t.xs_stride; P.opnd_offset = t.opnd_offset;
+        P.ksteps = t.ksteps; P.sbo_bytes = t.sbo_bytes;
+        P.used_cols = t.used_cols; P.n_tiles_n = t.n_tiles_n; P.n_last = t.n_last; P.tc_lags = t.tc_lags; P.tail_start = t.tail_start;
+        P.tail_lt = t.tail_lt; P.tail_streams = t.tail_streams; P.tail_tiles_per_stream = t.tail_tiles_per_stream;
+        P.n_time_tiles = t.n_time_tiles;
+        P.tc_scale = t.tc_scale; P.tc_unscale = 1.0f / (t.tc_scale * t.tc_scale);
+        e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.smem_bytes, t.grid,
+                          ctx->stream);
     } else {
         AbcAcfParams P{};
         P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
@@ -452,6 +486,26 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
         if (tf > best) best = tf;
     }
     *tflops_out = best;
+    return ITJL_OK;
+}
+
+int itjl_tc_probe(itjl_ctx* ctx, const void* image, int64_t n_bytes, const int32_t* ops, int32_t n_ops,
+                  uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t idesc, float* out) {
+    if (!ctx || !image || !ops || !out) return fail(ctx, ITJL_ERR_ARG, "itjl_tc_probe: null argument");
+    if (n_bytes < 16 || (n_bytes & 15) || n_bytes > 200 * 1024 || n_ops < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_tc_probe: bad image size / op count");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload(ctx, ctx->data, image, (size_t)n_bytes);
+    if (rc == ITJL_OK) rc = upload(ctx, ctx->scratch, ops, (size_t)n_ops * 4 * sizeof(int32_t));
+    if (rc != ITJL_OK) return rc;
+    const size_t out_bytes = (size_t)128 * 512 * sizeof(float);
+    ITJL_CUDA(ctx, ctx->out.reserve(out_bytes));
+    ITJL_CUDA(ctx, cudaMemsetAsync(ctx->out.p, 0, out_bytes, ctx->stream));
+    cudaError_t e = tc_probe_launch(ctx->data.p, (int)n_bytes, (const int4*)ctx->scratch.p, n_ops, lbo_bytes, sbo_bytes,
+                                    idesc, (float*)ctx->out.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_tc_probe: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ITJL_OK;
 }
 

@@ -111,6 +111,46 @@ cudaError_t acw_tau_launch(const double* acf, int64_t n_rows, int64_t ld, int n_
                            cudaStream_t st);
 int acf_max_reach(int n_t, int max_smem);
 
+// ---- abc_tc_kernels.cu --------------------------------------------------------------
+struct AbcTcGeometry {
+    int groups, chunk, xs_stride, opnd_offset;
+    int rows_total, ksteps, sbo_bytes;
+    int used_cols, n_tiles_n, n_last, tc_lags, tail_start;
+    int tail_lt, tail_streams, tail_tiles_per_stream, n_time_tiles;
+    float tc_scale;
+    int grid;
+    size_t smem_bytes;
+};
+struct AbcTcParams {
+    const double* theta;
+    int64_t n_particles;
+    int n_theta;
+    int n_t, n_trials, n_lags;
+    double dt;
+    int update, kind, distance;
+    uint32_t k0, k1, c3_noise, c3_init;
+    int64_t particle_offset;
+    const float* target;
+    const uint32_t* mask_bits;
+    const int* n_valid;
+    int mask_words;
+    const double* u0;
+    const double* noise;
+    const double* phases;
+    double* dist_out;
+    double* stats_out;
+    // geometry (AbcTcGeometry)
+    int groups, chunk, xs_stride, opnd_offset;
+    int ksteps, sbo_bytes;
+    int used_cols, n_tiles_n, n_last, tc_lags, tail_start;
+    int tail_lt, tail_streams, tail_tiles_per_stream, n_time_tiles;
+    float tc_scale, tc_unscale;
+};
+int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g);
+cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, size_t smem, int grid, cudaStream_t st);
+cudaError_t tc_probe_launch(const void* image_dev, int n_bytes, const int4* ops_dev, int n_ops, uint32_t lbo,
+                            uint32_t sbo, uint32_t idesc, float* out_dev, cudaStream_t st);
+
 // ---- peak_kernels.cu -----------------------------------------------------------------
 cudaError_t fp32_peak_launch(float* sink, int blocks, int iters, cudaStream_t st);
 double fp32_peak_flops_per_launch(int blocks, int iters);

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
+#include "tc05.cuh"
 
 namespace itjl {
 
@@ -82,19 +83,43 @@ struct SimCache {
     bool valid = false;
 };
 
-// Simulate trial `trial` into xs[0 .. chunk*NT) with a CTA of NT threads.  On return (after the
+// Tensor-core sink (TC = true): pass B also emits the series, scaled by the power of two
+// `scale`, as an fp16 hi/lo pair (x = hi + lo to ~22 bits) in the MN-major no-swizzle operand
+// layout of tcgen05.mma (tc05.cuh): sample j = 128 i + a goes to byte (a/8)*sbo + 16 i + 2 (a%8).
+// `wait_bar` guards the operand buffer: it completes when the MMAs that read the previous
+// contents have retired.
+struct TcSink {
+    unsigned char* hi;
+    unsigned char* lo;
+    int sbo;
+    float scale;
+    uint64_t* wait_bar;
+    uint32_t wait_parity;
+    bool write_back;          // also store the fp32 series to xs (needed by the FFMA tail lags)
+};
+
+__device__ __forceinline__ void sim_sync(int bar_id, int nt) {
+    if (bar_id == 0) __syncthreads();
+    else tc::named_bar_sync(bar_id, nt);
+}
+
+// Simulate trial `trial` into xs[0 .. chunk*NT) with NT threads (the whole CTA, or - with
+// `bar_id` != 0 - one NT-thread group of it synchronising on that named barrier; `tid` is the
+// thread's index within the group).  On return (after the
 // caller's __syncthreads()) xs holds
 //   kScaleUnitNorm : (x - mean) / sqrt(sum (x-mean)^2)                (ACF kernels)
 //                    with MISSING: the comp_ac_time_missing centring, masked samples = -m2
 //   kScaleStd      : (x - mean) / std_{n-1} * scale + shift            (PSD kernel, generator)
 //   kScaleRaw      : x                                                 (standardize = false)
 // and zeros for j >= n_t.
-template <int NT, bool MISSING, bool OSC>
+template <int NT, bool MISSING, bool OSC, bool TC = false>
 __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts& oc, int trial,
                                                float* __restrict__ xs, SimShared<NT>* sh, int mode,
-                                               float scale, float shift, SimCache& cache) {
+                                               float scale, float shift, SimCache& cache,
+                                               int tid = threadIdx.x, int bar_id = 0,
+                                               const TcSink* sink = nullptr) {
     constexpr int NW = NT / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     const int j0 = tid * g.chunk;
     const float eps = oc.eps, s = oc.s;
 
@@ -189,7 +214,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
     }
     if (lane == 31) { sh->scanA[warp] = A; sh->scanB[warp] = B; }
-    __syncthreads();
+    sim_sync(bar_id, NT);
     float xw = x0;                                   // state entering this warp's first chunk
     for (int w = 0; w < warp; ++w) xw = fmaf(sh->scanA[w], xw, sh->scanB[w]);
     const float Aprev = __shfl_up_sync(0xffffffffu, A, 1);
@@ -210,7 +235,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         sh->sums[warp][0] = r0; sh->sums[warp][1] = r1;
         sh->sums[warp][2] = r2; sh->sums[warp][3] = r3;
     }
-    __syncthreads();
+    sim_sync(bar_id, NT);
     double SX = 0.0, SXX = 0.0, VX = 0.0, VXX = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
@@ -242,31 +267,56 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     }
 
     // ---- pass B: out = (y + p c - m) r + shift = y r + p (c r) + (shift - m r) -----------
+    if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
     if (j0 < g.n_t) {
         float pb = OSC ? oc.sc : 1.f;
         const float crf = c * rf;
         const float k0 = fmaf(-mf, rf, shift);
-        for (int q = 0; q < g.chunk; q += 4) {
+        constexpr int STEP = TC ? 8 : 4;                 // TC: chunk is a multiple of 8
+        for (int q = 0; q < g.chunk; q += STEP) {
             const int j = j0 + q;
-            float4 v4 = *reinterpret_cast<const float4*>(xs + j);
-            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            float v[STEP];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int h = 0; h < STEP; h += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(xs + j + h);
+                v[h] = v4.x; v[h + 1] = v4.y; v[h + 2] = v4.z; v[h + 3] = v4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < STEP; ++i) {
                 pb = fmaf(-eps, pb, pb);
                 v[i] = fmaf(v[i], rf, fmaf(pb, crf, k0));
             }
-            if (MISSING || j + 3 >= g.n_t) {
+            if (MISSING || j + STEP - 1 >= g.n_t) {
                 uint32_t mbits = 0u;
-                if (MISSING && j < g.n_t) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
+                if (MISSING && j < g.n_t) mbits = (mrow[j >> 5] >> (j & 31)) & (STEP == 8 ? 0xFFu : 0xFu);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < STEP; ++i) {
                     if (MISSING && ((mbits >> i) & 1u)) v[i] = miss_val;
                     if (j + i >= g.n_t) v[i] = 0.f;
                 }
             }
-            *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
+            if (!TC || sink->write_back) {
+#pragma unroll
+                for (int h = 0; h < STEP; h += 4)
+                    *reinterpret_cast<float4*>(xs + j + h) = make_float4(v[h], v[h + 1], v[h + 2], v[h + 3]);
+            }
+            if (TC) {
+                uint32_t hp[4], lp[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float s0 = v[2 * h] * sink->scale, s1 = v[2 * h + 1] * sink->scale;
+                    const __half2 hh = __floats2half2_rn(s0, s1);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                    hp[h] = *reinterpret_cast<const uint32_t*>(&hh);
+                    lp[h] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                const int off = ((j & 127) >> 3) * sink->sbo + (j >> 7) * 16;
+                *reinterpret_cast<uint4*>(sink->hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *reinterpret_cast<uint4*>(sink->lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            }
         }
-    } else {
+    } else if (!TC || sink->write_back) {
         for (int q = 0; q < g.chunk; q += 4)
             *reinterpret_cast<float4*>(xs + j0 + q) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
