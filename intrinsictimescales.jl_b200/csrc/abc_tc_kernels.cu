@@ -16,40 +16,62 @@ namespace itjl {
 // (src/core/abc.jl:174-195) = generate_data + summary_stats (comp_ac_fft / comp_ac_time_missing,
 // src/stats/summary.jl:46-63, 455-484) + distance_function (src/stats/distances.jl:29-53).
 //
-// Lag sums as a Gram product.  With the centred unit-norm series cut into rows of T = 128
-// samples, X[i][a] = x'[128 i + a],
+// Lag sums as a Gram product.  With the centred unit-norm series cut into rows of 128 samples,
+// X[i][a] = x'[128 i + a],
 //     D_s[a][b] = sum_i X[i][a] * X[i+s][b]   =  sum over t = 128 i + a of x'_t x'_{t + 128 s + b - a},
-// so ac[l] = sum over {(s, a, b): 128 s + b - a = l} of D_s[a][b].  Each D_s is one
-// tcgen05.mma chain (M = 128 rows a, N = 128 columns b, K = rows i of every trial of the
-// particle) accumulating in fp32 in tensor memory; 4 tiles = all 512 TMEM columns cover lags
-// 0..384.  Both operands are the SAME shared-memory buffer in the MN-major no-swizzle layout
-// (K rows 16 B apart), the B operand of D_s simply starts s rows later.  x' is fed as an fp16
-// hi/lo pair (hi*hi + hi*lo + lo*hi: ~22-bit operands, fp32 accumulate) - 3 MMAs per tile.
-// Lags beyond the TMEM capacity (n_lags > 385) are summed by the register-tiled FFMA loop of
-// lagsum.cuh on the same fp32 series.
+// so with the "virtual column" v = 128 s + b every accumulator cell (a, v) holds products of lag
+// v - a, and ac[l] = sum of the cells on the diagonal v - a = l.  Each D_s is a tcgen05.mma chain
+// (K = the rows i of the trials) accumulating in fp32 in tensor memory.  Both operands are the
+// SAME shared-memory buffer in the MN-major no-swizzle layout (K rows 16 B apart); the B operand
+// of D_s simply starts s rows later.  x' is fed as an fp16 hi/lo pair (hi*hi + hi*lo + lo*hi:
+// ~22-bit operands) - 3 MMAs per tile and K step.
 //
-// CTA = G simulate groups of 128 threads (one trial each at a time, Philox + blocked scan as in
-// simulate.cuh, named barriers) + one issuer warp.  Persistent: one CTA per SM loops over
-// particles; the issuer's single thread waits for a group's "operands ready" mbarrier, issues
-// that trial's MMAs and commits to the group's "operands free" mbarrier, so the tensor pipe
-// runs under the simulation of the following trials.  Per particle the accumulators are drained
-// once (tcgen05.ld), summed along diagonals through a skewed shared-memory transpose, and the
-// distance is formed in fp64.
+// Tensor-memory plans (128 lanes x 512 columns of fp32):
+//   A  (n_lags <= 385)   tiles s = 0 .. 3, M = 128 (cell row a = TMEM lane), N = 128: lags 0 .. 384.
+//   B  (n_lags <= 449)   the lower-left quadrant of D_0 (a >= 64, b < 64) only holds negative lags
+//      (D_0 is symmetric), so D_0 is issued as two M = 64 MMAs - rows a < 64 x all 128 columns on
+//      the lower 16 lanes of every 32-lane quarter, rows a >= 64 x columns 64 .. 127 on the upper
+//      16 lanes (D address lane offset 16) - and the freed quadrant receives D_4 (rows a >= 64,
+//      b < 64, v = 512 + b): lags up to 448 without touching the CUDA cores.
+//   Lags beyond the plan's reach (<= 60 of them) are summed by the register-tiled FFMA loop of
+//   lagsum.cuh on the fp32 series.
+//
+// Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
+// zero (measured, benchmarks/tc_probe2.py), so a long positive chain loses ~0.5 ulp per product:
+// 1.8e-5 relative over 50 trials x 5000 samples.  The accumulators are therefore drained every
+// `seg_trials` trials (~400 K rows) and the segment sums are added in fp32 registers (round to
+// nearest), which keeps the bias below 3e-6.
+//
+// Warp roles (one persistent CTA per SM):
+//   G simulate groups of 128 threads - one trial each at a time: Philox + blocked scan as in
+//     simulate.cuh on named barriers, operands written as fp16 hi/lo planes;
+//   4 epilogue warps (one per TMEM lane quarter).  Each also issues a quarter of the MMA ops: it
+//     waits for a group's "operands ready" mbarrier, issues its MMAs of that trial (one elected
+//     lane, descriptors warp-uniform) and commits to the group's "operands free" mbarrier; after
+//     the last trial of a segment it commits to "accumulators ready".  All four then tcgen05.ld
+//     the accumulators, sum them along diagonals
+//     through a skewed shared-memory transpose into registers, release the tensor memory, and after
+//     the particle's last segment form the trial mean and the distance in fp64.
+// The tensor pipe and the epilogue therefore run under the simulation of the following trials.
+// (20 warps: the register file is allocated in units of 4 warps, 21 would cap at 80 registers.)
 constexpr int kTcGroupThreads = 128;
 constexpr int kTcMaxGroups = 4;
-constexpr int kTcMaxThreads = kTcGroupThreads * kTcMaxGroups + 32;
+constexpr int kTcEpiThreads = 128;
+constexpr int kTcMaxThreads = kTcGroupThreads * kTcMaxGroups + kTcEpiThreads;   // 20 warps x 96 registers
 constexpr int kTcZFloats = 33 * 32;                 // per-warp skew scratch
-constexpr int kTcBarAll = 8;                        // named barrier over all simulate threads
+constexpr int kTcBarEpi = 8;                        // named barrier over the epilogue warps
+constexpr int kTcLagTab = 512;                      // lag table entries (tensor-core lags < 449)
+constexpr int kTcMaxTail = 64;                      // FFMA tail lags per group row in tailsum
 
-template <bool MISSING, bool OSC>
+template <bool MISSING, bool OSC, bool MIXED>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kTcMaxGroups];
     __shared__ __align__(8) uint64_t bar_empty[kTcMaxGroups];
-    __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty;
+    __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty, bar_tail_full, bar_tail_free;
     __shared__ uint32_t tmem_slot;
     __shared__ SimShared<kTcGroupThreads> shs[kTcMaxGroups];
-    __shared__ double red[kTcMaxGroups * 4];
+    __shared__ double red[4];
 
     const int G = P.groups;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -57,17 +79,22 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     const int op_bytes = 16 * P.sbo_bytes;                       // one fp16 operand plane (hi or lo)
     float* stag = reinterpret_cast<float*>(smem_raw);            // G staging buffers of xs_stride floats
     unsigned char* opnd = smem_raw + (size_t)P.opnd_offset;      // G x {hi, lo} planes
+    float* epi = reinterpret_cast<float*>(smem_raw + (size_t)P.epi_offset);
+    float* lagtab = epi + 4 * kTcZFloats;                        // [kTcLagTab]
+    float* tailsum = lagtab + kTcLagTab;                         // [G][kTcMaxTail]
 
     // ---- one-time setup ------------------------------------------------------------------
     {
         uint4* z = reinterpret_cast<uint4*>(smem_raw);
-        const int n16 = (P.opnd_offset + G * 2 * op_bytes) / 16;
+        const int n16 = (int)(P.smem_bytes / 16);
         for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
-        for (int g = 0; g < G; ++g) { tc::mbar_init(&bar_full[g], kTcGroupThreads); tc::mbar_init(&bar_empty[g], 1); }
-        tc::mbar_init(&bar_acc_full, 1);
-        tc::mbar_init(&bar_acc_empty, (uint32_t)n_sim);
+        for (int g = 0; g < G; ++g) { tc::mbar_init(&bar_full[g], kTcGroupThreads); tc::mbar_init(&bar_empty[g], 4); }
+        tc::mbar_init(&bar_acc_full, 4);
+        tc::mbar_init(&bar_acc_empty, 4);
+        tc::mbar_init(&bar_tail_full, (uint32_t)n_sim);
+        tc::mbar_init(&bar_tail_free, 1);
         tc::fence_mbar_init();
     }
     if (warp == 4 * G) tc::tmem_alloc(&tmem_slot, 512);
@@ -77,49 +104,10 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp == 4 * G) {
-        // ================= MMA issuer (one thread) ==========================================
-        if (lane == 0) {
-            const uint32_t idesc_full = tc::make_idesc_f16_mn(128, 128);
-            const uint32_t idesc_last = tc::make_idesc_f16_mn(128, P.n_last);
-            const uint32_t opnd_addr = tc::smem_u32(opnd);
-            uint32_t it = 0;
-            for (int64_t particle = blockIdx.x; particle < P.n_particles; particle += gridDim.x, ++it) {
-                tc::mbar_wait(&bar_acc_empty, (it & 1u) ^ 1u);   // previous particle drained
-                tc::fence_after_thread_sync();
-                for (int trial = 0; trial < P.n_trials; ++trial) {
-                    const int g = trial % G;
-                    const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
-                    const uint32_t k = it * n_g + (uint32_t)(trial / G);
-                    tc::mbar_wait(&bar_full[g], k & 1u);
-                    tc::fence_after_thread_sync();
-                    const uint32_t hi_addr = opnd_addr + (uint32_t)(g * 2 * op_bytes);
-                    const uint64_t d_hi = tc::make_smem_desc(hi_addr, 128u, (uint32_t)P.sbo_bytes);
-                    const uint64_t d_lo = tc::make_smem_desc(hi_addr + (uint32_t)op_bytes, 128u, (uint32_t)P.sbo_bytes);
-                    for (int ks = 0; ks < P.ksteps; ++ks) {
-                        const uint64_t a_hi = d_hi + (uint64_t)(ks * 16);          // 16 rows x 16 B, in 16 B units
-                        const uint64_t a_lo = d_lo + (uint64_t)(ks * 16);
-                        const uint32_t first = (trial == 0 && ks == 0) ? 0u : 1u;
-                        for (int s = 0; s < P.n_tiles_n; ++s) {
-                            const uint32_t idesc = (s == P.n_tiles_n - 1) ? idesc_last : idesc_full;
-                            const uint32_t d_t = tmem_base + (uint32_t)(128 * s);
-                            const uint64_t b_hi = a_hi + (uint64_t)s, b_lo = a_lo + (uint64_t)s;
-                            tc::mma_f16_ss(d_t, a_hi, b_hi, idesc, first);
-                            tc::mma_f16_ss(d_t, a_hi, b_lo, idesc, 1u);
-                            tc::mma_f16_ss(d_t, a_lo, b_hi, idesc, 1u);
-                        }
-                    }
-                    tc::mma_commit(&bar_empty[g]);                // operands of this trial are free again
-                }
-                tc::mma_commit(&bar_acc_full);                    // accumulators of this particle complete
-            }
-        }
-        __syncwarp();
-    } else {
+    if (warp < 4 * G) {
         // ================= simulate groups ===================================================
         const int g = warp >> 2;
         const int tid_g = tid & (kTcGroupThreads - 1);
-        const int lq = warp & 3;                                  // TMEM lane quarter of this warp
         float* xs = stag + (size_t)g * P.xs_stride;
         SimShared<kTcGroupThreads>* sh = &shs[g];
         const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
@@ -129,6 +117,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         sink.lo = sink.hi + op_bytes;
         sink.sbo = P.sbo_bytes;
         sink.scale = P.tc_scale;
+        sink.unscale = 1.0f / P.tc_scale;
         sink.wait_bar = &bar_empty[g];
         sink.write_back = P.tail_lt > 0;
 
@@ -142,14 +131,10 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         const int tail_row = P.tail_lt * TK;
 
         SimArgs sa;
-        sa.n_t = P.n_t; sa.chunk = P.chunk;
+        sa.n_t = P.n_t; sa.chunk = P.chunk; sa.xs_tstride = P.xs_tstride;
         sa.inv_n = 1.0 / (double)P.n_t; sa.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
         sa.k0 = P.k0; sa.k1 = P.k1; sa.c3_noise = P.c3_noise; sa.c3_init = P.c3_init;
         sa.mask_bits = P.mask_bits; sa.n_valid = P.n_valid; sa.mask_words = P.mask_words;
-
-        const int n_cb = (P.used_cols + 31) / 32;                 // 32-column accumulator blocks
-        float* zs = xs + lq * kTcZFloats;                         // this warp's skew scratch
-        float* tab = xs + 4 * kTcZFloats;                         // this group's diagonal-sum table
 
         uint32_t it = 0;
         for (int64_t particle = blockIdx.x; particle < P.n_particles; particle += gridDim.x, ++it) {
@@ -186,78 +171,179 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 }
             }
 
-            // ---- epilogue: drain the accumulators, diagonal sums, distance ---------------------
-            tc::mbar_wait(&bar_acc_full, it & 1u);
-            tc::fence_after_thread_sync();
-            for (int c = g, slot = 0; c < n_cb; c += G, ++slot) {
-                float v[32];
-                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * lq) << 16) + (uint32_t)(32 * c), v);
+            if (P.tail_lt > 0) {
+                // hand this group's tail-lag sums to the epilogue warps
+                if (tail_active) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) zs[i * 33 + lane] = v[i];
-                __syncwarp();
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int l = 0; l < 32; ++l) {
-                    const float val = zs[((l + lane) & 31) * 33 + l];
-                    if (l + lane < 32) s1 += val; else s2 += val;
+                    for (int j = 0; j < TK; ++j) xs[stream * tail_row + tile * TK + j] = acc[j];
                 }
-                float* t = tab + (slot * 4 + lq) * 64;
-                t[lane] = s1; t[32 + lane] = s2;
-                __syncwarp();
+                tc::named_bar_sync(1 + g, kTcGroupThreads);
+                tc::mbar_wait(&bar_tail_free, (it & 1u) ^ 1u);    // previous particle's sums consumed
+                if (tid_g < tail_row) {
+                    float s = 0.f;
+                    for (int st = 0; st < P.tail_streams; ++st) s += xs[st * tail_row + tid_g];
+                    tailsum[g * kTcMaxTail + tid_g] = s;
+                }
+                tc::named_bar_sync(1 + g, kTcGroupThreads);
+                // the partials may have touched the zero pad behind the series
+                for (int i = P.chunk * kTcGroupThreads + tid_g; i < P.xs_stride; i += kTcGroupThreads) xs[i] = 0.f;
+                tc::mbar_arrive(&bar_tail_full);                  // release: tailsum stores above
+                tc::named_bar_sync(1 + g, kTcGroupThreads);
             }
-            tc::fence_before_thread_sync();
-            tc::mbar_arrive(&bar_acc_empty);                      // TMEM may be overwritten
-            tc::named_bar_sync(kTcBarAll, n_sim);                 // tables complete
+        }
+    } else {
+        // ================= epilogue warps (lane 0 of the first one also issues the MMAs) ========
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int e_tid = tid - 4 * G * 32;                       // 0 .. 127
+        float* zs = epi + q * kTcZFloats;
+        const int e_warp = warp - 4 * G;                          // issues the MMA ops o = e_warp, e_warp + 4, ..
+        const uint32_t opnd_addr = tc::smem_u32(opnd);
+        const int n_cb = (P.used_cols + 31) / 32;                 // 32-column accumulator blocks
+        const double inv_trials = 1.0 / (double)P.n_trials;
 
-            // FFMA tail partials go below the tables (the skew scratch is dead after the barrier)
-            if (tail_active) {
+        uint32_t it = 0, seg_it = 0;
+        for (int64_t particle = blockIdx.x; particle < P.n_particles; particle += gridDim.x, ++it) {
+            // per block: diagonal sums  [0] offset +lane, [1] offset lane - 32; mixed blocks (plan B,
+            // c < 4) keep the two 16-lane halves apart: [2], [3] belong to the upper half
+            float ds[16][2];
+            float du[4][2];
 #pragma unroll
-                for (int j = 0; j < TK; ++j) xs[stream * tail_row + tile * TK + j] = acc[j];
-            }
-            const double inv_trials = 1.0 / (double)P.n_trials;
-            double local = 0.0;
-            for (int k = tid; k < P.tc_lags; k += n_sim) {
-                // lag k = 32 u + r collects block diagonals (c - lq = u, offset r) and (c - lq = u + 1, r - 32)
-                const int u = k >> 5, r = k & 31;
-                float s = 0.f;
+            for (int c = 0; c < 16; ++c) { ds[c][0] = 0.f; ds[c][1] = 0.f; }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c1 = u + q;
-                    if (c1 < n_cb) s += stag[(size_t)(c1 % G) * P.xs_stride + 4 * kTcZFloats + ((c1 / G) * 4 + q) * 64 + r];
-                    const int c2 = u + 1 + q;
-                    if (r > 0 && c2 < n_cb) s += stag[(size_t)(c2 % G) * P.xs_stride + 4 * kTcZFloats + ((c2 / G) * 4 + q) * 64 + 32 + r];
+            for (int c = 0; c < 4; ++c) { du[c][0] = 0.f; du[c][1] = 0.f; }
+
+            for (int seg0 = 0; seg0 < P.n_trials; seg0 += P.seg_trials, ++seg_it) {
+                {
+                    // ---- issue this warp's share of the segment's MMAs as the groups deliver their trials
+                    // (whole warp, convergent: one elected lane issues, see tc05.cuh) ----------------
+                    tc::mbar_wait(&bar_acc_empty, (seg_it & 1u) ^ 1u);   // previous segment drained
+                    tc::fence_after_thread_sync();
+                    const int seg1 = min(seg0 + P.seg_trials, P.n_trials);
+                    for (int trial = seg0; trial < seg1; ++trial) {
+                        const int g = trial % G;
+                        const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
+                        const uint32_t k = it * n_g + (uint32_t)(trial / G);
+                        tc::mbar_wait(&bar_full[g], k & 1u);
+                        tc::fence_after_thread_sync();
+                        const uint32_t hi_addr = opnd_addr + (uint32_t)(g * 2 * op_bytes);
+                        const uint64_t d_hi = tc::make_smem_desc(hi_addr, 128u, (uint32_t)P.sbo_bytes);
+                        const uint64_t d_lo = tc::make_smem_desc(hi_addr + (uint32_t)op_bytes, 128u, (uint32_t)P.sbo_bytes);
+                        for (int ks = 0; ks < P.ksteps; ++ks) {
+                            const uint32_t first = (trial == seg0 && ks == 0) ? 0u : 1u;
+                            for (int o = e_warp; o < P.n_ops; o += 4) {
+                                // descriptor start addresses are in 16 B units: K rows are 16 B apart
+                                const uint64_t a_off = (uint64_t)(ks * 16 + P.op_a_off[o]);
+                                const uint64_t b_off = (uint64_t)(ks * 16 + P.op_b_off[o]);
+                                const uint32_t d_t = tmem_base + P.op_taddr[o];
+                                const uint32_t idesc = P.op_idesc[o];
+                                tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_hi + b_off, idesc, first);
+                                tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_lo + b_off, idesc, 1u);
+                                tc::mma_f16_ss_elect(d_t, d_lo + a_off, d_hi + b_off, idesc, 1u);
+                            }
+                        }
+                        tc::mma_commit_elect(&bar_empty[g]);      // operands of this trial are free again
+                    }
+                    tc::mma_commit_elect(&bar_acc_full);          // accumulators of this segment complete
                 }
-                const double v = (double)(s * P.tc_unscale) * inv_trials;
+                __syncwarp();
+                tc::mbar_wait(&bar_acc_full, seg_it & 1u);
+                tc::fence_after_thread_sync();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c < n_cb) {
+                        float v[32];
+                        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) zs[i * 33 + lane] = v[i];
+                        __syncwarp();
+                        if (MIXED && c < 4) {
+                            float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                const int col = (r + lane) & 31;
+                                const float lo = zs[col * 33 + r];
+                                const float up = zs[col * 33 + 16 + r];
+                                if (r + lane < 32) { s1 += lo; u1 += up; } else { s2 += lo; u2 += up; }
+                            }
+                            ds[c][0] += s1; ds[c][1] += s2; du[c][0] += u1; du[c][1] += u2;
+                        } else {
+                            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                            for (int l = 0; l < 32; ++l) {
+                                const float val = zs[((l + lane) & 31) * 33 + l];
+                                if (l + lane < 32) s1 += val; else s2 += val;
+                            }
+                            ds[c][0] += s1; ds[c][1] += s2;
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_acc_empty);   // this quarter of the tensor memory is free
+            }
+
+            // ---- fold the diagonal sums into the lag table (fixed order: deterministic) ----------
+            for (int ph = 0; ph < 4; ++ph) {
+                if (ph == q) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        if (c < n_cb) {
+                            if (MIXED && c < 4) {
+                                const int base = 32 * c - 16 * q;
+                                const int ubase = base - 64 + (c < 2 ? 512 : 0);
+                                int k = base + lane;
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
+                                __syncwarp();
+                                k -= 32;
+                                if (lane >= 17 && k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
+                                __syncwarp();
+                                k = ubase + lane;
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += du[c][0];
+                                __syncwarp();
+                                k -= 32;
+                                if (lane >= 17 && k >= 0 && k < P.tc_lags) lagtab[k] += du[c][1];
+                                __syncwarp();
+                            } else {
+                                int k = 32 * (c - q) + lane;
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
+                                __syncwarp();
+                                k -= 32;
+                                if (lane >= 1 && k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+                tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
+            }
+
+            // ---- trial mean, distance ---------------------------------------------------------------
+            if (P.tail_lt > 0) tc::mbar_wait(&bar_tail_full, it & 1u);
+            double local = 0.0;
+            for (int k = e_tid; k < P.n_lags; k += kTcEpiThreads) {
+                float s;
+                if (k < P.tc_lags) {
+                    s = lagtab[k] * P.tc_unscale;
+                } else {
+                    s = 0.f;
+                    for (int gg = 0; gg < G; ++gg) s += tailsum[gg * kTcMaxTail + (k - P.tail_start)];
+                }
+                const double v = (double)s * inv_trials;
                 if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
                 const double tgt = (double)P.target[k];
                 const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
                 local += e * e;
             }
-            if (P.tail_lt > 0) {
-                tc::named_bar_sync(kTcBarAll, n_sim);             // partials of every group written
-                for (int k = P.tc_lags + tid; k < P.n_lags; k += n_sim) {
-                    const int kk = k - P.tail_start;
-                    float s = 0.f;
-                    for (int gg = 0; gg < G; ++gg)
-                        for (int st = 0; st < P.tail_streams; ++st) s += stag[(size_t)gg * P.xs_stride + st * tail_row + kk];
-                    const double v = (double)s * inv_trials;
-                    if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
-                    const double tgt = (double)P.target[k];
-                    const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
-                    local += e * e;
-                }
-            }
             local = warp_sum(local);
-            if (lane == 0) red[warp] = local;
-            tc::named_bar_sync(kTcBarAll, n_sim);
-            if (tid == 0) {
-                double d = 0.0;
-                for (int w = 0; w < 4 * G; ++w) d += red[w];
-                P.dist_out[particle] = d / (double)P.n_lags;
+            if (lane == 0) red[q] = local;
+            tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
+            if (e_tid == 0) {
+                P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
+                if (P.tail_lt > 0) tc::mbar_arrive(&bar_tail_free);
             }
-            // the scratch / tables / partials may have touched the zero pad behind the series
-            for (int i = P.chunk * kTcGroupThreads + tid_g; i < P.xs_stride; i += kTcGroupThreads) xs[i] = 0.f;
-            tc::named_bar_sync(kTcBarAll, n_sim);
+            for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0.f;
+            tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
         }
     }
 
@@ -271,19 +357,43 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
 int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g) {
     if (n_t < 16 || n_lags < 1 || n_lags > n_t) return -1;
     const int max_tail = 60;                               // more FFMA tail lags than this: not worth it
-    int used_cols = ((n_lags + 127) + 15) & ~15;
-    if (used_cols > 512) used_cols = 512;
-    if (used_cols < 32) used_cols = 32;
-    g->used_cols = used_cols;
-    g->tc_lags = (n_lags < used_cols - 127) ? n_lags : used_cols - 127;
+    const int rows_data = (n_t + 127) / 128;
+    g->ksteps = (rows_data + 15) / 16;
+    int max_shift;
+    g->n_ops = 0;
+    auto add_op = [&](int a_blk, int b_row, int b_blk, int m, int n, int lane, int col) {
+        const int o = g->n_ops++;
+        g->op_a_blk[o] = a_blk; g->op_b_row[o] = b_row; g->op_b_blk[o] = b_blk;
+        g->op_idesc[o] = tc::make_idesc_f16_mn(m, n);
+        g->op_taddr[o] = ((uint32_t)lane << 16) | (uint32_t)col;
+    };
+    if (n_lags <= 385) {
+        // plan A
+        int used_cols = ((n_lags + 127) + 15) & ~15;
+        if (used_cols < 32) used_cols = 32;
+        g->used_cols = used_cols;
+        g->tc_lags = n_lags;
+        g->mixed = 0;
+        const int n_tiles = (used_cols + 127) / 128;
+        for (int s = 0; s < n_tiles; ++s) add_op(0, s, 0, 128, s == n_tiles - 1 ? used_cols - 128 * s : 128, 0, 128 * s);
+        max_shift = n_tiles - 1;
+    } else {
+        // plan B
+        int n4 = ((n_lags - 385) + 15) & ~15;
+        if (n4 > 64) n4 = 64;
+        g->used_cols = 512;
+        g->tc_lags = n_lags < 385 + n4 ? n_lags : 385 + n4;
+        g->mixed = 1;
+        add_op(0, 0, 0, 64, 128, 0, 0);                    // D_0 rows a < 64
+        add_op(8, 0, 8, 64, 64, 16, 64);                   // D_0 rows a >= 64, columns 64 .. 127
+        for (int s = 1; s < 4; ++s) add_op(0, s, 0, 128, 128, 0, 128 * s);
+        add_op(8, 4, 0, 64, n4, 16, 0);                    // D_4 rows a >= 64, columns < n4
+        max_shift = 4;
+    }
     g->tail_start = g->tc_lags & ~3;                       // FFMA tail window starts 16 B aligned
     const int tail = (n_lags > g->tc_lags) ? n_lags - g->tail_start : 0;
     if (tail > max_tail) return -2;
-    g->n_tiles_n = (used_cols + 127) / 128;
-    g->n_last = used_cols - 128 * (g->n_tiles_n - 1);
-    const int rows_data = (n_t + 127) / 128;
-    g->ksteps = (rows_data + 15) / 16;
-    g->rows_total = 16 * g->ksteps + g->n_tiles_n - 1;
+    g->rows_total = 16 * g->ksteps + max_shift;
     if ((g->rows_total & 1) == 0) g->rows_total++;           // odd row count: 16 B blocks spread over all banks
     g->sbo_bytes = g->rows_total * 16;
     int c = (n_t + kTcGroupThreads - 1) / kTcGroupThreads;
@@ -292,8 +402,12 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     g->n_time_tiles = (n_t + TT - 1) / TT;
     g->tail_lt = (tail + TK - 1) / TK;
     g->tail_streams = 0; g->tail_tiles_per_stream = 0;
-    int need = g->chunk * kTcGroupThreads;
+    // staging: private per-thread chunks; padded by 4 floats (conflict-free float4 accesses) unless the
+    // FFMA tail needs the series in order
+    g->xs_tstride = g->tail_lt > 0 ? g->chunk : g->chunk + 4;
+    int need = g->xs_tstride * kTcGroupThreads;
     if (g->tail_lt > 0) {
+        if (g->tail_lt * TK > kTcMaxTail) return -2;
         g->tail_streams = kTcGroupThreads / g->tail_lt;
         if (g->tail_streams > g->n_time_tiles) g->tail_streams = g->n_time_tiles;
         g->tail_tiles_per_stream = (g->n_time_tiles + g->tail_streams - 1) / g->tail_streams;
@@ -303,47 +417,60 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         const int part = g->tail_streams * g->tail_lt * TK;
         if (need < part) need = part;
     }
-    const int n_cb = (used_cols + 31) / 32;
+    const int stride = (need + 31) & ~31;
     const size_t opnd = (size_t)2 * 16 * g->sbo_bytes;
-    const size_t fixed = 1024;                              // alignment slack
+    const size_t epi = (size_t)(4 * kTcZFloats + kTcLagTab + kTcMaxGroups * kTcMaxTail) * sizeof(float);
     int groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
     for (; groups >= 1; --groups) {
-        const int slots = (n_cb + groups - 1) / groups;
-        int stride = need;
-        const int scratch = 4 * kTcZFloats + slots * 4 * 64;
-        if (stride < scratch) stride = scratch;
-        stride = (stride + 31) & ~31;
-        const size_t total = (size_t)groups * ((size_t)stride * sizeof(float) + opnd) + fixed;
-        if ((int64_t)total <= (int64_t)max_smem - 6 * 1024) {   // static shared (barriers, scan) stays below 6 KB
+        const size_t opnd_off = ((size_t)groups * stride * sizeof(float) + 127) & ~(size_t)127;
+        const size_t epi_off = (opnd_off + (size_t)groups * opnd + 127) & ~(size_t)127;
+        const size_t total = (epi_off + epi + 15) & ~(size_t)15;
+        if ((int64_t)total + 1024 <= (int64_t)max_smem - 4 * 1024) {   // static shared (barriers, scan) stays below 4 KB
             g->groups = groups; g->xs_stride = stride;
-            g->opnd_offset = (int)(((size_t)groups * stride * sizeof(float) + 127) & ~(size_t)127);
-            g->smem_bytes = (size_t)g->opnd_offset + (size_t)groups * opnd;
+            g->opnd_offset = (int)opnd_off; g->epi_offset = (int)epi_off;
+            g->smem_bytes = total;
             break;
         }
     }
     if (groups < 1) return -3;
+    // trials per accumulator segment: ~768 K rows (truncation bias ~6.8e-9 per K row at lags with
+    // ac ~ 1, measured at C5: 2.3e-6 / 4.8e-6 / 1.7e-5 for 384 / 768 / 2496 rows), a multiple of the
+    // group count
+    const int rows_trial = 16 * g->ksteps;
+    int seg = (768 + rows_trial / 2) / rows_trial;
+    seg = (seg / g->groups) * g->groups;
+    if (seg < g->groups) seg = g->groups;
+    const char* e_seg = getenv("ITJL_TC_SEG");
+    if (e_seg && atoi(e_seg) > 0) seg = atoi(e_seg);
+    g->seg_trials = seg;
     int p2 = 1; while (p2 * p2 < n_t) p2 <<= 1;                 // power of two near sqrt(n_t): series ~ N(0,1)
     g->tc_scale = (float)p2;
     g->grid = sm_count;
     return 0;
 }
 
-cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, size_t smem, int grid, cudaStream_t st) {
-    void (*kern)(const AbcTcParams) =
-        missing ? (osc ? k_abc_acf_tc<true, true> : k_abc_acf_tc<true, false>)
-                : (osc ? k_abc_acf_tc<false, true> : k_abc_acf_tc<false, false>);
+cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, bool mixed, size_t smem, int grid,
+                          cudaStream_t st) {
+    void (*kern)(const AbcTcParams);
+    if (mixed)
+        kern = missing ? (osc ? k_abc_acf_tc<true, true, true> : k_abc_acf_tc<true, false, true>)
+                       : (osc ? k_abc_acf_tc<false, true, true> : k_abc_acf_tc<false, false, true>);
+    else
+        kern = missing ? (osc ? k_abc_acf_tc<true, true, false> : k_abc_acf_tc<true, false, false>)
+                       : (osc ? k_abc_acf_tc<false, true, false> : k_abc_acf_tc<false, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if ((int64_t)grid > P.n_particles) grid = (int)P.n_particles;
-    kern<<<grid, kTcGroupThreads * P.groups + 32, smem, st>>>(P);
+    kern<<<grid, kTcGroupThreads * P.groups + kTcEpiThreads, smem, st>>>(P);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
 // Probe: copy a caller-built fp16 shared-memory image, issue the listed tcgen05.mma ops
-// (M = 128, one thread), drain the whole 128 x 512 fp32 accumulator block to `out`.
+// (one thread), drain the whole 128 x 512 fp32 accumulator block to `out`.
 // Used by tests/test_gpu_tc_probe.py to check the MN-major no-swizzle layout, the row-shifted
-// B operand and the instruction descriptor against exact integer Gram products.
+// B operand, the M = 64 lane mapping and the instruction descriptor against exact integer Gram
+// products.  ops[i] = {A byte offset, B byte offset, TMEM address offset (lane << 16 | column), accumulate}.
 __global__ void __launch_bounds__(128, 1) k_tc_probe(const uint4* __restrict__ image, int n_vec16,
                                                      const int4* __restrict__ ops, int n_ops, uint32_t lbo,
                                                      uint32_t sbo, uint32_t idesc, float* __restrict__ out) {

@@ -15,7 +15,7 @@ char g_err[512] = {0};
 
 using namespace itjl;
 
-static const bool kTcDefault = false;     // default path of the fused ACF kernel when ITJL_ABC_TC is unset
+static const bool kTcDefault = true;      // default path of the fused ACF kernel when ITJL_ABC_TC is unset
 
 struct itjl_model {
     itjl_ctx* ctx = nullptr;
@@ -265,14 +265,22 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.mask_words = m->mask_words;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
-        P.groups = t.groups; P.chunk = t.chunk; P.xs_stride = t.xs_stride; P.opnd_offset = t.opnd_offset;
+        P.groups = t.groups; P.chunk = t.chunk; P.xs_tstride = t.xs_tstride; P.xs_stride = t.xs_stride;
+        P.opnd_offset = t.opnd_offset; P.epi_offset = t.epi_offset;
         P.ksteps = t.ksteps; P.sbo_bytes = t.sbo_bytes;
-        P.used_cols = t.used_cols; P.n_tiles_n = t.n_tiles_n; P.n_last = t.n_last; P.tc_lags = t.tc_lags; P.tail_start = t.tail_start;
+        P.used_cols = t.used_cols; P.tc_lags = t.tc_lags; P.tail_start = t.tail_start; P.seg_trials = t.seg_trials;
         P.tail_lt = t.tail_lt; P.tail_streams = t.tail_streams; P.tail_tiles_per_stream = t.tail_tiles_per_stream;
         P.n_time_tiles = t.n_time_tiles;
+        P.n_ops = t.n_ops;
+        for (int o = 0; o < t.n_ops; ++o) {
+            P.op_a_off[o] = (uint32_t)(t.op_a_blk[o] * (t.sbo_bytes / 16));
+            P.op_b_off[o] = (uint32_t)(t.op_b_row[o] + t.op_b_blk[o] * (t.sbo_bytes / 16));
+            P.op_idesc[o] = t.op_idesc[o]; P.op_taddr[o] = t.op_taddr[o];
+        }
         P.tc_scale = t.tc_scale; P.tc_unscale = 1.0f / (t.tc_scale * t.tc_scale);
-        e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.smem_bytes, t.grid,
-                          ctx->stream);
+        P.smem_bytes = t.smem_bytes;
+        e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,
+                          t.smem_bytes, t.grid, ctx->stream);
     } else {
         AbcAcfParams P{};
         P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;

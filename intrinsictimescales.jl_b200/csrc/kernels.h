@@ -112,11 +112,16 @@ cudaError_t acw_tau_launch(const double* acf, int64_t n_rows, int64_t ld, int n_
 int acf_max_reach(int n_t, int max_smem);
 
 // ---- abc_tc_kernels.cu --------------------------------------------------------------
+constexpr int kTcMaxOps = 6;
 struct AbcTcGeometry {
-    int groups, chunk, xs_stride, opnd_offset;
+    int groups, chunk, xs_tstride, xs_stride, opnd_offset, epi_offset;
     int rows_total, ksteps, sbo_bytes;
-    int used_cols, n_tiles_n, n_last, tc_lags, tail_start;
+    int used_cols, tc_lags, tail_start, mixed, seg_trials;
     int tail_lt, tail_streams, tail_tiles_per_stream, n_time_tiles;
+    // MMA ops of one K step: A / B operand start (8-row MN block, K-row shift), shape, TMEM address
+    int n_ops;
+    int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
+    uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
     float tc_scale;
     int grid;
     size_t smem_bytes;
@@ -140,14 +145,19 @@ struct AbcTcParams {
     double* dist_out;
     double* stats_out;
     // geometry (AbcTcGeometry)
-    int groups, chunk, xs_stride, opnd_offset;
+    int groups, chunk, xs_tstride, xs_stride, opnd_offset, epi_offset;
     int ksteps, sbo_bytes;
-    int used_cols, n_tiles_n, n_last, tc_lags, tail_start;
+    int used_cols, tc_lags, tail_start, seg_trials;
     int tail_lt, tail_streams, tail_tiles_per_stream, n_time_tiles;
+    int n_ops;
+    uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
+    uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
     float tc_scale, tc_unscale;
+    size_t smem_bytes;
 };
 int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g);
-cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, size_t smem, int grid, cudaStream_t st);
+cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, bool mixed, size_t smem, int grid,
+                          cudaStream_t st);
 cudaError_t tc_probe_launch(const void* image_dev, int n_bytes, const int4* ops_dev, int n_ops, uint32_t lbo,
                             uint32_t sbo, uint32_t idesc, float* out_dev, cudaStream_t st);
 

@@ -32,22 +32,27 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// ((r >> 9) + 0.5) * 2^-23 : exact in fp32, in (0, 1)
+// ((r >> 9) + 0.5) * 2^-23 : exact in fp32, in (0, 1).  Built without an integer->float
+// conversion: 0x3F800000 | (r >> 9) is the float 1 + (r >> 9) 2^-23 in [1, 2), and subtracting
+// 1 - 2^-24 is exact (the result is an odd multiple of 2^-24 below 1).
+__device__ __forceinline__ float u12(uint32_t r) {
+    return __uint_as_float(0x3F800000u | (r >> 9));
+}
 __device__ __forceinline__ float u01(uint32_t r) {
-    return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
+    return u12(r) - 0.99999994f;
 }
 
 // Box-Muller on the SFU: lg2.approx / sqrt.approx / sin.approx / cos.approx (absolute error of
 // a draw ~5e-7, far below the 1e-5 parity tolerance; the distribution is unaffected).
 // z0 = R cos(2 pi v), z1 = R sin(2 pi v), R = sqrt(-2 ln u); the angle is folded to
 // theta = 2 pi v - pi in (-pi, pi), where MUFU.SIN/COS are most accurate: cos(2 pi v) = -cos(theta).
+// With w = u12(rb) = 1 + v - 2^-24:  theta = 2 pi w - 3 pi + 2 pi 2^-24.
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
     const float u = u01(ra);
-    const float v = u01(rb);
     float l2, rad, s, c;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));
-    const float th = fmaf(v, 6.283185307179586f, -3.141592653589793f);
+    const float th = fmaf(u12(rb), 6.283185307179586f, -9.424777586262351f);
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
     z0 = -rad * c;

@@ -66,6 +66,8 @@ struct SimArgs {
     double inv_n;             // 1 / n_t
     float sqrt_nm1;           // sqrt(n_t - 1)
     int chunk;                // samples per thread (multiple of 4, chunk * NT >= n_t)
+    int xs_tstride = 0;       // TC sink only: floats between the staging chunks of consecutive threads
+                              // (chunk, or chunk + 4 to spread the float4 accesses over all banks)
     uint32_t k0, k1;          // Philox key (seed)
     uint32_t c3_noise, c3_init;
     uint32_t particle;        // global particle index (low 32 bits)
@@ -92,7 +94,7 @@ struct TcSink {
     unsigned char* hi;
     unsigned char* lo;
     int sbo;
-    float scale;
+    float scale, unscale;     // power of two and its reciprocal
     uint64_t* wait_bar;
     uint32_t wait_parity;
     bool write_back;          // also store the fp32 series to xs (needed by the FFMA tail lags)
@@ -121,6 +123,9 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     constexpr int NW = NT / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const int j0 = tid * g.chunk;
+    // staging position of this thread's chunk: linear (series order) unless the tensor-core sink
+    // keeps a private padded layout
+    float* __restrict__ xc = xs + (TC ? tid * g.xs_tstride : j0);
     const float eps = oc.eps, s = oc.s;
 
     // per-trial initial state and phase (stream 1, block 0)
@@ -199,7 +204,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                     }
                 }
             }
-            *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(xc + q) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
     if (need_p_sums) { cache.Sp = Sp; cache.Spp = Spp; cache.valid = true; }
@@ -267,7 +272,12 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     }
 
     // ---- pass B: out = (y + p c - m) r + shift = y r + p (c r) + (shift - m r) -----------
-    if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
+    if (TC) {
+        // the operands carry the power-of-two factor `scale`: fold it into the affine map
+        const float sc = sink->scale;
+        rf *= sc; miss_val *= sc; shift *= sc;
+        tc::mbar_wait(sink->wait_bar, sink->wait_parity);
+    }
     if (j0 < g.n_t) {
         float pb = OSC ? oc.sc : 1.f;
         const float crf = c * rf;
@@ -278,7 +288,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
             float v[STEP];
 #pragma unroll
             for (int h = 0; h < STEP; h += 4) {
-                const float4 v4 = *reinterpret_cast<const float4*>(xs + j + h);
+                const float4 v4 = *reinterpret_cast<const float4*>(xc + q + h);
                 v[h] = v4.x; v[h + 1] = v4.y; v[h + 2] = v4.z; v[h + 3] = v4.w;
             }
 #pragma unroll
@@ -295,19 +305,25 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                     if (j + i >= g.n_t) v[i] = 0.f;
                 }
             }
-            if (!TC || sink->write_back) {
+            if (!TC) {
 #pragma unroll
                 for (int h = 0; h < STEP; h += 4)
                     *reinterpret_cast<float4*>(xs + j + h) = make_float4(v[h], v[h + 1], v[h + 2], v[h + 3]);
             }
             if (TC) {
+                if (sink->write_back) {                  // unscaled fp32 series in series order (FFMA tail lags)
+                    const float us = sink->unscale;
+#pragma unroll
+                    for (int h = 0; h < STEP; h += 4)
+                        *reinterpret_cast<float4*>(xs + j + h) =
+                            make_float4(v[h] * us, v[h + 1] * us, v[h + 2] * us, v[h + 3] * us);
+                }
                 uint32_t hp[4], lp[4];
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    const float s0 = v[2 * h] * sink->scale, s1 = v[2 * h + 1] * sink->scale;
-                    const __half2 hh = __floats2half2_rn(s0, s1);
+                    const __half2 hh = __floats2half2_rn(v[2 * h], v[2 * h + 1]);
                     const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                    const __half2 ll = __floats2half2_rn(v[2 * h] - hf.x, v[2 * h + 1] - hf.y);
                     hp[h] = *reinterpret_cast<const uint32_t*>(&hh);
                     lp[h] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
