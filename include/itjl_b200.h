@@ -126,6 +126,10 @@ int itjl_abc_distances_dev(itjl_model* model, const double* theta_dev, int64_t n
 /* Algorithmic work of one itjl_abc_distances call, for roofline accounting:
  * flops_per_sample = 2*n_lags + 8 for the direct lag-sum kernels. */
 int itjl_model_work(const itjl_model* model, double* flops_per_sample, int64_t* samples_per_particle);
+/* Which fused kernel itjl_abc_distances launches for this model ("k_abc_acf_tc", "k_abc_acf", "k_abc_psd";
+ * `name_out` holds >= 32 bytes) and the tensor-core flops it EXECUTES per OU sample (fp16 hi/lo split,
+ * tile and K padding included; 0 for the CUDA-core kernels) - the algorithmic figure is itjl_model_work's. */
+int itjl_model_kernel_info(const itjl_model* model, char* name_out, double* tensor_flops_per_sample);
 
 /* ---- OU generator ----------------------------------------------------------------- */
 /* generate_ou_process(tau, true_D, dt, duration, num_trials; standardize)

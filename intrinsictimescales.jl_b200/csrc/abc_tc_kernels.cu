@@ -39,8 +39,8 @@ namespace itjl {
 // Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
 // zero (measured, benchmarks/tc_probe2.py), so a long positive chain loses ~0.5 ulp per product:
 // 1.8e-5 relative over 50 trials x 5000 samples.  The accumulators are therefore drained every
-// `seg_trials` trials (~400 K rows) and the segment sums are added in fp32 registers (round to
-// nearest), which keeps the bias below 3e-6.
+// `seg_trials` trials (~768 K rows) and the segment sums are added in fp32 registers (round to
+// nearest), which keeps the bias below 5e-6.
 //
 // Warp roles (one persistent CTA per SM):
 //   G simulate groups of 128 threads - one trial each at a time: Philox + blocked scan as in

@@ -221,6 +221,22 @@ int itjl_model_work(const itjl_model* m, double* flops_per_sample, int64_t* samp
     return ITJL_OK;
 }
 
+int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_flops_per_sample) {
+    if (!m || !name_out || !tensor_flops_per_sample) return fail(m ? m->ctx : nullptr, ITJL_ERR_ARG, "itjl_model_kernel_info: null argument");
+    *tensor_flops_per_sample = 0.0;
+    if (m->d.summary == ITJL_SUMMARY_PSD) { snprintf(name_out, 32, "k_abc_psd"); return ITJL_OK; }
+    if (!m->use_tc) { snprintf(name_out, 32, "k_abc_acf"); return ITJL_OK; }
+    snprintf(name_out, 32, "k_abc_acf_tc");
+    double f = 0.0;
+    for (int o = 0; o < m->tc.n_ops; ++o) {
+        const uint32_t id = m->tc.op_idesc[o];
+        const double M = (double)(((id >> 24) & 0x1Fu) << 4), N = (double)(((id >> 17) & 0x3Fu) << 3);
+        f += 2.0 * M * N * 16.0;
+    }
+    *tensor_flops_per_sample = f * 3.0 * m->tc.ksteps / (double)m->d.n_t;
+    return ITJL_OK;
+}
+
 }  // extern "C"
 
 // Launch the fused kernel for one batch; every pointer is a device pointer (or null).

@@ -149,6 +149,14 @@ class GpuModel:
         self.ctx.check(_lib.lib().itjl_model_work(self._h, ctypes.byref(f), ctypes.byref(s)))
         return f.value, s.value
 
+    def kernel_info(self):
+        """(name of the fused kernel this model launches, tensor-core flops executed per OU sample)."""
+        import ctypes
+        name = ctypes.create_string_buffer(32)
+        f = ctypes.c_double(0.0)
+        self.ctx.check(_lib.lib().itjl_model_kernel_info(self._h, name, ctypes.byref(f)))
+        return name.value.decode(), f.value
+
     def distances(self, theta, seed=0, generation=0, particle_offset=0, u0=None, noise=None,
                   phases=None, return_stats=False):
         """d[i] = generate_data_and_reduce(model, theta[i, :]) for a batch."""

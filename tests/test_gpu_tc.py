@@ -1,0 +1,183 @@
+"""GPU parity of the tensor-core (tcgen05 / TMEM) fused ACF kernel: the operand-layout probe, and
+k_abc_acf_tc against the fp64 oracle and against the CUDA-core kernel k_abc_acf on the same noise."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import models as omodels
+from oracle import ou as oou
+
+pytestmark = pytest.mark.gpu
+
+DT = 0.002
+ACF_TOL = 1e-5        # north_star (1): ACF within 1e-5 (values in [-1, 1])
+SBO = 256             # probe images: one K step (16 rows x 16 B) per 8-wide MN block
+REGION = 16 * SBO
+
+
+def idesc(m, n):
+    return (1 << 4) | (1 << 15) | (1 << 16) | ((n >> 3) << 17) | ((m >> 4) << 24)
+
+
+def probe(pkg, ctx, img, ops, lbo, sbo, idsc):
+    out = np.zeros((128, 512), dtype=np.float32)
+    ops = np.ascontiguousarray(np.asarray(ops, dtype=np.int32).reshape(-1, 4))
+    ctx.check(pkg._lib.lib().itjl_tc_probe(ctx.handle, img.ctypes.data_as(ctypes.c_void_p), img.nbytes,
+                                           ops.ctypes.data_as(ctypes.c_void_p), len(ops), lbo, sbo, idsc,
+                                           out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def test_probe_row_shifted_gram_is_exact(pkg, ctx):
+    """MN-major no-swizzle operands, B = the same buffer started s K-rows later: integer Gram
+    products X[:rows]^T X[s:s+rows] come back exactly (what the lag sums are built on)."""
+    T, ksteps, n_shift = 128, 2, 4
+    rows = 16 * ksteps
+    rows_total = rows + n_shift - 1
+    rng = np.random.default_rng(0)
+    x = rng.integers(-4, 5, size=rows_total * T).astype(np.float64)
+    sbo = rows_total * 16
+    img = np.zeros(16 * sbo // 2, dtype=np.float16)
+    j = np.arange(x.size)
+    i, a = j // T, j % T
+    img[((a // 8) * sbo + i * 16 + (a % 8) * 2) // 2] = x
+    X = x.reshape(rows_total, T)
+    ops = [[k * 256, (k * 16 + s) * 16, 128 * s, 1 if k > 0 else 0] for k in range(ksteps) for s in range(n_shift)]
+    out = probe(pkg, ctx, img, ops, 128, sbo, idesc(128, 128))
+    for s in range(n_shift):
+        assert np.array_equal(out[:, 128 * s:128 * (s + 1)], X[:rows].T @ X[s:s + rows])
+
+
+def test_probe_m64_lane_mapping_and_lane_offset(pkg, ctx):
+    """An M = 64 MMA writes row r to TMEM lane 32 (r / 16) + r % 16 (+ the D address' lane offset);
+    tensor-memory plan B of k_abc_acf_tc puts rows a >= 64 of D_0 and D_4 on the upper 16 lanes."""
+    img = np.zeros(2 * REGION // 2, dtype=np.float16)
+    a = np.arange(128)
+    img[((a // 8) * SBO + (a % 8) * 2) // 2] = a + 1                       # A[k=0][a] = a + 1
+    img[(REGION + (a // 8) * SBO + (a % 8) * 2) // 2] = 1.0                # B[k=0][b] = 1
+    out = probe(pkg, ctx, img, [[0, REGION, 0, 0], [8 * SBO, REGION, (16 << 16) | 0, 0]], 128, SBO, idesc(64, 32))
+    r = np.arange(64)
+    lanes = 32 * (r // 16) + r % 16
+    assert np.array_equal(out[lanes, 0], r + 1.0)              # rows 0..63 on the lower half lanes
+    assert np.array_equal(out[lanes + 16, 0], r + 65.0)        # A started 8 blocks later, lane offset 16
+    assert np.array_equal(out[lanes, 31], r + 1.0)
+
+
+def test_probe_accumulator_truncates_toward_zero(pkg, ctx):
+    """Documents why k_abc_acf_tc drains its accumulators every segment: products are aligned to the
+    fp32 accumulator and truncated toward zero (not rounded to nearest), also within one MMA."""
+    img = np.zeros(4 * REGION // 2, dtype=np.float16)
+    a = np.arange(128)
+    pos = lambda region, k: (region * REGION + (a // 8) * SBO + k * 16 + (a % 8) * 2) // 2
+    img[pos(2, 0)] = 4096.0
+    img[pos(3, 0)] = np.where(a % 2 == 0, 4096.0, -4096.0)                  # D = +-2^24
+    img[pos(0, 0)] = 1.75
+    img[pos(1, 0)] = np.where(a % 2 == 0, 1.0, -1.0)
+    out = probe(pkg, ctx, img, [[2 * REGION, 3 * REGION, 0, 0], [0, REGION, 0, 1]], 128, SBO, idesc(128, 32))
+    assert out[0, 0] == 2.0 ** 24 and out[0, 1] == -2.0 ** 24             # RN would give +-(2^24 + 2)
+    for k in range(16):
+        img[pos(0, k)] = 0.25
+        img[pos(1, k)] = 1.0
+    out = probe(pkg, ctx, img, [[2 * REGION, 3 * REGION, 0, 0], [0, REGION, 0, 1]], 128, SBO, idesc(128, 32))
+    assert out[0, 0] == 2.0 ** 24                                           # 16 x 0.25 = 4 is lost term by term
+
+
+def _models(pkg, n_t, n_trials, n_lags, missing=False, seed=3):
+    data = oou.generate_ou_process(0.3, 1.0, DT, n_t * DT, n_trials, seed=seed, n_t=n_t)
+    t = DT * np.arange(1, n_t + 1)
+    if missing:
+        rng = np.random.default_rng(seed)
+        for r in range(n_trials):
+            s = rng.integers(0, n_t - n_t // 10)
+            data[r, s:s + n_t // 10] = np.nan
+        om = omodels.one_timescale_with_missing_model(data, t, prior=[omodels.Uniform(0.05, 5)], n_lags=n_lags)
+        mk = lambda: pkg.one_timescale_with_missing_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)], n_lags=n_lags)
+    else:
+        om = omodels.one_timescale_model(data, t, prior=[omodels.Uniform(0.05, 5)], n_lags=n_lags)
+        mk = lambda: pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)], n_lags=n_lags)
+    return om, mk
+
+
+def _gpu_models(mk, ctx):
+    """(tensor-core model, CUDA-core model): the kernel is chosen at itjl_model_create (ITJL_ABC_TC)."""
+    old = os.environ.get("ITJL_ABC_TC")
+    try:
+        os.environ["ITJL_ABC_TC"] = "1"
+        g_tc = mk().gpu_model(ctx)
+        os.environ["ITJL_ABC_TC"] = "0"
+        g_ff = mk().gpu_model(ctx)
+    finally:
+        if old is None:
+            os.environ.pop("ITJL_ABC_TC", None)
+        else:
+            os.environ["ITJL_ABC_TC"] = old
+    assert g_tc.kernel_info()[0] == "k_abc_acf_tc" and g_tc.kernel_info()[1] > 0
+    assert g_ff.kernel_info() == ("k_abc_acf", 0.0)
+    return g_tc, g_ff
+
+
+# (n_t, n_trials, n_lags): tensor-memory plan A with 1..4 tiles, plan B (M = 64 split, 5th tile), plan B
+# plus FFMA tail lags, several accumulator segments (21 and 50 trials), fewer trials than groups
+SHAPES = [(1000, 5, 37), (601, 3, 20), (2500, 1, 300), (5000, 2, 385), (5000, 2, 386), (5000, 4, 414),
+          (5000, 21, 449), (5000, 3, 470), (3000, 50, 200), (5000, 50, 414)]
+
+
+@pytest.mark.parametrize("n_t,n_trials,n_lags", SHAPES)
+def test_tc_kernel_matches_oracle_and_cuda_core_kernel(pkg, ctx, n_t, n_trials, n_lags):
+    om, mk = _models(pkg, n_t, n_trials, n_lags)
+    g_tc, g_ff = _gpu_models(mk, ctx)
+    rng = np.random.default_rng(n_t + n_lags)
+    theta = np.array([[0.3], [4.9], [0.05], [1.2]])
+    P = theta.shape[0]
+    u0 = rng.standard_normal((P, n_trials))
+    noise = rng.standard_normal((P, n_trials, n_t))
+    d_tc, s_tc = g_tc.distances(theta, u0=u0, noise=noise, return_stats=True)
+    d_ff, s_ff = g_ff.distances(theta, u0=u0, noise=noise, return_stats=True)
+    for i in range(P):
+        ac = omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i]))
+        assert np.max(np.abs(s_tc[i] - ac)) <= ACF_TOL, (i, np.max(np.abs(s_tc[i] - ac)))
+        d_ref = np.mean((ac - om.data_sum_stats) ** 2)
+        assert abs(d_tc[i] - d_ref) <= 2 * np.sqrt(d_ref) * ACF_TOL + ACF_TOL ** 2 + 1e-5 * d_ref
+    assert np.max(np.abs(s_tc - s_ff)) <= ACF_TOL
+    # Philox mode: same stream in both kernels, same batching invariance
+    th = rng.uniform(0.05, 5.0, size=(40, 1))
+    a = g_tc.distances(th, seed=11, generation=2)
+    b = g_ff.distances(th, seed=11, generation=2)
+    assert np.all(np.abs(a - b) <= 2 * np.sqrt(np.maximum(b, 0)) * ACF_TOL + ACF_TOL ** 2 + 1e-5 * b)
+    parts = np.concatenate([g_tc.distances(th[:13], seed=11, generation=2),
+                            g_tc.distances(th[13:], seed=11, generation=2, particle_offset=13)])
+    assert np.array_equal(parts, a)                         # persistent-CTA scheduling does not leak into results
+
+
+def test_tc_kernel_missing_data_variant(pkg, ctx):
+    n_t, n_trials = 5000, 6
+    om, mk = _models(pkg, n_t, n_trials, None, missing=True)
+    g_tc, g_ff = _gpu_models(mk, ctx)
+    rng = np.random.default_rng(4)
+    theta = np.array([[0.3], [2.0], [0.07]])
+    u0 = rng.standard_normal((3, n_trials)); noise = rng.standard_normal((3, n_trials, n_t))
+    d_tc, s_tc = g_tc.distances(theta, u0=u0, noise=noise, return_stats=True)
+    d_ff, s_ff = g_ff.distances(theta, u0=u0, noise=noise, return_stats=True)
+    assert om.missing_mask.any()
+    for i in range(3):
+        ac = omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i]))
+        assert np.max(np.abs(s_tc[i] - ac)) <= ACF_TOL
+    assert np.max(np.abs(s_tc - s_ff)) <= ACF_TOL
+
+
+def test_unsupported_shapes_fall_back_to_cuda_core_kernel(pkg, ctx):
+    """n_lags beyond the tensor-memory plans + 60 tail lags: ITJL_ABC_TC unset picks k_abc_acf,
+    ITJL_ABC_TC=1 refuses."""
+    om, mk = _models(pkg, 2500, 1, 700)
+    old = os.environ.pop("ITJL_ABC_TC", None)
+    try:
+        assert mk().gpu_model(ctx).kernel_info()[0] == "k_abc_acf"
+        os.environ["ITJL_ABC_TC"] = "1"
+        with pytest.raises(pkg.ItjlError):
+            mk().gpu_model(ctx)
+    finally:
+        os.environ.pop("ITJL_ABC_TC", None)
+        if old is not None:
+            os.environ["ITJL_ABC_TC"] = old
