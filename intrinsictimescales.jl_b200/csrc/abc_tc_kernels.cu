@@ -3,7 +3,6 @@
 #include <stdlib.h>
 
 #include "kernels.h"
-#include "lagsum.cuh"
 #include "simulate.cuh"
 #include "tc05.cuh"
 
@@ -33,8 +32,7 @@ namespace itjl {
 //      the lower 16 lanes of every 32-lane quarter, rows a >= 64 x columns 64 .. 127 on the upper
 //      16 lanes (D address lane offset 16) - and the freed quadrant receives D_4 (rows a >= 64,
 //      b < 64, v = 512 + b): lags up to 448 without touching the CUDA cores.
-//   Lags beyond the plan's reach (<= 60 of them) are summed by the register-tiled FFMA loop of
-//   lagsum.cuh on the fp32 series.
+//   Longer lag windows run on the CUDA-core kernel k_abc_acf.
 //
 // Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
 // zero (measured, benchmarks/tc_probe2.py), so a long positive chain loses ~0.5 ulp per product:
@@ -44,44 +42,41 @@ namespace itjl {
 //
 // Warp roles (one persistent CTA per SM):
 //   G simulate groups of 128 threads - one trial each at a time: Philox + blocked scan as in
-//     simulate.cuh on named barriers, operands written as fp16 hi/lo planes;
+//     simulate.cuh on named barriers.  A group owns two operand buffers (fp16 hi/lo planes) and
+//     alternates between them; pass A parks its fp32 values inside the buffer and pass B converts
+//     them in place, so there is no staging buffer and the group only ever waits for the MMAs of
+//     the trial BEFORE the last one - drains and MMA latency are hidden behind a whole trial.
 //   4 epilogue warps (one per TMEM lane quarter).  Each also issues a quarter of the MMA ops: it
-//     waits for a group's "operands ready" mbarrier, issues its MMAs of that trial (one elected
-//     lane, descriptors warp-uniform) and commits to the group's "operands free" mbarrier; after
+//     waits for a buffer's "operands ready" mbarrier, issues its MMAs of that trial (one elected
+//     lane, descriptors warp-uniform) and commits to the buffer's "operands free" mbarrier; after
 //     the last trial of a segment it commits to "accumulators ready".  All four then tcgen05.ld
-//     the accumulators, sum them along diagonals
-//     through a skewed shared-memory transpose into registers, release the tensor memory, and after
-//     the particle's last segment form the trial mean and the distance in fp64.
-// The tensor pipe and the epilogue therefore run under the simulation of the following trials.
+//     the accumulators, sum them along diagonals by lane rotation (shuffles) into registers,
+//     release the tensor memory, and after the particle's last segment form the trial
+//     mean and the distance in fp64.
 // (20 warps: the register file is allocated in units of 4 warps, 21 would cap at 80 registers.)
 constexpr int kTcGroupThreads = 128;
 constexpr int kTcMaxGroups = 4;
 constexpr int kTcEpiThreads = 128;
 constexpr int kTcMaxThreads = kTcGroupThreads * kTcMaxGroups + kTcEpiThreads;   // 20 warps x 96 registers
-constexpr int kTcZFloats = 33 * 32;                 // per-warp skew scratch
 constexpr int kTcBarEpi = 8;                        // named barrier over the epilogue warps
-constexpr int kTcLagTab = 512;                      // lag table entries (tensor-core lags < 449)
-constexpr int kTcMaxTail = 64;                      // FFMA tail lags per group row in tailsum
+constexpr int kTcLagTab = 512;                      // lag table entries (tensor-core lags <= 449)
 
 template <bool MISSING, bool OSC, bool MIXED>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[kTcMaxGroups];
-    __shared__ __align__(8) uint64_t bar_empty[kTcMaxGroups];
-    __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty, bar_tail_full, bar_tail_free;
+    __shared__ __align__(8) uint64_t bar_full[kTcMaxGroups][2];      // [group][buffer] operands ready
+    __shared__ __align__(8) uint64_t bar_empty[kTcMaxGroups][2];     // [group][buffer] operands consumed
+    __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty;
     __shared__ uint32_t tmem_slot;
     __shared__ SimShared<kTcGroupThreads> shs[kTcMaxGroups];
     __shared__ double red[4];
 
     const int G = P.groups;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_sim = kTcGroupThreads * G;
     const int op_bytes = 16 * P.sbo_bytes;                       // one fp16 operand plane (hi or lo)
-    float* stag = reinterpret_cast<float*>(smem_raw);            // G staging buffers of xs_stride floats
-    unsigned char* opnd = smem_raw + (size_t)P.opnd_offset;      // G x {hi, lo} planes
+    unsigned char* opnd = smem_raw;                              // [G][2 buffers][hi, lo] planes
     float* epi = reinterpret_cast<float*>(smem_raw + (size_t)P.epi_offset);
-    float* lagtab = epi + 4 * kTcZFloats;                        // [kTcLagTab]
-    float* tailsum = lagtab + kTcLagTab;                         // [G][kTcMaxTail]
+    float* lagtab = epi;                                         // [kTcLagTab]
 
     // ---- one-time setup ------------------------------------------------------------------
     {
@@ -90,11 +85,10 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
-        for (int g = 0; g < G; ++g) { tc::mbar_init(&bar_full[g], kTcGroupThreads); tc::mbar_init(&bar_empty[g], 4); }
+        for (int g = 0; g < G; ++g)
+            for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_full[g][b], kTcGroupThreads); tc::mbar_init(&bar_empty[g][b], 4); }
         tc::mbar_init(&bar_acc_full, 4);
         tc::mbar_init(&bar_acc_empty, 4);
-        tc::mbar_init(&bar_tail_full, (uint32_t)n_sim);
-        tc::mbar_init(&bar_tail_free, 1);
         tc::fence_mbar_init();
     }
     if (warp == 4 * G) tc::tmem_alloc(&tmem_slot, 512);
@@ -108,30 +102,16 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         // ================= simulate groups ===================================================
         const int g = warp >> 2;
         const int tid_g = tid & (kTcGroupThreads - 1);
-        float* xs = stag + (size_t)g * P.xs_stride;
         SimShared<kTcGroupThreads>* sh = &shs[g];
         const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
+        unsigned char* my_opnd = opnd + (size_t)g * 4 * op_bytes;
 
         TcSink sink;
-        sink.hi = opnd + (size_t)g * 2 * op_bytes;
-        sink.lo = sink.hi + op_bytes;
         sink.sbo = P.sbo_bytes;
         sink.scale = P.tc_scale;
-        sink.unscale = 1.0f / P.tc_scale;
-        sink.wait_bar = &bar_empty[g];
-        sink.write_back = P.tail_lt > 0;
-
-        // FFMA tail lags [tc_lags, n_lags)
-        const int tile = P.tail_lt > 0 ? tid_g % P.tail_lt : 0;
-        const int stream = P.tail_lt > 0 ? tid_g / P.tail_lt : 0;
-        const bool tail_active = P.tail_lt > 0 && stream < P.tail_streams;
-        const int tail_k0 = P.tail_start + tile * TK;          // multiple of 4: float4 window loads
-        const int tile_begin = stream * P.tail_tiles_per_stream;
-        const int tile_end = min(tile_begin + P.tail_tiles_per_stream, P.n_time_tiles);
-        const int tail_row = P.tail_lt * TK;
 
         SimArgs sa;
-        sa.n_t = P.n_t; sa.chunk = P.chunk; sa.xs_tstride = P.xs_tstride;
+        sa.n_t = P.n_t; sa.chunk = P.chunk;
         sa.inv_n = 1.0 / (double)P.n_t; sa.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
         sa.k0 = P.k0; sa.k1 = P.k1; sa.c3_noise = P.c3_noise; sa.c3_init = P.c3_init;
         sa.mask_bits = P.mask_bits; sa.n_valid = P.n_valid; sa.mask_words = P.mask_words;
@@ -150,52 +130,26 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             sa.u0 = P.u0 ? P.u0 + pt : nullptr;
             sa.noise = P.noise ? P.noise + pt * P.n_t : nullptr;
             sa.phases = P.phases ? P.phases + pt : nullptr;
-
-            float acc[TK];
-#pragma unroll
-            for (int j = 0; j < TK; ++j) acc[j] = 0.f;
             SimCache sim_cache;
 
             uint32_t mine = 0;
             for (int trial = g; trial < P.n_trials; trial += G, ++mine) {
                 const uint32_t k = it * n_g + mine;               // this group's trial counter
-                sink.wait_parity = (k & 1u) ^ 1u;                 // MMAs of trial k-1 retired
-                simulate_trial<kTcGroupThreads, MISSING, OSC, true>(sa, oc, trial, xs, sh, kScaleUnitNorm, 1.0f, 0.0f,
+                const uint32_t buf = k & 1u;                      // operand buffers alternate
+                sink.hi = my_opnd + (size_t)buf * 2 * op_bytes;
+                sink.lo = sink.hi + op_bytes;
+                sink.wait_bar = &bar_empty[g][buf];
+                sink.wait_parity = ((k >> 1) & 1u) ^ 1u;          // MMAs of trial k - 2 (same buffer) retired
+                simulate_trial<kTcGroupThreads, MISSING, OSC, true>(sa, oc, trial, nullptr, sh, kScaleUnitNorm, 1.0f, 0.0f,
                                                                     sim_cache, tid_g, 1 + g, &sink);
                 tc::fence_proxy_async_smem();                     // my operand stores -> async proxy
-                tc::mbar_arrive(&bar_full[g]);
-                if (P.tail_lt > 0) {
-                    tc::named_bar_sync(1 + g, kTcGroupThreads);
-                    if (tail_active && tile_begin < tile_end) acf_tiles(xs, acc, tail_k0, tile_begin, tile_end);
-                    tc::named_bar_sync(1 + g, kTcGroupThreads);   // series is rewritten by the next trial
-                }
-            }
-
-            if (P.tail_lt > 0) {
-                // hand this group's tail-lag sums to the epilogue warps
-                if (tail_active) {
-#pragma unroll
-                    for (int j = 0; j < TK; ++j) xs[stream * tail_row + tile * TK + j] = acc[j];
-                }
-                tc::named_bar_sync(1 + g, kTcGroupThreads);
-                tc::mbar_wait(&bar_tail_free, (it & 1u) ^ 1u);    // previous particle's sums consumed
-                if (tid_g < tail_row) {
-                    float s = 0.f;
-                    for (int st = 0; st < P.tail_streams; ++st) s += xs[st * tail_row + tid_g];
-                    tailsum[g * kTcMaxTail + tid_g] = s;
-                }
-                tc::named_bar_sync(1 + g, kTcGroupThreads);
-                // the partials may have touched the zero pad behind the series
-                for (int i = P.chunk * kTcGroupThreads + tid_g; i < P.xs_stride; i += kTcGroupThreads) xs[i] = 0.f;
-                tc::mbar_arrive(&bar_tail_full);                  // release: tailsum stores above
-                tc::named_bar_sync(1 + g, kTcGroupThreads);
+                tc::mbar_arrive(&bar_full[g][buf]);
             }
         }
     } else {
-        // ================= epilogue warps (lane 0 of the first one also issues the MMAs) ========
+        // ================= epilogue warps (each also issues a quarter of the MMA ops) ============
         const int q = warp & 3;                                   // TMEM lane quarter this warp may read
         const int e_tid = tid - 4 * G * 32;                       // 0 .. 127
-        float* zs = epi + q * kTcZFloats;
         const int e_warp = warp - 4 * G;                          // issues the MMA ops o = e_warp, e_warp + 4, ..
         const uint32_t opnd_addr = tc::smem_u32(opnd);
         const int n_cb = (P.used_cols + 31) / 32;                 // 32-column accumulator blocks
@@ -204,7 +158,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         uint32_t it = 0, seg_it = 0;
         for (int64_t particle = blockIdx.x; particle < P.n_particles; particle += gridDim.x, ++it) {
             // per block: diagonal sums  [0] offset +lane, [1] offset lane - 32; mixed blocks (plan B,
-            // c < 4) keep the two 16-lane halves apart: [2], [3] belong to the upper half
+            // c < 4) keep the two 16-lane halves apart: du belongs to the upper half
             float ds[16][2];
             float du[4][2];
 #pragma unroll
@@ -223,9 +177,10 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                         const int g = trial % G;
                         const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
                         const uint32_t k = it * n_g + (uint32_t)(trial / G);
-                        tc::mbar_wait(&bar_full[g], k & 1u);
+                        const uint32_t buf = k & 1u;
+                        tc::mbar_wait(&bar_full[g][buf], (k >> 1) & 1u);
                         tc::fence_after_thread_sync();
-                        const uint32_t hi_addr = opnd_addr + (uint32_t)(g * 2 * op_bytes);
+                        const uint32_t hi_addr = opnd_addr + (uint32_t)((g * 2 + (int)buf) * 2 * op_bytes);
                         const uint64_t d_hi = tc::make_smem_desc(hi_addr, 128u, (uint32_t)P.sbo_bytes);
                         const uint64_t d_lo = tc::make_smem_desc(hi_addr + (uint32_t)op_bytes, 128u, (uint32_t)P.sbo_bytes);
                         for (int ks = 0; ks < P.ksteps; ++ks) {
@@ -241,41 +196,43 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                                 tc::mma_f16_ss_elect(d_t, d_lo + a_off, d_hi + b_off, idesc, 1u);
                             }
                         }
-                        tc::mma_commit_elect(&bar_empty[g]);      // operands of this trial are free again
+                        tc::mma_commit_elect(&bar_empty[g][buf]); // this warp's reads of the buffer have retired
                     }
-                    tc::mma_commit_elect(&bar_acc_full);          // accumulators of this segment complete
+                    tc::mma_commit_elect(&bar_acc_full);          // this warp's accumulators of the segment complete
                 }
                 __syncwarp();
                 tc::mbar_wait(&bar_acc_full, seg_it & 1u);
                 tc::fence_after_thread_sync();
+                // ---- drain: diagonal sums by lane rotation.  Lane t receives column i of TMEM lane
+                // (t + i) mod 32, i.e. the cell of diagonal (column - row) = -t, or 32 - t once t + i wraps ----
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     if (c < n_cb) {
                         float v[32];
                         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) zs[i * 33 + lane] = v[i];
-                        __syncwarp();
                         if (MIXED && c < 4) {
-                            float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f;
+                            // rows: lanes 0..15 = lower strip (a = 16 q + lane), 16..31 = upper strip
+                            float l0 = 0.f, l1 = 0.f, u0 = 0.f, u1 = 0.f;
 #pragma unroll
-                            for (int r = 0; r < 16; ++r) {
-                                const int col = (r + lane) & 31;
-                                const float lo = zs[col * 33 + r];
-                                const float up = zs[col * 33 + 16 + r];
-                                if (r + lane < 32) { s1 += lo; u1 += up; } else { s2 += lo; u2 += up; }
+                            for (int i = 0; i < 32; ++i) {
+                                const int src = lane + i;
+                                const float x = __shfl_sync(0xffffffffu, v[i], src & 31);
+                                const bool upper = (src & 16) != 0, wrap = src >= 32;
+                                l0 += (!upper && !wrap) ? x : 0.f;
+                                l1 += (!upper && wrap) ? x : 0.f;
+                                u0 += (upper && !wrap) ? x : 0.f;
+                                u1 += (upper && wrap) ? x : 0.f;
                             }
-                            ds[c][0] += s1; ds[c][1] += s2; du[c][0] += u1; du[c][1] += u2;
+                            ds[c][0] += l0; ds[c][1] += l1; du[c][0] += u0; du[c][1] += u1;
                         } else {
                             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                            for (int l = 0; l < 32; ++l) {
-                                const float val = zs[((l + lane) & 31) * 33 + l];
-                                if (l + lane < 32) s1 += val; else s2 += val;
+                            for (int i = 0; i < 32; ++i) {
+                                const float x = __shfl_sync(0xffffffffu, v[i], (lane + i) & 31);
+                                if (lane + i < 32) s1 += x; else s2 += x;
                             }
                             ds[c][0] += s1; ds[c][1] += s2;
                         }
-                        __syncwarp();
                     }
                 }
                 tc::fence_before_thread_sync();
@@ -290,26 +247,26 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                     for (int c = 0; c < 16; ++c) {
                         if (c < n_cb) {
                             if (MIXED && c < 4) {
-                                const int base = 32 * c - 16 * q;
-                                const int ubase = base - 64 + (c < 2 ? 512 : 0);
-                                int k = base + lane;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
+                                // lower strip: lag = 32 c - 16 q - lane (+ 32 after the wrap);
+                                // upper strip: rows a = 48 + 16 q + lane, columns of D_4 (c < 2) start at v = 512
+                                int k = 32 * c - 16 * q - lane;
+                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][0];
                                 __syncwarp();
-                                k -= 32;
-                                if (lane >= 17 && k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
+                                k += 32;
+                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][1];
                                 __syncwarp();
-                                k = ubase + lane;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += du[c][0];
+                                k = 32 * c - 48 - 16 * q - lane + (c < 2 ? 512 : 0);
+                                if (k >= 0 && k < P.n_lags) lagtab[k] += du[c][0];
                                 __syncwarp();
-                                k -= 32;
-                                if (lane >= 17 && k >= 0 && k < P.tc_lags) lagtab[k] += du[c][1];
+                                k += 32;
+                                if (k >= 0 && k < P.n_lags) lagtab[k] += du[c][1];
                                 __syncwarp();
                             } else {
-                                int k = 32 * (c - q) + lane;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
+                                int k = 32 * (c - q) - lane;
+                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][0];
                                 __syncwarp();
-                                k -= 32;
-                                if (lane >= 1 && k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
+                                k += 32;
+                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][1];
                                 __syncwarp();
                             }
                         }
@@ -319,17 +276,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             }
 
             // ---- trial mean, distance ---------------------------------------------------------------
-            if (P.tail_lt > 0) tc::mbar_wait(&bar_tail_full, it & 1u);
             double local = 0.0;
             for (int k = e_tid; k < P.n_lags; k += kTcEpiThreads) {
-                float s;
-                if (k < P.tc_lags) {
-                    s = lagtab[k] * P.tc_unscale;
-                } else {
-                    s = 0.f;
-                    for (int gg = 0; gg < G; ++gg) s += tailsum[gg * kTcMaxTail + (k - P.tail_start)];
-                }
-                const double v = (double)s * inv_trials;
+                const double v = (double)(lagtab[k] * P.tc_unscale) * inv_trials;
                 if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
                 const double tgt = (double)P.target[k];
                 const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
@@ -338,10 +287,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             local = warp_sum(local);
             if (lane == 0) red[q] = local;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
-            if (e_tid == 0) {
-                P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
-                if (P.tail_lt > 0) tc::mbar_arrive(&bar_tail_free);
-            }
+            if (e_tid == 0) P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
             for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0.f;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
         }
@@ -353,10 +299,32 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     if (warp == 4 * G) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// Bank conflicts (excess 128-byte wavefronts) of the simulate groups' 16-byte operand accesses for a
+// given MN-block stride: thread tid touches sample tid * chunk + q.
+static int tc_store_conflicts(int sbo_bytes, int chunk) {
+    int excess = 0;
+    for (int q = 0; q < chunk; q += 8) {
+        for (int w = 0; w < kTcGroupThreads / 32; ++w) {
+            for (int quarter = 0; quarter < 4; ++quarter) {           // 8 lanes x 16 B per wavefront
+                int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int l = 0; l < 8; ++l) {
+                    const int j = (w * 32 + quarter * 8 + l) * chunk + q;
+                    const int off = ((j & 127) >> 3) * sbo_bytes + (j >> 7) * 16;
+                    used[(off >> 4) & 7]++;
+                }
+                int mx = 0;
+                for (int b = 0; b < 8; ++b) mx = used[b] > mx ? used[b] : mx;
+                excess += mx - 1;
+            }
+        }
+    }
+    return excess;
+}
+
 // Geometry of the tensor-core kernel; returns 0 when the configuration is supported.
 int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g) {
     if (n_t < 16 || n_lags < 1 || n_lags > n_t) return -1;
-    const int max_tail = 60;                               // more FFMA tail lags than this: not worth it
+    if (n_lags > 449) return -2;                           // beyond the tensor-memory plans
     const int rows_data = (n_t + 127) / 128;
     g->ksteps = (rows_data + 15) / 16;
     int max_shift;
@@ -372,17 +340,14 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         int used_cols = ((n_lags + 127) + 15) & ~15;
         if (used_cols < 32) used_cols = 32;
         g->used_cols = used_cols;
-        g->tc_lags = n_lags;
         g->mixed = 0;
         const int n_tiles = (used_cols + 127) / 128;
         for (int s = 0; s < n_tiles; ++s) add_op(0, s, 0, 128, s == n_tiles - 1 ? used_cols - 128 * s : 128, 0, 128 * s);
         max_shift = n_tiles - 1;
     } else {
         // plan B
-        int n4 = ((n_lags - 385) + 15) & ~15;
-        if (n4 > 64) n4 = 64;
+        const int n4 = ((n_lags - 385) + 15) & ~15;        // <= 64
         g->used_cols = 512;
-        g->tc_lags = n_lags < 385 + n4 ? n_lags : 385 + n4;
         g->mixed = 1;
         add_op(0, 0, 0, 64, 128, 0, 0);                    // D_0 rows a < 64
         add_op(8, 0, 8, 64, 64, 16, 64);                   // D_0 rows a >= 64, columns 64 .. 127
@@ -390,49 +355,32 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         add_op(8, 4, 0, 64, n4, 16, 0);                    // D_4 rows a >= 64, columns < n4
         max_shift = 4;
     }
-    g->tail_start = g->tc_lags & ~3;                       // FFMA tail window starts 16 B aligned
-    const int tail = (n_lags > g->tc_lags) ? n_lags - g->tail_start : 0;
-    if (tail > max_tail) return -2;
-    g->rows_total = 16 * g->ksteps + max_shift;
-    if ((g->rows_total & 1) == 0) g->rows_total++;           // odd row count: 16 B blocks spread over all banks
-    g->sbo_bytes = g->rows_total * 16;
     int c = (n_t + kTcGroupThreads - 1) / kTcGroupThreads;
     g->chunk = (c + 7) & ~7;
-    // FFMA tail
-    g->n_time_tiles = (n_t + TT - 1) / TT;
-    g->tail_lt = (tail + TK - 1) / TK;
-    g->tail_streams = 0; g->tail_tiles_per_stream = 0;
-    // staging: private per-thread chunks; padded by 4 floats (conflict-free float4 accesses) unless the
-    // FFMA tail needs the series in order
-    g->xs_tstride = g->tail_lt > 0 ? g->chunk : g->chunk + 4;
-    int need = g->xs_tstride * kTcGroupThreads;
-    if (g->tail_lt > 0) {
-        if (g->tail_lt * TK > kTcMaxTail) return -2;
-        g->tail_streams = kTcGroupThreads / g->tail_lt;
-        if (g->tail_streams > g->n_time_tiles) g->tail_streams = g->n_time_tiles;
-        g->tail_tiles_per_stream = (g->n_time_tiles + g->tail_streams - 1) / g->tail_streams;
-        g->tail_streams = (g->n_time_tiles + g->tail_tiles_per_stream - 1) / g->tail_tiles_per_stream;
-        const int reach = (g->n_time_tiles + 2) * TT + g->tail_start + g->tail_lt * TK + TT;   // furthest window read
-        if (need < reach) need = reach;
-        const int part = g->tail_streams * g->tail_lt * TK;
-        if (need < part) need = part;
-    }
-    const int stride = (need + 31) & ~31;
-    const size_t opnd = (size_t)2 * 16 * g->sbo_bytes;
-    const size_t epi = (size_t)(4 * kTcZFloats + kTcLagTab + kTcMaxGroups * kTcMaxTail) * sizeof(float);
-    int groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
-    for (; groups >= 1; --groups) {
-        const size_t opnd_off = ((size_t)groups * stride * sizeof(float) + 127) & ~(size_t)127;
-        const size_t epi_off = (opnd_off + (size_t)groups * opnd + 127) & ~(size_t)127;
-        const size_t total = (epi_off + epi + 15) & ~(size_t)15;
-        if ((int64_t)total + 1024 <= (int64_t)max_smem - 4 * 1024) {   // static shared (barriers, scan) stays below 4 KB
-            g->groups = groups; g->xs_stride = stride;
-            g->opnd_offset = (int)opnd_off; g->epi_offset = (int)epi_off;
-            g->smem_bytes = total;
-            break;
-        }
-    }
+    // K rows per plane: data + shifted-B reach; among the strides that keep the group count, take the
+    // one with the fewest bank conflicts
+    const int rows_min = 16 * g->ksteps + max_shift;
+    const size_t epi = (size_t)kTcLagTab * sizeof(float);
+    const int want_groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
+    auto fit = [&](int rows, int groups, size_t* epi_off, size_t* total) {
+        const size_t buffer = (size_t)2 * 16 * rows * 16;   // hi + lo planes of one trial
+        *epi_off = ((size_t)groups * 2 * buffer + 127) & ~(size_t)127;
+        *total = (*epi_off + epi + 15) & ~(size_t)15;
+        return (int64_t)*total + 1024 <= (int64_t)max_smem - 2 * 1024;   // static shared (barriers, scan) stays below 2 KB
+    };
+    int groups = want_groups;
+    size_t epi_off = 0, total = 0;
+    while (groups >= 1 && !fit(rows_min, groups, &epi_off, &total)) --groups;
     if (groups < 1) return -3;
+    int best_rows = rows_min, best = 1 << 30;
+    for (int r = rows_min; r < rows_min + 8 && fit(r, groups, &epi_off, &total); ++r) {
+        const int cf = tc_store_conflicts(r * 16, g->chunk);
+        if (cf < best) { best = cf; best_rows = r; }
+    }
+    fit(best_rows, groups, &epi_off, &total);
+    g->rows_total = best_rows;
+    g->sbo_bytes = best_rows * 16;
+    g->groups = groups; g->epi_offset = (int)epi_off; g->smem_bytes = total;
     // trials per accumulator segment: ~768 K rows (truncation bias ~6.8e-9 per K row at lags with
     // ac ~ 1, measured at C5: 2.3e-6 / 4.8e-6 / 1.7e-5 for 384 / 768 / 2496 rows), a multiple of the
     // group count

@@ -281,12 +281,9 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.mask_words = m->mask_words;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
-        P.groups = t.groups; P.chunk = t.chunk; P.xs_tstride = t.xs_tstride; P.xs_stride = t.xs_stride;
-        P.opnd_offset = t.opnd_offset; P.epi_offset = t.epi_offset;
+        P.groups = t.groups; P.chunk = t.chunk; P.epi_offset = t.epi_offset;
         P.ksteps = t.ksteps; P.sbo_bytes = t.sbo_bytes;
-        P.used_cols = t.used_cols; P.tc_lags = t.tc_lags; P.tail_start = t.tail_start; P.seg_trials = t.seg_trials;
-        P.tail_lt = t.tail_lt; P.tail_streams = t.tail_streams; P.tail_tiles_per_stream = t.tail_tiles_per_stream;
-        P.n_time_tiles = t.n_time_tiles;
+        P.used_cols = t.used_cols; P.seg_trials = t.seg_trials;
         P.n_ops = t.n_ops;
         for (int o = 0; o < t.n_ops; ++o) {
             P.op_a_off[o] = (uint32_t)(t.op_a_blk[o] * (t.sbo_bytes / 16));

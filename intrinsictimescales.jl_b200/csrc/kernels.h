@@ -114,10 +114,9 @@ int acf_max_reach(int n_t, int max_smem);
 // ---- abc_tc_kernels.cu --------------------------------------------------------------
 constexpr int kTcMaxOps = 6;
 struct AbcTcGeometry {
-    int groups, chunk, xs_tstride, xs_stride, opnd_offset, epi_offset;
+    int groups, chunk, epi_offset;
     int rows_total, ksteps, sbo_bytes;
-    int used_cols, tc_lags, tail_start, mixed, seg_trials;
-    int tail_lt, tail_streams, tail_tiles_per_stream, n_time_tiles;
+    int used_cols, mixed, seg_trials;
     // MMA ops of one K step: A / B operand start (8-row MN block, K-row shift), shape, TMEM address
     int n_ops;
     int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
@@ -145,10 +144,9 @@ struct AbcTcParams {
     double* dist_out;
     double* stats_out;
     // geometry (AbcTcGeometry)
-    int groups, chunk, xs_tstride, xs_stride, opnd_offset, epi_offset;
+    int groups, chunk, epi_offset;
     int ksteps, sbo_bytes;
-    int used_cols, tc_lags, tail_start, seg_trials;
-    int tail_lt, tail_streams, tail_tiles_per_stream, n_time_tiles;
+    int used_cols, seg_trials;
     int n_ops;
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];

@@ -66,8 +66,6 @@ struct SimArgs {
     double inv_n;             // 1 / n_t
     float sqrt_nm1;           // sqrt(n_t - 1)
     int chunk;                // samples per thread (multiple of 4, chunk * NT >= n_t)
-    int xs_tstride = 0;       // TC sink only: floats between the staging chunks of consecutive threads
-                              // (chunk, or chunk + 4 to spread the float4 accesses over all banks)
     uint32_t k0, k1;          // Philox key (seed)
     uint32_t c3_noise, c3_init;
     uint32_t particle;        // global particle index (low 32 bits)
@@ -85,19 +83,21 @@ struct SimCache {
     bool valid = false;
 };
 
-// Tensor-core sink (TC = true): pass B also emits the series, scaled by the power of two
-// `scale`, as an fp16 hi/lo pair (x = hi + lo to ~22 bits) in the MN-major no-swizzle operand
-// layout of tcgen05.mma (tc05.cuh): sample j = 128 i + a goes to byte (a/8)*sbo + 16 i + 2 (a%8).
-// `wait_bar` guards the operand buffer: it completes when the MMAs that read the previous
-// contents have retired.
+// Tensor-core sink (TC = true): the trial is emitted, scaled by the power of two `scale`, as an fp16
+// hi/lo pair (x = hi + lo to ~22 bits) in the MN-major no-swizzle operand layout of tcgen05.mma
+// (tc05.cuh): the 8 samples j .. j+7 (j = 128 i + a, a % 8 == 0) occupy the 16 bytes at
+// (a/8)*sbo + 16 i of the hi plane and of the lo plane.  There is no separate staging buffer: pass A
+// parks its fp32 values in the very same 32 bytes (samples j..j+3 in the hi slot, j+4..j+7 in the lo
+// slot) and pass B converts them in place, each thread touching only its own slots.
+// `wait_bar` guards the buffer: it completes when the MMAs that read its previous contents have
+// retired (the caller alternates between two buffers, so that is the trial before the last one).
 struct TcSink {
     unsigned char* hi;
     unsigned char* lo;
     int sbo;
-    float scale, unscale;     // power of two and its reciprocal
+    float scale;              // power of two
     uint64_t* wait_bar;
     uint32_t wait_parity;
-    bool write_back;          // also store the fp32 series to xs (needed by the FFMA tail lags)
 };
 
 __device__ __forceinline__ void sim_sync(int bar_id, int nt) {
@@ -123,9 +123,6 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     constexpr int NW = NT / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const int j0 = tid * g.chunk;
-    // staging position of this thread's chunk: linear (series order) unless the tensor-core sink
-    // keeps a private padded layout
-    float* __restrict__ xc = xs + (TC ? tid * g.xs_tstride : j0);
     const float eps = oc.eps, s = oc.s;
 
     // per-trial initial state and phase (stream 1, block 0)
@@ -148,6 +145,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     const double* nz = g.noise ? g.noise + (size_t)trial * g.n_t : nullptr;
     const uint32_t* mrow = MISSING ? g.mask_bits + (size_t)trial * g.mask_words : nullptr;
     const bool need_p_sums = !cache.valid;
+    if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
     if (j0 < g.n_t) {
         for (int q = 0; q < g.chunk; q += 4) {
             const int j = j0 + q;
@@ -204,7 +202,13 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                     }
                 }
             }
-            *reinterpret_cast<float4*>(xc + q) = make_float4(v[0], v[1], v[2], v[3]);
+            if (TC) {
+                unsigned char* pl = (j & 4) ? sink->lo : sink->hi;
+                *reinterpret_cast<float4*>(pl + ((j & 127) >> 3) * sink->sbo + (j >> 7) * 16) =
+                    make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+                *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
+            }
         }
     }
     if (need_p_sums) { cache.Sp = Sp; cache.Spp = Spp; cache.valid = true; }
@@ -276,7 +280,6 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         // the operands carry the power-of-two factor `scale`: fold it into the affine map
         const float sc = sink->scale;
         rf *= sc; miss_val *= sc; shift *= sc;
-        tc::mbar_wait(sink->wait_bar, sink->wait_parity);
     }
     if (j0 < g.n_t) {
         float pb = OSC ? oc.sc : 1.f;
@@ -286,10 +289,15 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         for (int q = 0; q < g.chunk; q += STEP) {
             const int j = j0 + q;
             float v[STEP];
-#pragma unroll
-            for (int h = 0; h < STEP; h += 4) {
-                const float4 v4 = *reinterpret_cast<const float4*>(xc + q + h);
-                v[h] = v4.x; v[h + 1] = v4.y; v[h + 2] = v4.z; v[h + 3] = v4.w;
+            const int off = TC ? ((j & 127) >> 3) * sink->sbo + (j >> 7) * 16 : 0;
+            if (TC) {
+                const float4 a4 = *reinterpret_cast<const float4*>(sink->hi + off);
+                const float4 b4 = *reinterpret_cast<const float4*>(sink->lo + off);
+                v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w;
+                v[STEP - 4] = b4.x; v[STEP - 3] = b4.y; v[STEP - 2] = b4.z; v[STEP - 1] = b4.w;
+            } else {
+                const float4 v4 = *reinterpret_cast<const float4*>(xs + j);
+                v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
             }
 #pragma unroll
             for (int i = 0; i < STEP; ++i) {
@@ -311,13 +319,6 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                     *reinterpret_cast<float4*>(xs + j + h) = make_float4(v[h], v[h + 1], v[h + 2], v[h + 3]);
             }
             if (TC) {
-                if (sink->write_back) {                  // unscaled fp32 series in series order (FFMA tail lags)
-                    const float us = sink->unscale;
-#pragma unroll
-                    for (int h = 0; h < STEP; h += 4)
-                        *reinterpret_cast<float4*>(xs + j + h) =
-                            make_float4(v[h] * us, v[h + 1] * us, v[h + 2] * us, v[h + 3] * us);
-                }
                 uint32_t hp[4], lp[4];
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
@@ -327,12 +328,11 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                     hp[h] = *reinterpret_cast<const uint32_t*>(&hh);
                     lp[h] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
-                const int off = ((j & 127) >> 3) * sink->sbo + (j >> 7) * 16;
                 *reinterpret_cast<uint4*>(sink->hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 *reinterpret_cast<uint4*>(sink->lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
             }
         }
-    } else if (!TC || sink->write_back) {
+    } else if (!TC) {
         for (int q = 0; q < g.chunk; q += 4)
             *reinterpret_cast<float4*>(xs + j0 + q) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
