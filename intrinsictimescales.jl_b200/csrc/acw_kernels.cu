@@ -360,38 +360,32 @@ __global__ void k_acw_tau(const double* __restrict__ acf, int64_t n_rows, int64_
 //   C_k = P_k - m (2S - head_k - tail_k) + (n - k) m^2,  m = S / n,
 // head_k / tail_k = sums of the first / last k shifted samples.
 // Precision (north_star: "fp32 accumulate, fp64 check"): the shift is applied in fp64, the
-// products and the 32-step tile sums are fp32, tile sums are accumulated in fp64 - ACF error
-// ~1e-8.  Every crossing decision whose ACF value lies within 1e-6 of a threshold (0, 0.5, 1/e),
-// every slice containing a NaN (it propagates into P_k), every slice that has not crossed zero
-// within SK lags and every slice whose shifted mean is still large (n m^2 > C_0) is redone
-// in fp64 by k_acf_slices, so the crossing indices stay bit-exact against an fp64 reference.
-// Layout: a CTA streams SS = 64 adjacent slices (512 contiguous bytes per time step) of one
-// time segment through a 4-tile shared-memory ring of raw doubles filled by cp.async (tile = 32
-// time steps, two tiles in flight, one __syncthreads() per tile); thread = (slice, half of the
-// lags): samples are shifted and narrowed to fp32 as they are read, 16 accumulators + a 16-deep
-// circular register window, 16 FFMA per 2 LDS.64.  The shift is the mean of the slice's first
-// 32 samples (same arithmetic in k_acw_finish).
+// products are fp32 and flushed to fp64 every 256 samples - ACF error ~1e-8.  Every crossing
+// decision whose ACF value lies within 1e-6 of a threshold (0, 0.5, 1/e), every slice containing a
+// NaN (it propagates into P_k), every slice that has not crossed zero within SK lags and every
+// slice whose shifted mean is still large (n m^2 > C_0) is redone in fp64 by k_acf_slices, so the
+// crossing indices stay bit-exact against an fp64 reference.
+// Layout: thread = (slice, time segment); consecutive threads own consecutive slices, so every
+// time step of a warp is one coalesced 256-byte load straight into registers (16 loads in flight
+// per thread).  A thread keeps the 32 accumulators and a 32-deep circular window
+// of its slice in registers (static indexing: the time loop is unrolled by 32) - 32 FFMA per
+// sample next to one LDG.64, one DADD and one F2F.  A segment warms its window up on the 32
+// samples before it.  The shift is the mean of the slice's first 32 samples (same arithmetic in
+// k_acw_finish).  Partial sums go out as fp32 [segment][lag][slice] (coalesced).
 constexpr int SK = 32;     // lags of the streaming pass
-constexpr int SS = 64;     // slices per CTA
-constexpr int ST = 32;     // time steps per tile
-constexpr int SR = 128;    // ring rows = 4 tiles: halo, current, two in flight
 constexpr int SREF = 32;   // samples averaged for the per-slice shift
 constexpr int SPART = SK + 1;   // per (segment, slice): P_0..P_31, S
 constexpr int STREAM_THREADS = 128;
+constexpr int SFLUSH = 256;     // fp32 partial sums are folded into fp64 every SFLUSH samples
 constexpr double kStreamTol = 1e-6;
 
 struct AcwStreamParams {
     const double* data;
     int64_t n_slices;
     int n_t;
-    int n_seg, seg_len;          // time segments (seg_len multiple of ST)
-    double* part;                // [seg][slice][SPART]
+    int n_seg, seg_len;          // time segments (seg_len multiple of SK)
+    float* part;                 // [seg][SPART][slice]
 };
-
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
-}
 
 // per-slice shift: mean of the first min(SREF, n_t) samples, summed in time order
 __device__ __forceinline__ double slice_ref(const double* __restrict__ data, int64_t s, int64_t n_slices, int n_t) {
@@ -402,148 +396,176 @@ __device__ __forceinline__ double slice_ref(const double* __restrict__ data, int
 }
 
 __global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStreamParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*ring)[SS] = reinterpret_cast<double (*)[SS]>(smem_raw);      // [SR][SS]
-    const int tid = threadIdx.x;
-    const int sl = tid & (SS - 1);
-    const int half = tid >> 6;                         // warp-uniform
-    const int64_t s0 = (int64_t)blockIdx.x * SS;
+    const int64_t s = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    if (s >= P.n_slices) return;
     const int seg = blockIdx.y;
     const int tb = seg * P.seg_len;
-    const int te = min(tb + P.seg_len, P.n_t);
-    const int n_tiles = (te - tb + ST - 1) / ST;
+    const int te = min(tb + P.seg_len, P.n_t & ~(SK - 1));
+    const double* __restrict__ col = P.data + s;
+    const size_t ld = (size_t)P.n_slices;
+    const double ref = slice_ref(P.data, s, P.n_slices, P.n_t);
 
-    // ring tile q (q = 0 is the halo, time steps tb-32..tb-1; q >= 1 is data tile q-1) lives in
-    // rows [(q & 3) * ST, (q & 3) * ST + ST)
-    auto load_tile = [&](int q) {
-        const int t0 = tb + (q - 1) * ST;
-        double* base = &ring[(q & 3) * ST][0];
-        for (int i = tid; i < ST * SS; i += STREAM_THREADS) {
-            const int r = i / SS, c = i - r * SS;
-            const int t = t0 + r;
-            // rows outside [0, n_t) are only read as the halo of segment 0 (t < 0) or past te;
-            // both are masked where they are consumed (the shift would make a stored 0 non-zero)
-            if (t >= 0 && t < P.n_t && s0 + c < P.n_slices) cp_async8(base + i, P.data + (s0 + c) + (size_t)t * P.n_slices);
-            else base[i] = 0.0;
-        }
-        asm volatile("cp.async.commit_group;");
-    };
+    // fp64 running sums live in shared memory ([lag][thread]: conflict-free), touched every SFLUSH samples
+    __shared__ double acc64[SPART][STREAM_THREADS];
+    float acc[SK], C[SK];
+#pragma unroll
+    for (int j = 0; j < SK; ++j) { acc[j] = 0.f; acc64[j][threadIdx.x] = 0.0; }
+    acc64[SK][threadIdx.x] = 0.0;
+    float S = 0.f;
 
-    load_tile(0);
-    load_tile(1);
-    if (n_tiles > 1) load_tile(2); else asm volatile("cp.async.commit_group;");
-    const double ref = (s0 + sl < P.n_slices) ? slice_ref(P.data, s0 + sl, P.n_slices, P.n_t) : 0.0;
-
-    float acc[16], C[16];
-    double acc64[16];
+    // window warm-up: C[i] = y_{tb - 32 + i} (zero before the series starts)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { acc[j] = 0.f; C[j] = 0.f; acc64[j] = 0.0; }
-    double S64 = 0.0;
-
-    for (int tile = 0; tile < n_tiles; ++tile) {
-        asm volatile("cp.async.wait_group 1;");        // halo + tiles <= `tile` have landed
-        __syncthreads();                               // ... for every thread; tile-2's rows are free
-        if (tile + 2 < n_tiles) load_tile(tile + 3); else asm volatile("cp.async.commit_group;");
-        const double* cur = &ring[((tile + 1) & 3) * ST][sl];        // rows of this tile
-        const double* prev = &ring[(tile & 3) * ST][sl];             // rows of the previous tile / halo
-        const int t_tile = tb + tile * ST;
-        if (tile == 0) {
-            // circular window C[tau & 15] = y_tau, tau = t - 16 half: preload the 15 older samples
+    for (int h = 0; h < SK; h += 16) {
+        double x[16];
 #pragma unroll
-            for (int j = 1; j < 16; ++j) {
-                const int tau = t_tile - 16 * half - j;
-                C[(16 - j) & 15] = (tau >= 0) ? (float)(prev[(ST - 16 * half - j) * SS] - ref) : 0.f;
-            }
-        }
-        const int valid_rows = min(ST, te - t_tile);   // later rows belong to the next segment
-        float S = 0.f;
-#pragma unroll
-        for (int blk = 0; blk < ST; blk += 16) {
-            const double* dly = blk ? cur + (blk - 16) * SS : prev + (ST - 16) * SS;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float z = (float)(cur[(blk + i) * SS] - ref);
-                if (blk + i >= valid_rows) z = 0.f;
-                float d = z;
-                if (half) d = (t_tile + blk + i - 16 >= 0) ? (float)(dly[i * SS] - ref) : 0.f;
-                C[i] = d;                                // tau & 15 == i (tb and ST are multiples of 16)
-                S += z;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fmaf(z, C[(i - j) & 15], acc[j]);
-            }
+        for (int i = 0; i < 16; ++i) {
+            const int t = tb - SK + h + i;
+            x[i] = (t >= 0) ? col[(size_t)t * ld] : ref;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { acc64[j] += (double)acc[j]; acc[j] = 0.f; }
-        S64 += (double)S;
+        for (int i = 0; i < 16; ++i) C[h + i] = (float)(x[i] - ref);       // t < 0: ref - ref = 0
+        asm volatile("" ::: "memory");
     }
-    asm volatile("cp.async.wait_group 0;");
-    if (s0 + sl < P.n_slices) {
-        double* out = P.part + ((size_t)seg * P.n_slices + (s0 + sl)) * SPART;
+
+    // whole 32-sample blocks only: the host makes every segment a multiple of 32 samples and
+    // k_acw_finish adds the n_t % 32 samples at the end of the series in fp64.  Loads run half a
+    // block (16 samples) ahead of the arithmetic.
+    int since_flush = 0;
+    const double* __restrict__ p = col + (size_t)tb * ld;
+    double xa[16], xb[16];
+    if (tb + SK <= te) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[16 * half + j] = acc64[j];
-        if (half == 0) out[SK] = S64;
+        for (int i = 0; i < 16; ++i) { xa[i] = *p; p += ld; }
     }
+    for (int t0 = tb; t0 + SK <= te; t0 += SK) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { xb[i] = *p; p += ld; }
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float z = (float)(xa[i] - ref);
+            C[i] = z;                                      // (t - tb) & 31 == i
+            S += z;
+#pragma unroll
+            for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(i - j) & (SK - 1)], acc[j]);
+        }
+        asm volatile("" ::: "memory");
+        if (t0 + 2 * SK <= te) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xa[i] = *p; p += ld; }
+        }
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float z = (float)(xb[i] - ref);
+            C[16 + i] = z;
+            S += z;
+#pragma unroll
+            for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(16 + i - j) & (SK - 1)], acc[j]);
+        }
+        asm volatile("" ::: "memory");
+        since_flush += SK;
+        if (since_flush >= SFLUSH) {
+#pragma unroll
+            for (int j = 0; j < SK; ++j) { acc64[j][threadIdx.x] += (double)acc[j]; acc[j] = 0.f; }
+            acc64[SK][threadIdx.x] += (double)S; S = 0.f;
+            since_flush = 0;
+        }
+    }
+    float* out = P.part + (size_t)seg * SPART * ld + s;
+#pragma unroll
+    for (int j = 0; j < SK; ++j) out[(size_t)j * ld] = (float)(acc64[j][threadIdx.x] + (double)acc[j]);
+    out[(size_t)SK * ld] = (float)(acc64[SK][threadIdx.x] + (double)S);
 }
 
 struct AcwFinishParams {
     const double* data;
     int64_t n_slices;
     int n_t, n_seg;
-    const double* part;
+    const float* part;
     double* acf_work; int64_t cap;
     int32_t* n_done; int32_t* k0; int32_t* k50; int32_t* ke;
     int32_t* redo;               // [n_slices] 1 = needs the fp64 kernel
 };
 
-// one warp per slice, lane = lag
-__global__ void __launch_bounds__(128) k_acw_finish(const AcwFinishParams P) {
-    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (s >= P.n_slices) return;
-    const int k = threadIdx.x & 31;
-    double pk = 0.0, S = 0.0;
-    for (int g = 0; g < P.n_seg; ++g) {
-        const double* in = P.part + ((size_t)g * P.n_slices + s) * SPART;
-        pk += in[k];
-        S += in[SK];
+// CTA = 32 slices: the segment partials, the first 32 and the last 64 samples of every slice are
+// staged coalesced in shared memory ([row][slice] tiles), then one warp per slice (lane = lag)
+// derives the ACF and the crossings
+__global__ void __launch_bounds__(256) k_acw_finish(const AcwFinishParams P) {
+    __shared__ double tile[SPART][33];
+    __shared__ double head[SREF][33];          // samples 0 .. 31
+    __shared__ double tail[2 * SK][33];        // samples n_t - 64 .. n_t - 1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s0 = (int64_t)blockIdx.x * 32;
+    const size_t ld = (size_t)P.n_slices;
+    const bool col_ok = s0 + lane < P.n_slices;
+    for (int r = warp; r < SPART; r += 8) {
+        double v = 0.0;
+        if (col_ok)
+            for (int g = 0; g < P.n_seg; ++g) v += (double)P.part[((size_t)g * SPART + r) * ld + s0 + lane];
+        tile[r][lane] = v;
     }
-    const double n = (double)P.n_t;
-    const double m = S / n;
-    const double ref = slice_ref(P.data, s, P.n_slices, P.n_t);
-    // head_k = sum of the first k shifted samples, tail_k = sum of the last k: inclusive warp scans
-    double a = 0.0, b = 0.0;
-    if (k > 0 && k <= P.n_t) {
-        a = P.data[s + (size_t)(k - 1) * P.n_slices] - ref;
-        b = P.data[s + (size_t)(P.n_t - k) * P.n_slices] - ref;
+    for (int r = warp; r < SREF; r += 8) head[r][lane] = (col_ok && r < P.n_t) ? P.data[s0 + lane + (size_t)r * ld] : 0.0;
+    const int t_tail = P.n_t - 2 * SK;         // time index of tail row 0 (may be negative)
+    for (int r = warp; r < 2 * SK; r += 8) {
+        const int t = t_tail + r;
+        tail[r][lane] = (col_ok && t >= 0) ? P.data[s0 + lane + (size_t)t * ld] : 0.0;
     }
+    __syncthreads();
+    for (int w = warp; w < 32; w += 8) {
+        const int64_t s = s0 + w;
+        if (s >= P.n_slices) break;
+        const int k = lane;
+        double pk = tile[k][w], S = tile[SK][w];
+        const double n = (double)P.n_t;
+        // per-slice shift: same arithmetic as slice_ref()
+        double ref = 0.0;
+        const int mref = min(SREF, P.n_t);
+        for (int t = 0; t < mref; ++t) ref += head[t][w];
+        ref /= (double)mref;
+        // the n_t % 32 samples after the last whole block of the streaming pass, in fp64
+        for (int t = P.n_t & ~(SK - 1); t < P.n_t; ++t) {
+            const double yt = tail[t - t_tail][w] - ref;
+            if (t - k >= 0) pk += yt * (tail[t - k - t_tail][w] - ref);
+            S += yt;
+        }
+        const double m = S / n;
+        // head_k = sum of the first k shifted samples, tail_k = sum of the last k: inclusive warp scans
+        double a = 0.0, b = 0.0;
+        if (k > 0 && k <= P.n_t) {
+            a = head[k - 1][w] - ref;
+            b = tail[2 * SK - k][w] - ref;
+        }
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double ua = __shfl_up_sync(0xffffffffu, a, d), ub = __shfl_up_sync(0xffffffffu, b, d);
-        if (k >= d) { a += ua; b += ub; }
-    }
-    const double ck = pk - m * (2.0 * S - a - b) + (n - (double)k) * m * m;
-    const double c0 = __shfl_sync(0xffffffffu, ck, 0);
-    const bool in_range = k < P.n_t;
-    const double v = (k == 0) ? (c0 / c0) : ck / c0;
-    if (in_range) P.acf_work[(size_t)s * P.cap + k] = v;
-    const unsigned b0 = __ballot_sync(0xffffffffu, in_range && v <= 0.0);
-    const unsigned b50 = __ballot_sync(0xffffffffu, in_range && v <= 0.5);
-    const unsigned be = __ballot_sync(0xffffffffu, in_range && v <= kInvE);
-    const unsigned bad = __ballot_sync(0xffffffffu, in_range && !(v == v));      // NaN anywhere
-    const int f0 = b0 ? __ffs(b0) - 1 : -1;
-    // fp32 products: a value this close to a threshold, at a lag that matters for a crossing,
-    // is decided in fp64 instead
-    const bool matters = in_range && k > 0 && (f0 < 0 || k <= f0);
-    const bool close = fabs(v) < kStreamTol || fabs(v - 0.5) < kStreamTol || fabs(v - kInvE) < kStreamTol;
-    const unsigned unsure = __ballot_sync(0xffffffffu, matters && close);
-    if (k == 0) {
-        const int kmax = min(SK, P.n_t);
-        const bool ill = !(n * m * m <= c0);             // shifted mean still dominates: cancellation
-        const bool redo = ill || bad || unsure || (f0 < 0 && kmax < P.n_t);
-        P.redo[s] = redo ? 1 : 0;
-        P.n_done[s] = redo ? 0 : kmax;
-        P.k0[s] = f0;
-        P.k50[s] = b50 ? __ffs(b50) - 1 : -1;
-        P.ke[s] = be ? __ffs(be) - 1 : -1;
+        for (int d = 1; d < 32; d <<= 1) {
+            const double ua = __shfl_up_sync(0xffffffffu, a, d), ub = __shfl_up_sync(0xffffffffu, b, d);
+            if (k >= d) { a += ua; b += ub; }
+        }
+        const double ck = pk - m * (2.0 * S - a - b) + (n - (double)k) * m * m;
+        const double c0 = __shfl_sync(0xffffffffu, ck, 0);
+        const bool in_range = k < P.n_t;
+        const double v = (k == 0) ? (c0 / c0) : ck / c0;
+        if (in_range) P.acf_work[(size_t)s * P.cap + k] = v;
+        const unsigned b0 = __ballot_sync(0xffffffffu, in_range && v <= 0.0);
+        const unsigned b50 = __ballot_sync(0xffffffffu, in_range && v <= 0.5);
+        const unsigned be = __ballot_sync(0xffffffffu, in_range && v <= kInvE);
+        const unsigned bad = __ballot_sync(0xffffffffu, in_range && !(v == v));      // NaN anywhere
+        const int f0 = b0 ? __ffs(b0) - 1 : -1;
+        // fp32 products: a value this close to a threshold, at a lag that matters for a crossing,
+        // is decided in fp64 instead
+        const bool matters = in_range && k > 0 && (f0 < 0 || k <= f0);
+        const bool close = fabs(v) < kStreamTol || fabs(v - 0.5) < kStreamTol || fabs(v - kInvE) < kStreamTol;
+        const unsigned unsure = __ballot_sync(0xffffffffu, matters && close);
+        if (k == 0) {
+            const int kmax = min(SK, P.n_t);
+            const bool ill = !(n * m * m <= c0);             // shifted mean still dominates: cancellation
+            const bool redo = ill || bad || unsure || (f0 < 0 && kmax < P.n_t);
+            P.redo[s] = redo ? 1 : 0;
+            P.n_done[s] = redo ? 0 : kmax;
+            P.k0[s] = f0;
+            P.k50[s] = b50 ? __ffs(b50) - 1 : -1;
+            P.ke[s] = be ? __ffs(be) - 1 : -1;
+        }
     }
 }
 
@@ -578,32 +600,31 @@ cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, dou
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
                               int32_t* ke, int32_t* redo, cudaStream_t st) {
     AcwStreamParams S{};
-    S.data = data; S.n_slices = n_slices; S.n_t = n_t; S.n_seg = n_seg; S.seg_len = seg_len; S.part = part;
-    dim3 grid((unsigned)((n_slices + SS - 1) / SS), (unsigned)n_seg);
-    const size_t smem = (size_t)SR * SS * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k_acw_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_acw_stream<<<grid, STREAM_THREADS, smem, st>>>(S);
-    e = cudaGetLastError();
+    S.data = data; S.n_slices = n_slices; S.n_t = n_t; S.n_seg = n_seg; S.seg_len = seg_len;
+    S.part = reinterpret_cast<float*>(part);
+    dim3 grid((unsigned)((n_slices + STREAM_THREADS - 1) / STREAM_THREADS), (unsigned)n_seg);
+    k_acw_stream<<<grid, STREAM_THREADS, 0, st>>>(S);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AcwFinishParams F{};
-    F.data = data; F.n_slices = n_slices; F.n_t = n_t; F.n_seg = n_seg; F.part = part;
+    F.data = data; F.n_slices = n_slices; F.n_t = n_t; F.n_seg = n_seg; F.part = reinterpret_cast<const float*>(part);
     F.acf_work = acf_work; F.cap = cap; F.n_done = n_done; F.k0 = k0; F.k50 = k50; F.ke = ke;
     F.redo = redo;
-    k_acw_finish<<<(unsigned)((n_slices + 3) / 4), 128, 0, st>>>(F);
+    k_acw_finish<<<(unsigned)((n_slices + 31) / 32), 256, 0, st>>>(F);
     return cudaGetLastError();
 }
 int acw_stream_lags() { return SK; }
-size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return (size_t)n_seg * SPART * (size_t)n_slices; }
+// fp32 partials, counted in doubles for the caller's reserve()
+size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return ((size_t)n_seg * SPART * (size_t)n_slices + 1) / 2; }
 void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len) {
-    // enough CTAs for ~2 waves of 3 CTAs/SM; segments are multiples of the tile length
-    const int64_t ctas_per_seg = (n_slices + SS - 1) / SS;
-    int g = (int)((6LL * sm_count + ctas_per_seg - 1) / ctas_per_seg);
-    const int max_g = (n_t + 8 * ST - 1) / (8 * ST);          // keep >= 8 tiles per segment
+    // ~2 x 512 resident threads per SM; segments are multiples of 32 samples and at least 256 long
+    // (each one re-reads a 32-sample halo and writes 33 partial sums per slice)
+    int g = (int)((2LL * 512 * sm_count + n_slices - 1) / n_slices);
+    const int max_g = n_t / 256 > 0 ? n_t / 256 : 1;
     if (g > max_g) g = max_g;
     if (g < 1) g = 1;
     int len = (n_t + g - 1) / g;
-    len = ((len + ST - 1) / ST) * ST;
+    len = ((len + SK - 1) / SK) * SK;
     *seg_len = len;
     *n_seg = (n_t + len - 1) / len;
 }

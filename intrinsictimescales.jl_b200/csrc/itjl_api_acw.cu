@@ -189,6 +189,7 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
                                   (double*)ctx->out.p, cap, d_done, d_k0, d_k50, d_ke, d_redo, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_stream: %s", cudaGetErrorString(e));
             ctx->launches += 2;
+            if (ctx->timing) cudaEventRecord(ctx->ev1, ctx->stream);     // the streaming pass (k_acw_stream + k_acw_finish) alone
             h_redo.resize((size_t)n_slices);
             ITJL_CUDA(ctx, cudaMemcpyAsync(h_redo.data(), d_redo, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
             ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -211,9 +212,9 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
                                 d_done, d_k0, d_k50, d_ke, d_nan, nullptr, 0, ctx->max_smem_optin, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(scan): %s", cudaGetErrorString(e));
             ctx->launches++;
+            if (ctx->timing) cudaEventRecord(ctx->ev1, ctx->stream);
         }
         if (ctx->timing) {
-            cudaEventRecord(ctx->ev1, ctx->stream);
             cudaEventSynchronize(ctx->ev1);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
