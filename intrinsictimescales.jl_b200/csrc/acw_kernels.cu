@@ -395,7 +395,7 @@ __device__ __forceinline__ double slice_ref(const double* __restrict__ data, int
     return r / (double)m;
 }
 
-__global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStreamParams P) {
+__global__ void __launch_bounds__(STREAM_THREADS, 4) k_acw_stream(const AcwStreamParams P) {
     const int64_t s = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if (s >= P.n_slices) return;
     const int seg = blockIdx.y;
@@ -428,42 +428,28 @@ __global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream(const AcwStrea
     }
 
     // whole 32-sample blocks only: the host makes every segment a multiple of 32 samples and
-    // k_acw_finish adds the n_t % 32 samples at the end of the series in fp64.  Loads run half a
-    // block (16 samples) ahead of the arithmetic.
+    // k_acw_finish adds the n_t % 32 samples at the end of the series in fp64.
+    // (Tried and dropped, B200: loads issued half a block ahead of the math - 162 registers, 3 CTAs/SM,
+    // 116 us - and an extra prefetch.global.L2 96 steps ahead - 122 us - against 111 us for this loop:
+    // at 38 instructions per sample the pass is issue-bound, not latency-bound.)
     int since_flush = 0;
     const double* __restrict__ p = col + (size_t)tb * ld;
-    double xa[16], xb[16];
-    if (tb + SK <= te) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { xa[i] = *p; p += ld; }
-    }
     for (int t0 = tb; t0 + SK <= te; t0 += SK) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { xb[i] = *p; p += ld; }
-        asm volatile("" ::: "memory");
+        for (int h = 0; h < SK; h += 16) {
+            double x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float z = (float)(xa[i] - ref);
-            C[i] = z;                                      // (t - tb) & 31 == i
-            S += z;
+            for (int i = 0; i < 16; ++i) { x[i] = *p; p += ld; }
 #pragma unroll
-            for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(i - j) & (SK - 1)], acc[j]);
+            for (int i = 0; i < 16; ++i) {
+                const float z = (float)(x[i] - ref);
+                C[h + i] = z;                              // (t - tb) & 31 == h + i
+                S += z;
+#pragma unroll
+                for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(h + i - j) & (SK - 1)], acc[j]);
+            }
+            asm volatile("" ::: "memory");                 // keep the next 16 loads behind this half's math
         }
-        asm volatile("" ::: "memory");
-        if (t0 + 2 * SK <= te) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { xa[i] = *p; p += ld; }
-        }
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float z = (float)(xb[i] - ref);
-            C[16 + i] = z;
-            S += z;
-#pragma unroll
-            for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(16 + i - j) & (SK - 1)], acc[j]);
-        }
-        asm volatile("" ::: "memory");
         since_flush += SK;
         if (since_flush >= SFLUSH) {
 #pragma unroll
