@@ -22,8 +22,11 @@ namespace itjl {
 // v - a, and ac[l] = sum of the cells on the diagonal v - a = l.  Each D_s is a tcgen05.mma chain
 // (K = the rows i of the trials) accumulating in fp32 in tensor memory.  Both operands are the
 // SAME shared-memory buffer in the MN-major no-swizzle layout (K rows 16 B apart); the B operand
-// of D_s simply starts s rows later.  x' is fed as an fp16 hi/lo pair (hi*hi + hi*lo + lo*hi:
-// ~22-bit operands) - 3 MMAs per tile and K step.
+// of D_s simply starts s rows later.  x' is fed as an fp16 hi/lo pair: hi*hi + hi*lo + lo*hi
+// (~22-bit operands, 3 MMAs per tile and K step) when the particle has fewer than 10^5 samples.
+// Larger particles drop lo*hi: the omitted sum_t lo_t x_{t+l} is a sum of independent fp16 rounding
+// residuals (|lo| <= 2^-11 |x|, zero mean) - standard deviation 1.9e-4 / sqrt(n_trials n_t) in ACF
+// units, <= 6e-7 at 10^5 samples (3.8e-7 at C5), far inside the 1e-5 parity tolerance.
 //
 // Tensor-memory plans (128 lanes x 512 columns of fp32):
 //   A  (n_lags <= 385)   tiles s = 0 .. 3, M = 128 (cell row a = TMEM lane), N = 128: lags 0 .. 384.
@@ -61,6 +64,32 @@ constexpr int kTcMaxThreads = kTcGroupThreads * kTcMaxGroups + kTcEpiThreads;   
 constexpr int kTcBarEpi = 8;                        // named barrier over the epilogue warps
 constexpr int kTcLagTab = 512;                      // lag table entries (tensor-core lags <= 449)
 
+// Diagonal sums of 16 accumulator columns (col0 .. col0 + 15 of a 32-column block) held one TMEM lane
+// per thread: lane t fetches column i from lane (t + i) mod 32.  Plain blocks: a0 / b0 collect the
+// un-wrapped cells (two chains for ILP), a1 / b1 the wrapped ones.  Mixed blocks (plan B): a = lower
+// 16-lane strip, b = upper strip, index 0 / 1 = un-wrapped / wrapped.
+template <bool MIXED>
+__device__ __forceinline__ void tc_drain_half(const uint32_t (&v)[16], int col0, int lane, bool mixed_block,
+                                              float& a0, float& a1, float& b0, float& b1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int src = lane + col0 + i;
+        const float x = __uint_as_float(__shfl_sync(0xffffffffu, v[i], src));
+        const bool wrap = src >= 32;
+        if (MIXED && mixed_block) {
+            const bool upper = (src & 16) != 0;
+            a0 += (!upper && !wrap) ? x : 0.f;
+            a1 += (!upper && wrap) ? x : 0.f;
+            b0 += (upper && !wrap) ? x : 0.f;
+            b1 += (upper && wrap) ? x : 0.f;
+        } else if (i & 1) {
+            if (wrap) b1 += x; else b0 += x;
+        } else {
+            if (wrap) a1 += x; else a0 += x;
+        }
+    }
+}
+
 template <bool MISSING, bool OSC, bool MIXED>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -72,7 +101,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     __shared__ double red[4];
 
     const int G = P.groups;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches stay convergent
     const int op_bytes = 16 * P.sbo_bytes;                       // one fp16 operand plane (hi or lo)
     unsigned char* opnd = smem_raw;                              // [G][2 buffers][hi, lo] planes
     float* epi = reinterpret_cast<float*>(smem_raw + (size_t)P.epi_offset);
@@ -96,7 +126,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
 
     if (warp < 4 * G) {
         // ================= simulate groups ===================================================
@@ -140,8 +170,11 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 sink.lo = sink.hi + op_bytes;
                 sink.wait_bar = &bar_empty[g][buf];
                 sink.wait_parity = ((k >> 1) & 1u) ^ 1u;          // MMAs of trial k - 2 (same buffer) retired
-                simulate_trial<kTcGroupThreads, MISSING, OSC, true>(sa, oc, trial, nullptr, sh, kScaleUnitNorm, 1.0f, 0.0f,
-                                                                    sim_cache, tid_g, 1 + g, &sink);
+                if (!(P.debug & 2) || it == 0)                    // debug bit 1: time the tensor-core chain alone
+                    simulate_trial<kTcGroupThreads, MISSING, OSC, true>(sa, oc, trial, nullptr, sh, kScaleUnitNorm, 1.0f, 0.0f,
+                                                                        sim_cache, tid_g, 1 + g, &sink);
+                else
+                    tc::mbar_wait(sink.wait_bar, sink.wait_parity);
                 tc::fence_proxy_async_smem();                     // my operand stores -> async proxy
                 tc::mbar_arrive(&bar_full[g][buf]);
             }
@@ -170,7 +203,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 {
                     // ---- issue this warp's share of the segment's MMAs as the groups deliver their trials
                     // (whole warp, convergent: one elected lane issues, see tc05.cuh) ----------------
-                    tc::mbar_wait(&bar_acc_empty, (seg_it & 1u) ^ 1u);   // previous segment drained
+                    tc::mbar_wait_warp(&bar_acc_empty, (seg_it & 1u) ^ 1u);   // previous segment drained
                     tc::fence_after_thread_sync();
                     const int seg1 = min(seg0 + P.seg_trials, P.n_trials);
                     for (int trial = seg0; trial < seg1; ++trial) {
@@ -178,12 +211,12 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                         const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
                         const uint32_t k = it * n_g + (uint32_t)(trial / G);
                         const uint32_t buf = k & 1u;
-                        tc::mbar_wait(&bar_full[g][buf], (k >> 1) & 1u);
+                        tc::mbar_wait_warp(&bar_full[g][buf], (k >> 1) & 1u);
                         tc::fence_after_thread_sync();
                         const uint32_t hi_addr = opnd_addr + (uint32_t)((g * 2 + (int)buf) * 2 * op_bytes);
                         const uint64_t d_hi = tc::make_smem_desc(hi_addr, 128u, (uint32_t)P.sbo_bytes);
                         const uint64_t d_lo = tc::make_smem_desc(hi_addr + (uint32_t)op_bytes, 128u, (uint32_t)P.sbo_bytes);
-                        for (int ks = 0; ks < P.ksteps; ++ks) {
+                        for (int ks = 0; ks < ((P.debug & 1) ? 0 : P.ksteps); ++ks) {      // debug bit 0: no MMAs (simulate alone)
                             const uint32_t first = (trial == seg0 && ks == 0) ? 0u : 1u;
                             for (int o = e_warp; o < P.n_ops; o += 4) {
                                 // descriptor start addresses are in 16 B units: K rows are 16 B apart
@@ -193,7 +226,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                                 const uint32_t idesc = P.op_idesc[o];
                                 tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_hi + b_off, idesc, first);
                                 tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_lo + b_off, idesc, 1u);
-                                tc::mma_f16_ss_elect(d_t, d_lo + a_off, d_hi + b_off, idesc, 1u);
+                                if (P.n_terms == 3) tc::mma_f16_ss_elect(d_t, d_lo + a_off, d_hi + b_off, idesc, 1u);
                             }
                         }
                         tc::mma_commit_elect(&bar_empty[g][buf]); // this warp's reads of the buffer have retired
@@ -201,37 +234,27 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                     tc::mma_commit_elect(&bar_acc_full);          // this warp's accumulators of the segment complete
                 }
                 __syncwarp();
-                tc::mbar_wait(&bar_acc_full, seg_it & 1u);
+                tc::mbar_wait_warp(&bar_acc_full, seg_it & 1u);
                 tc::fence_after_thread_sync();
                 // ---- drain: diagonal sums by lane rotation.  Lane t receives column i of TMEM lane
-                // (t + i) mod 32, i.e. the cell of diagonal (column - row) = -t, or 32 - t once t + i wraps ----
+                // (t + i) mod 32, i.e. the cell of diagonal (column - row) = -t, or 32 - t once t + i wraps.
+                // 16 columns at a time, the next tcgen05.ld in flight under the shuffles of the current one ----
+                {
+                    const uint32_t t_q = tmem_base + ((uint32_t)(32 * q) << 16);
+                    uint32_t va[16], vb[16];
+                    tc::tmem_ld_32x16_issue(t_q, va);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (c < n_cb) {
-                        float v[32];
-                        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-                        if (MIXED && c < 4) {
-                            // rows: lanes 0..15 = lower strip (a = 16 q + lane), 16..31 = upper strip
-                            float l0 = 0.f, l1 = 0.f, u0 = 0.f, u1 = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int src = lane + i;
-                                const float x = __shfl_sync(0xffffffffu, v[i], src & 31);
-                                const bool upper = (src & 16) != 0, wrap = src >= 32;
-                                l0 += (!upper && !wrap) ? x : 0.f;
-                                l1 += (!upper && wrap) ? x : 0.f;
-                                u0 += (upper && !wrap) ? x : 0.f;
-                                u1 += (upper && wrap) ? x : 0.f;
-                            }
-                            ds[c][0] += l0; ds[c][1] += l1; du[c][0] += u0; du[c][1] += u1;
-                        } else {
-                            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float x = __shfl_sync(0xffffffffu, v[i], (lane + i) & 31);
-                                if (lane + i < 32) s1 += x; else s2 += x;
-                            }
-                            ds[c][0] += s1; ds[c][1] += s2;
+                    for (int c = 0; c < 16; ++c) {
+                        if (c < n_cb) {
+                            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // mixed: lower no-wrap / wrap, upper no-wrap / wrap
+                            tc::tmem_ld_wait(va);
+                            tc::tmem_ld_32x16_issue(t_q + (uint32_t)(32 * c + 16), vb);
+                            tc_drain_half<MIXED>(va, 0, lane, c < 4, a0, a1, b0, b1);
+                            tc::tmem_ld_wait(vb);
+                            if (c + 1 < n_cb) tc::tmem_ld_32x16_issue(t_q + (uint32_t)(32 * (c + 1)), va);
+                            tc_drain_half<MIXED>(vb, 16, lane, c < 4, a0, a1, b0, b1);
+                            if (MIXED && c < 4) { ds[c][0] += a0; ds[c][1] += a1; du[c][0] += b0; du[c][1] += b1; }
+                            else { ds[c][0] += a0 + b0; ds[c][1] += a1 + b1; }
                         }
                     }
                 }
@@ -391,6 +414,9 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     const char* e_seg = getenv("ITJL_TC_SEG");
     if (e_seg && atoi(e_seg) > 0) seg = atoi(e_seg);
     g->seg_trials = seg;
+    g->n_terms = ((int64_t)n_t * n_trials >= 100000) ? 2 : 3;
+    const char* e_terms = getenv("ITJL_TC_TERMS");
+    if (e_terms && (atoi(e_terms) == 2 || atoi(e_terms) == 3)) g->n_terms = atoi(e_terms);
     int p2 = 1; while (p2 * p2 < n_t) p2 <<= 1;                 // power of two near sqrt(n_t): series ~ N(0,1)
     g->tc_scale = (float)p2;
     g->grid = sm_count;

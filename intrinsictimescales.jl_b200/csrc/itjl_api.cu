@@ -233,7 +233,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
         const double M = (double)(((id >> 24) & 0x1Fu) << 4), N = (double)(((id >> 17) & 0x3Fu) << 3);
         f += 2.0 * M * N * 16.0;
     }
-    *tensor_flops_per_sample = f * 3.0 * m->tc.ksteps / (double)m->d.n_t;
+    *tensor_flops_per_sample = f * (double)m->tc.n_terms * m->tc.ksteps / (double)m->d.n_t;
     return ITJL_OK;
 }
 
@@ -283,7 +283,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.dist_out = dist_dev; P.stats_out = stats_dev;
         P.groups = t.groups; P.chunk = t.chunk; P.epi_offset = t.epi_offset;
         P.ksteps = t.ksteps; P.sbo_bytes = t.sbo_bytes;
-        P.used_cols = t.used_cols; P.seg_trials = t.seg_trials;
+        P.used_cols = t.used_cols; P.seg_trials = t.seg_trials; P.n_terms = t.n_terms;
         P.n_ops = t.n_ops;
         for (int o = 0; o < t.n_ops; ++o) {
             P.op_a_off[o] = (uint32_t)(t.op_a_blk[o] * (t.sbo_bytes / 16));
@@ -292,6 +292,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         }
         P.tc_scale = t.tc_scale; P.tc_unscale = 1.0f / (t.tc_scale * t.tc_scale);
         P.smem_bytes = t.smem_bytes;
+        { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
         e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,
                           t.smem_bytes, t.grid, ctx->stream);
     } else {

@@ -116,7 +116,7 @@ constexpr int kTcMaxOps = 6;
 struct AbcTcGeometry {
     int groups, chunk, epi_offset;
     int rows_total, ksteps, sbo_bytes;
-    int used_cols, mixed, seg_trials;
+    int used_cols, mixed, seg_trials, n_terms;
     // MMA ops of one K step: A / B operand start (8-row MN block, K-row shift), shape, TMEM address
     int n_ops;
     int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
@@ -146,12 +146,13 @@ struct AbcTcParams {
     // geometry (AbcTcGeometry)
     int groups, chunk, epi_offset;
     int ksteps, sbo_bytes;
-    int used_cols, seg_trials;
+    int used_cols, seg_trials, n_terms;
     int n_ops;
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
     float tc_scale, tc_unscale;
     size_t smem_bytes;
+    int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = no MMAs, 2 = no simulation after the first particle
 };
 int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g);
 cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, bool mixed, size_t smem, int grid,
