@@ -35,7 +35,8 @@ namespace itjl {
 //      the lower 16 lanes of every 32-lane quarter, rows a >= 64 x columns 64 .. 127 on the upper
 //      16 lanes (D address lane offset 16) - and the freed quadrant receives D_4 (rows a >= 64,
 //      b < 64, v = 512 + b): lags up to 448 without touching the CUDA cores.
-//   Longer lag windows run on the CUDA-core kernel k_abc_acf.
+//   Up to 60 further lags (n_lags <= 509) are summed by an FFMA loop that reads the trial back from its
+//   operand planes; longer lag windows run on the CUDA-core kernel k_abc_acf.
 //
 // Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
 // zero (measured, benchmarks/tc_probe2.py), so a long positive chain loses ~0.5 ulp per product:
@@ -90,12 +91,58 @@ __device__ __forceinline__ void tc_drain_half(const uint32_t (&v)[16], int col0,
     }
 }
 
+// ---- FFMA tail: the lags beyond the tensor-memory plans (449 .. 508), summed on the CUDA cores from
+// the operand planes themselves (x' = hi + lo, exact in fp32).  Thread = (tile of 16 lags) x (time
+// stream); a step multiplies 16 samples a[] with a 32-wide window b[] (256 FFMA per 8 LDS.128).
+constexpr int kTailK = 16;                          // lags per thread
+constexpr int kTailT = 16;                          // samples per step
+
+// the 8 samples j .. j + 7 (j % 8 == 0) of a trial, as fp32
+__device__ __forceinline__ void tc_load8(const unsigned char* hi, const unsigned char* lo, int sbo, int j, float* dst) {
+    const int off = ((j & 127) >> 3) * sbo + (j >> 7) * 16;
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + off);
+    const uint4 l = *reinterpret_cast<const uint4*>(lo + off);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[p]));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[p]));
+        dst[2 * p] = a.x + b.x; dst[2 * p + 1] = a.y + b.y;
+    }
+}
+
+// acc[j] += sum over steps [step_begin, step_end) of sum_i x[t0 + i] * x[t0 + i + k0 + j],  t0 = 16 step
+__device__ __forceinline__ void tc_tail_steps(const unsigned char* hi, const unsigned char* lo, int sbo,
+                                              float (&acc)[kTailK], int k0, int step_begin, int step_end) {
+    float a[kTailT], b[2 * kTailT];
+    int t0 = step_begin * kTailT;
+    tc_load8(hi, lo, sbo, t0 + k0, b); tc_load8(hi, lo, sbo, t0 + k0 + 8, b + 8);
+    for (int st = step_begin; st < step_end; st += 2, t0 += 2 * kTailT) {
+        // phase 0: window = b[0 .. 31]
+        tc_load8(hi, lo, sbo, t0 + k0 + 16, b + 16); tc_load8(hi, lo, sbo, t0 + k0 + 24, b + 24);
+        tc_load8(hi, lo, sbo, t0, a); tc_load8(hi, lo, sbo, t0 + 8, a + 8);
+#pragma unroll
+        for (int i = 0; i < kTailT; ++i)
+#pragma unroll
+            for (int j = 0; j < kTailK; ++j) acc[j] = fmaf(a[i], b[i + j], acc[j]);
+        if (st + 1 >= step_end) break;
+        // phase 1: window = b[16 .. 31], b[0 .. 15]
+        tc_load8(hi, lo, sbo, t0 + k0 + 32, b); tc_load8(hi, lo, sbo, t0 + k0 + 40, b + 8);
+        tc_load8(hi, lo, sbo, t0 + 16, a); tc_load8(hi, lo, sbo, t0 + 24, a + 8);
+#pragma unroll
+        for (int i = 0; i < kTailT; ++i)
+#pragma unroll
+            for (int j = 0; j < kTailK; ++j) acc[j] = fmaf(a[i], b[(kTailT + i + j) % (2 * kTailT)], acc[j]);
+    }
+}
+
 template <bool MISSING, bool OSC, bool MIXED>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kTcMaxGroups][2];      // [group][buffer] operands ready
     __shared__ __align__(8) uint64_t bar_empty[kTcMaxGroups][2];     // [group][buffer] operands consumed
-    __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty;
+    __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty, bar_tail_full, bar_tail_free;
+    __shared__ float tailred[kTcMaxGroups][4][4 * kTailK];           // [group][warp][tail lag] per-particle sums
     __shared__ uint32_t tmem_slot;
     __shared__ SimShared<kTcGroupThreads> shs[kTcMaxGroups];
     __shared__ double red[4];
@@ -119,6 +166,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_full[g][b], kTcGroupThreads); tc::mbar_init(&bar_empty[g][b], 4); }
         tc::mbar_init(&bar_acc_full, 4);
         tc::mbar_init(&bar_acc_empty, 4);
+        tc::mbar_init(&bar_tail_full, (uint32_t)(4 * G));
+        tc::mbar_init(&bar_tail_free, 1);
         tc::fence_mbar_init();
     }
     if (warp == 4 * G) tc::tmem_alloc(&tmem_slot, 512);
@@ -161,6 +210,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             sa.noise = P.noise ? P.noise + pt * P.n_t : nullptr;
             sa.phases = P.phases ? P.phases + pt : nullptr;
             SimCache sim_cache;
+            float tacc[kTailK];
+#pragma unroll
+            for (int j = 0; j < kTailK; ++j) tacc[j] = 0.f;
 
             uint32_t mine = 0;
             for (int trial = g; trial < P.n_trials; trial += G, ++mine) {
@@ -177,6 +229,31 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                     tc::mbar_wait(sink.wait_bar, sink.wait_parity);
                 tc::fence_proxy_async_smem();                     // my operand stores -> async proxy
                 tc::mbar_arrive(&bar_full[g][buf]);
+                if (P.tail_lt > 0) {
+                    // lags beyond the tensor-memory plan: read the trial back from its operand planes (the
+                    // MMAs only read them too; the buffer is rewritten two trials from now)
+                    tc::named_bar_sync(1 + g, kTcGroupThreads);
+                    const int tile = tid_g & (P.tail_lt - 1), stream = tid_g / P.tail_lt;
+                    const int s_begin = stream * P.tail_steps_per_stream;
+                    const int s_end = min(s_begin + P.tail_steps_per_stream, P.tail_steps);
+                    if (s_begin < s_end) tc_tail_steps(sink.hi, sink.lo, P.sbo_bytes, tacc, P.tail_start + tile * kTailK, s_begin, s_end);
+                }
+            }
+            if (P.tail_lt > 0) {
+                // reduce over the time streams of a warp (lanes with equal lane % tail_lt), hand the sums over
+#pragma unroll
+                for (int j = 0; j < kTailK; ++j) {
+                    float v = tacc[j];
+                    for (int o = 16; o >= P.tail_lt; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    tacc[j] = v;
+                }
+                tc::mbar_wait(&bar_tail_free, (it & 1u) ^ 1u);    // previous particle's sums consumed
+                if (lane < P.tail_lt) {
+#pragma unroll
+                    for (int j = 0; j < kTailK; ++j) tailred[g][warp & 3][lane * kTailK + j] = tacc[j];
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_tail_full);
             }
         }
     } else {
@@ -273,23 +350,23 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                                 // lower strip: lag = 32 c - 16 q - lane (+ 32 after the wrap);
                                 // upper strip: rows a = 48 + 16 q + lane, columns of D_4 (c < 2) start at v = 512
                                 int k = 32 * c - 16 * q - lane;
-                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][0];
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
                                 __syncwarp();
                                 k += 32;
-                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][1];
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
                                 __syncwarp();
                                 k = 32 * c - 48 - 16 * q - lane + (c < 2 ? 512 : 0);
-                                if (k >= 0 && k < P.n_lags) lagtab[k] += du[c][0];
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += du[c][0];
                                 __syncwarp();
                                 k += 32;
-                                if (k >= 0 && k < P.n_lags) lagtab[k] += du[c][1];
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += du[c][1];
                                 __syncwarp();
                             } else {
                                 int k = 32 * (c - q) - lane;
-                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][0];
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
                                 __syncwarp();
                                 k += 32;
-                                if (k >= 0 && k < P.n_lags) lagtab[k] += ds[c][1];
+                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
                                 __syncwarp();
                             }
                         }
@@ -299,9 +376,18 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             }
 
             // ---- trial mean, distance ---------------------------------------------------------------
+            if (P.tail_lt > 0) tc::mbar_wait(&bar_tail_full, it & 1u);
             double local = 0.0;
             for (int k = e_tid; k < P.n_lags; k += kTcEpiThreads) {
-                const double v = (double)(lagtab[k] * P.tc_unscale) * inv_trials;
+                float sk;
+                if (k < P.tc_lags) {
+                    sk = lagtab[k];
+                } else {
+                    sk = 0.f;
+                    for (int gg = 0; gg < G; ++gg)
+                        for (int w = 0; w < 4; ++w) sk += tailred[gg][w][k - P.tail_start];
+                }
+                const double v = (double)(sk * P.tc_unscale) * inv_trials;
                 if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
                 const double tgt = (double)P.target[k];
                 const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
@@ -310,7 +396,10 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             local = warp_sum(local);
             if (lane == 0) red[q] = local;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
-            if (e_tid == 0) P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
+            if (e_tid == 0) {
+                P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
+                if (P.tail_lt > 0) tc::mbar_arrive(&bar_tail_free);
+            }
             for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0.f;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
         }
@@ -347,7 +436,8 @@ static int tc_store_conflicts(int sbo_bytes, int chunk) {
 // Geometry of the tensor-core kernel; returns 0 when the configuration is supported.
 int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g) {
     if (n_t < 16 || n_lags < 1 || n_lags > n_t) return -1;
-    if (n_lags > 449) return -2;                           // beyond the tensor-memory plans
+    const int max_tail = 60;                               // FFMA tail lags beyond the tensor-memory plans
+    if (n_lags > 449 + max_tail) return -2;
     const int rows_data = (n_t + 127) / 128;
     g->ksteps = (rows_data + 15) / 16;
     int max_shift;
@@ -369,7 +459,8 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         max_shift = n_tiles - 1;
     } else {
         // plan B
-        const int n4 = ((n_lags - 385) + 15) & ~15;        // <= 64
+        int n4 = ((n_lags - 385) + 15) & ~15;
+        if (n4 > 64) n4 = 64;
         g->used_cols = 512;
         g->mixed = 1;
         add_op(0, 0, 0, 64, 128, 0, 0);                    // D_0 rows a < 64
@@ -378,18 +469,37 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         add_op(8, 4, 0, 64, n4, 16, 0);                    // D_4 rows a >= 64, columns < n4
         max_shift = 4;
     }
+    g->tc_lags = n_lags < 449 ? n_lags : 449;
+    if (n_lags <= 385) g->tc_lags = n_lags;
+    // FFMA tail: tiles of 16 lags from tail_start (a multiple of 8: 16-byte groups of the planes)
+    g->tail_start = g->tc_lags & ~7;
+    const int tail = n_lags > g->tc_lags ? n_lags - g->tail_start : 0;
+    g->tail_lt = tail == 0 ? 0 : (tail <= kTailK ? 1 : (tail <= 2 * kTailK ? 2 : 4));
+    if (tail > 4 * kTailK) return -2;
+    g->tail_steps = (n_t + kTailT - 1) / kTailT;
+    g->tail_steps_per_stream = 0;
+    if (g->tail_lt > 0) {
+        const int streams = kTcGroupThreads / g->tail_lt;
+        g->tail_steps_per_stream = (g->tail_steps + streams - 1) / streams;
+    }
     int c = (n_t + kTcGroupThreads - 1) / kTcGroupThreads;
     g->chunk = (c + 7) & ~7;
     // K rows per plane: data + shifted-B reach; among the strides that keep the group count, take the
     // one with the fewest bank conflicts
-    const int rows_min = 16 * g->ksteps + max_shift;
+    int rows_min = 16 * g->ksteps + max_shift;
+    if (g->tail_lt > 0) {
+        // furthest sample the tail window reads (zero rows behind the data)
+        const int reach = (g->tail_steps + 2) * kTailT + g->tail_start + g->tail_lt * kTailK + 2 * kTailT;
+        const int rows_tail = (reach + 127) / 128;
+        if (rows_tail > rows_min) rows_min = rows_tail;
+    }
     const size_t epi = (size_t)kTcLagTab * sizeof(float);
     const int want_groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
     auto fit = [&](int rows, int groups, size_t* epi_off, size_t* total) {
         const size_t buffer = (size_t)2 * 16 * rows * 16;   // hi + lo planes of one trial
         *epi_off = ((size_t)groups * 2 * buffer + 127) & ~(size_t)127;
         *total = (*epi_off + epi + 15) & ~(size_t)15;
-        return (int64_t)*total + 1024 <= (int64_t)max_smem - 2 * 1024;   // static shared (barriers, scan) stays below 2 KB
+        return (int64_t)*total + 1024 <= (int64_t)max_smem - 6 * 1024;   // static shared (barriers, scan, tail sums) stays below 6 KB
     };
     int groups = want_groups;
     size_t epi_off = 0, total = 0;

@@ -284,6 +284,8 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.groups = t.groups; P.chunk = t.chunk; P.epi_offset = t.epi_offset;
         P.ksteps = t.ksteps; P.sbo_bytes = t.sbo_bytes;
         P.used_cols = t.used_cols; P.seg_trials = t.seg_trials; P.n_terms = t.n_terms;
+        P.tc_lags = t.tc_lags; P.tail_start = t.tail_start; P.tail_lt = t.tail_lt; P.tail_steps = t.tail_steps;
+        P.tail_steps_per_stream = t.tail_steps_per_stream;
         P.n_ops = t.n_ops;
         for (int o = 0; o < t.n_ops; ++o) {
             P.op_a_off[o] = (uint32_t)(t.op_a_blk[o] * (t.sbo_bytes / 16));

@@ -117,6 +117,7 @@ struct AbcTcGeometry {
     int groups, chunk, epi_offset;
     int rows_total, ksteps, sbo_bytes;
     int used_cols, mixed, seg_trials, n_terms;
+    int tc_lags, tail_start, tail_lt, tail_steps, tail_steps_per_stream;
     // MMA ops of one K step: A / B operand start (8-row MN block, K-row shift), shape, TMEM address
     int n_ops;
     int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
@@ -147,6 +148,7 @@ struct AbcTcParams {
     int groups, chunk, epi_offset;
     int ksteps, sbo_bytes;
     int used_cols, seg_trials, n_terms;
+    int tc_lags, tail_start, tail_lt, tail_steps, tail_steps_per_stream;
     int n_ops;
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];

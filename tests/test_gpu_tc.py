@@ -119,9 +119,11 @@ def _gpu_models(mk, ctx):
 
 
 # (n_t, n_trials, n_lags): tensor-memory plan A with 1..4 tiles, plan B (M = 64 split, 5th tile), several
-# accumulator segments (21 and 50 trials), fewer trials than groups, odd buffer counts
+# accumulator segments (21 and 50 trials), fewer trials than groups, odd buffer counts, FFMA tail lags
+# (1, 2 and 4 lag tiles)
 SHAPES = [(1000, 5, 37), (601, 3, 20), (2500, 1, 300), (5000, 2, 385), (5000, 2, 386), (5000, 4, 414),
-          (5000, 21, 449), (5000, 3, 430), (3000, 50, 200), (5000, 50, 414), (5000, 7, 401)]
+          (5000, 21, 449), (5000, 3, 430), (3000, 50, 200), (5000, 50, 414), (5000, 7, 401),
+          (5000, 3, 463), (5000, 9, 470), (5000, 5, 509)]
 
 
 @pytest.mark.parametrize("n_t,n_trials,n_lags", SHAPES)
@@ -168,9 +170,9 @@ def test_tc_kernel_missing_data_variant(pkg, ctx):
 
 
 def test_unsupported_shapes_fall_back_to_cuda_core_kernel(pkg, ctx):
-    """n_lags beyond the tensor-memory plans (> 449): ITJL_ABC_TC unset picks k_abc_acf,
+    """n_lags beyond the tensor-memory plans + 60 tail lags: ITJL_ABC_TC unset picks k_abc_acf,
     ITJL_ABC_TC=1 refuses."""
-    om, mk = _models(pkg, 2500, 1, 450)
+    om, mk = _models(pkg, 2500, 1, 510)
     old = os.environ.pop("ITJL_ABC_TC", None)
     try:
         assert mk().gpu_model(ctx).kernel_info()[0] == "k_abc_acf"
