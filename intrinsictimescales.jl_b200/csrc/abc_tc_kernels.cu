@@ -136,7 +136,7 @@ __device__ __forceinline__ void tc_tail_steps(const unsigned char* hi, const uns
     }
 }
 
-template <bool MISSING, bool OSC, bool MIXED>
+template <bool MISSING, bool OSC, bool MIXED, bool TAIL>
 __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kTcMaxGroups][2];      // [group][buffer] operands ready
@@ -210,9 +210,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             sa.noise = P.noise ? P.noise + pt * P.n_t : nullptr;
             sa.phases = P.phases ? P.phases + pt : nullptr;
             SimCache sim_cache;
-            float tacc[kTailK];
+            float tacc[TAIL ? kTailK : 1];
 #pragma unroll
-            for (int j = 0; j < kTailK; ++j) tacc[j] = 0.f;
+            for (int j = 0; j < (TAIL ? kTailK : 1); ++j) tacc[j] = 0.f;
 
             uint32_t mine = 0;
             for (int trial = g; trial < P.n_trials; trial += G, ++mine) {
@@ -229,20 +229,22 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                     tc::mbar_wait(sink.wait_bar, sink.wait_parity);
                 tc::fence_proxy_async_smem();                     // my operand stores -> async proxy
                 tc::mbar_arrive(&bar_full[g][buf]);
-                if (P.tail_lt > 0) {
+                if (TAIL) {
                     // lags beyond the tensor-memory plan: read the trial back from its operand planes (the
                     // MMAs only read them too; the buffer is rewritten two trials from now)
                     tc::named_bar_sync(1 + g, kTcGroupThreads);
                     const int tile = tid_g & (P.tail_lt - 1), stream = tid_g / P.tail_lt;
                     const int s_begin = stream * P.tail_steps_per_stream;
                     const int s_end = min(s_begin + P.tail_steps_per_stream, P.tail_steps);
-                    if (s_begin < s_end) tc_tail_steps(sink.hi, sink.lo, P.sbo_bytes, tacc, P.tail_start + tile * kTailK, s_begin, s_end);
+                    if (s_begin < s_end)
+                        tc_tail_steps(sink.hi, sink.lo, P.sbo_bytes, reinterpret_cast<float (&)[kTailK]>(tacc),
+                                      P.tail_start + tile * kTailK, s_begin, s_end);
                 }
             }
-            if (P.tail_lt > 0) {
+            if (TAIL) {
                 // reduce over the time streams of a warp (lanes with equal lane % tail_lt), hand the sums over
 #pragma unroll
-                for (int j = 0; j < kTailK; ++j) {
+                for (int j = 0; j < (TAIL ? kTailK : 1); ++j) {
                     float v = tacc[j];
                     for (int o = 16; o >= P.tail_lt; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     tacc[j] = v;
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 tc::mbar_wait(&bar_tail_free, (it & 1u) ^ 1u);    // previous particle's sums consumed
                 if (lane < P.tail_lt) {
 #pragma unroll
-                    for (int j = 0; j < kTailK; ++j) tailred[g][warp & 3][lane * kTailK + j] = tacc[j];
+                    for (int j = 0; j < (TAIL ? kTailK : 1); ++j) tailred[g][warp & 3][lane * kTailK + j] = tacc[j];
                 }
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bar_tail_full);
@@ -376,11 +378,11 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             }
 
             // ---- trial mean, distance ---------------------------------------------------------------
-            if (P.tail_lt > 0) tc::mbar_wait(&bar_tail_full, it & 1u);
+            if (TAIL) tc::mbar_wait(&bar_tail_full, it & 1u);
             double local = 0.0;
             for (int k = e_tid; k < P.n_lags; k += kTcEpiThreads) {
                 float sk;
-                if (k < P.tc_lags) {
+                if (!TAIL || k < P.tc_lags) {
                     sk = lagtab[k];
                 } else {
                     sk = 0.f;
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
             if (e_tid == 0) {
                 P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
-                if (P.tail_lt > 0) tc::mbar_arrive(&bar_tail_free);
+                if (TAIL) tc::mbar_arrive(&bar_tail_free);
             }
             for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0.f;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
@@ -515,12 +517,15 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     g->sbo_bytes = best_rows * 16;
     g->groups = groups; g->epi_offset = (int)epi_off; g->smem_bytes = total;
     // trials per accumulator segment: ~768 K rows (truncation bias ~6.8e-9 per K row at lags with
-    // ac ~ 1, measured at C5: 2.3e-6 / 4.8e-6 / 1.7e-5 for 384 / 768 / 2496 rows), a multiple of the
-    // group count
+    // ac ~ 1, measured at C5: 2.3e-6 / 4.8e-6 / 1.7e-5 for 384 / 768 / 2496 rows), split evenly over the
+    // particle's trials
     const int rows_trial = 16 * g->ksteps;
     int seg = (768 + rows_trial / 2) / rows_trial;
-    seg = (seg / g->groups) * g->groups;
-    if (seg < g->groups) seg = g->groups;
+    if (seg < 1) seg = 1;
+    if (n_trials > 0) {                                    // equal segments: 50 trials -> 13, 13, 13, 11
+        const int n_seg = (n_trials + seg - 1) / seg;
+        seg = (n_trials + n_seg - 1) / n_seg;
+    }
     const char* e_seg = getenv("ITJL_TC_SEG");
     if (e_seg && atoi(e_seg) > 0) seg = atoi(e_seg);
     g->seg_trials = seg;
@@ -533,15 +538,17 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     return 0;
 }
 
+template <bool MIXED, bool TAIL>
+static void (*tc_pick(bool missing, bool osc))(const AbcTcParams) {
+    return missing ? (osc ? k_abc_acf_tc<true, true, MIXED, TAIL> : k_abc_acf_tc<true, false, MIXED, TAIL>)
+                   : (osc ? k_abc_acf_tc<false, true, MIXED, TAIL> : k_abc_acf_tc<false, false, MIXED, TAIL>);
+}
+
 cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, bool mixed, size_t smem, int grid,
                           cudaStream_t st) {
-    void (*kern)(const AbcTcParams);
-    if (mixed)
-        kern = missing ? (osc ? k_abc_acf_tc<true, true, true> : k_abc_acf_tc<true, false, true>)
-                       : (osc ? k_abc_acf_tc<false, true, true> : k_abc_acf_tc<false, false, true>);
-    else
-        kern = missing ? (osc ? k_abc_acf_tc<true, true, false> : k_abc_acf_tc<true, false, false>)
-                       : (osc ? k_abc_acf_tc<false, true, false> : k_abc_acf_tc<false, false, false>);
+    void (*kern)(const AbcTcParams) =
+        !mixed ? tc_pick<false, false>(missing, osc)
+               : (P.tail_lt > 0 ? tc_pick<true, true>(missing, osc) : tc_pick<true, false>(missing, osc));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if ((int64_t)grid > P.n_particles) grid = (int)P.n_particles;
