@@ -69,12 +69,24 @@ constexpr int kTcLagTab = 512;                      // lag table entries (tensor
 // per thread: lane t fetches column i from lane (t + i) mod 32.  Plain blocks: a0 / b0 collect the
 // un-wrapped cells (two chains for ILP), a1 / b1 the wrapped ones.  Mixed blocks (plan B): a = lower
 // 16-lane strip, b = upper strip, index 0 / 1 = un-wrapped / wrapped.
-template <bool MIXED>
-__device__ __forceinline__ void tc_drain_half(const uint32_t (&v)[16], int col0, int lane, bool mixed_block,
+// lag table entry += v, as 32-bit fixed point: integer atomics commute, so the result does not depend
+// on the order of the four warps (and ATOMS.ADD is native; a 64-bit add would be a CAS loop).  `fix` is
+// the power of two that maps the largest possible sum (lag 0: n_trials * scale^2) to 2^30, i.e. a
+// rounding of ~5e-10 of full scale per add.
+__device__ __forceinline__ void tc_lag_add(int* lagtab, int k, float v, int n, float fix, int* bad) {
+    if (k >= 0 && k < n) {
+        const float f = v * fix;
+        if (!(fabsf(f) < 2.0e9f)) *bad = 1;               // NaN / Inf: the particle's statistics become NaN
+        else atomicAdd(&lagtab[k], __float2int_rn(f));
+    }
+}
+
+template <bool MIXED, int COL0>
+__device__ __forceinline__ void tc_drain_half(const uint32_t (&v)[16], int lane, bool mixed_block,
                                               float& a0, float& a1, float& b0, float& b1) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int src = lane + col0 + i;
+        const int src = lane + COL0 + i;
         const float x = __uint_as_float(__shfl_sync(0xffffffffu, v[i], src));
         const bool wrap = src >= 32;
         if (MIXED && mixed_block) {
@@ -144,6 +156,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     __shared__ __align__(8) uint64_t bar_acc_full, bar_acc_empty, bar_tail_full, bar_tail_free;
     __shared__ float tailred[kTcMaxGroups][4][4 * kTailK];           // [group][warp][tail lag] per-particle sums
     __shared__ uint32_t tmem_slot;
+    __shared__ int nonfinite;                                         // a drained sum of the current particle was NaN / Inf
     __shared__ SimShared<kTcGroupThreads> shs[kTcMaxGroups];
     __shared__ double red[4];
 
@@ -152,8 +165,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches stay convergent
     const int op_bytes = 16 * P.sbo_bytes;                       // one fp16 operand plane (hi or lo)
     unsigned char* opnd = smem_raw;                              // [G][2 buffers][hi, lo] planes
-    float* epi = reinterpret_cast<float*>(smem_raw + (size_t)P.epi_offset);
-    float* lagtab = epi;                                         // [kTcLagTab]
+    int* lagtab = reinterpret_cast<int*>(smem_raw + (size_t)P.epi_offset);   // [kTcLagTab] fixed point
 
     // ---- one-time setup ------------------------------------------------------------------
     {
@@ -162,8 +174,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
+        nonfinite = 0;
         for (int g = 0; g < G; ++g)
-            for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_full[g][b], kTcGroupThreads); tc::mbar_init(&bar_empty[g][b], 4); }
+            for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_full[g][b], kTcGroupThreads / 32); tc::mbar_init(&bar_empty[g][b], 4); }
         tc::mbar_init(&bar_acc_full, 4);
         tc::mbar_init(&bar_acc_empty, 4);
         tc::mbar_init(&bar_tail_full, (uint32_t)(4 * G));
@@ -228,7 +241,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 else
                     tc::mbar_wait(sink.wait_bar, sink.wait_parity);
                 tc::fence_proxy_async_smem();                     // my operand stores -> async proxy
-                tc::mbar_arrive(&bar_full[g][buf]);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_full[g][buf]);    // one arrival per warp
                 if (TAIL) {
                     // lags beyond the tensor-memory plan: read the trial back from its operand planes (the
                     // MMAs only read them too; the buffer is rewritten two trials from now)
@@ -269,15 +283,6 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
 
         uint32_t it = 0, seg_it = 0;
         for (int64_t particle = blockIdx.x; particle < P.n_particles; particle += gridDim.x, ++it) {
-            // per block: diagonal sums  [0] offset +lane, [1] offset lane - 32; mixed blocks (plan B,
-            // c < 4) keep the two 16-lane halves apart: du belongs to the upper half
-            float ds[16][2];
-            float du[4][2];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) { ds[c][0] = 0.f; ds[c][1] = 0.f; }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { du[c][0] = 0.f; du[c][1] = 0.f; }
-
             for (int seg0 = 0; seg0 < P.n_trials; seg0 += P.seg_trials, ++seg_it) {
                 {
                     // ---- issue this warp's share of the segment's MMAs as the groups deliver their trials
@@ -317,23 +322,34 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 tc::fence_after_thread_sync();
                 // ---- drain: diagonal sums by lane rotation.  Lane t receives column i of TMEM lane
                 // (t + i) mod 32, i.e. the cell of diagonal (column - row) = -t, or 32 - t once t + i wraps.
-                // 16 columns at a time, the next tcgen05.ld in flight under the shuffles of the current one ----
-                {
+                // 16 columns at a time, the next tcgen05.ld in flight under the shuffles of the current one.
+                // The loop over blocks is NOT unrolled (the unrolled drain was instruction-fetch bound:
+                // 7 us per drain) and the sums go straight into the lag table as 32-bit fixed point
+                // (native 32-bit integer atomics: the order of the four warps does not matter - deterministic) ----
+                if (!(P.debug & 8)) {                             // debug bit 3: segment handshake without the drain
                     const uint32_t t_q = tmem_base + ((uint32_t)(32 * q) << 16);
                     uint32_t va[16], vb[16];
                     tc::tmem_ld_32x16_issue(t_q, va);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        if (c < n_cb) {
-                            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // mixed: lower no-wrap / wrap, upper no-wrap / wrap
-                            tc::tmem_ld_wait(va);
-                            tc::tmem_ld_32x16_issue(t_q + (uint32_t)(32 * c + 16), vb);
-                            tc_drain_half<MIXED>(va, 0, lane, c < 4, a0, a1, b0, b1);
-                            tc::tmem_ld_wait(vb);
-                            if (c + 1 < n_cb) tc::tmem_ld_32x16_issue(t_q + (uint32_t)(32 * (c + 1)), va);
-                            tc_drain_half<MIXED>(vb, 16, lane, c < 4, a0, a1, b0, b1);
-                            if (MIXED && c < 4) { ds[c][0] += a0; ds[c][1] += a1; du[c][0] += b0; du[c][1] += b1; }
-                            else { ds[c][0] += a0 + b0; ds[c][1] += a1 + b1; }
+#pragma unroll 1
+                    for (int c = 0; c < n_cb; ++c) {
+                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // mixed: lower no-wrap / wrap, upper no-wrap / wrap
+                        const bool mixed_block = MIXED && c < 4;
+                        tc::tmem_ld_wait(va);
+                        tc::tmem_ld_32x16_issue(t_q + (uint32_t)(32 * c + 16), vb);
+                        tc_drain_half<MIXED, 0>(va, lane, mixed_block, a0, a1, b0, b1);
+                        tc::tmem_ld_wait(vb);
+                        if (c + 1 < n_cb) tc::tmem_ld_32x16_issue(t_q + (uint32_t)(32 * (c + 1)), va);
+                        tc_drain_half<MIXED, 16>(vb, lane, mixed_block, a0, a1, b0, b1);
+                        if (mixed_block) {
+                            // lower strip: lag = 32 c - 16 q - lane (+ 32 after the wrap);
+                            // upper strip: rows a = 48 + 16 q + lane, columns of D_4 (c < 2) start at v = 512
+                            const int kl = 32 * c - 16 * q - lane;
+                            const int ku = 32 * c - 48 - 16 * q - lane + (c < 2 ? 512 : 0);
+                            tc_lag_add(lagtab, kl, a0, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, kl + 32, a1, P.tc_lags, P.tc_fix, &nonfinite);
+                            tc_lag_add(lagtab, ku, b0, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, ku + 32, b1, P.tc_lags, P.tc_fix, &nonfinite);
+                        } else {
+                            const int k = 32 * (c - q) - lane;
+                            tc_lag_add(lagtab, k, a0 + b0, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, k + 32, a1 + b1, P.tc_lags, P.tc_fix, &nonfinite);
                         }
                     }
                 }
@@ -342,48 +358,18 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 if (lane == 0) tc::mbar_arrive(&bar_acc_empty);   // this quarter of the tensor memory is free
             }
 
-            // ---- fold the diagonal sums into the lag table (fixed order: deterministic) ----------
-            for (int ph = 0; ph < 4; ++ph) {
-                if (ph == q) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        if (c < n_cb) {
-                            if (MIXED && c < 4) {
-                                // lower strip: lag = 32 c - 16 q - lane (+ 32 after the wrap);
-                                // upper strip: rows a = 48 + 16 q + lane, columns of D_4 (c < 2) start at v = 512
-                                int k = 32 * c - 16 * q - lane;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
-                                __syncwarp();
-                                k += 32;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
-                                __syncwarp();
-                                k = 32 * c - 48 - 16 * q - lane + (c < 2 ? 512 : 0);
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += du[c][0];
-                                __syncwarp();
-                                k += 32;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += du[c][1];
-                                __syncwarp();
-                            } else {
-                                int k = 32 * (c - q) - lane;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][0];
-                                __syncwarp();
-                                k += 32;
-                                if (k >= 0 && k < P.tc_lags) lagtab[k] += ds[c][1];
-                                __syncwarp();
-                            }
-                        }
-                    }
-                }
-                tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
-            }
+            tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);           // every quarter has added its last segment
 
             // ---- trial mean, distance ---------------------------------------------------------------
             if (TAIL) tc::mbar_wait(&bar_tail_full, it & 1u);
+            const bool bad_particle = nonfinite != 0;
             double local = 0.0;
             for (int k = e_tid; k < P.n_lags; k += kTcEpiThreads) {
                 float sk;
-                if (!TAIL || k < P.tc_lags) {
-                    sk = lagtab[k];
+                if (bad_particle) {
+                    sk = __int_as_float(0x7fc00000);
+                } else if (!TAIL || k < P.tc_lags) {
+                    sk = (float)lagtab[k] * P.tc_unfix;
                 } else {
                     sk = 0.f;
                     for (int gg = 0; gg < G; ++gg)
@@ -402,7 +388,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                 P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
                 if (TAIL) tc::mbar_arrive(&bar_tail_free);
             }
-            for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0.f;
+            for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0;
+            if (e_tid == 0) nonfinite = 0;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
         }
     }
@@ -495,7 +482,7 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         const int rows_tail = (reach + 127) / 128;
         if (rows_tail > rows_min) rows_min = rows_tail;
     }
-    const size_t epi = (size_t)kTcLagTab * sizeof(float);
+    const size_t epi = (size_t)kTcLagTab * sizeof(int);
     const int want_groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
     auto fit = [&](int rows, int groups, size_t* epi_off, size_t* total) {
         const size_t buffer = (size_t)2 * 16 * rows * 16;   // hi + lo planes of one trial
@@ -534,6 +521,10 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     if (e_terms && (atoi(e_terms) == 2 || atoi(e_terms) == 3)) g->n_terms = atoi(e_terms);
     int p2 = 1; while (p2 * p2 < n_t) p2 <<= 1;                 // power of two near sqrt(n_t): series ~ N(0,1)
     g->tc_scale = (float)p2;
+    // fixed-point unit of the lag table: n_trials * scale^2 * fix <= 2^30
+    double fix = 1073741824.0 / ((double)(n_trials > 0 ? n_trials : 1) * (double)p2 * (double)p2);
+    int e2 = 0; while (fix >= 2.0 && e2 < 30) { fix *= 0.5; ++e2; }
+    g->tc_fix = (float)(1u << e2);
     g->grid = sm_count;
     return 0;
 }

@@ -293,6 +293,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
             P.op_idesc[o] = t.op_idesc[o]; P.op_taddr[o] = t.op_taddr[o];
         }
         P.tc_scale = t.tc_scale; P.tc_unscale = 1.0f / (t.tc_scale * t.tc_scale);
+        P.tc_fix = t.tc_fix; P.tc_unfix = 1.0f / t.tc_fix;
         P.smem_bytes = t.smem_bytes;
         { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
         e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,

@@ -122,7 +122,7 @@ struct AbcTcGeometry {
     int n_ops;
     int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
-    float tc_scale;
+    float tc_scale, tc_fix;
     int grid;
     size_t smem_bytes;
 };
@@ -152,7 +152,7 @@ struct AbcTcParams {
     int n_ops;
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
-    float tc_scale, tc_unscale;
+    float tc_scale, tc_unscale, tc_fix, tc_unfix;
     size_t smem_bytes;
     int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = no MMAs, 2 = no simulation after the first particle
 };
