@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const AbcAcfP
     for (int k = tid; k < P.n_lags; k += NT) {
         float s = 0.f;
         for (int st = 0; st < P.n_streams; ++st) s += part[st * row + k];
-        const double v = (double)s * inv_trials;
+        const double v = __dmul_rn((double)s, inv_trials);   // no FMA contraction: same bits with and without stats_out
         if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
         const double tgt = (double)P.target[k];
         const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));

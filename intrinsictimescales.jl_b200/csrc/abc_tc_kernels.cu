@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                     for (int gg = 0; gg < G; ++gg)
                         for (int w = 0; w < 4; ++w) sk += tailred[gg][w][k - P.tail_start];
                 }
-                const double v = (double)(sk * P.tc_unscale) * inv_trials;
+                const double v = __dmul_rn((double)(sk * P.tc_unscale), inv_trials);   // no FMA contraction with the
+                                                                                      // subtraction below: same bits with and without stats_out
                 if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
                 const double tgt = (double)P.target[k];
                 const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
