@@ -86,7 +86,7 @@ int itjl_psd_hamming(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     int n2 = 2; while (n2 < n_t) n2 <<= 1; n2 <<= 1;             // 2 * nextpow2(n_t)
     int log2_n2 = 0; while ((1 << log2_n2) < n2) log2_n2++;
-    const size_t smem = (size_t)n2 * sizeof(float);
+    const size_t smem = psd_fft_smem_bytes(n2);
     if ((int64_t)smem > ctx->max_smem_optin) return fail(ctx, ITJL_ERR_ARG, "itjl_psd_hamming: FFT does not fit in shared memory");
     std::vector<float> win((size_t)n_t);
     std::vector<float2> tw((size_t)n2 / 2);

@@ -62,6 +62,7 @@ struct AbcPsdParams {
 };
 size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out);
 int psd_fft_pos(int k, int N);
+size_t psd_fft_smem_bytes(int n2);
 cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st);
 // standalone: comp_psd_adfriendly on stored data (n_slices x n_t col-major double)
 cudaError_t psd_data_launch(const double* data, int64_t n_slices, int n_t, int n2, int log2_n2,

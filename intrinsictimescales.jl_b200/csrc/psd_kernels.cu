@@ -29,63 +29,105 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// In-place radix-4 (+ final radix-2) DIF FFT of N complex points in shared memory (NT threads).
+// Shared-memory layout of the FFT buffer: one float2 of padding after every 16 points.  The stages
+// with quarter-span q >= 16 stay conflict free (32 consecutive points = two 128-byte wavefronts) and
+// the fused radix-16 tail below reads element e of 32 different 16-point groups at a stride of 17
+// float2 = 34 words - also two wavefronts, where the unpadded strides of 16 / 4 float2 cost 8.
+__host__ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
+__host__ __device__ __forceinline__ int fft_buf_len(int N) { return N + (N >> 4) + 1; }     // float2 entries
+
+__device__ __forceinline__ void bfly4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 a0 = make_float2(x0.x + x2.x, x0.y + x2.y);
+    const float2 a1 = make_float2(x0.x - x2.x, x0.y - x2.y);
+    const float2 a2 = make_float2(x1.x + x3.x, x1.y + x3.y);
+    const float2 a3 = make_float2(x1.x - x3.x, x1.y - x3.y);
+    x0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+    x1 = make_float2(a1.x + a3.y, a1.y - a3.x);      // a1 - i a3
+    x2 = make_float2(a0.x - a2.x, a0.y - a2.y);
+    x3 = make_float2(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
+}
+
+// In-place DIF FFT of N = 2^m >= 16 complex points in padded shared memory (NT threads): one radix-2
+// stage first when m is odd, radix-4 stages down to span 64, then the last two radix-4 stages (span 16
+// and 4) fused in registers, 16 points per thread.  Output in digit-reversed order (fft_pos).
 template <int NT>
 __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* __restrict__ U) {
     const int tid = threadIdx.x;
     int span = N;
-    while (span >= 4) {
+    int log2n = 0; while ((1 << log2n) < N) ++log2n;
+    if (log2n & 1) {
+        const int h = N >> 1;
+        for (int u = tid; u < h; u += NT) {
+            const float2 x0 = buf[fft_pad(u)], x1 = buf[fft_pad(u + h)];
+            buf[fft_pad(u)] = make_float2(x0.x + x1.x, x0.y + x1.y);
+            float2 y1 = make_float2(x0.x - x1.x, x0.y - x1.y);
+            if (u != 0) y1 = cmul(y1, __ldg(U + 2 * u));                 // W_N^u = U[2u]
+            buf[fft_pad(u + h)] = y1;
+        }
+        __syncthreads();
+        span = h;
+    }
+    while (span > 16) {
         const int q = span >> 2;
         const int tstep = (2 * N) / span;          // W_span^j = U[j * tstep]
         for (int u = tid; u < (N >> 2); u += NT) {
             const int j = u & (q - 1);
             const int base = (u / q) * span + j;
-            const float2 x0 = buf[base], x1 = buf[base + q], x2 = buf[base + 2 * q], x3 = buf[base + 3 * q];
-            const float2 a0 = make_float2(x0.x + x2.x, x0.y + x2.y);
-            const float2 a1 = make_float2(x0.x - x2.x, x0.y - x2.y);
-            const float2 a2 = make_float2(x1.x + x3.x, x1.y + x3.y);
-            const float2 a3 = make_float2(x1.x - x3.x, x1.y - x3.y);
-            const float2 y0 = make_float2(a0.x + a2.x, a0.y + a2.y);
-            float2 y1 = make_float2(a1.x + a3.y, a1.y - a3.x);      // a1 - i a3
-            float2 y2 = make_float2(a0.x - a2.x, a0.y - a2.y);
-            float2 y3 = make_float2(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
+            const int p0 = fft_pad(base), p1 = fft_pad(base + q), p2 = fft_pad(base + 2 * q), p3 = fft_pad(base + 3 * q);
+            float2 x0 = buf[p0], x1 = buf[p1], x2 = buf[p2], x3 = buf[p3];
+            bfly4(x0, x1, x2, x3);
             if (j != 0) {
                 // one table read per butterfly: W^2j and W^3j by complex multiplication
                 const float2 w1 = tw_lookup(U, j * tstep, N);
                 const float2 w2 = cmul(w1, w1);
                 const float2 w3 = cmul(w2, w1);
-                y1 = cmul(y1, w1);
-                y2 = cmul(y2, w2);
-                y3 = cmul(y3, w3);
+                x1 = cmul(x1, w1);
+                x2 = cmul(x2, w2);
+                x3 = cmul(x3, w3);
             }
-            buf[base] = y0; buf[base + q] = y1; buf[base + 2 * q] = y2; buf[base + 3 * q] = y3;
+            buf[p0] = x0; buf[p1] = x1; buf[p2] = x2; buf[p3] = x3;
         }
         __syncthreads();
         span = q;
     }
-    if (span == 2) {
-        for (int u = tid; u < (N >> 1); u += NT) {
-            const float2 x0 = buf[2 * u], x1 = buf[2 * u + 1];
-            buf[2 * u] = make_float2(x0.x + x1.x, x0.y + x1.y);
-            buf[2 * u + 1] = make_float2(x0.x - x1.x, x0.y - x1.y);
+    // span == 16: stages q = 4 and q = 1 of one 16-point group per thread; W_16^m are constants
+    {
+        constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+        for (int gidx = tid; gidx < (N >> 4); gidx += NT) {
+            float2* grp = buf + gidx * 17;
+            float2 x[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) x[e] = grp[e];
+            bfly4(x[0], x[4], x[8], x[12]);
+            bfly4(x[1], x[5], x[9], x[13]);
+            x[5] = cmul(x[5], make_float2(C1, -S1)); x[9] = cmul(x[9], make_float2(C2, -C2)); x[13] = cmul(x[13], make_float2(S1, -C1));
+            bfly4(x[2], x[6], x[10], x[14]);
+            x[6] = cmul(x[6], make_float2(C2, -C2)); x[10] = make_float2(x[10].y, -x[10].x); x[14] = cmul(x[14], make_float2(-C2, -C2));
+            bfly4(x[3], x[7], x[11], x[15]);
+            x[7] = cmul(x[7], make_float2(S1, -C1)); x[11] = cmul(x[11], make_float2(-C2, -C2)); x[15] = cmul(x[15], make_float2(-C1, S1));
+#pragma unroll
+            for (int b4 = 0; b4 < 16; b4 += 4) bfly4(x[b4], x[b4 + 1], x[b4 + 2], x[b4 + 3]);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) grp[e] = x[e];
         }
         __syncthreads();
     }
 }
 
-// storage position of frequency k after fft_inplace_dif
+// storage position (unpadded index) of frequency k after fft_inplace_dif
 __host__ __device__ __forceinline__ int fft_pos(int k, int N) {
     int p = 0, size = N;
+    int log2n = 0; while ((1 << log2n) < N) ++log2n;
+    if (log2n & 1) { size >>= 1; p += (k & 1) * size; k >>= 1; }
     while (size >= 4) { size >>= 2; p += (k & 3) * size; k >>= 2; }
-    if (size == 2) p += (k & 1);
     return p;
 }
 
 // |X[k]|^2 of the length-2N real FFT from the packed complex FFT, 1 <= k <= N-1
 __device__ __forceinline__ float real_fft_power(const float2* __restrict__ buf, int k, int N,
                                                 const float2* __restrict__ U) {
-    const float2 zk = buf[fft_pos(k, N)];
-    const float2 zn = buf[fft_pos(N - k, N)];
+    const float2 zk = buf[fft_pad(fft_pos(k, N))];
+    const float2 zn = buf[fft_pad(fft_pos(N - k, N))];
     const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);        // E = (Zk + conj Zn)/2
     const float dr = 0.5f * (zk.x - zn.x), di = 0.5f * (zk.y + zn.y);        // D = (Zk - conj Zn)/2
     const float or_ = di, oi = -dr;                                          // O = -i D
@@ -115,9 +157,9 @@ template <bool OSC>
 __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P) {
     constexpr int NT = kPsdThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats = N float2
-    float2* buf = reinterpret_cast<float2*>(smem_raw);
-    float* accb = xs + P.xs_len;                                    // n_stats
+    float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats: one simulated trial
+    float2* buf = reinterpret_cast<float2*>(xs + P.xs_len);         // padded FFT buffer, fft_buf_len(N) float2
+    float* accb = reinterpret_cast<float*>(buf + fft_buf_len(P.n2 >> 1));    // n_stats
     SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb + ((P.n_stats + 3) & ~3));
     __shared__ double red[NT / 32];
 
@@ -151,9 +193,18 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
         // standardised series * data_sd; the reference then adds data_mean and
         // comp_psd_adfriendly removes the mean again (summary.jl:209) - skipped both.
         simulate_trial<NT, false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, 0.0f, sim_cache);
-        for (int i = P.chunk * NT + tid; i < P.xs_len; i += NT) xs[i] = 0.f;
         __syncthreads();
-        for (int j = tid; j < P.n_t; j += NT) xs[j] *= __ldg(P.window + j);
+        // window, pack z[m] = x[2m] + i x[2m+1] into the padded FFT buffer, zero-pad to N points
+        // (xs holds zeros from n_t to chunk * NT)
+        for (int m = tid; m < N; m += NT) {
+            float2 z = make_float2(0.f, 0.f);
+            if (2 * m < P.n_t) {
+                const float2 v = *reinterpret_cast<const float2*>(xs + 2 * m);
+                z.x = v.x * __ldg(P.window + 2 * m);
+                if (2 * m + 1 < P.n_t) z.y = v.y * __ldg(P.window + 2 * m + 1);
+            }
+            buf[fft_pad(m)] = z;
+        }
         __syncthreads();
         fft_inplace_dif<NT>(buf, N, P.twiddle);
         for (int b = tid; b < P.n_stats; b += NT)
@@ -202,25 +253,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_psd_data(const double* __restri
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) mean += red[w];
     mean /= (double)n_t;
-    for (int j = tid; j < n2; j += kThreads)
-        xs[j] = (j < n_t) ? (float)((data[s + (size_t)j * n_slices] - mean) * (double)__ldg(window + j)) : 0.f;
+    for (int j = tid; j < n2; j += kThreads) {
+        const float v = (j < n_t) ? (float)((data[s + (size_t)j * n_slices] - mean) * (double)__ldg(window + j)) : 0.f;
+        xs[2 * fft_pad(j >> 1) + (j & 1)] = v;
+    }
     __syncthreads();
     fft_inplace_dif<kThreads>(buf, N, U);
     for (int k = 1 + tid; k < N; k += kThreads)
         out[s + (size_t)(k - 1) * n_slices] = (double)real_fft_power(buf, k, N, U) * psd_scale;
 }
 
-int psd_fft_pos(int k, int N) { return fft_pos(k, N); }
+int psd_fft_pos(int k, int N) { return fft_pad(fft_pos(k, N)); }      // position in the padded buffer
+size_t psd_fft_smem_bytes(int n2) { return (size_t)fft_buf_len(n2 / 2) * sizeof(float2); }
 
 size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out) {
     int c = (n_t + kPsdThreads - 1) / kPsdThreads;
     c = (c + 3) & ~3;
-    int xs_len = n2;                                   // N float2 = n2 floats
-    if (xs_len < c * kPsdThreads) xs_len = c * kPsdThreads;
+    const int xs_len = c * kPsdThreads;                // staging buffer of one simulated trial
     *chunk_out = c;
     *xs_len_out = xs_len;
-    return (size_t)xs_len * sizeof(float) + (size_t)((n_stats + 3) & ~3) * sizeof(float) +
-           sizeof(SimShared<kPsdThreads>);
+    return (size_t)xs_len * sizeof(float) + (size_t)fft_buf_len(n2 / 2) * sizeof(float2) +
+           (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPsdThreads>);
 }
 
 void psd_make_tables(int n_t, int n2, float* window_host, float2* twiddle_host, double* win_ss) {
