@@ -184,7 +184,9 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         std::vector<int4> binpos((size_t)d.n_stats);
         for (int64_t i = 0; i < d.n_stats; ++i) {
             const int k = d.freq_bins[i] + 1, N = m->n2 / 2;
-            binpos[i] = make_int4(psd_fft_pos(k, N), psd_fft_pos(N - k, N), k, 0);
+            int wx, wy;                                     // the bin's twiddle exp(-2 pi i k / n2), as float bits
+            memcpy(&wx, &tw[(size_t)k].x, 4); memcpy(&wy, &tw[(size_t)k].y, 4);
+            binpos[i] = make_int4(psd_fft_pos(k, N), psd_fft_pos(N - k, N), wx, wy);
         }
         rc = upload(ctx, m->bins, binpos.data(), binpos.size() * sizeof(int4));
         if (rc == ITJL_OK) rc = upload(ctx, m->window, win.data(), win.size() * sizeof(float));

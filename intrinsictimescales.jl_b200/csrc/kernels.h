@@ -50,7 +50,7 @@ struct AbcPsdParams {
     uint32_t k0, k1, c3_noise, c3_init;
     int64_t particle_offset;
     const float* target;        // n_stats
-    const int4* binpos;         // n_stats: {storage pos of Z[k], of Z[N-k], k, 0}, k = bin + 1
+    const int4* binpos;         // n_stats: {storage pos of Z[k], of Z[N-k], bits of the twiddle exp(-2 pi i k / n2)}, k = bin + 1
     const float* window;        // n_t Hamming window
     const float2* twiddle;      // n2/2 complex roots exp(-2 pi i k / (n2/2))... see psd_kernels.cu
     double psd_scale;           // 1 / (fs * sum(window^2))

@@ -29,6 +29,31 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+// Two-level twiddle table in shared memory: exp(-2 pi i idx / 2N) = A[idx >> 7] * B[idx & 127]
+// (2N/128 + 128 entries, 3 KB at N = 16384).  The butterflies of the large stages read twiddles all over
+// the 2N-entry table; from global memory those loads were the kernel's top stall (L2 latency - the
+// FFT buffer leaves no L1).
+constexpr int kTwLoBits = 7;
+__host__ __device__ __forceinline__ int tw2_entries(int N) {
+    const int hi = (2 * N) >> kTwLoBits;
+    return (hi > 0 ? hi : 1) + (1 << kTwLoBits);
+}
+struct Tw2 {
+    const float2* A;
+    const float2* B;
+    __device__ __forceinline__ float2 operator()(int idx) const {
+        return cmul(A[idx >> kTwLoBits], B[idx & ((1 << kTwLoBits) - 1)]);
+    }
+};
+// fills tab[0 .. tw2_entries(N)) from the global table U (all threads of the CTA; caller syncs)
+__device__ __forceinline__ Tw2 tw2_build(float2* tab, const float2* __restrict__ U, int N, int tid, int nt) {
+    const int hi = ((2 * N) >> kTwLoBits) > 0 ? ((2 * N) >> kTwLoBits) : 1;
+    for (int h = tid; h < hi; h += nt) tab[h] = tw_lookup(U, h << kTwLoBits, N);
+    for (int l = tid; l < (1 << kTwLoBits); l += nt) tab[hi + l] = (l < 2 * N) ? tw_lookup(U, l, N) : make_float2(1.f, 0.f);
+    Tw2 t; t.A = tab; t.B = tab + hi;
+    return t;
+}
+
 // Shared-memory layout of the FFT buffer: one float2 of padding after every 16 points.  The stages
 // with quarter-span q >= 16 stay conflict free (32 consecutive points = two 128-byte wavefronts) and
 // the fused radix-16 tail below reads element e of 32 different 16-point groups at a stride of 17
@@ -51,7 +76,7 @@ __device__ __forceinline__ void bfly4(float2& x0, float2& x1, float2& x2, float2
 // stage first when m is odd, radix-4 stages down to span 64, then the last two radix-4 stages (span 16
 // and 4) fused in registers, 16 points per thread.  Output in digit-reversed order (fft_pos).
 template <int NT>
-__device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* __restrict__ U) {
+__device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
     const int tid = threadIdx.x;
     int span = N;
     int log2n = 0; while ((1 << log2n) < N) ++log2n;
@@ -61,7 +86,7 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* _
             const float2 x0 = buf[fft_pad(u)], x1 = buf[fft_pad(u + h)];
             buf[fft_pad(u)] = make_float2(x0.x + x1.x, x0.y + x1.y);
             float2 y1 = make_float2(x0.x - x1.x, x0.y - x1.y);
-            if (u != 0) y1 = cmul(y1, __ldg(U + 2 * u));                 // W_N^u = U[2u]
+            if (u != 0) y1 = cmul(y1, tw(2 * u));                        // W_N^u = exp(-2 pi i 2u / 2N)
             buf[fft_pad(u + h)] = y1;
         }
         __syncthreads();
@@ -78,7 +103,7 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const float2* _
             bfly4(x0, x1, x2, x3);
             if (j != 0) {
                 // one table read per butterfly: W^2j and W^3j by complex multiplication
-                const float2 w1 = tw_lookup(U, j * tstep, N);
+                const float2 w1 = tw(j * tstep);
                 const float2 w2 = cmul(w1, w1);
                 const float2 w3 = cmul(w2, w1);
                 x1 = cmul(x1, w1);
@@ -137,17 +162,17 @@ __device__ __forceinline__ float real_fft_power(const float2* __restrict__ buf, 
     return xr * xr + xi * xi;
 }
 
-// same with the two storage positions precomputed on the host (AbcPsdParams::binpos)
-__device__ __forceinline__ float real_fft_power_at(const float2* __restrict__ buf, int4 bp,
-                                                   const float2* __restrict__ U) {
+// same with the two storage positions and the bin's twiddle precomputed on the host
+// (AbcPsdParams::binpos = {pos(k), pos(N - k), bits of cos, bits of -sin})
+__device__ __forceinline__ float real_fft_power_at(const float2* __restrict__ buf, int4 bp) {
     const float2 zk = buf[bp.x];
     const float2 zn = buf[bp.y];
     const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);
     const float dr = 0.5f * (zk.x - zn.x), di = 0.5f * (zk.y + zn.y);
     const float or_ = di, oi = -dr;
-    const float2 w = __ldg(U + bp.z);
-    const float xr = er + (w.x * or_ - w.y * oi);
-    const float xi = ei + (w.x * oi + w.y * or_);
+    const float wx = __int_as_float(bp.z), wy = __int_as_float(bp.w);
+    const float xr = er + (wx * or_ - wy * oi);
+    const float xi = ei + (wx * oi + wy * or_);
     return xr * xr + xi * xi;
 }
 
@@ -161,6 +186,7 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
     float2* buf = reinterpret_cast<float2*>(xs + P.xs_len);         // padded FFT buffer, fft_buf_len(N) float2
     float* accb = reinterpret_cast<float*>(buf + fft_buf_len(P.n2 >> 1));    // n_stats
     SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb + ((P.n_stats + 3) & ~3));
+    float2* twtab = reinterpret_cast<float2*>(sh + 1);
     __shared__ double red[NT / 32];
 
     const int tid = threadIdx.x;
@@ -188,6 +214,7 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
     g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;
 
     for (int b = tid; b < P.n_stats; b += NT) accb[b] = 0.f;
+    const Tw2 tw = tw2_build(twtab, P.twiddle, N, tid, NT);          // visible after the first __syncthreads() below
 
     for (int trial = 0; trial < P.n_trials; ++trial) {
         // standardised series * data_sd; the reference then adds data_mean and
@@ -206,9 +233,9 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
             buf[fft_pad(m)] = z;
         }
         __syncthreads();
-        fft_inplace_dif<NT>(buf, N, P.twiddle);
+        fft_inplace_dif<NT>(buf, N, tw);
         for (int b = tid; b < P.n_stats; b += NT)
-            accb[b] += real_fft_power_at(buf, __ldg(P.binpos + b), P.twiddle);
+            accb[b] += real_fft_power_at(buf, __ldg(P.binpos + b));
         __syncthreads();
     }
 
@@ -244,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_psd_data(const double* __restri
     const int tid = threadIdx.x;
     const int64_t s = blockIdx.x;
     const int N = n2 >> 1;
+    const Tw2 tw = tw2_build(buf + fft_buf_len(N), U, N, tid, kThreads);
     double local = 0.0;
     for (int j = tid; j < n_t; j += kThreads) local += data[s + (size_t)j * n_slices];
     local = warp_sum(local);
@@ -258,13 +286,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_psd_data(const double* __restri
         xs[2 * fft_pad(j >> 1) + (j & 1)] = v;
     }
     __syncthreads();
-    fft_inplace_dif<kThreads>(buf, N, U);
+    fft_inplace_dif<kThreads>(buf, N, tw);
     for (int k = 1 + tid; k < N; k += kThreads)
         out[s + (size_t)(k - 1) * n_slices] = (double)real_fft_power(buf, k, N, U) * psd_scale;
 }
 
 int psd_fft_pos(int k, int N) { return fft_pad(fft_pos(k, N)); }      // position in the padded buffer
-size_t psd_fft_smem_bytes(int n2) { return (size_t)fft_buf_len(n2 / 2) * sizeof(float2); }
+size_t psd_fft_smem_bytes(int n2) { return (size_t)(fft_buf_len(n2 / 2) + tw2_entries(n2 / 2)) * sizeof(float2); }
 
 size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out) {
     int c = (n_t + kPsdThreads - 1) / kPsdThreads;
@@ -273,7 +301,8 @@ size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_
     *chunk_out = c;
     *xs_len_out = xs_len;
     return (size_t)xs_len * sizeof(float) + (size_t)fft_buf_len(n2 / 2) * sizeof(float2) +
-           (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPsdThreads>);
+           (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPsdThreads>) +
+           (size_t)tw2_entries(n2 / 2) * sizeof(float2);
 }
 
 void psd_make_tables(int n_t, int n2, float* window_host, float2* twiddle_host, double* win_ss) {
