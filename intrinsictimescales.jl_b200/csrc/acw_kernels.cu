@@ -15,6 +15,8 @@
 // stream), 100 DFMA per 10 LDS.128.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace itjl {
@@ -487,8 +489,17 @@ __global__ void __launch_bounds__(256) k_acw_finish(const AcwFinishParams P) {
     const bool col_ok = s0 + lane < P.n_slices;
     for (int r = warp; r < SPART; r += 8) {
         double v = 0.0;
-        if (col_ok)
-            for (int g = 0; g < P.n_seg; ++g) v += (double)P.part[((size_t)g * SPART + r) * ld + s0 + lane];
+        if (col_ok) {
+            const float* src = P.part + (size_t)r * ld + s0 + lane;
+            const size_t gs = (size_t)SPART * ld;
+            int g = 0;
+            for (; g + 4 <= P.n_seg; g += 4) {              // four independent loads in flight
+                const float p0 = src[(size_t)g * gs], p1 = src[(size_t)(g + 1) * gs];
+                const float p2 = src[(size_t)(g + 2) * gs], p3 = src[(size_t)(g + 3) * gs];
+                v += (double)p0; v += (double)p1; v += (double)p2; v += (double)p3;
+            }
+            for (; g < P.n_seg; ++g) v += (double)src[(size_t)g * gs];
+        }
         tile[r][lane] = v;
     }
     for (int r = warp; r < SREF; r += 8) head[r][lane] = (col_ok && r < P.n_t) ? P.data[s0 + lane + (size_t)r * ld] : 0.0;
@@ -605,7 +616,9 @@ size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return ((size_t)n_
 void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len) {
     // ~2 x 512 resident threads per SM; segments are multiples of 32 samples and at least 256 long
     // (each one re-reads a 32-sample halo and writes 33 partial sums per slice)
-    int g = (int)((2LL * 512 * sm_count + n_slices - 1) / n_slices);
+    const char* e_w = getenv("ITJL_ACW_WAVES");
+    const int waves = (e_w && atoi(e_w) > 0) ? atoi(e_w) : 2;
+    int g = (int)(((long long)waves * 512 * sm_count + n_slices - 1) / n_slices);
     const int max_g = n_t / 256 > 0 ? n_t / 256 : 1;
     if (g > max_g) g = max_g;
     if (g < 1) g = 1;
