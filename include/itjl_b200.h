@@ -130,6 +130,12 @@ int itjl_model_work(const itjl_model* model, double* flops_per_sample, int64_t* 
  * `name_out` holds >= 32 bytes) and the tensor-core flops it EXECUTES per OU sample (fp16 hi/lo split,
  * tile and K padding included; 0 for the CUDA-core kernels) - the algorithmic figure is itjl_model_work's. */
 int itjl_model_kernel_info(const itjl_model* model, char* name_out, double* tensor_flops_per_sample);
+/* Host-only (no GPU needed): the tensor-memory plan k_abc_acf_tc would use for a model shape on a device
+ * with `max_smem_optin` bytes of opt-in shared memory per CTA and `sm_count` SMs (B200: 232448, 148).
+ * Returns ITJL_OK and fills out[0..15] = {groups, chunk, ksteps, rows_total, used_cols, mixed (plan B),
+ * seg_trials, n_terms, tc_lags, tail_start, tail_lt, n_ops, smem_bytes, grid, 0, 0}, or ITJL_ERR_ARG when
+ * the shape is outside the kernel's plans (the CUDA-core kernel k_abc_acf then runs). */
+int itjl_tc_plan(int64_t n_t, int64_t n_lags, int64_t n_trials, int32_t max_smem_optin, int32_t sm_count, int32_t* out);
 
 /* ---- OU generator ----------------------------------------------------------------- */
 /* generate_ou_process(tau, true_D, dt, duration, num_trials; standardize)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "itjl_acw": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "itjl_fit_expdecay": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
     "itjl_model_kernel_info": (ctypes.c_int, [_vp, _vp, _vp]),
+    "itjl_tc_plan": (ctypes.c_int, [_i64, _i64, _i64, _i32, _i32, _vp]),
     "itjl_fp32_peak": (ctypes.c_int, [_vp, _i32, _vp]),
     "itjl_ctx_timing_reset": (ctypes.c_int, [_vp]),
     "itjl_ctx_timing_get": (ctypes.c_int, [_vp, _vp, _vp]),

@@ -223,6 +223,17 @@ int itjl_model_work(const itjl_model* m, double* flops_per_sample, int64_t* samp
     return ITJL_OK;
 }
 
+int itjl_tc_plan(int64_t n_t, int64_t n_lags, int64_t n_trials, int32_t max_smem_optin, int32_t sm_count, int32_t* out) {
+    if (!out || n_t > INT32_MAX || n_lags > INT32_MAX || n_trials > INT32_MAX) return fail(nullptr, ITJL_ERR_ARG, "itjl_tc_plan: bad argument");
+    AbcTcGeometry g{};
+    const int rc = abc_tc_geometry((int)n_t, (int)n_lags, (int)n_trials, max_smem_optin, sm_count, &g);
+    if (rc != 0) return fail(nullptr, ITJL_ERR_ARG, "itjl_tc_plan: shape outside the tensor-core kernel's plans");
+    const int32_t v[16] = {g.groups, g.chunk, g.ksteps, g.rows_total, g.used_cols, g.mixed, g.seg_trials, g.n_terms,
+                           g.tc_lags, g.tail_start, g.tail_lt, g.n_ops, (int32_t)g.smem_bytes, g.grid, 0, 0};
+    memcpy(out, v, sizeof(v));
+    return ITJL_OK;
+}
+
 int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_flops_per_sample) {
     if (!m || !name_out || !tensor_flops_per_sample) return fail(m ? m->ctx : nullptr, ITJL_ERR_ARG, "itjl_model_kernel_info: null argument");
     *tensor_flops_per_sample = 0.0;

@@ -202,3 +202,27 @@ def test_two_term_split_error_model_over_many_particles(pkg, ctx):
     assert np.all(np.abs(d_tc - d_ff) <= 2 * np.sqrt(d_ff) * ACF_TOL + ACF_TOL ** 2 + 1e-5 * d_ff)
     # deterministic: integer fixed-point lag table, fixed segment order
     assert np.array_equal(g_tc.distances(theta[:300], seed=21, generation=4), d_tc[:300])   # also: stats_out does not change a bit
+
+
+def test_tc_kernel_oscillation_acf_variant(pkg, ctx):
+    """one_timescale_and_osc_model with the ACF summary (OSC = true template): n_t = 10 000 leaves room
+    for two simulate groups only; tensor-core and CUDA-core kernels agree with the oracle."""
+    dt, n_t, n_trials = 1 / 500, 10000, 5
+    t = dt * np.arange(1, n_t + 1)
+    data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.95], dt, n_t * dt, n_trials, 0.0, 1.0, seed=11, n_t=n_t)
+    po = [omodels.Normal(.1, .1), omodels.Normal(10, 5), omodels.Uniform(0, 1)]
+    om = omodels.one_timescale_and_osc_model(data, t, prior=po, summary_method="acf")
+    mk = lambda: pkg.one_timescale_and_osc_model(data, t, "abc", prior=[pkg.Normal(.1, .1), pkg.Normal(10, 5), pkg.Uniform(0, 1)],
+                                                 summary_method="acf")
+    assert mk().n_lags == om.n_lags <= 509
+    g_tc, g_ff = _gpu_models(mk, ctx)
+    rng = np.random.default_rng(2)
+    theta = np.array([[0.05, 10.0, 0.95], [0.1, 12.0, 0.5], [0.02, 8.0, 0.3]])
+    u0 = rng.standard_normal((3, n_trials)); noise = rng.standard_normal((3, n_trials, n_t))
+    phases = rng.uniform(0, 2 * np.pi, size=(3, n_trials))
+    d_tc, s_tc = g_tc.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
+    d_ff, s_ff = g_ff.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
+    for i in range(3):
+        ac = omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i], phases=phases[i]))
+        assert np.max(np.abs(s_tc[i] - ac)) <= 2e-5        # same tolerance as test_gpu_abc's oscillation ACF case
+    assert np.max(np.abs(s_tc - s_ff)) <= 2e-5

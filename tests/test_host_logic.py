@@ -116,3 +116,35 @@ def test_acw_and_model_argument_errors(pkg):
         pkg.check_model_inputs(np.zeros((2, 10)), t, "abc", "foo", None, None)
     with pytest.raises(ValueError, match="distance_method"):
         pkg.check_model_inputs(np.zeros((2, 10)), t, "abc", "acf", None, "cosine")
+
+
+def test_tensor_core_plan_selection_is_host_logic(pkg):
+    """itjl_tc_plan (no GPU): tensor-memory plan A / B, FFMA tail tiles, accumulator segments, hi/lo
+    terms and shared-memory fit of k_abc_acf_tc for the BASELINE shapes, on B200 limits."""
+    import ctypes
+    lib = pkg._lib.lib()
+    names = ["groups", "chunk", "ksteps", "rows_total", "used_cols", "mixed", "seg_trials", "n_terms",
+             "tc_lags", "tail_start", "tail_lt", "n_ops", "smem_bytes", "grid"]
+
+    def plan(n_t, n_lags, n_trials):
+        out = (ctypes.c_int32 * 16)()
+        rc = lib.itjl_tc_plan(n_t, n_lags, n_trials, 232448, 148, out)
+        return rc, dict(zip(names, list(out)))
+
+    rc, p = plan(5000, 414, 50)                       # C5: plan B, no tail, 4 x 13-trial segments, 2 terms
+    assert rc == 0 and p["mixed"] == 1 and p["n_ops"] == 6 and p["tail_lt"] == 0 and p["tc_lags"] == 414
+    assert p["groups"] == 4 and p["chunk"] == 40 and p["ksteps"] == 3 and p["seg_trials"] == 13 and p["n_terms"] == 2
+    assert p["rows_total"] >= 16 * 3 + 4 and p["smem_bytes"] + 6 * 1024 <= 232448 and p["grid"] == 148
+    rc, p = plan(5000, 463, 100)                      # C3: plan B + one tail tile of 16 lags from lag 448
+    assert rc == 0 and p["mixed"] == 1 and p["tc_lags"] == 449 and p["tail_start"] == 448 and p["tail_lt"] == 1
+    rc, p = plan(5000, 300, 2)                        # C1-like: plan A, one group per trial, 3 terms (1e4 samples)
+    assert rc == 0 and p["mixed"] == 0 and p["groups"] == 2 and p["n_terms"] == 3 and p["seg_trials"] == 2
+    assert p["used_cols"] == 432 and p["n_ops"] == 4
+    rc, p = plan(5000, 385, 8)                        # last shape of plan A: all 512 columns
+    assert rc == 0 and p["mixed"] == 0 and p["used_cols"] == 512
+    rc, p = plan(5000, 509, 8)
+    assert rc == 0 and p["tail_lt"] == 4
+    assert plan(5000, 510, 8)[0] == -1                # longer windows: CUDA-core kernel
+    rc, p = plan(10000, 430, 100)                     # longer trials: fewer simulate groups fit
+    assert rc == 0 and 1 <= p["groups"] < 4 and p["ksteps"] == 5
+    assert plan(8, 4, 2)[0] == -1 and plan(5000, 6000, 2)[0] == -1
