@@ -484,7 +484,8 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         if (rows_tail > rows_min) rows_min = rows_tail;
     }
     const size_t epi = (size_t)kTcLagTab * sizeof(int);
-    const int want_groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
+    int want_groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
+    { const char* e_g = getenv("ITJL_TC_GROUPS"); if (e_g && atoi(e_g) >= 1 && atoi(e_g) < want_groups) want_groups = atoi(e_g); }   // tuning only
     auto fit = [&](int rows, int groups, size_t* epi_off, size_t* total) {
         const size_t buffer = (size_t)2 * 16 * rows * 16;   // hi + lo planes of one trial
         *epi_off = ((size_t)groups * 2 * buffer + 127) & ~(size_t)127;
