@@ -41,8 +41,8 @@ namespace itjl {
 // Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
 // zero (measured, benchmarks/tc_probe2.py), so a long positive chain loses ~0.5 ulp per product:
 // 1.8e-5 relative over 50 trials x 5000 samples.  The accumulators are therefore drained every
-// `seg_trials` trials (~768 K rows) and the segment sums are added in fp32 registers (round to
-// nearest), which keeps the bias below 5e-6.
+// `seg_trials` trials (~768 K rows, equal segments) and the segment sums are added to a fixed-point
+// lag table, which keeps the bias below 5e-6.
 //
 // Warp roles (one persistent CTA per SM):
 //   G simulate groups of 128 threads - one trial each at a time: Philox + blocked scan as in
@@ -54,9 +54,9 @@ namespace itjl {
 //     waits for a buffer's "operands ready" mbarrier, issues its MMAs of that trial (one elected
 //     lane, descriptors warp-uniform) and commits to the buffer's "operands free" mbarrier; after
 //     the last trial of a segment it commits to "accumulators ready".  All four then tcgen05.ld
-//     the accumulators, sum them along diagonals by lane rotation (shuffles) into registers,
-//     release the tensor memory, and after the particle's last segment form the trial
-//     mean and the distance in fp64.
+//     the accumulators, sum them along diagonals by lane rotation (shuffles), add the sums to the
+//     lag table in shared memory, release the tensor memory, and after the particle's last segment
+//     form the trial mean and the distance in fp64.
 // (20 warps: the register file is allocated in units of 4 warps, 21 would cap at 80 registers.)
 constexpr int kTcGroupThreads = 128;
 constexpr int kTcMaxGroups = 4;
