@@ -16,6 +16,7 @@ from .abc import (ABCResults, abc_results, basic_abc, calc_weights, compute_adap
 from .acw import ACWResults, acw, possible_acwtypes
 from .models import (Normal, Uniform, TimescaleModel, check_model_inputs, distance_function,
                      draw_theta, generate_data, generate_data_and_reduce, one_timescale_and_osc_model,
+                     one_timescale_and_osc_with_missing_model,
                      one_timescale_model, one_timescale_with_missing_model, summary_stats)
 from .ou import generate_ou_process, generate_ou_with_oscillation
 from .summary import comp_ac_fft, comp_ac_time_missing, comp_psd_adfriendly

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const AbcAcfP
     g.noise = P.noise ? P.noise + pt * P.n_t : nullptr;
     g.phases = P.phases ? P.phases + pt : nullptr;
     g.mask_bits = P.mask_bits; g.n_valid = P.n_valid; g.mask_words = P.mask_words;
+    g.miss_mean_ratio = (OSC && P.data_sd != 0.0) ? (float)(P.data_mean / P.data_sd) : 0.f;
 
     // zero everything once: the pads at or beyond chunk*NT (and the shifted copies' ends) stay zero
     for (int i = tid; i < P.n_bufs * buf_floats; i += NT) xs0[i] = 0.f;

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         sa.inv_n = 1.0 / (double)P.n_t; sa.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
         sa.k0 = P.k0; sa.k1 = P.k1; sa.c3_noise = P.c3_noise; sa.c3_init = P.c3_init;
         sa.mask_bits = P.mask_bits; sa.n_valid = P.n_valid; sa.mask_words = P.mask_words;
+        sa.miss_mean_ratio = P.miss_mean_ratio;
 
         uint32_t it = 0;
         for (int64_t particle = blockIdx.x; particle < P.n_particles; particle += gridDim.x, ++it) {

@@ -308,6 +308,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.tc_scale = t.tc_scale; P.tc_unscale = 1.0f / (t.tc_scale * t.tc_scale);
         P.tc_fix = t.tc_fix; P.tc_unfix = 1.0f / t.tc_fix;
         P.smem_bytes = t.smem_bytes;
+        P.miss_mean_ratio = (d.kind == ITJL_KIND_OU_OSC && d.data_sd != 0.0) ? (float)(d.data_mean / d.data_sd) : 0.f;
         { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
         e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,
                           t.smem_bytes, t.grid, ctx->stream);

@@ -154,6 +154,7 @@ struct AbcTcParams {
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
     float tc_scale, tc_unscale, tc_fix, tc_unfix;
+    float miss_mean_ratio;       // data_mean / data_sd for the oscillation + missing-data model, else 0
     size_t smem_bytes;
     int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = no MMAs, 2 = no simulation after the first particle
 };

@@ -72,6 +72,8 @@ struct SimArgs {
     const double* u0;         // [trial] injected initial states of this particle, or null
     const double* noise;      // [trial][n_t] injected N(0,1) increments, or null
     const double* phases;     // [trial] injected phases (radians), or null
+    float miss_mean_ratio = 0.f;  // MISSING + OSC: data_mean / data_sd (the oscillation model adds data_mean
+                                  // before the mask is applied, so masked samples sit at -(mean of valid) - data_mean)
     const uint32_t* mask_bits;  // [trial][mask_words] missing-sample bitmap, or null
     const int* n_valid;         // [trial] number of valid samples
     int mask_words;
@@ -269,10 +271,16 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         const double nv = (double)g.n_valid[trial];
         const double m2 = (double)((float)(VX - nv * m) / (float)nv);
         const double mt = m + m2;
-        const float ssf = (float)(VXX - 2.0 * mt * VX + nv * mt * mt + (n - nv) * m2 * m2);
+        // masked samples: -m2 in units of the raw trial; the oscillation model (OSC) standardises the
+        // trial, scales by data_sd and ADDS data_mean before masking (one_timescale_and_osc_with_missing.jl
+        // :292-297 -> ou_process.jl:214), so there they sit at -(m2 + data_mean s_x / data_sd), s_x = the
+        // trial's std (n - 1)
+        double m2e = m2;
+        if (OSC) m2e += (double)g.miss_mean_ratio * sqrt((SXX - n * m * m) / (n - 1.0));
+        const float ssf = (float)(VXX - 2.0 * mt * VX + nv * mt * mt + (n - nv) * m2e * m2e);
         float r = rsqrtf(ssf);
         r = r * fmaf(-0.5f * ssf * r, r, 1.5f);
-        mf = (float)mt; rf = r; miss_val = (float)(-m2) * r;
+        mf = (float)mt; rf = r; miss_val = (float)(-m2e) * r;
     }
 
     // ---- pass B: out = (y + p c - m) r + shift = y r + p (c r) + (shift - m r) -----------

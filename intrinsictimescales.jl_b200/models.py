@@ -109,10 +109,10 @@ class GpuModel:
         self.ctx = ctx
         self.model = model
         d = _lib.ModelDesc()
-        d.kind = _lib.KIND_OU_OSC if model.kind == "one_timescale_and_osc" else _lib.KIND_OU
+        d.kind = _lib.KIND_OU_OSC if model.kind.startswith("one_timescale_and_osc") else _lib.KIND_OU
         if model.summary_method == "psd":
             d.summary = _lib.SUMMARY_PSD
-        elif model.kind == "one_timescale_with_missing":
+        elif model.kind.endswith("with_missing"):
             d.summary = _lib.SUMMARY_ACF_MISSING
         else:
             d.summary = _lib.SUMMARY_ACF
@@ -309,6 +309,29 @@ def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="ps
                           update=update)
 
 
+def one_timescale_and_osc_with_missing_model(data, time, fit_method="abc", summary_method="acf", prior=None,
+                                             n_lags=None, distance_method=None, distance_combined=False,
+                                             update="exact"):
+    """src/models/one_timescale_and_osc_with_missing.jl:159-222, ACF branch (the reference's default
+    summary_method = :psd is the Lomb-Scargle branch, outside the B200 hot path)."""
+    if distance_combined:
+        raise NotImplementedError("distance_combined is outside the B200 hot path")
+    data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
+    if summary_method != "acf":
+        raise NotImplementedError("the Lomb-Scargle PSD branch is outside the B200 hot path")
+    if prior is None:
+        raise NotImplementedError("the informed prior of the oscillation model needs the Lorentzian "
+                                  "knee fit (outside the B200 hot path): pass prior=[...] explicitly")
+    dt = float(time[1] - time[0]); T = float(time[-1])
+    mask = np.isnan(data)
+    acf_mean = summary.comp_ac_time_missing(data).mean(axis=0)
+    n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
+    return TimescaleModel("one_timescale_and_osc_with_missing", data, time, fit_method, "acf", lags, prior,
+                          distance_method or "linear", stats, dt, T, data.shape[0],
+                          float(np.nanmean(data)), float(np.nanstd(data, ddof=1)), n_lags=n_lags,
+                          missing_mask=mask, update=update)
+
+
 # ---------------------------------------------------------------- protocol ----
 def draw_theta(model, rng):
     """src/core/model.jl:154-156."""
@@ -318,10 +341,13 @@ def draw_theta(model, rng):
 def generate_data(model, theta, seed=0, ctx=None):
     """generate_data(model, theta): one synthetic data set, (numTrials, n_t)."""
     from . import ou
-    if model.kind == "one_timescale_and_osc":
-        return ou.generate_ou_with_oscillation(theta, model.dt, model.T, model.numTrials,
+    if model.kind.startswith("one_timescale_and_osc"):
+        data = ou.generate_ou_with_oscillation(theta, model.dt, model.T, model.numTrials,
                                                model.data_mean, model.data_sd, seed=seed,
                                                update=model.update, ctx=ctx)
+        if model.kind.endswith("with_missing"):
+            data[model.missing_mask] = np.nan
+        return data
     data = ou.generate_ou_process(theta[0], model.data_sd, model.dt, model.T, model.numTrials,
                                   seed=seed, update=model.update, ctx=ctx)
     if model.kind == "one_timescale_with_missing":
@@ -331,7 +357,7 @@ def generate_data(model, theta, seed=0, ctx=None):
 
 def summary_stats(model, data, ctx=None):
     if model.summary_method == "acf":
-        if model.kind == "one_timescale_with_missing":
+        if model.kind.endswith("with_missing"):
             return summary.comp_ac_time_missing(data, model.n_lags, ctx=ctx).mean(axis=0)
         return summary.comp_ac_fft(data, model.n_lags, ctx=ctx).mean(axis=0)
     psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt, ctx=ctx)

@@ -163,6 +163,26 @@ def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="ps
                  freqlims=freqlims, freq_idx=freq_idx, update=update)
 
 
+def one_timescale_and_osc_with_missing_model(data, time, fit_method="abc", summary_method="acf",
+                                             prior=None, n_lags=None, distance_method=None,
+                                             update="exact"):
+    """one_timescale_and_osc_with_missing.jl:159-222 (ACF branch; the PSD branch is Lomb-Scargle,
+    out of scope)."""
+    if summary_method != "acf":
+        raise NotImplementedError("Lomb-Scargle PSD branch is out of scope")
+    data, time, prior = _check_inputs(data, time, prior)
+    if prior is None:
+        raise NotImplementedError("informed prior needs the Lorentzian fit (out of scope)")
+    dt = float(time[1] - time[0]); T = float(time[-1])
+    mask = np.isnan(data)                                                      # :177
+    acf_mean = summary.comp_ac_time_missing(data).mean(axis=0)                 # :179-180
+    n_lags, lags, stats = _acf_setup(acf_mean, data.shape[1], dt, n_lags)      # :183-187
+    return Model("one_timescale_and_osc_with_missing", data, time, "acf",
+                 distance_method or "linear", prior, lags, stats, dt, T, data.shape[0],
+                 float(np.nanmean(data)), float(np.nanstd(data, ddof=1)),
+                 n_lags=n_lags, missing_mask=mask, update=update)
+
+
 # ------------------------------------------------------------------ protocol ----
 def draw_theta(model, rng):
     """model.jl:154-156."""
@@ -172,11 +192,15 @@ def draw_theta(model, rng):
 def generate_data(model, theta, **rng_spec):
     """generate_data methods; rng_spec = dict(seed, generation, particle) or explicit
     u0/noise/phases."""
-    if model.kind == "one_timescale_and_osc":
-        return ou.generate_ou_with_oscillation(theta, model.dt, model.T, model.numTrials,
+    if model.kind in ("one_timescale_and_osc", "one_timescale_and_osc_with_missing"):
+        data = ou.generate_ou_with_oscillation(theta, model.dt, model.T, model.numTrials,
                                                model.data_mean, model.data_sd,
                                                update=model.update, n_t=model.n_t,
                                                **rng_spec)
+        if model.kind == "one_timescale_and_osc_with_missing":
+            data = data.copy()
+            data[model.missing_mask] = np.nan             # and_osc_with_missing.jl:295
+        return data
     rng_spec.pop("phases", None)
     data = ou.generate_ou_process(theta[0], model.data_sd, model.dt, model.T,
                                   model.numTrials, update=model.update, n_t=model.n_t,
@@ -189,7 +213,7 @@ def generate_data(model, theta, **rng_spec):
 
 def summary_stats(model, data):
     if model.summary_method == "acf":
-        if model.kind == "one_timescale_with_missing":
+        if model.kind in ("one_timescale_with_missing", "one_timescale_and_osc_with_missing"):
             return summary.comp_ac_time_missing(data, model.n_lags).mean(axis=0)
         return summary.comp_ac_fft(data, model.n_lags).mean(axis=0)
     psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt)

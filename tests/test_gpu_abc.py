@@ -237,3 +237,45 @@ def test_full_size_properties_c5_shape(pkg, ctx):
     om = omodels.one_timescale_model(data, _time(n_t), prior=[omodels.Uniform(0.05, 5)])
     want = cport.abc_distances(om, theta[:2], seed=1, generation=1)
     assert np.all(np.abs(d[:2] - want) <= dist_tol(want))
+
+
+def test_oscillation_with_missing_model(pkg, ctx):
+    """one_timescale_and_osc_with_missing_model, ACF branch: the simulated trial is
+    standardised, scaled by data_sd, shifted by data_mean, masked with the data's NaN pattern, and
+    comp_ac_time_missing leaves the masked samples at -(mean of the valid samples) - so data_mean
+    matters.  Both fused kernels against the oracle, data with a clearly non-zero mean."""
+    import os
+    dt, n_t, n_trials = 1 / 500, 5000, 6
+    t = dt * np.arange(1, n_t + 1)
+    data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.9], dt, n_t * dt, n_trials, 1.7, 2.0, seed=4, n_t=n_t)
+    rng = np.random.default_rng(3)
+    for r in range(n_trials):
+        s = rng.integers(0, n_t - 500)
+        data[r, s:s + 500] = np.nan
+    po = [omodels.Uniform(0.01, 0.5), omodels.Uniform(5, 15), omodels.Uniform(0, 1)]
+    pp = [pkg.Uniform(0.01, 0.5), pkg.Uniform(5, 15), pkg.Uniform(0, 1)]
+    om = omodels.one_timescale_and_osc_with_missing_model(data, t, prior=po)
+    theta = np.array([[0.05, 10.0, 0.9], [0.1, 12.0, 0.5], [0.02, 8.0, 0.2]])
+    P = theta.shape[0]
+    u0 = rng.standard_normal((P, n_trials)); noise = rng.standard_normal((P, n_trials, n_t))
+    phases = rng.uniform(0, 2 * np.pi, size=(P, n_trials))
+    want = np.array([omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i], phases=phases[i]))
+                     for i in range(P)])
+    old = os.environ.get("ITJL_ABC_TC")
+    try:
+        for tc in ("1", "0"):
+            os.environ["ITJL_ABC_TC"] = tc
+            gm = pkg.one_timescale_and_osc_with_missing_model(data, t, "abc", prior=pp)
+            assert gm.n_lags == om.n_lags and abs(gm.data_mean - om.data_mean) < 1e-12 and abs(gm.data_mean) > 1.0
+            assert np.max(np.abs(gm.data_sum_stats - om.data_sum_stats)) < 1e-12
+            g = gm.gpu_model(ctx)
+            assert g.kernel_info()[0] == ("k_abc_acf_tc" if tc == "1" else "k_abc_acf")
+            d, stats = g.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
+            assert np.max(np.abs(stats - want)) <= 2e-5, (tc, np.max(np.abs(stats - want)))
+            d_ref = np.mean((want - om.data_sum_stats) ** 2, axis=1)
+            assert np.all(np.abs(d - d_ref) <= dist_tol(d_ref, 2e-5))
+    finally:
+        if old is None:
+            os.environ.pop("ITJL_ABC_TC", None)
+        else:
+            os.environ["ITJL_ABC_TC"] = old

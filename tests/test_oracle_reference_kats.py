@@ -252,3 +252,31 @@ def test_model_protocol_shapes():
     mi = models.one_timescale_model(data, t)                  # informed prior Normal(tau_hat, 20)
     assert isinstance(mi.prior[0], models.Normal) and mi.prior[0].sigma == 20.0
     assert mi.prior[0].mu == pytest.approx(0.3, rel=0.7)
+
+
+def test_osc_with_missing_model_acf_branch():
+    """test/test_one_timescale_and_osc_with_missing.jl:74-100 (generate_data keeps the NaN pattern) and
+    :209-268 (ACF branch: distance to self is 0, to a faster oscillation > 0), plus the masked-sample
+    quirk of comp_ac_time_missing with the model's data_mean (summary.jl:466-471)."""
+    from oracle import models as omodels, ou as oou, summary as osum
+    dt, T, n_trials = 1.0, 1000.0, 5
+    time = dt * np.arange(1, 1001)
+    d1 = oou.generate_ou_with_oscillation([20.0, 0.01, 0.5], dt, T, n_trials, 0.0, 1.0, seed=1)
+    d2 = oou.generate_ou_with_oscillation([20.0, 0.05, 0.5], dt, T, n_trials, 0.0, 1.0, seed=1)
+    mask = np.random.default_rng(0).random(d1.shape) < 0.1
+    d1[mask] = np.nan; d2[mask] = np.nan
+    prior = [omodels.Uniform(1, 100), omodels.Uniform(0.001, 0.1), omodels.Uniform(0, 1)]
+    m = omodels.one_timescale_and_osc_with_missing_model(d1, time, summary_method="acf", n_lags=100,
+                                                         distance_method="linear", prior=prior)
+    assert m.n_lags == 100 and m.missing_mask.shape == d1.shape and np.array_equal(m.missing_mask, mask)
+    s1, s2 = omodels.summary_stats(m, d1), omodels.summary_stats(m, d2)
+    assert np.allclose(s1, m.data_sum_stats, atol=0, rtol=0)
+    assert omodels.distance_function(m, s1, s1) == pytest.approx(0.0, abs=1e-10)
+    assert omodels.distance_function(m, s1, s2) > 0.0
+    sim = omodels.generate_data(m, np.array([20.0, 0.02, 0.5]), seed=3, generation=0, particle=0)
+    assert sim.shape == d1.shape and np.all(np.isnan(sim[mask])) and not np.any(np.isnan(sim[~mask]))
+    # masked samples of a series with mean mu enter the lag sums as -(mean of the valid samples)
+    x = np.array([[3.0, np.nan, 5.0, 4.0, np.nan, 6.0]])
+    z = np.array([3.0, 0.0, 5.0, 4.0, 0.0, 6.0]) - 4.5
+    want = np.array([np.dot(z[:6 - k], z[k:]) for k in range(3)]) / np.dot(z, z)
+    assert np.allclose(osum.comp_ac_time_missing(x, 3)[0], want, atol=1e-15)
