@@ -32,11 +32,17 @@ class ACWResults:
 
 def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
         average_over_trials=False, ctx=None):
-    """Compute ACW measures of every trial of `data` ((trials, time), time last).
+    """Compute ACW measures of every slice of `data` along its time dimension.
 
-    Returns ACWResults; `acw_results` is a list in the order of `acwtypes` (a single
-    entry when one type is requested), each entry a vector over trials (scalar for a
-    vector input or average_over_trials=True).  Lags without a crossing give NaN.
+    `dims` is the time dimension in the reference's convention: 1-based, default = the last one
+    (acw.jl:113); -1 also means last.  Slices run over all other dimensions (get_slices,
+    utils.jl:863-866); results have the shape of `data` without the time dimension and `acf` has the lags
+    where time was (stack_and_reshape, utils.jl:890-895).  The library call itself always sees a
+    (slices x time) matrix with the slice index fastest.
+
+    Returns ACWResults; `acw_results` is a list in the order of `acwtypes` (a single entry when one type
+    is requested), each entry an array over slices (scalar for a vector input or
+    average_over_trials=True).  Lags without a crossing give NaN.
     """
     if acwtypes is None:
         acwtypes = list(possible_acwtypes)
@@ -53,9 +59,18 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     was_vector = data.ndim == 1
     if was_vector:
         data = data.reshape(1, -1)                              # acw.jl:122-125
-    if data.ndim != 2 or (dims is not None and dims not in (-1, data.ndim - 1, data.ndim)):
-        raise NotImplementedError("the B200 path handles (trials, time) data with dims = last")
-    d = np.asfortranarray(data)
+        dims = None
+    nd = data.ndim
+    if dims is None or dims == -1:
+        dims = nd
+    if not (isinstance(dims, (int, np.integer)) and 1 <= dims <= nd):
+        raise ValueError(f"dims must be a dimension of data (1 .. {nd}, or -1 for the last one), got {dims!r}")
+    t_axis = int(dims) - 1
+    other_shape = tuple(n for i, n in enumerate(data.shape) if i != t_axis)
+    if average_over_trials and nd != 2:
+        raise NotImplementedError("average_over_trials is implemented for (trials, time) matrices")
+    # slices in the reference's order (column-major over the remaining dimensions), time last
+    d = np.asfortranarray(np.moveaxis(data, t_axis, -1).reshape((-1, data.shape[t_axis]), order="F"))
     n_slices, n_t = d.shape
     ctx = ctx or _lib.default_context()
     mask = 0
@@ -97,12 +112,18 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     results = []
     for t in acwtypes:
         v = res[t]
-        results.append(float(v[0]) if (was_vector or n_out == 1) else v)
+        if was_vector or n_out == 1:
+            results.append(float(v[0]))
+        else:
+            results.append(v.reshape(other_shape, order="F"))
     acf = lags = None
     if return_acf:
         acf = acf_buf[: n_out * n_lags_used].reshape((n_out, n_lags_used), order="F")
         if was_vector:
             acf = acf[0]
+        elif n_out == n_slices:
+            # lags go where time was
+            acf = np.moveaxis(acf.reshape(other_shape + (n_lags_used,), order="F"), -1, t_axis)
         lags = np.arange(n_lags_used, dtype=np.float64) * dt
     x_dim = None if acf is None else acf.ndim
     return ACWResults(float(fs), results[0] if len(results) == 1 else results,

@@ -120,3 +120,41 @@ def test_acw_full_size_c2(pkg, ctx):
     assert np.all(r["acw50"] == 0.01) and np.all(r["acweuler"] == 0.01)     # white noise: lag 1
     assert np.all(r["acw0"] >= 0.01) and got.n_lags == math.ceil(1.1 * round(r["acw0"].max() * 100))
     assert np.all(r["acw0"] >= r["acweuler"]) and np.all(r["acweuler"] >= r["acw50"])
+
+
+def test_acw_nd_input_and_dims(pkg, ctx):
+    """N-d inputs and dims != last (acw.jl:113, get_slices / stack_and_reshape,
+    utils.jl:863-895): every slice gives the same numbers as the (slices, time) call, results take
+    the shape of the remaining dimensions and the lags sit where time was."""
+    rng = np.random.default_rng(5)
+    n_t = 1500
+    base = np.empty((3, 4, n_t))
+    for i in range(3):
+        for j in range(4):
+            x = np.zeros(n_t); a = np.exp(-1.0 / (5 + 10 * i + 3 * j))
+            e = rng.standard_normal(n_t)
+            for k in range(1, n_t):
+                x[k] = a * x[k - 1] + e[k]
+            base[i, j] = x
+    types = ["acw0", "acw50", "acweuler", "tau"]
+    flat = pkg.acw(base.reshape(12, n_t), 100.0, acwtypes=types, ctx=ctx)          # rows in C order
+    r3 = pkg.acw(base, 100.0, acwtypes=types, ctx=ctx)                             # dims = 3 (last)
+    moved = np.moveaxis(base, -1, 1)                                               # (3, time, 4)
+    rm = pkg.acw(moved, 100.0, acwtypes=types, dims=2, ctx=ctx)
+    assert r3.n_lags == flat.n_lags == rm.n_lags
+    for k in range(len(types)):
+        want = np.asarray(flat.acw_results[k]).reshape(3, 4)
+        assert r3.acw_results[k].shape == (3, 4) and rm.acw_results[k].shape == (3, 4)
+        assert np.array_equal(r3.acw_results[k], want, equal_nan=True)
+        assert np.array_equal(rm.acw_results[k], want, equal_nan=True)
+    assert r3.acf.shape == (3, 4, r3.n_lags) and rm.acf.shape == (3, rm.n_lags, 4)
+    assert np.array_equal(r3.acf, flat.acf.reshape(3, 4, -1))
+    assert np.array_equal(np.moveaxis(rm.acf, 1, -1), r3.acf)
+    # 2-D with time first (dims = 1)
+    r1 = pkg.acw(base[0].T.copy(), 100.0, acwtypes=types, dims=1, ctx=ctx)
+    r2 = pkg.acw(base[0], 100.0, acwtypes=types, ctx=ctx)
+    for k in range(len(types)):
+        assert np.array_equal(r1.acw_results[k], r2.acw_results[k], equal_nan=True)
+    assert r1.acf.shape == (r1.n_lags, 4) and np.array_equal(r1.acf.T, r2.acf)
+    with pytest.raises(ValueError):
+        pkg.acw(base, 100.0, dims=4, ctx=ctx)
