@@ -80,6 +80,8 @@ class TimescaleModel:
     freq_idx: Any = None
     dims: int = 2
     distance_combined: bool = False
+    weights: Any = None            # [w_stats, w_tau] of combined_distance (one_timescale.jl:278-290)
+    data_tau: Any = None           # fit_expdecay(lags, data_sum_stats) when distance_combined
     missing_mask: Any = None
     update: str = "exact"
     _gpu: dict = field(default_factory=dict, repr=False)
@@ -167,10 +169,26 @@ class GpuModel:
         stats = np.empty((n, self.n_stats), dtype=np.float64) if return_stats else None
         cast = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         u0, noise, phases = cast(u0), cast(noise), cast(phases)
+        combined = bool(self.model.distance_combined)
+        if combined and stats is None:
+            stats = np.empty((n, self.n_stats), dtype=np.float64)
         self.ctx.check(_lib.lib().itjl_abc_distances(
             self._h, _lib.ptr(th), n, p, int(seed), int(generation), int(particle_offset),
             _lib.ptr(u0), _lib.ptr(noise), _lib.ptr(phases), _lib.ptr(out), _lib.ptr(stats)))
+        if combined:
+            out = self._combine(out, stats)
         return (out, stats) if return_stats else out
+
+    def _combine(self, d_stats, stats):
+        """combined_distance (one_timescale.jl:278-290): w1 * distance(stats) + w2 * (data_tau - tau_sim)^2,
+        tau_sim = fit_expdecay(lags, simulated mean ACF) fitted on the device for the whole batch."""
+        from . import utils
+        m = self.model
+        ok = np.isfinite(stats).all(axis=1)
+        tau = np.full(stats.shape[0], np.nan)
+        if ok.any():
+            tau[ok] = np.atleast_1d(utils.fit_expdecay(m.lags_freqs, stats[ok], ctx=self.ctx))
+        return m.weights[0] * d_stats + m.weights[1] * (m.data_tau - tau) ** 2
 
     def generation(self, theta, epsilon, min_accepted, seed=0, generation=0, particle_offset=0):
         """Distances + accept mask + sequential stop for a batch (abc.jl:181-199)."""
@@ -178,10 +196,18 @@ class GpuModel:
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
         n, p = theta.shape
         th = np.asfortranarray(theta)
-        dist = np.empty(n, dtype=np.float64)
         isacc = np.empty(n, dtype=np.uint8)
         n_total = ctypes.c_int64(0)
         n_acc = ctypes.c_int64(0)
+        if self.model.distance_combined:
+            # distances need the per-particle exp-decay fit: score, combine, then the device accept / stop rule
+            dist = np.ascontiguousarray(self.distances(theta, seed=seed, generation=generation,
+                                                       particle_offset=particle_offset))
+            self.ctx.check(_lib.lib().itjl_abc_accept(self.ctx.handle, _lib.ptr(dist), n, float(epsilon),
+                                                      int(min_accepted), _lib.ptr(isacc), ctypes.byref(n_total),
+                                                      ctypes.byref(n_acc)))
+            return dist, isacc.astype(bool), int(n_total.value), int(n_acc.value)
+        dist = np.empty(n, dtype=np.float64)
         self.ctx.check(_lib.lib().itjl_abc_generation(
             self._h, _lib.ptr(th), n, p, int(seed), int(generation), int(particle_offset),
             float(epsilon), int(min_accepted), _lib.ptr(dist), _lib.ptr(isacc),
@@ -246,11 +272,25 @@ def _acf_branch(acf_mean, n, dt, n_lags, prior):
     return n_lags, lags, stats, prior
 
 
+def _combined(model, distance_combined, weights, data_tau, ctx):
+    """distance_combined = true of the ACF branch (one_timescale.jl:166-169, 278-290): the timescale of
+    the data's mean ACF is fitted once at construction."""
+    if not distance_combined:
+        return model
+    from . import utils
+    w = [0.5, 0.5] if weights is None else [float(x) for x in weights]
+    if len(w) != 2:
+        raise ValueError("weights must have length 2 for the ACF summary")
+    model.distance_combined = True
+    model.weights = w
+    model.data_tau = float(data_tau) if data_tau is not None else float(
+        utils.fit_expdecay(model.lags_freqs, model.data_sum_stats, ctx=ctx))
+    return model
+
+
 def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prior=None,
                         n_lags=None, distance_method=None, distance_combined=False,
-                        update="exact"):
-    if distance_combined:
-        raise NotImplementedError("distance_combined is outside the B200 hot path")
+                        weights=None, data_tau=None, update="exact", ctx=None):
     data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
     if summary_method != "acf":
         raise NotImplementedError("summary_method=:psd of one_timescale_model (DSP periodogram) "
@@ -258,16 +298,15 @@ def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prio
     dt = float(time[1] - time[0]); T = float(time[-1])
     acf_mean = summary.comp_ac_fft(data).mean(axis=0)
     n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
-    return TimescaleModel("one_timescale", data, time, fit_method, "acf", lags, prior,
-                          distance_method or "linear", stats, dt, T, data.shape[0],
-                          float(data.mean()), float(data.std(ddof=1)), n_lags=n_lags, update=update)
+    m = TimescaleModel("one_timescale", data, time, fit_method, "acf", lags, prior,
+                       distance_method or "linear", stats, dt, T, data.shape[0],
+                       float(data.mean()), float(data.std(ddof=1)), n_lags=n_lags, update=update)
+    return _combined(m, distance_combined, weights, data_tau, ctx)
 
 
 def one_timescale_with_missing_model(data, time, fit_method="abc", summary_method="acf", prior=None,
                                      n_lags=None, distance_method=None, distance_combined=False,
-                                     update="exact"):
-    if distance_combined:
-        raise NotImplementedError("distance_combined is outside the B200 hot path")
+                                     weights=None, data_tau=None, update="exact", ctx=None):
     data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
     if summary_method != "acf":
         raise NotImplementedError("the Lomb-Scargle PSD branch is outside the B200 hot path")
@@ -275,17 +314,19 @@ def one_timescale_with_missing_model(data, time, fit_method="abc", summary_metho
     mask = np.isnan(data)
     acf_mean = summary.comp_ac_time_missing(data).mean(axis=0)
     n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
-    return TimescaleModel("one_timescale_with_missing", data, time, fit_method, "acf", lags, prior,
-                          distance_method or "linear", stats, dt, T, data.shape[0],
-                          float(np.nanmean(data)), float(np.nanstd(data, ddof=1)), n_lags=n_lags,
-                          missing_mask=mask, update=update)
+    m = TimescaleModel("one_timescale_with_missing", data, time, fit_method, "acf", lags, prior,
+                       distance_method or "linear", stats, dt, T, data.shape[0],
+                       float(np.nanmean(data)), float(np.nanstd(data, ddof=1)), n_lags=n_lags,
+                       missing_mask=mask, update=update)
+    return _combined(m, distance_combined, weights, data_tau, ctx)
 
 
 def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="psd", prior=None,
                                 n_lags=None, distance_method=None, freqlims=None,
                                 distance_combined=False, update="exact"):
     if distance_combined:
-        raise NotImplementedError("distance_combined is outside the B200 hot path")
+        raise NotImplementedError("distance_combined of the oscillation models needs the oscillation-peak "
+                                  "search (outside the B200 hot path)")
     data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
     if prior is None:
         raise NotImplementedError("the informed prior of the oscillation model needs the Lorentzian "

@@ -8,7 +8,7 @@ Follows
       :270-272, :333-349,
   /root/reference/src/models/one_timescale_and_osc.jl:98-189, :263-266, :289-297,
       :368-393.
-Out of scope: distance_combined, the DSP-periodogram PSD
+Out of scope: distance_combined of the oscillation models, the DSP-periodogram PSD
 branch of one_timescale_model, Lomb-Scargle PSD, informed priors that need the
 Lorentzian/knee fits.
 """
@@ -68,6 +68,9 @@ class Model:
     freq_idx: np.ndarray = None
     missing_mask: np.ndarray = None
     update: str = "exact"
+    distance_combined: bool = False
+    weights: list = None
+    data_tau: float = None
     n_t: int = field(default=None)
 
     def __post_init__(self):
@@ -100,6 +103,14 @@ def _acf_setup(acf_mean, n, dt, n_lags):
         n_lags = int(math.floor(a0 * 1.1))
     lags = (np.arange(n, dtype=np.float64) * dt)[:n_lags]
     return n_lags, lags, acf_mean[:n_lags]
+
+
+def with_combined_distance(model, weights=(0.5, 0.5), data_tau=None):
+    """distance_combined = true (one_timescale.jl:166-169): data_tau = fit_expdecay(lags, data_sum_stats)."""
+    model.distance_combined = True
+    model.weights = [float(w) for w in weights]
+    model.data_tau = float(data_tau) if data_tau is not None else acwred.fit_expdecay(model.lags_freqs, model.data_sum_stats)
+    return model
 
 
 def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prior=None,
@@ -221,6 +232,14 @@ def summary_stats(model, data):
 
 
 def distance_function(model, sum_stats, data_sum_stats):
+    if model.distance_combined:
+        # one_timescale.jl:306-320 + combined_distance :278-290 (ACF branch)
+        d1 = (distances.linear_distance(sum_stats, data_sum_stats) if model.distance_method == "linear"
+              else distances.logarithmic_distance(sum_stats, data_sum_stats))
+        if not np.all(np.isfinite(sum_stats)):
+            return float("nan")
+        tau_sim = acwred.fit_expdecay(model.lags_freqs, sum_stats)
+        return model.weights[0] * d1 + model.weights[1] * distances.linear_distance(model.data_tau, tau_sim)
     if model.distance_method == "linear":
         return distances.linear_distance(sum_stats, data_sum_stats)
     if model.distance_method == "logarithmic":

@@ -279,3 +279,40 @@ def test_oscillation_with_missing_model(pkg, ctx):
             os.environ.pop("ITJL_ABC_TC", None)
         else:
             os.environ["ITJL_ABC_TC"] = old
+
+
+def test_distance_combined_acf_branch(pkg, ctx):
+    """distance_combined = true of one_timescale_model (one_timescale.jl:166-169, 278-320):
+    w1 * distance(ACF) + w2 * (data_tau - fit_expdecay(lags, simulated ACF))^2, scored in batches
+    (fused kernel -> statistics -> batched exp-decay fit on the device) and through basic_abc's accept
+    rule; against the oracle's serial restatement on the same noise."""
+    n_t, n_trials = 3000, 4
+    data = oou.generate_ou_process(0.3, 1.0, DT, n_t * DT, n_trials, seed=21, n_t=n_t)
+    om = omodels.with_combined_distance(
+        omodels.one_timescale_model(data, _time(n_t), prior=[omodels.Uniform(0.05, 5)]), weights=(0.3, 0.7))
+    gm = pkg.one_timescale_model(data, _time(n_t), "abc", prior=[pkg.Uniform(0.05, 5)], distance_combined=True,
+                                 weights=[0.3, 0.7], ctx=ctx)
+    assert gm.distance_combined and gm.weights == [0.3, 0.7]
+    assert gm.data_tau == pytest.approx(om.data_tau, rel=1e-6)
+    rng = np.random.default_rng(8)
+    theta = np.array([[0.3], [0.1], [1.0], [2.5], [0.05]])
+    P = theta.shape[0]
+    u0 = rng.standard_normal((P, n_trials)); noise = rng.standard_normal((P, n_trials, n_t))
+    want = np.array([omodels.generate_data_and_reduce(om, theta[i], u0=u0[i], noise=noise[i]) for i in range(P)])
+    g = gm.gpu_model(ctx)
+    got = g.distances(theta, u0=u0, noise=noise)
+    # the tau term amplifies the 1e-5 ACF tolerance by d tau / d ACF ~ tau * n_lags^(1/2)
+    assert np.all(np.abs(got - want) <= 2e-3 * np.abs(want) + 1e-6), (got, want)
+    # the plain distance is the w1 part
+    gp = pkg.one_timescale_model(data, _time(n_t), "abc", prior=[pkg.Uniform(0.05, 5)]).gpu_model(ctx)
+    d_plain, stats = gp.distances(theta, u0=u0, noise=noise, return_stats=True)
+    tau_sim = pkg.fit_expdecay(gm.lags_freqs, stats, ctx=ctx)
+    assert np.allclose(got, 0.3 * d_plain + 0.7 * (gm.data_tau - tau_sim) ** 2, rtol=1e-12, atol=0)
+    # batched generation: accept mask / stop index follow the combined distances
+    th = rng.uniform(0.05, 3.0, size=(200, 1))
+    d_all = g.distances(th, seed=4, generation=1)
+    eps = float(np.median(d_all))
+    d, isacc, n_total, n_acc = g.generation(th, eps, 30, seed=4, generation=1)
+    assert np.array_equal(d, d_all)
+    assert n_total == oabc.stop_index(d_all, eps, 30) and n_acc == 30
+    assert np.array_equal(isacc[:n_total], (d_all <= eps)[:n_total])
