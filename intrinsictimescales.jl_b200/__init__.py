@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import Context, ItjlError, default_context, library_path
 from .abc import (ABCResults, abc_results, basic_abc, calc_weights, compute_adaptive_alpha,
                   draw_theta_pmc, effective_sample_size, find_MAP, get_param_dict_abc, int_fit,
-                  pmc_abc, select_epsilon, weighted_covar)
+                  pmc_abc, posterior_predictive, select_epsilon, weighted_covar)
 from .acw import ACWResults, acw, possible_acwtypes
 from .models import (Normal, Uniform, TimescaleModel, check_model_inputs, distance_function,
                      draw_theta, generate_data, generate_data_and_reduce, one_timescale_and_osc_model,

@@ -335,3 +335,24 @@ def int_fit(model, param_dict=None, **kw):
     params.update(kw)
     params.pop("N", None)
     return pmc_abc(model, **params)
+
+
+def posterior_predictive(container, model, n_samples=100, rng=None, seed=0, ctx=None):
+    """Numerical part of posterior_predictive (ext/IntPlottingExt/IntPlottingExt.jl:105-128): summary
+    statistics of data simulated at `n_samples` rows drawn with replacement from the posterior, their mean and
+    2.5 % / 97.5 % quantiles.  One batched launch of the fused kernel instead of n_samples generate_data +
+    summary_stats calls; the plotting stays with the caller.  Returns a dict with `theta_samples`,
+    `predictions` (n_samples, n_stats), `pred_mean`, `pred_lower`, `pred_upper`, `x` (= model.lags_freqs)."""
+    rng = rng or np.random.default_rng()
+    final_theta = np.atleast_2d(np.asarray(container.final_theta, dtype=np.float64))
+    idx = rng.integers(0, final_theta.shape[0], size=int(n_samples))
+    theta = final_theta[idx]
+    plain = model
+    if model.distance_combined:                 # the statistics do not depend on the distance
+        import copy
+        plain = copy.copy(model); plain.distance_combined = False; plain._gpu = {}
+    _, stats = plain.gpu_model(ctx).distances(theta, seed=seed, generation=0, return_stats=True)
+    return {"theta_samples": theta, "predictions": stats, "pred_mean": stats.mean(axis=0),
+            "pred_lower": np.array([percentile(stats[:, i], 2.5) for i in range(stats.shape[1])]),
+            "pred_upper": np.array([percentile(stats[:, i], 97.5) for i in range(stats.shape[1])]),
+            "x": np.asarray(model.lags_freqs)}

@@ -52,3 +52,24 @@ def test_posterior_matches_oracle_within_mc_error(pkg, ctx):
     assert abs(mo.mean() - mg.mean()) < 3 * se + 0.1 * so.mean()
     # posterior widths agree within a factor the replicate scatter supports
     assert 0.5 < sg.mean() / so.mean() < 2.0
+
+
+def test_posterior_predictive_statistics(pkg, ctx):
+    """posterior_predictive's numbers (IntPlottingExt.jl:105-128): batched summary statistics at posterior
+    draws; mean and 95 % band bracket the data's ACF for a posterior concentrated at the true timescale."""
+    import numpy as np
+    from oracle import ou as oou
+    dt, n_t, n_trials = 0.002, 5000, 10
+    data = oou.generate_ou_process(0.3, 1.0, dt, n_t * dt, n_trials, seed=2, n_t=n_t)
+    t = dt * np.arange(1, n_t + 1)
+    model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)])
+    post = pkg.ABCResults([], [], [], [], np.random.default_rng(0).normal(0.3, 0.02, size=(500, 1)), np.ones(500) / 500, np.array([0.3]))
+    pp = pkg.posterior_predictive(post, model, n_samples=200, rng=np.random.default_rng(1), seed=5, ctx=ctx)
+    assert pp["predictions"].shape == (200, model.n_lags) and pp["theta_samples"].shape == (200, 1)
+    assert np.all(pp["pred_lower"] <= pp["pred_mean"]) and np.all(pp["pred_mean"] <= pp["pred_upper"])
+    assert np.allclose(pp["predictions"][:, 0], 1.0, atol=1e-5)
+    inside = (model.data_sum_stats >= pp["pred_lower"] - 1e-9) & (model.data_sum_stats <= pp["pred_upper"] + 1e-9)
+    assert inside.mean() > 0.5          # neighbouring lags are strongly correlated: a sanity check, not a coverage test
+    # same numbers as scoring the same draws directly
+    _, stats = model.gpu_model(ctx).distances(pp["theta_samples"], seed=5, generation=0, return_stats=True)
+    assert np.array_equal(stats, pp["predictions"])
