@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -20,7 +21,7 @@ static const bool kTcDefault = true;      // default path of the fused ACF kerne
 struct itjl_model {
     itjl_ctx* ctx = nullptr;
     itjl_model_desc d{};
-    DevBuf target, mask_bits, n_valid, bins, window, twiddle;
+    DevBuf target, mask_bits, n_valid, bins, binidx, window, twiddle;
     int mask_words = 0;
     AbcAcfGeometry geo{};
     AbcTcGeometry tc{};
@@ -181,14 +182,26 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         double win_ss = 0.0;
         psd_make_tables((int)d.n_t, m->n2, win.data(), tw.data(), &win_ss);
         m->psd_scale = 1.0 / ((1.0 / d.dt) * win_ss);
+        // bin table sorted by storage position: consecutive threads then read neighbouring shared-memory words
+        // (in frequency order consecutive bins sit N/4 points apart - the same bank); binidx maps back
         std::vector<int4> binpos((size_t)d.n_stats);
+        std::vector<int32_t> order((size_t)d.n_stats);
+        for (int64_t i = 0; i < d.n_stats; ++i) order[(size_t)i] = (int32_t)i;
+        {
+            const int N = m->n2 / 2;
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                return psd_fft_pos(d.freq_bins[a] + 1, N) < psd_fft_pos(d.freq_bins[b] + 1, N);
+            });
+        }
         for (int64_t i = 0; i < d.n_stats; ++i) {
-            const int k = d.freq_bins[i] + 1, N = m->n2 / 2;
+            const int k = d.freq_bins[order[(size_t)i]] + 1, N = m->n2 / 2;
             int wx, wy;                                     // the bin's twiddle exp(-2 pi i k / n2), as float bits
             memcpy(&wx, &tw[(size_t)k].x, 4); memcpy(&wy, &tw[(size_t)k].y, 4);
-            binpos[i] = make_int4(psd_fft_pos(k, N), psd_fft_pos(N - k, N), wx, wy);
+            binpos[(size_t)i] = make_int4(psd_fft_pos(k, N), psd_fft_pos(N - k, N), wx, wy);
         }
-        rc = upload(ctx, m->bins, binpos.data(), binpos.size() * sizeof(int4));
+        rc = upload(ctx, m->binidx, order.data(), order.size() * sizeof(int32_t));
+        if (rc == ITJL_OK)
+            rc = upload(ctx, m->bins, binpos.data(), binpos.size() * sizeof(int4));
         if (rc == ITJL_OK) rc = upload(ctx, m->window, win.data(), win.size() * sizeof(float));
         if (rc == ITJL_OK) rc = upload(ctx, m->twiddle, tw.data(), tw.size() * sizeof(float2));
         // the host vectors above are block-local: finish the copies before they are destroyed
@@ -204,7 +217,7 @@ int itjl_model_destroy(itjl_model* m) {
     if (!m) return ITJL_OK;
     if (m->ctx) cudaSetDevice(m->ctx->device);
     m->target.release(); m->mask_bits.release(); m->n_valid.release();
-    m->bins.release(); m->window.release(); m->twiddle.release();
+    m->bins.release(); m->binidx.release(); m->window.release(); m->twiddle.release();
     delete m;
     return ITJL_OK;
 }
@@ -274,7 +287,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
         P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
         P.particle_offset = particle_offset;
-        P.target = (const float*)m->target.p; P.binpos = (const int4*)m->bins.p;
+        P.target = (const float*)m->target.p; P.binpos = (const int4*)m->bins.p; P.binidx = (const int32_t*)m->binidx.p;
         P.window = (const float*)m->window.p; P.twiddle = (const float2*)m->twiddle.p;
         P.psd_scale = m->psd_scale;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;

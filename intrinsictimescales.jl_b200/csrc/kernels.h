@@ -51,6 +51,7 @@ struct AbcPsdParams {
     int64_t particle_offset;
     const float* target;        // n_stats
     const int4* binpos;         // n_stats: {storage pos of Z[k], of Z[N-k], bits of the twiddle exp(-2 pi i k / n2)}, k = bin + 1
+    const int32_t* binidx;      // n_stats: statistic index of the i-th entry of binpos (sorted by storage position)
     const float* window;        // n_t Hamming window
     const float2* twiddle;      // n2/2 complex roots exp(-2 pi i k / (n2/2))... see psd_kernels.cu
     double psd_scale;           // 1 / (fs * sum(window^2))

@@ -92,12 +92,13 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
         __syncthreads();
         span = h;
     }
+    int log2q = 0; while ((4 << log2q) < span) ++log2q;          // q = span / 4 = 2^log2q
     while (span > 16) {
         const int q = span >> 2;
         const int tstep = (2 * N) / span;          // W_span^j = U[j * tstep]
         for (int u = tid; u < (N >> 2); u += NT) {
             const int j = u & (q - 1);
-            const int base = (u / q) * span + j;
+            const int base = ((u >> log2q) << (log2q + 2)) + j;
             const int p0 = fft_pad(base), p1 = fft_pad(base + q), p2 = fft_pad(base + 2 * q), p3 = fft_pad(base + 3 * q);
             float2 x0 = buf[p0], x1 = buf[p1], x2 = buf[p2], x3 = buf[p3];
             bfly4(x0, x1, x2, x3);
@@ -114,6 +115,7 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
         }
         __syncthreads();
         span = q;
+        log2q -= 2;
     }
     // span == 16: stages q = 4 and q = 1 of one 16-point group per thread; W_16^m are constants
     {
@@ -243,8 +245,9 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
     double local = 0.0;
     for (int b = tid; b < P.n_stats; b += NT) {
         const double v = (double)accb[b] * sc;
-        if (P.stats_out) P.stats_out[(size_t)particle * P.n_stats + b] = v;
-        const double tgt = (double)P.target[b];
+        const int bi = __ldg(P.binidx + b);                      // accb is in storage order
+        if (P.stats_out) P.stats_out[(size_t)particle * P.n_stats + bi] = v;
+        const double tgt = (double)P.target[bi];
         const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
         local += e * e;
     }
