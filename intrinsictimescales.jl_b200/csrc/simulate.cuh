@@ -178,7 +178,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 if (OSC) {
                     double turns = fma(oc.fdt, (double)(j + i + 1), phase_turns);
                     turns -= rint(turns);
-                    v[i] = fmaf(oc.so, sinpif(2.0f * (float)turns), oc.sc * y);
+                    v[i] = fmaf(oc.so, __sinf(6.283185307179586f * (float)turns), oc.sc * y);   // turns in [-0.5, 0.5]: MUFU.SIN at its best (abs error 5e-7)
                     pp[i] = oc.sc * p;
                 }
             }
