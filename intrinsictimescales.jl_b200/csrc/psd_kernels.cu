@@ -72,9 +72,60 @@ __device__ __forceinline__ void bfly4(float2& x0, float2& x1, float2& x2, float2
     x3 = make_float2(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
 }
 
+// One radix-16 DIF pass (= two radix-4 stages kept in registers) over groups of span S = 16 q:
+// butterfly u takes the 16 points base + e q, e = 0 .. 15.  Level 1 works on (e0, e0 + 4, e0 + 8, e0 + 12)
+// with twiddles W_S^((j + e0 q) r) = W_S^(j r) * W_16^(e0 r); level 2 on (4 r .. 4 r + 3) with
+// W_(S/4)^(j r') = (W_S^(4 j))^r'.  Results go back in place, so the digit-reversed order is that of
+// two consecutive radix-4 stages.  q = 1 (S = 16) is the twiddle-free tail of the transform.
+template <int NT>
+__device__ __forceinline__ void fft_radix16_pass(float2* __restrict__ buf, int N, int span, const Tw2& tw) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+    const int q = span >> 4;
+    int log2q = 0; while ((1 << log2q) < q) ++log2q;
+    const int tstep = (2 * N) / span;              // W_span^j = exp(-2 pi i j tstep / 2N)
+    for (int u = threadIdx.x; u < (N >> 4); u += NT) {
+        const int j = u & (q - 1);
+        const int base = ((u >> log2q) << (log2q + 4)) + j;
+        float2 x[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = buf[fft_pad(base + e * q)];
+        bfly4(x[0], x[4], x[8], x[12]);
+        bfly4(x[1], x[5], x[9], x[13]);
+        x[5] = cmul(x[5], make_float2(C1, -S1)); x[9] = cmul(x[9], make_float2(C2, -C2)); x[13] = cmul(x[13], make_float2(S1, -C1));
+        bfly4(x[2], x[6], x[10], x[14]);
+        x[6] = cmul(x[6], make_float2(C2, -C2)); x[10] = make_float2(x[10].y, -x[10].x); x[14] = cmul(x[14], make_float2(-C2, -C2));
+        bfly4(x[3], x[7], x[11], x[15]);
+        x[7] = cmul(x[7], make_float2(S1, -C1)); x[11] = cmul(x[11], make_float2(-C2, -C2)); x[15] = cmul(x[15], make_float2(-C1, S1));
+        if (j != 0) {
+            const float2 t1 = tw(j * tstep);
+            const float2 t2 = cmul(t1, t1);
+            const float2 t3 = cmul(t2, t1);
+#pragma unroll
+            for (int e0 = 0; e0 < 4; ++e0) {
+                x[e0 + 4] = cmul(x[e0 + 4], t1); x[e0 + 8] = cmul(x[e0 + 8], t2); x[e0 + 12] = cmul(x[e0 + 12], t3);
+            }
+        }
+#pragma unroll
+        for (int b4 = 0; b4 < 16; b4 += 4) bfly4(x[b4], x[b4 + 1], x[b4 + 2], x[b4 + 3]);
+        if (j != 0) {
+            const float2 s1 = tw(4 * j * tstep);
+            const float2 s2 = cmul(s1, s1);
+            const float2 s3 = cmul(s2, s1);
+#pragma unroll
+            for (int b4 = 0; b4 < 16; b4 += 4) {
+                x[b4 + 1] = cmul(x[b4 + 1], s1); x[b4 + 2] = cmul(x[b4 + 2], s2); x[b4 + 3] = cmul(x[b4 + 3], s3);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) buf[fft_pad(base + e * q)] = x[e];
+    }
+    __syncthreads();
+}
+
 // In-place DIF FFT of N = 2^m >= 16 complex points in padded shared memory (NT threads): one radix-2
-// stage first when m is odd, radix-4 stages down to span 64, then the last two radix-4 stages (span 16
-// and 4) fused in registers, 16 points per thread.  Output in digit-reversed order (fft_pos).
+// stage first when m is odd, one radix-4 stage when the remaining log2 is not a multiple of 4, then
+// radix-16 passes (two radix-4 stages per shared-memory round trip) down to the twiddle-free tail.
+// Output in digit-reversed order (fft_pos).
 template <int NT>
 __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
     const int tid = threadIdx.x;
@@ -91,11 +142,12 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
         }
         __syncthreads();
         span = h;
+        --log2n;
     }
-    int log2q = 0; while ((4 << log2q) < span) ++log2q;          // q = span / 4 = 2^log2q
-    while (span > 16) {
+    if (log2n & 2) {                                   // log2(span) = 2 mod 4: one radix-4 stage
         const int q = span >> 2;
-        const int tstep = (2 * N) / span;          // W_span^j = U[j * tstep]
+        int log2q = 0; while ((1 << log2q) < q) ++log2q;
+        const int tstep = (2 * N) / span;
         for (int u = tid; u < (N >> 2); u += NT) {
             const int j = u & (q - 1);
             const int base = ((u >> log2q) << (log2q + 2)) + j;
@@ -103,7 +155,6 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
             float2 x0 = buf[p0], x1 = buf[p1], x2 = buf[p2], x3 = buf[p3];
             bfly4(x0, x1, x2, x3);
             if (j != 0) {
-                // one table read per butterfly: W^2j and W^3j by complex multiplication
                 const float2 w1 = tw(j * tstep);
                 const float2 w2 = cmul(w1, w1);
                 const float2 w3 = cmul(w2, w1);
@@ -115,30 +166,8 @@ __device__ void fft_inplace_dif(float2* __restrict__ buf, int N, const Tw2 tw) {
         }
         __syncthreads();
         span = q;
-        log2q -= 2;
     }
-    // span == 16: stages q = 4 and q = 1 of one 16-point group per thread; W_16^m are constants
-    {
-        constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
-        for (int gidx = tid; gidx < (N >> 4); gidx += NT) {
-            float2* grp = buf + gidx * 17;
-            float2 x[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) x[e] = grp[e];
-            bfly4(x[0], x[4], x[8], x[12]);
-            bfly4(x[1], x[5], x[9], x[13]);
-            x[5] = cmul(x[5], make_float2(C1, -S1)); x[9] = cmul(x[9], make_float2(C2, -C2)); x[13] = cmul(x[13], make_float2(S1, -C1));
-            bfly4(x[2], x[6], x[10], x[14]);
-            x[6] = cmul(x[6], make_float2(C2, -C2)); x[10] = make_float2(x[10].y, -x[10].x); x[14] = cmul(x[14], make_float2(-C2, -C2));
-            bfly4(x[3], x[7], x[11], x[15]);
-            x[7] = cmul(x[7], make_float2(S1, -C1)); x[11] = cmul(x[11], make_float2(-C2, -C2)); x[15] = cmul(x[15], make_float2(-C1, S1));
-#pragma unroll
-            for (int b4 = 0; b4 < 16; b4 += 4) bfly4(x[b4], x[b4 + 1], x[b4 + 2], x[b4 + 3]);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) grp[e] = x[e];
-        }
-        __syncthreads();
-    }
+    for (; span >= 16; span >>= 4) fft_radix16_pass<NT>(buf, N, span, tw);
 }
 
 // storage position (unpadded index) of frequency k after fft_inplace_dif
