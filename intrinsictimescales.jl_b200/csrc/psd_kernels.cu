@@ -81,8 +81,8 @@ template <int NT>
 __device__ __forceinline__ void fft_radix16_pass(float2* __restrict__ buf, int N, int span, const Tw2& tw) {
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
     const int q = span >> 4;
-    int log2q = 0; while ((1 << log2q) < q) ++log2q;
-    const int tstep = (2 * N) / span;              // W_span^j = exp(-2 pi i j tstep / 2N)
+    const int log2q = 31 - __clz(q);
+    const int tstep = (2 * N) >> (log2q + 4);      // W_span^j = exp(-2 pi i j tstep / 2N)
     for (int u = threadIdx.x; u < (N >> 4); u += NT) {
         const int j = u & (q - 1);
         const int base = ((u >> log2q) << (log2q + 4)) + j;
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
         __syncthreads();
         // window, pack z[m] = x[2m] + i x[2m+1] into the padded FFT buffer, zero-pad to N points
         // (xs holds zeros from n_t to chunk * NT)
+#pragma unroll 4
         for (int m = tid; m < N; m += NT) {
             float2 z = make_float2(0.f, 0.f);
             if (2 * m < P.n_t) {
