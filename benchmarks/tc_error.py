@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""ACF error of the tensor-core kernel against the CUDA-core kernel over many particles, as a function of
+the accumulator segment length (diagnostic for the drain interval)."""
+import os, subprocess, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def child(tag):
+    import __graft_entry__ as ge
+    import bench
+    pkg = ge.load_package()
+    ctx = pkg.default_context(0)
+    data, t = bench.observed_data_host()
+    model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)])
+    g = model.gpu_model(ctx)
+    theta = np.random.default_rng(7).uniform(0.05, 5.0, size=(1184, 1))
+    d, s = g.distances(theta, seed=21, generation=4, return_stats=True)
+    np.save(f"gpurun_out/tc_err_{tag}.npy", s)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "child":
+        child(sys.argv[2])
+    else:
+        os.makedirs("gpurun_out", exist_ok=True)
+        runs = [("ffma", {"ITJL_ABC_TC": "0"})] + [(f"seg{k}", {"ITJL_ABC_TC": "1", "ITJL_TC_SEG": str(k)}) for k in (8, 13, 17, 25)]
+        for tag, env in runs:
+            e = dict(os.environ); e.update(env)
+            subprocess.run([sys.executable, __file__, "child", tag], env=e, timeout=300)
+        ref = np.load("gpurun_out/tc_err_ffma.npy")
+        for tag, _ in runs[1:]:
+            err = np.load(f"gpurun_out/tc_err_{tag}.npy") - ref
+            print(f"{tag}: max |err| {np.abs(err).max():.2e}  rms {np.sqrt(np.mean(err ** 2)):.2e}  mean {err.mean():+.2e}  "
+                  f"99.9% {np.quantile(np.abs(err), 0.999):.2e}")
