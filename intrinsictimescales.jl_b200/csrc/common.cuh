@@ -42,6 +42,9 @@ struct itjl_ctx {
     int64_t timed_launches = 0;
     double timed_ms = 0.0;
     itjl::DevBuf theta, dist, stats, u0, noise, phases, flags, scratch, data, out, out2, out3, part;
+    // pinned staging ring of the large host -> device uploads (itjl_api_acw.cu)
+    void* pin[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pin_ev[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace itjl {

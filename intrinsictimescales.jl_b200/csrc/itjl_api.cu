@@ -78,6 +78,10 @@ int itjl_ctx_destroy(itjl_ctx* ctx) {
                       &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3, &ctx->part};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
+        if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ITJL_OK;
