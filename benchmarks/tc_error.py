@@ -25,12 +25,15 @@ if __name__ == "__main__":
         child(sys.argv[2])
     else:
         os.makedirs("gpurun_out", exist_ok=True)
-        runs = [("ffma", {"ITJL_ABC_TC": "0"})] + [(f"seg{k}", {"ITJL_ABC_TC": "1", "ITJL_TC_SEG": str(k)}) for k in (8, 13, 17, 25)]
+        segs = [int(a) for a in sys.argv[1:]] or [8, 13, 17, 25, 50]
+        runs = [("ffma", {"ITJL_ABC_TC": "0"})] + [(f"seg{k}", {"ITJL_ABC_TC": "1", "ITJL_TC_SEG": str(k)}) for k in segs]
         for tag, env in runs:
             e = dict(os.environ); e.update(env)
             subprocess.run([sys.executable, __file__, "child", tag], env=e, timeout=300)
         ref = np.load("gpurun_out/tc_err_ffma.npy")
         for tag, _ in runs[1:]:
             err = np.load(f"gpurun_out/tc_err_{tag}.npy") - ref
+            slope = float((ref * err).sum() / (ref * ref).sum())        # bias proportional to the value
             print(f"{tag}: max |err| {np.abs(err).max():.2e}  rms {np.sqrt(np.mean(err ** 2)):.2e}  mean {err.mean():+.2e}  "
-                  f"99.9% {np.quantile(np.abs(err), 0.999):.2e}")
+                  f"99.9% {np.quantile(np.abs(err), 0.999):.2e}  slope {slope:+.2e}  "
+                  + "  ".join(f"ac~{lo:.1f}: {np.mean(err[(ref >= lo) & (ref < hi)]):+.2e}" for lo, hi in ((0.9, 1.01), (0.5, 0.9), (0.1, 0.5))))

@@ -28,7 +28,7 @@
 namespace itjl {
 
 template <int NT, bool MISSING, bool OSC>
-__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const AbcAcfParams P) {
+__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const __grid_constant__ AbcAcfParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int buf_floats = P.xs_stride;
     float* xs0 = reinterpret_cast<float*>(smem_raw);
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const AbcAcfP
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
     g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
-    g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
+    g.keys = &P.keys; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
     g.particle = (uint32_t)(P.particle_offset + particle);
     const size_t pt = (size_t)particle * P.n_trials;
     g.u0 = P.u0 ? P.u0 + pt : nullptr;

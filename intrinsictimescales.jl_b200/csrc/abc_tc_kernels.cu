@@ -39,10 +39,12 @@ namespace itjl {
 //   operand planes; longer lag windows run on the CUDA-core kernel k_abc_acf.
 //
 // Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
-// zero (measured, benchmarks/tc_probe2.py), so a long positive chain loses ~0.5 ulp per product:
-// 1.8e-5 relative over 50 trials x 5000 samples.  The accumulators are therefore drained every
-// `seg_trials` trials (~768 K rows, equal segments) and the segment sums are added to a fixed-point
-// lag table, which keeps the bias below 5e-6.
+// zero (measured, benchmarks/tc_probe2.py), so a long positive chain shrinks: 1.1e-5 relative at lags
+// with ac ~ 1 over 50 trials x 5000 samples.  Because every trial adds the same sum of squares the
+// chain grows linearly and the loss is, to first order, a known factor on the drained sum; the
+// epilogue multiplies it back (abc_tc_geometry: bias_a, bias_b), leaving ~1e-6.  The accumulators are
+// drained every `seg_trials` trials (<= ~2048 K rows, equal segments: once per particle at C5) and the
+// segment sums are added to a fixed-point lag table.
 //
 // Warp roles (one persistent CTA per SM):
 //   G simulate groups of 128 threads - one trial each at a time: Philox + blocked scan as in
@@ -149,7 +151,7 @@ __device__ __forceinline__ void tc_tail_steps(const unsigned char* hi, const uns
 }
 
 template <bool MISSING, bool OSC, bool MIXED, bool TAIL>
-__global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcParams P) {
+__global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_constant__ AbcTcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kTcMaxGroups][2];      // [group][buffer] operands ready
     __shared__ __align__(8) uint64_t bar_empty[kTcMaxGroups][2];     // [group][buffer] operands consumed
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
         SimArgs sa;
         sa.n_t = P.n_t; sa.chunk = P.chunk;
         sa.inv_n = 1.0 / (double)P.n_t; sa.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
-        sa.k0 = P.k0; sa.k1 = P.k1; sa.c3_noise = P.c3_noise; sa.c3_init = P.c3_init;
+        sa.keys = &P.keys; sa.c3_noise = P.c3_noise; sa.c3_init = P.c3_init;
         sa.mask_bits = P.mask_bits; sa.n_valid = P.n_valid; sa.mask_words = P.mask_words;
         sa.miss_mean_ratio = P.miss_mean_ratio;
 
@@ -371,6 +373,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const AbcTcPara
                     sk = __int_as_float(0x7fc00000);
                 } else if (!TAIL || k < P.tc_lags) {
                     sk = (float)lagtab[k] * P.tc_unfix;
+                    // undo the accumulator's round-toward-zero to first order (abc_tc_geometry)
+                    const float acn = fminf(fabsf(sk) * P.tc_unscale * (float)inv_trials, 1.0f);
+                    sk = fmaf(sk, fmaf(P.bias_b * 0.63661977f, asinf(acn), P.bias_a), sk);
                 } else {
                     sk = 0.f;
                     for (int gg = 0; gg < G; ++gg)
@@ -506,22 +511,41 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     g->rows_total = best_rows;
     g->sbo_bytes = best_rows * 16;
     g->groups = groups; g->epi_offset = (int)epi_off; g->smem_bytes = total;
-    // trials per accumulator segment: ~768 K rows (truncation bias ~6.8e-9 per K row at lags with
-    // ac ~ 1, measured at C5: 2.3e-6 / 4.8e-6 / 1.7e-5 for 384 / 768 / 2496 rows), split evenly over the
-    // particle's trials
+    // trials per accumulator segment: up to ~2048 K rows of samples (the whole particle at C5), split evenly
+    // over the particle's trials.  The accumulator's round-toward-zero costs ~5.5e-9 per K row at lags
+    // with ac ~ 1 (measured at C5: 2.5e-6 / 5.3e-6 / 1.1e-5 for 520 / 1000 / 2000 rows); the epilogue undoes
+    // it to first order (bias_a / bias_b below), which leaves < 1.2e-6 at 2000 rows
     const int rows_trial = 16 * g->ksteps;
-    int seg = (768 + rows_trial / 2) / rows_trial;
+    int seg = 2048 / rows_data;
     if (seg < 1) seg = 1;
-    if (n_trials > 0) {                                    // equal segments: 50 trials -> 13, 13, 13, 11
+    if (n_trials > 0) {                                    // equal segments: 100 trials x 40 rows -> 50, 50
         const int n_seg = (n_trials + seg - 1) / seg;
         seg = (n_trials + n_seg - 1) / n_seg;
     }
+    (void)rows_trial;
     const char* e_seg = getenv("ITJL_TC_SEG");
     if (e_seg && atoi(e_seg) > 0) seg = atoi(e_seg);
     g->seg_trials = seg;
     g->n_terms = ((int64_t)n_t * n_trials >= 100000) ? 2 : 3;
     const char* e_terms = getenv("ITJL_TC_TERMS");
     if (e_terms && (atoi(e_terms) == 2 || atoi(e_terms) == 3)) g->n_terms = atoi(e_terms);
+    // The tensor-core accumulator rounds toward zero (tests/test_gpu_tc.py, probe): a cell that grows
+    // linearly to c over R accumulate steps loses sum_i ulp(c i / R) / 2 = R 2^-24 phi(c) c with
+    // phi in [1/3, 3/8] whatever the binade of c (measured: 1.85e-8 = 0.31 2^-24 per tcgen05.mma), and each
+    // product is truncated on alignment to the accumulator (measured 4.7e-9 per K row, times the sign
+    // imbalance (2/pi) asin(ac) of the products; constants fitted at 2000-row segments, 1184 particles,
+    // benchmarks/tc_error.py).  Every trial contributes the same sum of squares, so the
+    // growth is linear and the loss is a factor on the drained sums:
+    //     S_true = S (1 + bias_a + bias_b (2/pi) asin|ac|),
+    // bias_a = 1.85e-8 x (MMAs per accumulator per segment), bias_b = 4.7e-9 x (K rows per segment).
+    {
+        const int n_seg = n_trials > 0 ? (n_trials + seg - 1) / seg : 1;
+        const double trials_seg = n_trials > 0 ? (double)n_trials / n_seg : 1.0;
+        g->bias_a = (float)(1.85e-8 * trials_seg * g->ksteps * g->n_terms);
+        g->bias_b = (float)(4.7e-9 * trials_seg * rows_data);
+        const char* e_bias = getenv("ITJL_TC_BIAS");
+        if (e_bias && atoi(e_bias) == 0) g->bias_a = g->bias_b = 0.f;
+    }
     int p2 = 1; while (p2 * p2 < n_t) p2 <<= 1;                 // power of two near sqrt(n_t): series ~ N(0,1)
     g->tc_scale = (float)p2;
     // fixed-point unit of the lag table: n_trials * scale^2 * fix <= 2^30

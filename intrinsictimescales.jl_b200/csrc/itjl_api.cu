@@ -288,7 +288,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.chunk = m->psd_chunk; P.xs_len = m->psd_xs_len; P.n2 = m->n2; P.log2_n2 = m->log2_n2;
         P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
         P.update = d.update; P.kind = d.kind; P.distance = d.distance;
-        P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+        P.keys = philox_keys(seed);
         P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
         P.particle_offset = particle_offset;
         P.target = (const float*)m->target.p; P.binpos = (const int4*)m->bins.p; P.binidx = (const int32_t*)m->binidx.p;
@@ -303,7 +303,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
         P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_lags = (int)d.n_stats;
         P.dt = d.dt; P.update = d.update; P.kind = d.kind; P.distance = d.distance;
-        P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+        P.keys = philox_keys(seed);
         P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
         P.particle_offset = particle_offset;
         P.target = (const float*)m->target.p;
@@ -324,6 +324,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         }
         P.tc_scale = t.tc_scale; P.tc_unscale = 1.0f / (t.tc_scale * t.tc_scale);
         P.tc_fix = t.tc_fix; P.tc_unfix = 1.0f / t.tc_fix;
+        P.bias_a = t.bias_a; P.bias_b = t.bias_b;
         P.smem_bytes = t.smem_bytes;
         P.miss_mean_ratio = (d.kind == ITJL_KIND_OU_OSC && d.data_sd != 0.0) ? (float)(d.data_mean / d.data_sd) : 0.f;
         { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
@@ -337,7 +338,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.n_streams = m->geo.n_streams; P.tiles_per_stream = m->geo.tiles_per_stream; P.n_tiles = m->geo.n_tiles;
         P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
         P.update = d.update; P.kind = d.kind; P.distance = d.distance;
-        P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+        P.keys = philox_keys(seed);
         P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
         P.particle_offset = particle_offset;
         P.target = (const float*)m->target.p;
@@ -477,7 +478,7 @@ static int generate_common(itjl_ctx* ctx, int kind, double tau, double freq, dou
     if ((int64_t)smem > ctx->max_smem_optin) return fail(ctx, ITJL_ERR_ARG, "generate_ou: n_t too large for one CTA");
     P.tau = tau; P.freq = freq; P.coeff = coeff; P.dt = dt;
     P.update = update; P.kind = kind; P.mode = mode; P.scale = (float)scale; P.shift = (float)shift;
-    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32);
+    P.keys = philox_keys(seed);
     P.c3_noise = philox_c3(kStreamNoise, 0); P.c3_init = philox_c3(kStreamInit, 0); P.particle = 0;
     int rc = ITJL_OK;
     if (u0) { rc = upload(ctx, ctx->u0, u0, (size_t)n_trials * sizeof(double)); P.u0 = (const double*)ctx->u0.p; }

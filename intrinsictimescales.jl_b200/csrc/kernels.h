@@ -1,6 +1,7 @@
 // Internal declarations shared between the kernel translation units and the C-ABI layer.
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace itjl {
 
@@ -14,7 +15,8 @@ struct AbcAcfParams {
     int lt, n_streams, tiles_per_stream, n_tiles;
     double dt, data_mean, data_sd;
     int update, kind, distance;
-    uint32_t k0, k1, c3_noise, c3_init;
+    PhiloxKeys keys;
+    uint32_t c3_noise, c3_init;
     int64_t particle_offset;
     const float* target;
     const uint32_t* mask_bits;
@@ -47,7 +49,8 @@ struct AbcPsdParams {
     int n2, log2_n2;            // zero-padded real FFT length 2*nextpow2(n_t)
     double dt, data_mean, data_sd;
     int update, kind, distance;
-    uint32_t k0, k1, c3_noise, c3_init;
+    PhiloxKeys keys;
+    uint32_t c3_noise, c3_init;
     int64_t particle_offset;
     const float* target;        // n_stats
     const int4* binpos;         // n_stats: {storage pos of Z[k], of Z[N-k], bits of the twiddle exp(-2 pi i k / n2)}, k = bin + 1
@@ -77,7 +80,8 @@ struct OuGenParams {
     double tau, freq, coeff, dt;
     int update, kind, mode;     // mode: kScale*
     float scale, shift;
-    uint32_t k0, k1, c3_noise, c3_init, particle;
+    PhiloxKeys keys;
+    uint32_t c3_noise, c3_init, particle;
     const double* u0;
     const double* noise;
     const double* phases;
@@ -119,6 +123,7 @@ struct AbcTcGeometry {
     int groups, chunk, epi_offset;
     int rows_total, ksteps, sbo_bytes;
     int used_cols, mixed, seg_trials, n_terms;
+    float bias_a, bias_b;        // first-order correction of the accumulator's round-toward-zero (see abc_tc_geometry)
     int tc_lags, tail_start, tail_lt, tail_steps, tail_steps_per_stream;
     // MMA ops of one K step: A / B operand start (8-row MN block, K-row shift), shape, TMEM address
     int n_ops;
@@ -135,7 +140,8 @@ struct AbcTcParams {
     int n_t, n_trials, n_lags;
     double dt;
     int update, kind, distance;
-    uint32_t k0, k1, c3_noise, c3_init;
+    PhiloxKeys keys;
+    uint32_t c3_noise, c3_init;
     int64_t particle_offset;
     const float* target;
     const uint32_t* mask_bits;
@@ -155,6 +161,7 @@ struct AbcTcParams {
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
     float tc_scale, tc_unscale, tc_fix, tc_unfix;
+    float bias_a, bias_b;
     float miss_mean_ratio;       // data_mean / data_sd for the oscillation + missing-data model, else 0
     size_t smem_bytes;
     int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = no MMAs, 2 = no simulation after the first particle

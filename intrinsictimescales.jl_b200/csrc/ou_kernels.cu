@@ -8,7 +8,7 @@
 namespace itjl {
 
 template <bool OSC>
-__global__ void __launch_bounds__(kThreads) k_ou_generate(const OuGenParams P) {
+__global__ void __launch_bounds__(kThreads) k_ou_generate(const __grid_constant__ OuGenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);
     SimShared<kThreads>* sh = reinterpret_cast<SimShared<kThreads>*>(xs + (size_t)P.chunk * kThreads);
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(kThreads) k_ou_generate(const OuGenParams P) {
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
     g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
-    g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
+    g.keys = &P.keys; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
     g.particle = P.particle;
     g.u0 = P.u0; g.noise = P.noise; g.phases = P.phases;
     g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;

@@ -18,16 +18,32 @@ __host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t stream, uint64_t
     return ((stream & 0xFu) << 28) | (uint32_t)(generation & 0x0FFFFFFFull);
 }
 
+// The ten round keys (k0 + r W0, k1 + r W1) depend on the seed only: the host expands them once per
+// launch into the kernel parameters, so the rounds read them as constant-bank operands instead of
+// holding twenty registers (or re-adding the Weyl constants) in every thread.
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+
+__host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0; K.k[2 * r + 1] = k1;
+        k0 += kPhiloxW0; k1 += kPhiloxW1;
+    }
+    return K;
+}
+
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+                                              const PhiloxKeys& K, uint32_t (&out)[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
         c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
-        k0 += kPhiloxW0; k1 += kPhiloxW1;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }

@@ -210,7 +210,7 @@ __device__ __forceinline__ float real_fft_power_at(const float2* __restrict__ bu
 constexpr int kPsdThreads = 512;      // fused PSD kernel: 1 CTA/SM (the FFT buffer fills shared memory)
 
 template <bool OSC>
-__global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P) {
+__global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const __grid_constant__ AbcPsdParams P) {
     constexpr int NT = kPsdThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats: one simulated trial
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const AbcPsdParams P
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
     g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
-    g.k0 = P.k0; g.k1 = P.k1; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
+    g.keys = &P.keys; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
     g.particle = (uint32_t)(P.particle_offset + particle);
     const size_t pt = (size_t)particle * P.n_trials;
     g.u0 = P.u0 ? P.u0 + pt : nullptr;

@@ -66,7 +66,7 @@ struct SimArgs {
     double inv_n;             // 1 / n_t
     float sqrt_nm1;           // sqrt(n_t - 1)
     int chunk;                // samples per thread (multiple of 4, chunk * NT >= n_t)
-    uint32_t k0, k1;          // Philox key (seed)
+    const PhiloxKeys* keys;   // Philox round keys (seed), in the kernel parameters
     uint32_t c3_noise, c3_init;
     uint32_t particle;        // global particle index (low 32 bits)
     const double* u0;         // [trial] injected initial states of this particle, or null
@@ -132,7 +132,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     double phase_turns;
     {
         uint32_t r[4];
-        philox4x32_10(0u, (uint32_t)trial, g.particle, g.c3_init, g.k0, g.k1, r);
+        philox4x32_10(0u, (uint32_t)trial, g.particle, g.c3_init, *g.keys, r);
         float z1;
         box_muller(r[0], r[1], x0, z1);
         phase_turns = (double)u01(r[2]);
@@ -149,25 +149,8 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     const bool need_p_sums = !cache.valid;
     if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
     if (j0 < g.n_t) {
-        for (int q = 0; q < g.chunk; q += 4) {
-            const int j = j0 + q;
-            float z[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t mbits = 0u;
-            const bool full = (j + 3 < g.n_t);
-            if (j < g.n_t) {
-                if (nz) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (j + i < g.n_t) z[i] = (float)nz[j + i];
-                } else {
-                    uint32_t r[4];
-                    philox4x32_10((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise,
-                                  g.k0, g.k1, r);
-                    box_muller(r[0], r[1], z[0], z[1]);
-                    box_muller(r[2], r[3], z[2], z[3]);
-                }
-                if (MISSING) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
-            }
+        // recurrence + partial sums + store of the four samples j .. j+3 driven by z[0..3]
+        auto advance4 = [&](const int j, const float (&z)[4], const bool full, const uint32_t mbits) {
             float v[4], pp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -211,6 +194,44 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
             } else {
                 *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
             }
+        };
+        int q = 0;
+        if (!MISSING && !nz) {
+            // interior of the trial, Philox noise: two counter blocks (eight samples) per iteration in one
+            // basic block, so the two ten-round chains and their Box-Muller transforms interleave
+            for (; q + 8 <= g.chunk && j0 + q + 7 < g.n_t; q += 8) {
+                const int j = j0 + q;
+                uint32_t ra[4], rb[4];
+                philox4x32_10((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise, *g.keys, ra);
+                philox4x32_10((uint32_t)(j >> 2) + 1u, (uint32_t)trial, g.particle, g.c3_noise, *g.keys, rb);
+                float za[4], zb[4];
+                box_muller(ra[0], ra[1], za[0], za[1]);
+                box_muller(ra[2], ra[3], za[2], za[3]);
+                box_muller(rb[0], rb[1], zb[0], zb[1]);
+                box_muller(rb[2], rb[3], zb[2], zb[3]);
+                advance4(j, za, true, 0u);
+                advance4(j + 4, zb, true, 0u);
+            }
+        }
+        for (; q < g.chunk; q += 4) {
+            const int j = j0 + q;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t mbits = 0u;
+            const bool full = (j + 3 < g.n_t);
+            if (j < g.n_t) {
+                if (nz) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (j + i < g.n_t) z[i] = (float)nz[j + i];
+                } else {
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise, *g.keys, r);
+                    box_muller(r[0], r[1], z[0], z[1]);
+                    box_muller(r[2], r[3], z[2], z[3]);
+                }
+                if (MISSING) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
+            }
+            advance4(j, z, full, mbits);
         }
     }
     if (need_p_sums) { cache.Sp = Sp; cache.Spp = Spp; cache.valid = true; }

@@ -139,10 +139,12 @@ static void ws_destroy(workspace* w) {
     fft_plan_destroy(w->plan); free(w->x); free(w->re); free(w->im); free(w->acc); free(w->win); free(w);
 }
 
-/* one particle: returns the distance */
+/* one particle: returns the distance; stats_out (optional, n_stats) receives the trial-mean
+ * summary statistic the distance was computed from */
 static double particle_distance(const oracle_model_desc* m, workspace* w, const double* theta,
                                 uint64_t seed, uint64_t gen, uint64_t particle,
-                                const double* u0_in, const double* noise_in, const double* phase_in) {
+                                const double* u0_in, const double* noise_in, const double* phase_in,
+                                double* stats_out) {
     const int n = (int)m->n_t, ntr = (int)m->n_trials;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const double tau = theta[0];
@@ -245,12 +247,18 @@ static double particle_distance(const oracle_model_desc* m, workspace* w, const 
                 w->acc[j] += (w->re[j] * w->re[j] + w->im[j] * w->im[j]) * scl;
         }
     }
-    if (bad) return NAN;
+    if (bad) {
+        if (stats_out) for (int k = 0; k < (int)m->n_stats; ++k) stats_out[k] = NAN;
+        return NAN;
+    }
+    /* trial means in place (freq_bins is increasing, so acc[bins[k] + 1] is read before acc[k] is
+       overwritten); the distance loop below is the same code with and without stats_out */
+    for (int k = 0; k < (int)m->n_stats; ++k)
+        w->acc[k] = ((m->summary == 2) ? w->acc[m->freq_bins[k] + 1] : w->acc[k]) / ntr;   /* +1: DC dropped */
+    if (stats_out) memcpy(stats_out, w->acc, sizeof(double) * (size_t)m->n_stats);
     double d = 0.0;
     for (int k = 0; k < (int)m->n_stats; ++k) {
-        double v;
-        if (m->summary == 2) v = w->acc[m->freq_bins[k] + 1] / ntr;   /* +1: DC dropped */
-        else v = w->acc[k] / ntr;
+        double v = w->acc[k];
         double e = (m->distance == 0) ? (v - m->target_stats[k]) : (log(v) - log(m->target_stats[k]));
         d += e * e;
     }
@@ -264,6 +272,7 @@ typedef struct {
     const oracle_model_desc* m; const double* theta; int64_t n_particles; int32_t n_theta;
     uint64_t seed, generation; int64_t particle_offset;
     const double *u0, *noise, *phases; double* dist_out; atomic_llong* next;
+    double* stats_out;                       /* optional (n_particles, n_stats) row-major */
 } job_t;
 
 static void* worker(void* arg) {
@@ -280,7 +289,8 @@ static void* worker(void* arg) {
                                            (uint64_t)(j->particle_offset + i),
                                            j->u0 ? j->u0 + pt : NULL,
                                            j->noise ? j->noise + pt * m->n_t : NULL,
-                                           j->phases ? j->phases + pt : NULL);
+                                           j->phases ? j->phases + pt : NULL,
+                                           j->stats_out ? j->stats_out + (size_t)i * m->n_stats : NULL);
     }
     ws_destroy(w);
     return NULL;
@@ -291,20 +301,28 @@ int itjl_oracle_max_threads(void) {
     return n > 0 ? (int)n : 1;
 }
 
-int itjl_oracle_abc_distances(const oracle_model_desc* m, const double* theta, int64_t n_particles,
-                              int32_t n_theta, uint64_t seed, uint64_t generation,
-                              int64_t particle_offset, const double* u0, const double* noise,
-                              const double* phases, double* dist_out, int32_t n_threads) {
+int itjl_oracle_abc_stats(const oracle_model_desc* m, const double* theta, int64_t n_particles,
+                          int32_t n_theta, uint64_t seed, uint64_t generation,
+                          int64_t particle_offset, const double* u0, const double* noise,
+                          const double* phases, double* dist_out, double* stats_out, int32_t n_threads) {
     if (n_threads <= 0) n_threads = itjl_oracle_max_threads();
     if (n_threads > 256) n_threads = 256;
     if ((int64_t)n_threads > n_particles) n_threads = (int32_t)(n_particles > 0 ? n_particles : 1);
     atomic_llong next = 0;
     job_t job = {m, theta, n_particles, n_theta, seed, generation, particle_offset,
-                 u0, noise, phases, dist_out, &next};
+                 u0, noise, phases, dist_out, &next, stats_out};
     if (n_threads == 1) { worker(&job); return 0; }
     pthread_t tid[256];
     for (int t = 0; t < n_threads; ++t)
         if (pthread_create(&tid[t], NULL, worker, &job) != 0) return -1;
     for (int t = 0; t < n_threads; ++t) pthread_join(tid[t], NULL);
     return 0;
+}
+
+int itjl_oracle_abc_distances(const oracle_model_desc* m, const double* theta, int64_t n_particles,
+                              int32_t n_theta, uint64_t seed, uint64_t generation,
+                              int64_t particle_offset, const double* u0, const double* noise,
+                              const double* phases, double* dist_out, int32_t n_threads) {
+    return itjl_oracle_abc_stats(m, theta, n_particles, n_theta, seed, generation, particle_offset,
+                                 u0, noise, phases, dist_out, NULL, n_threads);
 }

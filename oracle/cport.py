@@ -38,6 +38,7 @@ def lib():
         build()                      # make is a no-op when the .so is up to date
         _lib = ctypes.CDLL(_SO)
         _lib.itjl_oracle_abc_distances.restype = ctypes.c_int
+        _lib.itjl_oracle_abc_stats.restype = ctypes.c_int
         _lib.itjl_oracle_max_threads.restype = ctypes.c_int
     return _lib
 
@@ -77,8 +78,9 @@ def model_arrays(model):
 
 
 def abc_distances(model, theta, seed=0, generation=0, particle_offset=0, u0=None, noise=None,
-                  phases=None, n_threads=0):
-    """theta: (n_particles, p).  Returns float64 distances."""
+                  phases=None, n_threads=0, return_stats=False):
+    """theta: (n_particles, p).  Returns float64 distances (and, with return_stats, the
+    (n_particles, n_stats) trial-mean summary statistics they were computed from)."""
     theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
     n, p = theta.shape
     th = np.asfortranarray(theta)
@@ -92,12 +94,14 @@ def abc_distances(model, theta, seed=0, generation=0, particle_offset=0, u0=None
         keep[id(a)] = a
         return ctypes.c_void_p(a.ctypes.data)
 
-    rc = lib().itjl_oracle_abc_distances(ctypes.byref(d), ctypes.c_void_p(th.ctypes.data),
-                                         ctypes.c_int64(n), ctypes.c_int32(p),
-                                         ctypes.c_uint64(seed), ctypes.c_uint64(generation),
-                                         ctypes.c_int64(particle_offset), ptr(u0), ptr(noise),
-                                         ptr(phases), ctypes.c_void_p(out.ctypes.data),
-                                         ctypes.c_int32(n_threads))
+    stats = np.empty((n, int(d.n_stats)), dtype=np.float64) if return_stats else None
+    rc = lib().itjl_oracle_abc_stats(ctypes.byref(d), ctypes.c_void_p(th.ctypes.data),
+                                     ctypes.c_int64(n), ctypes.c_int32(p),
+                                     ctypes.c_uint64(seed), ctypes.c_uint64(generation),
+                                     ctypes.c_int64(particle_offset), ptr(u0), ptr(noise),
+                                     ptr(phases), ctypes.c_void_p(out.ctypes.data),
+                                     ctypes.c_void_p(stats.ctypes.data) if return_stats else None,
+                                     ctypes.c_int32(n_threads))
     if rc != 0:
-        raise RuntimeError(f"itjl_oracle_abc_distances -> {rc}")
-    return out
+        raise RuntimeError(f"itjl_oracle_abc_stats -> {rc}")
+    return (out, stats) if return_stats else out

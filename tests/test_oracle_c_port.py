@@ -58,3 +58,21 @@ def test_osc_matches_numpy_oracle(summary_method):
     dc = cport.abc_distances(m, th, seed=5, generation=3)
     dn = [models.generate_data_and_reduce(m, x, seed=5, generation=3, particle=i) for i, x in enumerate(th)]
     assert np.allclose(dc, dn, rtol=1e-9, atol=1e-14)
+
+
+def test_statistics_output_matches_numpy_oracle():
+    """itjl_oracle_abc_stats: the per-particle trial-mean statistics behind each distance (used by the
+    many-particle GPU parity test of the tensor-core kernel) equal the NumPy oracle's."""
+    n = 1500
+    data = ou.generate_ou_process(0.15, 1.0, DT, _time(n)[-1], 3, seed=123, n_t=n)
+    data_m = data.copy(); data_m[1, 200:320] = np.nan
+    for m in (models.one_timescale_model(data, _time(n), prior=[models.Uniform(0.05, 5)]),
+              models.one_timescale_with_missing_model(data_m, _time(n), prior=[models.Uniform(0.05, 5)])):
+        th = np.array([[0.15], [1.0], [0.05], [-0.001]])
+        d, s = cport.abc_distances(m, th, seed=8, generation=2, return_stats=True)
+        assert s.shape == (4, m.n_lags) and np.isnan(s[-1]).all() and np.isnan(d[-1])
+        for i in range(3):
+            ref = models.summary_stats(m, models.generate_data(m, th[i], seed=8, generation=2, particle=i))
+            assert np.allclose(s[i], ref, rtol=0, atol=1e-12)
+            assert np.isclose(d[i], np.mean((ref - m.data_sum_stats) ** 2), rtol=1e-10)
+        assert np.array_equal(d, cport.abc_distances(m, th, seed=8, generation=2), equal_nan=True)
