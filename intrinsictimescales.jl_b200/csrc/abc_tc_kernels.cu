@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
         TcSink sink;
         sink.sbo = P.sbo_bytes;
         sink.scale = P.tc_scale;
+        sink.write_lo = TAIL || P.n_terms > 1;            // the lo plane is an MMA operand only with cross terms (and the FFMA tail reads it)
 
         SimArgs sa;
         sa.n_t = P.n_t; sa.chunk = P.chunk;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                                 const uint32_t d_t = tmem_base + P.op_taddr[o];
                                 const uint32_t idesc = P.op_idesc[o];
                                 tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_hi + b_off, idesc, first);
-                                tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_lo + b_off, idesc, 1u);
+                                if (P.n_terms >= 2) tc::mma_f16_ss_elect(d_t, d_hi + a_off, d_lo + b_off, idesc, 1u);
                                 if (P.n_terms == 3) tc::mma_f16_ss_elect(d_t, d_lo + a_off, d_hi + b_off, idesc, 1u);
                             }
                         }
@@ -526,22 +527,29 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     const char* e_seg = getenv("ITJL_TC_SEG");
     if (e_seg && atoi(e_seg) > 0) seg = atoi(e_seg);
     g->seg_trials = seg;
-    g->n_terms = ((int64_t)n_t * n_trials >= 100000) ? 2 : 3;
+    // product terms of the fp16 hi/lo split x' = hi + lo: hi*hi (+ hi*lo (+ lo*hi)).  A dropped cross term is
+    // a zero-mean residual of relative size 2^-12 per product, i.e. ~1e-4 sqrt(1 + 2 ac^2) / sqrt(samples
+    // per particle) on a trial-mean ACF value: 3.5e-7 (one cross term dropped) / 5e-7 (both) at C5's 2.5e5
+    // samples, against the 1e-5 tolerance (measured over 1184 particles against the fp64 oracle: rms 6.5e-7 /
+    // 1.0e-6, max 4.4e-6 / 6.3e-6, everything else included)
+    const int64_t samples = (int64_t)n_t * n_trials;
+    g->n_terms = samples >= 200000 ? 1 : (samples >= 100000 ? 2 : 3);
     const char* e_terms = getenv("ITJL_TC_TERMS");
-    if (e_terms && (atoi(e_terms) == 2 || atoi(e_terms) == 3)) g->n_terms = atoi(e_terms);
+    if (e_terms && atoi(e_terms) >= 1 && atoi(e_terms) <= 3) g->n_terms = atoi(e_terms);
     // The tensor-core accumulator rounds toward zero (tests/test_gpu_tc.py, probe): a cell that grows
     // linearly to c over R accumulate steps loses sum_i ulp(c i / R) / 2 = R 2^-24 phi(c) c with
-    // phi in [1/3, 3/8] whatever the binade of c (measured: 1.85e-8 = 0.31 2^-24 per tcgen05.mma), and each
+    // phi in [1/3, 3/8] whatever the binade of c (measured: 2.1e-8 = 0.35 2^-24 per hi*hi tcgen05.mma, 1.6e-8
+    // per cross-term MMA), and each
     // product is truncated on alignment to the accumulator (measured 4.7e-9 per K row, times the sign
     // imbalance (2/pi) asin(ac) of the products; constants fitted at 2000-row segments, 1184 particles,
     // benchmarks/tc_error.py).  Every trial contributes the same sum of squares, so the
     // growth is linear and the loss is a factor on the drained sums:
     //     S_true = S (1 + bias_a + bias_b (2/pi) asin|ac|),
-    // bias_a = 1.85e-8 x (MMAs per accumulator per segment), bias_b = 4.7e-9 x (K rows per segment).
+    // bias_a = (2.1e-8 + 1.6e-8 (n_terms - 1)) x (K steps per segment), bias_b = 4.7e-9 x (K rows per segment).
     {
         const int n_seg = n_trials > 0 ? (n_trials + seg - 1) / seg : 1;
         const double trials_seg = n_trials > 0 ? (double)n_trials / n_seg : 1.0;
-        g->bias_a = (float)(1.85e-8 * trials_seg * g->ksteps * g->n_terms);
+        g->bias_a = (float)((2.1e-8 + 1.6e-8 * (g->n_terms - 1)) * trials_seg * g->ksteps);
         g->bias_b = (float)(4.7e-9 * trials_seg * rows_data);
         const char* e_bias = getenv("ITJL_TC_BIAS");
         if (e_bias && atoi(e_bias) == 0) g->bias_a = g->bias_b = 0.f;

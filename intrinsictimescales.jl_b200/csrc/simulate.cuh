@@ -98,6 +98,7 @@ struct TcSink {
     unsigned char* lo;
     int sbo;
     float scale;              // power of two
+    bool write_lo;            // false: only the hi plane is consumed (single-term products), skip the residuals
     uint64_t* wait_bar;
     uint32_t wait_parity;
 };
@@ -349,16 +350,25 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
             }
             if (TC) {
                 uint32_t hp[4], lp[4];
+                if (sink->write_lo) {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const __half2 hh = __floats2half2_rn(v[2 * h], v[2 * h + 1]);
-                    const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(v[2 * h] - hf.x, v[2 * h + 1] - hf.y);
-                    hp[h] = *reinterpret_cast<const uint32_t*>(&hh);
-                    lp[h] = *reinterpret_cast<const uint32_t*>(&ll);
+                    for (int h = 0; h < 4; ++h) {
+                        const __half2 hh = __floats2half2_rn(v[2 * h], v[2 * h + 1]);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(v[2 * h] - hf.x, v[2 * h + 1] - hf.y);
+                        hp[h] = *reinterpret_cast<const uint32_t*>(&hh);
+                        lp[h] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    *reinterpret_cast<uint4*>(sink->hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                    *reinterpret_cast<uint4*>(sink->lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const __half2 hh = __floats2half2_rn(v[2 * h], v[2 * h + 1]);
+                        hp[h] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(sink->hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 }
-                *reinterpret_cast<uint4*>(sink->hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                *reinterpret_cast<uint4*>(sink->lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
             }
         }
     } else if (!TC) {

@@ -185,10 +185,10 @@ def test_unsupported_shapes_fall_back_to_cuda_core_kernel(pkg, ctx):
             os.environ["ITJL_ABC_TC"] = old
 
 
-def test_two_term_split_and_rounding_correction_over_many_particles(pkg, ctx):
-    """C5 shape (50 x 5000 = 2.5e5 samples per particle => hi*hi + hi*lo only, ONE accumulator segment per
+def test_single_term_products_and_rounding_correction_over_many_particles(pkg, ctx):
+    """C5 shape (50 x 5000 = 2.5e5 samples per particle => hi*hi products only, ONE accumulator segment per
     particle): the summary statistics of 1184 Philox-driven particles against the fp64 C restatement of the
-    reference.  The dropped lo*hi term behaves like the documented zero-mean residual, and the
+    reference.  The dropped cross terms behave like the documented zero-mean residual, and the
     round-toward-zero of the tensor-core accumulator (-1.1e-5 at lags with ac ~ 1 when uncorrected) is
     removed by the epilogue's first-order correction: no error proportional to the value is left.
     The CUDA-core kernel (fp32 FFMA sums of the same series) is held to the same tolerance."""
@@ -197,7 +197,7 @@ def test_two_term_split_and_rounding_correction_over_many_particles(pkg, ctx):
     g_tc, g_ff = _gpu_models(mk, ctx)
     plan = (ctypes.c_int32 * 16)()
     assert pkg._lib.lib().itjl_tc_plan(5000, 414, 50, 232448, 148, plan) == 0
-    assert plan[6] == 50 and plan[7] == 2                   # seg_trials, n_terms
+    assert plan[6] == 50 and plan[7] == 1                   # seg_trials, n_terms
     rng = np.random.default_rng(7)
     theta = rng.uniform(0.05, 5.0, size=(1184, 1))
     d_tc, s_tc = g_tc.distances(theta, seed=21, generation=4, return_stats=True)

@@ -131,9 +131,9 @@ def test_tensor_core_plan_selection_is_host_logic(pkg):
         rc = lib.itjl_tc_plan(n_t, n_lags, n_trials, 232448, 148, out)
         return rc, dict(zip(names, list(out)))
 
-    rc, p = plan(5000, 414, 50)                       # C5: plan B, no tail, one 50-trial segment, 2 terms
+    rc, p = plan(5000, 414, 50)                       # C5: plan B, no tail, one 50-trial segment, hi*hi only (2.5e5 samples)
     assert rc == 0 and p["mixed"] == 1 and p["n_ops"] == 6 and p["tail_lt"] == 0 and p["tc_lags"] == 414
-    assert p["groups"] == 4 and p["chunk"] == 40 and p["ksteps"] == 3 and p["seg_trials"] == 50 and p["n_terms"] == 2
+    assert p["groups"] == 4 and p["chunk"] == 40 and p["ksteps"] == 3 and p["seg_trials"] == 50 and p["n_terms"] == 1
     assert p["rows_total"] >= 16 * 3 + 4 and p["smem_bytes"] + 6 * 1024 <= 232448 and p["grid"] == 148
     rc, p = plan(5000, 463, 100)                      # C3: plan B + one tail tile of 16 lags from lag 448
     assert rc == 0 and p["mixed"] == 1 and p["tc_lags"] == 449 and p["tail_start"] == 448 and p["tail_lt"] == 1
