@@ -75,8 +75,8 @@ constexpr int kTcLagTab = 512;                      // lag table entries (tensor
 // on the order of the four warps (and ATOMS.ADD is native; a 64-bit add would be a CAS loop).  `fix` is
 // the power of two that maps the largest possible sum (lag 0: n_trials * scale^2) to 2^30, i.e. a
 // rounding of ~5e-10 of full scale per add.
-__device__ __forceinline__ void tc_lag_add(int* lagtab, int k, float v, int n, float fix, int* bad) {
-    if (k >= 0 && k < n) {
+__device__ __forceinline__ void tc_lag_add(int* lagtab, int k, float v, int lo, int n, float fix, int* bad) {
+    if (k >= lo && k < n) {
         const float f = v * fix;
         if (!(fabsf(f) < 2.0e9f)) *bad = 1;               // NaN / Inf: the particle's statistics become NaN
         else atomicAdd(&lagtab[k], __float2int_rn(f));
@@ -349,11 +349,11 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                             // upper strip: rows a = 48 + 16 q + lane, columns of D_4 (c < 2) start at v = 512
                             const int kl = 32 * c - 16 * q - lane;
                             const int ku = 32 * c - 48 - 16 * q - lane + (c < 2 ? 512 : 0);
-                            tc_lag_add(lagtab, kl, a0, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, kl + 32, a1, P.tc_lags, P.tc_fix, &nonfinite);
-                            tc_lag_add(lagtab, ku, b0, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, ku + 32, b1, P.tc_lags, P.tc_fix, &nonfinite);
+                            tc_lag_add(lagtab, kl, a0, P.k_lo, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, kl + 32, a1, P.k_lo, P.tc_lags, P.tc_fix, &nonfinite);
+                            tc_lag_add(lagtab, ku, b0, P.k_lo, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, ku + 32, b1, P.k_lo, P.tc_lags, P.tc_fix, &nonfinite);
                         } else {
                             const int k = 32 * (c - q) - lane;
-                            tc_lag_add(lagtab, k, a0 + b0, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, k + 32, a1 + b1, P.tc_lags, P.tc_fix, &nonfinite);
+                            tc_lag_add(lagtab, k, a0 + b0, P.k_lo, P.tc_lags, P.tc_fix, &nonfinite); tc_lag_add(lagtab, k + 32, a1 + b1, P.k_lo, P.tc_lags, P.tc_fix, &nonfinite);
                         }
                     }
                 }
@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
             if (TAIL) tc::mbar_wait(&bar_tail_full, it & 1u);
             const bool bad_particle = nonfinite != 0;
             double local = 0.0;
-            for (int k = e_tid; k < P.n_lags; k += kTcEpiThreads) {
+            // this launch's lag window: relative lags [k_lo, k_hi) of the table, absolute lag = lag_base + k
+            const int k_hi = TAIL ? P.n_lags : min(P.tc_lags, P.n_lags - P.lag_base);
+            for (int k = P.k_lo + e_tid; k < k_hi; k += kTcEpiThreads) {
                 float sk;
                 if (bad_particle) {
                     sk = __int_as_float(0x7fc00000);
@@ -384,8 +386,9 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                 }
                 const double v = __dmul_rn((double)(sk * P.tc_unscale), inv_trials);   // no FMA contraction with the
                                                                                       // subtraction below: same bits with and without stats_out
-                if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + k] = v;
-                const double tgt = (double)P.target[k];
+                const int ka = P.lag_base + k;
+                if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + ka] = v;
+                const double tgt = (double)P.target[ka];
                 const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
                 local += e * e;
             }
@@ -393,7 +396,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
             if (lane == 0) red[q] = local;
             tc::named_bar_sync(kTcBarEpi, kTcEpiThreads);
             if (e_tid == 0) {
-                P.dist_out[particle] = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
+                const double part = (red[0] + red[1] + red[2] + red[3]) / (double)P.n_lags;
+                P.dist_out[particle] = P.accumulate ? P.dist_out[particle] + part : part;   // second window: launches are stream ordered
                 if (TAIL) tc::mbar_arrive(&bar_tail_free);
             }
             for (int k = e_tid; k < kTcLagTab; k += kTcEpiThreads) lagtab[k] = 0;
@@ -433,8 +437,15 @@ static int tc_store_conflicts(int sbo_bytes, int chunk) {
 // Geometry of the tensor-core kernel; returns 0 when the configuration is supported.
 int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g) {
     if (n_t < 16 || n_lags < 1 || n_lags > n_t) return -1;
-    const int max_tail = 60;                               // FFMA tail lags beyond the tensor-memory plans
-    if (n_lags > 449 + max_tail) return -2;
+    // FFMA tail lags beyond the tensor-memory plans.  The tail code handles up to 60 (four tiles of 16), but
+    // only one tile pays: at C5 shape 2.8e11 samples/s with a 16-lag tail against 2.4e11 for a second lag
+    // window, 2.3e11 / 1.7e11 with two / four tail tiles
+    int max_tail = 15;
+    { const char* e_t = getenv("ITJL_TC_TAIL_MAX"); if (e_t && atoi(e_t) >= 0 && atoi(e_t) <= 60) max_tail = atoi(e_t); }   // tuning only
+    // n_lags 465 .. 769: two launches (lag windows), the second with the B operand 3 rows further down
+    g->n_windows = n_lags > 449 + max_tail ? 2 : 1;
+    g->win1_s0 = 3; g->win1_used_cols = 0;
+    if (n_lags > 128 * g->win1_s0 + 385) return -2;
     const int rows_data = (n_t + 127) / 128;
     g->ksteps = (rows_data + 15) / 16;
     int max_shift;
@@ -468,9 +479,13 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     }
     g->tc_lags = n_lags < 449 ? n_lags : 449;
     if (n_lags <= 385) g->tc_lags = n_lags;
+    if (g->n_windows == 2) {
+        g->win1_used_cols = (((n_lags - 128 * g->win1_s0) + 127) + 15) & ~15;      // <= 512
+        max_shift = g->win1_s0 + (g->win1_used_cols + 127) / 128 - 1;
+    }
     // FFMA tail: tiles of 16 lags from tail_start (a multiple of 8: 16-byte groups of the planes)
     g->tail_start = g->tc_lags & ~7;
-    const int tail = n_lags > g->tc_lags ? n_lags - g->tail_start : 0;
+    const int tail = (n_lags > g->tc_lags && g->n_windows == 1) ? n_lags - g->tail_start : 0;
     g->tail_lt = tail == 0 ? 0 : (tail <= kTailK ? 1 : (tail <= 2 * kTailK ? 2 : 4));
     if (tail > 4 * kTailK) return -2;
     g->tail_steps = (n_t + kTailT - 1) / kTailT;

@@ -9,6 +9,7 @@
 
 #include "kernels.h"
 #include "philox.cuh"
+#include "tc05.cuh"
 
 namespace itjl {
 char g_err[512] = {0};
@@ -246,7 +247,7 @@ int itjl_tc_plan(int64_t n_t, int64_t n_lags, int64_t n_trials, int32_t max_smem
     const int rc = abc_tc_geometry((int)n_t, (int)n_lags, (int)n_trials, max_smem_optin, sm_count, &g);
     if (rc != 0) return fail(nullptr, ITJL_ERR_ARG, "itjl_tc_plan: shape outside the tensor-core kernel's plans");
     const int32_t v[16] = {g.groups, g.chunk, g.ksteps, g.rows_total, g.used_cols, g.mixed, g.seg_trials, g.n_terms,
-                           g.tc_lags, g.tail_start, g.tail_lt, g.n_ops, (int32_t)g.smem_bytes, g.grid, 0, 0};
+                           g.tc_lags, g.tail_start, g.tail_lt, g.n_ops, (int32_t)g.smem_bytes, g.grid, g.n_windows, 0};
     memcpy(out, v, sizeof(v));
     return ITJL_OK;
 }
@@ -263,6 +264,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
         const double M = (double)(((id >> 24) & 0x1Fu) << 4), N = (double)(((id >> 17) & 0x3Fu) << 3);
         f += 2.0 * M * N * 16.0;
     }
+    if (m->tc.n_windows == 2) f += 2.0 * 128.0 * (double)m->tc.win1_used_cols * 16.0;
     *tensor_flops_per_sample = f * (double)m->tc.n_terms * m->tc.ksteps / (double)m->d.n_t;
     return ITJL_OK;
 }
@@ -328,8 +330,30 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.smem_bytes = t.smem_bytes;
         P.miss_mean_ratio = (d.kind == ITJL_KIND_OU_OSC && d.data_sd != 0.0) ? (float)(d.data_mean / d.data_sd) : 0.f;
         { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
+        P.k_lo = 0; P.lag_base = 0; P.accumulate = 0;
         e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,
                           t.smem_bytes, t.grid, ctx->stream);
+        if (e == cudaSuccess && t.n_windows == 2) {
+            // second lag window: same trajectories (same Philox counters), B operand win1_s0 rows further
+            // down, plan-A tiles; scores the lags [449, n_lags) and adds its share of the distance
+            P.lag_base = 128 * t.win1_s0;
+            P.k_lo = t.tc_lags - P.lag_base;
+            P.tc_lags = (int)d.n_stats - P.lag_base;
+            P.used_cols = t.win1_used_cols;
+            P.accumulate = 1;
+            P.tail_lt = 0;
+            const int n_tiles = (t.win1_used_cols + 127) / 128;
+            P.n_ops = n_tiles;
+            for (int s2 = 0; s2 < n_tiles; ++s2) {
+                const int n = s2 == n_tiles - 1 ? t.win1_used_cols - 128 * s2 : 128;
+                P.op_a_off[s2] = 0u;
+                P.op_b_off[s2] = (uint32_t)(t.win1_s0 + s2);
+                P.op_idesc[s2] = tc::make_idesc_f16_mn(128, n);
+                P.op_taddr[s2] = (uint32_t)(128 * s2);
+            }
+            e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, false,
+                              t.smem_bytes, t.grid, ctx->stream);
+        }
     } else {
         AbcAcfParams P{};
         P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;

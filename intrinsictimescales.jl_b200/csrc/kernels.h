@@ -129,6 +129,10 @@ struct AbcTcGeometry {
     int n_ops;
     int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
+    // second lag window (n_lags 465 .. 769): the same kernel launched once more with the B operand a
+    // further win1_s0 = 3 rows down (plan-A tiles), accumulator column v <-> lag 128 win1_s0 + v - a;
+    // it scores the lags [449, n_lags) and adds its part of the distance to the first launch's
+    int n_windows, win1_s0, win1_used_cols;
     float tc_scale, tc_fix;
     int grid;
     size_t smem_bytes;
@@ -157,6 +161,9 @@ struct AbcTcParams {
     int ksteps, sbo_bytes;
     int used_cols, seg_trials, n_terms;
     int tc_lags, tail_start, tail_lt, tail_steps, tail_steps_per_stream;
+    int k_lo;                    // lag window of this launch: accumulator lags [k_lo, tc_lags) relative to lag_base
+    int lag_base;                // absolute lag of relative lag 0 (0, or 128 win1_s0 for the second window)
+    int accumulate;              // 1: add this window's share of the distance to dist_out (second window)
     int n_ops;
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];

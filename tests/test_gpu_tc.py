@@ -120,16 +120,26 @@ def _gpu_models(mk, ctx):
 
 # (n_t, n_trials, n_lags): tensor-memory plan A with 1..4 tiles, plan B (M = 64 split, 5th tile), several
 # accumulator segments (21 and 50 trials), fewer trials than groups, odd buffer counts, FFMA tail lags
-# (1, 2 and 4 lag tiles)
+# (one lag tile), two lag windows (n_lags 465 .. 769: second launch with the B operand 3 rows down)
 SHAPES = [(1000, 5, 37), (601, 3, 20), (2500, 1, 300), (5000, 2, 385), (5000, 2, 386), (5000, 4, 414),
           (5000, 21, 449), (5000, 3, 430), (3000, 50, 200), (5000, 50, 414), (5000, 7, 401),
-          (5000, 3, 463), (5000, 9, 470), (5000, 5, 509)]
+          (5000, 3, 463), (5000, 9, 470), (5000, 5, 509),
+          (5000, 5, 510), (5000, 3, 600), (5000, 12, 769), (3000, 4, 700)]
 
 
-@pytest.mark.parametrize("n_t,n_trials,n_lags", SHAPES)
-def test_tc_kernel_matches_oracle_and_cuda_core_kernel(pkg, ctx, n_t, n_trials, n_lags):
+# ITJL_TC_TAIL_MAX = 60: the two- and four-tile FFMA tails (no longer chosen by default: a second lag window is faster)
+@pytest.mark.parametrize("n_t,n_trials,n_lags,tail_max", [s + (None,) for s in SHAPES] + [(5000, 9, 470, 60), (5000, 5, 509, 60)])
+def test_tc_kernel_matches_oracle_and_cuda_core_kernel(pkg, ctx, n_t, n_trials, n_lags, tail_max):
     om, mk = _models(pkg, n_t, n_trials, n_lags)
-    g_tc, g_ff = _gpu_models(mk, ctx)
+    old = os.environ.pop("ITJL_TC_TAIL_MAX", None)
+    try:
+        if tail_max is not None:
+            os.environ["ITJL_TC_TAIL_MAX"] = str(tail_max)
+        g_tc, g_ff = _gpu_models(mk, ctx)
+    finally:
+        os.environ.pop("ITJL_TC_TAIL_MAX", None)
+        if old is not None:
+            os.environ["ITJL_TC_TAIL_MAX"] = old
     rng = np.random.default_rng(n_t + n_lags)
     theta = np.array([[0.3], [4.9], [0.05], [1.2]])
     P = theta.shape[0]
@@ -153,9 +163,10 @@ def test_tc_kernel_matches_oracle_and_cuda_core_kernel(pkg, ctx, n_t, n_trials, 
     assert np.array_equal(parts, a)                         # persistent-CTA scheduling does not leak into results
 
 
-def test_tc_kernel_missing_data_variant(pkg, ctx):
+@pytest.mark.parametrize("n_lags", [None, 600])          # default window; two lag windows
+def test_tc_kernel_missing_data_variant(pkg, ctx, n_lags):
     n_t, n_trials = 5000, 6
-    om, mk = _models(pkg, n_t, n_trials, None, missing=True)
+    om, mk = _models(pkg, n_t, n_trials, n_lags, missing=True)
     g_tc, g_ff = _gpu_models(mk, ctx)
     rng = np.random.default_rng(4)
     theta = np.array([[0.3], [2.0], [0.07]])
@@ -170,9 +181,8 @@ def test_tc_kernel_missing_data_variant(pkg, ctx):
 
 
 def test_unsupported_shapes_fall_back_to_cuda_core_kernel(pkg, ctx):
-    """n_lags beyond the tensor-memory plans + 60 tail lags: ITJL_ABC_TC unset picks k_abc_acf,
-    ITJL_ABC_TC=1 refuses."""
-    om, mk = _models(pkg, 2500, 1, 510)
+    """n_lags beyond two lag windows (769): ITJL_ABC_TC unset picks k_abc_acf, ITJL_ABC_TC=1 refuses."""
+    om, mk = _models(pkg, 2500, 1, 770)
     old = os.environ.pop("ITJL_ABC_TC", None)
     try:
         assert mk().gpu_model(ctx).kernel_info()[0] == "k_abc_acf"

@@ -124,7 +124,7 @@ def test_tensor_core_plan_selection_is_host_logic(pkg):
     import ctypes
     lib = pkg._lib.lib()
     names = ["groups", "chunk", "ksteps", "rows_total", "used_cols", "mixed", "seg_trials", "n_terms",
-             "tc_lags", "tail_start", "tail_lt", "n_ops", "smem_bytes", "grid"]
+             "tc_lags", "tail_start", "tail_lt", "n_ops", "smem_bytes", "grid", "n_windows"]
 
     def plan(n_t, n_lags, n_trials):
         out = (ctypes.c_int32 * 16)()
@@ -142,9 +142,15 @@ def test_tensor_core_plan_selection_is_host_logic(pkg):
     assert p["used_cols"] == 432 and p["n_ops"] == 4
     rc, p = plan(5000, 385, 8)                        # last shape of plan A: all 512 columns
     assert rc == 0 and p["mixed"] == 0 and p["used_cols"] == 512
-    rc, p = plan(5000, 509, 8)
-    assert rc == 0 and p["tail_lt"] == 4
-    assert plan(5000, 510, 8)[0] == -1                # longer windows: CUDA-core kernel
+    rc, p = plan(5000, 464, 8)                        # last shape with an FFMA tail (one tile of 16 lags)
+    assert rc == 0 and p["tail_lt"] == 1 and p["n_windows"] == 1
+    rc, p = plan(5000, 465, 8)                        # beyond: a second lag window is faster than more tail tiles
+    assert rc == 0 and p["tail_lt"] == 0 and p["n_windows"] == 2
+    rc, p = plan(5000, 510, 8)                        # two lag windows (second launch), no tail, rows for the deeper shift
+    assert rc == 0 and p["n_windows"] == 2 and p["tail_lt"] == 0 and p["tc_lags"] == 449
+    rc, p = plan(5000, 769, 50)
+    assert rc == 0 and p["n_windows"] == 2 and p["groups"] == 4 and p["rows_total"] >= 48 + 6   # B rows up to 47 + 3 + 3
+    assert plan(5000, 770, 8)[0] == -1                # longer windows: CUDA-core kernel
     rc, p = plan(10000, 430, 100)                     # longer trials: fewer simulate groups fit
     assert rc == 0 and 1 <= p["groups"] < 4 and p["ksteps"] == 5
     assert plan(8, 4, 2)[0] == -1 and plan(5000, 6000, 2)[0] == -1
