@@ -442,10 +442,11 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     // window, 2.3e11 / 1.7e11 with two / four tail tiles
     int max_tail = 15;
     { const char* e_t = getenv("ITJL_TC_TAIL_MAX"); if (e_t && atoi(e_t) >= 0 && atoi(e_t) <= 60) max_tail = atoi(e_t); }   // tuning only
-    // n_lags 465 .. 769: two launches (lag windows), the second with the B operand 3 rows further down
-    g->n_windows = n_lags > 449 + max_tail ? 2 : 1;
+    // n_lags 465 .. 1537: up to four launches (lag windows), each with the B operand 3 more rows down
+    // window w >= 1 moves the B operand 3 w rows down and covers the lags [384 w, 384 w + 385)
+    g->n_windows = n_lags > 449 + max_tail ? 1 + (n_lags - 385 + 383) / 384 : 1;
     g->win1_s0 = 3; g->win1_used_cols = 0;
-    if (n_lags > 128 * g->win1_s0 + 385) return -2;
+    if (g->n_windows > kTcMaxWindows) return -2;
     const int rows_data = (n_t + 127) / 128;
     g->ksteps = (rows_data + 15) / 16;
     int max_shift;
@@ -479,9 +480,11 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     }
     g->tc_lags = n_lags < 449 ? n_lags : 449;
     if (n_lags <= 385) g->tc_lags = n_lags;
-    if (g->n_windows == 2) {
-        g->win1_used_cols = (((n_lags - 128 * g->win1_s0) + 127) + 15) & ~15;      // <= 512
-        max_shift = g->win1_s0 + (g->win1_used_cols + 127) / 128 - 1;
+    if (g->n_windows >= 2) {
+        // accumulator columns of the LAST window (the ones before it use all 512)
+        const int base = 128 * g->win1_s0 * (g->n_windows - 1);
+        g->win1_used_cols = (((n_lags - base) + 127) + 15) & ~15;      // <= 512
+        max_shift = g->win1_s0 * (g->n_windows - 1) + (g->win1_used_cols + 127) / 128 - 1;
     }
     // FFMA tail: tiles of 16 lags from tail_start (a multiple of 8: 16-byte groups of the planes)
     g->tail_start = g->tc_lags & ~7;

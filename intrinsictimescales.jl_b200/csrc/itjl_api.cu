@@ -264,7 +264,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
         const double M = (double)(((id >> 24) & 0x1Fu) << 4), N = (double)(((id >> 17) & 0x3Fu) << 3);
         f += 2.0 * M * N * 16.0;
     }
-    if (m->tc.n_windows == 2) f += 2.0 * 128.0 * (double)m->tc.win1_used_cols * 16.0;
+    for (int w = 1; w < m->tc.n_windows; ++w) f += 2.0 * 128.0 * (w == m->tc.n_windows - 1 ? (double)m->tc.win1_used_cols : 512.0) * 16.0;
     *tensor_flops_per_sample = f * (double)m->tc.n_terms * m->tc.ksteps / (double)m->d.n_t;
     return ITJL_OK;
 }
@@ -333,21 +333,23 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.k_lo = 0; P.lag_base = 0; P.accumulate = 0;
         e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,
                           t.smem_bytes, t.grid, ctx->stream);
-        if (e == cudaSuccess && t.n_windows == 2) {
-            // second lag window: same trajectories (same Philox counters), B operand win1_s0 rows further
-            // down, plan-A tiles; scores the lags [449, n_lags) and adds its share of the distance
-            P.lag_base = 128 * t.win1_s0;
-            P.k_lo = t.tc_lags - P.lag_base;
-            P.tc_lags = (int)d.n_stats - P.lag_base;
-            P.used_cols = t.win1_used_cols;
+        for (int w = 1; w < t.n_windows && e == cudaSuccess; ++w) {
+            // further lag windows: same trajectories (same Philox counters), B operand 3 w rows further
+            // down, plan-A tiles; window w scores the lags from where window w - 1 stopped (449, then
+            // 384 w + 1) and adds its share of the distance
+            const int used = w == t.n_windows - 1 ? t.win1_used_cols : 512;
+            P.lag_base = 128 * t.win1_s0 * w;
+            P.k_lo = (w == 1 ? t.tc_lags : P.lag_base + 1) - P.lag_base;
+            P.tc_lags = std::min((int)d.n_stats - P.lag_base, 385);
+            P.used_cols = used;
             P.accumulate = 1;
             P.tail_lt = 0;
-            const int n_tiles = (t.win1_used_cols + 127) / 128;
+            const int n_tiles = (used + 127) / 128;
             P.n_ops = n_tiles;
             for (int s2 = 0; s2 < n_tiles; ++s2) {
-                const int n = s2 == n_tiles - 1 ? t.win1_used_cols - 128 * s2 : 128;
+                const int n = s2 == n_tiles - 1 ? used - 128 * s2 : 128;
                 P.op_a_off[s2] = 0u;
-                P.op_b_off[s2] = (uint32_t)(t.win1_s0 + s2);
+                P.op_b_off[s2] = (uint32_t)(t.win1_s0 * w + s2);
                 P.op_idesc[s2] = tc::make_idesc_f16_mn(128, n);
                 P.op_taddr[s2] = (uint32_t)(128 * s2);
             }

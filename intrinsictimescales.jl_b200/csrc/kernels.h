@@ -119,6 +119,7 @@ int acf_max_reach(int n_t, int max_smem);
 
 // ---- abc_tc_kernels.cu --------------------------------------------------------------
 constexpr int kTcMaxOps = 6;
+constexpr int kTcMaxWindows = 4;                   // lag windows (launches) of the tensor-core kernel: n_lags <= 1537
 struct AbcTcGeometry {
     int groups, chunk, epi_offset;
     int rows_total, ksteps, sbo_bytes;
@@ -129,10 +130,10 @@ struct AbcTcGeometry {
     int n_ops;
     int op_a_blk[kTcMaxOps], op_b_row[kTcMaxOps], op_b_blk[kTcMaxOps];
     uint32_t op_idesc[kTcMaxOps], op_taddr[kTcMaxOps];
-    // second lag window (n_lags 465 .. 769): the same kernel launched once more with the B operand a
-    // further win1_s0 = 3 rows down (plan-A tiles), accumulator column v <-> lag 128 win1_s0 + v - a;
-    // it scores the lags [449, n_lags) and adds its part of the distance to the first launch's
-    int n_windows, win1_s0, win1_used_cols;
+    // further lag windows (n_lags 465 .. 1537): the same kernel launched again, window w with the B operand
+    // win1_s0 w = 3 w rows further down (plan-A tiles), accumulator column v <-> lag 384 w + v - a; it scores
+    // the lags the windows before it have not (from 449, resp. 384 w + 1) and adds its part of the distance
+    int n_windows, win1_s0, win1_used_cols;      // win1_used_cols: accumulator columns of the last window
     float tc_scale, tc_fix;
     int grid;
     size_t smem_bytes;
@@ -162,7 +163,7 @@ struct AbcTcParams {
     int used_cols, seg_trials, n_terms;
     int tc_lags, tail_start, tail_lt, tail_steps, tail_steps_per_stream;
     int k_lo;                    // lag window of this launch: accumulator lags [k_lo, tc_lags) relative to lag_base
-    int lag_base;                // absolute lag of relative lag 0 (0, or 128 win1_s0 for the second window)
+    int lag_base;                // absolute lag of relative lag 0 (384 w for lag window w)
     int accumulate;              // 1: add this window's share of the distance to dist_out (second window)
     int n_ops;
     uint32_t op_a_off[kTcMaxOps], op_b_off[kTcMaxOps];      // descriptor start offsets, 16 B units

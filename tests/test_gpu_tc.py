@@ -120,11 +120,12 @@ def _gpu_models(mk, ctx):
 
 # (n_t, n_trials, n_lags): tensor-memory plan A with 1..4 tiles, plan B (M = 64 split, 5th tile), several
 # accumulator segments (21 and 50 trials), fewer trials than groups, odd buffer counts, FFMA tail lags
-# (one lag tile), two lag windows (n_lags 465 .. 769: second launch with the B operand 3 rows down)
+# (one lag tile), two to four lag windows (n_lags 465 .. 1537: further launches with the B operand 3 rows down each)
 SHAPES = [(1000, 5, 37), (601, 3, 20), (2500, 1, 300), (5000, 2, 385), (5000, 2, 386), (5000, 4, 414),
           (5000, 21, 449), (5000, 3, 430), (3000, 50, 200), (5000, 50, 414), (5000, 7, 401),
           (5000, 3, 463), (5000, 9, 470), (5000, 5, 509),
-          (5000, 5, 510), (5000, 3, 600), (5000, 12, 769), (3000, 4, 700)]
+          (5000, 5, 510), (5000, 3, 600), (5000, 12, 769), (3000, 4, 700),
+          (5000, 3, 1000), (5000, 2, 1537), (3000, 4, 1200)]
 
 
 # ITJL_TC_TAIL_MAX = 60: the two- and four-tile FFMA tails (no longer chosen by default: a second lag window is faster)
@@ -181,8 +182,8 @@ def test_tc_kernel_missing_data_variant(pkg, ctx, n_lags):
 
 
 def test_unsupported_shapes_fall_back_to_cuda_core_kernel(pkg, ctx):
-    """n_lags beyond two lag windows (769): ITJL_ABC_TC unset picks k_abc_acf, ITJL_ABC_TC=1 refuses."""
-    om, mk = _models(pkg, 2500, 1, 770)
+    """n_lags beyond four lag windows (1537): ITJL_ABC_TC unset picks k_abc_acf, ITJL_ABC_TC=1 refuses."""
+    om, mk = _models(pkg, 2500, 1, 1538)
     old = os.environ.pop("ITJL_ABC_TC", None)
     try:
         assert mk().gpu_model(ctx).kernel_info()[0] == "k_abc_acf"

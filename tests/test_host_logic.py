@@ -150,7 +150,10 @@ def test_tensor_core_plan_selection_is_host_logic(pkg):
     assert rc == 0 and p["n_windows"] == 2 and p["tail_lt"] == 0 and p["tc_lags"] == 449
     rc, p = plan(5000, 769, 50)
     assert rc == 0 and p["n_windows"] == 2 and p["groups"] == 4 and p["rows_total"] >= 48 + 6   # B rows up to 47 + 3 + 3
-    assert plan(5000, 770, 8)[0] == -1                # longer windows: CUDA-core kernel
+    rc, p = plan(5000, 1153, 8)                       # three windows need 57 rows: only three simulate groups fit
+    assert rc == 0 and p["n_windows"] == 3 and p["groups"] == 3 and p["rows_total"] >= 48 + 9
+    assert plan(5000, 1537, 8)[1]["n_windows"] == 4
+    assert plan(5000, 1538, 8)[0] == -1               # longer windows: CUDA-core kernel
     rc, p = plan(10000, 430, 100)                     # longer trials: fewer simulate groups fit
     assert rc == 0 and 1 <= p["groups"] < 4 and p["ksteps"] == 5
     assert plan(8, 4, 2)[0] == -1 and plan(5000, 6000, 2)[0] == -1
