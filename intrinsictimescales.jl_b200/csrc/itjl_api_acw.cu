@@ -10,10 +10,20 @@
 using namespace itjl;
 
 // Host -> device upload of the caller's (pageable) matrix.  Large inputs go through a ring of three
-// pinned 16 MB staging buffers: four host threads copy chunk c into a buffer while the DMA engine is
+// pinned 16 MB staging buffers: copy_threads() host threads copy chunk c into a buffer while the DMA engine is
 // still draining chunk c - 1 (a plain cudaMemcpy from pageable memory runs at ~11 GB/s on this box,
 // the staged pipeline at ~25-30 GB/s; C2's 400 MB: 36 ms -> ~15 ms).
 static const size_t kPinChunk = (size_t)16 << 20;
+// host threads that copy between the caller's pageable array and the pinned staging ring
+// (ITJL_COPY_THREADS, default: half the hardware threads, at most 8)
+constexpr int kMaxCopyThreads = 16;
+static int copy_threads() {
+    const char* e = getenv("ITJL_COPY_THREADS");
+    int n = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);
+    if (!e && n > 8) n = 8;
+    return n < 1 ? 1 : (n > kMaxCopyThreads ? kMaxCopyThreads : n);
+}
+
 static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t) {
     const size_t bytes = (size_t)n_slices * n_t * sizeof(double);
     ITJL_CUDA(ctx, ctx->data.reserve(bytes));
@@ -28,7 +38,7 @@ static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int6
     }
     const char* src = reinterpret_cast<const char*>(data);
     char* dst = reinterpret_cast<char*>(ctx->data.p);
-    const int n_threads = 4;
+    const int n_threads = copy_threads();
     size_t off = 0;
     for (int c = 0; off < bytes; ++c, off += kPinChunk) {
         const int b = c % 3;
@@ -36,7 +46,7 @@ static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int6
         if (c >= 3) ITJL_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[b]));       // the DMA out of this buffer is done
         char* stage = reinterpret_cast<char*>(ctx->pin[b]);
         const size_t part = ((n / n_threads) + 4095) & ~(size_t)4095;
-        std::thread workers[n_threads - 1];
+        std::thread workers[kMaxCopyThreads];
         for (int t = 1; t < n_threads; ++t) {
             const size_t lo = (size_t)t * part < n ? (size_t)t * part : n;
             const size_t hi = (size_t)(t + 1) * part < n ? (size_t)(t + 1) * part : n;
@@ -51,7 +61,7 @@ static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int6
 }
 
 // Device -> host download of a large result (the exported ACF matrix) through the same pinned ring:
-// DMA of chunk c + 1 runs while four host threads copy chunk c out to the caller's pageable array.
+// DMA of chunk c + 1 runs while the host threads copy chunk c out to the caller's pageable array.
 static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
     const char* e_pin = getenv("ITJL_PINNED_UPLOAD");
     if (bytes < 4 * kPinChunk || (e_pin && atoi(e_pin) == 0)) {
@@ -72,14 +82,14 @@ static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, si
         return e != cudaSuccess ? e : cudaEventRecord(ctx->pin_ev[c % 3], ctx->stream);
     };
     for (size_t c = 0; c < 2 && c < n_chunks; ++c) ITJL_CUDA(ctx, issue(c));
-    const int n_threads = 4;
+    const int n_threads = copy_threads();
     for (size_t c = 0; c < n_chunks; ++c) {
         if (c + 2 < n_chunks) ITJL_CUDA(ctx, issue(c + 2));      // buffer (c + 2) % 3 was emptied at chunk c - 1
         ITJL_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[c % 3]));
         const char* stage = reinterpret_cast<const char*>(ctx->pin[c % 3]);
         const size_t n = chunk_len(c), off = c * kPinChunk;
         const size_t part = ((n / n_threads) + 4095) & ~(size_t)4095;
-        std::thread workers[n_threads - 1];
+        std::thread workers[kMaxCopyThreads];
         for (int t = 1; t < n_threads; ++t) {
             const size_t lo = (size_t)t * part < n ? (size_t)t * part : n;
             const size_t hi = (size_t)(t + 1) * part < n ? (size_t)(t + 1) * part : n;
