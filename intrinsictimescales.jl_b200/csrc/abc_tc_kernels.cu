@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
 }
 
 // Bank conflicts (excess 128-byte wavefronts) of the simulate groups' 16-byte operand accesses for a
-// given MN-block stride: thread tid touches sample tid * chunk + q.
+// given MN-block stride: lane l of quarter `quarter` of warp w owns chunk 16 (l % 8) + 4 w + quarter
+// (simulate.cuh) and touches sample chunk_idx * chunk + q.  (Zero for 40-sample chunks whatever the stride.)
 static int tc_store_conflicts(int sbo_bytes, int chunk) {
     int excess = 0;
     for (int q = 0; q < chunk; q += 8) {
@@ -421,7 +422,7 @@ static int tc_store_conflicts(int sbo_bytes, int chunk) {
             for (int quarter = 0; quarter < 4; ++quarter) {           // 8 lanes x 16 B per wavefront
                 int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (int l = 0; l < 8; ++l) {
-                    const int j = (w * 32 + quarter * 8 + l) * chunk + q;
+                    const int j = (16 * l + 4 * w + quarter) * chunk + q;
                     const int off = ((j & 127) >> 3) * sbo_bytes + (j >> 7) * 16;
                     used[(off >> 4) & 7]++;
                 }

@@ -54,8 +54,8 @@ __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int up
 
 template <int NT>
 struct SimShared {
-    float scanA[NT / 32];
-    float scanB[NT / 32];
+    float scanA[NT / 32 < 32 ? 32 : NT / 32];      // (32 entries: the tensor-core sink scans 8 x 4 blocks)
+    float scanB[NT / 32 < 32 ? 32 : NT / 32];
     double sums[NT / 32][4];
 };
 
@@ -125,7 +125,13 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                                                const TcSink* sink = nullptr) {
     constexpr int NW = NT / 32;
     const int lane = tid & 31, warp = tid >> 5;
-    const int j0 = tid * g.chunk;
+    // Chunk owned by this thread.  Plain: chunk = tid.  Tensor-core sink (NT = 128): chunk = 16 m + 4 warp + qt
+    // with m = lane % 8, qt = lane / 8 - the eight lanes of a quarter warp then own chunks 16 apart, whose
+    // operand slots (five per 40-sample chunk) fall into the SAME 8-sample block 80 slots = 5 K rows apart:
+    // eight different 16-byte bank groups, so every 128-bit plane access is conflict free (chunk = tid is a
+    // 2-way conflict whatever the row count).
+    const int chunk_idx = TC ? 16 * (lane & 7) + 4 * warp + (lane >> 3) : tid;
+    const int j0 = chunk_idx * g.chunk;
     const float eps = oc.eps, s = oc.s;
 
     // per-trial initial state and phase (stream 1, block 0)
@@ -241,19 +247,47 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
 
     // ---- scan of the chunk-end affine maps x -> A x + B ----------------------------
     float A = p, B = y;
+    float c;                                         // carry into this chunk
+    if (!TC) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float Ap = __shfl_up_sync(0xffffffffu, A, d);
-        const float Bp = __shfl_up_sync(0xffffffffu, B, d);
-        if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
+        for (int d = 1; d < 32; d <<= 1) {
+            const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+            const float Bp = __shfl_up_sync(0xffffffffu, B, d);
+            if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
+        }
+        if (lane == 31) { sh->scanA[warp] = A; sh->scanB[warp] = B; }
+        sim_sync(bar_id, NT);
+        float xw = x0;                                   // state entering this warp's first chunk
+        for (int w = 0; w < warp; ++w) xw = fmaf(sh->scanA[w], xw, sh->scanB[w]);
+        const float Aprev = __shfl_up_sync(0xffffffffu, A, 1);
+        const float Bprev = __shfl_up_sync(0xffffffffu, B, 1);
+        c = (lane == 0) ? xw : fmaf(Aprev, xw, Bprev);
+    } else {
+        // chunk order = (m, warp, qt): scan the four quarters of this warp for each m (lanes m, m + 8, m + 16,
+        // m + 24), publish the 8 x 4 block maps in chunk order, and let every warp scan that 32-entry table
+#pragma unroll
+        for (int d = 8; d < 32; d <<= 1) {
+            const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+            const float Bp = __shfl_up_sync(0xffffffffu, B, d);
+            if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
+        }
+        if (lane >= 24) { sh->scanA[4 * (lane - 24) + warp] = A; sh->scanB[4 * (lane - 24) + warp] = B; }
+        sim_sync(bar_id, NT);
+        float TA = sh->scanA[lane], TB = sh->scanB[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float Ap = __shfl_up_sync(0xffffffffu, TA, d);
+            const float Bp = __shfl_up_sync(0xffffffffu, TB, d);
+            if (lane >= d) { TB = fmaf(TA, Bp, TB); TA *= Ap; }
+        }
+        const int e = 4 * (lane & 7) + warp;             // my block; state entering it = blocks 0 .. e - 1 applied to x0
+        const float PA = __shfl_sync(0xffffffffu, TA, (e + 31) & 31);
+        const float PB = __shfl_sync(0xffffffffu, TB, (e + 31) & 31);
+        const float xw = (e == 0) ? x0 : fmaf(PA, x0, PB);
+        const float Aprev = __shfl_up_sync(0xffffffffu, A, 8);
+        const float Bprev = __shfl_up_sync(0xffffffffu, B, 8);
+        c = (lane < 8) ? xw : fmaf(Aprev, xw, Bprev);
     }
-    if (lane == 31) { sh->scanA[warp] = A; sh->scanB[warp] = B; }
-    sim_sync(bar_id, NT);
-    float xw = x0;                                   // state entering this warp's first chunk
-    for (int w = 0; w < warp; ++w) xw = fmaf(sh->scanA[w], xw, sh->scanB[w]);
-    const float Aprev = __shfl_up_sync(0xffffffffu, A, 1);
-    const float Bprev = __shfl_up_sync(0xffffffffu, B, 1);
-    const float c = (lane == 0) ? xw : fmaf(Aprev, xw, Bprev);   // carry into this chunk
 
     // ---- mean / sum of squares from the partial sums --------------------------------
     double r0 = (double)fmaf(c, Sp, Sy);
