@@ -182,7 +182,7 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
             if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { delete m; return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
         m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
         if ((int64_t)m->psd_smem > ctx->max_smem_optin) { delete m; return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
-        std::vector<float> win((size_t)d.n_t);
+        std::vector<float> win((size_t)d.n_t + 1, 0.0f);          // +1: the kernel reads the window as float2 pairs
         std::vector<float2> tw((size_t)m->n2 / 2);
         double win_ss = 0.0;
         psd_make_tables((int)d.n_t, m->n2, win.data(), tw.data(), &win_ss);

@@ -254,16 +254,18 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const __grid_constan
         __syncthreads();
         // window, pack z[m] = x[2m] + i x[2m+1] into the padded FFT buffer, zero-pad to N points
         // (xs holds zeros from n_t to chunk * NT)
-#pragma unroll 4
-        for (int m = tid; m < N; m += NT) {
-            float2 z = make_float2(0.f, 0.f);
-            if (2 * m < P.n_t) {
-                const float2 v = *reinterpret_cast<const float2*>(xs + 2 * m);
-                z.x = v.x * __ldg(P.window + 2 * m);
-                if (2 * m + 1 < P.n_t) z.y = v.y * __ldg(P.window + 2 * m + 1);
-            }
-            buf[fft_pad(m)] = z;
+        // data part (window loads from L2, several in flight), then the zero padding (stores only)
+        const int m_data = (P.n_t + 1) >> 1;
+#pragma unroll 5
+        for (int m = tid; m < m_data; m += NT) {
+            const float2 v = *reinterpret_cast<const float2*>(xs + 2 * m);
+            const float2 w = __ldg(reinterpret_cast<const float2*>(P.window) + m);   // window is padded to an even length
+            buf[fft_pad(m)] = make_float2(v.x * w.x, (2 * m + 1 < P.n_t) ? v.y * w.y : 0.f);
         }
+        const int m_zero = ((m_data + NT - 1) / NT) * NT;     // first multiple of NT at or above m_data
+#pragma unroll 4
+        for (int m = m_zero + tid - NT; m < N; m += NT)
+            if (m >= m_data) buf[fft_pad(m)] = make_float2(0.f, 0.f);
         __syncthreads();
         fft_inplace_dif<NT>(buf, N, tw);
         for (int b = tid; b < P.n_stats; b += NT)
