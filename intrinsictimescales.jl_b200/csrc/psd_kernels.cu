@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const __grid_constan
             if (m >= m_data) buf[fft_pad(m)] = make_float2(0.f, 0.f);
         __syncthreads();
         fft_inplace_dif<NT>(buf, N, tw);
+        // bin table rows come from L2 (16 B each, 100 KB per trial): four in flight
+#pragma unroll 4
         for (int b = tid; b < P.n_stats; b += NT)
             accb[b] += real_fft_power_at(buf, __ldg(P.binpos + b));
         __syncthreads();
