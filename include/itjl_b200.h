@@ -133,7 +133,8 @@ int itjl_model_kernel_info(const itjl_model* model, char* name_out, double* tens
 /* Host-only (no GPU needed): the tensor-memory plan k_abc_acf_tc would use for a model shape on a device
  * with `max_smem_optin` bytes of opt-in shared memory per CTA and `sm_count` SMs (B200: 232448, 148).
  * Returns ITJL_OK and fills out[0..15] = {groups, chunk, ksteps, rows_total, used_cols, mixed (plan B),
- * seg_trials, n_terms, tc_lags, tail_start, tail_lt, n_ops, smem_bytes, grid, 0, 0}, or ITJL_ERR_ARG when
+ * seg_trials, n_terms, tc_lags, tail_start, tail_lt, n_ops, smem_bytes, grid, n_windows (kernel launches
+ * per batch: lag windows of 385 lags beyond the first 449), 0}, or ITJL_ERR_ARG when
  * the shape is outside the kernel's plans (the CUDA-core kernel k_abc_acf then runs). */
 int itjl_tc_plan(int64_t n_t, int64_t n_lags, int64_t n_trials, int32_t max_smem_optin, int32_t sm_count, int32_t* out);
 
