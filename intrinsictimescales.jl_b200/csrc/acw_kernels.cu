@@ -741,18 +741,32 @@ int acw_stream_lags() { return SK; }
 // fp32 partials, counted in doubles for the caller's reserve()
 size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return ((size_t)n_seg * SPART * (size_t)n_slices + 1) / 2; }
 void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len) {
-    // ~2 x 512 resident threads per SM; segments are multiples of 32 samples and at least 256 long
-    // (each one re-reads a 32-sample halo and writes 33 partial sums per slice)
+    // The grid is (blocks of 128 slices) x (time segments); 4 CTAs of 128 threads are resident per SM
+    // (128 registers per thread).  Pick the segment count whose grid fills whole waves of those slots:
+    // cost = waves x (segment length + 32-sample halo); segments are multiples of 32 samples and at least
+    // 256 long (each one also writes 33 partial sums per slice).  C2 (10 000 x 5000): 7 segments of 736
+    // samples, 553 of 592 slots, one wave (16 segments were 2.13 waves, i.e. three rounds).
     const char* e_w = getenv("ITJL_ACW_WAVES");
-    const int waves = (e_w && atoi(e_w) > 0) ? atoi(e_w) : 2;
-    int g = (int)(((long long)waves * 512 * sm_count + n_slices - 1) / n_slices);
+    const int force_waves = (e_w && atoi(e_w) > 0) ? atoi(e_w) : 0;
+    const long long slots = 4LL * sm_count;
+    const long long blocks = (n_slices + 127) / 128;
     const int max_g = n_t / 256 > 0 ? n_t / 256 : 1;
-    if (g > max_g) g = max_g;
-    if (g < 1) g = 1;
-    int len = (n_t + g - 1) / g;
-    len = ((len + SK - 1) / SK) * SK;
-    *seg_len = len;
-    *n_seg = (n_t + len - 1) / len;
+    long long best_cost = -1;
+    int best_len = ((n_t + SK - 1) / SK) * SK;
+    for (int waves = 1; waves <= 4; ++waves) {
+        if (force_waves && waves != force_waves) continue;
+        long long g = waves * slots / blocks;
+        if (g < 1) g = 1;
+        if (g > max_g) g = max_g;
+        int len = (int)((n_t + g - 1) / g);
+        len = ((len + SK - 1) / SK) * SK;
+        const long long segs = (n_t + len - 1) / len;
+        const long long rounds = (segs * blocks + slots - 1) / slots;
+        const long long cost = rounds * (len + SK);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_len = len; }
+    }
+    *seg_len = best_len;
+    *n_seg = (n_t + best_len - 1) / best_len;
 }
 
 cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int missing, int max_lags,
