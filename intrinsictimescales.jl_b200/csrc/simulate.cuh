@@ -57,6 +57,7 @@ struct SimShared {
     float scanA[NT / 32 < 32 ? 32 : NT / 32];      // (32 entries: the tensor-core sink scans 8 x 4 blocks)
     float scanB[NT / 32 < 32 ? 32 : NT / 32];
     double sums[NT / 32][4];
+    float x0;                                      // the trial's initial state, drawn by warp 0 (plain OU model)
 };
 
 enum : int { kScaleUnitNorm = 0, kScaleStd = 1, kScaleRaw = 2 };
@@ -135,9 +136,11 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     const float eps = oc.eps, s = oc.s;
 
     // per-trial initial state and phase (stream 1, block 0)
-    float x0;
-    double phase_turns;
-    {
+    // (plain OU model: only warp 0 draws it and hands it over through shared memory - it is first needed
+    // after the scan's barrier; the oscillation model needs the phase in pass A, every thread draws)
+    float x0 = 0.f;
+    double phase_turns = 0.0;
+    if (OSC || warp == 0) {
         uint32_t r[4];
         philox4x32_10(0u, (uint32_t)trial, g.particle, g.c3_init, *g.keys, r);
         float z1;
@@ -145,6 +148,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         phase_turns = (double)u01(r[2]);
         if (g.u0) x0 = (float)g.u0[trial];
         if (OSC && g.phases) phase_turns = g.phases[trial] * 0.15915494309189535;
+        if (!OSC && lane == 0) sh->x0 = x0;
     }
 
     // ---- pass A: local recurrence from a zero state + partial sums -----------------
@@ -257,6 +261,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         }
         if (lane == 31) { sh->scanA[warp] = A; sh->scanB[warp] = B; }
         sim_sync(bar_id, NT);
+        if (!OSC) x0 = sh->x0;
         float xw = x0;                                   // state entering this warp's first chunk
         for (int w = 0; w < warp; ++w) xw = fmaf(sh->scanA[w], xw, sh->scanB[w]);
         const float Aprev = __shfl_up_sync(0xffffffffu, A, 1);
@@ -273,6 +278,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         }
         if (lane >= 24) { sh->scanA[4 * (lane - 24) + warp] = A; sh->scanB[4 * (lane - 24) + warp] = B; }
         sim_sync(bar_id, NT);
+        if (!OSC) x0 = sh->x0;
         float TA = sh->scanA[lane], TB = sh->scanB[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
