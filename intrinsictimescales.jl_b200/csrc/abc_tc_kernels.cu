@@ -384,9 +384,10 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                     for (int gg = 0; gg < G; ++gg)
                         for (int w = 0; w < 4; ++w) sk += tailred[gg][w][k - P.tail_start];
                 }
-                const double v = __dmul_rn((double)(sk * P.tc_unscale), inv_trials);   // no FMA contraction with the
+                double v = __dmul_rn((double)(sk * P.tc_unscale), inv_trials);         // no FMA contraction with the
                                                                                       // subtraction below: same bits with and without stats_out
                 const int ka = P.lag_base + k;
+                if (ka == 0 && isfinite(v)) v = 1.0;              // ac[0] = acov[0] / acov[0] is exactly 1 in the reference (summary.jl:58, 479)
                 if (P.stats_out) P.stats_out[(size_t)particle * P.n_lags + ka] = v;
                 const double tgt = (double)P.target[ka];
                 const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
