@@ -52,10 +52,15 @@ def model_arrays(model):
     keep = {}
     keep["target"] = np.ascontiguousarray(model.data_sum_stats, dtype=np.float64)
     d = ModelDesc()
-    d.kind = 1 if model.kind == "one_timescale_and_osc" else 0
+    if model.kind not in ("one_timescale", "one_timescale_with_missing", "one_timescale_and_osc",
+                          "one_timescale_and_osc_with_missing") or getattr(model, "distance_combined", False):
+        raise ValueError(f"the C restatement does not cover model kind {model.kind!r} / distance_combined")
+    d.kind = 1 if model.kind in ("one_timescale_and_osc", "one_timescale_and_osc_with_missing") else 0
     if model.summary_method == "psd":
+        if model.kind.endswith("with_missing"):
+            raise ValueError("the C restatement has no Lomb-Scargle PSD")
         d.summary = SUMMARY["psd"]
-    elif model.kind == "one_timescale_with_missing":
+    elif model.kind.endswith("with_missing"):
         d.summary = SUMMARY["acf_missing"]
     else:
         d.summary = SUMMARY["acf"]

@@ -76,3 +76,21 @@ def test_statistics_output_matches_numpy_oracle():
             assert np.allclose(s[i], ref, rtol=0, atol=1e-12)
             assert np.isclose(d[i], np.mean((ref - m.data_sum_stats) ** 2), rtol=1e-10)
         assert np.array_equal(d, cport.abc_distances(m, th, seed=8, generation=2), equal_nan=True)
+
+
+def test_osc_with_missing_matches_numpy_oracle_and_uncovered_models_are_refused():
+    n = 1600
+    data = ou.generate_ou_with_oscillation([0.05, 10.0, 0.9], DT, _time(n)[-1], 4, 0.5, 2.0, seed=17, n_t=n)
+    for r in range(4):
+        data[r, 90 * r + 40:90 * r + 200] = np.nan
+    prior = [models.Normal(.1, .1), models.Normal(10, 5), models.Uniform(0, 1)]
+    m = models.one_timescale_and_osc_with_missing_model(data, _time(n), prior=prior)
+    th = np.array([[0.05, 10, 0.9], [0.1, 12, 0.5], [0.02, 8, 1.2]])
+    dc, sc = cport.abc_distances(m, th, seed=4, generation=2, return_stats=True)
+    for i, x in enumerate(th):
+        ref = models.summary_stats(m, models.generate_data(m, x, seed=4, generation=2, particle=i))
+        assert np.allclose(sc[i], ref, rtol=0, atol=1e-12)
+        assert np.isclose(dc[i], models.generate_data_and_reduce(m, x, seed=4, generation=2, particle=i), rtol=1e-9)
+    plain = models.one_timescale_model(np.nan_to_num(data), _time(n), prior=[models.Uniform(0.05, 5)])
+    with pytest.raises(ValueError):
+        cport.abc_distances(models.with_combined_distance(plain), np.array([[0.3]]))
