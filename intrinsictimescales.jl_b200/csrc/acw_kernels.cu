@@ -92,9 +92,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_acf_slices(const AcfSliceParams
 
     int start = 0, stop = P.max_lags;
     if (P.mode == 1) {
-        start = P.n_done[s];
+        // resume on a whole lag tile: a previous fill may have stopped at any lag count (the caller's n_lags),
+        // and the tile loop reads the series with 16-byte loads at lag offsets that must stay even
+        start = (P.n_done[s] / TKD) * TKD;
         stop = P.need;
-        if (start >= stop) return;                // uniform per CTA
+        if (P.n_done[s] >= stop) return;          // uniform per CTA
     }
 
     // ---- load + centre -------------------------------------------------------------
@@ -783,9 +785,9 @@ cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int m
 
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
                             double* acf_work, int64_t cap, int32_t* n_done, const int32_t* slice_list,
-                            int64_t n_list, int max_smem, cudaStream_t st) {
+                            int64_t n_list, int max_smem, cudaStream_t st, int32_t* nan_flag) {
     AcfSliceParams P{};
-    P.slice_list = slice_list;
+    P.slice_list = slice_list; P.nan_flag = nan_flag;
     P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.missing = missing; P.mode = 1;
     P.max_lags = need; P.need = need; P.acf_work = acf_work; P.cap = cap; P.n_done = n_done;
     return launch_slices(P, need, max_smem, slice_list ? n_list : n_slices, st);

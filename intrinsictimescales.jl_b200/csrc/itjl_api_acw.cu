@@ -110,13 +110,14 @@ static int check_data_args(itjl_ctx* ctx, const double* data, int64_t n_slices, 
 }
 
 // Device-side ACF of every slice up to n_lags into ctx->out (row-per-slice, ld = cap).
-static int acf_all(itjl_ctx* ctx, int64_t n_slices, int n_t, int n_lags, int missing, int64_t cap, bool reset) {
+static int acf_all(itjl_ctx* ctx, int64_t n_slices, int n_t, int n_lags, int missing, int64_t cap, bool reset,
+                   int32_t* nan_flag = nullptr) {
     ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
     ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 6 + 4) * sizeof(int32_t)));
     int32_t* n_done = (int32_t*)ctx->flags.p;
     if (reset) ITJL_CUDA(ctx, cudaMemsetAsync(n_done, 0, (size_t)n_slices * sizeof(int32_t), ctx->stream));
     cudaError_t e = acf_fill_launch((const double*)ctx->data.p, n_slices, n_t, missing, n_lags,
-                                    (double*)ctx->out.p, cap, n_done, nullptr, 0, ctx->max_smem_optin, ctx->stream);
+                                    (double*)ctx->out.p, cap, n_done, nullptr, 0, ctx->max_smem_optin, ctx->stream, nan_flag);
     if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
     ctx->launches++;
     return ITJL_OK;
@@ -254,6 +255,7 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     int64_t cap = 0;
     bool all_streamed = false;       // every slice holds the streaming pass's 32 lags
     int64_t n_redo = 0;              // slices redone by the fp64 kernel (their indices stay in d_list)
+    int32_t has_nan = 0;             // some slice has a NaN (the reference then takes comp_ac_time_missing)
     cudaError_t e;
 
     if (!average_over_trials) {
@@ -309,7 +311,6 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
         ITJL_CUDA(ctx, cudaMemcpyAsync(h_k0.data(), d_k0, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
         ITJL_CUDA(ctx, cudaMemcpyAsync(h_k50.data(), d_k50, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
         ITJL_CUDA(ctx, cudaMemcpyAsync(h_ke.data(), d_ke, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        int32_t has_nan = 0;
         ITJL_CUDA(ctx, cudaMemcpyAsync(&has_nan, d_nan, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (has_nan && user_lags > 0) {
@@ -327,10 +328,12 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
         int L = (int)(user_lags > 0 ? user_lags : 64);
         if (L > reach) L = reach;
         bool first = true;
+        ITJL_CUDA(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int32_t), ctx->stream));
         for (;;) {
             cap = reach;
-            rc = acf_all(ctx, n_slices, nt, L, 1, cap, first);
+            rc = acf_all(ctx, n_slices, nt, L, 1, cap, first, first ? d_nan : nullptr);
             if (rc != ITJL_OK) return rc;
+            if (first) ITJL_CUDA(ctx, cudaMemcpyAsync(&has_nan, d_nan, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             first = false;
             ITJL_CUDA(ctx, ctx->out2.reserve((size_t)reach * sizeof(double)));
             e = acf_mean_launch((const double*)ctx->out.p, n_slices, cap, L, (double*)ctx->out2.p, ctx->stream);
@@ -344,6 +347,9 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
             ITJL_CUDA(ctx, cudaMemcpyAsync(h_ke.data(), d_ke, 4, cudaMemcpyDeviceToHost, ctx->stream));
             ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (h_k0[0] >= 0 || L >= reach) break;
+            // NaN data + user n_lags: the reference only computes n_lags lags (acw.jl:151-152), a later
+            // crossing of the mean ACF does not exist for it
+            if (has_nan && user_lags > 0) break;
             L = (L * 4 > reach) ? reach : L * 4;
         }
         lags_avail = L;
@@ -361,21 +367,25 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     if (n_lags > reach) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags exceeds the shared-memory reach for this n_t");
     *n_lags_io = n_lags;
 
-    // make sure every row holds n_lags lags
+    // make sure every row holds n_lags lags - and, for the AUC of complete data, the first slice's whole
+    // window: the reference integrates acf[0 : acw0) of the full-length comp_ac_fft ACF before it cuts the
+    // rows to n_lags (acw.jl:194-213); with NaNs it only ever has n_lags lags
+    int64_t fill_lags = n_lags;
+    if ((typemask & ITJL_AUC) && !has_nan && h_k0[0] > fill_lags) fill_lags = h_k0[0];
     if (!average_over_trials) {
-        if (!(all_streamed && n_lags <= acw_stream_lags())) {
+        if (!(all_streamed && fill_lags <= acw_stream_lags())) {
             // streamed slices already hold 32 lags: when that is enough only the redone ones need filling
-            const bool only_list = n_redo > 0 && n_lags <= acw_stream_lags();
-            e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)n_lags, (double*)ctx->out.p, cap,
+            const bool only_list = n_redo > 0 && fill_lags <= acw_stream_lags();
+            e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)fill_lags, (double*)ctx->out.p, cap,
                                 d_done, only_list ? d_list : nullptr, only_list ? n_redo : 0,
                                 ctx->max_smem_optin, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_slices(fill): %s", cudaGetErrorString(e));
             ctx->launches++;
         }
-    } else if (n_lags > lags_avail) {
-        rc = acf_all(ctx, n_slices, nt, (int)n_lags, 1, cap, false);
+    } else if (fill_lags > lags_avail) {
+        rc = acf_all(ctx, n_slices, nt, (int)fill_lags, 1, cap, false);
         if (rc != ITJL_OK) return rc;
-        e = acf_mean_launch((const double*)ctx->out.p, n_slices, cap, (int)n_lags, (double*)ctx->out2.p, ctx->stream);
+        e = acf_mean_launch((const double*)ctx->out.p, n_slices, cap, (int)fill_lags, (double*)ctx->out2.p, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_mean: %s", cudaGetErrorString(e));
         ctx->launches++;
     }
@@ -392,7 +402,7 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     if (typemask & ITJL_AUC) {
         // window = floor(Int, acw0_sample[1]) of the FIRST slice (acw.jl:194)
         const int w = h_k0[0];
-        if (w < 2 || w > n_lags) {
+        if (w < 2 || w > fill_lags) {
             for (int64_t i = 0; i < n_out; ++i) auc[i] = NAN;    // reference throws here
         } else {
             prime_strides(w, strides);

@@ -104,7 +104,7 @@ size_t acw_stream_part_doubles(int64_t n_slices, int n_seg);
 void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len);
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
                             double* acf_work, int64_t cap, int32_t* n_done, const int32_t* slice_list,
-                            int64_t n_list, int max_smem, cudaStream_t st);
+                            int64_t n_list, int max_smem, cudaStream_t st, int32_t* nan_flag = nullptr);
 cudaError_t acf_cross_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, int32_t* k0,
                              int32_t* k50, int32_t* ke, cudaStream_t st);
 cudaError_t acf_mean_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double* out,

@@ -87,6 +87,28 @@ def test_acw_with_nans_user_lags_vector_and_average(pkg, ctx):
     assert one.acwtypes == "acw50" and np.asarray(one.acw_results).shape == (20,)
 
 
+def test_acw_user_lags_shorter_than_the_zero_crossing(pkg, ctx):
+    """Found by benchmarks/acw_fuzz.py.  Long-memory data whose mean ACF has not crossed zero within the
+    user's n_lags: (1) average_over_trials used to resume the lag fill at an odd lag count (misaligned
+    16-byte loads: the call failed); (2) with NaNs the reference only ever sees n_lags lags, so there is no
+    crossing (NaN), while complete data are searched over all lags; (3) the AUC of complete data integrates
+    the first slice's whole window even when it is longer than n_lags."""
+    rng = np.random.default_rng(5)
+    d = np.cumsum(rng.standard_normal((40, 3730)), axis=1) * 0.05 + rng.standard_normal((40, 3730))
+    dn = d.copy()
+    for r in range(0, 40, 2):
+        dn[r, 100 * r:100 * r + 400] = np.nan
+    types = ["acw0", "acw50", "acweuler", "tau"]
+    for data in (d, dn):
+        for n_lags in (455, 100, 33):
+            check_against_oracle(pkg, ctx, data, 100.0, types=types, n_lags=n_lags, average=True, tau_rtol=1e-4)
+            check_against_oracle(pkg, ctx, data, 100.0, types=types, n_lags=n_lags, tau_rtol=1e-4)
+    k0 = oacw.acw(d, 100.0, acwtypes=["acw0"])["k0"]
+    assert k0[0] > 40
+    got, want = check_against_oracle(pkg, ctx, d, 100.0, n_lags=40, tau_rtol=1e-4)      # AUC window > n_lags
+    assert np.all(np.isfinite(dict(zip(TYPES, got.acw_results))["auc"]))
+
+
 def test_acw_edge_cases(pkg, ctx):
     # never crosses zero -> NaN + n_lags = n (acw.jl:203-207); AUC then throws like the reference
     t = np.arange(600, dtype=np.float64)
