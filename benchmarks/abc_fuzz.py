@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""basic_abc (batched, GPU) against the reference's serial loop on oracle distances for random epsilon /
+max_iter / min_accepted and NaN-producing proposals - diagnostic."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge
+from oracle import abc as oabc, cport, models as om, ou as oou
+pkg = ge.load_package()
+ctx = pkg.default_context(0)
+rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+DT = 0.002
+bad = 0
+for case in range(n_cases):
+    n_t = int(rng.integers(300, 3000)); n_trials = int(rng.choice([1, 2, 5]))
+    data = oou.generate_ou_process(0.3, 1.0, DT, n_t * DT, n_trials, seed=case + 1, n_t=n_t)
+    t = DT * np.arange(1, n_t + 1)
+    mo = om.one_timescale_model(data, t, prior=[om.Uniform(0.05, 5)])
+    mg = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)])
+    max_iter = int(rng.choice([1, 7, 100, 777, 3000])); min_acc = int(rng.choice([1, 5, 50, 10000]))
+    props = rng.uniform(0.05, 2.0, size=(max_iter, 1))
+    neg = rng.random(max_iter) < 0.1
+    props[neg, 0] = -rng.uniform(0.0005, 0.01, size=int(neg.sum()))       # diverging trajectories -> NaN distance
+    d_ref = cport.abc_distances(mo, props, seed=9, generation=case)
+    fin = d_ref[np.isfinite(d_ref)]
+    srt = np.sort(fin)
+    j = int(rng.integers(0, max(1, srt.size - 1)))
+    eps = float(0.5 * (srt[j] + srt[min(j + 1, srt.size - 1)])) if fin.size else 1.0     # between two distances
+    want = oabc.basic_abc(lambda th, i, g: d_ref[i], None, 1, eps, max_iter, min_acc, proposals=props)
+    got = pkg.basic_abc(mg, eps, max_iter, min_acc, proposals=props, seed=9, generation=case, ctx=ctx)
+    tol = 2 * np.sqrt(np.maximum(np.nan_to_num(d_ref), 0)) * 1e-5 + 1e-10 + 1e-5 * np.nan_to_num(d_ref)
+    margin = np.abs(d_ref - eps) <= tol
+    msgs = []
+    if margin[: want["n_total"]].any():
+        print(f"case {case}: a distance within tolerance of epsilon - skipped"); continue
+    if got["n_total"] != want["n_total"] or got["n_accepted"] != want["n_accepted"]:
+        dgpu = mg.gpu_model(ctx).distances(props, seed=9, generation=case)
+        diff = np.nonzero((dgpu <= eps) != (d_ref <= eps))[0]
+        if np.all(props[diff, 0] < 0) and np.all(np.isnan(dgpu[diff])):
+            # documented: tau < 0 diverges; fp32 overflows to NaN (never accepted, as in the reference,
+            # whose SDE solver fails there) where the oracle's closed-form fp64 update is still finite
+            print(f"case {case}: decisions differ only at tau < 0 where fp32 overflowed ({diff.size} proposals) - expected"); continue
+        msgs.append(f"n_total {got['n_total']} vs {want['n_total']}, n_accepted {got['n_accepted']} vs {want['n_accepted']}; "
+                    f"decisions differ at {[(int(i), round(float(props[i, 0]), 5), float(d_ref[i]), float(dgpu[i])) for i in diff[:4]]} eps={eps:.4g}")
+    elif not np.array_equal(got["isaccepted"], want["isaccepted"]) or not np.array_equal(got["theta_accepted"], want["theta_accepted"]):
+        msgs.append("accept mask / accepted theta differ")
+    else:
+        dw, dg = want["distances"], got["distances"]
+        pos = props[: dw.size, 0] > 0
+        # tau < 0 diverges: fp32 overflows (NaN) before the oracle's fp64 does (huge, finite) - rejected either way
+        if not np.array_equal(np.isnan(dw)[pos], np.isnan(dg)[pos]) or np.any(np.isnan(dw) & ~np.isnan(dg)): msgs.append("NaN pattern of distances differs")
+        elif not np.all(np.abs(np.nan_to_num(dg - dw))[pos] <= tol[: dw.size][pos]): msgs.append("distances beyond tolerance")
+    bad += bool(msgs)
+    print(f"case {case}: n_t={n_t} trials={n_trials} max_iter={max_iter} min_acc={min_acc} n_total={want['n_total']} n_acc={want['n_accepted']} nan={int(np.isnan(d_ref[:want['n_total']]).sum())}",
+          "-> ok" if not msgs else "-> " + "; ".join(msgs) + "   <-- MISMATCH", flush=True)
+print("mismatches", bad)
