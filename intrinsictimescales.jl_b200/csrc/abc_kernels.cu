@@ -27,6 +27,8 @@
 
 namespace itjl {
 
+constexpr int kFlushTiles = 32;       // level-one sums of k_abc_acf cover at most 32 time tiles (640 samples)
+
 template <int NT, bool MISSING, bool OSC>
 __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const __grid_constant__ AbcAcfParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -86,9 +88,15 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const __grid_
             simulate_trial<NT, MISSING, OSC>(g, oc, trial, xs, sh, kScaleUnitNorm, 1.0f, 0.0f, sim_cache);
         __syncthreads();
         if (P.debug & 2) continue;                            // debug bit 1: time the simulator alone
-        if (active && tile_begin < tile_end) acf_tiles(xs, acc, k0, tile_begin, tile_end);
+        // (and at most kFlushTiles x 20 samples per level-one sum: with few time streams - long lag windows -
+        // one thread owns most of a trial, 1e-5 .. 2e-5 off on 12 000-sample trials of the missing-data model)
+        if (active) {
+            for (int tb = tile_begin; tb < tile_end; tb += kFlushTiles) {
+                acf_tiles(xs, acc, k0, tb, min(tb + kFlushTiles, tile_end));
 #pragma unroll
-        for (int j = 0; j < TK; ++j) { tot[j] += acc[j]; acc[j] = 0.f; }
+                for (int j = 0; j < TK; ++j) { tot[j] += acc[j]; acc[j] = 0.f; }
+            }
+        }
         if (P.n_bufs == 1) __syncthreads();              // single buffer: lag sum done before it is rewritten
     }
 

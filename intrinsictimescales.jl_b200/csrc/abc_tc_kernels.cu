@@ -437,7 +437,7 @@ static int tc_store_conflicts(int sbo_bytes, int chunk) {
 }
 
 // Geometry of the tensor-core kernel; returns 0 when the configuration is supported.
-int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g) {
+int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g, int min_terms) {
     if (n_t < 16 || n_lags < 1 || n_lags > n_t) return -1;
     // FFMA tail lags beyond the tensor-memory plans.  The tail code handles up to 60 (four tiles of 16), but
     // only one tile pays: at C5 shape 2.8e11 samples/s with a 16-lag tail against 2.4e11 for a second lag
@@ -554,6 +554,13 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     // 1.0e-6, max 4.4e-6 / 6.3e-6, everything else included)
     const int64_t samples = (int64_t)n_t * n_trials;
     g->n_terms = samples >= 200000 ? 1 : (samples >= 100000 ? 2 : 3);
+    // The zero-mean argument needs independent rounding residuals.  The masked samples of the missing-data
+    // models all carry ONE value and hence one residual: every masked-masked pair is off by the same
+    // 2^-12-relative amount.  Small for the plain model (the value is the trial's mean offset: 2 terms keep it
+    // below 1e-6), but the oscillation model parks them at -(mean of valid) - data_mean s_x / data_sd, which
+    // can dominate the sum of squares (7e-5 on the ACF with hi*hi only, found by benchmarks/model_fuzz.py):
+    // the caller asks for at least 2 resp. all 3 terms there
+    if (g->n_terms < min_terms) g->n_terms = min_terms;
     const char* e_terms = getenv("ITJL_TC_TERMS");
     if (e_terms && atoi(e_terms) >= 1 && atoi(e_terms) <= 3) g->n_terms = atoi(e_terms);
     // The tensor-core accumulator rounds toward zero (tests/test_gpu_tc.py, probe): a cell that grows

@@ -158,7 +158,8 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         // the tensor-core kernel whenever the shape is supported
         const char* e_tc = getenv("ITJL_ABC_TC");
         const int want_tc = e_tc ? atoi(e_tc) : -1;
-        const int tcg = abc_tc_geometry((int)d.n_t, (int)d.n_stats, (int)d.n_trials, ctx->max_smem_optin, ctx->sm_count, &m->tc);
+        const int min_terms = d.summary == ITJL_SUMMARY_ACF_MISSING ? (d.kind == ITJL_KIND_OU_OSC ? 3 : 2) : 1;
+        const int tcg = abc_tc_geometry((int)d.n_t, (int)d.n_stats, (int)d.n_trials, ctx->max_smem_optin, ctx->sm_count, &m->tc, min_terms);
         if (want_tc == 1 && tcg != 0) { delete m; return fail(ctx, ITJL_ERR_ARG, "ITJL_ABC_TC=1 but the tensor-core kernel does not support this shape"); }
         m->use_tc = (tcg == 0) && (want_tc != 0) && (want_tc >= 1 || kTcDefault);
     }

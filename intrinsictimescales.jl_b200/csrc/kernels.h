@@ -174,7 +174,7 @@ struct AbcTcParams {
     size_t smem_bytes;
     int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = no MMAs, 2 = no simulation after the first particle
 };
-int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g);
+int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g, int min_terms = 1);
 cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, bool mixed, size_t smem, int grid,
                           cudaStream_t st);
 cudaError_t tc_probe_launch(const void* image_dev, int n_bytes, const int4* ops_dev, int n_ops, uint32_t lbo,

@@ -316,3 +316,24 @@ def test_distance_combined_acf_branch(pkg, ctx):
     assert np.array_equal(d, d_all)
     assert n_total == oabc.stop_index(d_all, eps, 30) and n_acc == 30
     assert np.array_equal(isacc[:n_total], (d_all <= eps)[:n_total])
+
+
+def test_oscillation_with_missing_model_many_long_trials(pkg, ctx):
+    """Found by benchmarks/model_fuzz.py: with data_mean != 0 the masked samples of this model sit at one large
+    value; with hi*hi tensor-core products only, their common fp16 rounding error put 7e-5 on the ACF at
+    50 x 11 000 samples.  The model now always uses the three-term split."""
+    dt, n_t, n_trials = 1 / 250, 11000, 50
+    t = dt * np.arange(1, n_t + 1)
+    data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.9], dt, n_t * dt, n_trials, 0.8, 0.6, seed=49, n_t=n_t)
+    rng = np.random.default_rng(3)
+    for r in range(n_trials):
+        s = int(rng.integers(0, n_t - n_t // 10)); data[r, s:s + n_t // 10] = np.nan
+    po = [omodels.Normal(.1, .1), omodels.Normal(10, 5), omodels.Uniform(0, 1)]
+    pp = [pkg.Normal(.1, .1), pkg.Normal(10, 5), pkg.Uniform(0, 1)]
+    om = omodels.one_timescale_and_osc_with_missing_model(data, t, prior=po)
+    gm = pkg.one_timescale_and_osc_with_missing_model(data, t, "abc", prior=pp)
+    theta = np.array([[0.05, 10.0, 0.9], [0.1, 12.0, 0.5], [0.02, 8.0, 0.3], [0.2, 11.0, 0.7]])
+    want, s_want = cport.abc_distances(om, theta, seed=4, generation=2, return_stats=True)
+    got, s_got = gm.gpu_model(ctx).distances(theta, seed=4, generation=2, return_stats=True)
+    assert np.max(np.abs(s_got - s_want)) <= 2e-5, np.max(np.abs(s_got - s_want))
+    assert np.all(np.abs(got - want) <= dist_tol(want, 2e-5))
