@@ -41,14 +41,17 @@ for case in range(n_cases):
                 sm = "acf" if kind == "osc_acf" else "psd"
                 mo = om.one_timescale_and_osc_model(data, t, prior=po, summary_method=sm)
                 mg = pkg.one_timescale_and_osc_model(data, t, "abc", prior=pp, summary_method=sm)
-                tol = 2e-5 if sm == "acf" else 5e-5; rel = sm == "psd"
+                tol = 2e-5 if sm == "acf" else 1e-5; rel = sm == "psd"
         g = mg.gpu_model(ctx)
         d_or, s_or = cport.abc_distances(mo, theta, seed=4, generation=2, return_stats=True)
         d, s = g.distances(theta, seed=4, generation=2, return_stats=True)
     except Exception as e:                                    # noqa: BLE001 - diagnostic: report and go on
         print(f"case {case}: {kind} n_t={n_t} trials={n_trials} fs={fs}: {type(e).__name__}: {e}"); continue
-    err = np.abs(s - s_or) / (np.abs(s_or) if rel else 1.0)
+    # PSD statistics: error relative to the spectrum's peak (a trial-mean periodogram has bins orders of magnitude
+    # below it, where the fp32 FFT's rounding - relative to the peak - is all that is left); the log distance is
+    # compared as well
+    err = np.abs(s - s_or) / (np.max(np.abs(s_or), axis=1, keepdims=True) if rel else 1.0)
     derr = np.abs(d - d_or) / np.maximum(np.abs(d_or), 1e-30)
-    flag = "" if np.nanmax(err) <= tol else "   <-- ABOVE TOLERANCE"
+    flag = "" if (np.nanmax(err) <= tol and (not rel or np.nanmax(derr) <= 1e-4)) else "   <-- ABOVE TOLERANCE"
     print(f"case {case}: {kind} n_t={n_t} trials={n_trials} fs={fs} n_stats={s.shape[1]} {g.kernel_info()[0]} "
           f"max {'rel' if rel else 'abs'} stat err {np.nanmax(err):.2e} max rel dist err {np.nanmax(derr):.2e}{flag}", flush=True)

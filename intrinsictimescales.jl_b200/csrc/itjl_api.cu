@@ -30,6 +30,7 @@ struct itjl_model {
     // PSD
     int n2 = 0, log2_n2 = 0, psd_chunk = 0, psd_xs_len = 0;
     size_t psd_smem = 0;
+    bool psd_accb_global = false;   // PSD bin sums in global memory (too many selected bins for shared memory)
     double psd_scale = 0.0;
 };
 
@@ -182,6 +183,11 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         for (int64_t i = 0; i < d.n_stats; ++i)
             if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { delete m; return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
         m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
+        if ((int64_t)m->psd_smem > ctx->max_smem_optin) {
+            // many selected bins (e.g. fs = 250 Hz: 80 % of 16 384): keep the per-particle bin sums in global memory
+            m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len, false);
+            m->psd_accb_global = true;
+        }
         if ((int64_t)m->psd_smem > ctx->max_smem_optin) { delete m; return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
         std::vector<float> win((size_t)d.n_t + 1, 0.0f);          // +1: the kernel reads the window as float2 pairs
         std::vector<float2> tw((size_t)m->n2 / 2);
@@ -299,7 +305,28 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.psd_scale = m->psd_scale;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
-        e = abc_psd_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
+        if (!m->psd_accb_global) {
+            e = abc_psd_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
+        } else {
+            // sub-batches of at most 2048 particles, each with its own row of bin sums in a scratch buffer
+            const int64_t sub = 2048, pad = ((int64_t)d.n_stats + 3) & ~(int64_t)3;
+            const cudaError_t er = ctx->scratch.reserve((size_t)std::min<int64_t>(sub, n_particles) * pad * sizeof(float));
+            if (er != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "PSD bin-sum scratch: %s", cudaGetErrorString(er));
+            e = cudaSuccess;
+            for (int64_t lo = 0; lo < n_particles && e == cudaSuccess; lo += sub) {
+                AbcPsdParams Q = P;
+                Q.grid = std::min<int64_t>(sub, n_particles - lo);
+                Q.accb_global = (float*)ctx->scratch.p;
+                Q.theta = theta_dev + lo;                         // column-major: the stride stays n_particles
+                Q.particle_offset = particle_offset + lo;
+                Q.dist_out = dist_dev + lo;
+                Q.stats_out = stats_dev ? stats_dev + lo * d.n_stats : nullptr;
+                Q.u0 = u0_dev ? u0_dev + lo * d.n_trials : nullptr;
+                Q.noise = noise_dev ? noise_dev + lo * d.n_trials * d.n_t : nullptr;
+                Q.phases = phases_dev ? phases_dev + lo * d.n_trials : nullptr;
+                e = abc_psd_launch(Q, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
+            }
+        }
     } else if (m->use_tc) {
         AbcTcParams P{};
         const AbcTcGeometry& t = m->tc;

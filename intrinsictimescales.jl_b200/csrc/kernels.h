@@ -63,8 +63,11 @@ struct AbcPsdParams {
     const double* phases;
     double* dist_out;
     double* stats_out;
+    float* accb_global = nullptr;   // per-particle bin sums in global memory [grid][(n_stats + 3) & ~3] when they do not fit
+                                    // in shared memory beside the FFT buffer (many selected bins), else null
+    int64_t grid = 0;               // CTAs of this launch (a sub-batch of the particles when accb_global is used)
 };
-size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out);
+size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out, bool accb_in_smem = true);
 int psd_fft_pos(int k, int N);
 size_t psd_fft_smem_bytes(int n2);
 cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st);

@@ -215,8 +215,10 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const __grid_constan
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                 // xs_len floats: one simulated trial
     float2* buf = reinterpret_cast<float2*>(xs + P.xs_len);         // padded FFT buffer, fft_buf_len(N) float2
-    float* accb = reinterpret_cast<float*>(buf + fft_buf_len(P.n2 >> 1));    // n_stats
-    SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb + ((P.n_stats + 3) & ~3));
+    float* accb_smem = reinterpret_cast<float*>(buf + fft_buf_len(P.n2 >> 1));    // n_stats (or nothing: sums in global memory)
+    const int n_stats_pad = (P.n_stats + 3) & ~3;
+    float* accb = P.accb_global ? P.accb_global + (size_t)blockIdx.x * n_stats_pad : accb_smem;
+    SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb_smem + (P.accb_global ? 0 : n_stats_pad));
     float2* twtab = reinterpret_cast<float2*>(sh + 1);
     __shared__ double red[NT / 32];
 
@@ -331,14 +333,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_psd_data(const double* __restri
 int psd_fft_pos(int k, int N) { return fft_pad(fft_pos(k, N)); }      // position in the padded buffer
 size_t psd_fft_smem_bytes(int n2) { return (size_t)(fft_buf_len(n2 / 2) + tw2_entries(n2 / 2)) * sizeof(float2); }
 
-size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out) {
+size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out, bool accb_in_smem) {
     int c = (n_t + kPsdThreads - 1) / kPsdThreads;
     c = (c + 3) & ~3;
     const int xs_len = c * kPsdThreads;                // staging buffer of one simulated trial
     *chunk_out = c;
     *xs_len_out = xs_len;
     return (size_t)xs_len * sizeof(float) + (size_t)fft_buf_len(n2 / 2) * sizeof(float2) +
-           (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPsdThreads>) +
+           (accb_in_smem ? (size_t)((n_stats + 3) & ~3) * sizeof(float) : 0) + sizeof(SimShared<kPsdThreads>) +
            (size_t)tw2_entries(n2 / 2) * sizeof(float2);
 }
 
@@ -361,7 +363,7 @@ cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStr
     void (*kern)(const AbcPsdParams) = osc ? k_abc_psd<true> : k_abc_psd<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)P.n_particles, kPsdThreads, smem, st>>>(P);
+    kern<<<(unsigned)(P.grid > 0 ? P.grid : P.n_particles), kPsdThreads, smem, st>>>(P);
     return cudaGetLastError();
 }
 

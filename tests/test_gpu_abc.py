@@ -337,3 +337,29 @@ def test_oscillation_with_missing_model_many_long_trials(pkg, ctx):
     got, s_got = gm.gpu_model(ctx).distances(theta, seed=4, generation=2, return_stats=True)
     assert np.max(np.abs(s_got - s_want)) <= 2e-5, np.max(np.abs(s_got - s_want))
     assert np.all(np.abs(got - want) <= dist_tol(want, 2e-5))
+
+
+def test_psd_model_with_more_selected_bins_than_fit_in_shared_memory(pkg, ctx):
+    """fs = 250 Hz, n_t > 8192: 0.5 < f < 100 selects 13 042 of the 16 383 bins - their per-particle sums do
+    not fit beside the 32 768-point FFT in shared memory (this used to be refused).  They then live in a
+    global scratch buffer, 2048 particles per launch; found by benchmarks/model_fuzz.py."""
+    fs, n_t, n_trials, P = 250.0, 9501, 2, 2051
+    dt = 1 / fs
+    t = dt * np.arange(1, n_t + 1)
+    data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.9], dt, n_t * dt, n_trials, 0.0, 1.0, seed=3, n_t=n_t)
+    po = [omodels.Normal(.1, .1), omodels.Normal(10, 5), omodels.Uniform(0, 1)]
+    pp = [pkg.Normal(.1, .1), pkg.Normal(10, 5), pkg.Uniform(0, 1)]
+    om = omodels.one_timescale_and_osc_model(data, t, prior=po, summary_method="psd")
+    gm = pkg.one_timescale_and_osc_model(data, t, "abc", prior=pp, summary_method="psd")
+    assert om.data_sum_stats.size == gm.data_sum_stats.size == 13042
+    rng = np.random.default_rng(0)
+    theta = np.stack([np.abs(rng.normal(.1, .05, P)) + 0.01, rng.normal(10, 3, P), rng.uniform(0.05, 0.95, P)], axis=1)
+    g = gm.gpu_model(ctx)
+    got = g.distances(theta, seed=4, generation=2)
+    idx = [0, 1, 2047, 2048, 2050]                               # both launches, and their seam
+    want = np.array([cport.abc_distances(om, theta[i:i + 1], seed=4, generation=2, particle_offset=i)[0] for i in idx])
+    assert np.all(np.abs(got[idx] - want) <= 1e-5 * want)
+    got5, stats5 = g.distances(theta[:5], seed=4, generation=2, return_stats=True)
+    _, s_or = cport.abc_distances(om, theta[:5], seed=4, generation=2, return_stats=True)
+    assert np.array_equal(got5, got[:5])
+    assert np.max(np.abs(stats5 - s_or) / s_or.max(axis=1, keepdims=True)) <= 1e-5
