@@ -12,9 +12,10 @@ pkg = ge.load_package()
 ctx = pkg.default_context(0)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+small = len(sys.argv) > 3 and sys.argv[3] == "small"      # short series (16 .. 299 samples)
 worst = 0.0
 for case in range(n_cases):
-    n_t = int(rng.integers(300, 12000))
+    n_t = int(rng.integers(300, 12000)) if not small else int(rng.integers(16, 300))
     n_trials = int(rng.choice([1, 2, 3, 4, 5, 7, 13, 30, 64]))
     n_lags = int(rng.integers(2, min(n_t, 1537) + 1))
     missing = bool(rng.integers(0, 4) == 0)
@@ -32,7 +33,7 @@ for case in range(n_cases):
             g = mk(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags).gpu_model(ctx)
         except pkg.ItjlError as e:
             res[tc] = None; print(f"case {case}: n_t={n_t} trials={n_trials} lags={n_lags} missing={missing} TC={tc}: {e}"); continue
-        theta = np.random.default_rng(case).uniform(0.05, 5.0, size=(8, 1))
+        theta = np.random.default_rng(case).uniform(0.005 if small else 0.05, 5.0, size=(8, 1))
         res[tc] = g.distances(theta, seed=3, generation=1, return_stats=True) + (g.kernel_info()[0],)
     if res["1"] is None or res["0"] is None:
         continue
