@@ -22,11 +22,11 @@ namespace itjl {
 // v - a, and ac[l] = sum of the cells on the diagonal v - a = l.  Each D_s is a tcgen05.mma chain
 // (K = the rows i of the trials) accumulating in fp32 in tensor memory.  Both operands are the
 // SAME shared-memory buffer in the MN-major no-swizzle layout (K rows 16 B apart); the B operand
-// of D_s simply starts s rows later.  x' is fed as an fp16 hi/lo pair: hi*hi + hi*lo + lo*hi
-// (~22-bit operands, 3 MMAs per tile and K step) when the particle has fewer than 10^5 samples.
-// Larger particles drop lo*hi: the omitted sum_t lo_t x_{t+l} is a sum of independent fp16 rounding
-// residuals (|lo| <= 2^-11 |x|, zero mean) - standard deviation 1.9e-4 / sqrt(n_trials n_t) in ACF
-// units, <= 6e-7 at 10^5 samples (3.8e-7 at C5), far inside the 1e-5 parity tolerance.
+// of D_s simply starts s rows later.  x' is fed as an fp16 hi/lo pair; the number of product terms
+// follows the particle size (abc_tc_geometry): hi*hi + hi*lo + lo*hi (~22-bit operands) below 10^5
+// samples, hi*hi + hi*lo up to 2 10^5, hi*hi alone above - a dropped cross term is a sum of independent
+// zero-mean fp16 rounding residuals, ~1e-4 / sqrt(n_trials n_t) in ACF units.  The missing-data models keep
+// cross terms whatever their size: their masked samples share one value, hence one residual.
 //
 // Tensor-memory plans (128 lanes x 512 columns of fp32):
 //   A  (n_lags <= 385)   tiles s = 0 .. 3, M = 128 (cell row a = TMEM lane), N = 128: lags 0 .. 384.
@@ -35,8 +35,11 @@ namespace itjl {
 //      the lower 16 lanes of every 32-lane quarter, rows a >= 64 x columns 64 .. 127 on the upper
 //      16 lanes (D address lane offset 16) - and the freed quadrant receives D_4 (rows a >= 64,
 //      b < 64, v = 512 + b): lags up to 448 without touching the CUDA cores.
-//   Up to 60 further lags (n_lags <= 509) are summed by an FFMA loop that reads the trial back from its
-//   operand planes; longer lag windows run on the CUDA-core kernel k_abc_acf.
+//   Up to 16 further lags (n_lags <= 464) are summed by an FFMA loop that reads the trial back from its
+//   operand planes (the loop handles 60, but beyond one tile a second launch is faster).
+//   Lag windows (n_lags <= 1537): the kernel is launched again with the B operand 3 w rows further down
+//   (plan-A tiles, column v <-> lag 384 w + v - a) for the lags the launches before it have not scored;
+//   longer windows run on the CUDA-core kernel k_abc_acf.
 //
 // Accumulator rounding.  tcgen05.mma aligns every product to the accumulator and truncates toward
 // zero (measured, benchmarks/tc_probe2.py), so a long positive chain shrinks: 1.1e-5 relative at lags
