@@ -1,0 +1,63 @@
+"""Seeded random shapes through both fused ACF kernels against the fp64 C oracle.
+
+The shapes are drawn the way benchmarks/tc_fuzz.py and benchmarks/model_fuzz.py draw them; those runs found
+the accumulator stagnation of the CUDA-core kernel, the shared rounding residual of masked samples in the
+tensor-core kernel and the lag-window / tail seams - this keeps a fixed sample of them in the suite."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cport
+from oracle import models as omodels
+from oracle import ou as oou
+
+pytestmark = pytest.mark.gpu
+
+ACF_TOL = 1e-5
+
+
+def _cases():
+    rng = np.random.default_rng(2024)
+    out = []
+    for case in range(14):
+        n_t = int(rng.integers(300, 12000))
+        n_trials = int(rng.choice([1, 2, 3, 5, 7, 13, 30]))
+        n_lags = int(rng.integers(2, min(n_t, 1537) + 1))
+        missing = bool(rng.integers(0, 3) == 0)
+        out.append((case, n_t, n_trials, n_lags, missing))
+    return out
+
+
+@pytest.mark.parametrize("case,n_t,n_trials,n_lags,missing", _cases())
+def test_random_shape_both_kernels_against_fp64_oracle(pkg, ctx, case, n_t, n_trials, n_lags, missing):
+    dt = 0.002
+    data = oou.generate_ou_process(0.3, 1.0, dt, n_t * dt, n_trials, seed=case + 1, n_t=n_t)
+    if missing:
+        rng = np.random.default_rng(case)
+        for r in range(n_trials):
+            s = int(rng.integers(0, n_t - n_t // 10))
+            data[r, s:s + n_t // 10] = np.nan
+    t = dt * np.arange(1, n_t + 1)
+    if missing:
+        om = omodels.one_timescale_with_missing_model(data, t, prior=[omodels.Uniform(0.05, 5)], n_lags=n_lags)
+        mk = lambda: pkg.one_timescale_with_missing_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)], n_lags=n_lags)
+    else:
+        om = omodels.one_timescale_model(data, t, prior=[omodels.Uniform(0.05, 5)], n_lags=n_lags)
+        mk = lambda: pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)], n_lags=n_lags)
+    theta = np.random.default_rng(100 + case).uniform(0.05, 5.0, size=(6, 1))
+    d_or, s_or = cport.abc_distances(om, theta, seed=3, generation=1, return_stats=True)
+    old = os.environ.get("ITJL_ABC_TC")
+    try:
+        for tc in ("1", "0"):
+            os.environ["ITJL_ABC_TC"] = tc
+            g = mk().gpu_model(ctx)
+            d, s = g.distances(theta, seed=3, generation=1, return_stats=True)
+            err = np.max(np.abs(s - s_or))
+            assert err <= ACF_TOL, (g.kernel_info()[0], n_t, n_trials, n_lags, missing, err)
+            assert np.all(np.abs(d - d_or) <= 2 * np.sqrt(d_or) * ACF_TOL + ACF_TOL ** 2 + 1e-5 * d_or)
+    finally:
+        if old is None:
+            os.environ.pop("ITJL_ABC_TC", None)
+        else:
+            os.environ["ITJL_ABC_TC"] = old
