@@ -180,3 +180,52 @@ def test_acw_nd_input_and_dims(pkg, ctx):
     assert r1.acf.shape == (r1.n_lags, 4) and np.array_equal(r1.acf.T, r2.acf)
     with pytest.raises(ValueError):
         pkg.acw(base, 100.0, dims=4, ctx=ctx)
+
+
+def _random_acw_cases():
+    rng = np.random.default_rng(77)
+    out = []
+    for case in range(12):
+        out.append((case, int(rng.choice([1, 2, 7, 33, 129])), int(rng.integers(40, 6000)), float(rng.choice([1.0, 100.0, 500.0])),
+                    ["randn", "ou", "ou_offset", "smooth"][int(rng.integers(0, 4))], bool(rng.integers(0, 3) == 0),
+                    bool(rng.integers(0, 4) == 0), None if rng.integers(0, 3) else int(rng.integers(2, 700))))
+    return out
+
+
+@pytest.mark.parametrize("case,n_slices,n_t,fs,gen,nan,average,n_lags", _random_acw_cases())
+def test_acw_random_inputs_against_oracle(pkg, ctx, case, n_slices, n_t, fs, gen, nan, average, n_lags):
+    """A fixed sample of benchmarks/acw_fuzz.py: indices bit-exact, values within the 1e-5 tolerance, the
+    same exceptions as the oracle."""
+    rng = np.random.default_rng(1000 + case)
+    if gen == "randn":
+        d = rng.standard_normal((n_slices, n_t))
+    elif gen == "smooth":
+        d = np.cumsum(rng.standard_normal((n_slices, n_t)), axis=1) * 0.05 + rng.standard_normal((n_slices, n_t))
+    else:
+        d = oou.generate_ou_process(float(rng.uniform(0.02, 2.0)) * (100.0 / fs), 1.0, 1 / fs, n_t / fs, n_slices, seed=case + 1, n_t=n_t)
+        if gen == "ou_offset":
+            d = d * float(rng.uniform(0.1, 10)) + float(rng.normal(0, 100))
+    if nan:
+        for r in range(n_slices):
+            if rng.integers(0, 2):
+                s = int(rng.integers(0, max(1, n_t - n_t // 8)))
+                d[r, s:s + max(1, n_t // 8)] = np.nan
+    if n_lags is not None:
+        n_lags = min(n_lags, n_t // 2)
+    types = ["acw0", "acw50", "acweuler", "tau"]
+    try:
+        want = oacw.acw(d, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average)
+    except ValueError:
+        with pytest.raises(ValueError):
+            pkg.acw(d, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average, ctx=ctx)
+        return
+    got = pkg.acw(d, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average, ctx=ctx)
+    res = dict(zip(types, got.acw_results))
+    assert got.n_lags == want["n_lags"]
+    for name, key in [("acw0", "k0"), ("acw50", "k50"), ("acweuler", "ke")]:
+        w = np.where(want[key] >= 0, want[key] * (1.0 / fs), np.nan)
+        assert np.array_equal(np.atleast_1d(res[name]), w, equal_nan=True), name
+    a = np.atleast_2d(got.acf)
+    assert a.shape == want["acf"].shape and np.array_equal(np.isnan(a), np.isnan(want["acf"]))
+    assert np.nanmax(np.abs(a - want["acf"]), initial=0.0) < 1e-5
+    assert np.allclose(np.atleast_1d(res["tau"]), want["tau"], rtol=1e-2, atol=0, equal_nan=True)
