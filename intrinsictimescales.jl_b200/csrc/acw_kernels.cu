@@ -435,7 +435,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 4) k_acw_stream(const AcwStrea
     // k_acw_finish adds the n_t % 32 samples at the end of the series in fp64.
     // (Tried and dropped, B200: loads issued half a block ahead of the math - 162 registers, 3 CTAs/SM,
     // 116 us - and an extra prefetch.global.L2 96 steps ahead - 122 us - against 111 us for this loop:
-    // at 38 instructions per sample the pass is issue-bound, not latency-bound.)
+    // 38 instructions per sample fill 65 % of the issue slots and 16 resident warps per SM (128 registers per
+    // thread) leave DRAM latency exposed - trading registers for load depth loses on both counts.)
     int since_flush = 0;
     const double* __restrict__ p = col + (size_t)tb * ld;
     for (int t0 = tb; t0 + SK <= te; t0 += SK) {
