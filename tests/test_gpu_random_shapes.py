@@ -61,3 +61,51 @@ def test_random_shape_both_kernels_against_fp64_oracle(pkg, ctx, case, n_t, n_tr
             os.environ.pop("ITJL_ABC_TC", None)
         else:
             os.environ["ITJL_ABC_TC"] = old
+
+
+def _model_cases():
+    rng = np.random.default_rng(4242)
+    out = []
+    for case in range(10):
+        out.append((case, ["osc_acf", "osc_psd", "osc_acf_missing", "plain_em"][int(rng.integers(0, 4))], int(rng.integers(400, 12000)),
+                    int(rng.choice([1, 2, 5, 20, 50])), float(rng.choice([250.0, 500.0, 1000.0])), bool(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("case,kind,n_t,n_trials,fs,shifted", _model_cases())
+def test_random_shape_oscillation_and_em_models_against_fp64_oracle(pkg, ctx, case, kind, n_t, n_trials, fs, shifted):
+    """A fixed sample of benchmarks/model_fuzz.py: oscillation model with the ACF and the PSD summary, with
+    missing data (data_mean != 0 moves the masked samples), and the Euler-Maruyama update."""
+    dt = 1.0 / fs
+    t = dt * np.arange(1, n_t + 1)
+    rng = np.random.default_rng(500 + case)
+    po = [omodels.Normal(.1, .1), omodels.Normal(10, 5), omodels.Uniform(0, 1)]
+    pp = [pkg.Normal(.1, .1), pkg.Normal(10, 5), pkg.Uniform(0, 1)]
+    rel = False
+    if kind == "plain_em":
+        data = oou.generate_ou_process(0.3, 1.0, dt, n_t * dt, n_trials, seed=case + 1, n_t=n_t)
+        om = omodels.one_timescale_model(data, t, prior=[omodels.Uniform(0.05, 5)], update="em")
+        gm = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)], update="em")
+        theta = rng.uniform(0.05, 5.0, size=(5, 1)); tol = 1e-5
+    else:
+        dm, ds = (float(rng.normal(0, 1)), float(rng.uniform(0.5, 3))) if shifted else (0.0, 1.0)
+        data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.9], dt, n_t * dt, n_trials, dm, ds, seed=case + 1, n_t=n_t)
+        theta = np.stack([np.abs(rng.normal(.1, .05, 5)) + 0.01, rng.normal(10, 3, 5), rng.uniform(0.05, 0.95, 5)], axis=1)
+        if kind == "osc_acf_missing":
+            for r in range(n_trials):
+                s = int(rng.integers(0, n_t - n_t // 10))
+                data[r, s:s + n_t // 10] = np.nan
+            om = omodels.one_timescale_and_osc_with_missing_model(data, t, prior=po)
+            gm = pkg.one_timescale_and_osc_with_missing_model(data, t, "abc", prior=pp)
+            tol = 2e-5
+        else:
+            sm = "acf" if kind == "osc_acf" else "psd"
+            om = omodels.one_timescale_and_osc_model(data, t, prior=po, summary_method=sm)
+            gm = pkg.one_timescale_and_osc_model(data, t, "abc", prior=pp, summary_method=sm)
+            tol = 2e-5 if sm == "acf" else 1e-5
+            rel = sm == "psd"
+    d_or, s_or = cport.abc_distances(om, theta, seed=4, generation=2, return_stats=True)
+    d, s = gm.gpu_model(ctx).distances(theta, seed=4, generation=2, return_stats=True)
+    scale = np.max(np.abs(s_or), axis=1, keepdims=True) if rel else 1.0      # PSD: relative to the spectrum's peak
+    assert np.max(np.abs(s - s_or) / scale) <= tol
+    assert np.all(np.abs(d - d_or) <= 2 * np.sqrt(d_or) * tol + tol ** 2 + 1e-4 * d_or)
