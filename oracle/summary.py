@@ -4,6 +4,7 @@ Follows /root/reference/src/stats/summary.jl:
   comp_ac_fft           :46-63 (vector), :79-89 (array)
   comp_psd_adfriendly   :183-235
   comp_ac_time_missing  :455-484 (vector), :486-496 (array)
+  comp_psd (periodogram) :111-160 (DSP.jl semantics restated, see comp_psd_periodogram_vec)
 and /root/reference/src/stats/bat_autocor.jl:21-24 (_ac_next_pow_two).
 Arrays are (trials, time): the reference's default dims=ndims(data).
 """
@@ -103,4 +104,46 @@ def comp_psd_adfriendly(data, fs):
     """summary.jl:183-202 on (trials, time) -> ((trials, n2/2-1), freqs)."""
     data = np.atleast_2d(np.asarray(data, dtype=np.float64))
     rows = [comp_psd_adfriendly_vec(r, fs) for r in data]
+    return np.stack([r[0] for r in rows]), rows[0][1]
+
+
+# ---- comp_psd, method = "periodogram" (SURVEY 8f.1) ---------------------------------------------
+def nextfastfft(n):
+    """DSP.jl `nextfastfft(n)` = nextprod([2, 3, 5, 7], n): the smallest 7-smooth integer >= n."""
+    m = int(n)
+    while True:
+        r = m
+        for p in (2, 3, 5, 7):
+            while r % p == 0:
+                r //= p
+        if r == 1:
+            return m
+        m += 1
+
+
+def comp_psd_periodogram_vec(x, fs):
+    """summary.jl:146-155: `dsp.periodogram(x; fs=fs, window=dsp.hamming)` without the DC bin.
+    DSP.jl 0.8 (third-party, not under /root/reference; restated from its documented behaviour, UNPINNED
+    until tests/golden/reference_v1.json exists): no detrending; the window function is called with
+    the signal length (symmetric Hamming, 0.54 - 0.46 cos(2 pi k / (n - 1))); nfft = nextfastfft(n), zero
+    padded; one-sided real FFT; power = |X|^2 / (fs * sum(w^2)), doubled except at DC and - for even nfft -
+    at Nyquist; freq = rfftfreq(nfft, fs)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    nfft = nextfastfft(n)
+    w = hamming_window(n)
+    xf = np.fft.rfft(x * w, nfft)
+    p = np.abs(xf) ** 2 / (fs * np.sum(w ** 2))
+    if nfft % 2 == 0:
+        p[1:-1] *= 2.0
+    else:
+        p[1:] *= 2.0
+    freqs = np.fft.rfftfreq(nfft, 1.0 / fs)
+    return p[1:], freqs[1:]
+
+
+def comp_psd_periodogram(data, fs):
+    """summary.jl:111-144 on (trials, time) -> ((trials, nfft/2), freqs)."""
+    data = np.atleast_2d(np.asarray(data, dtype=np.float64))
+    rows = [comp_psd_periodogram_vec(r, fs) for r in data]
     return np.stack([r[0] for r in rows]), rows[0][1]
