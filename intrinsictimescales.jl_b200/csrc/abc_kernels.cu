@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) k_abc_acf(const __grid_
         coeff = P.theta[particle + 2 * P.n_particles];
     }
     const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
-                                       freq, coeff);
+                                       freq, coeff, P.n_t, true, !MISSING);
 
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
@@ -185,6 +185,7 @@ static int abc_acf_geometry_cfg(int n_t, int n_lags, int max_smem, int nt, int n
     g->n_streams = (g->n_tiles + g->tiles_per_stream - 1) / g->tiles_per_stream;
     int c = (n_t + nt - 1) / nt;
     g->chunk = (c + 3) & ~3;
+    if (g->chunk > kQtab) return -3;
     int need = (g->n_tiles + g->lt + 2) * TT;               // furthest window read
     int stride = g->chunk * nt;
     if (stride < need) stride = need;

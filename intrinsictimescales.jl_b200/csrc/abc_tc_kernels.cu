@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                 freq = P.theta[particle + P.n_particles];
                 coeff = P.theta[particle + 2 * P.n_particles];
             }
-            const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU, freq, coeff);
+            const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU, freq, coeff, P.n_t, true, !MISSING);
             sa.particle = (uint32_t)(P.particle_offset + particle);
             const size_t pt = (size_t)particle * P.n_trials;
             sa.u0 = P.u0 ? P.u0 + pt : nullptr;
@@ -504,6 +504,7 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     }
     int c = (n_t + kTcGroupThreads - 1) / kTcGroupThreads;
     g->chunk = (c + 7) & ~7;
+    if (g->chunk > kQtab) return -3;
     // K rows per plane: data + shifted-B reach; among the strides that keep the group count, take the
     // one with the fewest bank conflicts
     int rows_min = 16 * g->ksteps + max_shift;
@@ -520,7 +521,8 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         const size_t buffer = (size_t)2 * 16 * rows * 16;   // hi + lo planes of one trial
         *epi_off = ((size_t)groups * 2 * buffer + 127) & ~(size_t)127;
         *total = (*epi_off + epi + 15) & ~(size_t)15;
-        return (int64_t)*total + 1024 <= (int64_t)max_smem - 6 * 1024;   // static shared (barriers, scan, tail sums) stays below 6 KB
+        // static shared memory: barriers, the groups' scan tables and carry-power tables (~6.6 KB), tail sums (+4 KB)
+        return (int64_t)*total + 1024 <= (int64_t)max_smem - (g->tail_lt > 0 ? 11 : 7) * 1024;
     };
     int groups = want_groups;
     size_t epi_off = 0, total = 0;

@@ -11,6 +11,9 @@ namespace itjl {
 
 constexpr int kThreads = 256;          // CTA size of the fused simulate+summary kernels
 constexpr int kWarps = kThreads / 32;
+// samples per thread of the blocked-scan simulation (simulate.cuh keeps a table of that many carry powers per
+// particle): 256 threads x 221 floats already fill the shared memory of one CTA
+constexpr int kQtab = 224;
 
 // Grow-only device scratch buffer.
 struct DevBuf {

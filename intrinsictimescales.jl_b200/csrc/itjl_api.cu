@@ -528,8 +528,8 @@ static int generate_common(itjl_ctx* ctx, int kind, double tau, double freq, dou
     P.n_t = (int)n_t; P.n_trials = (int)n_trials;
     int c = (int)((n_t + kThreads - 1) / kThreads);
     P.chunk = (c + 3) & ~3;
-    const size_t smem = (size_t)P.chunk * kThreads * sizeof(float) + 256;
-    if ((int64_t)smem > ctx->max_smem_optin) return fail(ctx, ITJL_ERR_ARG, "generate_ou: n_t too large for one CTA");
+    const size_t smem = (size_t)P.chunk * kThreads * sizeof(float) + 2048;
+    if ((int64_t)smem > ctx->max_smem_optin || P.chunk > kQtab) return fail(ctx, ITJL_ERR_ARG, "generate_ou: n_t too large for one CTA");
     P.tau = tau; P.freq = freq; P.coeff = coeff; P.dt = dt;
     P.update = update; P.kind = kind; P.mode = mode; P.scale = (float)scale; P.shift = (float)shift;
     P.keys = philox_keys(seed);

@@ -13,8 +13,10 @@ __global__ void __launch_bounds__(kThreads) k_ou_generate(const __grid_constant_
     float* xs = reinterpret_cast<float*>(smem_raw);
     SimShared<kThreads>* sh = reinterpret_cast<SimShared<kThreads>*>(xs + (size_t)P.chunk * kThreads);
     const int trial = blockIdx.x;
+    // the output is the trajectory itself: a growing one may be rescaled when it is standardised anyway,
+    // never time-reversed
     const OuConsts oc = make_ou_consts(P.tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
-                                       P.freq, P.coeff);
+                                       P.freq, P.coeff, P.n_t, P.mode == kScaleStd, false);
     SimCache sim_cache;
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;

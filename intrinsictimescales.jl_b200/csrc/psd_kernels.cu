@@ -59,7 +59,7 @@ __device__ __forceinline__ Tw2 tw2_build(float2* tab, const float2* __restrict__
 // the fused radix-16 tail below reads element e of 32 different 16-point groups at a stride of 17
 // float2 = 34 words - also two wavefronts, where the unpadded strides of 16 / 4 float2 cost 8.
 __host__ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
-__host__ __device__ __forceinline__ int fft_buf_len(int N) { return N + (N >> 4) + 1; }     // float2 entries
+__host__ __device__ __forceinline__ int fft_buf_len(int N) { return (N + (N >> 4) + 2) & ~1; }     // float2 entries (even: what follows stays 16-byte aligned)
 
 __device__ __forceinline__ void bfly4(float2& x0, float2& x1, float2& x2, float2& x3) {
     const float2 a0 = make_float2(x0.x + x2.x, x0.y + x2.y);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const __grid_constan
         coeff = P.theta[particle + 2 * P.n_particles];
     }
     const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
-                                       freq, coeff);
+                                       freq, coeff, P.n_t, true, true);   // |FFT| of the Hamming-windowed trial is reversal invariant
     SimCache sim_cache;
     SimArgs g;
     g.n_t = P.n_t; g.chunk = P.chunk;
@@ -335,7 +335,7 @@ size_t psd_fft_smem_bytes(int n2) { return (size_t)(fft_buf_len(n2 / 2) + tw2_en
 
 size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out, bool accb_in_smem) {
     int c = (n_t + kPsdThreads - 1) / kPsdThreads;
-    c = (c + 3) & ~3;
+    c = (c + 3) & ~3;                                   // (<= kQtab: n_t <= 2^24 / ... is bounded by the FFT buffer long before)
     const int xs_len = c * kPsdThreads;                // staging buffer of one simulated trial
     *chunk_out = c;
     *xs_len_out = xs_len;

@@ -9,8 +9,16 @@
 // a zero state (Philox noise generated in registers), the chunk-end affine maps
 // (a^chunk, y_end) are combined by a warp-shuffle + shared-memory scan, and the carry-in
 // is added back as p_j * carry with p_j = a^(j+1).  Mean and sum of squares follow
-// analytically from per-thread partial sums (S_y, S_yy, S_yp, S_p, S_pp), so the trial
+// analytically from per-thread partial sums (S_y, S_yy, S_yu, S_p, S_pp), so the trial
 // needs exactly two passes over its chunk and three __syncthreads().
+//
+// The powers enter as q_j = 1 - a^(j+1), a table of `chunk` floats per particle computed in fp64
+// (SimShared::qtab) and read four at a time: x_j = y_j + c - c q_j.  Carrying p_j itself by the fp32
+// recurrence p <- p - eps p rounds the SAME way at every step when eps is small (p ~ 1, the decrement a
+// fixed number of ulps): a systematic error of the decay rate of 0.5 ulp / (eps / 2^-24), i.e. 1e-3 at
+// tau = 500 dt-steps x 1000, which put 1e-5 .. 4e-5 on the ACF of near-unit-root trials (|tau| >> T: most of
+// what the README's Normal(tau_hat, 20) prior proposes).  The affine maps are composed in the same form,
+// (Q, B) with Q = 1 - A.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -24,10 +32,34 @@ struct OuConsts {
     float sc;     // sqrt(coeff)            (1 for the plain OU model)
     float so;     // sqrt(1-coeff)*sqrt(2)  (0 for the plain OU model)
     double fdt;   // freq * dt, in turns per sample
+    float x0_mul; // factor on the drawn initial state (1; e^-G for a growing trajectory, see below)
+    float x0_add; // added to it (0; 1 with x0_mul = 0 for the noise-free limit)
+    double lna;   // ln a (NaN when a <= 0: Euler-Maruyama with dt > tau), a64 = a: for the table of 1 - a^(j+1)
+    double a64;
 };
 
+// q_j = 1 - a^(j+1) in fp64 (one call per table entry and particle)
+__device__ __forceinline__ float ou_q(const OuConsts& oc, int j) {
+    const double k = (double)(j + 1);
+    return (float)(oc.lna == oc.lna ? -expm1(k * oc.lna) : 1.0 - pow(oc.a64, k));
+}
+
+// Growing trajectories (tau < 0: a > 1).  The reference integrates them like any other draw of its prior - the
+// README's Normal(tau_hat, 20) proposes a negative tau half of the time - and its fp64 state stays finite up to
+// a log-growth G = n_t ln a of ~354.  fp32 sums of squares overflow from G ~ 40, so such a trial is simulated
+// in a scaled form; every statistic downstream is scale free (the trial is standardised first):
+//   G <= 30        : as is.
+//   30 < G <= 80   : initial state and innovations times e^-G (the trial then ends at O(1)); the oscillation
+//                    term, < 1e-13 of the trial's scale, is dropped.
+//   80 < G <= 354  : the innovations are < e^-70 of the samples that carry any weight, so the trial IS the
+//                    exponential C a^t; its statistics equal those of its time reversal a^-j, which is
+//                    what is generated (x0 = 1, no noise, coefficient 1/a).  Not `reversible` (a missing-data
+//                    mask is tied to the time axis): NaN - a documented deviation, the reference is finite there.
+//   G > 354        : fp64 overflows as well (x^2 > 1.8e308): NaN, like the reference.
+// `scalable` is false for standardize = false (the raw values are the output).
 __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int update, int kind,
-                                                   double freq, double coeff) {
+                                                   double freq, double coeff, int n_t = 0, bool scalable = true,
+                                                   bool reversible = true) {
     OuConsts c;
     double eps, s;
     if (update == ITJL_UPDATE_EXACT) {
@@ -39,9 +71,8 @@ __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int up
         eps = dt / tau;
         s = sqrt(dt);
     }
-    c.eps = (float)eps;
-    c.s = (float)s;
     c.sc = 1.0f; c.so = 0.0f; c.fdt = 0.0;
+    c.x0_mul = 1.0f; c.x0_add = 0.0f;
     if (kind == ITJL_KIND_OU_OSC) {
         // ou_process.jl:189-196: only values outside [0, 1] are moved
         if (coeff < 0.0) coeff = 1e-4; else if (coeff > 1.0) coeff = 1.0 - 1e-4;
@@ -49,14 +80,31 @@ __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int up
         c.so = (float)(sqrt(1.0 - coeff) * 1.4142135623730951);
         c.fdt = freq * dt;
     }
+    if (eps < 0.0 && scalable && n_t > 0) {
+        const double G = (double)n_t * log1p(-eps);          // ln a^n
+        if (G > 354.0 || (G > 80.0 && !reversible)) {
+            eps = NAN;
+        } else if (G > 80.0) {
+            eps = 1.0 - 1.0 / (1.0 - eps);                   // coefficient 1/a
+            s = 0.0; c.so = 0.0f; c.x0_mul = 0.0f; c.x0_add = 1.0f;
+        } else if (G > 30.0) {
+            const double g = exp(-G);
+            s *= g; c.so = 0.0f; c.x0_mul = (float)g;
+        }
+    }
+    c.eps = (float)eps;
+    c.s = (float)s;
+    c.a64 = 1.0 - eps;
+    c.lna = (update == ITJL_UPDATE_EXACT && c.x0_add == 0.0f) ? -dt / tau : log1p(-eps);   // NaN for a <= 0
     return c;
 }
 
 template <int NT>
 struct SimShared {
-    float scanA[NT / 32 < 32 ? 32 : NT / 32];      // (32 entries: the tensor-core sink scans 8 x 4 blocks)
+    float scanA[NT / 32 < 32 ? 32 : NT / 32];      // Q = 1 - A of the chunk-end maps (32 entries: the tensor-core sink scans 8 x 4 blocks)
     float scanB[NT / 32 < 32 ? 32 : NT / 32];
     double sums[NT / 32][4];
+    __align__(16) float qtab[kQtab];               // q_j = 1 - a^(j+1), j < chunk <= kQtab, of the current particle
     float x0;                                      // the trial's initial state, drawn by warp 0 (plain OU model)
 };
 
@@ -147,53 +195,64 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         box_muller(r[0], r[1], x0, z1);
         phase_turns = (double)u01(r[2]);
         if (g.u0) x0 = (float)g.u0[trial];
+        x0 = fmaf(x0, oc.x0_mul, oc.x0_add);
         if (OSC && g.phases) phase_turns = g.phases[trial] * 0.15915494309189535;
         if (!OSC && lane == 0) sh->x0 = x0;
     }
 
+    // ---- table of q_j = 1 - a^(j+1) (first trial of the particle in this group) -------
+    if (!cache.valid) {
+        sim_sync(bar_id, NT);                            // nobody still reads the previous particle's table
+        for (int j = tid; j < g.chunk; j += NT) sh->qtab[j] = ou_q(oc, j);
+        sim_sync(bar_id, NT);
+    }
+
     // ---- pass A: local recurrence from a zero state + partial sums -----------------
-    float y = 0.f, p = 1.f;
-    float Sy = 0.f, Syy = 0.f, Syp = 0.f, Sp = 0.f, Spp = 0.f;
-    float Vy = 0.f, Vyy = 0.f, Vyp = 0.f, Vp = 0.f, Vpp = 0.f;   // valid-only sums (MISSING)
+    // x_j = v_j + cs p_j, p_j = 1 - q_j, cs = (sqrt(coeff) x) carry: v is everything that does not depend on
+    // the carry (the local recurrence, plus the oscillation term)
+    float y = 0.f;
+    float Sy = 0.f, Syy = 0.f, Syu = 0.f, Sp = 0.f, Spp = 0.f;
+    float Vy = 0.f, Vyy = 0.f, Vyu = 0.f, Vp = 0.f, Vpp = 0.f;   // valid-only sums (MISSING)
     const double* nz = g.noise ? g.noise + (size_t)trial * g.n_t : nullptr;
     const uint32_t* mrow = MISSING ? g.mask_bits + (size_t)trial * g.mask_words : nullptr;
     const bool need_p_sums = !cache.valid;
+    const float* qt = sh->qtab;
     if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
     if (j0 < g.n_t) {
-        // recurrence + partial sums + store of the four samples j .. j+3 driven by z[0..3]
-        auto advance4 = [&](const int j, const float (&z)[4], const bool full, const uint32_t mbits) {
-            float v[4], pp[4];
+        // recurrence + partial sums + store of the four samples j .. j+3 driven by z[0..3]; u = q of these samples
+        auto advance4 = [&](const int j, const float (&z)[4], const float4 u4, const bool full, const uint32_t mbits) {
+            const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+            float v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 y = fmaf(-eps, y, y);
                 y = fmaf(s, z[i], y);
-                p = fmaf(-eps, p, p);
-                v[i] = y; pp[i] = p;
+                v[i] = y;
                 if (OSC) {
                     double turns = fma(oc.fdt, (double)(j + i + 1), phase_turns);
                     turns -= rint(turns);
                     v[i] = fmaf(oc.so, __sinf(6.283185307179586f * (float)turns), oc.sc * y);   // turns in [-0.5, 0.5]: MUFU.SIN at its best (abs error 5e-7)
-                    pp[i] = oc.sc * p;
                 }
             }
             if (full && !MISSING) {                      // common case: no per-sample predicates
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syp = fmaf(v[i], pp[i], Syp);
+                    Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syu = fmaf(v[i], u[i], Syu);
                 }
                 if (need_p_sums) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { Sp += pp[i]; Spp = fmaf(pp[i], pp[i], Spp); }
+                    for (int i = 0; i < 4; ++i) { const float pe = 1.0f - u[i]; Sp += pe; Spp = fmaf(pe, pe, Spp); }
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (j + i < g.n_t) {
-                        Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syp = fmaf(v[i], pp[i], Syp);
-                        if (need_p_sums) { Sp += pp[i]; Spp = fmaf(pp[i], pp[i], Spp); }
+                        const float pe = 1.0f - u[i];
+                        Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syu = fmaf(v[i], u[i], Syu);
+                        if (need_p_sums) { Sp += pe; Spp = fmaf(pe, pe, Spp); }
                         if (MISSING && !((mbits >> i) & 1u)) {
-                            Vy += v[i]; Vyy = fmaf(v[i], v[i], Vyy); Vyp = fmaf(v[i], pp[i], Vyp);
-                            Vp += pp[i]; Vpp = fmaf(pp[i], pp[i], Vpp);
+                            Vy += v[i]; Vyy = fmaf(v[i], v[i], Vyy); Vyu = fmaf(v[i], u[i], Vyu);
+                            Vp += pe; Vpp = fmaf(pe, pe, Vpp);
                         }
                     }
                 }
@@ -221,8 +280,8 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 box_muller(ra[2], ra[3], za[2], za[3]);
                 box_muller(rb[0], rb[1], zb[0], zb[1]);
                 box_muller(rb[2], rb[3], zb[2], zb[3]);
-                advance4(j, za, true, 0u);
-                advance4(j + 4, zb, true, 0u);
+                advance4(j, za, *reinterpret_cast<const float4*>(qt + q), true, 0u);
+                advance4(j + 4, zb, *reinterpret_cast<const float4*>(qt + q + 4), true, 0u);
             }
         }
         for (; q < g.chunk; q += 4) {
@@ -243,65 +302,67 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 }
                 if (MISSING) mbits = (mrow[j >> 5] >> (j & 31)) & 0xFu;
             }
-            advance4(j, z, full, mbits);
+            advance4(j, z, *reinterpret_cast<const float4*>(qt + q), full, mbits);
         }
     }
     if (need_p_sums) { cache.Sp = Sp; cache.Spp = Spp; cache.valid = true; }
     else { Sp = cache.Sp; Spp = cache.Spp; }
 
-    // ---- scan of the chunk-end affine maps x -> A x + B ----------------------------
-    float A = p, B = y;
+    // ---- scan of the chunk-end affine maps x -> (1 - Q) x + B ------------------------
+    // composition "earlier (Qp, Bp), then (Q, B)":  B <- Bp - Q Bp + B,  Q <- Q + Qp - Q Qp
+    float Q = (j0 < g.n_t) ? qt[g.chunk - 1] : 0.f, B = y;
     float c;                                         // carry into this chunk
     if (!TC) {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+            const float Qp = __shfl_up_sync(0xffffffffu, Q, d);
             const float Bp = __shfl_up_sync(0xffffffffu, B, d);
-            if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
+            if (lane >= d) { B = fmaf(-Q, Bp, Bp + B); Q = fmaf(-Q, Qp, Q + Qp); }
         }
-        if (lane == 31) { sh->scanA[warp] = A; sh->scanB[warp] = B; }
+        if (lane == 31) { sh->scanA[warp] = Q; sh->scanB[warp] = B; }
         sim_sync(bar_id, NT);
         if (!OSC) x0 = sh->x0;
         float xw = x0;                                   // state entering this warp's first chunk
-        for (int w = 0; w < warp; ++w) xw = fmaf(sh->scanA[w], xw, sh->scanB[w]);
-        const float Aprev = __shfl_up_sync(0xffffffffu, A, 1);
+        for (int w = 0; w < warp; ++w) xw = fmaf(-sh->scanA[w], xw, xw + sh->scanB[w]);
+        const float Qprev = __shfl_up_sync(0xffffffffu, Q, 1);
         const float Bprev = __shfl_up_sync(0xffffffffu, B, 1);
-        c = (lane == 0) ? xw : fmaf(Aprev, xw, Bprev);
+        c = (lane == 0) ? xw : fmaf(-Qprev, xw, xw + Bprev);
     } else {
         // chunk order = (m, warp, qt): scan the four quarters of this warp for each m (lanes m, m + 8, m + 16,
         // m + 24), publish the 8 x 4 block maps in chunk order, and let every warp scan that 32-entry table
 #pragma unroll
         for (int d = 8; d < 32; d <<= 1) {
-            const float Ap = __shfl_up_sync(0xffffffffu, A, d);
+            const float Qp = __shfl_up_sync(0xffffffffu, Q, d);
             const float Bp = __shfl_up_sync(0xffffffffu, B, d);
-            if (lane >= d) { B = fmaf(A, Bp, B); A *= Ap; }
+            if (lane >= d) { B = fmaf(-Q, Bp, Bp + B); Q = fmaf(-Q, Qp, Q + Qp); }
         }
-        if (lane >= 24) { sh->scanA[4 * (lane - 24) + warp] = A; sh->scanB[4 * (lane - 24) + warp] = B; }
+        if (lane >= 24) { sh->scanA[4 * (lane - 24) + warp] = Q; sh->scanB[4 * (lane - 24) + warp] = B; }
         sim_sync(bar_id, NT);
         if (!OSC) x0 = sh->x0;
-        float TA = sh->scanA[lane], TB = sh->scanB[lane];
+        float TQ = sh->scanA[lane], TB = sh->scanB[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const float Ap = __shfl_up_sync(0xffffffffu, TA, d);
+            const float Qp = __shfl_up_sync(0xffffffffu, TQ, d);
             const float Bp = __shfl_up_sync(0xffffffffu, TB, d);
-            if (lane >= d) { TB = fmaf(TA, Bp, TB); TA *= Ap; }
+            if (lane >= d) { TB = fmaf(-TQ, Bp, Bp + TB); TQ = fmaf(-TQ, Qp, TQ + Qp); }
         }
         const int e = 4 * (lane & 7) + warp;             // my block; state entering it = blocks 0 .. e - 1 applied to x0
-        const float PA = __shfl_sync(0xffffffffu, TA, (e + 31) & 31);
+        const float PQ = __shfl_sync(0xffffffffu, TQ, (e + 31) & 31);
         const float PB = __shfl_sync(0xffffffffu, TB, (e + 31) & 31);
-        const float xw = (e == 0) ? x0 : fmaf(PA, x0, PB);
-        const float Aprev = __shfl_up_sync(0xffffffffu, A, 8);
+        const float xw = (e == 0) ? x0 : fmaf(-PQ, x0, x0 + PB);
+        const float Qprev = __shfl_up_sync(0xffffffffu, Q, 8);
         const float Bprev = __shfl_up_sync(0xffffffffu, B, 8);
-        c = (lane < 8) ? xw : fmaf(Aprev, xw, Bprev);
+        c = (lane < 8) ? xw : fmaf(-Qprev, xw, xw + Bprev);
     }
+    const float cs = OSC ? oc.sc * c : c;            // the oscillation model mixes sqrt(coeff) x OU
 
     // ---- mean / sum of squares from the partial sums --------------------------------
-    double r0 = (double)fmaf(c, Sp, Sy);
-    double r1 = (double)fmaf(c * c, Spp, fmaf(2.0f * c, Syp, Syy));
+    double r0 = (double)fmaf(cs, Sp, Sy);
+    double r1 = (double)fmaf(cs * cs, Spp, fmaf(2.0f * cs, Sy - Syu, Syy));
     double r2 = 0.0, r3 = 0.0;
     if (MISSING) {
-        r2 = (double)fmaf(c, Vp, Vy);
-        r3 = (double)fmaf(c * c, Vpp, fmaf(2.0f * c, Vyp, Vyy));
+        r2 = (double)fmaf(cs, Vp, Vy);
+        r3 = (double)fmaf(cs * cs, Vpp, fmaf(2.0f * cs, Vy - Vyu, Vyy));
     }
     r0 = warp_sum(r0); r1 = warp_sum(r1);
     if (MISSING) { r2 = warp_sum(r2); r3 = warp_sum(r3); }
@@ -318,7 +379,8 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     }
     const double n = (double)g.n_t;
     double m = SX * g.inv_n;
-    float mf, rf, miss_val = 0.f;
+    float rf, miss_val = 0.f;
+    double mc;                                       // what is subtracted from every sample
     if (!MISSING) {
         // sums are combined in fp64 (cancellation in SXX - n m^2); the final reciprocal square
         // root is an fp32 rsqrt refined by one Newton step (relative error < 1e-7)
@@ -327,7 +389,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         r = r * fmaf(-0.5f * ssf * r, r, 1.5f);
         if (mode == kScaleStd) r *= scale * g.sqrt_nm1;
         else if (mode == kScaleRaw) { r = 1.0f; m = 0.0; }
-        mf = (float)m; rf = r;
+        mc = m; rf = r;
     } else {
         // comp_ac_time_missing (summary.jl:460-471) applied to the standardised, masked
         // trial: valid z = x - m_all, masked z = 0; m2 = mean of valid z; every entry -= m2.
@@ -343,23 +405,22 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         const float ssf = (float)(VXX - 2.0 * mt * VX + nv * mt * mt + (n - nv) * m2e * m2e);
         float r = rsqrtf(ssf);
         r = r * fmaf(-0.5f * ssf * r, r, 1.5f);
-        mf = (float)mt; rf = r; miss_val = (float)(-m2e) * r;
+        mc = mt; rf = r; miss_val = (float)(-m2e) * r;
     }
 
-    // ---- pass B: out = (y + p c - m) r + shift = y r + p (c r) + (shift - m r) -----------
+    // ---- pass B: out = (v + cs - cs q - m) r + shift = v r - q (cs r) + ((cs - m) r + shift) ----------
     if (TC) {
         // the operands carry the power-of-two factor `scale`: fold it into the affine map
         const float sc = sink->scale;
         rf *= sc; miss_val *= sc; shift *= sc;
     }
     if (j0 < g.n_t) {
-        float pb = OSC ? oc.sc : 1.f;
-        const float crf = c * rf;
-        const float k0 = fmaf(-mf, rf, shift);
+        const float ncrf = -cs * rf;
+        const float k0 = fmaf((float)((double)cs - mc), rf, shift);
         constexpr int STEP = TC ? 8 : 4;                 // TC: chunk is a multiple of 8
         for (int q = 0; q < g.chunk; q += STEP) {
             const int j = j0 + q;
-            float v[STEP];
+            float v[STEP], u[STEP];
             const int off = TC ? ((j & 127) >> 3) * sink->sbo + (j >> 7) * 16 : 0;
             if (TC) {
                 const float4 a4 = *reinterpret_cast<const float4*>(sink->hi + off);
@@ -371,10 +432,12 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
             }
 #pragma unroll
-            for (int i = 0; i < STEP; ++i) {
-                pb = fmaf(-eps, pb, pb);
-                v[i] = fmaf(v[i], rf, fmaf(pb, crf, k0));
+            for (int h = 0; h < STEP; h += 4) {
+                const float4 u4 = *reinterpret_cast<const float4*>(qt + q + h);
+                u[h] = u4.x; u[h + 1] = u4.y; u[h + 2] = u4.z; u[h + 3] = u4.w;
             }
+#pragma unroll
+            for (int i = 0; i < STEP; ++i) v[i] = fmaf(v[i], rf, fmaf(u[i], ncrf, k0));
             if (MISSING || j + STEP - 1 >= g.n_t) {
                 uint32_t mbits = 0u;
                 if (MISSING && j < g.n_t) mbits = (mrow[j >> 5] >> (j & 31)) & (STEP == 8 ? 0xFFu : 0xFu);

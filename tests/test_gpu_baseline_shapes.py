@@ -41,7 +41,9 @@ def test_c1_readme_shape_including_negative_and_large_tau(pkg, ctx):
     # what Normal(tau_hat, 20) actually proposes: half of it negative, most of it >> the 10 s of data
     rng = np.random.default_rng(3)
     theta = np.concatenate([rng.normal(gm.prior[0].mu, 20.0, size=180),
-                            [0.3, 0.05, 0.011, 1.0, 5.0, 40.0, 75.0, -0.02, -0.5, -3.0, -16.0, -60.0]]).reshape(-1, 1)
+                            [0.3, 0.05, 0.011, 1.0, 5.0, 40.0, 75.0, -0.02, -0.5, -3.0, -16.0, -60.0,
+                             # growing trajectories (simulate.cuh: scaled for 30 < G <= 80, time-reversed exponential above)
+                             -0.3, -0.25, -0.2, -0.15, -0.126, -0.124, -0.1, -0.05, -0.03]]).reshape(-1, 1)
     d_or, s_or = cport.abc_distances(om, theta, seed=9, generation=1, return_stats=True)
     d, s = gm.gpu_model(ctx).distances(theta, seed=9, generation=1, return_stats=True)
     fin = np.isfinite(d_or)
