@@ -8,6 +8,15 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 from oracle import abc as oabc, cport, models as om, ou as oou
 pkg = ge.load_package()
+
+
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    return _tuning.from_env(ctx or pkg.default_context())
+
 ctx = pkg.default_context(0)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 30
@@ -36,7 +45,7 @@ for case in range(n_cases):
     if margin[: want["n_total"]].any():
         print(f"case {case}: a distance within tolerance of epsilon - skipped"); continue
     if got["n_total"] != want["n_total"] or got["n_accepted"] != want["n_accepted"]:
-        dgpu = mg.gpu_model(ctx).distances(props, seed=9, generation=case)
+        dgpu = mg.gpu_model(_tun(ctx)).distances(props, seed=9, generation=case)
         diff = np.nonzero((dgpu <= eps) != (d_ref <= eps))[0]
         if np.all(props[diff, 0] < 0) and np.all(np.isnan(dgpu[diff])):
             # documented: tau < 0 diverges; fp32 overflows to NaN (never accepted, as in the reference,

@@ -8,6 +8,15 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 from oracle import ou as oou, cport, models as om
 pkg = ge.load_package()
+
+
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    return _tuning.from_env(ctx or pkg.default_context())
+
 ctx = pkg.default_context(0)
 dt = 0.002
 for n_t, n_trials, n_lags in [(7722, 8, 100), (7722, 64, 100), (7722, 64, 400), (7722, 64, 1208), (5000, 50, 414), (5000, 200, 414), (2000, 500, 100)]:
@@ -18,7 +27,7 @@ for n_t, n_trials, n_lags in [(7722, 8, 100), (7722, 64, 100), (7722, 64, 400), 
     d, s = cport.abc_distances(m, theta, seed=3, generation=1, return_stats=True)
     for tc in ("0", "1"):
         os.environ["ITJL_ABC_TC"] = tc
-        g = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags).gpu_model(ctx)
+        g = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags).gpu_model(_tun(ctx))
         dg, sg = g.distances(theta, seed=3, generation=1, return_stats=True)
         e = sg - s
         print(f"n_t={n_t} trials={n_trials} L={n_lags} {g.kernel_info()[0]:13s} max|err|={np.abs(e).max():.2e} "

@@ -8,6 +8,15 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 from oracle import ou as oou, cport, models as om
 pkg = ge.load_package()
+
+
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    return _tuning.from_env(ctx or pkg.default_context())
+
 ctx = pkg.default_context(0)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 30
@@ -42,7 +51,7 @@ for case in range(n_cases):
                 mo = om.one_timescale_and_osc_model(data, t, prior=po, summary_method=sm)
                 mg = pkg.one_timescale_and_osc_model(data, t, "abc", prior=pp, summary_method=sm)
                 tol = 2e-5 if sm == "acf" else 1e-5; rel = sm == "psd"
-        g = mg.gpu_model(ctx)
+        g = mg.gpu_model(_tun(ctx))
         d_or, s_or = cport.abc_distances(mo, theta, seed=4, generation=2, return_stats=True)
         d, s = g.distances(theta, seed=4, generation=2, return_stats=True)
     except Exception as e:                                    # noqa: BLE001 - diagnostic: report and go on

@@ -15,6 +15,15 @@ torch.cuda.set_device(local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pkg = ge.load_package()
+
+
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    return _tuning.from_env(ctx or pkg.default_context())
+
 from importlib import import_module
 distributed = import_module("itjl_b200.distributed")
 from oracle import ou as oou
@@ -27,7 +36,7 @@ for n_t, n_trials, n_lags in [(5000, 10, None), (3000, 4, 700)]:
     model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags)
     scorer = distributed.gpu_sharded_scorer(model, ctx=ctx, seed=3)
     props = np.random.default_rng(1).uniform(0.05, 5.0, size=(4001, 1))
-    d_all = model.gpu_model(ctx).distances(props, seed=3, generation=2)           # every rank: the whole batch on its own GPU
+    d_all = model.gpu_model(_tun(ctx)).distances(props, seed=3, generation=2)           # every rank: the whole batch on its own GPU
     eps = float(np.sort(d_all)[400] * 0.5 + np.sort(d_all)[401] * 0.5)
     sharded = pkg.basic_abc(model, eps, 4001, 333, scorer=scorer, proposals=props, generation=2)
     single = pkg.basic_abc(model, eps, 4001, 333, proposals=props, seed=3, generation=2, ctx=ctx)

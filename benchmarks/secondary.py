@@ -16,6 +16,15 @@ import __graft_entry__ as ge  # noqa: E402
 MEASURED_HBM_GBS = 6453.1
 
 
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    import __graft_entry__ as _ge
+    return _tuning.from_env(ctx or _ge.load_package().default_context())
+
+
 def ou_data(pkg, tau, dt, n_t, n_trials, seed):
     return pkg.generate_ou_process(tau, 1.0, dt, n_t * dt, n_trials, seed=seed)
 
@@ -45,7 +54,7 @@ def bench_acw(pkg, ctx, kind, reps=5):
 
 
 def bench_distances(pkg, ctx, model, n_particles, label, reps=3):
-    gm = model.gpu_model(ctx)
+    gm = model.gpu_model(_tun(ctx))
     fl, spp = gm.work()
     rng = np.random.default_rng(1)
     theta = np.stack([np.asarray(p.rand(rng, n_particles)) for p in model.prior], axis=1)

@@ -11,6 +11,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    import __graft_entry__ as _ge
+    return _tuning.from_env(ctx or _ge.load_package().default_context())
+
+
 def child(mode, n_particles, tag):
     os.environ["ITJL_ABC_TC"] = mode
     import __graft_entry__ as ge
@@ -19,7 +28,7 @@ def child(mode, n_particles, tag):
     ctx = pkg.default_context(0)
     data, t = bench.observed_data_host()
     model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)])
-    gm = model.gpu_model(ctx)
+    gm = model.gpu_model(_tun(ctx))
     rng = np.random.default_rng(3)
     theta = rng.uniform(0.05, 5.0, size=(n_particles, 1))
     # oracle comparison with injected noise on 6 particles (incl. long and short timescales)

@@ -7,10 +7,19 @@ os.environ["ITJL_ABC_TC"] = "1"
 import __graft_entry__ as ge
 import bench
 pkg = ge.load_package()
+
+
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    return _tuning.from_env(ctx or pkg.default_context())
+
 ctx = pkg.default_context(0)
 data, t = bench.observed_data_host()
 model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)])
-g = model.gpu_model(ctx)
+g = model.gpu_model(_tun(ctx))
 rng = np.random.default_rng(7)
 theta = rng.uniform(0.05, 5.0, size=(1184, 1))
 a = g.distances(theta, seed=21, generation=4)
@@ -27,7 +36,7 @@ print("after stats call, first 300: n diff", int((a[:300] != c).sum()))
 from oracle import ou as oou
 data2 = oou.generate_ou_process(0.3, 1.0, 0.002, 10.0, 50, seed=3, n_t=5000)
 m2 = pkg.one_timescale_model(data2, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=414)
-g2 = m2.gpu_model(ctx)
+g2 = m2.gpu_model(_tun(ctx))
 x1, s1 = g2.distances(theta, seed=21, generation=4, return_stats=True)
 x2 = g2.distances(theta[:300], seed=21, generation=4)
 d = x1[:300] != x2

@@ -7,6 +7,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    import __graft_entry__ as _ge
+    return _tuning.from_env(ctx or _ge.load_package().default_context())
+
+
 def child(tag):
     import __graft_entry__ as ge
     import bench
@@ -14,7 +23,7 @@ def child(tag):
     ctx = pkg.default_context(0)
     data, t = bench.observed_data_host()
     model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)])
-    g = model.gpu_model(ctx)
+    g = model.gpu_model(_tun(ctx))
     theta = np.random.default_rng(7).uniform(0.05, 5.0, size=(1184, 1))
     d, s = g.distances(theta, seed=21, generation=4, return_stats=True)
     np.save(f"gpurun_out/tc_err_{tag}.npy", s)

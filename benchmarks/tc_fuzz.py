@@ -9,6 +9,15 @@ import __graft_entry__ as ge
 from oracle import ou as oou
 
 pkg = ge.load_package()
+
+
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    return _tuning.from_env(ctx or pkg.default_context())
+
 ctx = pkg.default_context(0)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 40
@@ -30,7 +39,7 @@ for case in range(n_cases):
     for tc in ("1", "0"):
         os.environ["ITJL_ABC_TC"] = tc
         try:
-            g = mk(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags).gpu_model(ctx)
+            g = mk(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags).gpu_model(_tun(ctx))
         except pkg.ItjlError as e:
             res[tc] = None; print(f"case {case}: n_t={n_t} trials={n_trials} lags={n_lags} missing={missing} TC={tc}: {e}"); continue
         theta = np.random.default_rng(case).uniform(0.005 if small else 0.05, 5.0, size=(8, 1))

@@ -11,6 +11,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    import __graft_entry__ as _ge
+    return _tuning.from_env(ctx or _ge.load_package().default_context())
+
+
 def child(n_lags, n_particles):
     import __graft_entry__ as ge
     import bench
@@ -18,7 +27,7 @@ def child(n_lags, n_particles):
     ctx = pkg.default_context(0)
     data, t = bench.observed_data_host()
     model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags)
-    gm = model.gpu_model(ctx)
+    gm = model.gpu_model(_tun(ctx))
     rng = np.random.default_rng(3)
     theta = rng.uniform(0.05, 5.0, size=(n_particles, 1))
     gm.distances(theta[:296], seed=9, generation=1)

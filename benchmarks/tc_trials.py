@@ -6,6 +6,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _tun(ctx=None):
+    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
+    import os as _os, sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import _tuning
+    import __graft_entry__ as _ge
+    return _tuning.from_env(ctx or _ge.load_package().default_context())
+
+
 def child(n_trials, n_lags, n_particles):
     import __graft_entry__ as ge
     from oracle import ou as oou
@@ -14,7 +23,7 @@ def child(n_trials, n_lags, n_particles):
     dt, n_t = 0.002, 5000
     data = oou.generate_ou_process(0.3, 1.0, dt, n_t * dt, n_trials, seed=3, n_t=n_t)
     m = pkg.one_timescale_model(data, dt * np.arange(1, n_t + 1), "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags)
-    g = m.gpu_model(ctx)
+    g = m.gpu_model(_tun(ctx))
     theta = np.random.default_rng(0).uniform(0.05, 5.0, size=(n_particles, 1))
     g.distances(theta[:296], seed=1, generation=1)
     ctx.timing_reset()

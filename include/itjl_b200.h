@@ -18,7 +18,11 @@
  *     dims = 2).
  *   - fp64 at the boundary; fp32 arithmetic inside the fused simulate+summary kernels,
  *     fp64 inside the acw kernels (bit-exact crossing indices against an fp64 reference).
- *   - one context = one GPU + one stream; a context is not re-entrant (serialise calls).
+ *   - one context = one GPU + one stream (or, from itjl_ctx_create_multi, one per GPU of the box); every call
+ *     that takes a context or one of its models holds the context's lock for its duration, so a context can
+ *     be shared between host threads: concurrent calls are serialised, not undefined.
+ *   - the library never reads the environment: everything that changes which kernel runs or how it rounds is
+ *     in itjl_tuning, per context.
  *   - a non-finite simulated trajectory yields distance = NaN (the observable contract of
  *     src/utils/ou_process.jl:56-61 + src/core/abc.jl:185).
  */
@@ -50,10 +54,53 @@ enum { ITJL_UPDATE_EXACT = 0, ITJL_UPDATE_EM = 1 };
 /* acw type mask bits (src/core/acw.jl:132, acf_acwtypes) */
 enum { ITJL_ACW0 = 1, ITJL_ACW50 = 2, ITJL_ACWEULER = 4, ITJL_AUC = 8, ITJL_TAU = 16 };
 
+/* ---- tuning ------------------------------------------------------------------------ */
+/* Per-context knobs (itjl_tuning_default gives the values below).  They replace the ITJL_* environment
+ * switches of the first version: a model reads them once, in itjl_model_create. */
+typedef struct {
+    int32_t abc_tc;          /* fused ACF kernel: -1 automatic (tensor-core kernel k_abc_acf_tc when the shape has a plan
+                                AND its predicted error is within tc_error_bound, else the CUDA-core kernel k_abc_acf);
+                                0 always k_abc_acf (fp32 FFMA lag sums: the exact-parity switch); 1 always k_abc_acf_tc
+                                (itjl_model_create fails when the shape has no plan) */
+    int32_t tc_terms;        /* 0 automatic (from the error model); 1 / 2 / 3 product terms of the fp16 hi/lo split */
+    int32_t tc_tail_max;     /* -1 default (15): lags beyond a tensor-memory plan summed by the FFMA tail (<= 60) */
+    int32_t tc_groups;       /* 0 automatic; 1..4 simulate groups */
+    int32_t tc_seg_trials;   /* 0 automatic; trials per accumulator segment (drain) */
+    int32_t tc_bias;         /* 1 (default): undo the accumulator's round-toward-zero to first order; 0 off */
+    int32_t abc_threads;     /* 0 automatic; 128 / 256 threads per CTA of k_abc_acf */
+    int32_t abc_bufs;        /* 0 automatic; 1 / 2 trial buffers of k_abc_acf */
+    int32_t acw_stream;      /* 1 (default): acw() starts with the one-read streaming pass; 0: shared-memory kernel only */
+    int32_t acw_waves;       /* 0 automatic; time segments of the streaming pass sized for this many waves of CTAs */
+    int32_t pinned_upload;   /* 1 (default): large host <-> device copies go through the pinned staging ring */
+    int32_t copy_threads;    /* 0 automatic (half the hardware threads, at most 8); host threads feeding that ring */
+    int32_t pmc_fp32;        /* -1 automatic (fp32 pair sums above 1e8 pairs); 0 always fp64; 1 always fp32 */
+    int32_t reserved;
+    double tc_error_bound;   /* 5e-6: bound on the predicted |error| of a trial-mean ACF value of k_abc_acf_tc */
+} itjl_tuning;
+int itjl_tuning_default(itjl_tuning* out);
+int itjl_ctx_set_tuning(itjl_ctx* ctx, const itjl_tuning* t);
+int itjl_ctx_get_tuning(const itjl_ctx* ctx, itjl_tuning* out);
+
 /* ---- library / context ------------------------------------------------------------ */
 const char* itjl_version(void);
 int itjl_device_count(int* n_out);
 int itjl_ctx_create(int device, itjl_ctx** ctx_out);
+/* One process driving n_dev GPUs (what a Julia host gets): one sub-context and stream per device and an NCCL
+ * communicator over them (ncclCommInitAll; libnccl.so.2 is loaded on first use, the library itself does not
+ * link it).  itjl_model_create / itjl_abc_distances / itjl_abc_generation / itjl_pmc_weights on such a
+ * context shard the particles over the devices as contiguous ranges of the global particle index, all-gather
+ * the per-particle results device to device and return them exactly as the single-GPU calls do (the Philox
+ * streams are keyed on the global index: results do not depend on n_dev).  Everything else runs on the
+ * first device.  dev_ids = NULL means devices 0 .. n_dev-1. */
+int itjl_ctx_create_multi(int n_dev, const int* dev_ids, itjl_ctx** ctx_out);
+/* One process per GPU (torchrun / MPI): rank 0 calls itjl_comm_unique_id, ships the 128 bytes to every rank by
+ * its own means, then every rank attaches its single-device context to the communicator (ncclCommInitRank,
+ * collective).  The sharded calls listed above are then COLLECTIVE: every rank passes the same arguments
+ * and receives the full result. */
+int itjl_comm_unique_id(void* id_out_128_bytes);
+int itjl_ctx_attach_comm(itjl_ctx* ctx, int rank, int world, const void* id_128_bytes);
+/* rank / world size of the context's communicator (0 / 1 without one) and the number of devices this process drives */
+int itjl_ctx_world(const itjl_ctx* ctx, int* rank, int* world, int* n_local);
 int itjl_ctx_destroy(itjl_ctx* ctx);
 const char* itjl_last_error(const itjl_ctx* ctx);
 int itjl_ctx_synchronize(itjl_ctx* ctx);
@@ -123,6 +170,21 @@ int itjl_abc_distances_dev(itjl_model* model, const double* theta_dev, int64_t n
                            int32_t n_theta, uint64_t seed, uint64_t generation,
                            int64_t particle_offset, double* dist_dev);
 
+/* ---- between generations: PMC weights and covariance ---------------------------------- */
+/* calc_weights(theta_prev, theta, tau_squared, weights, prior)  (src/core/abc.jl:520-567, the multi-parameter
+ * branch :547-566, which is also the intended formula of the 1-parameter branch):
+ *     w_i = prior_pdf[i] / sum_j weights_prev[j] N(theta[i, :]; theta_prev[j, :], tau_squared),
+ * normalised to sum 1 when `normalize` != 0.  theta_prev (n_prev x n_theta) and theta (n x n_theta) are
+ * column-major, tau_squared (n_theta x n_theta, symmetric positive definite), n_theta <= 4.  prior_pdf[i] =
+ * prod_k pdf(prior[k], theta[i, k]) is evaluated by the caller (Distributions.pdf on the Julia side): the
+ * library knows no distribution families.  n * n_prev Gaussian evaluations on the device (k_pmc_mixture);
+ * on a multi-GPU context the rows i are sharded and the result all-gathered. */
+int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, const double* theta, int64_t n,
+                     int32_t n_theta, const double* tau_squared, const double* weights_prev,
+                     const double* prior_pdf, int32_t normalize, double* weights_out);
+/* weighted_covar(x, w)  (src/core/abc.jl:582-613): x (n x n_theta) column-major, cov_out (n_theta x n_theta). */
+int itjl_weighted_covar(itjl_ctx* ctx, const double* x, int64_t n, int32_t n_theta, const double* w, double* cov_out);
+
 /* Algorithmic work of one itjl_abc_distances call, for roofline accounting:
  * flops_per_sample = 2*n_lags + 8 for the direct lag-sum kernels. */
 int itjl_model_work(const itjl_model* model, double* flops_per_sample, int64_t* samples_per_particle);
@@ -137,6 +199,12 @@ int itjl_model_kernel_info(const itjl_model* model, char* name_out, double* tens
  * per batch: lag windows of 385 lags beyond the first 449), 0}, or ITJL_ERR_ARG when
  * the shape is outside the kernel's plans (the CUDA-core kernel k_abc_acf then runs). */
 int itjl_tc_plan(int64_t n_t, int64_t n_lags, int64_t n_trials, int32_t max_smem_optin, int32_t sm_count, int32_t* out);
+/* The error model behind abc_tc = -1 (host only): predicted bound on |error| of a trial-mean ACF value of
+ * k_abc_acf_tc with `n_terms` product terms for a model of n_trials x n_t samples, `seg_rows` 128-sample rows per
+ * accumulator segment and a fraction `mask_frac` of masked samples (missing-data models; `mean_ratio` =
+ * data_mean / data_sd of the oscillation + missing-data model, whose masked samples sit at that offset, else 0).  DESIGN.md section 4 derives it;
+ * tests/test_gpu_tc.py holds the kernel to it. */
+double itjl_tc_predicted_error(int64_t n_t, int64_t n_trials, int32_t n_terms, int32_t seg_rows, double mask_frac, double mean_ratio);
 
 /* ---- OU generator ----------------------------------------------------------------- */
 /* generate_ou_process(tau, true_D, dt, duration, num_trials; standardize)
@@ -158,6 +226,13 @@ int itjl_generate_ou_osc(itjl_ctx* ctx, double tau, double freq, double coeff, d
 /* comp_ac_fft(data; dims = 2, n_lags)  (src/stats/summary.jl:46-63, 79-89) computed as the
  * mathematically identical time-domain lag sum.  out: (n_slices x n_lags) column-major. */
 int itjl_acf(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t n_lags, double* out);
+/* Strided variants: element (slice s, time t) lives at data[s * slice_stride + t * time_stride]
+ * (strides in elements, > 0).  slice_stride = 1, time_stride = n_slices is the layout of the calls above
+ * (`dims = 2` of a Julia matrix); slice_stride = n_t, time_stride = 1 is `dims = 1` (time down the columns):
+ * the matrix is uploaded as it lies and transposed on the device, no host copy.  `missing` != 0 selects
+ * comp_ac_time_missing. */
+int itjl_acf_strided(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t slice_stride,
+                     int64_t time_stride, int64_t n_lags, int32_t missing, double* out);
 /* comp_ac_time_missing(data; dims = 2, n_lags)  (src/stats/summary.jl:455-496); NaN = missing. */
 int itjl_acf_missing(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t n_lags,
                      double* out);
@@ -182,6 +257,20 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
              int32_t* k0, int32_t* k50, int32_t* ke, double* auc, double* tau,
              double* acf_out, int64_t acf_capacity);
 
+/* itjl_acw on a strided matrix (see itjl_acf_strided). */
+int itjl_acw_strided(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t slice_stride,
+                     int64_t time_stride, double fs, uint32_t typemask, int32_t average_over_trials,
+                     int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke, double* auc, double* tau,
+                     double* acf_out, int64_t acf_capacity);
+/* Device-resident data: upload once (itjl_data_upload keeps the matrix on the device, in the context), then
+ * any number of itjl_acw_resident calls run without host -> device traffic - what a Julia caller doing repeated
+ * acw() calls on the same recording pays.  itjl_data_upload takes the same strides as above. */
+int itjl_data_upload(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t slice_stride,
+                     int64_t time_stride);
+int itjl_acw_resident(itjl_ctx* ctx, double fs, uint32_t typemask, int32_t average_over_trials,
+                      int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke, double* auc, double* tau,
+                      double* acf_out, int64_t acf_capacity);
+
 /* fit_expdecay(lags, acf; dims = 2) with lags = (0:n_lags-1)*dt  (src/utils/utils.jl:113-138):
  * acf is (n_rows x n_lags) column-major; tau_out has n_rows entries. */
 int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt,
@@ -195,6 +284,9 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out);
  * measured with CUDA events on the context stream around each dominant-kernel launch. */
 int itjl_ctx_timing_reset(itjl_ctx* ctx);
 int itjl_ctx_timing_get(itjl_ctx* ctx, int64_t* n_launches, double* total_ms);
+/* stop timing: launches are asynchronous again (while timing is on, every timed launch is followed by an
+ * event synchronisation, itjl_abc_distances_dev included) */
+int itjl_ctx_timing_stop(itjl_ctx* ctx);
 /* Tensor-core self-test: loads `image` (n_bytes of fp16 data, multiple of 16, <= 200 KiB) into shared
  * memory, issues `n_ops` tcgen05.mma (M = 128, kind::f16) described by ops[4*i .. 4*i+3] =
  * {A byte offset, B byte offset, TMEM column of D, accumulate flag} with the given no-swizzle

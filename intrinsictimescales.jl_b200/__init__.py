@@ -13,7 +13,7 @@ from ._lib import Context, ItjlError, default_context, library_path
 from .abc import (ABCResults, abc_results, basic_abc, calc_weights, compute_adaptive_alpha,
                   draw_theta_pmc, effective_sample_size, find_MAP, get_param_dict_abc, int_fit,
                   pmc_abc, posterior_predictive, select_epsilon, weighted_covar)
-from .acw import ACWResults, acw, possible_acwtypes
+from .acw import ACWResults, DeviceData, acw, possible_acwtypes, upload
 from .models import (Normal, Uniform, TimescaleModel, check_model_inputs, distance_function,
                      draw_theta, generate_data, generate_data_and_reduce, one_timescale_and_osc_model,
                      one_timescale_and_osc_with_missing_model,

@@ -33,6 +33,15 @@ class ModelDesc(ctypes.Structure):
                 ("freq_bins", ctypes.c_void_p)]
 
 
+class Tuning(ctypes.Structure):
+    """itjl_tuning (include/itjl_b200.h): per-context knobs; the library never reads the environment."""
+    _fields_ = [("abc_tc", ctypes.c_int32), ("tc_terms", ctypes.c_int32), ("tc_tail_max", ctypes.c_int32),
+                ("tc_groups", ctypes.c_int32), ("tc_seg_trials", ctypes.c_int32), ("tc_bias", ctypes.c_int32),
+                ("abc_threads", ctypes.c_int32), ("abc_bufs", ctypes.c_int32), ("acw_stream", ctypes.c_int32),
+                ("acw_waves", ctypes.c_int32), ("pinned_upload", ctypes.c_int32), ("copy_threads", ctypes.c_int32),
+                ("pmc_fp32", ctypes.c_int32), ("reserved", ctypes.c_int32), ("tc_error_bound", ctypes.c_double)]
+
+
 KIND_OU, KIND_OU_OSC = 0, 1
 SUMMARY_ACF, SUMMARY_ACF_MISSING, SUMMARY_PSD = 0, 1, 2
 DIST_LINEAR, DIST_LOG = 0, 1
@@ -74,6 +83,22 @@ SIGNATURES = {
     "itjl_ctx_timing_reset": (ctypes.c_int, [_vp]),
     "itjl_ctx_timing_get": (ctypes.c_int, [_vp, _vp, _vp]),
     "itjl_tc_probe": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i32, _u32, _u32, _u32, _vp]),
+    "itjl_tuning_default": (ctypes.c_int, [_vp]),
+    "itjl_ctx_set_tuning": (ctypes.c_int, [_vp, _vp]),
+    "itjl_ctx_get_tuning": (ctypes.c_int, [_vp, _vp]),
+    "itjl_ctx_create_multi": (ctypes.c_int, [ctypes.c_int, _vp, _vp]),
+    "itjl_comm_unique_id": (ctypes.c_int, [_vp]),
+    "itjl_ctx_attach_comm": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "itjl_ctx_world": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "itjl_pmc_weights": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "itjl_weighted_covar": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "itjl_tc_predicted_error": (_f64, [_i64, _i64, _i32, _i32, _f64, _f64]),
+    "itjl_acf_strided": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
+    "itjl_acw_strided": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f64, _u32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _i64]),
+    "itjl_data_upload": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64]),
+    "itjl_acw_resident": (ctypes.c_int, [_vp, _f64, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "itjl_ctx_timing_stop": (ctypes.c_int, [_vp]),
 }
 
 
@@ -115,14 +140,72 @@ def f64(a, order="C"):
 
 
 class Context:
-    """One GPU + one stream (itjl_ctx).  Not re-entrant."""
+    """One GPU + one stream (itjl_ctx), or - `devices=[...]` - one process driving several GPUs with the particles
+    of a generation sharded inside the library (itjl_ctx_create_multi).  Calls on one context are serialised by
+    the library's own lock."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self._h = ctypes.c_void_p()
-        rc = lib().itjl_ctx_create(int(device), ctypes.byref(self._h))
+        if devices is not None:
+            ids = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = lib().itjl_ctx_create_multi(len(devices), ids, ctypes.byref(self._h))
+            device = devices[0]
+        else:
+            rc = lib().itjl_ctx_create(int(device), ctypes.byref(self._h))
         if rc != 0:
             raise ItjlError(rc, lib().itjl_last_error(None).decode())
         self.device = int(device)
+        import weakref
+        self._models = weakref.WeakSet()        # itjl_model handles created on this context: destroyed before it
+
+    # ---- tuning (itjl_tuning) ----------------------------------------------------------
+    def get_tuning(self):
+        t = Tuning()
+        self.check(lib().itjl_ctx_get_tuning(self._h, ctypes.byref(t)))
+        return t
+
+    def set_tuning(self, **kw):
+        """Change knobs of itjl_tuning by name, e.g. set_tuning(abc_tc=0).  A model reads them when it is created."""
+        t = self.get_tuning()
+        for k, v in kw.items():
+            if k not in dict(Tuning._fields_):
+                raise KeyError(f"unknown tuning field {k!r}")
+            setattr(t, k, v)
+        self.check(lib().itjl_ctx_set_tuning(self._h, ctypes.byref(t)))
+
+    def reset_tuning(self):
+        t = Tuning()
+        lib().itjl_tuning_default(ctypes.byref(t))
+        self.check(lib().itjl_ctx_set_tuning(self._h, ctypes.byref(t)))
+
+    def tuned(self, **kw):
+        """Context manager: the given knobs inside the block, the previous values after it."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            old = self.get_tuning()
+            self.set_tuning(**kw)
+            try:
+                yield self
+            finally:
+                self.check(lib().itjl_ctx_set_tuning(self._h, ctypes.byref(old)))
+        return cm()
+
+    # ---- communicator ------------------------------------------------------------------
+    def attach_comm(self, rank, world, unique_id):
+        """Join an NCCL communicator of `world` processes (one GPU each): collective (ncclCommInitRank)."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self.check(lib().itjl_ctx_attach_comm(self._h, int(rank), int(world), buf))
+
+    def world(self):
+        """(rank, world size, devices driven by this process)."""
+        r, w, n = ctypes.c_int(0), ctypes.c_int(1), ctypes.c_int(1)
+        self.check(lib().itjl_ctx_world(self._h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(n)))
+        return r.value, w.value, n.value
+
+    def timing_stop(self):
+        self.check(lib().itjl_ctx_timing_stop(self._h))
 
     def check(self, rc):
         if rc != 0:
@@ -163,6 +246,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for m in list(getattr(self, "_models", ())):     # a model holds a pointer to its context
+                m.close()
             lib().itjl_ctx_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -171,6 +256,21 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+    buf = ctypes.create_string_buffer(128)
+    rc = lib().itjl_comm_unique_id(buf)
+    if rc != 0:
+        raise ItjlError(rc, lib().itjl_last_error(None).decode())
+    return buf.raw
+
+
+def tc_predicted_error(n_t, n_trials, n_terms, seg_rows, mask_frac=0.0, mean_ratio=0.0):
+    """The error model of the tensor-core ACF kernel (itjl_tc_predicted_error; host only)."""
+    return float(lib().itjl_tc_predicted_error(int(n_t), int(n_trials), int(n_terms), int(seg_rows), float(mask_frac),
+                                               float(mean_ratio)))
 
 
 _default_ctx = {}

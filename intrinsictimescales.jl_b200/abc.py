@@ -181,40 +181,41 @@ def select_epsilon(distances, current_epsilon, target_acc_rate=0.01, current_acc
     return current_epsilon            # reference: UndefVarError when the rate is exactly 0
 
 
-def calc_weights(theta_prev, theta, tau_squared, weights, prior, block=2048):
+def calc_weights(theta_prev, theta, tau_squared, weights, prior, ctx=None, normalize=True):
+    """calc_weights (abc.jl:520-567): w_i ~ prod_k pdf(prior_k, theta_ik) / sum_j w_j N(theta_i; theta_prev_j, tau^2).
+    The prior densities are evaluated here (the host owns the distribution objects, as Julia does); the
+    n x n_prev Gaussian mixture sum runs on the device (itjl_pmc_weights, k_pmc_mixture) - on a multi-GPU
+    context sharded over the rows and all-gathered."""
+    import ctypes
     theta_prev = np.atleast_2d(np.asarray(theta_prev, dtype=np.float64))
     theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
     if theta_prev.shape[0] == 1 and theta_prev.shape[1] != len(prior):
         theta_prev = theta_prev.T
     if theta.shape[0] == 1 and theta.shape[1] != len(prior):
         theta = theta.T
-    cov = np.atleast_2d(np.asarray(tau_squared, dtype=np.float64))
-    w = np.asarray(weights, dtype=np.float64)
     k = theta.shape[1]
-    prec = np.linalg.inv(cov)
-    norm = 1.0 / math.sqrt((2.0 * math.pi) ** k * np.linalg.det(cov))
+    cov = np.asfortranarray(np.atleast_2d(np.asarray(tau_squared, dtype=np.float64)))
+    w = np.ascontiguousarray(weights, dtype=np.float64)
     pri = np.ones(theta.shape[0])
     for j, p in enumerate(prior):
         pri *= p.pdf(theta[:, j])
-    new = np.empty(theta.shape[0])
-    for s in range(0, theta.shape[0], block):
-        diff = theta[s:s + block, None, :] - theta_prev[None, :, :]
-        quad = np.einsum("ijk,kl,ijl->ij", diff, prec, diff)
-        new[s:s + block] = pri[s:s + block] / ((np.exp(-0.5 * quad) * norm) @ w)
-    return new / new.sum()
+    pri = np.ascontiguousarray(pri)
+    tp, th = np.asfortranarray(theta_prev), np.asfortranarray(theta)
+    out = np.empty(theta.shape[0], dtype=np.float64)
+    ctx = ctx or _lib.default_context()
+    ctx.check(_lib.lib().itjl_pmc_weights(ctx.handle, _lib.ptr(tp), tp.shape[0], _lib.ptr(th), th.shape[0], int(k),
+                                          _lib.ptr(cov), _lib.ptr(w), _lib.ptr(pri), int(bool(normalize)), _lib.ptr(out)))
+    return out
 
 
-def weighted_covar(x, w):
-    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
-    w_norm = np.asarray(w, dtype=np.float64) / np.sum(w)
-    sumw = w_norm.sum()
-    if not math.isclose(sumw, 1.0, rel_tol=1e-10):
-        return np.zeros((x.shape[1], x.shape[1]))
-    sum2 = np.sum(w_norm ** 2)
-    xbar = (w_norm[:, None] * x).sum(axis=0)
-    xc = x - xbar
-    covar = (xc * w_norm[:, None]).T @ xc
-    return covar * sumw / (sumw * sumw - sum2)
+def weighted_covar(x, w, ctx=None):
+    """weighted_covar (abc.jl:582-613) on the device (itjl_weighted_covar)."""
+    x = np.asfortranarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = np.empty((x.shape[1], x.shape[1]), dtype=np.float64, order="F")
+    ctx = ctx or _lib.default_context()
+    ctx.check(_lib.lib().itjl_weighted_covar(ctx.handle, _lib.ptr(x), x.shape[0], x.shape[1], _lib.ptr(w), _lib.ptr(out)))
+    return np.ascontiguousarray(out)
 
 
 def effective_sample_size(w):
@@ -253,8 +254,14 @@ def pmc_abc(model, epsilon_0=1.0, max_iter=10000, min_accepted=100, steps=10, sa
             quantile_init=50.0, acc_rate_buffer=0.1, alpha_max=0.9, alpha_min=0.1, acc_rate_far=2.0,
             acc_rate_close=0.2, alpha_far_mult=1.5, alpha_close_mult=0.5, convergence_window=3,
             theta_rtol=1e-2, theta_atol=1e-3, rng=None, seed=0, ctx=None, scorer=None,
-            return_record=False, **_unused):
+            return_record=False, calc_weights_fn=None, weighted_covar_fn=None, **_unused):
+    """pmc_abc (abc.jl:287-502).  `scorer`, `calc_weights_fn(theta_prev, theta, tau_squared, weights, prior)` and
+    `weighted_covar_fn(x, w)` are injection points for host-logic tests that run without a GPU; by default the
+    particles are scored by the fused kernels and the weights / covariance by the device kernels of this
+    module - there is no CPU implementation of either in the product."""
     rng = rng or np.random.default_rng(seed)
+    cw = calc_weights_fn or (lambda a, b, c, d, e: calc_weights(a, b, c, d, e, ctx=ctx))
+    wc = weighted_covar_fn or (lambda x, w: weighted_covar(x, w, ctx=ctx))
     eps_kw = dict(target_acc_rate=target_acc_rate, distance_max=distance_max,
                   quantile_lower=quantile_lower, quantile_upper=quantile_upper,
                   quantile_init=quantile_init, acc_rate_buffer=acc_rate_buffer, alpha_max=alpha_max,
@@ -277,9 +284,14 @@ def pmc_abc(model, epsilon_0=1.0, max_iter=10000, min_accepted=100, steps=10, sa
                                seed=seed, generation=i_step, ctx=ctx, scorer=scorer)
             epsilon = select_epsilon(result["distances"], epsilon, **eps_kw)
             theta = result["theta_accepted"]
-            tau_squared = 2.0 * np.atleast_2d(np.cov(theta, rowvar=False)) + jitter * np.eye(ndim)
-            weights = np.full(theta.shape[0], 1.0 / theta.shape[0])
-            eff = effective_sample_size(weights)
+            if theta.shape[0] >= 2:
+                tau_squared = 2.0 * np.atleast_2d(np.cov(theta, rowvar=False)) + jitter * np.eye(ndim)
+            else:
+                # nothing (or one particle) accepted: the reference's cov() of that is NaN and its
+                # fill(1 / 0, 0) an empty vector; it leaves through the minAccRate exit below
+                tau_squared = np.full((ndim, ndim), np.nan)
+            weights = np.full(theta.shape[0], 1.0 / theta.shape[0]) if theta.shape[0] else np.zeros(0)
+            eff = effective_sample_size(weights) if theta.shape[0] else float("nan")
         else:
             prev = record[-1]
             result = basic_abc(model, epsilon, max_iter, min_accepted, pmc_mode=True,
@@ -291,9 +303,11 @@ def pmc_abc(model, epsilon_0=1.0, max_iter=10000, min_accepted=100, steps=10, sa
             if sample_only:
                 weights = np.zeros(0); tau_squared = np.zeros((0, 0))
             else:
-                weights = calc_weights(prev["theta_accepted"], theta, prev["tau_squared"],
-                                       prev["weights"], model.prior)
-                tau_squared = 2.0 * weighted_covar(theta, weights)
+                if theta.shape[0]:
+                    weights = cw(prev["theta_accepted"], theta, prev["tau_squared"], prev["weights"], model.prior)
+                    tau_squared = 2.0 * np.atleast_2d(wc(theta, weights))
+                else:
+                    weights = np.zeros(0); tau_squared = np.full((ndim, ndim), np.nan)
             current_acc_rate = result["n_accepted"] / result["n_total"]
             epsilon = select_epsilon(result["distances"], epsilon, current_acc_rate=current_acc_rate,
                                      iteration=i_step, total_iterations=steps, **eps_kw)

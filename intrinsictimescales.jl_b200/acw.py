@@ -30,6 +30,50 @@ class ACWResults:
     x_dim: Any
 
 
+class DeviceData:
+    """A (slices x time) matrix kept on the device by `upload(data, dims=...)`: repeated acw() calls on it
+    (different acwtypes, n_lags, averaging) pay no host -> device copy (itjl_data_upload / itjl_acw_resident).
+    Any other data call on the same context replaces it."""
+
+    def __init__(self, ctx, n_slices, n_t, other_shape, t_axis, was_vector):
+        self.ctx, self.n_slices, self.n_t = ctx, n_slices, n_t
+        self.other_shape, self.t_axis, self.was_vector = other_shape, t_axis, was_vector
+
+
+def _matrix_view(data, dims):
+    """(array to pass, n_slices, n_t, slice_stride, time_stride, other_shape, t_axis, was_vector): a 2-D input is
+    handed to the library as it lies in memory with its element strides (the device re-lays it: no host
+    transpose); N-d inputs are flattened to (slices x time) on the host in the reference's slice order."""
+    data = np.asarray(data, dtype=np.float64)
+    was_vector = data.ndim == 1
+    if was_vector:
+        data = data.reshape(1, -1)                              # acw.jl:122-125
+        dims = None
+    nd = data.ndim
+    if dims is None or dims == -1:
+        dims = nd
+    if not (isinstance(dims, (int, np.integer)) and 1 <= dims <= nd):
+        raise ValueError(f"dims must be a dimension of data (1 .. {nd}, or -1 for the last one), got {dims!r}")
+    t_axis = int(dims) - 1
+    other_shape = tuple(n for i, n in enumerate(data.shape) if i != t_axis)
+    if nd == 2 and (data.flags.c_contiguous or data.flags.f_contiguous) and data.size and min(data.shape) > 1:
+        s_axis = 1 - t_axis
+        es = data.itemsize
+        return (data, data.shape[s_axis], data.shape[t_axis], data.strides[s_axis] // es, data.strides[t_axis] // es,
+                other_shape, t_axis, was_vector)
+    # slices in the reference's order (column-major over the remaining dimensions), time last
+    d = np.asfortranarray(np.moveaxis(data, t_axis, -1).reshape((-1, data.shape[t_axis]), order="F"))
+    return d, d.shape[0], d.shape[1], 1, d.shape[0], other_shape, t_axis, was_vector
+
+
+def upload(data, dims=None, ctx=None):
+    """Put `data` on the device once; pass the returned DeviceData to acw() as often as needed."""
+    d, n_slices, n_t, ss, ts, other_shape, t_axis, was_vector = _matrix_view(data, dims)
+    ctx = ctx or _lib.default_context()
+    ctx.check(_lib.lib().itjl_data_upload(ctx.handle, _lib.ptr(d), n_slices, n_t, int(ss), int(ts)))
+    return DeviceData(ctx, n_slices, n_t, other_shape, t_axis, was_vector)
+
+
 def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
         average_over_trials=False, ctx=None):
     """Compute ACW measures of every slice of `data` along its time dimension.
@@ -55,24 +99,16 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     for t in acwtypes:
         if t not in _BITS:
             raise ValueError(f"Possible ACW types: {possible_acwtypes}, got {t!r}")
-    data = np.asarray(data, dtype=np.float64)
-    was_vector = data.ndim == 1
-    if was_vector:
-        data = data.reshape(1, -1)                              # acw.jl:122-125
-        dims = None
-    nd = data.ndim
-    if dims is None or dims == -1:
-        dims = nd
-    if not (isinstance(dims, (int, np.integer)) and 1 <= dims <= nd):
-        raise ValueError(f"dims must be a dimension of data (1 .. {nd}, or -1 for the last one), got {dims!r}")
-    t_axis = int(dims) - 1
-    other_shape = tuple(n for i, n in enumerate(data.shape) if i != t_axis)
-    if average_over_trials and nd != 2:
+    resident = isinstance(data, DeviceData)
+    if resident:
+        ctx = data.ctx
+        d, n_slices, n_t, ss, ts = None, data.n_slices, data.n_t, 1, data.n_slices
+        other_shape, t_axis, was_vector = data.other_shape, data.t_axis, data.was_vector
+    else:
+        d, n_slices, n_t, ss, ts, other_shape, t_axis, was_vector = _matrix_view(data, dims)
+        ctx = ctx or _lib.default_context()
+    if average_over_trials and len(other_shape) != 1:
         raise NotImplementedError("average_over_trials is implemented for (trials, time) matrices")
-    # slices in the reference's order (column-major over the remaining dimensions), time last
-    d = np.asfortranarray(np.moveaxis(data, t_axis, -1).reshape((-1, data.shape[t_axis]), order="F"))
-    n_slices, n_t = d.shape
-    ctx = ctx or _lib.default_context()
     mask = 0
     for t in acwtypes:
         mask |= _BITS[t]
@@ -91,10 +127,15 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
         cap = n_out * (int(n_lags) if n_lags is not None else n_t)
         acf_buf = np.empty(cap, dtype=np.float64)
     # always request acw0: the AUC window and the default n_lags derive from it
-    rc = _lib.lib().itjl_acw(ctx.handle, _lib.ptr(d), n_slices, n_t, float(fs), mask | _lib.ACW0,
-                             int(bool(average_over_trials)), ctypes.byref(nl), _lib.ptr(k0),
-                             _lib.ptr(k50), _lib.ptr(ke), _lib.ptr(auc), _lib.ptr(tau),
-                             _lib.ptr(acf_buf), cap)
+    if resident:
+        rc = _lib.lib().itjl_acw_resident(ctx.handle, float(fs), mask | _lib.ACW0, int(bool(average_over_trials)),
+                                          ctypes.byref(nl), _lib.ptr(k0), _lib.ptr(k50), _lib.ptr(ke), _lib.ptr(auc),
+                                          _lib.ptr(tau), _lib.ptr(acf_buf), cap)
+    else:
+        rc = _lib.lib().itjl_acw_strided(ctx.handle, _lib.ptr(d), n_slices, n_t, int(ss), int(ts),
+                                         float(fs), mask | _lib.ACW0, int(bool(average_over_trials)), ctypes.byref(nl),
+                                         _lib.ptr(k0), _lib.ptr(k50), _lib.ptr(ke), _lib.ptr(auc), _lib.ptr(tau),
+                                         _lib.ptr(acf_buf), cap)
     ctx.check(rc)
     n_lags_used = int(nl.value)
     dt = 1.0 / float(fs)

@@ -199,11 +199,11 @@ static int abc_acf_geometry_cfg(int n_t, int n_lags, int max_smem, int nt, int n
 
 // Default: 128-thread CTAs (up to 5 per SM: independent simulate / lag-sum phases interleave on
 // every SM sub-partition), one series buffer per CTA; 256 threads when there are more than 128
-// lag tiles.  ITJL_ABC_THREADS / ITJL_ABC_BUFS override for tuning.
-int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g) {
+// lag tiles.  itjl_tuning::abc_threads / abc_bufs override for tuning.
+int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g, const itjl_tuning* tun) {
     int nt = 128, n_bufs = 1;
-    if (const char* e = getenv("ITJL_ABC_THREADS")) nt = (atoi(e) == 256) ? 256 : 128;
-    if (const char* e = getenv("ITJL_ABC_BUFS")) n_bufs = (atoi(e) == 2) ? 2 : 1;
+    if (tun && tun->abc_threads) nt = (tun->abc_threads == 256) ? 256 : 128;
+    if (tun && tun->abc_bufs) n_bufs = (tun->abc_bufs == 2) ? 2 : 1;
     if ((n_lags + TK - 1) / TK > nt) nt = 256;
     int rc = abc_acf_geometry_cfg(n_t, n_lags, max_smem, nt, n_bufs, g);
     if (rc == -3 && n_bufs == 2) rc = abc_acf_geometry_cfg(n_t, n_lags, max_smem, nt, 1, g);

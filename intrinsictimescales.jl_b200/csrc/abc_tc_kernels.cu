@@ -440,13 +440,43 @@ static int tc_store_conflicts(int sbo_bytes, int chunk) {
 }
 
 // Geometry of the tensor-core kernel; returns 0 when the configuration is supported.
-int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g, int min_terms) {
+// ---- error model of the tensor-core lag sums -----------------------------------------------------------------
+// Bound on what the tensor-core lag sums ADD to the error of one trial-mean ACF value (values in [-1, 1]) over
+// the fp32 FFMA sums of the same simulated series, for a particle of N = n_trials * n_t samples.  (Both fused
+// kernels share the fp32 simulation, centring and conversion: up to ~5e-6 against the fp64 reference for
+// near-unit-root trials, tau >= T, ~1e-6 otherwise - measured, tests/test_gpu_tc.py; the total stays within the
+// 1e-5 of the contract when this bound is within the default 5e-6.)
+//   E_a  dropped cross terms of the fp16 hi/lo split.  x' = hi + lo with |lo| <= 2^-12 |x'|; a dropped term
+//        sum lo_t x'_{t+l} is a sum of N independent zero-mean residuals, in units of sum x'^2 = 1 per trial:
+//        rms kA sqrt(dropped terms) / sqrt(N), kA = 3.2e-4 (calibrated at C5, 1184 particles x 414 lags:
+//        rms 9.0e-7 with both cross terms dropped, maximum 4.7e-6).
+//   E_c  fp32 -> fp16 x 2 conversion and the fixed-point lag table: rms 2.5e-7.
+//   E_b  what the first-order correction of the accumulator's round-toward-zero leaves: <= 6e-10 per 128-sample
+//        row of a segment (1.2e-6 at 2000 rows, measured).
+//   E_m  missing-data models: the masked samples all carry ONE value v, so their rounding residual is common
+//        and every masked-masked product is off by the same relative 2^-11 (hi*hi only) or 2^-12 (one cross term
+//        kept); they contribute mask_frac * rho^2 to ac, rho^2 = n v^2 = (mean offset / std)^2 ~ 0.05 for the plain
+//        model, + (data_mean / data_sd)^2 for the oscillation model (whose masked samples sit at -data_mean).
+// bound = 4 sqrt(E_a^2 + E_c^2) + E_b + E_m   (4 sigma: the maximum over the ~1e5 .. 1e6 values of a test run).
+double abc_tc_predicted_error(int64_t n_t, int64_t n_trials, int n_terms, int seg_rows, double mask_frac, double mean_ratio) {
+    const double N = (double)n_t * (double)(n_trials > 0 ? n_trials : 1);
+    const int dropped = n_terms >= 3 ? 0 : 3 - n_terms;
+    const double e_a = 3.2e-4 * sqrt((double)dropped) / sqrt(N);
+    const double e_c = 2.5e-7;
+    const double e_b = 6e-10 * (double)seg_rows;
+    const double rho2 = 0.05 + mean_ratio * mean_ratio;
+    const double e_m = mask_frac * rho2 * (dropped == 2 ? 4.9e-4 : dropped == 1 ? 2.45e-4 : 1e-7);
+    return 4.0 * sqrt(e_a * e_a + e_c * e_c) + e_b + e_m;
+}
+
+int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g,
+                    const itjl_tuning* tun, double mask_frac, double mean_ratio, bool missing) {
     if (n_t < 16 || n_lags < 1 || n_lags > n_t) return -1;
     // FFMA tail lags beyond the tensor-memory plans.  The tail code handles up to 60 (four tiles of 16), but
     // only one tile pays: at C5 shape 2.8e11 samples/s with a 16-lag tail against 2.4e11 for a second lag
     // window, 2.3e11 / 1.7e11 with two / four tail tiles
     int max_tail = 15;
-    { const char* e_t = getenv("ITJL_TC_TAIL_MAX"); if (e_t && atoi(e_t) >= 0 && atoi(e_t) <= 60) max_tail = atoi(e_t); }   // tuning only
+    if (tun && tun->tc_tail_max >= 0 && tun->tc_tail_max <= 60) max_tail = tun->tc_tail_max;   // tuning only
     // n_lags 465 .. 1537: up to four launches (lag windows), each with the B operand 3 more rows down
     // window w >= 1 moves the B operand 3 w rows down and covers the lags [384 w, 384 w + 385)
     g->n_windows = n_lags > 449 + max_tail ? 1 + (n_lags - 385 + 383) / 384 : 1;
@@ -516,7 +546,7 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     }
     const size_t epi = (size_t)kTcLagTab * sizeof(int);
     int want_groups = n_trials < kTcMaxGroups ? (n_trials > 0 ? n_trials : 1) : kTcMaxGroups;   // no idle groups
-    { const char* e_g = getenv("ITJL_TC_GROUPS"); if (e_g && atoi(e_g) >= 1 && atoi(e_g) < want_groups) want_groups = atoi(e_g); }   // tuning only
+    if (tun && tun->tc_groups >= 1 && tun->tc_groups < want_groups) want_groups = tun->tc_groups;   // tuning only
     auto fit = [&](int rows, int groups, size_t* epi_off, size_t* total) {
         const size_t buffer = (size_t)2 * 16 * rows * 16;   // hi + lo planes of one trial
         *epi_off = ((size_t)groups * 2 * buffer + 127) & ~(size_t)127;
@@ -549,25 +579,39 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         seg = (n_trials + n_seg - 1) / n_seg;
     }
     (void)rows_trial;
-    const char* e_seg = getenv("ITJL_TC_SEG");
-    if (e_seg && atoi(e_seg) > 0) seg = atoi(e_seg);
+    // Product terms of the fp16 hi/lo split x' = hi + lo: hi*hi (+ hi*lo (+ lo*hi)), and trials per segment: the
+    // cheapest combination whose predicted error (abc_tc_predicted_error) is within the bound.  At C5 (2.5e5
+    // samples per particle) that is hi*hi alone and one segment; the missing-data models keep the cross terms
+    // they need through E_m (their masked samples share one rounding residual).  Fewer trials per segment
+    // (more drains) are tried when even three terms miss the bound; when nothing fits the caller falls back to
+    // the CUDA-core kernel.
+    const double bound = (tun && tun->tc_error_bound > 0.0) ? tun->tc_error_bound : 5e-6;
+    const int forced_terms = (tun && tun->tc_terms >= 1 && tun->tc_terms <= 3) ? tun->tc_terms : 0;
+    const int forced_seg = (tun && tun->tc_seg_trials > 0) ? tun->tc_seg_trials : 0;
+    const bool forced_kernel = tun && tun->abc_tc == 1;
+    const int min_terms = missing ? 2 : 1;             // see E_m: hi*hi alone is never worth it with a mask
+    auto even_seg = [&](int sg) {                      // equal segments: 100 trials with <= 51 per segment -> 50, 50
+        if (n_trials <= 0) return sg;
+        const int n_seg = (n_trials + sg - 1) / sg;
+        return (n_trials + n_seg - 1) / n_seg;
+    };
+    auto predicted = [&](int terms, int sg) {
+        return abc_tc_predicted_error(n_t, n_trials, terms, even_seg(sg) * rows_data, mask_frac, mean_ratio);
+    };
+    bool within = false;
+    int pick_terms = forced_terms ? forced_terms : 3, pick_seg = forced_seg ? forced_seg : 1;   // best effort
+    for (int sg = forced_seg ? forced_seg : seg; !within; sg = (sg + 1) / 2) {
+        for (int terms = forced_terms ? forced_terms : min_terms; terms <= 3 && !within; ++terms) {
+            if (predicted(terms, sg) <= bound) { within = true; pick_terms = terms; pick_seg = sg; }
+            if (forced_terms) break;
+        }
+        if (forced_seg || sg <= 1) break;
+    }
+    seg = even_seg(pick_seg);
     g->seg_trials = seg;
-    // product terms of the fp16 hi/lo split x' = hi + lo: hi*hi (+ hi*lo (+ lo*hi)).  A dropped cross term is
-    // a zero-mean residual of relative size 2^-12 per product, i.e. ~1e-4 sqrt(1 + 2 ac^2) / sqrt(samples
-    // per particle) on a trial-mean ACF value: 3.5e-7 (one cross term dropped) / 5e-7 (both) at C5's 2.5e5
-    // samples, against the 1e-5 tolerance (measured over 1184 particles against the fp64 oracle: rms 6.5e-7 /
-    // 1.0e-6, max 4.4e-6 / 6.3e-6, everything else included)
-    const int64_t samples = (int64_t)n_t * n_trials;
-    g->n_terms = samples >= 200000 ? 1 : (samples >= 100000 ? 2 : 3);
-    // The zero-mean argument needs independent rounding residuals.  The masked samples of the missing-data
-    // models all carry ONE value and hence one residual: every masked-masked pair is off by the same
-    // 2^-12-relative amount.  Small for the plain model (the value is the trial's mean offset: 2 terms keep it
-    // below 1e-6), but the oscillation model parks them at -(mean of valid) - data_mean s_x / data_sd, which
-    // can dominate the sum of squares (7e-5 on the ACF with hi*hi only, found by benchmarks/model_fuzz.py):
-    // the caller asks for at least 2 resp. all 3 terms there
-    if (g->n_terms < min_terms) g->n_terms = min_terms;
-    const char* e_terms = getenv("ITJL_TC_TERMS");
-    if (e_terms && atoi(e_terms) >= 1 && atoi(e_terms) <= 3) g->n_terms = atoi(e_terms);
+    g->n_terms = pick_terms;
+    g->pred_err = predicted(pick_terms, pick_seg);
+    const bool error_ok = within || forced_kernel;
     // The tensor-core accumulator rounds toward zero (tests/test_gpu_tc.py, probe): a cell that grows
     // linearly to c over R accumulate steps loses sum_i ulp(c i / R) / 2 = R 2^-24 phi(c) c with
     // phi in [1/3, 3/8] whatever the binade of c (measured: 2.1e-8 = 0.35 2^-24 per hi*hi tcgen05.mma, 1.6e-8
@@ -583,8 +627,7 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
         const double trials_seg = n_trials > 0 ? (double)n_trials / n_seg : 1.0;
         g->bias_a = (float)((2.1e-8 + 1.6e-8 * (g->n_terms - 1)) * trials_seg * g->ksteps);
         g->bias_b = (float)(4.7e-9 * trials_seg * rows_data);
-        const char* e_bias = getenv("ITJL_TC_BIAS");
-        if (e_bias && atoi(e_bias) == 0) g->bias_a = g->bias_b = 0.f;
+        if (tun && tun->tc_bias == 0) g->bias_a = g->bias_b = 0.f;
     }
     int p2 = 1; while (p2 * p2 < n_t) p2 <<= 1;                 // power of two near sqrt(n_t): series ~ N(0,1)
     g->tc_scale = (float)p2;
@@ -593,7 +636,7 @@ int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_coun
     int e2 = 0; while (fix >= 2.0 && e2 < 30) { fix *= 0.5; ++e2; }
     g->tc_fix = (float)(1u << e2);
     g->grid = sm_count;
-    return 0;
+    return error_ok ? 0 : -4;
 }
 
 template <bool MIXED, bool TAIL>

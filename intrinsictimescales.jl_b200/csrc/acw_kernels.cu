@@ -715,13 +715,12 @@ static cudaError_t launch_slices(AcfSliceParams& P, int reach, int max_smem, int
 
 cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                              int32_t* ke, int32_t* redo, cudaStream_t st) {
+                              int32_t* ke, int32_t* redo, cudaStream_t st, bool bulk_variant) {
     AcwStreamParams S{};
     S.data = data; S.n_slices = n_slices; S.n_t = n_t; S.n_seg = n_seg; S.seg_len = seg_len;
     S.part = reinterpret_cast<float*>(part);
     dim3 grid((unsigned)((n_slices + STREAM_THREADS - 1) / STREAM_THREADS), (unsigned)n_seg);
-    const char* e_bulk = getenv("ITJL_ACW_BULK");
-    const bool bulk = (n_slices % 2 == 0) && e_bulk && atoi(e_bulk) == 1;     // opt-in: measured slower (182 vs 150 us at C2)
+    const bool bulk = (n_slices % 2 == 0) && bulk_variant;     // opt-in: measured slower (182 vs 150 us at C2)
     cudaError_t e;
     if (bulk) {
         const size_t smem = sizeof(double) * ((size_t)BSTAGES * BT * BS + (size_t)SPART * STREAM_THREADS);
@@ -743,14 +742,12 @@ cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, dou
 int acw_stream_lags() { return SK; }
 // fp32 partials, counted in doubles for the caller's reserve()
 size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return ((size_t)n_seg * SPART * (size_t)n_slices + 1) / 2; }
-void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len) {
+void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves) {
     // The grid is (blocks of 128 slices) x (time segments); 4 CTAs of 128 threads are resident per SM
     // (128 registers per thread).  Pick the segment count whose grid fills whole waves of those slots:
     // cost = waves x (segment length + 32-sample halo); segments are multiples of 32 samples and at least
     // 256 long (each one also writes 33 partial sums per slice).  C2 (10 000 x 5000): 7 segments of 736
     // samples, 553 of 592 slots, one wave (16 segments were 2.13 waves, i.e. three rounds).
-    const char* e_w = getenv("ITJL_ACW_WAVES");
-    const int force_waves = (e_w && atoi(e_w) > 0) ? atoi(e_w) : 0;
     const long long slots = 4LL * sm_count;
     const long long blocks = (n_slices + 127) / 128;
     const int max_g = n_t / 256 > 0 ? n_t / 256 : 1;
@@ -825,6 +822,38 @@ cudaError_t acw_tau_launch(const double* acf, int64_t n_rows, int64_t ld, int n_
                            cudaStream_t st) {
     const int wpb = 4;
     k_acw_tau<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(acf, n_rows, ld, n_lags, dt, tau);
+    return cudaGetLastError();
+}
+
+// ---- strided input -> kernel layout ---------------------------------------------------------------------------
+// out[s + t * n_slices] = raw[s * ss + t * ts].  32 x 32 tiles through shared memory: the tile is read with
+// consecutive threads along whichever of (s, t) has the smaller stride in `raw` (ts = 1 for a Julia matrix with
+// time down the columns: coalesced 256-byte reads) and written with consecutive threads along s (coalesced).
+__global__ void __launch_bounds__(256) k_relayout(const double* __restrict__ raw, int64_t n_slices, int64_t n_t,
+                                                  int64_t ss, int64_t ts, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int64_t s0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 32 x 8
+    const bool t_fast = ts <= ss;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int a = ty + 8 * r;
+        const int64_t s = s0 + (t_fast ? a : tx), t = t0 + (t_fast ? tx : a);
+        if (s < n_slices && t < n_t) tile[t - t0][s - s0] = raw[s * ss + t * ts];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t t = t0 + ty + 8 * r, s = s0 + tx;
+        if (s < n_slices && t < n_t) out[s + t * n_slices] = tile[ty + 8 * r][tx];
+    }
+}
+
+cudaError_t relayout_launch(const double* raw, int64_t n_slices, int64_t n_t, int64_t ss, int64_t ts, double* out,
+                            cudaStream_t st) {
+    const dim3 grid((unsigned)((n_slices + 31) / 32), (unsigned)((n_t + 31) / 32));
+    if (grid.y > 65535) return cudaErrorInvalidValue;
+    k_relayout<<<grid, 256, 0, st>>>(raw, n_slices, n_t, ss, ts, out);
     return cudaGetLastError();
 }
 

@@ -1,9 +1,12 @@
 // Shared host/device helpers of libitjl_b200 (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
+#include <vector>
 
 #include "../../include/itjl_b200.h"
 
@@ -15,10 +18,15 @@ constexpr int kWarps = kThreads / 32;
 // particle): 256 threads x 221 floats already fill the shared memory of one CTA
 constexpr int kQtab = 224;
 
-// Grow-only device scratch buffer.
+// Grow-only device scratch buffer (freed with its owner: every error exit that deletes a context or a model
+// releases what was already allocated).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
@@ -30,9 +38,27 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// NVTX range of one C-ABI call (nsys / ncu --nvtx show the phases of a generation by name)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 }  // namespace itjl
 
 struct itjl_ctx {
+    // one call at a time per context: every entry point that takes a context (or a model of it) holds this
+    // lock for its whole duration, so a context may be shared between host threads (Julia tasks)
+    std::recursive_mutex mu;
+    itjl_tuning tuning{};
+    // multi-GPU (itjl_api_multi.cu): a parent context owns one sub-context per device of this process
+    // (itjl_ctx_create_multi), or a single-device context joins a communicator of several processes
+    // (itjl_ctx_attach_comm); `comm` is the ncclComm_t of THIS device, rank / world its place in it
+    std::vector<itjl_ctx*> subs;
+    itjl_ctx* parent = nullptr;
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    itjl::DevBuf gather;                // [world][width] all-gather buffer of per-particle values
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
@@ -42,9 +68,11 @@ struct itjl_ctx {
     int64_t launches = 0;
     // timing of the dominant kernel (events on `stream`)
     bool timing = false;
+    bool timing_sync = true;            // false: events are only recorded around the last timed launch
     int64_t timed_launches = 0;
     double timed_ms = 0.0;
-    itjl::DevBuf theta, dist, stats, u0, noise, phases, flags, scratch, data, out, out2, out3, part;
+    itjl::DevBuf theta, dist, stats, u0, noise, phases, flags, scratch, data, out, out2, out3, part, raw;
+    int64_t res_slices = 0, res_nt = 0;   // shape of the matrix itjl_data_upload left in `data` (0: none)
     // pinned staging ring of the large host -> device uploads (itjl_api_acw.cu)
     void* pin[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pin_ev[3] = {nullptr, nullptr, nullptr};
@@ -59,6 +87,10 @@ inline int fail(itjl_ctx* ctx, int code, const char* fmt, const char* a = "", co
     snprintf(dst, 512, fmt, a, b);
     return code;
 }
+
+#define ITJL_CAT2(a, b) a##b
+#define ITJL_CAT(a, b) ITJL_CAT2(a, b)
+#define ITJL_LOCK(ctx) std::lock_guard<std::recursive_mutex> ITJL_CAT(_itjl_lock_, __COUNTER__)((ctx)->mu)
 
 #define ITJL_CUDA(ctx, call)                                                              \
     do {                                                                                  \

@@ -7,7 +7,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "kernels.h"
+#include "api_internal.h"
 #include "philox.cuh"
 #include "tc05.cuh"
 
@@ -16,23 +16,6 @@ char g_err[512] = {0};
 }
 
 using namespace itjl;
-
-static const bool kTcDefault = true;      // default path of the fused ACF kernel when ITJL_ABC_TC is unset
-
-struct itjl_model {
-    itjl_ctx* ctx = nullptr;
-    itjl_model_desc d{};
-    DevBuf target, mask_bits, n_valid, bins, binidx, window, twiddle;
-    int mask_words = 0;
-    AbcAcfGeometry geo{};
-    AbcTcGeometry tc{};
-    bool use_tc = false;       // lag sums on the tensor cores (abc_tc_kernels.cu)
-    // PSD
-    int n2 = 0, log2_n2 = 0, psd_chunk = 0, psd_xs_len = 0;
-    size_t psd_smem = 0;
-    bool psd_accb_global = false;   // PSD bin sums in global memory (too many selected bins for shared memory)
-    double psd_scale = 0.0;
-};
 
 extern "C" {
 
@@ -44,6 +27,32 @@ int itjl_device_count(int* n_out) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { *n_out = 0; return fail(nullptr, ITJL_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
     *n_out = n;
+    return ITJL_OK;
+}
+
+int itjl_tuning_default(itjl_tuning* t) {
+    if (!t) return fail(nullptr, ITJL_ERR_ARG, "itjl_tuning_default: null output");
+    memset(t, 0, sizeof(*t));
+    t->abc_tc = -1; t->tc_tail_max = -1; t->tc_bias = 1; t->acw_stream = 1; t->pinned_upload = 1; t->pmc_fp32 = -1;
+    t->tc_error_bound = 5e-6;
+    return ITJL_OK;
+}
+
+int itjl_ctx_set_tuning(itjl_ctx* ctx, const itjl_tuning* t) {
+    if (!ctx || !t) return fail(ctx, ITJL_ERR_ARG, "itjl_ctx_set_tuning: null argument");
+    ITJL_LOCK(ctx);
+    if (t->abc_tc < -1 || t->abc_tc > 1 || t->tc_terms < 0 || t->tc_terms > 3 || t->tc_tail_max > 60 || t->tc_groups < 0 ||
+        t->tc_groups > 4 || t->tc_seg_trials < 0 || (t->abc_threads != 0 && t->abc_threads != 128 && t->abc_threads != 256) ||
+        t->abc_bufs < 0 || t->abc_bufs > 2 || t->copy_threads < 0 || t->pmc_fp32 < -1 || t->pmc_fp32 > 1 || !(t->tc_error_bound > 0.0))
+        return fail(ctx, ITJL_ERR_ARG, "itjl_ctx_set_tuning: value out of range");
+    ctx->tuning = *t;
+    for (itjl_ctx* sub : ctx->subs) sub->tuning = *t;
+    return ITJL_OK;
+}
+
+int itjl_ctx_get_tuning(const itjl_ctx* ctx, itjl_tuning* out) {
+    if (!ctx || !out) return fail(nullptr, ITJL_ERR_ARG, "itjl_ctx_get_tuning: null argument");
+    *out = ctx->tuning;
     return ITJL_OK;
 }
 
@@ -59,12 +68,16 @@ int itjl_ctx_create(int device, itjl_ctx** ctx_out) {
     itjl_ctx* ctx = new (std::nothrow) itjl_ctx();
     if (!ctx) return fail(nullptr, ITJL_ERR_ALLOC, "out of host memory");
     ctx->device = device;
+    itjl_tuning_default(&ctx->tuning);
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) {
         fail(nullptr, ITJL_ERR_CUDA, "itjl_ctx_create: %s", cudaGetErrorString(e));
+        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return ITJL_ERR_CUDA;
     }
@@ -74,10 +87,16 @@ int itjl_ctx_create(int device, itjl_ctx** ctx_out) {
 
 int itjl_ctx_destroy(itjl_ctx* ctx) {
     if (!ctx) return ITJL_OK;
+    comm_destroy(ctx);                                   // NCCL communicator(s), if any (itjl_api_multi.cu)
+    if (!ctx->subs.empty()) {                            // multi-GPU parent: no device resources of its own
+        for (itjl_ctx* sub : ctx->subs) itjl_ctx_destroy(sub);
+        delete ctx;
+        return ITJL_OK;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->theta, &ctx->dist, &ctx->stats, &ctx->u0, &ctx->noise, &ctx->phases,
-                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3, &ctx->part};
+                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3, &ctx->part, &ctx->gather, &ctx->raw};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 3; ++i) {
@@ -93,30 +112,51 @@ const char* itjl_last_error(const itjl_ctx* ctx) { return ctx ? ctx->err : g_err
 
 int itjl_ctx_synchronize(itjl_ctx* ctx) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    ITJL_LOCK(ctx);
+    if (!ctx->subs.empty()) {
+        for (itjl_ctx* sub : ctx->subs) { const int rc = itjl_ctx_synchronize(sub); if (rc != ITJL_OK) return rc; }
+        return ITJL_OK;
+    }
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ITJL_OK;
 }
 
-uint64_t itjl_ctx_stream(const itjl_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
-int64_t itjl_ctx_launch_count(const itjl_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int itjl_ctx_sm_count(const itjl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t itjl_ctx_stream(const itjl_ctx* ctx) { ctx = primary(const_cast<itjl_ctx*>(ctx)); return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+int64_t itjl_ctx_launch_count(const itjl_ctx* ctx) {
+    if (!ctx) return 0;
+    int64_t n = ctx->launches;
+    for (const itjl_ctx* sub : ctx->subs) n += sub->launches;
+    return n;
+}
+int itjl_ctx_sm_count(const itjl_ctx* ctx) { ctx = primary(const_cast<itjl_ctx*>(ctx)); return ctx ? ctx->sm_count : 0; }
 
 int itjl_ctx_timing_reset(itjl_ctx* ctx) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
-    ctx->timing = true; ctx->timed_launches = 0; ctx->timed_ms = 0.0;
+    ITJL_LOCK(ctx);
+    itjl_ctx* c = primary(ctx);
+    c->timing = true; c->timed_launches = 0; c->timed_ms = 0.0;
     return ITJL_OK;
 }
 int itjl_ctx_timing_get(itjl_ctx* ctx, int64_t* n_launches, double* total_ms) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
-    if (n_launches) *n_launches = ctx->timed_launches;
-    if (total_ms) *total_ms = ctx->timed_ms;
+    ITJL_LOCK(ctx);
+    itjl_ctx* c = primary(ctx);
+    if (n_launches) *n_launches = c->timed_launches;
+    if (total_ms) *total_ms = c->timed_ms;
+    return ITJL_OK;
+}
+int itjl_ctx_timing_stop(itjl_ctx* ctx) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    ITJL_LOCK(ctx);
+    primary(ctx)->timing = false;
     return ITJL_OK;
 }
 
 }  // extern "C"
 
 // ---- helpers ---------------------------------------------------------------------------
-static int upload(itjl_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
+int itjl::upload(itjl_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
     ITJL_CUDA(ctx, buf.reserve(bytes ? bytes : 1));
     if (bytes) ITJL_CUDA(ctx, cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return ITJL_OK;
@@ -139,6 +179,9 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
     if (!(d.dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "dt must be positive");
     if (d.summary == ITJL_SUMMARY_ACF_MISSING && !d.missing_mask) return fail(ctx, ITJL_ERR_ARG, "missing_mask required for the missing-data ACF");
     if (d.summary == ITJL_SUMMARY_PSD && !d.freq_bins) return fail(ctx, ITJL_ERR_ARG, "freq_bins required for the PSD summary");
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_model_create");
+    if (!ctx->subs.empty()) return multi_model_create(ctx, desc, model_out);   // one model per device
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
 
     itjl_model* m = new (std::nothrow) itjl_model();
@@ -150,19 +193,26 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
     for (int64_t i = 0; i < d.n_stats; ++i) tgt[i] = (float)d.target_stats[i];
     rc = upload(ctx, m->target, tgt.data(), tgt.size() * sizeof(float));
 
+    if (rc == ITJL_OK && d.missing_mask) {
+        int64_t masked = 0;
+        for (int64_t i = 0; i < d.n_trials * d.n_t; ++i) masked += d.missing_mask[i] != 0;
+        m->mask_frac = (double)masked / (double)(d.n_trials * d.n_t);
+    }
     if (rc == ITJL_OK && d.summary != ITJL_SUMMARY_PSD) {
-        if (d.n_stats > d.n_t) { delete m; return fail(ctx, ITJL_ERR_ARG, "n_lags must not exceed n_t"); }
-        int g = abc_acf_geometry((int)d.n_t, (int)d.n_stats, ctx->max_smem_optin, &m->geo);
-        if (g != 0) { delete m; return fail(ctx, ITJL_ERR_ARG, g == -2 ? "n_lags > 5120 is not supported by the fused ACF kernel" : "trial does not fit in shared memory (n_t too large)"); }
-        // tensor-core lag sums when the lag window fits the 512 TMEM columns (plus a short FFMA tail);
-        // ITJL_ABC_TC=0 forces the FFMA kernel, =1 the tensor-core kernel (error if unsupported), =2 picks
-        // the tensor-core kernel whenever the shape is supported
-        const char* e_tc = getenv("ITJL_ABC_TC");
-        const int want_tc = e_tc ? atoi(e_tc) : -1;
-        const int min_terms = d.summary == ITJL_SUMMARY_ACF_MISSING ? (d.kind == ITJL_KIND_OU_OSC ? 3 : 2) : 1;
-        const int tcg = abc_tc_geometry((int)d.n_t, (int)d.n_stats, (int)d.n_trials, ctx->max_smem_optin, ctx->sm_count, &m->tc, min_terms);
-        if (want_tc == 1 && tcg != 0) { delete m; return fail(ctx, ITJL_ERR_ARG, "ITJL_ABC_TC=1 but the tensor-core kernel does not support this shape"); }
-        m->use_tc = (tcg == 0) && (want_tc != 0) && (want_tc >= 1 || kTcDefault);
+        if (d.n_stats > d.n_t) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "n_lags must not exceed n_t"); }
+        int g = abc_acf_geometry((int)d.n_t, (int)d.n_stats, ctx->max_smem_optin, &m->geo, &ctx->tuning);
+        if (g != 0) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, g == -2 ? "n_lags > 5120 is not supported by the fused ACF kernel" : "trial does not fit in shared memory (n_t too large)"); }
+        // Tensor-core lag sums when the lag window fits the tensor-memory plans AND the error model
+        // (abc_tc_predicted_error) puts the plan within tuning.tc_error_bound; otherwise - and with
+        // tuning.abc_tc = 0 - the fp32 FFMA kernel.  abc_tc = 1 forces the tensor-core kernel.
+        const int want_tc = ctx->tuning.abc_tc;
+        const bool missing = d.summary == ITJL_SUMMARY_ACF_MISSING;
+        const double mean_ratio = (missing && d.kind == ITJL_KIND_OU_OSC && d.data_sd != 0.0) ? d.data_mean / d.data_sd : 0.0;
+        const int tcg = abc_tc_geometry((int)d.n_t, (int)d.n_stats, (int)d.n_trials, ctx->max_smem_optin, ctx->sm_count, &m->tc,
+                                        &ctx->tuning, m->mask_frac, mean_ratio, missing);
+        if (want_tc == 1 && tcg != 0) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "tuning.abc_tc = 1 but the tensor-core kernel does not support this shape"); }
+        m->use_tc = (tcg == 0) && (want_tc != 0);
+        m->tc_pred_err = m->use_tc ? m->tc.pred_err : 0.0;
     }
     if (rc == ITJL_OK && d.missing_mask) {
         m->mask_words = (int)((d.n_t + 31) / 32);
@@ -181,14 +231,14 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         m->n2 = 2 * nextpow2_int(d.n_t);
         m->log2_n2 = 0; while ((1 << m->log2_n2) < m->n2) m->log2_n2++;
         for (int64_t i = 0; i < d.n_stats; ++i)
-            if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { delete m; return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
+            if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
         m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
         if ((int64_t)m->psd_smem > ctx->max_smem_optin) {
             // many selected bins (e.g. fs = 250 Hz: 80 % of 16 384): keep the per-particle bin sums in global memory
             m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len, false);
             m->psd_accb_global = true;
         }
-        if ((int64_t)m->psd_smem > ctx->max_smem_optin) { delete m; return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
+        if ((int64_t)m->psd_smem > ctx->max_smem_optin || m->psd_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
         std::vector<float> win((size_t)d.n_t + 1, 0.0f);          // +1: the kernel reads the window as float2 pairs
         std::vector<float2> tw((size_t)m->n2 / 2);
         double win_ss = 0.0;
@@ -227,6 +277,11 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
 
 int itjl_model_destroy(itjl_model* m) {
     if (!m) return ITJL_OK;
+    if (!m->subs.empty()) {
+        for (itjl_model* sub : m->subs) itjl_model_destroy(sub);
+        delete m;
+        return ITJL_OK;
+    }
     if (m->ctx) cudaSetDevice(m->ctx->device);
     m->target.release(); m->mask_bits.release(); m->n_valid.release();
     m->bins.release(); m->binidx.release(); m->window.release(); m->twiddle.release();
@@ -236,6 +291,7 @@ int itjl_model_destroy(itjl_model* m) {
 
 int itjl_model_work(const itjl_model* m, double* flops_per_sample, int64_t* samples_per_particle) {
     if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    m = primary(const_cast<itjl_model*>(m));
     if (flops_per_sample) {
         if (m->d.summary == ITJL_SUMMARY_PSD) {
             // one n2-point real FFT per trial (2.5 n2 log2 n2) + |.|^2 on the selected bins + window etc.
@@ -252,15 +308,21 @@ int itjl_tc_plan(int64_t n_t, int64_t n_lags, int64_t n_trials, int32_t max_smem
     if (!out || n_t > INT32_MAX || n_lags > INT32_MAX || n_trials > INT32_MAX) return fail(nullptr, ITJL_ERR_ARG, "itjl_tc_plan: bad argument");
     AbcTcGeometry g{};
     const int rc = abc_tc_geometry((int)n_t, (int)n_lags, (int)n_trials, max_smem_optin, sm_count, &g);
-    if (rc != 0) return fail(nullptr, ITJL_ERR_ARG, "itjl_tc_plan: shape outside the tensor-core kernel's plans");
+    if (rc != 0 && rc != -4) return fail(nullptr, ITJL_ERR_ARG, "itjl_tc_plan: shape outside the tensor-core kernel's plans");
     const int32_t v[16] = {g.groups, g.chunk, g.ksteps, g.rows_total, g.used_cols, g.mixed, g.seg_trials, g.n_terms,
-                           g.tc_lags, g.tail_start, g.tail_lt, g.n_ops, (int32_t)g.smem_bytes, g.grid, g.n_windows, 0};
+                           g.tc_lags, g.tail_start, g.tail_lt, g.n_ops, (int32_t)g.smem_bytes, g.grid, g.n_windows,
+                           rc == -4 ? 1 : 0 /* 1: the error model sends this shape to the CUDA-core kernel */};
     memcpy(out, v, sizeof(v));
     return ITJL_OK;
 }
 
+double itjl_tc_predicted_error(int64_t n_t, int64_t n_trials, int32_t n_terms, int32_t seg_rows, double mask_frac, double mean_ratio) {
+    return abc_tc_predicted_error(n_t, n_trials, n_terms, seg_rows, mask_frac, mean_ratio);
+}
+
 int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_flops_per_sample) {
     if (!m || !name_out || !tensor_flops_per_sample) return fail(m ? m->ctx : nullptr, ITJL_ERR_ARG, "itjl_model_kernel_info: null argument");
+    m = primary(const_cast<itjl_model*>(m));
     *tensor_flops_per_sample = 0.0;
     if (m->d.summary == ITJL_SUMMARY_PSD) { snprintf(name_out, 32, "k_abc_psd"); return ITJL_OK; }
     if (!m->use_tc) { snprintf(name_out, 32, "k_abc_acf"); return ITJL_OK; }
@@ -279,7 +341,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
 }  // extern "C"
 
 // Launch the fused kernel for one batch; every pointer is a device pointer (or null).
-static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
+int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
                             uint64_t seed, uint64_t generation, int64_t particle_offset,
                             const double* u0_dev, const double* noise_dev, const double* phases_dev,
                             double* dist_dev, double* stats_dev) {
@@ -289,6 +351,8 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
     if (n_theta < need_theta) return fail(ctx, ITJL_ERR_ARG, "theta has too few columns for this model");
     if (n_particles < 1 || n_particles > 0x7fffffffll) return fail(ctx, ITJL_ERR_ARG, "n_particles out of range");
     cudaError_t e;
+    NvtxRange nvtx(d.summary == ITJL_SUMMARY_PSD ? "k_abc_psd" : (m->use_tc ? "k_abc_acf_tc" : "k_abc_acf"));
+    int n_launched = 1;
     if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
     if (d.summary == ITJL_SUMMARY_PSD) {
         AbcPsdParams P{};
@@ -313,7 +377,8 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
             const cudaError_t er = ctx->scratch.reserve((size_t)std::min<int64_t>(sub, n_particles) * pad * sizeof(float));
             if (er != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "PSD bin-sum scratch: %s", cudaGetErrorString(er));
             e = cudaSuccess;
-            for (int64_t lo = 0; lo < n_particles && e == cudaSuccess; lo += sub) {
+            n_launched = 0;
+            for (int64_t lo = 0; lo < n_particles && e == cudaSuccess; lo += sub, ++n_launched) {
                 AbcPsdParams Q = P;
                 Q.grid = std::min<int64_t>(sub, n_particles - lo);
                 Q.accb_global = (float*)ctx->scratch.p;
@@ -357,7 +422,9 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.bias_a = t.bias_a; P.bias_b = t.bias_b;
         P.smem_bytes = t.smem_bytes;
         P.miss_mean_ratio = (d.kind == ITJL_KIND_OU_OSC && d.data_sd != 0.0) ? (float)(d.data_mean / d.data_sd) : 0.f;
-        { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
+#ifdef ITJL_TUNING
+        { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }   // phase-isolation builds only (make EXTRA=-DITJL_TUNING)
+#endif
         P.k_lo = 0; P.lag_base = 0; P.accumulate = 0;
         e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, t.mixed != 0,
                           t.smem_bytes, t.grid, ctx->stream);
@@ -383,6 +450,7 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
             }
             e = abc_tc_launch(P, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC, false,
                               t.smem_bytes, t.grid, ctx->stream);
+            ++n_launched;
         }
     } else {
         AbcAcfParams P{};
@@ -400,12 +468,14 @@ static int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_pa
         P.mask_words = m->mask_words;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
+#ifdef ITJL_TUNING
         { const char* dbg = getenv("ITJL_ABC_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
+#endif
         e = abc_acf_launch(P, m->geo.threads, d.summary == ITJL_SUMMARY_ACF_MISSING, d.kind == ITJL_KIND_OU_OSC,
                            m->geo.smem_bytes, ctx->stream);
     }
     if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch fused abc kernel: %s", cudaGetErrorString(e));
-    ctx->launches++;
+    ctx->launches += n_launched;                      // every lag window / PSD sub-batch is a launch
     if (ctx->timing) {
         cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);
@@ -435,9 +505,23 @@ int itjl_abc_distances(itjl_model* m, const double* theta, int64_t n_particles, 
                        const double* u0, const double* noise, const double* phases,
                        double* dist_out, double* stats_out) {
     if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    if (!theta || !dist_out) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_distances: null theta / dist_out");
+    if (n_particles < 1 || n_theta < 1) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_distances: empty batch");
+    ITJL_LOCK(m->ctx);
+    NvtxRange nvtx("itjl_abc_distances");
+    if (is_sharded(m->ctx) && !u0 && !noise && !phases && !stats_out) {
+        // particles sharded over the communicator, distances all-gathered device to device
+        double* dist_dev = nullptr;
+        int rcs = sharded_distances(m, theta, n_particles, n_theta, seed, generation, particle_offset, &dist_dev);
+        if (rcs != ITJL_OK) return rcs;
+        itjl_ctx* c0 = primary(m->ctx);
+        ITJL_CUDA(m->ctx, cudaMemcpyAsync(dist_out, dist_dev, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+        ITJL_CUDA(m->ctx, cudaStreamSynchronize(c0->stream));
+        return ITJL_OK;
+    }
+    m = primary(m);                                    // injected inputs / statistics: first device only
     itjl_ctx* ctx = m->ctx;
-    if (!theta || !dist_out) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances: null theta / dist_out");
-    if (n_particles < 1 || n_theta < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances: empty batch");
+    ITJL_LOCK(ctx);
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = stage_inputs(m, theta, n_particles, n_theta, u0, noise, phases);
     if (rc != ITJL_OK) return rc;
@@ -459,6 +543,9 @@ int itjl_abc_distances_dev(itjl_model* m, const double* theta_dev, int64_t n_par
                            uint64_t seed, uint64_t generation, int64_t particle_offset, double* dist_dev) {
     if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
     if (!theta_dev || !dist_dev) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_distances_dev: null device pointer");
+    ITJL_LOCK(m->ctx);
+    m = primary(m);
+    ITJL_LOCK(m->ctx);
     ITJL_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
     return launch_distances(m, theta_dev, n_particles, n_theta, seed, generation, particle_offset,
                             nullptr, nullptr, nullptr, dist_dev, nullptr);
@@ -469,24 +556,37 @@ int itjl_abc_generation(itjl_model* m, const double* theta, int64_t n_particles,
                         double epsilon, int64_t min_accepted, double* dist_out, uint8_t* isaccepted,
                         int64_t* n_total, int64_t* n_accepted) {
     if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
-    itjl_ctx* ctx = m->ctx;
-    if (!theta || !dist_out || !isaccepted || !n_total || !n_accepted) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_generation: null argument");
-    if (n_particles < 1 || n_theta < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_generation: empty batch");
-    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = stage_inputs(m, theta, n_particles, n_theta, nullptr, nullptr, nullptr);
-    if (rc != ITJL_OK) return rc;
-    ITJL_CUDA(ctx, ctx->dist.reserve((size_t)n_particles * sizeof(double)));
+    if (!theta || !dist_out || !isaccepted || !n_total || !n_accepted) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_generation: null argument");
+    if (n_particles < 1 || n_theta < 1) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_generation: empty batch");
+    ITJL_LOCK(m->ctx);
+    NvtxRange nvtx("itjl_abc_generation");
+    const bool sharded = is_sharded(m->ctx);
+    itjl_ctx* ctx = primary(m->ctx);
+    ITJL_LOCK(ctx);
+    int rc = ITJL_OK;
+    double* dist_dev = nullptr;
+    if (sharded) {
+        rc = sharded_distances(m, theta, n_particles, n_theta, seed, generation, particle_offset, &dist_dev);
+        if (rc != ITJL_OK) return rc;
+        ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    } else {
+        ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+        rc = stage_inputs(m, theta, n_particles, n_theta, nullptr, nullptr, nullptr);
+        if (rc != ITJL_OK) return rc;
+        ITJL_CUDA(ctx, ctx->dist.reserve((size_t)n_particles * sizeof(double)));
+        rc = launch_distances(m, (const double*)ctx->theta.p, n_particles, n_theta, seed, generation, particle_offset,
+                              nullptr, nullptr, nullptr, (double*)ctx->dist.p, nullptr);
+        if (rc != ITJL_OK) return rc;
+        dist_dev = (double*)ctx->dist.p;
+    }
     ITJL_CUDA(ctx, ctx->flags.reserve((size_t)n_particles + 2 * sizeof(int64_t) + 16));
-    rc = launch_distances(m, (const double*)ctx->theta.p, n_particles, n_theta, seed, generation, particle_offset,
-                          nullptr, nullptr, nullptr, (double*)ctx->dist.p, nullptr);
-    if (rc != ITJL_OK) return rc;
     ITJL_CUDA(ctx, ctx->scratch.reserve(2 * sizeof(int64_t)));
-    cudaError_t e = abc_accept_launch((const double*)ctx->dist.p, n_particles, epsilon, min_accepted,
+    cudaError_t e = abc_accept_launch(dist_dev, n_particles, epsilon, min_accepted,
                                       (uint8_t*)ctx->flags.p, (int64_t*)ctx->scratch.p, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_abc_accept: %s", cudaGetErrorString(e));
     ctx->launches++;
     int64_t out2[2] = {0, 0};
-    ITJL_CUDA(ctx, cudaMemcpyAsync(dist_out, ctx->dist.p, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(dist_out, dist_dev, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ITJL_CUDA(ctx, cudaMemcpyAsync(isaccepted, ctx->flags.p, (size_t)n_particles, cudaMemcpyDeviceToHost, ctx->stream));
     ITJL_CUDA(ctx, cudaMemcpyAsync(out2, ctx->scratch.p, sizeof(out2), cudaMemcpyDeviceToHost, ctx->stream));
     ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -498,6 +598,9 @@ int itjl_abc_accept(itjl_ctx* ctx, const double* dist, int64_t n, double epsilon
                     uint8_t* isaccepted, int64_t* n_total, int64_t* n_accepted) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
     if (!dist || !isaccepted || !n_total || !n_accepted || n < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_accept: null / empty argument");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = upload(ctx, ctx->dist, dist, (size_t)n * sizeof(double));
     if (rc != ITJL_OK) return rc;
@@ -520,6 +623,10 @@ static int generate_common(itjl_ctx* ctx, int kind, double tau, double freq, dou
                            int64_t n_t, int64_t n_trials, int mode, double scale, double shift, int32_t update,
                            uint64_t seed, const double* u0, const double* noise, const double* phases, double* out) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_generate_ou");
     if (!out) return fail(ctx, ITJL_ERR_ARG, "generate_ou: null output");
     if (n_t < 4 || n_trials < 1 || !(dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "generate_ou: need n_t >= 4, n_trials >= 1, dt > 0");
     if (update != ITJL_UPDATE_EXACT && update != ITJL_UPDATE_EM) return fail(ctx, ITJL_ERR_ARG, "invalid update rule");
@@ -571,6 +678,9 @@ int itjl_generate_ou_osc(itjl_ctx* ctx, double tau, double freq, double coeff, d
 // ---- measurement -----------------------------------------------------------------------
 int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
     if (!ctx || !tflops_out) return fail(ctx, ITJL_ERR_ARG, "itjl_fp32_peak: null argument");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
     int micro = 0;                                   // tuning: negative iters select a microbenchmark
     if (iters < 0) { micro = -iters; iters = 5; }
     if (iters < 1) iters = 1;
@@ -603,6 +713,9 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
 int itjl_tc_probe(itjl_ctx* ctx, const void* image, int64_t n_bytes, const int32_t* ops, int32_t n_ops,
                   uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t idesc, float* out) {
     if (!ctx || !image || !ops || !out) return fail(ctx, ITJL_ERR_ARG, "itjl_tc_probe: null argument");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
     if (n_bytes < 16 || (n_bytes & 15) || n_bytes > 200 * 1024 || n_ops < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_tc_probe: bad image size / op count");
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = upload(ctx, ctx->data, image, (size_t)n_bytes);

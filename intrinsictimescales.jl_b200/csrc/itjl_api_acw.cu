@@ -5,7 +5,7 @@
 #include <thread>
 #include <vector>
 
-#include "kernels.h"
+#include "api_internal.h"
 
 using namespace itjl;
 
@@ -15,21 +15,19 @@ using namespace itjl;
 // the staged pipeline at ~25-30 GB/s; C2's 400 MB: 36 ms -> ~15 ms).
 static const size_t kPinChunk = (size_t)16 << 20;
 // host threads that copy between the caller's pageable array and the pinned staging ring
-// (ITJL_COPY_THREADS, default: half the hardware threads, at most 8)
+// (itjl_tuning::copy_threads, default: half the hardware threads, at most 8)
 constexpr int kMaxCopyThreads = 16;
-static int copy_threads() {
-    const char* e = getenv("ITJL_COPY_THREADS");
-    int n = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);
-    if (!e && n > 8) n = 8;
+static int copy_threads(const itjl_ctx* ctx) {
+    const int t = ctx->tuning.copy_threads;
+    int n = t > 0 ? t : (int)(std::thread::hardware_concurrency() / 2);
+    if (t <= 0 && n > 8) n = 8;
     return n < 1 ? 1 : (n > kMaxCopyThreads ? kMaxCopyThreads : n);
 }
 
-static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t) {
-    const size_t bytes = (size_t)n_slices * n_t * sizeof(double);
-    ITJL_CUDA(ctx, ctx->data.reserve(bytes));
-    const char* e_pin = getenv("ITJL_PINNED_UPLOAD");
-    if (bytes < 4 * kPinChunk || (e_pin && atoi(e_pin) == 0)) {
-        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->data.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+// `bytes` from the caller's array to the device buffer `dst_dev`
+static int upload_bytes(itjl_ctx* ctx, void* dst_dev, const void* data, size_t bytes) {
+    if (bytes < 4 * kPinChunk || ctx->tuning.pinned_upload == 0) {
+        ITJL_CUDA(ctx, cudaMemcpyAsync(dst_dev, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return ITJL_OK;
     }
     for (int i = 0; i < 3; ++i) {
@@ -37,8 +35,8 @@ static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int6
         if (!ctx->pin_ev[i]) ITJL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming));
     }
     const char* src = reinterpret_cast<const char*>(data);
-    char* dst = reinterpret_cast<char*>(ctx->data.p);
-    const int n_threads = copy_threads();
+    char* dst = reinterpret_cast<char*>(dst_dev);
+    const int n_threads = copy_threads(ctx);
     size_t off = 0;
     for (int c = 0; off < bytes; ++c, off += kPinChunk) {
         const int b = c % 3;
@@ -60,11 +58,31 @@ static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int6
     return ITJL_OK;
 }
 
+// The caller's matrix, element (s, t) at data[s * ss + t * ts], into ctx->data in the kernels' layout
+// (slice index fastest).  That layout is uploaded as it is; anything else is uploaded as it lies in host memory
+// (its whole span) and re-laid on the device by k_relayout - no host-side transpose.
+static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t ss = 1, int64_t ts = 0) {
+    if (ts == 0) ts = n_slices;
+    const size_t bytes = (size_t)n_slices * n_t * sizeof(double);
+    ctx->res_slices = ctx->res_nt = 0;                       // whatever was resident is overwritten
+    ITJL_CUDA(ctx, ctx->data.reserve(bytes));
+    if (ss == 1 && ts == n_slices) return upload_bytes(ctx, ctx->data.p, data, bytes);
+    if (ss < 1 || ts < 1) return fail(ctx, ITJL_ERR_ARG, "strides must be positive");
+    const size_t span = (size_t)((n_slices - 1) * ss + (n_t - 1) * ts + 1);
+    if (span > (size_t)4 * n_slices * n_t) return fail(ctx, ITJL_ERR_ARG, "strided view spans more than 4x its elements: copy it to a dense array first");
+    ITJL_CUDA(ctx, ctx->raw.reserve(span * sizeof(double)));
+    const int rc = upload_bytes(ctx, ctx->raw.p, data, span * sizeof(double));
+    if (rc != ITJL_OK) return rc;
+    const cudaError_t e = relayout_launch((const double*)ctx->raw.p, n_slices, n_t, ss, ts, (double*)ctx->data.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_relayout: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return ITJL_OK;
+}
+
 // Device -> host download of a large result (the exported ACF matrix) through the same pinned ring:
 // DMA of chunk c + 1 runs while the host threads copy chunk c out to the caller's pageable array.
 static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
-    const char* e_pin = getenv("ITJL_PINNED_UPLOAD");
-    if (bytes < 4 * kPinChunk || (e_pin && atoi(e_pin) == 0)) {
+    if (bytes < 4 * kPinChunk || ctx->tuning.pinned_upload == 0) {
         ITJL_CUDA(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         return ITJL_OK;
     }
@@ -82,7 +100,7 @@ static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, si
         return e != cudaSuccess ? e : cudaEventRecord(ctx->pin_ev[c % 3], ctx->stream);
     };
     for (size_t c = 0; c < 2 && c < n_chunks; ++c) ITJL_CUDA(ctx, issue(c));
-    const int n_threads = copy_threads();
+    const int n_threads = copy_threads(ctx);
     for (size_t c = 0; c < n_chunks; ++c) {
         if (c + 2 < n_chunks) ITJL_CUDA(ctx, issue(c + 2));      // buffer (c + 2) % 3 was emptied at chunk c - 1
         ITJL_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[c % 3]));
@@ -124,15 +142,19 @@ static int acf_all(itjl_ctx* ctx, int64_t n_slices, int n_t, int n_lags, int mis
 }
 
 static int acf_entry(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t n_lags,
-                     int missing, double* out, const char* who) {
+                     int missing, double* out, const char* who, int64_t ss = 1, int64_t ts = 0) {
     int rc = check_data_args(ctx, data, n_slices, n_t, who);
     if (rc != ITJL_OK) return rc;
     if (!out) return fail(ctx, ITJL_ERR_ARG, "%s: null output", who);
     if (n_lags < 1 || n_lags > n_t) return fail(ctx, ITJL_ERR_ARG, "%s: need 1 <= n_lags <= n_t", who);
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx(who);
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_lags > acf_max_reach((int)n_t, ctx->max_smem_optin))
         return fail(ctx, ITJL_ERR_ARG, "%s: n_t + n_lags does not fit in shared memory", who);
-    rc = upload_data(ctx, data, n_slices, n_t);
+    rc = upload_data(ctx, data, n_slices, n_t, ss, ts);
     if (rc != ITJL_OK) return rc;
     rc = acf_all(ctx, n_slices, (int)n_t, (int)n_lags, missing, n_lags, true);
     if (rc != ITJL_OK) return rc;
@@ -166,10 +188,20 @@ int itjl_acf_missing(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_
     return acf_entry(ctx, data, n_slices, n_t, n_lags, 1, out, "itjl_acf_missing");
 }
 
+int itjl_acf_strided(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t slice_stride,
+                     int64_t time_stride, int64_t n_lags, int32_t missing, double* out) {
+    if (slice_stride < 1 || time_stride < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_acf_strided: strides must be positive");
+    return acf_entry(ctx, data, n_slices, n_t, n_lags, missing ? 1 : 0, out, "itjl_acf_strided", slice_stride, time_stride);
+}
+
 int itjl_psd_hamming(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double* out) {
     int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_psd_hamming");
     if (rc != ITJL_OK) return rc;
     if (!out || !(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_psd_hamming: null output or fs <= 0");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_psd_hamming");
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     int n2 = 2; while (n2 < n_t) n2 <<= 1; n2 <<= 1;             // 2 * nextpow2(n_t)
     int log2_n2 = 0; while ((1 << log2_n2) < n2) log2_n2++;
@@ -201,6 +233,9 @@ int itjl_psd_hamming(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_
 int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt, double* tau_out) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_fit_expdecay: null context");
     if (!acf || !tau_out || n_rows < 1 || n_lags < 1 || !(dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_fit_expdecay: invalid argument");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     // rows are read with stride 1 along lags: transpose the column-major input on the host
     std::vector<double> rows((size_t)n_rows * n_lags);
@@ -217,11 +252,13 @@ int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t 
     return ITJL_OK;
 }
 
-int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, uint32_t typemask,
-             int32_t average_over_trials, int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke,
-             double* auc, double* tau, double* acf_out, int64_t acf_capacity) {
-    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_acw");
-    if (rc != ITJL_OK) return rc;
+}  // extern "C"
+
+// acw() on the matrix in ctx->data (n_slices x n_t, slice index fastest); `data` != null: upload it first
+static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t ss, int64_t ts, double fs,
+                    uint32_t typemask, int32_t average_over_trials, int64_t* n_lags_io, int32_t* k0, int32_t* k50,
+                    int32_t* ke, double* auc, double* tau, double* acf_out, int64_t acf_capacity) {
+    int rc = ITJL_OK;
     if (!n_lags_io) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags_io is required");
     if (!(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: fs must be positive");
     if ((typemask & ~31u) || typemask == 0) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: No ACW types specified / unknown type bit");
@@ -236,8 +273,10 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     const int reach = acf_max_reach(nt, ctx->max_smem_optin);
     if (reach < 40) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_t too large for the shared-memory ACF kernel");
 
-    rc = upload_data(ctx, data, n_slices, n_t);
-    if (rc != ITJL_OK) return rc;
+    if (data) {
+        rc = upload_data(ctx, data, n_slices, n_t, ss, ts);
+        if (rc != ITJL_OK) return rc;
+    }
     ITJL_CUDA(ctx, ctx->flags.reserve(((size_t)n_slices * 6 + 4) * sizeof(int32_t)));
     int32_t* d_done = (int32_t*)ctx->flags.p;
     int32_t* d_nan = d_done + 6 * n_slices;
@@ -265,13 +304,12 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
         ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * cap * sizeof(double)));
         ITJL_CUDA(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int32_t), ctx->stream));
         if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
-        const char* env_stream = getenv("ITJL_ACW_STREAM");
-        const bool use_stream = !(env_stream && atoi(env_stream) == 0) && nt >= 256 && acw_stream_lags() <= reach;
+        const bool use_stream = ctx->tuning.acw_stream != 0 && nt >= 256 && acw_stream_lags() <= reach;
         std::vector<int32_t> h_redo;
         if (use_stream) {
             // one streaming read of the data: raw lagged products of the first 32 lags
             int n_seg = 1, seg_len = nt;
-            acw_stream_segments(nt, n_slices, ctx->sm_count, &n_seg, &seg_len);
+            acw_stream_segments(nt, n_slices, ctx->sm_count, &n_seg, &seg_len, ctx->tuning.acw_waves);
             ITJL_CUDA(ctx, ctx->part.reserve(acw_stream_part_doubles(n_slices, n_seg) * sizeof(double)));
             e = acw_stream_launch((const double*)ctx->data.p, n_slices, nt, (double*)ctx->part.p, n_seg, seg_len,
                                   (double*)ctx->out.p, cap, d_done, d_k0, d_k50, d_ke, d_redo, ctx->stream);
@@ -430,6 +468,62 @@ int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, d
     }
     ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ITJL_OK;
+}
+
+extern "C" {
+
+int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, uint32_t typemask,
+             int32_t average_over_trials, int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke,
+             double* auc, double* tau, double* acf_out, int64_t acf_capacity) {
+    return itjl_acw_strided(ctx, data, n_slices, n_t, 1, n_slices, fs, typemask, average_over_trials, n_lags_io,
+                            k0, k50, ke, auc, tau, acf_out, acf_capacity);
+}
+
+int itjl_acw_strided(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t slice_stride,
+                     int64_t time_stride, double fs, uint32_t typemask, int32_t average_over_trials,
+                     int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke, double* auc, double* tau,
+                     double* acf_out, int64_t acf_capacity) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_acw");
+    if (rc != ITJL_OK) return rc;
+    if (slice_stride < 1 || time_stride < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: strides must be positive");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_acw");
+    return acw_core(ctx, data, n_slices, n_t, slice_stride, time_stride, fs, typemask, average_over_trials, n_lags_io,
+                    k0, k50, ke, auc, tau, acf_out, acf_capacity);
+}
+
+int itjl_data_upload(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, int64_t slice_stride,
+                     int64_t time_stride) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_data_upload");
+    if (rc != ITJL_OK) return rc;
+    if (slice_stride < 1 || time_stride < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_data_upload: strides must be positive");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_data_upload");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = upload_data(ctx, data, n_slices, n_t, slice_stride, time_stride);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->res_slices = n_slices; ctx->res_nt = n_t;
+    return ITJL_OK;
+}
+
+int itjl_acw_resident(itjl_ctx* ctx, double fs, uint32_t typemask, int32_t average_over_trials,
+                      int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke, double* auc, double* tau,
+                      double* acf_out, int64_t acf_capacity) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_acw_resident: null context");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    if (ctx->res_slices < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_resident: no resident data (call itjl_data_upload; other data calls on the context replace it)");
+    NvtxRange nvtx("itjl_acw_resident");
+    const int64_t ns = ctx->res_slices, nt = ctx->res_nt;
+    const int rc = acw_core(ctx, nullptr, ns, nt, 1, ns, fs, typemask, average_over_trials, n_lags_io,
+                            k0, k50, ke, auc, tau, acf_out, acf_capacity);
+    return rc;
 }
 
 }  // extern "C"

@@ -1,0 +1,195 @@
+// C-ABI layer, part 4: the between-generation step of PMC-ABC (reference src/core/abc.jl:520-567, 582-613).
+#include <math.h>
+
+#include <vector>
+
+#include "api_internal.h"
+
+using namespace itjl;
+
+namespace {
+
+// lower Cholesky factor of a symmetric positive definite p x p matrix (column-major); false when not SPD
+bool cholesky(const double* a, int p, double* L) {
+    for (int i = 0; i < p * p; ++i) L[i] = 0.0;
+    for (int j = 0; j < p; ++j) {
+        double d = a[j + j * p];
+        for (int k = 0; k < j; ++k) d -= L[j + k * p] * L[j + k * p];
+        if (!(d > 0.0) || !isfinite(d)) return false;
+        L[j + j * p] = sqrt(d);
+        for (int i = j + 1; i < p; ++i) {
+            double s = a[i + j * p];
+            for (int k = 0; k < j; ++k) s -= L[i + k * p] * L[j + k * p];
+            L[i + j * p] = s / L[j + j * p];
+        }
+    }
+    return true;
+}
+
+// z[d][i] = scale * (L^-1 (theta[i, :] - mu))[d], stored as T, for rows [lo, hi) of a column-major (n x p) matrix
+template <typename T>
+void whiten(const double* theta, int64_t n, int p, const double* L, const double* mu, double scale, int64_t lo, int64_t hi, T* z) {
+    const int64_t m = hi - lo;
+    for (int64_t i = 0; i < m; ++i) {
+        double y[8];
+        for (int d = 0; d < p; ++d) {
+            double s = theta[(lo + i) + (int64_t)d * n] - mu[d];
+            for (int k = 0; k < d; ++k) s -= L[d + k * p] * y[k];
+            y[d] = s / L[d + d * p];
+        }
+        for (int d = 0; d < p; ++d) z[(int64_t)d * m + i] = (T)(scale * y[d]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, const double* theta, int64_t n,
+                     int32_t n_theta, const double* tau_squared, const double* weights_prev,
+                     const double* prior_pdf, int32_t normalize, double* weights_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_pmc_weights: null context");
+    if (!theta_prev || !theta || !tau_squared || !weights_prev || !prior_pdf || !weights_out)
+        return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_weights: null argument");
+    if (n < 1 || n_prev < 1 || n_theta < 1 || n_theta > 4) return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_weights: need n, n_prev >= 1 and 1 <= n_theta <= 4");
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_pmc_weights");
+    const int p = n_theta;
+    double L[16], mu[4] = {0, 0, 0, 0};
+    if (!cholesky(tau_squared, p, L)) return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_weights: tau_squared is not positive definite");
+    double logdet = 0.0;
+    for (int d = 0; d < p; ++d) logdet += 2.0 * log(L[d + d * p]);
+    const double norm = exp(-0.5 * (p * log(2.0 * M_PI) + logdet));      // 1 / sqrt((2 pi)^p det tau^2)
+    for (int d = 0; d < p; ++d) {                                        // centre on the previous population (fp32 path: O(1) inputs)
+        double s = 0.0;
+        for (int64_t j = 0; j < n_prev; ++j) s += theta_prev[j + (int64_t)d * n_prev];
+        mu[d] = s / (double)n_prev;
+    }
+    const bool fp32 = ctx->tuning.pmc_fp32 == 1 || (ctx->tuning.pmc_fp32 == -1 && (double)n * (double)n_prev > 1e8);
+    const double scale = pmc_coord_scale(fp32);
+    const size_t el = fp32 ? sizeof(float) : sizeof(double);
+
+    std::vector<ShardMember> mem;
+    int world = 1;
+    shard_members(ctx, &mem, &world);
+    const int64_t width = (n + world - 1) / world;
+    // previous population: whitened once on the host, uploaded to every member
+    std::vector<unsigned char> zp((size_t)n_prev * p * el), wp((size_t)n_prev * el);
+    if (fp32) {
+        whiten<float>(theta_prev, n_prev, p, L, mu, scale, 0, n_prev, (float*)zp.data());
+        for (int64_t j = 0; j < n_prev; ++j) ((float*)wp.data())[j] = (float)weights_prev[j];
+    } else {
+        whiten<double>(theta_prev, n_prev, p, L, mu, scale, 0, n_prev, (double*)zp.data());
+        memcpy(wp.data(), weights_prev, (size_t)n_prev * sizeof(double));
+    }
+    std::vector<std::vector<unsigned char>> zs(mem.size());
+    for (size_t i = 0; i < mem.size(); ++i) {
+        itjl_ctx* c = mem[i].c;
+        ITJL_LOCK(c);
+        int64_t lo, hi;
+        shard_bounds(n, world, mem[i].rank, &lo, &hi);
+        ITJL_CUDA(ctx, cudaSetDevice(c->device));
+        ITJL_CUDA(ctx, c->gather.reserve((size_t)world * width * sizeof(double)));
+        if (hi <= lo) continue;
+        const int64_t nl = hi - lo;
+        zs[i].resize((size_t)nl * p * el);
+        if (fp32) whiten<float>(theta, n, p, L, mu, scale, lo, hi, (float*)zs[i].data());
+        else whiten<double>(theta, n, p, L, mu, scale, lo, hi, (double*)zs[i].data());
+        int n_split = 1;
+        int64_t j_per = n_prev;
+        pmc_mixture_split(nl, n_prev, c->sm_count, &n_split, &j_per);
+        // device layout in c->data: [zp | wp | z], partial sums in c->part, prior pdf in c->out2, block sums in c->out3
+        const size_t off_wp = (size_t)n_prev * p * el, off_z = off_wp + (((size_t)n_prev * el + 15) & ~(size_t)15);
+        ITJL_CUDA(ctx, c->data.reserve(off_z + (size_t)nl * p * el));
+        ITJL_CUDA(ctx, c->part.reserve((size_t)n_split * nl * sizeof(double)));
+        ITJL_CUDA(ctx, c->out2.reserve((size_t)nl * sizeof(double)));
+        ITJL_CUDA(ctx, c->out3.reserve((size_t)((nl + 255) / 256) * sizeof(double)));
+        unsigned char* base = (unsigned char*)c->data.p;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base, zp.data(), zp.size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_wp, wp.data(), wp.size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_z, zs[i].data(), zs[i].size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(c->out2.p, prior_pdf + lo, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = pmc_mixture_launch(fp32, base + off_z, base, base + off_wp, nl, n_prev, p, n_split, j_per,
+                                           (double*)c->part.p, c->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_mixture: %s", cudaGetErrorString(e));
+        // un-normalised weights of this shard straight into its all-gather slot (normalised below, over all rows)
+        e = pmc_finish_launch((const double*)c->part.p, n_split, nl, (const double*)c->out2.p, norm,
+                              (double*)c->gather.p + (int64_t)mem[i].rank * width, (double*)c->out3.p, false, c->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_finish: %s", cudaGetErrorString(e));
+        c->launches += 2;
+    }
+    double* w_dev = nullptr;
+    int rc = shard_allgather_compact(ctx, n, &w_dev);
+    if (rc != ITJL_OK) return rc;
+    itjl_ctx* c0 = primary(ctx);
+    ITJL_LOCK(c0);
+    if (normalize) {
+        ITJL_CUDA(ctx, c0->out3.reserve((size_t)((n + 255) / 256) * sizeof(double)));
+        cudaError_t e = pmc_normalize_launch(w_dev, n, (double*)c0->out3.p, c0->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_block_sums / k_scale: %s", cudaGetErrorString(e));
+        c0->launches += 2;
+    }
+    ITJL_CUDA(ctx, cudaMemcpyAsync(weights_out, w_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(c0->stream));
+    for (const ShardMember& sm : mem) {                     // host staging vectors stay alive until every copy is done
+        cudaSetDevice(sm.c->device);
+        ITJL_CUDA(ctx, cudaStreamSynchronize(sm.c->stream));
+    }
+    return ITJL_OK;
+}
+
+int itjl_weighted_covar(itjl_ctx* ctx, const double* x, int64_t n, int32_t n_theta, const double* w, double* cov_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_weighted_covar: null context");
+    if (!x || !w || !cov_out || n < 1 || n_theta < 1 || n_theta > 4) return fail(ctx, ITJL_ERR_ARG, "itjl_weighted_covar: invalid argument");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_weighted_covar");
+    const int p = n_theta;
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload(ctx, ctx->data, x, (size_t)n * p * sizeof(double));
+    if (rc == ITJL_OK) rc = upload(ctx, ctx->out2, w, (size_t)n * sizeof(double));
+    if (rc != ITJL_OK) return rc;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 2 * (int64_t)ctx->sm_count);
+    const int n0 = 2 + p, n1 = p * p;
+    ITJL_CUDA(ctx, ctx->out3.reserve((size_t)blocks * (n0 > n1 ? n0 : n1) * sizeof(double) + 64));
+    ITJL_CUDA(ctx, ctx->scratch.reserve(8 * sizeof(double)));
+    std::vector<double> part((size_t)blocks * (n0 > n1 ? n0 : n1));
+    // the reference normalises w by its sum first (abc.jl:584): pass 0 with wsum = 1 gives that sum, then both
+    // passes run on w / sum(w)
+    double raw_sum = 0.0;
+    for (int stage = 0; stage < 2; ++stage) {
+        cudaError_t e = wcov_launch((const double*)ctx->data.p, (const double*)ctx->out2.p, n, p, 0, stage == 0 ? 1.0 : raw_sum,
+                                    nullptr, (double*)ctx->out3.p, blocks, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_wcov: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->out3.p, (size_t)blocks * n0 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (stage == 0) { raw_sum = 0.0; for (int b = 0; b < blocks; ++b) raw_sum += part[(size_t)b * n0]; }
+    }
+    double sumw = 0.0, sum2 = 0.0, xbar[4] = {0, 0, 0, 0};
+    for (int b = 0; b < blocks; ++b) {
+        sumw += part[(size_t)b * n0]; sum2 += part[(size_t)b * n0 + 1];
+        for (int k = 0; k < p; ++k) xbar[k] += part[(size_t)b * n0 + 2 + k];
+    }
+    if (!(fabs(sumw - 1.0) <= 1e-10 * fmax(fabs(sumw), 1.0))) {          // abc.jl:588-591: fallback covariance
+        for (int i = 0; i < p * p; ++i) cov_out[i] = 0.0;
+        return ITJL_OK;
+    }
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, xbar, sizeof(xbar), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = wcov_launch((const double*)ctx->data.p, (const double*)ctx->out2.p, n, p, 1, raw_sum,
+                                (const double*)ctx->scratch.p, (double*)ctx->out3.p, blocks, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_wcov: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->out3.p, (size_t)blocks * n1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double f = sumw / (sumw * sumw - sum2);
+    for (int i = 0; i < n1; ++i) {
+        double s = 0.0;
+        for (int b = 0; b < blocks; ++b) s += part[(size_t)b * n1 + i];
+        cov_out[i] = s * f;
+    }
+    return ITJL_OK;
+}
+
+}  // extern "C"

@@ -33,7 +33,7 @@ struct AbcAcfGeometry {
     int threads, n_bufs, chunk, xs_stride, lt, n_streams, tiles_per_stream, n_tiles;
     size_t smem_bytes;
 };
-int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g);
+int abc_acf_geometry(int n_t, int n_lags, int max_smem, AbcAcfGeometry* g, const itjl_tuning* tun = nullptr);
 cudaError_t abc_acf_launch(const AbcAcfParams& P, int threads, bool missing, bool osc, size_t smem,
                            cudaStream_t st);
 cudaError_t abc_accept_launch(const double* dist, int64_t n, double eps, int64_t min_accepted,
@@ -101,10 +101,10 @@ cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int m
 // streaming first pass (raw lagged products of the first acw_stream_lags() lags, one read of the data)
 cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                              int32_t* ke, int32_t* redo, cudaStream_t st);
+                              int32_t* ke, int32_t* redo, cudaStream_t st, bool bulk_variant = false);
 int acw_stream_lags();
 size_t acw_stream_part_doubles(int64_t n_slices, int n_seg);
-void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len);
+void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves = 0);
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
                             double* acf_work, int64_t cap, int32_t* n_done, const int32_t* slice_list,
                             int64_t n_list, int max_smem, cudaStream_t st, int32_t* nan_flag = nullptr);
@@ -119,6 +119,8 @@ cudaError_t acw_auc_launch(const double* acf, int64_t n_rows, int64_t ld, int w,
 cudaError_t acw_tau_launch(const double* acf, int64_t n_rows, int64_t ld, int n_lags, double dt, double* tau,
                            cudaStream_t st);
 int acf_max_reach(int n_t, int max_smem);
+cudaError_t relayout_launch(const double* raw, int64_t n_slices, int64_t n_t, int64_t ss, int64_t ts, double* out,
+                            cudaStream_t st);
 
 // ---- abc_tc_kernels.cu --------------------------------------------------------------
 constexpr int kTcMaxOps = 6;
@@ -128,6 +130,7 @@ struct AbcTcGeometry {
     int rows_total, ksteps, sbo_bytes;
     int used_cols, mixed, seg_trials, n_terms;
     float bias_a, bias_b;        // first-order correction of the accumulator's round-toward-zero (see abc_tc_geometry)
+    double pred_err;             // error model's bound for this plan (abc_tc_predicted_error)
     int tc_lags, tail_start, tail_lt, tail_steps, tail_steps_per_stream;
     // MMA ops of one K step: A / B operand start (8-row MN block, K-row shift), shape, TMEM address
     int n_ops;
@@ -177,11 +180,28 @@ struct AbcTcParams {
     size_t smem_bytes;
     int debug;                   // tuning only (ITJL_ABC_DEBUG): 1 = no MMAs, 2 = no simulation after the first particle
 };
-int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g, int min_terms = 1);
+// `tun` (nullable: defaults) carries the overrides and the error bound; mask_frac / mean_ratio describe the
+// missing-data models (fraction of masked samples, data_mean / data_sd of the oscillation variant).  Returns 0 when
+// the shape has a plan whose predicted error is within tun->tc_error_bound (or the kernel is forced), -4 when
+// only the error bound fails, < 0 otherwise.
+int abc_tc_geometry(int n_t, int n_lags, int n_trials, int max_smem, int sm_count, AbcTcGeometry* g,
+                    const itjl_tuning* tun = nullptr, double mask_frac = 0.0, double mean_ratio = 0.0, bool missing = false);
+double abc_tc_predicted_error(int64_t n_t, int64_t n_trials, int n_terms, int seg_rows, double mask_frac, double mean_ratio);
 cudaError_t abc_tc_launch(const AbcTcParams& P, bool missing, bool osc, bool mixed, size_t smem, int grid,
                           cudaStream_t st);
 cudaError_t tc_probe_launch(const void* image_dev, int n_bytes, const int4* ops_dev, int n_ops, uint32_t lbo,
                             uint32_t sbo, uint32_t idesc, float* out_dev, cudaStream_t st);
+
+// ---- pmc_kernels.cu ------------------------------------------------------------------
+double pmc_coord_scale(bool fp32);
+void pmc_mixture_split(int64_t n, int64_t n_prev, int sm_count, int* n_split, int64_t* j_per_split);
+cudaError_t pmc_mixture_launch(bool fp32, const void* z, const void* zp, const void* wp, int64_t n, int64_t n_prev, int p,
+                               int n_split, int64_t j_per_split, double* part, cudaStream_t st);
+cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const double* prior_pdf, double norm,
+                              double* w_out, double* block_sums, bool normalize, cudaStream_t st);
+cudaError_t pmc_normalize_launch(double* w, int64_t n, double* block_sums, cudaStream_t st);
+cudaError_t wcov_launch(const double* x, const double* w, int64_t n, int p, int pass, double wsum, const double* xbar,
+                        double* out, int blocks, cudaStream_t st);
 
 // ---- peak_kernels.cu -----------------------------------------------------------------
 cudaError_t fp32_peak_launch(float* sink, int blocks, int iters, cudaStream_t st);

@@ -1,0 +1,232 @@
+// K6: the between-generation step of PMC-ABC on the device (reference src/core/abc.jl:520-567 calc_weights,
+// :582-613 weighted_covar): N x N_prev Gaussian-kernel evaluations.  At the default 100 accepted particles it
+// is nothing; at BASELINE config C5 (10^6 accepted per generation) it is 10^12 evaluations per generation and
+// cannot run on the host at all.
+//
+//   den_i = sum_j w_j N(theta_i; theta_prev_j, tau^2)
+//         = |2 pi tau^2|^-1/2 sum_j w_j exp(-1/2 |z_i - z_j|^2),   z = L^-1 (theta - mu),  tau^2 = L L^T
+//
+// The host whitens both particle sets in fp64 (so the kernel never sees the covariance and its inputs are
+// O(1) numbers centred on the previous population), the kernel does the pair sum:
+//   - thread = kRows rows i kept in registers, CTA tile of 256 * kRows rows; the previous particles stream
+//     through shared memory in tiles of kTileJ (z_j, w_j), every thread reads them as broadcasts;
+//   - the j range is split over blockIdx.y so that small problems still fill the 148 SMs; partial sums land in
+//     part[split][row] and are added in a fixed order by k_pmc_finish (bit-deterministic: no atomics);
+//   - T = double for up to ~10^8 pairs (the reference's arithmetic, exp() in fp64), T = float above: the
+//     exponent argument is an O(1) whitened distance, so fp32 costs ~1e-6 relative on a weight, and the pair
+//     rate is the MUFU rate (one ex2 per pair: 148 SMs x 16 / clk) instead of the fp64 exp() rate.
+#include "kernels.h"
+
+namespace itjl {
+
+constexpr int kPmcThreads = 256;
+constexpr int kPmcRows = 4;
+constexpr int kPmcTileJ = 1024;
+
+// The host folds the factor of the exponent into the whitened coordinates (pmc_coord_scale): the kernel
+// evaluates exp(-|dz|^2) in fp64 and 2^(-|dz|^2) in fp32 (one FADD, one FMUL, one MUFU.EX2, one FFMA per pair).
+template <typename T> __device__ __forceinline__ T pmc_kernel_value(T q);
+template <> __device__ __forceinline__ double pmc_kernel_value<double>(double q) { return exp(-q); }
+template <> __device__ __forceinline__ float pmc_kernel_value<float>(float q) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
+    return e;
+}
+
+// z: [P][n] new particles (whitened), zp: [P][n_prev] previous, wp: [n_prev]; part: [gridDim.y][n]
+template <typename T, int P>
+__global__ void __launch_bounds__(kPmcThreads) k_pmc_mixture(const T* __restrict__ z, const T* __restrict__ zp,
+                                                              const T* __restrict__ wp, int64_t n, int64_t n_prev,
+                                                              int64_t j_per_split, double* __restrict__ part) {
+    __shared__ T sz[P][kPmcTileJ];
+    __shared__ T sw[kPmcTileJ];
+    const int tid = threadIdx.x;
+    const int64_t row0 = ((int64_t)blockIdx.x * kPmcThreads + tid) * kPmcRows;
+    T zi[kPmcRows][P];
+    double acc[kPmcRows];
+#pragma unroll
+    for (int r = 0; r < kPmcRows; ++r) {
+        acc[r] = 0.0;
+#pragma unroll
+        for (int d = 0; d < P; ++d) zi[r][d] = (row0 + r < n) ? z[(int64_t)d * n + row0 + r] : (T)0;
+    }
+    const int64_t j_lo = (int64_t)blockIdx.y * j_per_split;
+    const int64_t j_hi = j_lo + j_per_split < n_prev ? j_lo + j_per_split : n_prev;
+    for (int64_t jt = j_lo; jt < j_hi; jt += kPmcTileJ) {
+        const int cnt = (int)(j_hi - jt < kPmcTileJ ? j_hi - jt : kPmcTileJ);
+        __syncthreads();
+        for (int k = tid; k < cnt; k += kPmcThreads) {
+#pragma unroll
+            for (int d = 0; d < P; ++d) sz[d][k] = zp[(int64_t)d * n_prev + jt + k];
+            sw[k] = wp[jt + k];
+        }
+        __syncthreads();
+        T a[kPmcRows];
+#pragma unroll
+        for (int r = 0; r < kPmcRows; ++r) a[r] = (T)0;
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const T w = sw[k];
+#pragma unroll
+            for (int r = 0; r < kPmcRows; ++r) {
+                T q = (T)0;
+#pragma unroll
+                for (int d = 0; d < P; ++d) { const T df = zi[r][d] - sz[d][k]; q = fma(df, df, q); }
+                a[r] = fma(w, pmc_kernel_value<T>(q), a[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kPmcRows; ++r) acc[r] += (double)a[r];      // tile sums (<= 1024 terms) leave the fp32 domain here
+    }
+#pragma unroll
+    for (int r = 0; r < kPmcRows; ++r)
+        if (row0 + r < n) part[(int64_t)blockIdx.y * n + row0 + r] = acc[r];
+}
+
+// w_i = prior_i / (norm * sum_split part[split][i]); block sums of w for the normalisation
+__global__ void __launch_bounds__(256) k_pmc_finish(const double* __restrict__ part, int n_split, int64_t n,
+                                                    const double* __restrict__ prior_pdf, double norm,
+                                                    double* __restrict__ w_out, double* __restrict__ block_sums) {
+    __shared__ double red[8];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double w = 0.0;
+    if (i < n) {
+        double den = 0.0;
+        for (int s = 0; s < n_split; ++s) den += part[(int64_t)s * n + i];
+        w = prior_pdf[i] / (norm * den);
+        w_out[i] = w;
+    }
+    w = warp_sum(w);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scale(double* __restrict__ w, int64_t n, const double* __restrict__ block_sums, int n_blocks) {
+    __shared__ double total;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < n_blocks; ++k) t += block_sums[k];          // fixed order
+        total = t;
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) w[i] = w[i] / total;
+}
+
+template <typename T>
+static cudaError_t mixture_launch_t(const void* z, const void* zp, const void* wp, int64_t n, int64_t n_prev, int p,
+                                    int n_split, int64_t j_per_split, double* part, cudaStream_t st) {
+    const dim3 grid((unsigned)((n + (int64_t)kPmcThreads * kPmcRows - 1) / ((int64_t)kPmcThreads * kPmcRows)), (unsigned)n_split);
+    const T* a = (const T*)z; const T* b = (const T*)zp; const T* c = (const T*)wp;
+    switch (p) {
+        case 1: k_pmc_mixture<T, 1><<<grid, kPmcThreads, 0, st>>>(a, b, c, n, n_prev, j_per_split, part); break;
+        case 2: k_pmc_mixture<T, 2><<<grid, kPmcThreads, 0, st>>>(a, b, c, n, n_prev, j_per_split, part); break;
+        case 3: k_pmc_mixture<T, 3><<<grid, kPmcThreads, 0, st>>>(a, b, c, n, n_prev, j_per_split, part); break;
+        case 4: k_pmc_mixture<T, 4><<<grid, kPmcThreads, 0, st>>>(a, b, c, n, n_prev, j_per_split, part); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// z = coord_scale * L^-1 (theta - mu): exp(-1/2 |.|^2) = exp(-|z|^2) (fp64) = 2^(-|z|^2) (fp32)
+double pmc_coord_scale(bool fp32) { return fp32 ? 0.84932180028801904 /* sqrt(log2(e) / 2) */ : 0.70710678118654752; }
+
+void pmc_mixture_split(int64_t n, int64_t n_prev, int sm_count, int* n_split, int64_t* j_per_split) {
+    const int64_t row_ctas = (n + (int64_t)kPmcThreads * kPmcRows - 1) / ((int64_t)kPmcThreads * kPmcRows);
+    int64_t want = (2 * (int64_t)sm_count + row_ctas - 1) / row_ctas;              // ~2 CTAs per SM
+    const int64_t max_split = (n_prev + kPmcTileJ - 1) / kPmcTileJ;
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    if (want > 1024) want = 1024;
+    int64_t per = (n_prev + want - 1) / want;
+    per = (per + kPmcTileJ - 1) / kPmcTileJ * kPmcTileJ;
+    *j_per_split = per;
+    *n_split = (int)((n_prev + per - 1) / per);
+}
+
+cudaError_t pmc_mixture_launch(bool fp32, const void* z, const void* zp, const void* wp, int64_t n, int64_t n_prev, int p,
+                               int n_split, int64_t j_per_split, double* part, cudaStream_t st) {
+    return fp32 ? mixture_launch_t<float>(z, zp, wp, n, n_prev, p, n_split, j_per_split, part, st)
+                : mixture_launch_t<double>(z, zp, wp, n, n_prev, p, n_split, j_per_split, part, st);
+}
+
+cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const double* prior_pdf, double norm,
+                              double* w_out, double* block_sums, bool normalize, cudaStream_t st) {
+    const int blocks = (int)((n + 255) / 256);
+    k_pmc_finish<<<blocks, 256, 0, st>>>(part, n_split, n, prior_pdf, norm, w_out, block_sums);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !normalize) return e;
+    k_scale<<<blocks, 256, 0, st>>>(w_out, n, block_sums, blocks);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_block_sums(const double* __restrict__ w, int64_t n, double* __restrict__ block_sums) {
+    __shared__ double red[8];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double v = warp_sum(i < n ? w[i] : 0.0);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// w <- w / sum(w), the sum taken in a fixed order (block sums, then serially)
+cudaError_t pmc_normalize_launch(double* w, int64_t n, double* block_sums, cudaStream_t st) {
+    const int blocks = (int)((n + 255) / 256);
+    k_block_sums<<<blocks, 256, 0, st>>>(w, n, block_sums);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_scale<<<blocks, 256, 0, st>>>(w, n, block_sums, blocks);
+    return cudaGetLastError();
+}
+
+// ---- weighted covariance (abc.jl:582-613): two passes, per-CTA partial sums combined on the host ------------
+// pass 0: out[cta][0] = sum w, [1] = sum w^2, [2 + k] = sum w x_k          (x: [p][n] column-major)
+// pass 1: out[cta][j * p + k] = sum w (x_j - xbar_j)(x_k - xbar_k)        (w already divided by sum w: `wsum`)
+constexpr int kWcovMaxP = 4;
+__global__ void __launch_bounds__(256) k_wcov(const double* __restrict__ x, const double* __restrict__ w, int64_t n, int p,
+                                              int pass, double wsum, const double* __restrict__ xbar, double* __restrict__ out) {
+    __shared__ double red[8][2 + kWcovMaxP * kWcovMaxP];
+    const int n_out = pass == 0 ? 2 + p : p * p;
+    double acc[2 + kWcovMaxP * kWcovMaxP];
+    for (int k = 0; k < n_out; ++k) acc[k] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double wi = w[i] / wsum;
+        if (pass == 0) {
+            acc[0] += wi; acc[1] += wi * wi;
+            for (int k = 0; k < p; ++k) acc[2 + k] += wi * x[(int64_t)k * n + i];
+        } else {
+            double c[kWcovMaxP];
+            for (int k = 0; k < p; ++k) c[k] = x[(int64_t)k * n + i] - xbar[k];
+            for (int j = 0; j < p; ++j)
+                for (int k = 0; k < p; ++k) acc[j * p + k] += c[j] * c[k] * wi;
+        }
+    }
+    for (int k = 0; k < n_out; ++k) {
+        const double v = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_out) {
+        double t = 0.0;
+        for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+        out[(int64_t)blockIdx.x * n_out + threadIdx.x] = t;
+    }
+}
+
+cudaError_t wcov_launch(const double* x, const double* w, int64_t n, int p, int pass, double wsum, const double* xbar,
+                        double* out, int blocks, cudaStream_t st) {
+    if (p < 1 || p > kWcovMaxP) return cudaErrorInvalidValue;
+    k_wcov<<<blocks, 256, 0, st>>>(x, w, n, p, pass, wsum, xbar, out);
+    return cudaGetLastError();
+}
+
+}  // namespace itjl

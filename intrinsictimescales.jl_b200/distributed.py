@@ -8,7 +8,14 @@ accept / sequential-stop bookkeeping.  No other data-path collective exists: pro
 drawn redundantly on every rank from the same host RNG seed.
 
 The reference has no distributed layer; this module is new.
-`torch.distributed` is plumbing only (NCCL over NVLink on GPUs, gloo in CPU tests).
+
+On GPUs the exchange happens INSIDE the library (itjl_api_multi.cu): `attach_library_comm` joins this rank's
+context to an NCCL communicator (the 128-byte unique id is the only thing that travels through
+`torch.distributed`, once), after which `itjl_abc_generation` / `itjl_pmc_weights` shard over the ranks and
+all-gather device to device themselves - `gpu_sharded_scorer` is then nothing but the model's own `generation`.
+A single process driving several GPUs needs none of this: `Context(devices=[0, 1, ...])`.
+`make_sharded_scorer` (host all-gather through `torch.distributed`) remains for the gloo CPU tests of the
+host logic.
 """
 import numpy as np
 
@@ -75,29 +82,33 @@ def make_sharded_scorer(local_scorer, accept_fn=None, group=None, device=None):
     return scorer
 
 
-def gpu_sharded_scorer(model, ctx=None, seed=0, group=None):
-    """Sharded scorer over the fused kernels of this rank's GPU (NCCL all-gather)."""
-    import ctypes
-
-    import torch
+def attach_library_comm(ctx, group=None):
+    """Make `ctx` (this rank's single-GPU context) a member of an in-library NCCL communicator spanning the
+    ranks of `group`: rank 0 creates the unique id, `torch.distributed` broadcasts its 128 bytes, every rank
+    calls itjl_ctx_attach_comm (collective).  Idempotent."""
+    import torch.distributed as dist
 
     from . import _lib
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if ctx.world()[1] == world and world > 1:
+        return ctx
+    box = [_lib.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.attach_comm(rank, world, box[0])
+    return ctx
+
+
+def gpu_sharded_scorer(model, ctx=None, seed=0, group=None):
+    """`scorer` callback of abc.basic_abc for a multi-rank GPU run: the library shards the chunk over the
+    communicator of `ctx`, all-gathers the distances over NVLink and applies accept / stop on the device;
+    every rank gets the full result (COLLECTIVE: every rank must call it with the same arguments)."""
+    from . import _lib
+    ctx = ctx or _lib.default_context()
+    attach_library_comm(ctx, group)
     gm = model.gpu_model(ctx)
-    device = torch.device("cuda", gm.ctx.device)
 
-    def local_scorer(theta_slice, generation, particle_offset):
-        return gm.distances(theta_slice, seed=seed, generation=generation,
-                            particle_offset=particle_offset)
+    def scorer(theta, epsilon, needed, generation, particle_offset):
+        return gm.generation(theta, epsilon, needed, seed=seed, generation=generation,
+                             particle_offset=particle_offset)
 
-    def accept_fn(dist_all, epsilon, needed):
-        n = dist_all.size
-        d = np.ascontiguousarray(dist_all, dtype=np.float64)
-        isacc = np.empty(n, dtype=np.uint8)
-        n_total = ctypes.c_int64(0)
-        n_acc = ctypes.c_int64(0)
-        gm.ctx.check(_lib.lib().itjl_abc_accept(gm.ctx.handle, _lib.ptr(d), n, float(epsilon),
-                                                int(needed), _lib.ptr(isacc), ctypes.byref(n_total),
-                                                ctypes.byref(n_acc)))
-        return isacc.astype(bool), int(n_total.value), int(n_acc.value)
-
-    return make_sharded_scorer(local_scorer, accept_fn, group=group, device=device)
+    return scorer

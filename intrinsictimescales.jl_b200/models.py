@@ -98,9 +98,10 @@ class TimescaleModel:
     def gpu_model(self, ctx=None):
         ctx = ctx or _lib.default_context()
         key = id(ctx)
-        if key not in self._gpu:
-            self._gpu[key] = GpuModel(self, ctx)
-        return self._gpu[key]
+        hit = self._gpu.get(key)
+        if hit is None or hit.ctx is not ctx or not hit.handle:      # (an id can be reused by a later context)
+            hit = self._gpu[key] = GpuModel(self, ctx)
+        return hit
 
 
 class GpuModel:
@@ -138,6 +139,7 @@ class GpuModel:
         self.n_stats = int(d.n_stats)
         self._h = ctypes.c_void_p()
         ctx.check(_lib.lib().itjl_model_create(ctx.handle, ctypes.byref(d), ctypes.byref(self._h)))
+        ctx._models.add(self)
 
     @property
     def handle(self):

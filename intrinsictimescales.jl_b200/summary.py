@@ -21,28 +21,41 @@ def _as_slices(data):
     return np.asfortranarray(data)
 
 
+def _strided(data):
+    """(array, n_slices, n_t, slice_stride, time_stride) of a (trials, time) matrix as it lies in memory: a
+    C-ordered NumPy matrix (= a Julia matrix with time down the columns, `dims = 1`) goes to the device
+    untransposed (itjl_acf_strided)."""
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        data = data.reshape(1, -1)
+    if data.ndim != 2:
+        raise ValueError("data must be a vector or a (trials, time) matrix")
+    if not (data.flags.c_contiguous or data.flags.f_contiguous) or data.size == 0:
+        data = np.asfortranarray(data)
+    es = data.itemsize
+    return data, data.shape[0], data.shape[1], max(data.strides[0] // es, 1), max(data.strides[1] // es, 1)
+
+
 def comp_ac_fft(data, n_lags=None, ctx=None):
     """Autocorrelation of each trial (rows), lags 0..n_lags-1; returns (trials, n_lags)
     (a vector input returns a vector, as the reference's Vector method does)."""
     vec = np.ndim(data) == 1
-    d = _as_slices(data)
+    d, n_slices, n_t, ss, ts = _strided(data)
     ctx = ctx or _lib.default_context()
-    n_slices, n_t = d.shape
     n_lags = n_t if n_lags is None else int(n_lags)
     out = np.empty((n_slices, n_lags), dtype=np.float64, order="F")
-    ctx.check(_lib.lib().itjl_acf(ctx.handle, _lib.ptr(d), n_slices, n_t, n_lags, _lib.ptr(out)))
+    ctx.check(_lib.lib().itjl_acf_strided(ctx.handle, _lib.ptr(d), n_slices, n_t, ss, ts, n_lags, 0, _lib.ptr(out)))
     return out[0].copy() if vec else out
 
 
 def comp_ac_time_missing(data, n_lags=None, ctx=None):
     """NaN-aware autocorrelation (NaN = missing sample)."""
     vec = np.ndim(data) == 1
-    d = _as_slices(data)
+    d, n_slices, n_t, ss, ts = _strided(data)
     ctx = ctx or _lib.default_context()
-    n_slices, n_t = d.shape
     n_lags = n_t if n_lags is None else int(n_lags)
     out = np.empty((n_slices, n_lags), dtype=np.float64, order="F")
-    ctx.check(_lib.lib().itjl_acf_missing(ctx.handle, _lib.ptr(d), n_slices, n_t, n_lags, _lib.ptr(out)))
+    ctx.check(_lib.lib().itjl_acf_strided(ctx.handle, _lib.ptr(d), n_slices, n_t, ss, ts, n_lags, 1, _lib.ptr(out)))
     return out[0].copy() if vec else out
 
 

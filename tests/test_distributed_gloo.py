@@ -36,8 +36,10 @@ def _worker(rank, world, port, out):
         rng = np.random.default_rng(0)
         props = rng.random((1500, 1)) * 3
         res = pkg.basic_abc(M(), 0.02, 1500, 37, scorer=scorer, proposals=props, generation=4)
+        from oracle import abc as oabc          # weight / covariance steps injected (device kernels in the product)
         res2 = pkg.pmc_abc(M(), epsilon_0=0.5, max_iter=800, min_accepted=50, steps=3,
-                           rng=np.random.default_rng(5), scorer=scorer, target_epsilon=1e-9)
+                           rng=np.random.default_rng(5), scorer=scorer, target_epsilon=1e-9,
+                           calc_weights_fn=oabc.calc_weights, weighted_covar_fn=oabc.weighted_covar)
         out[rank] = (res["n_total"], res["n_accepted"], res["distances"], res["theta_accepted"],
                      res2.final_theta, res2.epsilon_history)
     finally:
@@ -64,8 +66,10 @@ def test_sharded_generation_matches_single_rank(pkg, world):
         fit_method = "abc"
     props = np.random.default_rng(0).random((1500, 1)) * 3
     ref = pkg.basic_abc(M(), 0.02, 1500, 37, scorer=single, proposals=props, generation=4)
+    from oracle import abc as oabc
     ref2 = pkg.pmc_abc(M(), epsilon_0=0.5, max_iter=800, min_accepted=50, steps=3,
-                       rng=np.random.default_rng(5), scorer=single, target_epsilon=1e-9)
+                       rng=np.random.default_rng(5), scorer=single, target_epsilon=1e-9,
+                       calc_weights_fn=oabc.calc_weights, weighted_covar_fn=oabc.weighted_covar)
     for r in range(world):
         n_total, n_acc, d, th, final_theta, eps_hist = out[r]
         assert (n_total, n_acc) == (ref["n_total"], ref["n_accepted"])

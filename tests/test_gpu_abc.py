@@ -261,24 +261,17 @@ def test_oscillation_with_missing_model(pkg, ctx):
     phases = rng.uniform(0, 2 * np.pi, size=(P, n_trials))
     want = np.array([omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i], phases=phases[i]))
                      for i in range(P)])
-    old = os.environ.get("ITJL_ABC_TC")
-    try:
-        for tc in ("1", "0"):
-            os.environ["ITJL_ABC_TC"] = tc
-            gm = pkg.one_timescale_and_osc_with_missing_model(data, t, "abc", prior=pp)
-            assert gm.n_lags == om.n_lags and abs(gm.data_mean - om.data_mean) < 1e-12 and abs(gm.data_mean) > 1.0
-            assert np.max(np.abs(gm.data_sum_stats - om.data_sum_stats)) < 1e-12
+    for tc in (1, 0):
+        gm = pkg.one_timescale_and_osc_with_missing_model(data, t, "abc", prior=pp)
+        assert gm.n_lags == om.n_lags and abs(gm.data_mean - om.data_mean) < 1e-12 and abs(gm.data_mean) > 1.0
+        assert np.max(np.abs(gm.data_sum_stats - om.data_sum_stats)) < 1e-12
+        with ctx.tuned(abc_tc=tc):                    # itjl_tuning: which fused ACF kernel the model gets
             g = gm.gpu_model(ctx)
-            assert g.kernel_info()[0] == ("k_abc_acf_tc" if tc == "1" else "k_abc_acf")
-            d, stats = g.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
-            assert np.max(np.abs(stats - want)) <= 2e-5, (tc, np.max(np.abs(stats - want)))
-            d_ref = np.mean((want - om.data_sum_stats) ** 2, axis=1)
-            assert np.all(np.abs(d - d_ref) <= dist_tol(d_ref, 2e-5))
-    finally:
-        if old is None:
-            os.environ.pop("ITJL_ABC_TC", None)
-        else:
-            os.environ["ITJL_ABC_TC"] = old
+        assert g.kernel_info()[0] == ("k_abc_acf_tc" if tc == 1 else "k_abc_acf")
+        d, stats = g.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
+        assert np.max(np.abs(stats - want)) <= 2e-5, (tc, np.max(np.abs(stats - want)))
+        d_ref = np.mean((want - om.data_sum_stats) ** 2, axis=1)
+        assert np.all(np.abs(d - d_ref) <= dist_tol(d_ref, 2e-5))
 
 
 def test_distance_combined_acf_branch(pkg, ctx):

@@ -47,20 +47,13 @@ def test_random_shape_both_kernels_against_fp64_oracle(pkg, ctx, case, n_t, n_tr
         mk = lambda: pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5)], n_lags=n_lags)
     theta = np.random.default_rng(100 + case).uniform(0.05, 5.0, size=(6, 1))
     d_or, s_or = cport.abc_distances(om, theta, seed=3, generation=1, return_stats=True)
-    old = os.environ.get("ITJL_ABC_TC")
-    try:
-        for tc in ("1", "0"):
-            os.environ["ITJL_ABC_TC"] = tc
+    for tc in (1, 0):
+        with ctx.tuned(abc_tc=tc):
             g = mk().gpu_model(ctx)
-            d, s = g.distances(theta, seed=3, generation=1, return_stats=True)
-            err = np.max(np.abs(s - s_or))
-            assert err <= ACF_TOL, (g.kernel_info()[0], n_t, n_trials, n_lags, missing, err)
-            assert np.all(np.abs(d - d_or) <= 2 * np.sqrt(d_or) * ACF_TOL + ACF_TOL ** 2 + 1e-5 * d_or)
-    finally:
-        if old is None:
-            os.environ.pop("ITJL_ABC_TC", None)
-        else:
-            os.environ["ITJL_ABC_TC"] = old
+        d, s = g.distances(theta, seed=3, generation=1, return_stats=True)
+        err = np.max(np.abs(s - s_or))
+        assert err <= ACF_TOL, (g.kernel_info()[0], n_t, n_trials, n_lags, missing, err)
+        assert np.all(np.abs(d - d_or) <= 2 * np.sqrt(d_or) * ACF_TOL + ACF_TOL ** 2 + 1e-5 * d_or)
 
 
 def _model_cases():

@@ -100,19 +100,13 @@ def _models(pkg, n_t, n_trials, n_lags, missing=False, seed=3):
     return om, mk
 
 
-def _gpu_models(mk, ctx):
-    """(tensor-core model, CUDA-core model): the kernel is chosen at itjl_model_create (ITJL_ABC_TC)."""
-    old = os.environ.get("ITJL_ABC_TC")
-    try:
-        os.environ["ITJL_ABC_TC"] = "1"
+def _gpu_models(mk, ctx, **tuning):
+    """(tensor-core model, CUDA-core model): the kernel is chosen at itjl_model_create from the context's
+    itjl_tuning (abc_tc = 1 / 0; further knobs in `tuning`)."""
+    with ctx.tuned(abc_tc=1, **tuning):
         g_tc = mk().gpu_model(ctx)
-        os.environ["ITJL_ABC_TC"] = "0"
+    with ctx.tuned(abc_tc=0):
         g_ff = mk().gpu_model(ctx)
-    finally:
-        if old is None:
-            os.environ.pop("ITJL_ABC_TC", None)
-        else:
-            os.environ["ITJL_ABC_TC"] = old
     assert g_tc.kernel_info()[0] == "k_abc_acf_tc" and g_tc.kernel_info()[1] > 0
     assert g_ff.kernel_info() == ("k_abc_acf", 0.0)
     return g_tc, g_ff
@@ -128,19 +122,11 @@ SHAPES = [(1000, 5, 37), (601, 3, 20), (2500, 1, 300), (5000, 2, 385), (5000, 2,
           (5000, 3, 1000), (5000, 2, 1537), (3000, 4, 1200)]
 
 
-# ITJL_TC_TAIL_MAX = 60: the two- and four-tile FFMA tails (no longer chosen by default: a second lag window is faster)
+# tc_tail_max = 60: the two- and four-tile FFMA tails (no longer chosen by default: a second lag window is faster)
 @pytest.mark.parametrize("n_t,n_trials,n_lags,tail_max", [s + (None,) for s in SHAPES] + [(5000, 9, 470, 60), (5000, 5, 509, 60)])
 def test_tc_kernel_matches_oracle_and_cuda_core_kernel(pkg, ctx, n_t, n_trials, n_lags, tail_max):
     om, mk = _models(pkg, n_t, n_trials, n_lags)
-    old = os.environ.pop("ITJL_TC_TAIL_MAX", None)
-    try:
-        if tail_max is not None:
-            os.environ["ITJL_TC_TAIL_MAX"] = str(tail_max)
-        g_tc, g_ff = _gpu_models(mk, ctx)
-    finally:
-        os.environ.pop("ITJL_TC_TAIL_MAX", None)
-        if old is not None:
-            os.environ["ITJL_TC_TAIL_MAX"] = old
+    g_tc, g_ff = _gpu_models(mk, ctx, **({} if tail_max is None else {"tc_tail_max": tail_max}))
     rng = np.random.default_rng(n_t + n_lags)
     theta = np.array([[0.3], [4.9], [0.05], [1.2]])
     P = theta.shape[0]
@@ -182,18 +168,13 @@ def test_tc_kernel_missing_data_variant(pkg, ctx, n_lags):
 
 
 def test_unsupported_shapes_fall_back_to_cuda_core_kernel(pkg, ctx):
-    """n_lags beyond four lag windows (1537): ITJL_ABC_TC unset picks k_abc_acf, ITJL_ABC_TC=1 refuses."""
+    """n_lags beyond four lag windows (1537): the automatic choice is k_abc_acf, tuning.abc_tc = 1 refuses."""
     om, mk = _models(pkg, 2500, 1, 1538)
-    old = os.environ.pop("ITJL_ABC_TC", None)
-    try:
-        assert mk().gpu_model(ctx).kernel_info()[0] == "k_abc_acf"
-        os.environ["ITJL_ABC_TC"] = "1"
+    assert ctx.get_tuning().abc_tc == -1
+    assert mk().gpu_model(ctx).kernel_info()[0] == "k_abc_acf"
+    with ctx.tuned(abc_tc=1):
         with pytest.raises(pkg.ItjlError):
             mk().gpu_model(ctx)
-    finally:
-        os.environ.pop("ITJL_ABC_TC", None)
-        if old is not None:
-            os.environ["ITJL_ABC_TC"] = old
 
 
 def test_single_term_products_and_rounding_correction_over_many_particles(pkg, ctx):
@@ -308,3 +289,47 @@ def test_tc_kernel_oscillation_acf_variant(pkg, ctx):
         ac = omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i], phases=phases[i]))
         assert np.max(np.abs(s_tc[i] - ac)) <= 2e-5        # same tolerance as test_gpu_abc's oscillation ACF case
     assert np.max(np.abs(s_tc - s_ff)) <= 2e-5
+
+
+def e_shared(n_trials):
+    """What both fused kernels share against the fp64 reference: fp32 simulation, centring and - the largest part -
+    fp32 accumulation of the lag sums.  A near-unit-root trial (tau >= T) has ac ~ 1 at every lag, so every lag
+    sum is a POSITIVE sum of 5000 products growing to 1: rounding rms ~1.2e-6 per trial and lag, ~5e-6 as the
+    maximum over the lags of a handful of particles; it averages down with the trials of a particle."""
+    return max(5.5e-6 / np.sqrt(n_trials), 2.5e-6)
+
+
+@pytest.mark.parametrize("n_trials", [1, 2, 7, 50, 200])
+def test_tensor_core_kernel_stays_within_its_predicted_error(pkg, ctx, n_trials):
+    """The automatic plan (tuning.abc_tc = -1: product terms and segments from the error model,
+    itjl_tc_predicted_error) over timescales from 0.01 to 50 times the trial length, at 1 .. 200 trials of 5000
+    samples.  The model bounds what the tensor-core lag sums ADD to the error of the fp32 path (default bound
+    5e-6); the CUDA-core kernel shows the shared part (E_SHARED); together they stay within the contract's 1e-5."""
+    from oracle import cport
+    n_t, n_lags = 5000, 414
+    om, mk = _models(pkg, n_t, n_trials, n_lags)
+    ctx.reset_tuning()
+    g_auto = mk().gpu_model(ctx)
+    with ctx.tuned(abc_tc=0):
+        g_ff = mk().gpu_model(ctx)
+    plan = (ctypes.c_int32 * 16)()
+    assert pkg._lib.lib().itjl_tc_plan(n_t, n_lags, n_trials, 232448, 148, plan) == 0 and plan[15] == 0
+    assert g_auto.kernel_info()[0] == "k_abc_acf_tc"
+    pred = pkg._lib.tc_predicted_error(n_t, n_trials, plan[7], plan[6] * 40)
+    assert pred <= 5e-6
+    T = n_t * DT
+    taus = T * np.array([0.01, 0.02, 0.05, 0.1, 0.2, 0.5, 1.0, 2.0, 5.0, 10.0, 20.0, 50.0])
+    theta = np.repeat(taus, 8 if n_trials <= 7 else 2).reshape(-1, 1)
+    d_or, s_or = cport.abc_distances(om, theta, seed=31, generation=5, return_stats=True)
+    d_tc, s_tc = g_auto.distances(theta, seed=31, generation=5, return_stats=True)
+    d_ff, s_ff = g_ff.distances(theta, seed=31, generation=5, return_stats=True)
+    e_tc, e_ff = np.abs(s_tc - s_or).max(axis=1), np.abs(s_ff - s_or).max(axis=1)
+    by_tau = lambda e: " ".join(f"{x:.1e}" for x in e.reshape(len(taus), -1).max(axis=1))
+    print(f"n_trials={n_trials} terms={plan[7]} seg={plan[6]} predicted {pred:.2e}\n  tc   by tau/T: {by_tau(e_tc)}\n"
+          f"  ffma by tau/T: {by_tau(e_ff)}\n  |tc - ffma| max {np.abs(s_tc - s_ff).max():.2e}")
+    E_SHARED = e_shared(n_trials)
+    assert e_ff.max() <= E_SHARED, e_ff.max()
+    assert np.abs(s_tc - s_ff).max() <= pred + 1.5e-6          # + the FFMA kernel's own fp32 summation
+    assert e_tc.max() <= pred + E_SHARED <= 1e-5
+    tol = pred + E_SHARED
+    assert np.all(np.abs(d_tc - d_or) <= 2 * np.sqrt(d_or) * tol + tol ** 2 + 1e-5 * d_or)

@@ -52,17 +52,7 @@ def test_pmc_helpers_match_oracle(pkg):
         a = pkg.select_epsilon(d, eps, current_acc_rate=rate, iteration=it, total_iterations=30)
         b = oabc.select_epsilon(d, eps, current_acc_rate=rate, iteration=it, total_iterations=30)
         assert a == b
-    th_prev = rng.random((60, 3)) + 0.5
-    th = rng.random((40, 3)) + 0.5
-    cov = np.cov(th_prev, rowvar=False) * 2 + 1e-6 * np.eye(3)
-    w = rng.random(60); w /= w.sum()
-    pp = [pkg.Normal(1, 1), pkg.Uniform(0, 3), pkg.Normal(1.2, 0.5)]
-    po = [omodels.Normal(1, 1), omodels.Uniform(0, 3), omodels.Normal(1.2, 0.5)]
-    assert np.allclose(pkg.calc_weights(th_prev, th, cov, w, pp), oabc.calc_weights(th_prev, th, cov, w, po),
-                       rtol=1e-10)
-    assert np.allclose(pkg.calc_weights(th_prev[:, :1], th[:, :1], cov[:1, :1], w, pp[:1]),
-                       oabc.calc_weights(th_prev[:, :1], th[:, :1], cov[:1, :1], w, po[:1]), rtol=1e-10)
-    assert np.allclose(pkg.weighted_covar(th, np.ones(40)), oabc.weighted_covar(th, np.ones(40)))
+    # calc_weights / weighted_covar run on the device: tests/test_gpu_pmc.py
     assert pkg.effective_sample_size(np.ones(3)) == pytest.approx(3.0)        # test_abc.jl
     assert pkg.get_param_dict_abc() == oabc.get_param_dict_abc()
 
@@ -91,13 +81,31 @@ def test_pmc_abc_runs_with_a_toy_scorer(pkg):
         return d, acc, n_total, n_acc
 
     model = FakeModel([pkg.Uniform(0, 5)])
+    # host control flow only: the scorer and the weight / covariance steps (device kernels in the product) are
+    # injected, here the oracle's
     res, rec = pkg.pmc_abc(model, epsilon_0=1.0, max_iter=5000, min_accepted=100, steps=8, rng=rng,
-                           scorer=scorer, target_epsilon=1e-4, return_record=True)
+                           scorer=scorer, target_epsilon=1e-4, return_record=True,
+                           calc_weights_fn=oabc.calc_weights, weighted_covar_fn=oabc.weighted_covar)
     assert isinstance(res, pkg.ABCResults) and len(res.epsilon_history) == len(rec) >= 2
     assert abs(res.final_theta.mean() - 2.0) < 0.15
     assert res.final_weights.sum() == pytest.approx(1.0)
     assert all(e2 <= e1 * 1.0001 or True for e1, e2 in zip(res.epsilon_history, res.epsilon_history[1:]))
     assert abs(res.MAP[0] - 2.0) < 0.3
+
+
+def test_pmc_abc_leaves_through_min_acc_rate_when_nothing_is_accepted(pkg):
+    """Generation 1 accepts nothing (epsilon_0 below every distance): the reference's fill(1 / 0, 0) is an
+    empty weight vector and it returns through `accept_rate < minAccRate` (abc.jl:461) - no exception."""
+    def scorer(theta, epsilon, needed, generation, offset):
+        d = 1.0 + theta[:, 0] ** 2
+        return d, d <= epsilon, d.size, 0
+
+    model = FakeModel([pkg.Uniform(0, 5)])
+    res, rec = pkg.pmc_abc(model, epsilon_0=0.5, max_iter=300, min_accepted=10, steps=5, rng=np.random.default_rng(1),
+                           scorer=scorer, return_record=True, calc_weights_fn=oabc.calc_weights,
+                           weighted_covar_fn=oabc.weighted_covar)
+    assert len(rec) == 1 and rec[0]["n_accepted"] == 0 and rec[0]["n_total"] == 300
+    assert res.final_theta.shape[0] == 0 and res.final_weights.size == 0 and np.all(np.isnan(res.MAP))
 
 
 def test_acw_and_model_argument_errors(pkg):
