@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N benchmarks/multi_gpu_check.py: the particle-sharded scorer over N GPUs (NCCL
-all-gather of distances) must return exactly what one GPU returns - distances bit-identical, same stop index,
-same accepted set, same PMC history (results invariant to the GPU count)."""
+"""torchrun --nproc-per-node N benchmarks/multi_gpu_check.py: particles sharded over N GPUs INSIDE the library
+(itjl_ctx_attach_comm: one process per GPU, ncclAllGather of distances / weights device to device) must return
+exactly what one GPU returns - distances bit-identical, same stop index, same accepted set, same PMC history,
+same PMC weights (results invariant to the GPU count).  Rank 0 then repeats the comparison with ONE
+process driving all N GPUs (itjl_ctx_create_multi, what a Julia host uses)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,42 +17,67 @@ torch.cuda.set_device(local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pkg = ge.load_package()
-
-
-def _tun(ctx=None):
-    """ITJL_* environment switches of this script -> the context's itjl_tuning (benchmarks/_tuning.py)."""
-    import os as _os, sys as _sys
-    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
-    import _tuning
-    return _tuning.from_env(ctx or pkg.default_context())
-
 from importlib import import_module
 distributed = import_module("itjl_b200.distributed")
 from oracle import ou as oou
-ctx = pkg.default_context(local)
+
+ctx = pkg.Context(local)                     # joins the communicator: its calls are collective
+distributed.attach_library_comm(ctx)
+solo = pkg.Context(local)                    # plain single-GPU context of this rank
+assert ctx.world() == (rank, world, 1) and solo.world() == (0, 1, 1)
+
+
+def compare(model, sharded_ctx, tag):
+    scorer = distributed.gpu_sharded_scorer(model, ctx=sharded_ctx, seed=3) if sharded_ctx is ctx else None
+    props = np.random.default_rng(1).uniform(0.05, 5.0, size=(4001, 1))
+    d_all = model.gpu_model(solo).distances(props, seed=3, generation=2)
+    d_sh = model.gpu_model(sharded_ctx).distances(props, seed=3, generation=2)
+    eps = float(np.sort(d_all)[400] * 0.5 + np.sort(d_all)[401] * 0.5)
+    kw = dict(scorer=scorer) if scorer else dict(ctx=sharded_ctx, seed=3)
+    sharded = pkg.basic_abc(model, eps, 4001, 333, proposals=props, generation=2, **kw)
+    single = pkg.basic_abc(model, eps, 4001, 333, proposals=props, seed=3, generation=2, ctx=solo)
+    same = (sharded["n_total"] == single["n_total"] and sharded["n_accepted"] == single["n_accepted"]
+            and np.array_equal(sharded["distances"], single["distances"]) and np.array_equal(sharded["theta_accepted"], single["theta_accepted"])
+            and np.array_equal(d_sh, d_all))
+    pk = dict(epsilon_0=1.0, max_iter=3000, min_accepted=100, steps=4, target_epsilon=1e-9)
+    r_sh = pkg.pmc_abc(model, rng=np.random.default_rng(7), seed=3, ctx=sharded_ctx, **pk)
+    r_si = pkg.pmc_abc(model, rng=np.random.default_rng(7), seed=3, ctx=solo, **pk)
+    same_pmc = (np.array_equal(r_sh.final_theta, r_si.final_theta) and r_sh.epsilon_history == r_si.epsilon_history
+                and np.array_equal(r_sh.final_weights, r_si.final_weights))
+    # PMC weights at a size where the rows really spread over the GPUs (fp32 pair sums above 1e8 pairs)
+    rg = np.random.default_rng(3)
+    th_prev, th = rg.gamma(4.0, 0.1, (15000, 1)), rg.gamma(4.0, 0.1, (9001, 1))
+    w = rg.uniform(0.5, 1.5, 15000); w /= w.sum()
+    cov = np.array([[2.0 * th_prev.var()]])
+    w_sh = pkg.calc_weights(th_prev, th, cov, w, [pkg.Uniform(0, 5)], ctx=sharded_ctx)
+    w_si = pkg.calc_weights(th_prev, th, cov, w, [pkg.Uniform(0, 5)], ctx=solo)
+    same_w = np.array_equal(w_sh, w_si)
+    print(f"[{tag}] rank {rank}/{world}: n_lags={model.n_lags}: basic_abc identical={same} (n_total {sharded['n_total']}, accepted "
+          f"{sharded['n_accepted']}); pmc_abc identical={same_pmc} (eps history {[round(e, 5) for e in r_sh.epsilon_history]}); "
+          f"calc_weights identical={same_w}", flush=True)
+    return same and same_pmc and same_w
+
+
 ok = True
+models = []
 for n_t, n_trials, n_lags in [(5000, 10, None), (3000, 4, 700)]:
     dt = 0.002
     data = oou.generate_ou_process(0.3, 1.0, dt, n_t * dt, n_trials, seed=5, n_t=n_t)
     t = dt * np.arange(1, n_t + 1)
-    model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags)
-    scorer = distributed.gpu_sharded_scorer(model, ctx=ctx, seed=3)
-    props = np.random.default_rng(1).uniform(0.05, 5.0, size=(4001, 1))
-    d_all = model.gpu_model(_tun(ctx)).distances(props, seed=3, generation=2)           # every rank: the whole batch on its own GPU
-    eps = float(np.sort(d_all)[400] * 0.5 + np.sort(d_all)[401] * 0.5)
-    sharded = pkg.basic_abc(model, eps, 4001, 333, scorer=scorer, proposals=props, generation=2)
-    single = pkg.basic_abc(model, eps, 4001, 333, proposals=props, seed=3, generation=2, ctx=ctx)
-    same = (sharded["n_total"] == single["n_total"] and sharded["n_accepted"] == single["n_accepted"]
-            and np.array_equal(sharded["distances"], single["distances"]) and np.array_equal(sharded["theta_accepted"], single["theta_accepted"])
-            and np.array_equal(sharded["distances"], d_all[: sharded["n_total"]]))
-    r_sh = pkg.pmc_abc(model, epsilon_0=1.0, max_iter=3000, min_accepted=100, steps=4, rng=np.random.default_rng(7), scorer=scorer, target_epsilon=1e-9)
-    r_si = pkg.pmc_abc(model, epsilon_0=1.0, max_iter=3000, min_accepted=100, steps=4, rng=np.random.default_rng(7), seed=3, ctx=ctx, target_epsilon=1e-9)
-    same_pmc = np.array_equal(r_sh.final_theta, r_si.final_theta) and r_sh.epsilon_history == r_si.epsilon_history
-    print(f"rank {rank}/{world}: n_t={n_t} n_lags={model.n_lags}: basic_abc identical={same} (n_total {sharded['n_total']}, accepted {sharded['n_accepted']}); "
-          f"pmc_abc identical={same_pmc} (eps history {[round(e, 5) for e in r_sh.epsilon_history]})", flush=True)
-    ok = ok and same and same_pmc
+    model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.05, 5.0)], n_lags=n_lags, ctx=solo)
+    models.append(model)
+    ok = compare(model, ctx, "one process per GPU") and ok
 flag = torch.tensor([0 if ok else 1], device=torch.device("cuda", local))
 dist.all_reduce(flag)
+ctx.close()
+dist.barrier()
+if rank == 0:
+    multi = pkg.Context(devices=list(range(world)))          # one process, all GPUs (ncclCommInitAll)
+    assert multi.world() == (0, world, world)
+    ok1 = all(compare(m, multi, "one process, all GPUs") for m in models)
+    multi.close()
+    flag += 0 if ok1 else 1
+dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
     print("MULTI-GPU CHECK", "PASSED" if flag.item() == 0 else "FAILED")

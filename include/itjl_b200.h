@@ -185,6 +185,14 @@ int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, co
 /* weighted_covar(x, w)  (src/core/abc.jl:582-613): x (n x n_theta) column-major, cov_out (n_theta x n_theta). */
 int itjl_weighted_covar(itjl_ctx* ctx, const double* x, int64_t n, int32_t n_theta, const double* w, double* cov_out);
 
+/* The same on a communicator of single-device contexts (itjl_ctx_attach_comm; COLLECTIVE): theta_dev holds ALL
+ * n_particles on this rank's device, the rank scores its contiguous share, the shares are all-gathered over
+ * NVLink and dist_dev (device, n_particles) receives every distance.  Asynchronous on the context stream.
+ * Without a communicator it is itjl_abc_distances_dev. */
+int itjl_abc_distances_sharded_dev(itjl_model* model, const double* theta_dev, int64_t n_particles,
+                                   int32_t n_theta, uint64_t seed, uint64_t generation,
+                                   int64_t particle_offset, double* dist_dev);
+
 /* Algorithmic work of one itjl_abc_distances call, for roofline accounting:
  * flops_per_sample = 2*n_lags + 8 for the direct lag-sum kernels. */
 int itjl_model_work(const itjl_model* model, double* flops_per_sample, int64_t* samples_per_particle);

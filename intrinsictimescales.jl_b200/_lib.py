@@ -68,6 +68,7 @@ SIGNATURES = {
     "itjl_abc_generation": (ctypes.c_int, [_vp, _vp, _i64, _i32, _u64, _u64, _i64, _f64, _i64, _vp, _vp, _vp, _vp]),
     "itjl_abc_accept": (ctypes.c_int, [_vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     "itjl_abc_distances_dev": (ctypes.c_int, [_vp, _vp, _i64, _i32, _u64, _u64, _i64, _vp]),
+    "itjl_abc_distances_sharded_dev": (ctypes.c_int, [_vp, _vp, _i64, _i32, _u64, _u64, _i64, _vp]),
     "itjl_model_work": (ctypes.c_int, [_vp, _vp, _vp]),
     "itjl_generate_ou": (ctypes.c_int, [_vp, _f64, _f64, _f64, _i64, _i64, _i32, _i32, _u64, _vp, _vp, _vp]),
     "itjl_generate_ou_osc": (ctypes.c_int, [_vp, _f64, _f64, _f64, _f64, _i64, _i64, _f64, _f64, _i32, _u64,

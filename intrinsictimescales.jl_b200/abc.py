@@ -62,8 +62,13 @@ def draw_theta_pmc(model, theta_prev, weights, tau_squared, rng, n=1, jitter=1e-
     p = theta_prev.shape[1]
     cov = np.atleast_2d(np.asarray(tau_squared, dtype=np.float64)) + jitter * np.eye(p)
     chol = np.linalg.cholesky(cov)
-    cdf = np.cumsum(w / w.sum())
-    idx = np.minimum(np.searchsorted(cdf, rng.random(n), side="right"), w.size - 1)
+    if n >= 4096:
+        # large batches (the 10^6-particle sweep): multinomial counts + a random order are the same i.i.d.
+        # resampling as n inverse-cdf look-ups, without n cache-missing binary searches
+        idx = rng.permutation(np.repeat(np.arange(w.size), rng.multinomial(n, w / w.sum())))
+    else:
+        cdf = np.cumsum(w / w.sum())
+        idx = np.minimum(np.searchsorted(cdf, rng.random(n), side="right"), w.size - 1)
     stars = theta_prev[idx]
     out = stars + rng.standard_normal((n, p)) @ chol.T
     bad = np.nonzero(np.any(out < 0, axis=1))[0]
@@ -164,9 +169,9 @@ def select_epsilon(distances, current_epsilon, target_acc_rate=0.01, current_acc
     valid = valid[valid < distance_max]
     if valid.size == 0:
         return current_epsilon
-    q_lower = percentile(valid, quantile_lower)
-    q_init = percentile(valid, quantile_init)
-    q_upper = percentile(valid, quantile_upper)
+    # one selection pass for the three order statistics (StatsBase.percentile = quantile type 7)
+    q_lower, q_init, q_upper = (float(q) for q in np.percentile(valid, [quantile_lower, quantile_init, quantile_upper],
+                                                               method="linear"))
     alpha = compute_adaptive_alpha(iteration, current_acc_rate, target_acc_rate, alpha_max=alpha_max,
                                    alpha_min=alpha_min, total_iterations=total_iterations,
                                    acc_rate_far=acc_rate_far, acc_rate_close=acc_rate_close,

@@ -37,7 +37,7 @@ int upload(itjl_ctx* ctx, DevBuf& buf, const void* host, size_t bytes);
 int launch_distances(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
                      uint64_t seed, uint64_t generation, int64_t particle_offset,
                      const double* u0_dev, const double* noise_dev, const double* phases_dev,
-                     double* dist_dev, double* stats_dev);
+                     double* dist_dev, double* stats_dev, int64_t theta_ld = 0);
 
 // contiguous shard of `rank` when n items are split over `world` ranks (same rule as distributed.py::shard_bounds)
 inline void shard_bounds(int64_t n, int world, int rank, int64_t* lo, int64_t* hi) {

@@ -344,7 +344,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
 int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
                             uint64_t seed, uint64_t generation, int64_t particle_offset,
                             const double* u0_dev, const double* noise_dev, const double* phases_dev,
-                            double* dist_dev, double* stats_dev) {
+                            double* dist_dev, double* stats_dev, int64_t theta_ld) {
     itjl_ctx* ctx = m->ctx;
     const itjl_model_desc& d = m->d;
     const int need_theta = (d.kind == ITJL_KIND_OU_OSC) ? 3 : 1;
@@ -356,7 +356,7 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
     if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
     if (d.summary == ITJL_SUMMARY_PSD) {
         AbcPsdParams P{};
-        P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
+        P.theta = theta_dev; P.n_particles = n_particles; P.theta_ld = theta_ld > 0 ? theta_ld : n_particles; P.n_theta = n_theta;
         P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_stats = (int)d.n_stats;
         P.chunk = m->psd_chunk; P.xs_len = m->psd_xs_len; P.n2 = m->n2; P.log2_n2 = m->log2_n2;
         P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
@@ -382,7 +382,7 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
                 AbcPsdParams Q = P;
                 Q.grid = std::min<int64_t>(sub, n_particles - lo);
                 Q.accb_global = (float*)ctx->scratch.p;
-                Q.theta = theta_dev + lo;                         // column-major: the stride stays n_particles
+                Q.theta = theta_dev + lo;                         // column-major: the leading dimension stays
                 Q.particle_offset = particle_offset + lo;
                 Q.dist_out = dist_dev + lo;
                 Q.stats_out = stats_dev ? stats_dev + lo * d.n_stats : nullptr;
@@ -395,7 +395,7 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
     } else if (m->use_tc) {
         AbcTcParams P{};
         const AbcTcGeometry& t = m->tc;
-        P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
+        P.theta = theta_dev; P.n_particles = n_particles; P.theta_ld = theta_ld > 0 ? theta_ld : n_particles; P.n_theta = n_theta;
         P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_lags = (int)d.n_stats;
         P.dt = d.dt; P.update = d.update; P.kind = d.kind; P.distance = d.distance;
         P.keys = philox_keys(seed);
@@ -454,7 +454,7 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
         }
     } else {
         AbcAcfParams P{};
-        P.theta = theta_dev; P.n_particles = n_particles; P.n_theta = n_theta;
+        P.theta = theta_dev; P.n_particles = n_particles; P.theta_ld = theta_ld > 0 ? theta_ld : n_particles; P.n_theta = n_theta;
         P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_lags = (int)d.n_stats;
         P.chunk = m->geo.chunk; P.xs_stride = m->geo.xs_stride; P.n_bufs = m->geo.n_bufs; P.lt = m->geo.lt;
         P.n_streams = m->geo.n_streams; P.tiles_per_stream = m->geo.tiles_per_stream; P.n_tiles = m->geo.n_tiles;

@@ -238,6 +238,33 @@ int itjl_ctx_create_multi(int n_dev, const int* dev_ids, itjl_ctx** ctx_out) {
     return ITJL_OK;
 }
 
+int itjl_abc_distances_sharded_dev(itjl_model* m, const double* theta_dev, int64_t n_particles, int32_t n_theta,
+                                   uint64_t seed, uint64_t generation, int64_t particle_offset, double* dist_dev) {
+    if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    itjl_ctx* ctx = m->ctx;
+    if (!theta_dev || !dist_dev || n_particles < 1 || n_theta < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances_sharded_dev: invalid argument");
+    if (!ctx->subs.empty()) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances_sharded_dev: device pointers belong to one device; use a single-device context (itjl_ctx_attach_comm)");
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_abc_distances_sharded_dev");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int world = ctx->world;
+    const int64_t width = (n_particles + world - 1) / world;
+    int64_t lo, hi;
+    shard_bounds(n_particles, world, ctx->rank, &lo, &hi);
+    ITJL_CUDA(ctx, ctx->gather.reserve((size_t)world * width * sizeof(double)));
+    if (hi > lo) {
+        const int rc = launch_distances(m, theta_dev + lo, hi - lo, n_theta, seed, generation, particle_offset + lo,
+                                        nullptr, nullptr, nullptr, (double*)ctx->gather.p + (int64_t)ctx->rank * width, nullptr,
+                                        n_particles);
+        if (rc != ITJL_OK) return rc;
+    }
+    double* all = nullptr;
+    const int rc = shard_allgather_compact(ctx, n_particles, &all);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(dist_dev, all, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return ITJL_OK;
+}
+
 int itjl_ctx_world(const itjl_ctx* ctx, int* rank, int* world, int* n_local) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
     if (rank) *rank = ctx->subs.empty() ? ctx->rank : 0;

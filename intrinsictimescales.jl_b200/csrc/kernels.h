@@ -7,8 +7,9 @@ namespace itjl {
 
 // ---- abc_kernels.cu ------------------------------------------------------------------
 struct AbcAcfParams {
-    const double* theta;
+    const double* theta;         // (n_particles x n_theta) column-major, leading dimension theta_ld
     int64_t n_particles;
+    int64_t theta_ld;
     int n_theta;
     int n_t, n_trials, n_lags;
     int chunk, xs_stride, n_bufs;
@@ -41,8 +42,9 @@ cudaError_t abc_accept_launch(const double* dist, int64_t n, double eps, int64_t
 
 // ---- psd_kernels.cu ------------------------------------------------------------------
 struct AbcPsdParams {
-    const double* theta;
+    const double* theta;         // (n_particles x n_theta) column-major, leading dimension theta_ld
     int64_t n_particles;
+    int64_t theta_ld;
     int n_theta;
     int n_t, n_trials, n_stats;
     int chunk, xs_len;          // simulate chunk; floats in the staging buffer
@@ -145,8 +147,9 @@ struct AbcTcGeometry {
     size_t smem_bytes;
 };
 struct AbcTcParams {
-    const double* theta;
+    const double* theta;         // (n_particles x n_theta) column-major, leading dimension theta_ld
     int64_t n_particles;
+    int64_t theta_ld;
     int n_theta;
     int n_t, n_trials, n_lags;
     double dt;

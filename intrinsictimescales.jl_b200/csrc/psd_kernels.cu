@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(kPsdThreads, 1) k_abc_psd(const __grid_constan
     const double tau = P.theta[particle];
     double freq = 0.0, coeff = 1.0;
     if (OSC) {
-        freq = P.theta[particle + P.n_particles];
-        coeff = P.theta[particle + 2 * P.n_particles];
+        freq = P.theta[particle + P.theta_ld];
+        coeff = P.theta[particle + 2 * P.theta_ld];
     }
     const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU,
                                        freq, coeff, P.n_t, true, true);   // |FFT| of the Hamming-windowed trial is reversal invariant

@@ -224,6 +224,15 @@ class GpuModel:
             self._h, ctypes.c_void_p(theta_dev_ptr), int(n_particles), int(n_theta), int(seed),
             int(generation), int(particle_offset), ctypes.c_void_p(dist_dev_ptr)))
 
+    def distances_sharded_dev(self, theta_dev_ptr, n_particles, n_theta, dist_dev_ptr, seed=0, generation=0,
+                              particle_offset=0):
+        """Collective device-pointer variant: this rank scores its share of the n_particles in theta_dev, the
+        library all-gathers, dist_dev receives all of them (itjl_abc_distances_sharded_dev)."""
+        import ctypes
+        self.ctx.check(_lib.lib().itjl_abc_distances_sharded_dev(
+            self._h, ctypes.c_void_p(theta_dev_ptr), int(n_particles), int(n_theta), int(seed),
+            int(generation), int(particle_offset), ctypes.c_void_p(dist_dev_ptr)))
+
     def close(self):
         if self._h:
             _lib.lib().itjl_model_destroy(self._h)

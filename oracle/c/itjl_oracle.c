@@ -5,7 +5,9 @@
  * cpu_baseline / --impl reference legs of bench.py.  Never linked or called by the
  * product library (libitjl_b200.so).
  *
- * It restates, in the reference's own arithmetic order (fp64, FFT-based ACF), the body
+ * It restates, in the reference's own arithmetic (fp64, FFT-based ACF; the FFT itself is a vectorised
+ * radix-2 with two real trials per complex transform, where the reference hands FFTW one complex transform
+ * per real trial - the baseline should not be slower than what it stands for), the body
  * of the serial loop in /root/reference/src/core/abc.jl:174-195:
  *   generate_data_and_reduce          src/core/model.jl:146-151
  *   generate_ou_process(_sciml)       src/utils/ou_process.jl:46-62, 114-148
@@ -51,18 +53,24 @@ static inline uint32_t c3_word(uint32_t stream, uint64_t gen) {
 }
 
 /* --------------------------------------------------------------- FFT ---- */
+/* In-place radix-2 decimation-in-time complex FFT, written so that the CPU baseline is not a straw man:
+ * the twiddles of every stage lie contiguously (tw + half - 1), so the butterfly loop of a stage is
+ * stride-1 in all six arrays and gcc vectorises it (AVX2 / AVX-512 with -march=native); the first two
+ * stages (twiddles 1 and -i) are fused into one multiplication-free radix-4 pass.  Real input is exploited
+ * by the callers: two trials ride in one complex transform (see pair_acf / pair_psd). */
 typedef struct { int n; double* wr; double* wi; int* rev; } fft_plan;
 
 static fft_plan* fft_plan_create(int n) {
     fft_plan* p = (fft_plan*)malloc(sizeof(fft_plan));
     p->n = n;
-    p->wr = (double*)malloc(sizeof(double) * (n / 2));
-    p->wi = (double*)malloc(sizeof(double) * (n / 2));
-    p->rev = (int*)malloc(sizeof(int) * n);
-    for (int i = 0; i < n / 2; ++i) {
-        p->wr[i] = cos(-2.0 * PI * i / n);
-        p->wi[i] = sin(-2.0 * PI * i / n);
-    }
+    p->wr = (double*)malloc(sizeof(double) * (size_t)(n > 1 ? n : 2));
+    p->wi = (double*)malloc(sizeof(double) * (size_t)(n > 1 ? n : 2));
+    p->rev = (int*)malloc(sizeof(int) * (size_t)n);
+    for (int half = 1; half < n; half <<= 1)              /* stage with butterflies of span `half` */
+        for (int j = 0; j < half; ++j) {
+            p->wr[half - 1 + j] = cos(-PI * (double)j / (double)half);
+            p->wi[half - 1 + j] = sin(-PI * (double)j / (double)half);
+        }
     int bits = 0; while ((1 << bits) < n) ++bits;
     for (int i = 0; i < n; ++i) {
         int r = 0;
@@ -74,21 +82,38 @@ static fft_plan* fft_plan_create(int n) {
 static void fft_plan_destroy(fft_plan* p) { free(p->wr); free(p->wi); free(p->rev); free(p); }
 
 /* in-place forward complex FFT (inverse = conj trick by caller) */
-static void fft_exec(const fft_plan* p, double* re, double* im) {
-    int n = p->n;
+static void fft_exec(const fft_plan* p, double* restrict re, double* restrict im) {
+    const int n = p->n;
     for (int i = 0; i < n; ++i) {
         int r = p->rev[i];
         if (r > i) { double t = re[i]; re[i] = re[r]; re[r] = t; t = im[i]; im[i] = im[r]; im[r] = t; }
     }
-    for (int len = 2; len <= n; len <<= 1) {
-        int half = len >> 1, step = n / len;
+    int len = 2;
+    if (n >= 4) {
+        /* stages len = 2 and len = 4 in one pass: twiddles 1, 1, 1, -i */
+        for (int s = 0; s < n; s += 4) {
+            double ar = re[s] + re[s + 1], ai = im[s] + im[s + 1];
+            double br = re[s] - re[s + 1], bi = im[s] - im[s + 1];
+            double cr = re[s + 2] + re[s + 3], ci = im[s + 2] + im[s + 3];
+            double dr = re[s + 2] - re[s + 3], di = im[s + 2] - im[s + 3];
+            re[s] = ar + cr; im[s] = ai + ci;
+            re[s + 2] = ar - cr; im[s + 2] = ai - ci;
+            re[s + 1] = br + di; im[s + 1] = bi - dr;       /* (dr + i di) * (-i) = di - i dr */
+            re[s + 3] = br - di; im[s + 3] = bi + dr;
+        }
+        len = 8;
+    }
+    for (; len <= n; len <<= 1) {
+        const int half = len >> 1;
+        const double* restrict wr = p->wr + (half - 1);
+        const double* restrict wi = p->wi + (half - 1);
         for (int s = 0; s < n; s += len) {
+            double* restrict ra = re + s; double* restrict ia = im + s;
+            double* restrict rb = re + s + half; double* restrict ib = im + s + half;
             for (int j = 0; j < half; ++j) {
-                double wr = p->wr[j * step], wi = p->wi[j * step];
-                int a = s + j, b = a + half;
-                double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
-                re[b] = re[a] - xr; im[b] = im[a] - xi;
-                re[a] += xr; im[a] += xi;
+                double xr = rb[j] * wr[j] - ib[j] * wi[j], xi = rb[j] * wi[j] + ib[j] * wr[j];
+                rb[j] = ra[j] - xr; ib[j] = ia[j] - xi;
+                ra[j] += xr; ia[j] += xi;
             }
         }
     }
@@ -115,6 +140,7 @@ typedef struct {
     fft_plan* plan;
     int n_fft;
     double win_ss;
+    int pending;          /* 1: the real part of (re, im) holds a trial waiting for its partner */
 } workspace;
 
 static workspace* ws_create(const oracle_model_desc* m) {
@@ -137,6 +163,44 @@ static workspace* ws_create(const oracle_model_desc* m) {
 }
 static void ws_destroy(workspace* w) {
     fft_plan_destroy(w->plan); free(w->x); free(w->re); free(w->im); free(w->acc); free(w->win); free(w);
+}
+
+/* Two real sequences x1 (in re) and x2 (in im), zero padded to n_fft, transformed at once:
+ *   Z = FFT(x1 + i x2),  X1[k] = (Z[k] + conj Z[N-k]) / 2,  X2[k] = (Z[k] - conj Z[N-k]) / (2 i).
+ * `count` = 1 when im is all zero (a last unpaired trial). */
+static void pair_acf(workspace* w, int n_stats, int count) {
+    const int N = w->n_fft;
+    double* restrict re = w->re; double* restrict im = w->im;
+    fft_exec(w->plan, re, im);
+    /* power spectra P1, P2 (real, even in k) packed as W = P1 + i P2; FFT(W) = N (acov1 + i acov2): the
+       forward transform of a real even sequence equals N times its inverse (summary.jl:56-58) */
+    for (int k = 0; k <= N / 2; ++k) {
+        const int nk = (N - k) & (N - 1);
+        const double zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+        const double p1 = 0.25 * ((zr + yr) * (zr + yr) + (zi - yi) * (zi - yi));
+        const double p2 = 0.25 * ((zi + yi) * (zi + yi) + (yr - zr) * (yr - zr));
+        re[k] = p1; im[k] = p2; re[nk] = p1; im[nk] = p2;
+    }
+    fft_exec(w->plan, re, im);
+    const double inv1 = 1.0 / re[0];
+    for (int k = 0; k < n_stats; ++k) w->acc[k] += re[k] * inv1;
+    if (count == 2) {
+        const double inv2 = 1.0 / im[0];
+        for (int k = 0; k < n_stats; ++k) w->acc[k] += im[k] * inv2;
+    }
+}
+
+static void pair_psd(workspace* w, double scl, int count) {
+    const int N = w->n_fft;
+    double* restrict re = w->re; double* restrict im = w->im;
+    fft_exec(w->plan, re, im);
+    for (int k = 0; k < N / 2; ++k) {
+        const int nk = (N - k) & (N - 1);
+        const double zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+        const double p1 = 0.25 * ((zr + yr) * (zr + yr) + (zi - yi) * (zi - yi));
+        const double p2 = 0.25 * ((zi + yi) * (zi + yi) + (yr - zr) * (yr - zr));
+        w->acc[k] += (count == 2 ? p1 + p2 : p1) * scl;
+    }
 }
 
 /* one particle: returns the distance; stats_out (optional, n_stats) receives the trial-mean
@@ -205,19 +269,16 @@ static double particle_distance(const oracle_model_desc* m, workspace* w, const 
         if (bad) break;
 
         if (m->summary == 0) {
-            /* comp_ac_fft */
+            /* comp_ac_fft, two trials per complex transform: trial `pending` rides in the real part, this
+               one in the imaginary part; a last unpaired trial is flushed after the loop */
             double m2 = 0.0;
             for (int j = 0; j < n; ++j) m2 += w->x[j];
             m2 /= n;
-            for (int j = 0; j < n; ++j) { w->re[j] = w->x[j] - m2; w->im[j] = 0.0; }
-            for (int j = n; j < w->n_fft; ++j) { w->re[j] = 0.0; w->im[j] = 0.0; }
-            fft_exec(w->plan, w->re, w->im);
-            for (int j = 0; j < w->n_fft; ++j) {
-                w->re[j] = w->re[j] * w->re[j] + w->im[j] * w->im[j]; w->im[j] = 0.0;
-            }
-            fft_exec(w->plan, w->re, w->im);     /* real even input: forward == inverse * n */
-            double inv0 = 1.0 / w->re[0];
-            for (int k = 0; k < (int)m->n_stats; ++k) w->acc[k] += w->re[k] * inv0;
+            double* dst = w->pending ? w->im : w->re;
+            for (int j = 0; j < n; ++j) dst[j] = w->x[j] - m2;
+            for (int j = n; j < w->n_fft; ++j) dst[j] = 0.0;
+            if (w->pending) { pair_acf(w, (int)m->n_stats, 2); w->pending = 0; }
+            else w->pending = 1;
         } else if (m->summary == 1) {
             /* comp_ac_time_missing with the model's mask applied (NaN -> 0, then
                subtract the valid-sample mean from every entry) */
@@ -235,18 +296,24 @@ static double particle_distance(const oracle_model_desc* m, workspace* w, const 
                 w->acc[k] += acc / ssq;
             }
         } else {
-            /* comp_psd_adfriendly */
+            /* comp_psd_adfriendly, two trials per complex transform */
             double m2 = 0.0;
             for (int j = 0; j < n; ++j) m2 += w->x[j];
             m2 /= n;
-            for (int j = 0; j < n; ++j) { w->re[j] = (w->x[j] - m2) * w->win[j]; w->im[j] = 0.0; }
-            for (int j = n; j < w->n_fft; ++j) { w->re[j] = 0.0; w->im[j] = 0.0; }
-            fft_exec(w->plan, w->re, w->im);
-            double scl = 1.0 / ((1.0 / m->dt) * w->win_ss);
-            for (int j = 0; j < w->n_fft / 2; ++j)
-                w->acc[j] += (w->re[j] * w->re[j] + w->im[j] * w->im[j]) * scl;
+            double* dst = w->pending ? w->im : w->re;
+            for (int j = 0; j < n; ++j) dst[j] = (w->x[j] - m2) * w->win[j];
+            for (int j = n; j < w->n_fft; ++j) dst[j] = 0.0;
+            const double scl = 1.0 / ((1.0 / m->dt) * w->win_ss);
+            if (w->pending) { pair_psd(w, scl, 2); w->pending = 0; }
+            else w->pending = 1;
         }
     }
+    if (!bad && w->pending) {                  /* odd number of trials: the last one alone (imaginary part zero) */
+        for (int j = 0; j < w->n_fft; ++j) w->im[j] = 0.0;
+        if (m->summary == 0) pair_acf(w, (int)m->n_stats, 1);
+        else pair_psd(w, 1.0 / ((1.0 / m->dt) * w->win_ss), 1);
+    }
+    w->pending = 0;
     if (bad) {
         if (stats_out) for (int k = 0; k < (int)m->n_stats; ++k) stats_out[k] = NAN;
         return NAN;
