@@ -469,122 +469,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 4) k_acw_stream(const AcwStrea
     out[(size_t)SK * ld] = (float)(acc64[SK][threadIdx.x] + (double)S);
 }
 
-// ---- the same pass with the loads taken off the threads: bulk asynchronous copies (TMA, 1-D) ------------
-// CTA = 128 adjacent slices x one time segment.  One thread streams tiles of 8 time steps (8 rows of
-// 128 x 8 B = 1 KB, contiguous in the column-major input) into a 4-stage shared-memory ring with
-// cp.async.bulk + mbarrier complete_tx; the 128 threads consume them (thread = slice, conflict-free
-// LDS.64) with the register window / accumulators of k_acw_stream.  No load or address arithmetic in
-// the math loop, and the copies run 3 tiles ahead whatever the warps are doing.  Needs an even number of
-// slices (16-byte alignment of every row start).  Measured on the B200 (C2): 182 us for the pass against
-// ~150 us with k_acw_stream (140 registers, 12 warps / SM, a barrier round trip per 8 samples), so it is
-// opt-in only (ITJL_ACW_BULK=1) - kept as the starting point for a tensor-core version of the pass.
-constexpr int BT = 8;                  // time steps per tile (4 stages x 8 KB + 33 KB of fp64 sums: 3 CTAs / SM)
-constexpr int BSTAGES = 4;
-constexpr int BS = STREAM_THREADS;     // slices per CTA
-
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(STREAM_THREADS, 3) k_acw_stream_bulk(const AcwStreamParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*ring)[BT][BS] = reinterpret_cast<double (*)[BT][BS]>(smem_raw);           // [BSTAGES][BT][BS]
-    double (*acc64)[STREAM_THREADS] = reinterpret_cast<double (*)[STREAM_THREADS]>(smem_raw + sizeof(double) * BSTAGES * BT * BS);
-    __shared__ __align__(8) unsigned long long bar_full[BSTAGES], bar_empty[BSTAGES];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t s0 = (int64_t)blockIdx.x * BS;
-    const int valid = (int)min((int64_t)BS, P.n_slices - s0);
-    const int64_t s = s0 + tid;
-    const int seg = blockIdx.y;
-    const int tb = seg * P.seg_len;
-    const int te = min(tb + P.seg_len, P.n_t & ~(SK - 1));
-    const size_t ld = (size_t)P.n_slices;
-    constexpr int TPW = SK / BT;                                 // tiles per 32-sample window period
-    const int n_tiles = te > tb ? TPW + (te - tb) / BT : 0;     // the first TPW tiles = the 32-sample halo before tb
-
-    if (tid == 0) {
-        for (int i = 0; i < BSTAGES; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar_full[i])), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar_empty[i])), "r"(STREAM_THREADS / 32));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // producer (thread 0): tile q -> stage q % BSTAGES; rows before the series starts are not copied
-    auto issue_tile = [&](int q) {
-        const int st = q % BSTAGES;
-        if (q >= BSTAGES) {
-            const unsigned parity = (unsigned)((q / BSTAGES - 1) & 1);
-            unsigned ok = 0;
-            while (!ok)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(ok) : "r"(smem_addr(&bar_empty[st])), "r"(parity) : "memory");
-        }
-        const int t0 = tb - SK + q * BT;
-        const unsigned bytes = (t0 >= 0) ? (unsigned)(BT * valid * 8) : 0u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar_full[st])), "r"(bytes) : "memory");
-        if (t0 >= 0) {
-            for (int r = 0; r < BT; ++r)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_addr(&ring[st][r][0])), "l"(P.data + (size_t)(t0 + r) * ld + s0), "r"((unsigned)(valid * 8)),
-                               "r"(smem_addr(&bar_full[st])) : "memory");
-        }
-    };
-    if (tid == 0)
-        for (int q = 0; q < BSTAGES - 1 && q < n_tiles; ++q) issue_tile(q);
-
-    const bool active = tid < valid;
-    const double ref = active ? slice_ref(P.data, s, P.n_slices, P.n_t) : 0.0;
-    float acc[SK], C[SK];
-#pragma unroll
-    for (int j = 0; j < SK; ++j) { acc[j] = 0.f; acc64[j][tid] = 0.0; C[j] = 0.f; }
-    acc64[SK][tid] = 0.0;
-    float S = 0.f;
-    int since_flush = 0;
-
-    for (int q0 = 0; q0 < n_tiles; q0 += TPW) {                 // TPW tiles = one 32-sample window period
-#pragma unroll
-        for (int half = 0; half < TPW; ++half) {
-            const int q = q0 + half;
-            const int st = q % BSTAGES;
-            if (tid == 0 && q + BSTAGES - 1 < n_tiles) issue_tile(q + BSTAGES - 1);
-            {
-                const unsigned parity = (unsigned)((q / BSTAGES) & 1);
-                unsigned ok = 0;
-                while (!ok)
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                                 : "=r"(ok) : "r"(smem_addr(&bar_full[st])), "r"(parity) : "memory");
-            }
-            const bool before_start = tb - SK + q * BT < 0;     // segment 0: the halo is zeros
-            const bool halo = q < TPW;
-#pragma unroll
-            for (int i = 0; i < BT; ++i) {
-                const float z = before_start ? 0.f : (float)(ring[st][i][tid] - ref);
-                C[half * BT + i] = z;                              // (t - tb) & 31 == 16 half + i
-                if (!halo) {
-                    S += z;
-#pragma unroll
-                    for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(half * BT + i - j) & (SK - 1)], acc[j]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_empty[st])) : "memory");
-        }
-        if (q0 >= TPW) since_flush += SK;
-        if (since_flush >= SFLUSH) {
-#pragma unroll
-            for (int j = 0; j < SK; ++j) { acc64[j][tid] += (double)acc[j]; acc[j] = 0.f; }
-            acc64[SK][tid] += (double)S; S = 0.f;
-            since_flush = 0;
-        }
-    }
-    if (active) {
-        float* out = P.part + (size_t)seg * SPART * ld + s;
-#pragma unroll
-        for (int j = 0; j < SK; ++j) out[(size_t)j * ld] = (float)(acc64[j][tid] + (double)acc[j]);
-        out[(size_t)SK * ld] = (float)(acc64[SK][tid] + (double)S);
-    }
-}
+// Measured and not kept (B200, C2 = randn 10000 x 5000; this kernel: 102 us, 55 % of the measured HBM rate):
+//  - packed fp32 pairs (FFMA2, `__ffma2_rn`): the FMA pipe rate is the same (74 TFLOP/s either way,
+//    benchmarks/micro/ffma2_rate.cu), only issue slots are saved; the time-pair formulation needs 64 accumulator +
+//    32 window registers (142-168 per thread, 8-12 warps per SM): 125-170 us;
+//  - a TMA ring (producer warp, cp.async.bulk rows of 1 KB into 3-4 stages of 16 time steps, consumers pull a tile
+//    into registers and hand the stage back): 125 us with FFMA, 125-132 us with FFMA2 - and 90 us with the lag
+//    products compiled out altogether, i.e. the ring of 1 KB rows itself tops out at 4.4 TB/s, no better than what
+//    plain coalesced LDG.64 already delivers here;
+//  - round 1's variants (deeper LDG pipelining, L2 prefetch, in-line cp.async.bulk producer): 116-182 us.
+// The pass is bounded by how the (slice-fastest, 80 KB per time step) layout can be streamed per slice block, not
+// by the FMA pipe (44 us of work) nor by raw HBM bandwidth (62 us).
 
 struct AcwFinishParams {
     const double* data;
@@ -715,21 +610,13 @@ static cudaError_t launch_slices(AcfSliceParams& P, int reach, int max_smem, int
 
 cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                              int32_t* ke, int32_t* redo, cudaStream_t st, bool bulk_variant) {
+                              int32_t* ke, int32_t* redo, cudaStream_t st) {
     AcwStreamParams S{};
     S.data = data; S.n_slices = n_slices; S.n_t = n_t; S.n_seg = n_seg; S.seg_len = seg_len;
     S.part = reinterpret_cast<float*>(part);
     dim3 grid((unsigned)((n_slices + STREAM_THREADS - 1) / STREAM_THREADS), (unsigned)n_seg);
-    const bool bulk = (n_slices % 2 == 0) && bulk_variant;     // opt-in: measured slower (182 vs 150 us at C2)
     cudaError_t e;
-    if (bulk) {
-        const size_t smem = sizeof(double) * ((size_t)BSTAGES * BT * BS + (size_t)SPART * STREAM_THREADS);
-        e = cudaFuncSetAttribute(k_acw_stream_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_acw_stream_bulk<<<grid, STREAM_THREADS, smem, st>>>(S);
-    } else {
-        k_acw_stream<<<grid, STREAM_THREADS, 0, st>>>(S);
-    }
+    k_acw_stream<<<grid, STREAM_THREADS, 0, st>>>(S);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AcwFinishParams F{};

@@ -103,7 +103,7 @@ cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int m
 // streaming first pass (raw lagged products of the first acw_stream_lags() lags, one read of the data)
 cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                              int32_t* ke, int32_t* redo, cudaStream_t st, bool bulk_variant = false);
+                              int32_t* ke, int32_t* redo, cudaStream_t st);
 int acw_stream_lags();
 size_t acw_stream_part_doubles(int64_t n_slices, int n_seg);
 void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves = 0);
