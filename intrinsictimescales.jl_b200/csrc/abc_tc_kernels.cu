@@ -443,8 +443,8 @@ static int tc_store_conflicts(int sbo_bytes, int chunk) {
 // ---- error model of the tensor-core lag sums -----------------------------------------------------------------
 // Bound on what the tensor-core lag sums ADD to the error of one trial-mean ACF value (values in [-1, 1]) over
 // the fp32 FFMA sums of the same simulated series, for a particle of N = n_trials * n_t samples.  (Both fused
-// kernels share the fp32 simulation, centring and conversion: up to ~5e-6 against the fp64 reference for
-// near-unit-root trials, tau >= T, ~1e-6 otherwise - measured, tests/test_gpu_tc.py; the total stays within the
+// kernels share the fp32 simulation, centring and conversion: <= 1.3e-6 against the fp64 reference from
+// tau = T / 100 to tau = 50 T, 1 to 200 trials - measured, tests/test_gpu_tc.py; the total stays well within the
 // 1e-5 of the contract when this bound is within the default 5e-6.)
 //   E_a  dropped cross terms of the fp16 hi/lo split.  x' = hi + lo with |lo| <= 2^-12 |x'|; a dropped term
 //        sum lo_t x'_{t+l} is a sum of N independent zero-mean residuals, in units of sum x'^2 = 1 per trial:

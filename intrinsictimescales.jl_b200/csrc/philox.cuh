@@ -1,4 +1,5 @@
-// Philox4x32-10 counter-based RNG + normal transform, device side.
+// Philox4x32-7 counter-based RNG + normal transform, device side (7 rounds: the Crush-resistant minimum of
+// Salmon et al., SC'11 - three rounds fewer than Random123's default is 3 of ~30 instructions per OU sample).
 // Bit-for-bit the stream specified in oracle/philox.py (counter layout, 23-bit uniforms,
 // Box-Muller with cos/sin ordering).  One Philox block feeds four consecutive samples.
 #pragma once
@@ -11,6 +12,8 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
+constexpr int kPhiloxRounds = 7;
+
 constexpr uint32_t kStreamNoise = 0u;
 constexpr uint32_t kStreamInit = 1u;
 
@@ -18,27 +21,27 @@ __host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t stream, uint64_t
     return ((stream & 0xFu) << 28) | (uint32_t)(generation & 0x0FFFFFFFull);
 }
 
-// The ten round keys (k0 + r W0, k1 + r W1) depend on the seed only: the host expands them once per
+// The round keys (k0 + r W0, k1 + r W1) depend on the seed only: the host expands them once per
 // launch into the kernel parameters, so the rounds read them as constant-bank operands instead of
 // holding twenty registers (or re-adding the Weyl constants) in every thread.
 struct PhiloxKeys {
-    uint32_t k[20];
+    uint32_t k[2 * kPhiloxRounds];
 };
 
 __host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
     PhiloxKeys K;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         K.k[2 * r] = k0; K.k[2 * r + 1] = k1;
         k0 += kPhiloxW0; k1 += kPhiloxW1;
     }
     return K;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKeys& K, uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r];

@@ -105,6 +105,7 @@ struct SimShared {
     float scanB[NT / 32 < 32 ? 32 : NT / 32];
     double sums[NT / 32][4];
     __align__(16) float qtab[kQtab];               // q_j = 1 - a^(j+1), j < chunk <= kQtab, of the current particle
+    double sp_full, spp_full;                      // sum_j (1 - q_j), sum_j (1 - q_j)^2 over a whole chunk, in fp64
     float x0;                                      // the trial's initial state, drawn by warp 0 (plain OU model)
 };
 
@@ -130,7 +131,7 @@ struct SimArgs {
 
 // Per-thread values that do not change from trial to trial (filled during the first trial).
 struct SimCache {
-    float Sp = 0.f, Spp = 0.f;     // sum p_j, sum p_j^2 over this thread's valid samples
+    double Sp = 0.0, Spp = 0.0;    // sum p_j, sum p_j^2 over this thread's samples (fp64: see simulate_trial)
     bool valid = false;
 };
 
@@ -190,7 +191,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     double phase_turns = 0.0;
     if (OSC || warp == 0) {
         uint32_t r[4];
-        philox4x32_10(0u, (uint32_t)trial, g.particle, g.c3_init, *g.keys, r);
+        philox4x32(0u, (uint32_t)trial, g.particle, g.c3_init, *g.keys, r);
         float z1;
         box_muller(r[0], r[1], x0, z1);
         phase_turns = (double)u01(r[2]);
@@ -201,21 +202,40 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     }
 
     // ---- table of q_j = 1 - a^(j+1) (first trial of the particle in this group) -------
+    // Their sums over a chunk, sum p_j and sum p_j^2 (p = 1 - q), enter every thread's share of the trial's sum of
+    // squares multiplied by carry^2.  Summed per thread in fp32 they come out with the SAME rounding error in every
+    // thread (same table, same order): a systematic relative error of ~2e-7 on the dominant term when the trial's
+    // mean is large against its spread - a near-unit-root trial, tau >= T - which the subtraction of n mean^2 amplifies
+    // into 2e-6 .. 1e-5 on the normalisation, i.e. on every ACF value of a single-trial particle.  They are
+    // therefore summed once per particle in fp64 (warp 0) and combined with the carry in fp64.
     if (!cache.valid) {
         sim_sync(bar_id, NT);                            // nobody still reads the previous particle's table
         for (int j = tid; j < g.chunk; j += NT) sh->qtab[j] = ou_q(oc, j);
         sim_sync(bar_id, NT);
+        if (warp == 0) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int j = lane; j < g.chunk; j += 32) { const double pe = 1.0 - (double)sh->qtab[j]; a1 += pe; a2 += pe * pe; }
+            a1 = warp_sum(a1); a2 = warp_sum(a2);
+            if (lane == 0) { sh->sp_full = a1; sh->spp_full = a2; }
+        }
+        sim_sync(bar_id, NT);
+        const int n_th = min(max(g.n_t - j0, 0), g.chunk);               // samples this thread owns
+        if (n_th == g.chunk) { cache.Sp = sh->sp_full; cache.Spp = sh->spp_full; }
+        else {
+            double a1 = 0.0, a2 = 0.0;
+            for (int j = 0; j < n_th; ++j) { const double pe = 1.0 - (double)sh->qtab[j]; a1 += pe; a2 += pe * pe; }
+            cache.Sp = a1; cache.Spp = a2;
+        }
     }
 
     // ---- pass A: local recurrence from a zero state + partial sums -----------------
     // x_j = v_j + cs p_j, p_j = 1 - q_j, cs = (sqrt(coeff) x) carry: v is everything that does not depend on
     // the carry (the local recurrence, plus the oscillation term)
     float y = 0.f;
-    float Sy = 0.f, Syy = 0.f, Syu = 0.f, Sp = 0.f, Spp = 0.f;
-    float Vy = 0.f, Vyy = 0.f, Vyu = 0.f, Vp = 0.f, Vpp = 0.f;   // valid-only sums (MISSING)
+    float Sy = 0.f, Syy = 0.f, Syu = 0.f;
+    float Vy = 0.f, Vyy = 0.f, Vyu = 0.f, Mp = 0.f, Mpp = 0.f;   // valid-only sums; sums of p, p^2 over the MASKED samples (MISSING)
     const double* nz = g.noise ? g.noise + (size_t)trial * g.n_t : nullptr;
     const uint32_t* mrow = MISSING ? g.mask_bits + (size_t)trial * g.mask_words : nullptr;
-    const bool need_p_sums = !cache.valid;
     const float* qt = sh->qtab;
     if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
     if (j0 < g.n_t) {
@@ -239,20 +259,14 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 for (int i = 0; i < 4; ++i) {
                     Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syu = fmaf(v[i], u[i], Syu);
                 }
-                if (need_p_sums) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float pe = 1.0f - u[i]; Sp += pe; Spp = fmaf(pe, pe, Spp); }
-                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (j + i < g.n_t) {
-                        const float pe = 1.0f - u[i];
                         Sy += v[i]; Syy = fmaf(v[i], v[i], Syy); Syu = fmaf(v[i], u[i], Syu);
-                        if (need_p_sums) { Sp += pe; Spp = fmaf(pe, pe, Spp); }
-                        if (MISSING && !((mbits >> i) & 1u)) {
-                            Vy += v[i]; Vyy = fmaf(v[i], v[i], Vyy); Vyu = fmaf(v[i], u[i], Vyu);
-                            Vp += pe; Vpp = fmaf(pe, pe, Vpp);
+                        if (MISSING) {
+                            if ((mbits >> i) & 1u) { const float pe = 1.0f - u[i]; Mp += pe; Mpp = fmaf(pe, pe, Mpp); }
+                            else { Vy += v[i]; Vyy = fmaf(v[i], v[i], Vyy); Vyu = fmaf(v[i], u[i], Vyu); }
                         }
                     }
                 }
@@ -268,13 +282,13 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         int q = 0;
         if (!MISSING && !nz) {
             // interior of the trial, Philox noise: two counter blocks (eight samples) per iteration in one
-            // basic block, so the two ten-round chains and their Box-Muller transforms interleave (four
+            // basic block, so the two seven-round chains and their Box-Muller transforms interleave (four
             // blocks per iteration measured no faster)
             for (; q + 8 <= g.chunk && j0 + q + 7 < g.n_t; q += 8) {
                 const int j = j0 + q;
                 uint32_t ra[4], rb[4];
-                philox4x32_10((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise, *g.keys, ra);
-                philox4x32_10((uint32_t)(j >> 2) + 1u, (uint32_t)trial, g.particle, g.c3_noise, *g.keys, rb);
+                philox4x32((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise, *g.keys, ra);
+                philox4x32((uint32_t)(j >> 2) + 1u, (uint32_t)trial, g.particle, g.c3_noise, *g.keys, rb);
                 float za[4], zb[4];
                 box_muller(ra[0], ra[1], za[0], za[1]);
                 box_muller(ra[2], ra[3], za[2], za[3]);
@@ -296,7 +310,7 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                         if (j + i < g.n_t) z[i] = (float)nz[j + i];
                 } else {
                     uint32_t r[4];
-                    philox4x32_10((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise, *g.keys, r);
+                    philox4x32((uint32_t)(j >> 2), (uint32_t)trial, g.particle, g.c3_noise, *g.keys, r);
                     box_muller(r[0], r[1], z[0], z[1]);
                     box_muller(r[2], r[3], z[2], z[3]);
                 }
@@ -305,8 +319,8 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
             advance4(j, z, *reinterpret_cast<const float4*>(qt + q), full, mbits);
         }
     }
-    if (need_p_sums) { cache.Sp = Sp; cache.Spp = Spp; cache.valid = true; }
-    else { Sp = cache.Sp; Spp = cache.Spp; }
+    cache.valid = true;
+    const double Sp = cache.Sp, Spp = cache.Spp;
 
     // ---- scan of the chunk-end affine maps x -> (1 - Q) x + B ------------------------
     // composition "earlier (Qp, Bp), then (Q, B)":  B <- Bp - Q Bp + B,  Q <- Q + Qp - Q Qp
@@ -357,12 +371,13 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     const float cs = OSC ? oc.sc * c : c;            // the oscillation model mixes sqrt(coeff) x OU
 
     // ---- mean / sum of squares from the partial sums --------------------------------
-    double r0 = (double)fmaf(cs, Sp, Sy);
-    double r1 = (double)fmaf(cs * cs, Spp, fmaf(2.0f * cs, Sy - Syu, Syy));
+    const double csd = (double)cs;
+    double r0 = fma(csd, Sp, (double)Sy);
+    double r1 = fma(csd * csd, Spp, (double)fmaf(2.0f * cs, Sy - Syu, Syy));
     double r2 = 0.0, r3 = 0.0;
     if (MISSING) {
-        r2 = (double)fmaf(cs, Vp, Vy);
-        r3 = (double)fmaf(cs * cs, Vpp, fmaf(2.0f * cs, Vy - Vyu, Vyy));
+        r2 = fma(csd, Sp - (double)Mp, (double)Vy);
+        r3 = fma(csd * csd, Spp - (double)Mpp, (double)fmaf(2.0f * cs, Vy - Vyu, Vyy));
     }
     r0 = warp_sum(r0); r1 = warp_sum(r1);
     if (MISSING) { r2 = warp_sum(r2); r3 = warp_sum(r3); }

@@ -4,7 +4,7 @@ Mirrors src/utils/ou_process.jl: generate_ou_process (:46-62), generate_ou_with_
 (:176-218).  The reference solves the SDE with the adaptive SOSRA scheme and samples it
 every dt; the kernels use the exact OU transition that solve converges to
 (`update="exact"`, default) or Euler-Maruyama (`update="em"`).  Randomness comes from a
-Philox4x32-10 stream keyed by `seed` (the reference's `rng` / `deq_seed` pair); `u0`,
+Philox4x32-7 stream keyed by `seed` (the reference's `rng` / `deq_seed` pair); `u0`,
 `noise` and `phases` can be injected for parity tests.
 """
 import math

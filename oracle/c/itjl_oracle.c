@@ -17,7 +17,7 @@
  *   comp_psd_adfriendly               src/stats/summary.jl:204-235
  *   linear_/logarithmic_distance      src/stats/distances.jl:29-31, 51-53
  * The SDE solve is restated as the exact OU transition (see oracle/ou.py header);
- * the noise stream is the Philox4x32-10 stream specified in oracle/philox.py.
+ * the noise stream is the Philox4x32-7 stream specified in oracle/philox.py.
  * PARITY: unpinned against Julia itself (not installable here); pinned against the
  * NumPy oracle, which is pinned against the reference's KATs (tests/).
  */
@@ -32,8 +32,9 @@
 #define PI 3.14159265358979323846
 
 /* ------------------------------------------------------------ Philox ---- */
-static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-    for (int r = 0; r < 10; ++r) {
+#define PHILOX_ROUNDS 7     /* oracle/philox.py: ROUNDS */
+static void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
@@ -228,7 +229,7 @@ static double particle_distance(const oracle_model_desc* m, workspace* w, const 
         double u0, phase;
         {
             uint32_t c[4] = {0u, (uint32_t)tr, (uint32_t)particle, c3_word(1, gen)};
-            philox4x32_10(c, k0, k1);
+            philox4x32(c, k0, k1);
             double z1;
             box_muller(c[0], c[1], &u0, &z1);
             phase = 2.0 * PI * u01(c[2]);
@@ -242,7 +243,7 @@ static double particle_distance(const oracle_model_desc* m, workspace* w, const 
                 for (int q = 0; q < 4 && j + q < n; ++q) z[q] = noise_in[(size_t)tr * n + j + q];
             } else {
                 uint32_t c[4] = {(uint32_t)(j >> 2), (uint32_t)tr, (uint32_t)particle, c3_word(0, gen)};
-                philox4x32_10(c, k0, k1);
+                philox4x32(c, k0, k1);
                 box_muller(c[0], c[1], &z[0], &z[1]);
                 box_muller(c[2], c[3], &z[2], &z[3]);
             }

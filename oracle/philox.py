@@ -1,5 +1,7 @@
-"""Philox4x32-10 counter-based RNG (Salmon et al., SC'11; Random123) and the
-normal / uniform transforms shared by the oracle and the CUDA kernels.
+"""Philox4x32 counter-based RNG (Salmon et al., SC'11; Random123) with ROUNDS = 7 rounds - the
+Crush-resistant minimum of the paper (its table 2; Philox4x32-7 passes BigCrush, 10 rounds is the
+conservative default) - and the normal / uniform transforms shared by the oracle and the CUDA kernels.
+Round 1 of this project used 10 rounds; the stream is a specification of this project, not of the reference.
 
 The reference draws its noise inside StochasticDiffEq's SOSRA solver
 (/root/reference/src/utils/ou_process.jl:136-138), whose stream cannot be
@@ -29,15 +31,18 @@ STREAM_NOISE = 0
 STREAM_INIT = 1
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10.  All inputs broadcastable integer arrays; returns
+ROUNDS = 7
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=ROUNDS):
+    """Vectorised Philox4x32-`rounds`.  All inputs broadcastable integer arrays; returns
     four uint32 arrays."""
     c0, c1, c2, c3 = np.broadcast_arrays(*[np.asarray(c, dtype=np.uint64) & MASK32
                                            for c in (c0, c1, c2, c3)])
     c0 = c0.copy(); c1 = c1.copy(); c2 = c2.copy(); c3 = c3.copy()
     k0 = int(k0) & 0xFFFFFFFF
     k1 = int(k1) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0 = p0 >> np.uint64(32)
@@ -51,6 +56,11 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
         k1 = (k1 + W1) & 0xFFFFFFFF
     return (c0.astype(np.uint32), c1.astype(np.uint32),
             c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """The 10-round variant (Random123's default; only the known-answer tests use it)."""
+    return philox4x32(c0, c1, c2, c3, k0, k1, rounds=10)
 
 
 def u01(r):
@@ -77,7 +87,7 @@ def noise_normals(seed, generation, particle, trial, n):
     """xi_0 .. xi_{n-1} for one (particle, trial): block b -> xi_{4b..4b+3}."""
     nb = (n + 3) // 4
     b = np.arange(nb, dtype=np.uint64)
-    r0, r1, r2, r3 = philox4x32_10(b, trial, int(particle) & 0xFFFFFFFF,
+    r0, r1, r2, r3 = philox4x32(b, trial, int(particle) & 0xFFFFFFFF,
                                    c3_word(STREAM_NOISE, generation),
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     z0, z1 = box_muller(r0, r1)
@@ -88,7 +98,7 @@ def noise_normals(seed, generation, particle, trial, n):
 
 def init_state_and_phase(seed, generation, particle, trial):
     """(u0 ~ N(0,1), phase ~ U(0, 2 pi)) for one (particle, trial)."""
-    r0, r1, r2, _ = philox4x32_10(0, trial, int(particle) & 0xFFFFFFFF,
+    r0, r1, r2, _ = philox4x32(0, trial, int(particle) & 0xFFFFFFFF,
                                   c3_word(STREAM_INIT, generation),
                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     z0, _ = box_muller(r0, r1)

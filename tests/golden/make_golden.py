@@ -18,7 +18,7 @@ from oracle import acw, models, ou, philox, summary  # noqa: E402
 dt, n_t = 0.002, 600
 t = dt * np.arange(1, n_t + 1)
 out = {}
-out["philox_block"] = np.array(philox.philox4x32_10(np.arange(4), 1, 2, philox.c3_word(0, 3), 7, 9)).astype(np.uint32)
+out["philox_block"] = np.array(philox.philox4x32(np.arange(4), 1, 2, philox.c3_word(0, 3), 7, 9)).astype(np.uint32)
 out["normals"] = philox.noise_normals(seed=7, generation=3, particle=2, trial=1, n=16)
 u0, ph = philox.init_state_and_phase(7, 3, 2, 1)
 out["u0_phase"] = np.array([u0, ph])

@@ -12,7 +12,7 @@ T = DT * np.arange(1, N_T + 1)
 
 
 def test_oracle_reproduces_golden_vectors():
-    got = np.array(philox.philox4x32_10(np.arange(4), 1, 2, philox.c3_word(0, 3), 7, 9)).astype(np.uint32)
+    got = np.array(philox.philox4x32(np.arange(4), 1, 2, philox.c3_word(0, 3), 7, 9)).astype(np.uint32)
     assert np.array_equal(got, G["philox_block"])
     assert np.allclose(philox.noise_normals(7, 3, 2, 1, 16), G["normals"], rtol=1e-14)
     x = ou.generate_ou_process(0.05, 1.0, DT, N_T * DT, 3, seed=7, n_t=N_T)
