@@ -47,7 +47,9 @@ typedef enum {
 } itjl_status;
 
 enum { ITJL_KIND_OU = 0, ITJL_KIND_OU_OSC = 1 };
-enum { ITJL_SUMMARY_ACF = 0, ITJL_SUMMARY_ACF_MISSING = 1, ITJL_SUMMARY_PSD = 2 };
+enum { ITJL_SUMMARY_ACF = 0, ITJL_SUMMARY_ACF_MISSING = 1,
+       ITJL_SUMMARY_PSD = 2,      /* comp_psd_adfriendly: demeaned, n2 = 2 nextpow2(n) (the oscillation models) */
+       ITJL_SUMMARY_PGRAM = 3 };  /* comp_psd = DSP.periodogram: nfft = nextfastfft(n), one-sided (one_timescale_model, :psd) */
 enum { ITJL_DIST_LINEAR = 0, ITJL_DIST_LOG = 1 };
 enum { ITJL_UPDATE_EXACT = 0, ITJL_UPDATE_EM = 1 };
 
@@ -127,7 +129,8 @@ typedef struct {
     int64_t n_stats;       /* length(model.data_sum_stats): n_lags (ACF) or count(freq_idx) (PSD) */
     const double* target_stats;   /* model.data_sum_stats, n_stats */
     const uint8_t* missing_mask;  /* Matrix{UInt8}(model.missing_mask), (n_trials x n_t) col-major, or NULL */
-    const int32_t* freq_bins;     /* PSD: findall(model.freq_idx) .- 1 (0-based into psd[2:n2/2]), n_stats; else NULL */
+    const int32_t* freq_bins;     /* PSD / PGRAM: findall(model.freq_idx) .- 1 (0-based into the power vector the summary returns,
+                                     whose first entry is the bin after DC), n_stats; else NULL */
 } itjl_model_desc;
 
 int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** model_out);
@@ -247,6 +250,20 @@ int itjl_acf_missing(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_
 /* comp_psd_adfriendly(data, fs; dims = 2)[1]  (src/stats/summary.jl:183-235).
  * out: (n_slices x (n2/2 - 1)) column-major with n2 = 2 * nextpow2(n_t). */
 int itjl_psd_hamming(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double* out);
+/* comp_psd(data, fs; dims = 2, method = "periodogram")[1]  (src/stats/summary.jl:111-155): DSP.periodogram with the
+ * Hamming window, nfft = itjl_nextfastfft(n_t), one-sided, DC dropped.  fp64.
+ * out: (n_slices x nfft/2) column-major; freqs[k] = (k + 1) fs / nfft. */
+int itjl_psd_periodogram(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double* out);
+/* DSP.nextfastfft(n) = nextprod([2, 3, 5, 7], n)  (host only) */
+int64_t itjl_nextfastfft(int64_t n);
+/* comp_psd_lombscargle(times, data, nanmask, dt; dims = 2)[1]  (src/stats/summary.jl:321-356) for times =
+ * dt:dt:n_t*dt: the generalised (floating-mean, standard-normalised) Lomb-Scargle periodogram of the valid
+ * samples of every slice (NaN = missing) on the grid f0 + k df, k < n_freq (the caller passes LombScargle.jl's
+ * autofrequency grid: df = 1 / (5 (n_t - 1) dt), f0 = df / 2, up to 1 / (2 dt)).  Evaluated exactly;
+ * LombScargle.jl's default for more than 200 samples is the Press-Rybicki approximation of the same quantity.
+ * out: (n_slices x n_freq) column-major. */
+int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double dt,
+                         double f0, double df, int64_t n_freq, double* out);
 
 /* ---- acw() ------------------------------------------------------------------------ */
 /* The ACF-based part of acw(data, fs; acwtypes, n_lags, average_over_trials)

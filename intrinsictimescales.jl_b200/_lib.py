@@ -43,7 +43,7 @@ class Tuning(ctypes.Structure):
 
 
 KIND_OU, KIND_OU_OSC = 0, 1
-SUMMARY_ACF, SUMMARY_ACF_MISSING, SUMMARY_PSD = 0, 1, 2
+SUMMARY_ACF, SUMMARY_ACF_MISSING, SUMMARY_PSD, SUMMARY_PGRAM = 0, 1, 2, 3
 DIST_LINEAR, DIST_LOG = 0, 1
 UPDATE_EXACT, UPDATE_EM = 0, 1
 ACW0, ACW50, ACWEULER, AUC, TAU = 1, 2, 4, 8, 16
@@ -100,6 +100,9 @@ SIGNATURES = {
     "itjl_data_upload": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64]),
     "itjl_acw_resident": (ctypes.c_int, [_vp, _f64, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "itjl_ctx_timing_stop": (ctypes.c_int, [_vp]),
+    "itjl_psd_periodogram": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
+    "itjl_nextfastfft": (_i64, [_i64]),
+    "itjl_psd_lombscargle": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _f64, _f64, _i64, _vp]),
 }
 
 

@@ -19,6 +19,10 @@ struct itjl_model {
     size_t psd_smem = 0;
     bool psd_accb_global = false;  // PSD bin sums in global memory (too many selected bins for shared memory)
     double psd_scale = 0.0;
+    // DSP-convention periodogram (ITJL_SUMMARY_PGRAM)
+    itjl::FftPlan pg_plan{};
+    int pg_chunk = 0;
+    size_t pg_smem = 0;
     // multi-GPU parent model: one model per device of the parent context (itjl_api_multi.cu)
     std::vector<itjl_model*> subs;
 };

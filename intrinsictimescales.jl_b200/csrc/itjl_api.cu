@@ -171,14 +171,14 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
     *model_out = nullptr;
     const itjl_model_desc& d = *desc;
     if (d.kind != ITJL_KIND_OU && d.kind != ITJL_KIND_OU_OSC) return fail(ctx, ITJL_ERR_ARG, "model kind must be OU or OU_OSC");
-    if (d.summary < ITJL_SUMMARY_ACF || d.summary > ITJL_SUMMARY_PSD) return fail(ctx, ITJL_ERR_ARG, "invalid summary method");
+    if (d.summary < ITJL_SUMMARY_ACF || d.summary > ITJL_SUMMARY_PGRAM) return fail(ctx, ITJL_ERR_ARG, "invalid summary method");
     if (d.distance != ITJL_DIST_LINEAR && d.distance != ITJL_DIST_LOG) return fail(ctx, ITJL_ERR_ARG, "Distance method must be :linear or :logarithmic");
     if (d.update != ITJL_UPDATE_EXACT && d.update != ITJL_UPDATE_EM) return fail(ctx, ITJL_ERR_ARG, "invalid update rule");
     if (d.n_trials < 1 || d.n_t < 4 || d.n_t > (1 << 24)) return fail(ctx, ITJL_ERR_ARG, "n_trials >= 1 and 4 <= n_t <= 2^24 required");
     if (d.n_stats < 1 || !d.target_stats) return fail(ctx, ITJL_ERR_ARG, "target_stats / n_stats missing");
     if (!(d.dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "dt must be positive");
     if (d.summary == ITJL_SUMMARY_ACF_MISSING && !d.missing_mask) return fail(ctx, ITJL_ERR_ARG, "missing_mask required for the missing-data ACF");
-    if (d.summary == ITJL_SUMMARY_PSD && !d.freq_bins) return fail(ctx, ITJL_ERR_ARG, "freq_bins required for the PSD summary");
+    if ((d.summary == ITJL_SUMMARY_PSD || d.summary == ITJL_SUMMARY_PGRAM) && !d.freq_bins) return fail(ctx, ITJL_ERR_ARG, "freq_bins required for the PSD summary");
     ITJL_LOCK(ctx);
     NvtxRange nvtx("itjl_model_create");
     if (!ctx->subs.empty()) return multi_model_create(ctx, desc, model_out);   // one model per device
@@ -198,7 +198,7 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         for (int64_t i = 0; i < d.n_trials * d.n_t; ++i) masked += d.missing_mask[i] != 0;
         m->mask_frac = (double)masked / (double)(d.n_trials * d.n_t);
     }
-    if (rc == ITJL_OK && d.summary != ITJL_SUMMARY_PSD) {
+    if (rc == ITJL_OK && d.summary != ITJL_SUMMARY_PSD && d.summary != ITJL_SUMMARY_PGRAM) {
         if (d.n_stats > d.n_t) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "n_lags must not exceed n_t"); }
         int g = abc_acf_geometry((int)d.n_t, (int)d.n_stats, ctx->max_smem_optin, &m->geo, &ctx->tuning);
         if (g != 0) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, g == -2 ? "n_lags > 5120 is not supported by the fused ACF kernel" : "trial does not fit in shared memory (n_t too large)"); }
@@ -269,6 +269,26 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         // the host vectors above are block-local: finish the copies before they are destroyed
         if (rc == ITJL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ITJL_ERR_CUDA, "model upload failed");
     }
+    if (rc == ITJL_OK && d.summary == ITJL_SUMMARY_PGRAM) {
+        // dsp.periodogram: nfft = nextfastfft(n_t); bins index power[2:end], i.e. rfft bin k = bin + 1 <= nfft / 2
+        const int nfft = next_fast_len((int)d.n_t);
+        if (d.n_t > 65536 || !fft_plan_make(nfft, &m->pg_plan)) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "periodogram: n_t too large"); }
+        for (int64_t i = 0; i < d.n_stats; ++i)
+            if (d.freq_bins[i] < 0 || d.freq_bins[i] >= nfft / 2) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
+        m->pg_smem = abc_pgram_smem_bytes((int)d.n_t, nfft, (int)d.n_stats, &m->pg_chunk);
+        if ((int64_t)m->pg_smem > ctx->max_smem_optin || m->pg_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "periodogram FFT does not fit in shared memory (n_t too large)"); }
+        std::vector<float> win((size_t)d.n_t);
+        std::vector<float2> roots((size_t)roots_two_level_entries(nfft));
+        std::vector<int32_t> bins((size_t)d.n_stats);
+        for (int64_t i = 0; i < d.n_stats; ++i) bins[(size_t)i] = d.freq_bins[i] + 1;
+        double win_ss = 0.0;
+        pgram_make_tables((int)d.n_t, nfft, win.data(), nullptr, roots.data(), nullptr, &win_ss);
+        m->psd_scale = 1.0 / ((1.0 / d.dt) * win_ss);
+        rc = upload(ctx, m->binidx, bins.data(), bins.size() * sizeof(int32_t));
+        if (rc == ITJL_OK) rc = upload(ctx, m->window, win.data(), win.size() * sizeof(float));
+        if (rc == ITJL_OK) rc = upload(ctx, m->twiddle, roots.data(), roots.size() * sizeof(float2));
+        if (rc == ITJL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ITJL_ERR_CUDA, "model upload failed");
+    }
     if (rc == ITJL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ITJL_ERR_CUDA, "model upload failed");
     if (rc != ITJL_OK) { itjl_model_destroy(m); return rc; }
     *model_out = m;
@@ -296,6 +316,10 @@ int itjl_model_work(const itjl_model* m, double* flops_per_sample, int64_t* samp
         if (m->d.summary == ITJL_SUMMARY_PSD) {
             // one n2-point real FFT per trial (2.5 n2 log2 n2) + |.|^2 on the selected bins + window etc.
             *flops_per_sample = (2.5 * m->n2 * m->log2_n2 + 3.0 * (double)m->d.n_stats) / (double)m->d.n_t + 12.0;
+        } else if (m->d.summary == ITJL_SUMMARY_PGRAM) {
+            // one nfft-point real FFT per trial (two trials per complex transform)
+            const double nfft = (double)m->pg_plan.n;
+            *flops_per_sample = (2.5 * nfft * log2(nfft) + 3.0 * (double)m->d.n_stats) / (double)m->d.n_t + 12.0;
         } else {
             *flops_per_sample = 2.0 * (double)m->d.n_stats + 8.0;
         }
@@ -325,6 +349,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
     m = primary(const_cast<itjl_model*>(m));
     *tensor_flops_per_sample = 0.0;
     if (m->d.summary == ITJL_SUMMARY_PSD) { snprintf(name_out, 32, "k_abc_psd"); return ITJL_OK; }
+    if (m->d.summary == ITJL_SUMMARY_PGRAM) { snprintf(name_out, 32, "k_abc_pgram"); return ITJL_OK; }
     if (!m->use_tc) { snprintf(name_out, 32, "k_abc_acf"); return ITJL_OK; }
     snprintf(name_out, 32, "k_abc_acf_tc");
     double f = 0.0;
@@ -351,7 +376,7 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
     if (n_theta < need_theta) return fail(ctx, ITJL_ERR_ARG, "theta has too few columns for this model");
     if (n_particles < 1 || n_particles > 0x7fffffffll) return fail(ctx, ITJL_ERR_ARG, "n_particles out of range");
     cudaError_t e;
-    NvtxRange nvtx(d.summary == ITJL_SUMMARY_PSD ? "k_abc_psd" : (m->use_tc ? "k_abc_acf_tc" : "k_abc_acf"));
+    NvtxRange nvtx(d.summary == ITJL_SUMMARY_PSD ? "k_abc_psd" : d.summary == ITJL_SUMMARY_PGRAM ? "k_abc_pgram" : (m->use_tc ? "k_abc_acf_tc" : "k_abc_acf"));
     int n_launched = 1;
     if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
     if (d.summary == ITJL_SUMMARY_PSD) {
@@ -392,6 +417,22 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
                 e = abc_psd_launch(Q, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
             }
         }
+    } else if (d.summary == ITJL_SUMMARY_PGRAM) {
+        AbcPgramParams P{};
+        P.theta = theta_dev; P.n_particles = n_particles; P.theta_ld = theta_ld > 0 ? theta_ld : n_particles; P.n_theta = n_theta;
+        P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_stats = (int)d.n_stats;
+        P.chunk = m->pg_chunk; P.plan = m->pg_plan;
+        P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
+        P.update = d.update; P.kind = d.kind; P.distance = d.distance;
+        P.keys = philox_keys(seed);
+        P.c3_noise = philox_c3(kStreamNoise, generation); P.c3_init = philox_c3(kStreamInit, generation);
+        P.particle_offset = particle_offset;
+        P.target = (const float*)m->target.p; P.bins = (const int32_t*)m->binidx.p;
+        P.window = (const float*)m->window.p; P.roots = (const float2*)m->twiddle.p;
+        P.psd_scale = m->psd_scale;
+        P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
+        P.dist_out = dist_dev; P.stats_out = stats_dev;
+        e = abc_pgram_launch(P, d.kind == ITJL_KIND_OU_OSC, m->pg_smem, ctx->stream);
     } else if (m->use_tc) {
         AbcTcParams P{};
         const AbcTcGeometry& t = m->tc;

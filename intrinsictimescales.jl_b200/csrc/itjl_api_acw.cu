@@ -1,6 +1,7 @@
 // C-ABI layer, part 2: summary statistics on stored data and acw()
 // (reference src/stats/summary.jl:46-89, 183-235, 455-496 and src/core/acw.jl:141-231).
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <thread>
 #include <vector>
@@ -227,6 +228,69 @@ int itjl_psd_hamming(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_
     ctx->launches++;
     ITJL_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
     ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // win / tw stay alive until here
+    return ITJL_OK;
+}
+
+int64_t itjl_nextfastfft(int64_t n) { return n > 0 && n <= (1 << 30) ? (int64_t)next_fast_len((int)n) : -1; }
+
+int itjl_psd_periodogram(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double* out) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_psd_periodogram");
+    if (rc != ITJL_OK) return rc;
+    if (!out || !(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_psd_periodogram: null output or fs <= 0");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_psd_periodogram");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    FftPlan plan;
+    const int nfft = n_t <= 65536 ? next_fast_len((int)n_t) : 0;
+    if (!nfft || !fft_plan_make(nfft, &plan)) return fail(ctx, ITJL_ERR_ARG, "itjl_psd_periodogram: n_t > 65536 is not supported");
+    std::vector<double> win((size_t)n_t);
+    std::vector<double2> roots((size_t)nfft);
+    double win_ss = 0.0;
+    pgram_make_tables((int)n_t, nfft, nullptr, win.data(), nullptr, roots.data(), &win_ss);
+    rc = upload_data(ctx, data, n_slices, n_t);
+    if (rc != ITJL_OK) return rc;
+    const int grid = (int)std::min<int64_t>((n_slices + 1) / 2, (int64_t)ctx->sm_count * 4);
+    ITJL_CUDA(ctx, ctx->scratch.reserve(win.size() * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->out3.reserve(roots.size() * sizeof(double2)));
+    ITJL_CUDA(ctx, ctx->out2.reserve((size_t)grid * 2 * nfft * sizeof(double2)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out3.p, roots.data(), roots.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t obytes = (size_t)n_slices * (nfft / 2) * sizeof(double);
+    ITJL_CUDA(ctx, ctx->out.reserve(obytes));
+    cudaError_t e = pgram_data_launch((const double*)ctx->data.p, n_slices, (int)n_t, plan, (const double*)ctx->scratch.p,
+                                      (const double2*)ctx->out3.p, 1.0 / (fs * win_ss), (double2*)ctx->out2.p, grid,
+                                      (double*)ctx->out.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pgram_data: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    rc = download_large(ctx, out, ctx->out.p, obytes);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // win / roots stay alive until here
+    return ITJL_OK;
+}
+
+int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double dt,
+                         double f0, double df, int64_t n_freq, double* out) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_psd_lombscargle");
+    if (rc != ITJL_OK) return rc;
+    if (!out || !(dt > 0.0) || !(df > 0.0) || !(f0 >= 0.0) || n_freq < 1 || n_freq > (1 << 24) || n_slices > 65535)
+        return fail(ctx, ITJL_ERR_ARG, "itjl_psd_lombscargle: invalid argument (need dt, df > 0, f0 >= 0, 1 <= n_freq <= 2^24, n_slices <= 65535)");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_psd_lombscargle");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = upload_data(ctx, data, n_slices, n_t);
+    if (rc != ITJL_OK) return rc;
+    const size_t obytes = (size_t)n_slices * n_freq * sizeof(double);
+    ITJL_CUDA(ctx, ctx->out.reserve(obytes));
+    cudaError_t e = lomb_scargle_launch((const double*)ctx->data.p, n_slices, (int)n_t, dt, f0, df, (int)n_freq, (double*)ctx->out.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_lomb_scargle: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    rc = download_large(ctx, out, ctx->out.p, obytes);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ITJL_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
+#include "fft_mixed.cuh"
 
 namespace itjl {
 
@@ -78,6 +79,41 @@ cudaError_t psd_data_launch(const double* data, int64_t n_slices, int n_t, int n
                             const float* window, const float2* twiddle, double psd_scale,
                             double* out, size_t smem, cudaStream_t st);
 void psd_make_tables(int n_t, int n2, float* window_host, float2* twiddle_host, double* win_ss);
+
+// ---- pgram_kernels.cu ----------------------------------------------------------------
+struct AbcPgramParams {
+    const double* theta;         // (n_particles x n_theta) column-major, leading dimension theta_ld
+    int64_t n_particles;
+    int64_t theta_ld;
+    int n_theta;
+    int n_t, n_trials, n_stats;
+    int chunk;                  // simulate chunk (samples per thread)
+    FftPlan plan;               // nfft = nextfastfft(n_t) and its radices
+    double dt, data_mean, data_sd;
+    int update, kind, distance;
+    PhiloxKeys keys;
+    uint32_t c3_noise, c3_init;
+    int64_t particle_offset;
+    const float* target;        // n_stats
+    const int32_t* bins;        // n_stats: rfft bin k (>= 1) of each statistic
+    const float* window;        // n_t symmetric Hamming window
+    const float2* roots;        // two-level table of the nfft-th roots of unity (roots_two_level_entries(nfft))
+    double psd_scale;           // 1 / (fs * sum(window^2))
+    const double* u0;
+    const double* noise;
+    const double* phases;
+    double* dist_out;
+    double* stats_out;
+};
+size_t abc_pgram_smem_bytes(int n_t, int nfft, int n_stats, int* chunk_out);
+void pgram_make_tables(int n_t, int nfft, float* window_f, double* window_d, float2* roots2_f, double2* roots_d, double* win_ss);
+cudaError_t abc_pgram_launch(const AbcPgramParams& P, bool osc, size_t smem, cudaStream_t st);
+// stored data (n_slices x n_t col-major double), fp64: all nfft/2 bins of every slice; scratch = grid * 2 * nfft double2
+cudaError_t pgram_data_launch(const double* data, int64_t n_slices, int n_t, const FftPlan& plan, const double* window,
+                              const double2* roots, double psd_scale, double2* scratch, int grid, double* out, cudaStream_t st);
+// generalised Lomb-Scargle periodogram of stored data with NaN gaps on the grid f0 + k df, k < n_freq
+cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq,
+                                double* out, cudaStream_t st);
 
 // ---- ou_kernels.cu -------------------------------------------------------------------
 struct OuGenParams {

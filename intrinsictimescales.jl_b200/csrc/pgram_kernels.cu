@@ -1,0 +1,284 @@
+// K6: DSP.jl-convention periodogram (reference src/stats/summary.jl:146-155, `dsp.periodogram(x; fs, window =
+// hamming)`), the summary statistic of one_timescale_model(summary_method = :psd)
+// (src/models/one_timescale.jl:177-203, :255) and the spectrum behind acw(...; acwtypes = :knee)
+// (src/core/acw.jl:244).  Conventions restated in oracle/summary.py::comp_psd_periodogram_vec: no detrending,
+// symmetric Hamming window of the signal's length, nfft = nextfastfft(n) = the next 7-smooth integer (5000 for
+// 10 s at 500 Hz - not a power of two), one-sided power |X|^2 / (fs sum w^2), doubled except at DC and Nyquist,
+// DC bin dropped.
+//
+//   k_abc_pgram<OSC> : fused simulate -> periodogram -> trial mean -> distance, one CTA per particle.  Two trials
+//                      share one nfft-point complex transform (trial A = real part, trial B = imaginary part):
+//                      |X_A[k]|^2 + |X_B[k]|^2 = (|Z[k]|^2 + |Z[nfft - k]|^2) / 2, and only the trial SUM is needed.
+//                      Mixed-radix Stockham FFT (fft_mixed.cuh) ping-ponging between two shared-memory buffers.
+//   k_pgram_data     : the same spectrum of stored data in fp64 (two slices per transform, buffers in a per-CTA
+//                      global scratch area that stays in L2), all nfft / 2 bins out.
+//   k_lomb_scargle   : generalised Lomb-Scargle periodogram of stored data with NaN gaps (summary.jl:254-356)
+#include <math.h>
+
+#include "fft_mixed.cuh"
+#include "kernels.h"
+#include "simulate.cuh"
+
+namespace itjl {
+
+constexpr int kPgramThreads = 512;
+
+template <bool OSC>
+__global__ void __launch_bounds__(kPgramThreads, 1) k_abc_pgram(const __grid_constant__ AbcPgramParams P) {
+    constexpr int NT = kPgramThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);                          // chunk * NT floats: one simulated trial
+    Cx<float>* bufa = reinterpret_cast<Cx<float>*>(xs + P.chunk * NT);        // nfft complex points
+    Cx<float>* bufb = bufa + P.plan.n;
+    float* accb = reinterpret_cast<float*>(bufb + P.plan.n);                 // n_stats bin sums (padded to 4)
+    SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb + ((P.n_stats + 3) & ~3));
+    Cx<float>* rtab = reinterpret_cast<Cx<float>*>(sh + 1);                  // two-level roots of unity
+    __shared__ double red[NT / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t particle = blockIdx.x;
+    const int nfft = P.plan.n;
+
+    const double tau = P.theta[particle];
+    double freq = 0.0, coeff = 1.0;
+    if (OSC) {
+        freq = P.theta[particle + P.theta_ld];
+        coeff = P.theta[particle + 2 * P.theta_ld];
+    }
+    // not reversible: the window is symmetric but no mean is removed by the periodogram - the standardised trial
+    // has mean zero either way, so the reversed exponential is still the same statistic
+    const OuConsts oc = make_ou_consts(tau, P.dt, P.update, OSC ? ITJL_KIND_OU_OSC : ITJL_KIND_OU, freq, coeff, P.n_t, true, true);
+    SimCache sim_cache;
+    SimArgs g;
+    g.n_t = P.n_t; g.chunk = P.chunk;
+    g.inv_n = 1.0 / (double)P.n_t; g.sqrt_nm1 = sqrtf((float)(P.n_t - 1));
+    g.keys = &P.keys; g.c3_noise = P.c3_noise; g.c3_init = P.c3_init;
+    g.particle = (uint32_t)(P.particle_offset + particle);
+    const size_t pt = (size_t)particle * P.n_trials;
+    g.u0 = P.u0 ? P.u0 + pt : nullptr;
+    g.noise = P.noise ? P.noise + pt * P.n_t : nullptr;
+    g.phases = P.phases ? P.phases + pt : nullptr;
+    g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;
+
+    // generate_ou_process(tau, data_sd, ...) has mean zero (one_timescale.jl:226-228); the oscillation generator adds data_mean
+    const float shift = OSC ? (float)P.data_mean : 0.f;
+    for (int b = tid; b < P.n_stats; b += NT) accb[b] = 0.f;
+    const int n_hi = (nfft + (1 << kRootLoBits) - 1) >> kRootLoBits;
+    for (int e = tid; e < n_hi + (1 << kRootLoBits); e += NT) {
+        const float2 r = __ldg(P.roots + e);
+        rtab[e] = {r.x, r.y};
+    }
+    const RootsTwoLevel<float> roots{rtab, rtab + n_hi};
+
+    for (int trial = 0; trial < P.n_trials; trial += 2) {
+        // trial A -> real parts, trial B -> imaginary parts (zero when n_trials is odd), both windowed, zero padded
+        simulate_trial<NT, false, OSC>(g, oc, trial, xs, sh, kScaleStd, (float)P.data_sd, shift, sim_cache);
+        __syncthreads();
+        for (int m = tid; m < nfft; m += NT) bufa[m].x = m < P.n_t ? xs[m] * __ldg(P.window + m) : 0.f;
+        __syncthreads();
+        if (trial + 1 < P.n_trials) {
+            simulate_trial<NT, false, OSC>(g, oc, trial + 1, xs, sh, kScaleStd, (float)P.data_sd, shift, sim_cache);
+            __syncthreads();
+            for (int m = tid; m < nfft; m += NT) bufa[m].y = m < P.n_t ? xs[m] * __ldg(P.window + m) : 0.f;
+        } else {
+            for (int m = tid; m < nfft; m += NT) bufa[m].y = 0.f;
+        }
+        __syncthreads();
+        const Cx<float>* z = fft_mixed_cta<float>(P.plan, bufa, bufb, roots);
+        for (int b = tid; b < P.n_stats; b += NT) {
+            const int k = __ldg(P.bins + b);
+            const Cx<float> zk = z[k], zn = z[nfft - k];
+            accb[b] += fmaf(zk.x, zk.x, zk.y * zk.y) + fmaf(zn.x, zn.x, zn.y * zn.y);
+        }
+        __syncthreads();
+    }
+
+    // power = |X|^2 / (fs sum w^2), doubled except at Nyquist (DC is never selected); 0.5: the pair identity above
+    const double sc = 0.5 * P.psd_scale / (double)P.n_trials;
+    double local = 0.0;
+    for (int b = tid; b < P.n_stats; b += NT) {
+        const int k = __ldg(P.bins + b);
+        const double v = (double)accb[b] * sc * ((2 * k == nfft) ? 1.0 : 2.0);
+        if (P.stats_out) P.stats_out[(size_t)particle * P.n_stats + b] = v;
+        const double tgt = (double)P.target[b];
+        const double e = (P.distance == ITJL_DIST_LINEAR) ? (v - tgt) : (log(v) - log(tgt));
+        local += e * e;
+    }
+    local = warp_sum(local);
+    if ((tid & 31) == 0) red[tid >> 5] = local;
+    __syncthreads();
+    if (tid == 0) {
+        double d = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) d += red[w];
+        P.dist_out[particle] = d / (double)P.n_stats;
+    }
+}
+
+size_t abc_pgram_smem_bytes(int n_t, int nfft, int n_stats, int* chunk_out) {
+    int c = (n_t + kPgramThreads - 1) / kPgramThreads;
+    c = (c + 3) & ~3;
+    *chunk_out = c;
+    return (size_t)c * kPgramThreads * sizeof(float) + (size_t)2 * nfft * sizeof(float2) +
+           (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPgramThreads>) +
+           (size_t)roots_two_level_entries(nfft) * sizeof(float2);
+}
+
+void pgram_make_tables(int n_t, int nfft, float* window_f, double* window_d, float2* roots2_f, double2* roots_d, double* win_ss) {
+    const double PI = 3.14159265358979323846;
+    double ss = 0.0;
+    for (int i = 0; i < n_t; ++i) {
+        const double w = n_t > 1 ? 0.54 - 0.46 * cos(2.0 * PI * (double)i / (double)(n_t - 1)) : 1.0;   // DSP.hamming(n): symmetric
+        if (window_f) window_f[i] = (float)w;
+        if (window_d) window_d[i] = w;
+        ss += w * w;
+    }
+    *win_ss = ss;
+    if (roots2_f) {
+        const int hi = (nfft + (1 << kRootLoBits) - 1) >> kRootLoBits;
+        for (int h = 0; h < hi; ++h) {
+            const double ang = -2.0 * PI * (double)(h << kRootLoBits) / (double)nfft;
+            roots2_f[h] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        for (int l = 0; l < (1 << kRootLoBits); ++l) {
+            const double ang = -2.0 * PI * (double)l / (double)nfft;
+            roots2_f[hi + l] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    }
+    if (roots_d)
+        for (int k = 0; k < nfft; ++k) {
+            const double ang = -2.0 * PI * (double)k / (double)nfft;
+            roots_d[k] = make_double2(cos(ang), sin(ang));
+        }
+}
+
+cudaError_t abc_pgram_launch(const AbcPgramParams& P, bool osc, size_t smem, cudaStream_t st) {
+    void (*kern)(const AbcPgramParams) = osc ? k_abc_pgram<true> : k_abc_pgram<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)P.n_particles, kPgramThreads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+// ---- stored data, fp64 ----------------------------------------------------------------------------------------
+constexpr int kPgramDataThreads = 256;
+
+// CTA b transforms the slice pairs b, b + gridDim.x, ...; scratch: 2 nfft double2 per CTA.
+// out: (n_slices x nfft/2) column-major, bin k = 1 .. nfft/2.
+__global__ void __launch_bounds__(kPgramDataThreads) k_pgram_data(const double* __restrict__ data, int64_t n_slices, int n_t,
+                                                                  const __grid_constant__ FftPlan plan,
+                                                                  const double* __restrict__ window, const double2* __restrict__ roots_tab,
+                                                                  double psd_scale, double2* __restrict__ scratch, double* __restrict__ out) {
+    const int tid = threadIdx.x, nfft = plan.n;
+    Cx<double>* a = reinterpret_cast<Cx<double>*>(scratch) + (size_t)blockIdx.x * 2 * nfft;
+    Cx<double>* b = a + nfft;
+    const RootsTable<double> roots{reinterpret_cast<const Cx<double>*>(roots_tab)};
+    const int64_t n_pairs = (n_slices + 1) / 2;
+    for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const int64_t s0 = 2 * pr, s1 = s0 + 1;
+        for (int m = tid; m < nfft; m += kPgramDataThreads) {
+            Cx<double> v = {0.0, 0.0};
+            if (m < n_t) {
+                const double w = window[m];
+                v.x = data[s0 + (size_t)m * n_slices] * w;
+                if (s1 < n_slices) v.y = data[s1 + (size_t)m * n_slices] * w;
+            }
+            a[m] = v;
+        }
+        __syncthreads();
+        const Cx<double>* z = fft_mixed_cta<double>(plan, a, b, roots);
+        for (int k = 1 + tid; k <= nfft / 2; k += kPgramDataThreads) {
+            const Cx<double> zk = z[k], zn = z[nfft - k];
+            // X_A = (Z[k] + conj Z[n-k]) / 2,  X_B = (Z[k] - conj Z[n-k]) / 2i
+            const double ar = 0.5 * (zk.x + zn.x), ai = 0.5 * (zk.y - zn.y);
+            const double br = 0.5 * (zk.y + zn.y), bi = -0.5 * (zk.x - zn.x);
+            const double f = psd_scale * ((2 * k == nfft) ? 1.0 : 2.0);
+            out[s0 + (size_t)(k - 1) * n_slices] = (ar * ar + ai * ai) * f;
+            if (s1 < n_slices) out[s1 + (size_t)(k - 1) * n_slices] = (br * br + bi * bi) * f;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t pgram_data_launch(const double* data, int64_t n_slices, int n_t, const FftPlan& plan, const double* window,
+                              const double2* roots, double psd_scale, double2* scratch, int grid, double* out, cudaStream_t st) {
+    k_pgram_data<<<grid, kPgramDataThreads, 0, st>>>(data, n_slices, n_t, plan, window, roots, psd_scale, scratch, out);
+    return cudaGetLastError();
+}
+
+// ---- Lomb-Scargle -----------------------------------------------------------------------------------------------
+// Generalised Lomb-Scargle periodogram (floating mean, standard normalisation: what LombScargle.jl's
+// `lombscargle(plan(times, signal; frequencies))` computes with its defaults fit_mean = true, center_data = true,
+// normalization = :standard) of every slice with NaN = missing, on the common grid f_k = f0 + k df.  Samples sit
+// on the regular grid t_j = (j + 1) dt, so the phasor of frequency k advances by a fixed rotation per sample
+// (fp64 recurrence, re-seeded from sincospi every 256 samples).  Thread = frequency, CTA = (slice, block of
+// frequencies); the slice (centred, NaN -> flag) is staged in shared memory in tiles.
+constexpr int kLsThreads = 128;
+constexpr int kLsTile = 1024;
+
+__global__ void __launch_bounds__(kLsThreads) k_lomb_scargle(const double* __restrict__ data, int64_t n_slices, int n_t, double dt,
+                                                             double f0, double df, int n_freq, double* __restrict__ out) {
+    __shared__ double ys[kLsTile];
+    __shared__ double red[2][kLsThreads / 32];
+    const int tid = threadIdx.x;
+    const int64_t s = blockIdx.y;
+    const int k = blockIdx.x * kLsThreads + tid;
+    // mean over the valid samples (center_data)
+    double sum = 0.0, cnt = 0.0;
+    for (int j = tid; j < n_t; j += kLsThreads) {
+        const double v = data[s + (size_t)j * n_slices];
+        if (v == v) { sum += v; cnt += 1.0; }
+    }
+    sum = warp_sum(sum); cnt = warp_sum(cnt);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = sum; red[1][tid >> 5] = cnt; }
+    __syncthreads();
+    sum = 0.0; cnt = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLsThreads / 32; ++w) { sum += red[0][w]; cnt += red[1][w]; }
+    const double mean = sum / cnt;
+
+    const double f = f0 + df * (double)k;
+    const double turn = f * dt;                       // turns per sample
+    double rs, rc;
+    sincospi(2.0 * turn, &rs, &rc);                   // rotation per sample
+    double C = 0.0, S = 0.0, YC = 0.0, YS = 0.0, CC = 0.0, CS = 0.0, YY = 0.0;
+    for (int t0 = 0; t0 < n_t; t0 += kLsTile) {
+        __syncthreads();
+        for (int j = tid; j < kLsTile && t0 + j < n_t; j += kLsThreads) ys[j] = data[s + (size_t)(t0 + j) * n_slices] - mean;   // NaN stays NaN
+        __syncthreads();
+        const int lim = min(kLsTile, n_t - t0);
+        double c = 1.0, sn = 0.0;
+        for (int j = 0; j < lim; ++j) {
+            if ((j & 255) == 0) {
+                double ph = turn * (double)(t0 + j + 1);     // t = (j + 1) dt
+                ph -= floor(ph);
+                sincospi(2.0 * ph, &sn, &c);
+            }
+            const double y = ys[j];
+            if (y == y) {
+                C += c; S += sn; YC = fma(y, c, YC); YS = fma(y, sn, YS);
+                CC = fma(c, c, CC); CS = fma(c, sn, CS); YY = fma(y, y, YY);
+            }
+            const double c2 = c * rc - sn * rs;
+            sn = fma(sn, rc, c * rs);
+            c = c2;
+        }
+    }
+    if (k >= n_freq) return;
+    // weights 1 / n_valid; Y = 0 after centring
+    const double w = 1.0 / cnt;
+    C *= w; S *= w; YC *= w; YS *= w; CC *= w; CS *= w; YY *= w;
+    const double SS = (1.0 - CC) - S * S;
+    CC -= C * C; CS -= C * S;
+    const double D = CC * SS - CS * CS;
+    out[s + (size_t)k * n_slices] = (SS * YC * YC + CC * YS * YS - 2.0 * CS * YC * YS) / (YY * D);
+}
+
+cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq,
+                                double* out, cudaStream_t st) {
+    dim3 grid((unsigned)((n_freq + kLsThreads - 1) / kLsThreads), (unsigned)n_slices);
+    k_lomb_scargle<<<grid, kLsThreads, 0, st>>>(data, n_slices, n_t, dt, f0, df, n_freq, out);
+    return cudaGetLastError();
+}
+
+}  // namespace itjl

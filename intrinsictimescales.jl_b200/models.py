@@ -114,7 +114,8 @@ class GpuModel:
         d = _lib.ModelDesc()
         d.kind = _lib.KIND_OU_OSC if model.kind.startswith("one_timescale_and_osc") else _lib.KIND_OU
         if model.summary_method == "psd":
-            d.summary = _lib.SUMMARY_PSD
+            # one_timescale_model: comp_psd (DSP periodogram); the oscillation models: comp_psd_adfriendly
+            d.summary = _lib.SUMMARY_PGRAM if model.kind == "one_timescale" else _lib.SUMMARY_PSD
         elif model.kind.endswith("with_missing"):
             d.summary = _lib.SUMMARY_ACF_MISSING
         else:
@@ -124,7 +125,8 @@ class GpuModel:
         d.n_trials = int(model.numTrials)
         d.n_t = int(model.n_t)
         d.dt = float(model.dt)
-        d.data_mean = float(model.data_mean)
+        # generate_data of the plain OU models never adds the mean (one_timescale.jl:226-228)
+        d.data_mean = float(model.data_mean) if model.kind.startswith("one_timescale_and_osc") else 0.0
         d.data_sd = float(model.data_sd)
         self._target = np.ascontiguousarray(model.data_sum_stats, dtype=np.float64)
         d.n_stats = self._target.shape[0]
@@ -299,14 +301,43 @@ def _combined(model, distance_combined, weights, data_tau, ctx):
     return model
 
 
+def _one_timescale_psd(data, time, fit_method, prior, distance_method, freqlims, distance_combined, weights,
+                       data_tau, update, dt, T, ctx):
+    """PSD branch of one_timescale_model (one_timescale.jl:177-203): comp_psd = DSP periodogram, frequencies
+    inside freqlims (default (0.5, 100)), logarithmic distance; informed prior and combined distance through the
+    Lorentzian knee (tau_from_knee(find_knee_frequency(...)[2]))."""
+    psd, freqs = summary.comp_psd(data, 1.0 / dt, ctx=ctx)
+    mean_psd = psd.mean(axis=0)
+    if freqlims is None:
+        freqlims = (0.5, 100.0)
+    freq_idx = (freqs < freqlims[1]) & (freqs > freqlims[0])
+    lags_freqs = freqs[freq_idx]
+    stats = np.ascontiguousarray(mean_psd[freq_idx])
+    if prior is None:
+        prior = [Normal(utils.tau_from_knee(utils.find_knee_frequency(stats, lags_freqs, ctx=ctx)[1]), 20.0)]
+    m = TimescaleModel("one_timescale", data, time, fit_method, "psd", lags_freqs, prior,
+                       distance_method or "logarithmic", stats, dt, T, data.shape[0],
+                       float(data.mean()), float(data.std(ddof=1)), freqlims=freqlims, freq_idx=freq_idx,
+                       update=update)
+    if distance_combined:
+        w = [0.5, 0.5] if weights is None else [float(x) for x in weights]
+        if len(w) != 2:
+            raise ValueError("weights must have length 2")
+        m.distance_combined = True
+        m.weights = w
+        m.data_tau = float(data_tau) if data_tau is not None else float(
+            utils.tau_from_knee(utils.find_knee_frequency(stats, lags_freqs, ctx=ctx)[1]))
+    return m
+
+
 def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prior=None,
                         n_lags=None, distance_method=None, distance_combined=False,
-                        weights=None, data_tau=None, update="exact", ctx=None):
+                        weights=None, data_tau=None, update="exact", ctx=None, freqlims=None):
     data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
-    if summary_method != "acf":
-        raise NotImplementedError("summary_method=:psd of one_timescale_model (DSP periodogram) "
-                                  "is a 'next' row (SURVEY.md 8f.1)")
     dt = float(time[1] - time[0]); T = float(time[-1])
+    if summary_method == "psd":
+        return _one_timescale_psd(data, time, fit_method, prior, distance_method, freqlims, distance_combined,
+                                  weights, data_tau, update, dt, T, ctx)
     acf_mean = summary.comp_ac_fft(data).mean(axis=0)
     n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
     m = TimescaleModel("one_timescale", data, time, fit_method, "acf", lags, prior,
@@ -412,7 +443,10 @@ def summary_stats(model, data, ctx=None):
         if model.kind.endswith("with_missing"):
             return summary.comp_ac_time_missing(data, model.n_lags, ctx=ctx).mean(axis=0)
         return summary.comp_ac_fft(data, model.n_lags, ctx=ctx).mean(axis=0)
-    psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt, ctx=ctx)
+    if model.kind == "one_timescale":
+        psd, _ = summary.comp_psd(data, 1.0 / model.dt, ctx=ctx)                 # one_timescale.jl:255
+    else:
+        psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt, ctx=ctx)
     return psd.mean(axis=0)[model.freq_idx]
 
 

@@ -8,9 +8,10 @@ Follows
       :270-272, :333-349,
   /root/reference/src/models/one_timescale_and_osc.jl:98-189, :263-266, :289-297,
       :368-393.
-Out of scope: distance_combined of the oscillation models, the DSP-periodogram PSD
-branch of one_timescale_model, Lomb-Scargle PSD, informed priors that need the
-Lorentzian/knee fits.
+The PSD branch of one_timescale_model is the DSP periodogram (summary.comp_psd_periodogram); informed priors
+and combined distances that need the Lorentzian knee go through oracle/knee.py.
+Out of scope: the Lomb-Scargle PSD branch of the missing-data MODELS (the stored-data
+periodogram is in summary.py).
 """
 import math
 from dataclasses import dataclass, field
@@ -114,12 +115,23 @@ def with_combined_distance(model, weights=(0.5, 0.5), data_tau=None):
 
 
 def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prior=None,
-                        n_lags=None, distance_method=None, update="exact"):
-    """one_timescale.jl:135-175 (ACF branch)."""
-    if summary_method != "acf":
-        raise NotImplementedError("oracle covers the ACF branch only (SURVEY 8f.1)")
+                        n_lags=None, distance_method=None, update="exact", freqlims=None):
+    """one_timescale.jl:135-175 (ACF branch), :177-203 (PSD branch: comp_psd = DSP periodogram)."""
     data, time, prior = _check_inputs(data, time, prior)
     dt = float(time[1] - time[0]); T = float(time[-1])
+    if summary_method == "psd":
+        psd, freqs = summary.comp_psd_periodogram(data, 1.0 / dt)              # :179-180
+        mean_psd = psd.mean(axis=0)
+        if freqlims is None:
+            freqlims = (0.5, 100.0)                                           # :181-183
+        freq_idx = (freqs < freqlims[1]) & (freqs > freqlims[0])              # :184
+        lags_freqs, stats = freqs[freq_idx], mean_psd[freq_idx]
+        if prior is None:                                                     # :187-190 -> :24-26
+            from . import knee
+            prior = [Normal(knee.tau_from_knee(knee.find_knee_frequency(stats, lags_freqs)[1]), 20.0)]
+        return Model("one_timescale", data, time, "psd", distance_method or "logarithmic", prior,
+                     lags_freqs, stats, dt, T, data.shape[0], float(data.mean()), float(data.std(ddof=1)),
+                     freqlims=freqlims, freq_idx=freq_idx, update=update)
     acf_mean = summary.comp_ac_fft(data).mean(axis=0)
     n_lags, lags, stats = _acf_setup(acf_mean, data.shape[1], dt, n_lags)
     if prior is None:
@@ -227,7 +239,10 @@ def summary_stats(model, data):
         if model.kind in ("one_timescale_with_missing", "one_timescale_and_osc_with_missing"):
             return summary.comp_ac_time_missing(data, model.n_lags).mean(axis=0)
         return summary.comp_ac_fft(data, model.n_lags).mean(axis=0)
-    psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt)
+    if model.kind == "one_timescale":
+        psd, _ = summary.comp_psd_periodogram(data, 1.0 / model.dt)              # one_timescale.jl:255
+    else:
+        psd, _ = summary.comp_psd_adfriendly(data, 1.0 / model.dt)
     return psd.mean(axis=0)[model.freq_idx]
 
 
