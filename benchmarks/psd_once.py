@@ -22,9 +22,11 @@ data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.95], dt, n_t * dt, n_tria
 m = pkg.one_timescale_and_osc_model(data, t, "abc", prior=[pkg.Normal(.1, .1), pkg.Normal(10, 5), pkg.Uniform(0, 1)], summary_method="psd")
 g = m.gpu_model(_tun(ctx))
 rng = np.random.default_rng(0)
-theta = np.stack([np.abs(rng.normal(.1, .05, 592)) + 0.01, rng.normal(10, 3, 592), rng.uniform(0.05, 0.95, 592)], axis=1)
+NP = int(os.environ.get('NP', 592))
+print(g.kernel_info())
+theta = np.stack([np.abs(rng.normal(.1, .05, NP)) + 0.01, rng.normal(10, 3, NP), rng.uniform(0.05, 0.95, NP)], axis=1)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     ctx.timing_reset()
     d = g.distances(theta, seed=1, generation=1)
     n, ms = ctx.timing_get()
-print("kernel ms", ms / max(n, 1), "samples/s", 592 * n_trials * n_t / (ms / max(n, 1) * 1e-3), "nan", int(np.isnan(d).sum()))
+print("kernel ms", ms / max(n, 1), "samples/s", NP * n_trials * n_t / (ms / max(n, 1) * 1e-3), "nan", int(np.isnan(d).sum()))

@@ -76,7 +76,8 @@ typedef struct {
     int32_t pinned_upload;   /* 1 (default): large host <-> device copies go through the pinned staging ring */
     int32_t copy_threads;    /* 0 automatic (half the hardware threads, at most 8); host threads feeding that ring */
     int32_t pmc_fp32;        /* -1 automatic (fp32 pair sums above 1e8 pairs); 0 always fp64; 1 always fp32 */
-    int32_t reserved;
+    int32_t psd_v2;          /* 1 (default): PSD models with 4096 < n_t <= 16384 run the warp-specialised kernel k_abc_psd2;
+                                0: always k_abc_psd */
     double tc_error_bound;   /* 5e-6: bound on the predicted |error| of a trial-mean ACF value of k_abc_acf_tc */
 } itjl_tuning;
 int itjl_tuning_default(itjl_tuning* out);

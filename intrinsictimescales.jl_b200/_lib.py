@@ -39,7 +39,7 @@ class Tuning(ctypes.Structure):
                 ("tc_groups", ctypes.c_int32), ("tc_seg_trials", ctypes.c_int32), ("tc_bias", ctypes.c_int32),
                 ("abc_threads", ctypes.c_int32), ("abc_bufs", ctypes.c_int32), ("acw_stream", ctypes.c_int32),
                 ("acw_waves", ctypes.c_int32), ("pinned_upload", ctypes.c_int32), ("copy_threads", ctypes.c_int32),
-                ("pmc_fp32", ctypes.c_int32), ("reserved", ctypes.c_int32), ("tc_error_bound", ctypes.c_double)]
+                ("pmc_fp32", ctypes.c_int32), ("psd_v2", ctypes.c_int32), ("tc_error_bound", ctypes.c_double)]
 
 
 KIND_OU, KIND_OU_OSC = 0, 1

@@ -19,6 +19,8 @@ struct itjl_model {
     size_t psd_smem = 0;
     bool psd_accb_global = false;  // PSD bin sums in global memory (too many selected bins for shared memory)
     double psd_scale = 0.0;
+    bool psd_v2 = false;           // warp-specialised kernel k_abc_psd2 (4096 < n_t <= 16384 and everything fits)
+    int psd_round0_bins = 0;
     // DSP-convention periodogram (ITJL_SUMMARY_PGRAM)
     itjl::FftPlan pg_plan{};
     int pg_chunk = 0;

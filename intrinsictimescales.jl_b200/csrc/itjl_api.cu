@@ -33,7 +33,7 @@ int itjl_device_count(int* n_out) {
 int itjl_tuning_default(itjl_tuning* t) {
     if (!t) return fail(nullptr, ITJL_ERR_ARG, "itjl_tuning_default: null output");
     memset(t, 0, sizeof(*t));
-    t->abc_tc = -1; t->tc_tail_max = -1; t->tc_bias = 1; t->acw_stream = 1; t->pinned_upload = 1; t->pmc_fp32 = -1;
+    t->abc_tc = -1; t->tc_tail_max = -1; t->tc_bias = 1; t->acw_stream = 1; t->pinned_upload = 1; t->pmc_fp32 = -1; t->psd_v2 = 1;
     t->tc_error_bound = 5e-6;
     return ITJL_OK;
 }
@@ -232,14 +232,23 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         m->log2_n2 = 0; while ((1 << m->log2_n2) < m->n2) m->log2_n2++;
         for (int64_t i = 0; i < d.n_stats; ++i)
             if (d.freq_bins[i] < 0 || d.freq_bins[i] >= m->n2 / 2 - 1) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
-        m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
-        if ((int64_t)m->psd_smem > ctx->max_smem_optin) {
-            // many selected bins (e.g. fs = 250 Hz: 80 % of 16 384): keep the per-particle bin sums in global memory
-            m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len, false);
-            m->psd_accb_global = true;
+        // k_abc_psd2 (warp-specialised, pruned first stage) when the shape is in its range and everything fits in
+        // shared memory; tuning.psd_v2 = 0 keeps the first kernel
+        if (ctx->tuning.psd_v2 != 0 && abc_psd2_supported((int)d.n_t, m->n2)) {
+            const size_t sm2 = abc_psd2_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
+            if ((int64_t)sm2 <= ctx->max_smem_optin && m->psd_chunk <= kQtab) { m->psd_v2 = true; m->psd_smem = sm2; }
         }
-        if ((int64_t)m->psd_smem > ctx->max_smem_optin || m->psd_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
-        std::vector<float> win((size_t)d.n_t + 1, 0.0f);          // +1: the kernel reads the window as float2 pairs
+        if (!m->psd_v2) {
+            m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
+            if ((int64_t)m->psd_smem > ctx->max_smem_optin) {
+                // many selected bins (e.g. fs = 250 Hz: 80 % of 16 384): keep the per-particle bin sums in global memory
+                m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len, false);
+                m->psd_accb_global = true;
+            }
+            if ((int64_t)m->psd_smem > ctx->max_smem_optin || m->psd_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
+        }
+        // window padded with zeros to the simulate buffer (k_abc_psd2 multiplies inside the simulator, 16 bytes at a time)
+        std::vector<float> win((size_t)std::max<int64_t>(d.n_t + 1, m->psd_xs_len) + 4, 0.0f);
         std::vector<float2> tw((size_t)m->n2 / 2);
         double win_ss = 0.0;
         psd_make_tables((int)d.n_t, m->n2, win.data(), tw.data(), &win_ss);
@@ -249,17 +258,25 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         std::vector<int4> binpos((size_t)d.n_stats);
         std::vector<int32_t> order((size_t)d.n_stats);
         for (int64_t i = 0; i < d.n_stats; ++i) order[(size_t)i] = (int32_t)i;
-        {
-            const int N = m->n2 / 2;
-            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-                return psd_fft_pos(d.freq_bins[a] + 1, N) < psd_fft_pos(d.freq_bins[b] + 1, N);
-            });
-        }
+        const int N = m->n2 / 2;
+        auto bin_addr = [&](int k, int* round) {
+            int addr = 0; *round = 0;
+            if (m->psd_v2) abc_psd2_bin(k, N, &addr, round); else addr = psd_fft_pos(k, N);
+            return addr;
+        };
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            int ra, rb;
+            const int pa = bin_addr(d.freq_bins[a] + 1, &ra), pb = bin_addr(d.freq_bins[b] + 1, &rb);
+            return ra != rb ? ra < rb : pa < pb;
+        });
+        m->psd_round0_bins = 0;
         for (int64_t i = 0; i < d.n_stats; ++i) {
-            const int k = d.freq_bins[order[(size_t)i]] + 1, N = m->n2 / 2;
-            int wx, wy;                                     // the bin's twiddle exp(-2 pi i k / n2), as float bits
+            const int k = d.freq_bins[order[(size_t)i]] + 1;
+            int wx, wy, r0, r1;                             // the bin's twiddle exp(-2 pi i k / n2), as float bits
             memcpy(&wx, &tw[(size_t)k].x, 4); memcpy(&wy, &tw[(size_t)k].y, 4);
-            binpos[(size_t)i] = make_int4(psd_fft_pos(k, N), psd_fft_pos(N - k, N), wx, wy);
+            const int pk = bin_addr(k, &r0), pn = bin_addr(N - k, &r1);
+            binpos[(size_t)i] = make_int4(pk, pn, wx, wy);
+            if (r0 == 0) m->psd_round0_bins = (int)i + 1;
         }
         rc = upload(ctx, m->binidx, order.data(), order.size() * sizeof(int32_t));
         if (rc == ITJL_OK)
@@ -348,7 +365,7 @@ int itjl_model_kernel_info(const itjl_model* m, char* name_out, double* tensor_f
     if (!m || !name_out || !tensor_flops_per_sample) return fail(m ? m->ctx : nullptr, ITJL_ERR_ARG, "itjl_model_kernel_info: null argument");
     m = primary(const_cast<itjl_model*>(m));
     *tensor_flops_per_sample = 0.0;
-    if (m->d.summary == ITJL_SUMMARY_PSD) { snprintf(name_out, 32, "k_abc_psd"); return ITJL_OK; }
+    if (m->d.summary == ITJL_SUMMARY_PSD) { snprintf(name_out, 32, m->psd_v2 ? "k_abc_psd2" : "k_abc_psd"); return ITJL_OK; }
     if (m->d.summary == ITJL_SUMMARY_PGRAM) { snprintf(name_out, 32, "k_abc_pgram"); return ITJL_OK; }
     if (!m->use_tc) { snprintf(name_out, 32, "k_abc_acf"); return ITJL_OK; }
     snprintf(name_out, 32, "k_abc_acf_tc");
@@ -394,7 +411,10 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
         P.psd_scale = m->psd_scale;
         P.u0 = u0_dev; P.noise = noise_dev; P.phases = phases_dev;
         P.dist_out = dist_dev; P.stats_out = stats_dev;
-        if (!m->psd_accb_global) {
+        P.round0_bins = m->psd_round0_bins;
+        if (m->psd_v2) {
+            e = abc_psd2_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
+        } else if (!m->psd_accb_global) {
             e = abc_psd_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
         } else {
             // sub-batches of at most 2048 particles, each with its own row of bin sums in a scratch buffer

@@ -69,11 +69,17 @@ struct AbcPsdParams {
     float* accb_global = nullptr;   // per-particle bin sums in global memory [grid][(n_stats + 3) & ~3] when they do not fit
                                     // in shared memory beside the FFT buffer (many selected bins), else null
     int64_t grid = 0;               // CTAs of this launch (a sub-batch of the particles when accb_global is used)
+    int round0_bins = 0;            // k_abc_psd2: entries of binpos that belong to the first round of sub-transforms
 };
 size_t abc_psd_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out, bool accb_in_smem = true);
 int psd_fft_pos(int k, int N);
 size_t psd_fft_smem_bytes(int n2);
 cudaError_t abc_psd_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st);
+// psd2_kernels.cu: warp-specialised version for 4096 < n_t <= 16384
+bool abc_psd2_supported(int n_t, int n2);
+size_t abc_psd2_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out);
+void abc_psd2_bin(int k, int N, int* addr, int* round);
+cudaError_t abc_psd2_launch(const AbcPsdParams& P, bool osc, size_t smem, cudaStream_t st);
 // standalone: comp_psd_adfriendly on stored data (n_slices x n_t col-major double)
 cudaError_t psd_data_launch(const double* data, int64_t n_slices, int n_t, int n2, int log2_n2,
                             const float* window, const float2* twiddle, double psd_scale,

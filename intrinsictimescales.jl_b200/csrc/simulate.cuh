@@ -127,6 +127,7 @@ struct SimArgs {
     const uint32_t* mask_bits;  // [trial][mask_words] missing-sample bitmap, or null
     const int* n_valid;         // [trial] number of valid samples
     int mask_words;
+    const float* win = nullptr;   // optional window (chunk * NT floats, 16-byte aligned): the output is multiplied by it (plain sink only)
 };
 
 // Per-thread values that do not change from trial to trial (filled during the first trial).
@@ -463,6 +464,10 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
                 }
             }
             if (!TC) {
+                if (g.win) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.win + j));
+                    v[0] *= w4.x; v[1] *= w4.y; v[2] *= w4.z; v[3] *= w4.w;
+                }
 #pragma unroll
                 for (int h = 0; h < STEP; h += 4)
                     *reinterpret_cast<float4*>(xs + j + h) = make_float4(v[h], v[h + 1], v[h + 2], v[h + 3]);
