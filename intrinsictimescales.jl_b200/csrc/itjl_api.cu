@@ -413,6 +413,9 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
         P.dist_out = dist_dev; P.stats_out = stats_dev;
         P.round0_bins = m->psd_round0_bins;
         if (m->psd_v2) {
+#ifdef ITJL_TUNING
+            { const char* dbg = getenv("ITJL_PSD_DEBUG"); P.grid = dbg ? atoi(dbg) : 0; }   // tuning builds only
+#endif
             e = abc_psd2_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);
         } else if (!m->psd_accb_global) {
             e = abc_psd_launch(P, d.kind == ITJL_KIND_OU_OSC, m->psd_smem, ctx->stream);

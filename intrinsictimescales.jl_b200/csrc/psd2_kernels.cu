@@ -5,9 +5,15 @@
 //
 // What changed against k_abc_psd (measured there: simulate 24 %, window / pack 10 %, FFT + bins 66 % of a trial,
 // serialised by __syncthreads, 59 % issue slots):
-//   * warp specialisation: a simulate group (4 warps) produces trial t + 1 - already multiplied by the window -
+//   * warp specialisation: a simulate group (12 warps) produces trial t + 1 - already multiplied by the window -
 //     into one of two trial buffers while the transform group (16 warps) works on trial t; full / empty
 //     mbarriers per buffer, named barriers inside the groups, no CTA-wide barrier in the trial loop.
+//     Measured at C4 (clock64 around the waits, make EXTRA=-DITJL_TUNING; ITJL_PSD_DEBUG=4 / 8 runs one group alone):
+//     transform group alone 17.0 k cycles per trial at 80 registers (18.3 k at 72), simulate group alone 13.6 k with
+//     4 or 8 warps (it is latency bound: Philox / Box-Muller chains), 10.6 k with 12 warps, four counter blocks per
+//     iteration and the fp32 phase increments; together 30.7 k (4 warps: the transform group waits 39 % of the
+//     time), 24.1 k (8 warps), 21.6 k (12 warps, 72 registers per thread: both groups wait < 3 %).  Which warp ids
+//     the simulate group gets and suspend-hint / nanosleep waits made no difference.
 //   * the zero padding is never stored or transformed.  The first DIF stage of radix R0 = N / 4096 splits the
 //     transform into R0 independent 4096-point transforms of y_J[p] = w_N^(J p) sum_m z[p + 4096 m] W_R0^(J m);
 //     only m = 0 and (for p + 4096 < n_t / 2) m = 1 are non-zero, so y_J is formed in registers straight from the
@@ -25,7 +31,10 @@
 
 namespace itjl {
 
-constexpr int kPsd2SimThreads = 128;
+#ifndef ITJL_PSD2_KPRE
+#define ITJL_PSD2_KPRE 1   // bin-table rows fetched under the last pass (release builds measured: 1: 1.29e11, 2: 1.24e11, 3: 1.19e11, 4: 1.21e11 samples/s at C4)
+#endif
+constexpr int kPsd2SimThreads = 384;
 constexpr int kPsd2FftThreads = 512;
 constexpr int kPsd2Threads = kPsd2SimThreads + kPsd2FftThreads;
 constexpr int kSub = 4096;                        // points of one sub-transform
@@ -88,9 +97,10 @@ __device__ __forceinline__ void r16_butterfly(float2 (&x)[16], float2 a0, float2
 
 // First pass of sub-transform J (of R0): thread u < 256 owns points p = u + 256 e.  z = the windowed trial as
 // float2 pairs, z_len = number of pairs stored (zeros beyond the data are stored up to there, nothing beyond).
+// t1 = W_4096^u, s1 = W_1024^u (the pass twiddles of thread u), c = w_N^(J u): constant over the trials, kept in registers
 template <int R0, int J>
-__device__ __forceinline__ void psd2_pass1(const float2* __restrict__ z, int z_len, float2* __restrict__ buf, int u, int Ntab,
-                                           const Tw2& tw) {
+__device__ __forceinline__ void psd2_pass1(const float2* __restrict__ z, int z_len, float2* __restrict__ buf, int u,
+                                           const float2 t1, const float2 s1, const float2 c) {
     float2 x[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -107,44 +117,27 @@ __device__ __forceinline__ void psd2_pass1(const float2* __restrict__ z, int z_l
         if (J != 0 && e != 0) v = cmul(v, w64((R0 == 4 ? 1 : 2) * J * e));
         x[e] = v;
     }
-    // pass twiddles of the 4096-point transform (span 4096, q = 256, index u): W_4096^u = tw(u * 2 Ntab / 4096);
-    // the per-thread factor w_N^(J u) = tw(2 J u) multiplies every output
-    const int tstep = (2 * Ntab) >> 12;
-    if (J == 0) {
-        if (u != 0) {
-            const float2 t1 = tw(u * tstep);
-            const float2 t2 = cmul(t1, t1);
-            const float2 t3 = cmul(t2, t1);
-            r16_butterfly<false, true, true>(x, t1, t1, t2, t3, tw(4 * u * tstep));
-        } else {
-            r16_butterfly<false, false, false>(x, x[0], x[0], x[0], x[0], x[0]);
-        }
-    } else {
-        const float2 c = tw(2 * J * u);
-        const float2 t1 = tw(u * tstep);
-        const float2 t2 = cmul(t1, t1);
-        const float2 t3 = cmul(t2, t1);
-        r16_butterfly<true, true, true>(x, c, cmul(t1, c), cmul(t2, c), cmul(t3, c), tw(4 * u * tstep));
-    }
+    // pass twiddles of the 4096-point transform (span 4096, q = 256, index u); the per-thread factor w_N^(J u)
+    // multiplies every output
+    const float2 t2 = cmul(t1, t1);
+    const float2 t3 = cmul(t2, t1);
+    if (J == 0) r16_butterfly<false, true, true>(x, t1, t1, t2, t3, s1);
+    else r16_butterfly<true, true, true>(x, c, cmul(t1, c), cmul(t2, c), cmul(t3, c), s1);
 #pragma unroll
     for (int e = 0; e < 16; ++e) buf[fft_pad(u + 256 * e)] = x[e];
 }
 
 // passes 2 (span 256) and 3 (span 16, twiddle free) of a 4096-point transform, thread u < 256
-__device__ __forceinline__ void psd2_pass2(float2* __restrict__ buf, int u, int Ntab, const Tw2& tw) {
+__device__ __forceinline__ void psd2_pass2(float2* __restrict__ buf, int u, const float2 t1, const float2 s1) {
     const int j = u & 15;
     const int base = ((u >> 4) << 8) + j;
-    const int tstep = (2 * Ntab) >> 8;
     float2 x[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) x[e] = buf[fft_pad(base + 16 * e)];
-    if (j != 0) {
-        const float2 t1 = tw(j * tstep);
+    {
         const float2 t2 = cmul(t1, t1);
         const float2 t3 = cmul(t2, t1);
-        r16_butterfly<false, true, true>(x, t1, t1, t2, t3, tw(4 * j * tstep));
-    } else {
-        r16_butterfly<false, false, false>(x, x[0], x[0], x[0], x[0], x[0]);
+        r16_butterfly<false, true, true>(x, t1, t1, t2, t3, s1);
     }
 #pragma unroll
     for (int e = 0; e < 16; ++e) buf[fft_pad(base + 16 * e)] = x[e];
@@ -160,17 +153,17 @@ __device__ __forceinline__ void psd2_pass3(float2* __restrict__ buf, int u) {
 }
 
 template <int R0>
-__device__ __forceinline__ void psd2_pass1_any(int J, const float2* z, int z_len, float2* buf, int u, int Ntab, const Tw2& tw) {
+__device__ __forceinline__ void psd2_pass1_any(int J, const float2* z, int z_len, float2* buf, int u, float2 t1, float2 s1, float2 c) {
     if (R0 == 4) {
         switch (J) {
-            case 0: psd2_pass1<4, 0>(z, z_len, buf, u, Ntab, tw); break;
-            case 1: psd2_pass1<4, 1>(z, z_len, buf, u, Ntab, tw); break;
-            case 2: psd2_pass1<4, 2>(z, z_len, buf, u, Ntab, tw); break;
-            default: psd2_pass1<4, 3>(z, z_len, buf, u, Ntab, tw); break;
+            case 0: psd2_pass1<4, 0>(z, z_len, buf, u, t1, s1, c); break;
+            case 1: psd2_pass1<4, 1>(z, z_len, buf, u, t1, s1, c); break;
+            case 2: psd2_pass1<4, 2>(z, z_len, buf, u, t1, s1, c); break;
+            default: psd2_pass1<4, 3>(z, z_len, buf, u, t1, s1, c); break;
         }
     } else {
-        if (J == 0) psd2_pass1<2, 0>(z, z_len, buf, u, Ntab, tw);
-        else psd2_pass1<2, 1>(z, z_len, buf, u, Ntab, tw);
+        if (J == 0) psd2_pass1<2, 0>(z, z_len, buf, u, t1, s1, c);
+        else psd2_pass1<2, 1>(z, z_len, buf, u, t1, s1, c);
     }
 }
 
@@ -182,17 +175,21 @@ __global__ void __launch_bounds__(kPsd2Threads, 1) k_abc_psd2(const __grid_const
     float* accb = reinterpret_cast<float*>(bufs + 2 * kSubBuf);              // n_stats bin sums, in table order
     const int n_stats_pad = (P.n_stats + 3) & ~3;
     SimShared<kPsd2SimThreads>* sh = reinterpret_cast<SimShared<kPsd2SimThreads>*>(accb + n_stats_pad);
-    float2* twtab = reinterpret_cast<float2*>(sh + 1);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(twtab + tw2_entries(P.n2 >> 1));      // full[2], empty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sh + 1);                    // full[2], empty[2]
     __shared__ double red[kPsd2FftThreads / 32];
 
-    const int tid = threadIdx.x;
+#ifdef ITJL_PSD2_SIM_FIRST
+    const int tid0 = threadIdx.x;
+    const bool is_sim = tid0 < kPsd2SimThreads;                              // simulate group = the LOWEST warp ids
+    const int tid = is_sim ? tid0 + kPsd2FftThreads : tid0 - kPsd2SimThreads;   // role-local numbering as below
+#else
+    const int tid = threadIdx.x;                                             // transform group first, simulate group = the highest warp ids
+#endif
     const int64_t particle = blockIdx.x;
     const int N = P.n2 >> 1;
 
-    for (int b = tid; b < P.n_stats; b += kPsd2Threads) accb[b] = 0.f;
-    const Tw2 tw = tw2_build(twtab, P.twiddle, N, tid, kPsd2Threads);
-    if (tid == 0) {
+    for (int b = threadIdx.x; b < P.n_stats; b += kPsd2Threads) accb[b] = 0.f;
+    if (threadIdx.x == 0) {
         tc::mbar_init(&bars[0], kPsd2SimThreads); tc::mbar_init(&bars[1], kPsd2SimThreads);
         tc::mbar_init(&bars[2], kPsd2FftThreads); tc::mbar_init(&bars[3], kPsd2FftThreads);
         tc::fence_mbar_init();
@@ -222,15 +219,30 @@ __global__ void __launch_bounds__(kPsd2Threads, 1) k_abc_psd2(const __grid_const
         g.phases = P.phases ? P.phases + pt : nullptr;
         g.mask_bits = nullptr; g.n_valid = nullptr; g.mask_words = 0;
         g.win = P.window;
+#ifdef ITJL_TUNING
+        long long s_wait = 0; const long long s_t0 = clock64();
+#endif
         for (int trial = 0; trial < P.n_trials; ++trial) {
             const int b = trial & 1;
+#ifdef ITJL_TUNING
+            const long long w0 = clock64();
+#endif
             if (trial >= 2) tc::mbar_wait(&bars[2 + b], ((trial >> 1) - 1) & 1);     // the transform group has read trial - 2
+#ifdef ITJL_TUNING
+            s_wait += clock64() - w0;
+#endif
             // standardised series * data_sd (the reference adds data_mean and comp_psd_adfriendly removes the mean
             // again, summary.jl:209 - both skipped), times the Hamming window
-            simulate_trial<kPsd2SimThreads, false, OSC>(g, oc, trial, xs0 + b * P.xs_len, sh, kScaleStd, (float)P.data_sd, 0.0f,
+#ifdef ITJL_TUNING
+            if (!(P.grid & 8))
+#endif
+            simulate_trial<kPsd2SimThreads, false, OSC, false, true>(g, oc, trial, xs0 + b * P.xs_len, sh, kScaleStd, (float)P.data_sd, 0.0f,
                                                         sim_cache, stid, kBarSim);
             tc::mbar_arrive(&bars[b]);
         }
+#ifdef ITJL_TUNING
+        if (blockIdx.x == 0 && stid == 0) printf("sim group: total %lld clk, waiting for a free buffer %lld clk\n", clock64() - s_t0, s_wait);
+#endif
         return;
     }
 
@@ -239,32 +251,65 @@ __global__ void __launch_bounds__(kPsd2Threads, 1) k_abc_psd2(const __grid_const
     float2* mybuf = bufs + half * kSubBuf;
     const int z_len = P.xs_len >> 1;
     constexpr int kRounds = R0 == 4 ? 2 : 1;
+    // this thread's twiddles (the same for every trial): exp(-2 pi i idx / 2N) from the global table, once
+    const float2 p1_t1 = tw_lookup(P.twiddle, u * ((2 * N) >> 12), N), p1_s1 = tw_lookup(P.twiddle, 4 * u * ((2 * N) >> 12), N);
+    const float2 p2_t1 = tw_lookup(P.twiddle, (u & 15) * ((2 * N) >> 8), N), p2_s1 = tw_lookup(P.twiddle, 4 * (u & 15) * ((2 * N) >> 8), N);
+    const float2 c_r0 = tw_lookup(P.twiddle, 2 * (R0 == 4 ? 2 * half : half) * u, N);        // w_N^(J u) of round 0 ...
+    const float2 c_r1 = tw_lookup(P.twiddle, 2 * (1 + 2 * half) * u, N);                      // ... and round 1
+#ifdef ITJL_TUNING
+    long long f_wait = 0; const long long f_t0 = clock64();
+#endif
     for (int trial = 0; trial < P.n_trials; ++trial) {
         const int b = trial & 1;
         const float2* z = reinterpret_cast<const float2*>(xs0 + b * P.xs_len);
+#ifdef ITJL_TUNING
+        const long long w0 = clock64();
+#endif
         tc::mbar_wait(&bars[b], (trial >> 1) & 1);
+#ifdef ITJL_TUNING
+        f_wait += clock64() - w0;
+#endif
         int bin_lo = 0;
+#ifdef ITJL_TUNING
+        if (P.grid & 4) { tc::mbar_arrive(&bars[2 + b]); continue; }
+#endif
 #pragma unroll 1
         for (int round = 0; round < kRounds; ++round) {
             // R0 = 4: round 0 transforms J = 0 (half 0) and 2 (half 1), round 1 J = 1 and 3; R0 = 2: J = half
             const int J = R0 == 4 ? round + 2 * half : half;
-            psd2_pass1_any<R0>(J, z, z_len, mybuf, u, N, tw);
+            psd2_pass1_any<R0>(J, z, z_len, mybuf, u, p1_t1, p1_s1, round == 0 ? c_r0 : c_r1);
             if (round == kRounds - 1) tc::mbar_arrive(&bars[2 + b]);         // last read of the trial buffer
             tc::named_bar_sync(kBarHalf0 + half, 256);
-            psd2_pass2(mybuf, u, N, tw);
+            psd2_pass2(mybuf, u, p2_t1, p2_s1);
             tc::named_bar_sync(kBarHalf0 + half, 256);
+            // bins of this round (table sorted by round, then storage position): the first rows are fetched from L2
+            // under the last pass
+            const int bin_hi = round == 0 ? P.round0_bins : P.n_stats;
+            constexpr int kPre = ITJL_PSD2_KPRE;
+            int4 pre[kPre];
+#pragma unroll
+            for (int i = 0; i < kPre; ++i) {
+                const int bb = bin_lo + tid + i * kPsd2FftThreads;
+                pre[i] = bb < bin_hi ? __ldg(P.binpos + bb) : make_int4(0, 0, 0, 0);
+            }
             psd2_pass3(mybuf, u);
             tc::named_bar_sync(kBarFft, kPsd2FftThreads);
-            // bins of this round (table sorted by round, then storage position): rows come from L2, four in flight
-            const int bin_hi = round == 0 ? P.round0_bins : P.n_stats;
+#pragma unroll
+            for (int i = 0; i < kPre; ++i) {
+                const int bb = bin_lo + tid + i * kPsd2FftThreads;
+                if (bb < bin_hi) accb[bb] += real_fft_power_at(bufs, pre[i]);
+            }
 #pragma unroll 4
-            for (int bb = bin_lo + tid; bb < bin_hi; bb += kPsd2FftThreads)
+            for (int bb = bin_lo + tid + kPre * kPsd2FftThreads; bb < bin_hi; bb += kPsd2FftThreads)
                 accb[bb] += real_fft_power_at(bufs, __ldg(P.binpos + bb));
             bin_lo = bin_hi;
             tc::named_bar_sync(kBarFft, kPsd2FftThreads);
         }
     }
 
+#ifdef ITJL_TUNING
+    if (blockIdx.x == 0 && tid == 0) printf("transform group: total %lld clk, waiting for a trial %lld clk\n", clock64() - f_t0, f_wait);
+#endif
     const double sc = P.psd_scale / (double)P.n_trials;
     double local = 0.0;
     for (int bb = tid; bb < P.n_stats; bb += kPsd2FftThreads) {
@@ -290,13 +335,16 @@ __global__ void __launch_bounds__(kPsd2Threads, 1) k_abc_psd2(const __grid_const
 bool abc_psd2_supported(int n_t, int n2) { return n2 == 16384 || n2 == 32768 ? n_t > 4 : false; }
 
 size_t abc_psd2_smem_bytes(int n_t, int n2, int n_stats, int* chunk_out, int* xs_len_out) {
+    // samples per simulate thread: a multiple of 4 with chunk / 4 odd, so that the 16-byte accesses of a warp at a
+    // stride of `chunk` floats spread over all banks (chunk = 80: 16 wavefronts per access instead of 4)
     int c = (n_t + kPsd2SimThreads - 1) / kPsd2SimThreads;
-    c = (c + 7) & ~7;
+    c = (c + 3) & ~3;
+    if (((c >> 2) & 1) == 0) c += 4;
     *chunk_out = c;
     *xs_len_out = c * kPsd2SimThreads;
     return (size_t)2 * c * kPsd2SimThreads * sizeof(float) + (size_t)2 * kSubBuf * sizeof(float2) +
            (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPsd2SimThreads>) +
-           (size_t)tw2_entries(n2 / 2) * sizeof(float2) + 4 * sizeof(uint64_t);
+           4 * sizeof(uint64_t);
 }
 
 // position of bin k (1 <= k < N) of the packed transform in the two sub-transform buffers, and its round

@@ -32,6 +32,7 @@ struct OuConsts {
     float sc;     // sqrt(coeff)            (1 for the plain OU model)
     float so;     // sqrt(1-coeff)*sqrt(2)  (0 for the plain OU model)
     double fdt;   // freq * dt, in turns per sample
+    float fdt_f;  // the same in fp32, reduced to [-0.5, 0.5]
     float x0_mul; // factor on the drawn initial state (1; e^-G for a growing trajectory, see below)
     float x0_add; // added to it (0; 1 with x0_mul = 0 for the noise-free limit)
     double lna;   // ln a (NaN when a <= 0: Euler-Maruyama with dt > tau), a64 = a: for the table of 1 - a^(j+1)
@@ -71,7 +72,7 @@ __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int up
         eps = dt / tau;
         s = sqrt(dt);
     }
-    c.sc = 1.0f; c.so = 0.0f; c.fdt = 0.0;
+    c.sc = 1.0f; c.so = 0.0f; c.fdt = 0.0; c.fdt_f = 0.0f;
     c.x0_mul = 1.0f; c.x0_add = 0.0f;
     if (kind == ITJL_KIND_OU_OSC) {
         // ou_process.jl:189-196: only values outside [0, 1] are moved
@@ -79,6 +80,7 @@ __device__ __forceinline__ OuConsts make_ou_consts(double tau, double dt, int up
         c.sc = (float)sqrt(coeff);
         c.so = (float)(sqrt(1.0 - coeff) * 1.4142135623730951);
         c.fdt = freq * dt;
+        c.fdt_f = (float)(c.fdt - rint(c.fdt));
     }
     if (eps < 0.0 && scalable && n_t > 0) {
         const double G = (double)n_t * log1p(-eps);          // ln a^n
@@ -168,7 +170,9 @@ __device__ __forceinline__ void sim_sync(int bar_id, int nt) {
 //   kScaleStd      : (x - mean) / std_{n-1} * scale + shift            (PSD kernel, generator)
 //   kScaleRaw      : x                                                 (standardize = false)
 // and zeros for j >= n_t.
-template <int NT, bool MISSING, bool OSC, bool TC = false>
+// WIDE: four Philox counter blocks (16 samples) per iteration of the interior loop instead of two - for callers that
+// run few simulate warps (latency bound: k_abc_psd2's simulate group); with 16+ warps it measured no faster.
+template <int NT, bool MISSING, bool OSC, bool TC = false, bool WIDE = false>
 __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts& oc, int trial,
                                                float* __restrict__ xs, SimShared<NT>* sh, int mode,
                                                float scale, float shift, SimCache& cache,
@@ -244,15 +248,25 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
         auto advance4 = [&](const int j, const float (&z)[4], const float4 u4, const bool full, const uint32_t mbits) {
             const float u[4] = {u4.x, u4.y, u4.z, u4.w};
             float v[4];
+            // oscillation phase of the four samples: the first one reduced to [-0.5, 0.5] turns in fp64, the others
+            // by fp32 increments of freq * dt turns, each re-reduced by the 1.5 * 2^23 rounding trick (two FADDs on the
+            // FMA pipe; the per-sample fp64 fma / rint / conversions kept the XU pipe busy): <= 1.5e-7 turns off,
+            // below MUFU.SIN's own 5e-7
+            float turns0 = 0.f;
+            if (OSC) {
+                double t = fma(oc.fdt, (double)(j + 1), phase_turns);
+                t -= rint(t);
+                turns0 = (float)t;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 y = fmaf(-eps, y, y);
                 y = fmaf(s, z[i], y);
                 v[i] = y;
                 if (OSC) {
-                    double turns = fma(oc.fdt, (double)(j + i + 1), phase_turns);
-                    turns -= rint(turns);
-                    v[i] = fmaf(oc.so, __sinf(6.283185307179586f * (float)turns), oc.sc * y);   // turns in [-0.5, 0.5]: MUFU.SIN at its best (abs error 5e-7)
+                    float turns = fmaf((float)i, oc.fdt_f, turns0);
+                    turns -= (turns + 12582912.0f) - 12582912.0f;
+                    v[i] = fmaf(oc.so, __sinf(6.283185307179586f * turns), oc.sc * y);   // turns in [-0.5, 0.5]: MUFU.SIN at its best (abs error 5e-7)
                 }
             }
             if (full && !MISSING) {                      // common case: no per-sample predicates
@@ -281,6 +295,24 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
             }
         };
         int q = 0;
+        if (WIDE && !MISSING && !nz) {
+            for (; q + 16 <= g.chunk && j0 + q + 15 < g.n_t; q += 16) {
+                const int j = j0 + q;
+                uint32_t r[4][4];
+                float z[4][4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    philox4x32((uint32_t)(j >> 2) + (uint32_t)b, (uint32_t)trial, g.particle, g.c3_noise, *g.keys, r[b]);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    box_muller(r[b][0], r[b][1], z[b][0], z[b][1]);
+                    box_muller(r[b][2], r[b][3], z[b][2], z[b][3]);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    advance4(j + 4 * b, z[b], *reinterpret_cast<const float4*>(qt + q + 4 * b), true, 0u);
+            }
+        }
         if (!MISSING && !nz) {
             // interior of the trial, Philox noise: two counter blocks (eight samples) per iteration in one
             // basic block, so the two seven-round chains and their Box-Muller transforms interleave (four
