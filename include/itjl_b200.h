@@ -266,6 +266,39 @@ int64_t itjl_nextfastfft(int64_t n);
 int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double dt,
                          double f0, double df, int64_t n_freq, double* out);
 
+/* ---- PSD-side reducers: Lorentzian knee, oscillation peak, FOOOF-style loop ------------------------ */
+/* find_knee_frequency / fooof_fit / find_oscillation_peak / fit_gaussian of src/utils/utils.jl:479-538, 598-675,
+ * 721-765, 813-838 for every row of psd (n_rows x n_freq; col_major = 0: rows contiguous, as itjl_abc_distances'
+ * stats_out; 1: Julia (n_rows x n_freq) matrix), freqs ascending.  The reference's residuals make its
+ * Levenberg-Marquardt solve a least-ABSOLUTE-deviation fit; the library returns the argmin of mean |model - psd|
+ * reached from the reference's initial guess (deterministic Nelder-Mead, fp64), knee confined to (0, max(freqs)].
+ *   fooof = 0: [amp, knee] = find_knee_frequency(psd, freqs; min_freq, max_freq); peak_out (may be NULL) =
+ *              find_oscillation_peak(psd - lorentzian, freqs; min_freq, max_freq) (NaN: no peak) - the two numbers
+ *              distance_function of the PSD models needs (one_timescale.jl:311-316, one_timescale_and_osc.jl:377-384);
+ *   fooof = 1: fooof_fit(psd, freqs; min_freq, max_freq, oscillation_peak = true, max_peaks, return_only_knee = true):
+ *              frequencies outside [min_freq, max_freq] dropped, up to max_peaks Gaussians removed, knee refitted
+ *              (when no peak is found the first knee is returned; the reference throws UndefVarError there);
+ *   fooof = 2: as 0 with lorentzian_initial_guess (utils.jl:423-445) in place of the fit - what the informed prior of
+ *              the oscillation models uses (one_timescale_and_osc.jl:16-28);
+ *   fooof = 3: peak_out = find_oscillation_peak(psd, freqs; min_freq, max_freq) of the rows themselves (knee = NaN).
+ * Only the default constrained = false, allow_variable_exponent = false branch.  amp_out / peak_out may be NULL. */
+int itjl_fit_knee(itjl_ctx* ctx, const double* psd, int64_t n_rows, int64_t n_freq, int32_t col_major,
+                  const double* freqs, double min_freq, double max_freq, int32_t fooof, int32_t max_peaks,
+                  double* knee_out, double* amp_out, double* peak_out);
+
+/* The :knee branch of acw(data, fs; acwtypes = :knee, freqlims, average_over_trials, oscillation_peak, max_peaks)
+ * (src/core/acw.jl:242-270) in one call: spectrum of every slice on the device (comp_psd periodogram; with NaN in
+ * the data comp_psd_lombscargle on LombScargle.autofrequency(dt:dt:n_t*dt; maximum_frequency = fs/2)), optional
+ * mean over the slices, then itjl_fit_knee's fooof loop (flags bit 0 = oscillation_peak) or the plain knee.
+ * freq_lo / freq_hi: freqlims, NaN = (freqs[1], freqs[end]).  knee_out: n_out knee FREQUENCIES (tau =
+ * 1 / (2 pi knee)), n_out = 1 when flags bit 1 (average_over_trials) else n_slices.  psd_out: NULL or
+ * (n_out x *n_freq_out) column-major, capacity psd_capacity doubles; freqs_out: NULL or n_freq doubles
+ * (itjl_acw_knee_nfreq gives the size beforehand). */
+int itjl_acw_knee(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double freq_lo, double freq_hi,
+                  uint32_t flags, int32_t max_peaks, double* knee_out, double* psd_out, int64_t psd_capacity,
+                  double* freqs_out, int64_t* n_freq_out);
+int64_t itjl_acw_knee_nfreq(int64_t n_t, int32_t has_nan);
+
 /* ---- acw() ------------------------------------------------------------------------ */
 /* The ACF-based part of acw(data, fs; acwtypes, n_lags, average_over_trials)
  * (src/core/acw.jl:141-231) with the reducers of src/utils/utils.jl:113-138, 218-345.

@@ -103,6 +103,9 @@ SIGNATURES = {
     "itjl_psd_periodogram": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
     "itjl_nextfastfft": (_i64, [_i64]),
     "itjl_psd_lombscargle": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _f64, _f64, _i64, _vp]),
+    "itjl_fit_knee": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _vp]),
+    "itjl_acw_knee": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _f64, _f64, _u32, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "itjl_acw_knee_nfreq": (_i64, [_i64, _i32]),
 }
 
 

@@ -1,5 +1,6 @@
 """`acw(data, fs; ...)` on the GPU - mirror of src/core/acw.jl:109-307 for the ACF-based
-acwtypes (:acw0, :acw50, :acweuler, :auc, :tau).  `:knee` is outside the accelerated path.
+acwtypes (:acw0, :acw50, :acweuler, :auc, :tau) and for :knee (acw.jl:242-270: periodogram or Lomb-Scargle
+spectrum of every slice, then the FOOOF-style knee fit - itjl_acw_knee).
 """
 import ctypes
 import math
@@ -10,7 +11,7 @@ import numpy as np
 
 from . import _lib
 
-possible_acwtypes = ["acw0", "acw50", "acweuler", "auc", "tau"]
+possible_acwtypes = ["acw0", "acw50", "acweuler", "auc", "tau", "knee"]
 _BITS = {"acw0": _lib.ACW0, "acw50": _lib.ACW50, "acweuler": _lib.ACWEULER,
          "auc": _lib.AUC, "tau": _lib.TAU}
 
@@ -74,8 +75,48 @@ def upload(data, dims=None, ctx=None):
     return DeviceData(ctx, n_slices, n_t, other_shape, t_axis, was_vector)
 
 
+def _acw_knee(data, dims, fs, freqlims, average_over_trials, oscillation_peak, max_peaks, return_psd, ctx):
+    """The :knee branch (acw.jl:242-270) -> (tau per slice, psd, freqs, freqlims)."""
+    from .utils import tau_from_knee
+    d, n_slices, n_t, ss, ts, other_shape, t_axis, was_vector = _matrix_view(data, dims)
+    if not (ss == 1 and ts == n_slices):
+        # (slices x time) with the slice index fastest, as the library's spectrum kernels read it
+        d = np.asfortranarray(np.moveaxis(np.asarray(data, dtype=np.float64).reshape(
+            (1, -1) if was_vector else np.shape(data)), t_axis, -1).reshape((-1, n_t), order="F"))
+    if average_over_trials and len(other_shape) != 1:
+        raise NotImplementedError("average_over_trials is implemented for (trials, time) matrices")
+    has_nan = bool(np.isnan(d).any())
+    nb = int(_lib.lib().itjl_acw_knee_nfreq(n_t, int(has_nan)))
+    if nb < 3:
+        raise ValueError("acw(:knee): the time series is too short or too long for the spectrum kernels")
+    n_out = 1 if average_over_trials else n_slices
+    knee = np.empty(n_out, dtype=np.float64)
+    psd = np.empty((n_out, nb), dtype=np.float64, order="F") if return_psd else None
+    freqs = np.empty(nb, dtype=np.float64)
+    lo, hi = (float("nan"), float("nan")) if freqlims is None else (float(freqlims[0]), float(freqlims[1]))
+    nf = ctypes.c_int64(0)
+    flags = (1 if oscillation_peak else 0) | (2 if average_over_trials else 0)
+    ctx.check(_lib.lib().itjl_acw_knee(ctx.handle, _lib.ptr(d), n_slices, n_t, float(fs), lo, hi, flags, int(max_peaks),
+                                       _lib.ptr(knee), _lib.ptr(psd), 0 if psd is None else psd.size, _lib.ptr(freqs),
+                                       ctypes.byref(nf)))
+    if freqlims is None:
+        freqlims = (float(freqs[0]), float(freqs[-1]))                      # acw.jl:255-257
+    tau = tau_from_knee(knee)
+    if was_vector or n_out == 1:
+        tau_out = float(tau[0])
+    else:
+        tau_out = tau.reshape(other_shape, order="F")
+    if psd is not None:
+        if was_vector:
+            psd = psd[0]
+        elif n_out == n_slices:
+            psd = np.moveaxis(psd.reshape(other_shape + (nb,), order="F"), -1, t_axis)
+    return tau_out, psd, freqs, freqlims
+
+
 def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
-        average_over_trials=False, ctx=None):
+        average_over_trials=False, ctx=None, freqlims=None, return_psd=True, oscillation_peak=True, max_peaks=1,
+        allow_variable_exponent=False, constrained=False):
     """Compute ACW measures of every slice of `data` along its time dimension.
 
     `dims` is the time dimension in the reference's convention: 1-based, default = the last one
@@ -97,9 +138,22 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     if len(acwtypes) == 0:
         raise ValueError(f"No ACW types specified. Possible ACW types: {possible_acwtypes}")
     for t in acwtypes:
-        if t not in _BITS:
+        if t not in _BITS and t != "knee":
             raise ValueError(f"Possible ACW types: {possible_acwtypes}, got {t!r}")
+    if allow_variable_exponent or constrained:
+        raise NotImplementedError("only constrained = false, allow_variable_exponent = false is on the B200 path")
     resident = isinstance(data, DeviceData)
+    knee_out = None
+    if "knee" in acwtypes:
+        if resident:
+            raise NotImplementedError("acw(:knee) needs the host array (the spectrum kernels upload it themselves)")
+        knee_out = _acw_knee(data, dims, fs, freqlims, average_over_trials, oscillation_peak, max_peaks, return_psd,
+                             ctx or _lib.default_context())
+        if all(t == "knee" for t in acwtypes):
+            tau_k, psd, freqs, fl = knee_out
+            return ACWResults(float(fs), tau_k if (single or len(acwtypes) == 1) else [tau_k] * len(acwtypes),
+                              acwtypes[0] if single else acwtypes, None, fl, None, psd, freqs, None,
+                              None if psd is None else psd.ndim)
     if resident:
         ctx = data.ctx
         d, n_slices, n_t, ss, ts = None, data.n_slices, data.n_t, 1, data.n_slices
@@ -111,7 +165,7 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
         raise NotImplementedError("average_over_trials is implemented for (trials, time) matrices")
     mask = 0
     for t in acwtypes:
-        mask |= _BITS[t]
+        mask |= _BITS.get(t, 0)
     n_out = 1 if average_over_trials else n_slices
     k0 = np.empty(n_out, dtype=np.int32)
     k50 = np.empty(n_out, dtype=np.int32)
@@ -152,6 +206,9 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     res = {"acw0": as_lag(k0), "acw50": as_lag(k50), "acweuler": as_lag(ke), "auc": auc, "tau": tau}
     results = []
     for t in acwtypes:
+        if t == "knee":
+            results.append(knee_out[0])
+            continue
         v = res[t]
         if was_vector or n_out == 1:
             results.append(float(v[0]))
@@ -167,6 +224,7 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
             acf = np.moveaxis(acf.reshape(other_shape + (n_lags_used,), order="F"), -1, t_axis)
         lags = np.arange(n_lags_used, dtype=np.float64) * dt
     x_dim = None if acf is None else acf.ndim
+    psd, freqs, fl = (knee_out[1], knee_out[2], knee_out[3]) if knee_out is not None else (None, None, None)
     return ACWResults(float(fs), results[0] if len(results) == 1 else results,
-                      acwtypes[0] if single else acwtypes, n_lags_used, None, acf, None, None,
+                      acwtypes[0] if single else acwtypes, n_lags_used, fl, acf, psd, freqs,
                       lags, x_dim)

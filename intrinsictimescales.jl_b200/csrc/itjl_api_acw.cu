@@ -294,6 +294,183 @@ int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, in
     return ITJL_OK;
 }
 
+// knee fit of the rows in `rows_dev` (row-major, ld doubles apart) on columns [i0, i0 + n); results in ctx->stats as
+// three consecutive arrays of n_rows doubles: knee, amp, peak
+static int knee_fit_dev(itjl_ctx* ctx, const double* rows_dev, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs_dev,
+                        double min_freq, double max_freq, int mode, int max_peaks) {
+    const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->sm_count * 4);
+    ITJL_CUDA(ctx, ctx->part.reserve((size_t)grid * 3 * n * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->stats.reserve((size_t)n_rows * 3 * sizeof(double)));
+    double* k = (double*)ctx->stats.p;
+    cudaError_t e = knee_fit_launch(rows_dev, n_rows, ld, i0, n, freqs_dev, min_freq, max_freq, mode, max_peaks, k, k + n_rows,
+                                    k + 2 * n_rows, (double*)ctx->part.p, grid, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_knee_fit: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return ITJL_OK;
+}
+
+// fooof_fit's frequency mask as a column window (freqs ascending)
+static bool freq_window(const double* freqs, int64_t n_freq, double lo, double hi, int* i0, int* n) {
+    int64_t a = 0, b = n_freq;
+    while (a < n_freq && !(freqs[a] >= lo)) ++a;
+    while (b > a && !(freqs[b - 1] <= hi)) --b;
+    *i0 = (int)a; *n = (int)(b - a);
+    return b - a >= 3;
+}
+
+int itjl_fit_knee(itjl_ctx* ctx, const double* psd, int64_t n_rows, int64_t n_freq, int32_t col_major,
+                  const double* freqs, double min_freq, double max_freq, int32_t fooof, int32_t max_peaks,
+                  double* knee_out, double* amp_out, double* peak_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_fit_knee: null context");
+    if (!psd || !freqs || !knee_out || n_rows < 1 || n_freq < 3 || n_freq > (1 << 24) || max_peaks < 0)
+        return fail(ctx, ITJL_ERR_ARG, "itjl_fit_knee: invalid argument (need psd, freqs, knee_out, n_rows >= 1, 3 <= n_freq <= 2^24)");
+    for (int64_t i = 1; i < n_freq; ++i)
+        if (!(freqs[i] > freqs[i - 1])) return fail(ctx, ITJL_ERR_ARG, "itjl_fit_knee: freqs must be strictly ascending");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_fit_knee");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int i0 = 0, n = (int)n_freq;
+    if (fooof < 0 || fooof > 3) return fail(ctx, ITJL_ERR_ARG, "itjl_fit_knee: fooof must be 0 .. 3");
+    if (fooof == 1 && !freq_window(freqs, n_freq, min_freq, max_freq, &i0, &n))
+        return fail(ctx, ITJL_ERR_ARG, "itjl_fit_knee: fewer than three frequencies inside [min_freq, max_freq]");
+    const size_t bytes = (size_t)n_rows * n_freq * sizeof(double);
+    ITJL_CUDA(ctx, ctx->out2.reserve(bytes));
+    ITJL_CUDA(ctx, ctx->out3.reserve((size_t)n_freq * sizeof(double)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out3.p, freqs, (size_t)n_freq * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (col_major) {
+        ITJL_CUDA(ctx, ctx->out.reserve(bytes));
+        int rc = upload_bytes(ctx, ctx->out.p, psd, bytes);
+        if (rc != ITJL_OK) return rc;
+        cudaError_t e = transpose_launch((const double*)ctx->out.p, n_rows, n_freq, (double*)ctx->out2.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_transpose: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    } else {
+        int rc = upload_bytes(ctx, ctx->out2.p, psd, bytes);
+        if (rc != ITJL_OK) return rc;
+    }
+    int rc = knee_fit_dev(ctx, (const double*)ctx->out2.p, n_rows, n_freq, i0, n, (const double*)ctx->out3.p, min_freq, max_freq,
+                          fooof, max_peaks);
+    if (rc != ITJL_OK) return rc;
+    const double* k = (const double*)ctx->stats.p;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(knee_out, k, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (amp_out) ITJL_CUDA(ctx, cudaMemcpyAsync(amp_out, k + n_rows, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (peak_out) ITJL_CUDA(ctx, cudaMemcpyAsync(peak_out, k + 2 * n_rows, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
+// LombScargle.autofrequency(dt:dt:n_t*dt; maximum_frequency = 1 / (2 dt)): df = 1 / (5 (n_t - 1) dt), f0 = df / 2
+static void ls_grid(int64_t n_t, double dt, double* f0, double* df, int64_t* n_freq) {
+    *df = 1.0 / (5.0 * (double)(n_t - 1) * dt);
+    *f0 = 0.5 * *df;
+    *n_freq = (int64_t)floor((0.5 / dt - *f0) / *df + 1e-9) + 1;
+}
+
+int64_t itjl_acw_knee_nfreq(int64_t n_t, int32_t has_nan) {
+    if (n_t < 2 || n_t > 65536) return -1;
+    if (!has_nan) return next_fast_len((int)n_t) / 2;
+    double f0, df; int64_t n;
+    ls_grid(n_t, 1.0, &f0, &df, &n);
+    return n;
+}
+
+int itjl_acw_knee(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, double freq_lo, double freq_hi,
+                  uint32_t flags, int32_t max_peaks, double* knee_out, double* psd_out, int64_t psd_capacity,
+                  double* freqs_out, int64_t* n_freq_out) {
+    int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_acw_knee");
+    if (rc != ITJL_OK) return rc;
+    if (!knee_out || !(fs > 0.0) || max_peaks < 0 || n_t > 65536) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_knee: invalid argument (fs > 0, n_t <= 65536)");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_acw_knee");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    bool has_nan = false;
+    for (int64_t i = 0, m = n_slices * n_t; i < m; ++i) if (data[i] != data[i]) { has_nan = true; break; }
+    const double dt = 1.0 / fs;
+    rc = upload_data(ctx, data, n_slices, n_t);
+    if (rc != ITJL_OK) return rc;
+    int64_t nb = 0;
+    std::vector<double> freqs;
+    if (!has_nan) {
+        FftPlan plan;
+        const int nfft = next_fast_len((int)n_t);
+        if (!fft_plan_make(nfft, &plan)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_knee: n_t too large");
+        nb = nfft / 2;
+        std::vector<double> win((size_t)n_t);
+        std::vector<double2> roots((size_t)nfft);
+        double win_ss = 0.0;
+        pgram_make_tables((int)n_t, nfft, nullptr, win.data(), nullptr, roots.data(), &win_ss);
+        const int grid = (int)std::min<int64_t>((n_slices + 1) / 2, (int64_t)ctx->sm_count * 4);
+        ITJL_CUDA(ctx, ctx->scratch.reserve(win.size() * sizeof(double)));
+        ITJL_CUDA(ctx, ctx->raw.reserve(roots.size() * sizeof(double2)));
+        ITJL_CUDA(ctx, ctx->out2.reserve((size_t)grid * 2 * nfft * sizeof(double2)));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, roots.data(), roots.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * nb * sizeof(double)));
+        cudaError_t e = pgram_data_launch((const double*)ctx->data.p, n_slices, (int)n_t, plan, (const double*)ctx->scratch.p,
+                                          (const double2*)ctx->raw.p, 1.0 / (fs * win_ss), (double2*)ctx->out2.p, grid,
+                                          (double*)ctx->out.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pgram_data: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // win / roots are block-local
+        freqs.resize((size_t)nb);
+        for (int64_t k = 0; k < nb; ++k) freqs[(size_t)k] = (double)(k + 1) * fs / (double)nfft;
+    } else {
+        if (n_slices > 65535) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_knee: more than 65535 slices with missing samples");
+        double f0, df;
+        ls_grid(n_t, dt, &f0, &df, &nb);
+        ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * nb * sizeof(double)));
+        cudaError_t e = lomb_scargle_launch((const double*)ctx->data.p, n_slices, (int)n_t, dt, f0, df, (int)nb, (double*)ctx->out.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_lomb_scargle: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        freqs.resize((size_t)nb);
+        for (int64_t k = 0; k < nb; ++k) freqs[(size_t)k] = f0 + df * (double)k;
+    }
+    if (n_freq_out) *n_freq_out = nb;
+    // average_over_trials: one mean spectrum
+    const bool average = (flags & 2u) != 0;
+    int64_t n_out = n_slices;
+    const double* spec = (const double*)ctx->out.p;                  // (n_out x nb) column-major
+    if (average) {
+        ITJL_CUDA(ctx, ctx->gather.reserve((size_t)nb * sizeof(double)));
+        cudaError_t e = col_mean_launch(spec, n_slices, nb, (double*)ctx->gather.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_col_mean: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        spec = (const double*)ctx->gather.p; n_out = 1;
+    }
+    if (psd_out) {
+        if (psd_capacity < n_out * nb) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_knee: psd_out too small");
+        rc = download_large(ctx, psd_out, spec, (size_t)n_out * nb * sizeof(double));
+        if (rc != ITJL_OK) return rc;
+    }
+    if (freqs_out) memcpy(freqs_out, freqs.data(), (size_t)nb * sizeof(double));
+    // freqlims default (freqs[1], freqs[end]) (acw.jl:255-257)
+    const double lo = freq_lo == freq_lo ? freq_lo : freqs.front(), hi = freq_hi == freq_hi ? freq_hi : freqs.back();
+    int i0 = 0, n = 0;
+    if (!freq_window(freqs.data(), nb, lo, hi, &i0, &n)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_knee: fewer than three frequencies inside freqlims");
+    // rows contiguous for the fit
+    ITJL_CUDA(ctx, ctx->out2.reserve((size_t)n_out * nb * sizeof(double)));
+    if (n_out > 1) {
+        cudaError_t e = transpose_launch(spec, n_out, nb, (double*)ctx->out2.p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_transpose: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    } else {
+        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out2.p, spec, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ITJL_CUDA(ctx, ctx->out3.reserve((size_t)nb * sizeof(double)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out3.p, freqs.data(), (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // fooof_fit always masks to [lo, hi]; oscillation_peak = false stops after the first Lorentzian (utils.jl:622-624)
+    rc = knee_fit_dev(ctx, (const double*)ctx->out2.p, n_out, nb, i0, n, (const double*)ctx->out3.p, lo, hi, (flags & 1u) ? 1 : 0,
+                      (flags & 1u) ? max_peaks : 0);
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(knee_out, ctx->stats.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // freqs stays alive until here
+    return ITJL_OK;
+}
+
 int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt, double* tau_out) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_fit_expdecay: null context");
     if (!acf || !tau_out || n_rows < 1 || n_lags < 1 || !(dt > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_fit_expdecay: invalid argument");

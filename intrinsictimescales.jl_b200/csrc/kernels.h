@@ -121,6 +121,13 @@ cudaError_t pgram_data_launch(const double* data, int64_t n_slices, int n_t, con
 cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq,
                                 double* out, cudaStream_t st);
 
+// ---- knee_kernels.cu -----------------------------------------------------------------
+cudaError_t knee_fit_launch(const double* rows, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs, double min_freq,
+                            double max_freq, int mode, int max_peaks, double* knee_out, double* amp_out, double* peak_out,
+                            double* work, int grid, cudaStream_t st);
+cudaError_t transpose_launch(const double* in, int64_t n_rows, int64_t n_cols, double* out, cudaStream_t st);
+cudaError_t col_mean_launch(const double* in, int64_t n_rows, int64_t n_cols, double* out, cudaStream_t st);
+
 // ---- ou_kernels.cu -------------------------------------------------------------------
 struct OuGenParams {
     int n_t, n_trials, chunk;

@@ -81,7 +81,8 @@ class TimescaleModel:
     dims: int = 2
     distance_combined: bool = False
     weights: Any = None            # [w_stats, w_tau] of combined_distance (one_timescale.jl:278-290)
-    data_tau: Any = None           # fit_expdecay(lags, data_sum_stats) when distance_combined
+    data_tau: Any = None           # fit_expdecay(lags, data_sum_stats) / tau_from_knee(...) when distance_combined
+    data_osc: Any = None           # oscillation peak of the data spectrum (oscillation models, PSD, distance_combined)
     missing_mask: Any = None
     update: str = "exact"
     _gpu: dict = field(default_factory=dict, repr=False)
@@ -184,15 +185,31 @@ class GpuModel:
         return (out, stats) if return_stats else out
 
     def _combine(self, d_stats, stats):
-        """combined_distance (one_timescale.jl:278-290): w1 * distance(stats) + w2 * (data_tau - tau_sim)^2,
-        tau_sim = fit_expdecay(lags, simulated mean ACF) fitted on the device for the whole batch."""
+        """combined_distance: w1 * distance(stats) + w2 * (data_tau - tau_sim)^2 [+ w3 * (data_osc - osc_sim)^2].
+        ACF (one_timescale.jl:278-290, :311-313): tau_sim = fit_expdecay(lags, simulated mean ACF); PSD
+        (one_timescale.jl:314-316, one_timescale_and_osc.jl:377-384): tau_sim = tau_from_knee(knee) of the Lorentzian
+        fit, osc_sim = find_oscillation_peak of its residual within freqlims - both fitted on the device for the
+        whole batch (itjl_fit_expdecay / itjl_fit_knee)."""
         from . import utils
         m = self.model
         ok = np.isfinite(stats).all(axis=1)
         tau = np.full(stats.shape[0], np.nan)
+        osc = np.full(stats.shape[0], np.nan)
         if ok.any():
-            tau[ok] = np.atleast_1d(utils.fit_expdecay(m.lags_freqs, stats[ok], ctx=self.ctx))
-        return m.weights[0] * d_stats + m.weights[1] * (m.data_tau - tau) ** 2
+            if m.summary_method == "acf":
+                tau[ok] = np.atleast_1d(utils.fit_expdecay(m.lags_freqs, stats[ok], ctx=self.ctx))
+            elif m.kind.startswith("one_timescale_and_osc"):
+                # the knee is fitted with find_knee_frequency's defaults; the peak search window [freqlims] contains every
+                # selected frequency (freq_idx is freqlims' open interval), i.e. it is the whole axis
+                fit, peak = utils.find_knee_frequency(stats[ok], m.lags_freqs, ctx=self.ctx, return_peak=True)
+                tau[ok] = utils.tau_from_knee(fit[:, 1])
+                osc[ok] = peak
+            else:
+                tau[ok] = utils.tau_from_knee(utils.find_knee_frequency(stats[ok], m.lags_freqs, ctx=self.ctx)[:, 1])
+        d = m.weights[0] * d_stats + m.weights[1] * (m.data_tau - tau) ** 2
+        if m.summary_method == "psd" and m.kind.startswith("one_timescale_and_osc"):
+            d = d + m.weights[2] * (m.data_osc - osc) ** 2
+        return d
 
     def generation(self, theta, epsilon, min_accepted, seed=0, generation=0, particle_offset=0):
         """Distances + accept mask + sequential stop for a batch (abc.jl:181-199)."""
@@ -363,33 +380,64 @@ def one_timescale_with_missing_model(data, time, fit_method="abc", summary_metho
     return _combined(m, distance_combined, weights, data_tau, ctx)
 
 
+def _osc_informed_prior(stats, lags_freqs, summary_method, ctx):
+    """informed_prior of the oscillation models (one_timescale_and_osc.jl:16-43): lorentzian_initial_guess (no fit)
+    of the statistic - also for the ACF, as the reference does -, oscillation peak of the residual over the whole
+    axis; PSD: Normal(1 / knee, 1), ACF: Normal(fit_expdecay, 20)."""
+    amp, knee = utils.lorentzian_initial_guess(stats, lags_freqs, ctx=ctx)
+    resid = np.asarray(stats, dtype=np.float64) - utils.lorentzian(lags_freqs, [amp, knee])
+    osc_peak = utils.find_oscillation_peak(resid, lags_freqs, lags_freqs[0], lags_freqs[-1], ctx=ctx)
+    if summary_method == "psd":
+        return [Normal(1.0 / knee, 1.0), Normal(osc_peak, 0.1), Uniform(0.0, 1.0)]
+    return [Normal(utils.fit_expdecay(lags_freqs, stats, ctx=ctx), 20.0), Normal(osc_peak, 0.1), Uniform(0.0, 1.0)]
+
+
 def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="psd", prior=None,
                                 n_lags=None, distance_method=None, freqlims=None,
-                                distance_combined=False, update="exact"):
-    if distance_combined:
-        raise NotImplementedError("distance_combined of the oscillation models needs the oscillation-peak "
-                                  "search (outside the B200 hot path)")
+                                distance_combined=False, weights=None, data_tau=None, data_osc=None,
+                                update="exact", ctx=None):
     data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
-    if prior is None:
-        raise NotImplementedError("the informed prior of the oscillation model needs the Lorentzian "
-                                  "knee fit (outside the B200 hot path): pass prior=[...] explicitly")
     dt = float(time[1] - time[0]); T = float(time[-1])
     mean, sd = float(data.mean()), float(data.std(ddof=1))
+    w = [0.5, 0.5] if weights is None else [float(x) for x in weights]
     if summary_method == "acf":
         acf_mean = summary.comp_ac_fft(data).mean(axis=0)
-        n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
-        return TimescaleModel("one_timescale_and_osc", data, time, fit_method, "acf", lags, prior,
-                              distance_method or "linear", stats, dt, T, data.shape[0], mean, sd,
-                              n_lags=n_lags, update=update)
-    psd, freqs = summary.comp_psd_adfriendly(data, 1.0 / dt)
+        n_lags, lags, stats, _ = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior if prior is not None else [None])
+        if prior is None:
+            prior = _osc_informed_prior(stats, lags, "acf", ctx)
+        m = TimescaleModel("one_timescale_and_osc", data, time, fit_method, "acf", lags, prior,
+                           distance_method or "linear", stats, dt, T, data.shape[0], mean, sd,
+                           n_lags=n_lags, update=update)
+        if len(w) != 2 and distance_combined:
+            raise ValueError("weights must have length 2 for the ACF summary")
+        return _combined(m, distance_combined, w, data_tau, ctx)
+    psd, freqs = summary.comp_psd_adfriendly(data, 1.0 / dt, ctx=ctx)
     mean_psd = psd.mean(axis=0)
     if freqlims is None:
         freqlims = (0.5, 100.0)
     freq_idx = (freqs < freqlims[1]) & (freqs > freqlims[0])
-    return TimescaleModel("one_timescale_and_osc", data, time, fit_method, "psd", freqs[freq_idx], prior,
-                          distance_method or "logarithmic", np.ascontiguousarray(mean_psd[freq_idx]),
-                          dt, T, data.shape[0], mean, sd, freqlims=freqlims, freq_idx=freq_idx,
-                          update=update)
+    lags_freqs = freqs[freq_idx]
+    stats = np.ascontiguousarray(mean_psd[freq_idx])
+    if prior is None:
+        prior = _osc_informed_prior(stats, lags_freqs, "psd", ctx)
+    m = TimescaleModel("one_timescale_and_osc", data, time, fit_method, "psd", lags_freqs, prior,
+                       distance_method or "logarithmic", stats, dt, T, data.shape[0], mean, sd,
+                       freqlims=freqlims, freq_idx=freq_idx, update=update)
+    if distance_combined:
+        # one_timescale_and_osc.jl:229-236; the PSD combination has three terms (:337-343)
+        if len(w) == 2:
+            raise ValueError("weights must have length 3 for the PSD summary of the oscillation model "
+                             "(the reference's default [0.5, 0.5] throws a BoundsError at weights[3])")
+        if len(w) != 3:
+            raise ValueError("weights must have length 3 for the PSD summary")
+        (amp, knee), _ = utils.find_knee_frequency(stats, lags_freqs, ctx=ctx, return_peak=True)
+        resid = stats - utils.lorentzian(lags_freqs, [amp, knee])
+        m.distance_combined = True
+        m.weights = w
+        m.data_tau = float(data_tau) if data_tau is not None else float(utils.tau_from_knee(knee))
+        m.data_osc = float(data_osc) if data_osc is not None else float(
+            utils.find_oscillation_peak(resid, lags_freqs, freqlims[0], freqlims[1], ctx=ctx))
+    return m
 
 
 def one_timescale_and_osc_with_missing_model(data, time, fit_method="abc", summary_method="acf", prior=None,
@@ -402,13 +450,14 @@ def one_timescale_and_osc_with_missing_model(data, time, fit_method="abc", summa
     data, time, prior = check_model_inputs(data, time, fit_method, summary_method, prior, distance_method)
     if summary_method != "acf":
         raise NotImplementedError("the Lomb-Scargle PSD branch is outside the B200 hot path")
-    if prior is None:
-        raise NotImplementedError("the informed prior of the oscillation model needs the Lorentzian "
-                                  "knee fit (outside the B200 hot path): pass prior=[...] explicitly")
     dt = float(time[1] - time[0]); T = float(time[-1])
     mask = np.isnan(data)
     acf_mean = summary.comp_ac_time_missing(data).mean(axis=0)
-    n_lags, lags, stats, prior = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior)
+    n_lags, lags, stats, _ = _acf_branch(acf_mean, data.shape[1], dt, n_lags, prior if prior is not None else [None])
+    if prior is None:
+        # informed_prior, ACF branch (one_timescale_and_osc_with_missing.jl:36-48): the oscillation prior is the fixed
+        # Normal(0.01, 0.05) there - the peak it computes is not used
+        prior = [Normal(utils.fit_expdecay(lags, stats), 20.0), Normal(0.01, 0.05), Uniform(0.0, 1.0)]
     return TimescaleModel("one_timescale_and_osc_with_missing", data, time, fit_method, "acf", lags, prior,
                           distance_method or "linear", stats, dt, T, data.shape[0],
                           float(np.nanmean(data)), float(np.nanstd(data, ddof=1)), n_lags=n_lags,

@@ -72,6 +72,7 @@ class Model:
     distance_combined: bool = False
     weights: list = None
     data_tau: float = None
+    data_osc: float = None
     n_t: int = field(default=None)
 
     def __post_init__(self):
@@ -106,12 +107,35 @@ def _acf_setup(acf_mean, n, dt, n_lags):
     return n_lags, lags, acf_mean[:n_lags]
 
 
-def with_combined_distance(model, weights=(0.5, 0.5), data_tau=None):
-    """distance_combined = true (one_timescale.jl:166-169): data_tau = fit_expdecay(lags, data_sum_stats)."""
+def with_combined_distance(model, weights=(0.5, 0.5), data_tau=None, data_osc=None):
+    """distance_combined = true.  ACF (one_timescale.jl:166-169): data_tau = fit_expdecay(lags, data_sum_stats); PSD of
+    one_timescale_model (:195-198): data_tau = tau_from_knee(find_knee_frequency(...)[2]); PSD of the oscillation model
+    (one_timescale_and_osc.jl:229-236): that and data_osc = find_oscillation_peak of the Lorentzian's residual within
+    freqlims, three weights."""
+    from . import knee
     model.distance_combined = True
     model.weights = [float(w) for w in weights]
-    model.data_tau = float(data_tau) if data_tau is not None else acwred.fit_expdecay(model.lags_freqs, model.data_sum_stats)
+    if model.summary_method == "acf":
+        model.data_tau = float(data_tau) if data_tau is not None else acwred.fit_expdecay(model.lags_freqs, model.data_sum_stats)
+        return model
+    u = knee.find_knee_frequency(model.data_sum_stats, model.lags_freqs)
+    model.data_tau = float(data_tau) if data_tau is not None else float(knee.tau_from_knee(u[1]))
+    if model.kind.startswith("one_timescale_and_osc"):
+        resid = model.data_sum_stats - knee.lorentzian(model.lags_freqs, u)
+        model.data_osc = float(data_osc) if data_osc is not None else knee.find_oscillation_peak(
+            resid, model.lags_freqs, model.freqlims[0], model.freqlims[1])
     return model
+
+
+def osc_informed_prior(stats, lags_freqs, summary_method):
+    """informed_prior of the oscillation models (one_timescale_and_osc.jl:16-43)."""
+    from . import knee
+    u0 = knee.lorentzian_initial_guess(stats, lags_freqs)
+    resid = np.asarray(stats) - knee.lorentzian(lags_freqs, u0)
+    peak = knee.find_oscillation_peak(resid, lags_freqs, lags_freqs[0], lags_freqs[-1])
+    if summary_method == "psd":
+        return [Normal(1.0 / u0[1], 1.0), Normal(peak, 0.1), Uniform(0.0, 1.0)]
+    return [Normal(acwred.fit_expdecay(lags_freqs, stats), 20.0), Normal(peak, 0.1), Uniform(0.0, 1.0)]
 
 
 def one_timescale_model(data, time, fit_method="abc", summary_method="acf", prior=None,
@@ -165,13 +189,13 @@ def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="ps
                                 freqlims=None, update="exact"):
     """one_timescale_and_osc.jl:98-189."""
     data, time, prior = _check_inputs(data, time, prior)
-    if prior is None:
-        raise NotImplementedError("informed prior needs the Lorentzian fit (out of scope)")
     dt = float(time[1] - time[0]); T = float(time[-1])
     mean, sd = float(data.mean()), float(data.std(ddof=1))
     if summary_method == "acf":
         acf_mean = summary.comp_ac_fft(data).mean(axis=0)
         n_lags, lags, stats = _acf_setup(acf_mean, data.shape[1], dt, n_lags)
+        if prior is None:
+            prior = osc_informed_prior(stats, lags, "acf")
         return Model("one_timescale_and_osc", data, time, "acf",
                      distance_method or "linear", prior, lags, stats, dt, T,
                      data.shape[0], mean, sd, n_lags=n_lags, update=update)
@@ -180,6 +204,8 @@ def one_timescale_and_osc_model(data, time, fit_method="abc", summary_method="ps
     if freqlims is None:
         freqlims = (0.5, 100.0)
     freq_idx = (freqs < freqlims[1]) & (freqs > freqlims[0])
+    if prior is None:
+        prior = osc_informed_prior(mean_psd[freq_idx], freqs[freq_idx], "psd")
     return Model("one_timescale_and_osc", data, time, "psd",
                  distance_method or "logarithmic", prior, freqs[freq_idx],
                  mean_psd[freq_idx], dt, T, data.shape[0], mean, sd,
@@ -248,13 +274,22 @@ def summary_stats(model, data):
 
 def distance_function(model, sum_stats, data_sum_stats):
     if model.distance_combined:
-        # one_timescale.jl:306-320 + combined_distance :278-290 (ACF branch)
+        # one_timescale.jl:306-320 + combined_distance :278-290; one_timescale_and_osc.jl:368-385 + :324-347
+        from . import knee
         d1 = (distances.linear_distance(sum_stats, data_sum_stats) if model.distance_method == "linear"
               else distances.logarithmic_distance(sum_stats, data_sum_stats))
         if not np.all(np.isfinite(sum_stats)):
             return float("nan")
-        tau_sim = acwred.fit_expdecay(model.lags_freqs, sum_stats)
-        return model.weights[0] * d1 + model.weights[1] * distances.linear_distance(model.data_tau, tau_sim)
+        if model.summary_method == "acf":
+            tau_sim = acwred.fit_expdecay(model.lags_freqs, sum_stats)
+            return model.weights[0] * d1 + model.weights[1] * distances.linear_distance(model.data_tau, tau_sim)
+        u = knee.find_knee_frequency(sum_stats, model.lags_freqs)
+        d = model.weights[0] * d1 + model.weights[1] * distances.linear_distance(model.data_tau, float(knee.tau_from_knee(u[1])))
+        if model.kind.startswith("one_timescale_and_osc"):
+            resid = np.asarray(sum_stats) - knee.lorentzian(model.lags_freqs, u)
+            osc = knee.find_oscillation_peak(resid, model.lags_freqs, model.freqlims[0], model.freqlims[1])
+            d += model.weights[2] * distances.linear_distance(model.data_osc, osc)
+        return d
     if model.distance_method == "linear":
         return distances.linear_distance(sum_stats, data_sum_stats)
     if model.distance_method == "logarithmic":

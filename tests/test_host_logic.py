@@ -112,7 +112,7 @@ def test_acw_and_model_argument_errors(pkg):
     with pytest.raises(ValueError):
         pkg.acw(np.zeros((2, 10)), 1.0, acwtypes=[])
     with pytest.raises(ValueError):
-        pkg.acw(np.zeros((2, 10)), 1.0, acwtypes=["knee"])
+        pkg.acw(np.zeros((2, 10)), 1.0, acwtypes=["acw25"])                 # not one of possible_acwtypes
     t = np.arange(1, 11.0)
     with pytest.raises(ValueError, match="Time vector length"):
         pkg.check_model_inputs(np.zeros((2, 9)), t, "abc", "acf", None, None)
