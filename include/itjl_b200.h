@@ -234,6 +234,13 @@ int itjl_generate_ou_osc(itjl_ctx* ctx, double tau, double freq, double coeff, d
                          uint64_t seed, const double* u0, const double* noise, const double* phases,
                          double* out);
 
+/* Models.generate_data(::TwoTimescaleModel, [tau1, tau2, coeff])  (src/models/two_timescale.jl:30-51, the
+ * generator of the reference's unfinished two-timescale model): sqrt(data_var) * (sqrt(coeff) * ou1 + sqrt(1 - coeff)
+ * * ou2) with ou_i = generate_ou_process(tau_i, 1 / tau_i, dt, duration, num_trials).  out: (n_trials x n_t)
+ * column-major. */
+int itjl_generate_ou_two(itjl_ctx* ctx, double tau1, double tau2, double coeff, double dt, int64_t n_t, int64_t n_trials,
+                         double data_var, int32_t update, uint64_t seed, double* out);
+
 /* ---- summary statistics on stored data -------------------------------------------- */
 /* comp_ac_fft(data; dims = 2, n_lags)  (src/stats/summary.jl:46-63, 79-89) computed as the
  * mathematically identical time-domain lag sum.  out: (n_slices x n_lags) column-major. */

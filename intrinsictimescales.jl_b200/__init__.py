@@ -18,7 +18,7 @@ from .models import (Normal, Uniform, TimescaleModel, check_model_inputs, distan
                      draw_theta, generate_data, generate_data_and_reduce, one_timescale_and_osc_model,
                      one_timescale_and_osc_with_missing_model,
                      one_timescale_model, one_timescale_with_missing_model, summary_stats)
-from .ou import generate_ou_process, generate_ou_with_oscillation
+from .ou import generate_ou_process, generate_ou_with_oscillation, generate_two_timescale
 from .summary import comp_ac_fft, comp_ac_time_missing, comp_psd_adfriendly
 from .utils import acw0, acw50, acweuler, expdecay, fit_expdecay, tau_from_acw50
 

@@ -685,7 +685,8 @@ int itjl_abc_accept(itjl_ctx* ctx, const double* dist, int64_t n, double epsilon
 // ---- OU generator ----------------------------------------------------------------------
 static int generate_common(itjl_ctx* ctx, int kind, double tau, double freq, double coeff, double dt,
                            int64_t n_t, int64_t n_trials, int mode, double scale, double shift, int32_t update,
-                           uint64_t seed, const double* u0, const double* noise, const double* phases, double* out) {
+                           uint64_t seed, const double* u0, const double* noise, const double* phases, double* out,
+                           uint32_t particle = 0) {
     if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "null context");
     ITJL_LOCK(ctx);
     ctx = primary(ctx);
@@ -704,7 +705,7 @@ static int generate_common(itjl_ctx* ctx, int kind, double tau, double freq, dou
     P.tau = tau; P.freq = freq; P.coeff = coeff; P.dt = dt;
     P.update = update; P.kind = kind; P.mode = mode; P.scale = (float)scale; P.shift = (float)shift;
     P.keys = philox_keys(seed);
-    P.c3_noise = philox_c3(kStreamNoise, 0); P.c3_init = philox_c3(kStreamInit, 0); P.particle = 0;
+    P.c3_noise = philox_c3(kStreamNoise, 0); P.c3_init = philox_c3(kStreamInit, 0); P.particle = particle;
     int rc = ITJL_OK;
     if (u0) { rc = upload(ctx, ctx->u0, u0, (size_t)n_trials * sizeof(double)); P.u0 = (const double*)ctx->u0.p; }
     if (rc == ITJL_OK && noise) { rc = upload(ctx, ctx->noise, noise, (size_t)n_trials * n_t * sizeof(double)); P.noise = (const double*)ctx->noise.p; }
@@ -737,6 +738,25 @@ int itjl_generate_ou_osc(itjl_ctx* ctx, double tau, double freq, double coeff, d
                          const double* u0, const double* noise, const double* phases, double* out) {
     return generate_common(ctx, ITJL_KIND_OU_OSC, tau, freq, coeff, dt, n_t, n_trials, 1, data_sd, data_mean,
                            update, seed, u0, noise, phases, out);
+}
+
+int itjl_generate_ou_two(itjl_ctx* ctx, double tau1, double tau2, double coeff, double dt, int64_t n_t, int64_t n_trials,
+                         double data_var, int32_t update, uint64_t seed, double* out) {
+    // Models.generate_data(::TwoTimescaleModel, theta) (src/models/two_timescale.jl:30-51): two standardised OU
+    // processes with D_i = 1 / tau_i, mixed sqrt(coeff) : sqrt(1 - coeff), scaled by sqrt(data_var).  The two
+    // processes use the Philox streams of particles 0 and 1; the mix itself is one pass over the result.
+    if (!ctx || !out) return fail(ctx, ITJL_ERR_ARG, "itjl_generate_ou_two: null argument");
+    if (!(coeff >= 0.0 && coeff <= 1.0) || !(data_var >= 0.0) || n_t < 4 || n_trials < 1)
+        return fail(ctx, ITJL_ERR_ARG, "itjl_generate_ou_two: need 0 <= coeff <= 1, data_var >= 0, n_t >= 4, n_trials >= 1");
+    ITJL_LOCK(ctx);
+    std::vector<double> second((size_t)n_trials * n_t);
+    int rc = generate_common(ctx, ITJL_KIND_OU, tau1, 0.0, 1.0, dt, n_t, n_trials, 1, 1.0 / tau1, 0.0, update, seed, nullptr, nullptr, nullptr, out, 0);
+    if (rc == ITJL_OK)
+        rc = generate_common(ctx, ITJL_KIND_OU, tau2, 0.0, 1.0, dt, n_t, n_trials, 1, 1.0 / tau2, 0.0, update, seed, nullptr, nullptr, nullptr, second.data(), 1);
+    if (rc != ITJL_OK) return rc;
+    const double a = sqrt(coeff) * sqrt(data_var), b = sqrt(1.0 - coeff) * sqrt(data_var);
+    for (size_t i = 0; i < second.size(); ++i) out[i] = a * out[i] + b * second[i];
+    return ITJL_OK;
 }
 
 // ---- measurement -----------------------------------------------------------------------

@@ -61,3 +61,15 @@ def generate_ou_with_oscillation(theta, dt, duration, num_trials, data_mean, dat
                                               int(seed), _lib.ptr(u0), _lib.ptr(noise),
                                               _lib.ptr(phases), _lib.ptr(out)))
     return out
+
+
+def generate_two_timescale(theta, dt, duration, num_trials, data_var=1.0, seed=0, update="exact", ctx=None):
+    """Models.generate_data(::TwoTimescaleModel, theta = [tau1, tau2, coeff]) (src/models/two_timescale.jl:30-51):
+    sqrt(data_var) * (sqrt(coeff) * ou1 + sqrt(1 - coeff) * ou2), ou_i = generate_ou_process(tau_i, 1 / tau_i, ...)."""
+    ctx = ctx or _lib.default_context()
+    n_t = n_time_points(dt, duration)
+    num_trials = int(num_trials)
+    out = np.empty((num_trials, n_t), dtype=np.float64, order="F")
+    ctx.check(_lib.lib().itjl_generate_ou_two(ctx.handle, float(theta[0]), float(theta[1]), float(theta[2]), float(dt), n_t,
+                                              num_trials, float(data_var), _UPDATE[update], int(seed), _lib.ptr(out)))
+    return out

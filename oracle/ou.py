@@ -127,3 +127,13 @@ def generate_ou_with_oscillation(theta, dt, duration, num_trials, data_mean, dat
     if not np.all(np.isfinite(out)):
         out = np.full((num_trials, n_t), np.nan)
     return out
+
+
+def generate_two_timescale(theta, dt, duration, num_trials, data_var=1.0, seed=0, update="exact", n_t=None):
+    """Models.generate_data(::TwoTimescaleModel, theta) (src/models/two_timescale.jl:30-51): the reference's unfinished
+    two-timescale model only has this generator.  ou_i = generate_ou_process(tau_i, 1 / tau_i, ...) (standardised, times
+    D_i = 1 / tau_i), mixed sqrt(coeff) : sqrt(1 - coeff), times sqrt(data_var).  Streams: particles 0 and 1 of `seed`."""
+    tau1, tau2, coeff = theta
+    o1 = generate_ou_process(tau1, 1.0 / tau1, dt, duration, num_trials, seed=seed, particle=0, update=update, n_t=n_t)
+    o2 = generate_ou_process(tau2, 1.0 / tau2, dt, duration, num_trials, seed=seed, particle=1, update=update, n_t=n_t)
+    return np.sqrt(data_var) * (np.sqrt(coeff) * o1 + np.sqrt(1.0 - coeff) * o2)

@@ -164,6 +164,15 @@ def test_acw_nd_input_and_dims(pkg, ctx):
     moved = np.moveaxis(base, -1, 1)                                               # (3, time, 4)
     rm = pkg.acw(moved, 100.0, acwtypes=types, dims=2, ctx=ctx)
     assert r3.n_lags == flat.n_lags == rm.n_lags
+    # ... and against the oracle, slice by slice in the reference's order
+    want = oacw.acw(base.reshape(12, n_t), 100.0, acwtypes=types)
+    assert r3.n_lags == want["n_lags"]
+    for name, key in [("acw0", "k0"), ("acw50", "k50"), ("acweuler", "ke")]:
+        w = np.where(want[key] >= 0, want[key] * (1.0 / 100.0), np.nan).reshape(3, 4)
+        assert np.array_equal(r3.acw_results[types.index(name)], w, equal_nan=True)
+        assert np.array_equal(rm.acw_results[types.index(name)], w, equal_nan=True)
+    assert np.max(np.abs(r3.acf.reshape(12, -1) - want["acf"])) < 1e-5
+    assert np.allclose(r3.acw_results[3].reshape(-1), want["tau"], rtol=1e-5)
     for k in range(len(types)):
         want = np.asarray(flat.acw_results[k]).reshape(3, 4)
         assert r3.acw_results[k].shape == (3, 4) and rm.acw_results[k].shape == (3, 4)

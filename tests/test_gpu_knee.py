@@ -41,8 +41,9 @@ def test_find_knee_frequency_batch(pkg, ctx, noise):
         # ... and it is the same point (an L1 objective is kinked: compared to 1e-6 relative, 1e-4 with heavy noise)
         tol = 1e-6 if noise < 0.2 else 1e-4
         assert abs(got[r, 1] - want[1]) <= tol * want[1] and abs(got[r, 0] - want[0]) <= tol * want[0], (r, got[r], want)
-        wp = oknee.find_oscillation_peak(P[r] - oknee.lorentzian(f, want), f, f[0], f[-1])
-        assert (np.isnan(wp) and np.isnan(peaks[r])) or peaks[r] == wp
+        if noise > 0 or r % 2:              # (the residual of an exact fit to a pure Lorentzian is rounding noise: no peak to compare)
+            wp = oknee.find_oscillation_peak(P[r] - oknee.lorentzian(f, want), f, f[0], f[-1])
+            assert (np.isnan(wp) and np.isnan(peaks[r])) or peaks[r] == wp
     one = pkg.utils.find_knee_frequency(P[3], f, ctx=ctx)
     assert one[1] == got[3, 1]
     g = pkg.utils.lorentzian_initial_guess(P, f, ctx=ctx)

@@ -119,3 +119,17 @@ def test_summary_argument_errors(pkg, ctx):
         pkg.comp_ac_fft(np.zeros((2, 100)), 101, ctx=ctx)
     with pytest.raises(pkg.ItjlError):
         pkg.comp_psd_adfriendly(np.zeros((2, 100)), -1.0, ctx=ctx)
+
+
+def test_two_timescale_generator(pkg, ctx):
+    """generate_data of the reference's TwoTimescaleModel (src/models/two_timescale.jl:30-51)."""
+    theta, dt, n_t, n_trials = [0.02, 0.4, 0.3], 0.002, 4000, 5
+    want = oou.generate_two_timescale(theta, dt, n_t * dt, n_trials, data_var=2.5, seed=9, n_t=n_t)
+    got = pkg.generate_two_timescale(theta, dt, n_t * dt, n_trials, data_var=2.5, seed=9, ctx=ctx)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-5 * np.abs(want).max()
+    # each component is standardised before mixing: var = data_var * (coeff / tau1^2 + (1 - coeff) / tau2^2) up to the
+    # sample cross-correlation of the two independent processes
+    v = 2.5 * (0.3 / 0.02 ** 2 + 0.7 / 0.4 ** 2)
+    assert abs(got.var(axis=1, ddof=1).mean() / v - 1.0) < 0.1
+    with pytest.raises(pkg.ItjlError):
+        pkg.generate_two_timescale([0.02, 0.4, 1.3], dt, n_t * dt, n_trials, ctx=ctx)
