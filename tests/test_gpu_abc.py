@@ -139,7 +139,7 @@ def test_oscillation_model(pkg, ctx, summary_method):
         # log-distance of PSDs: per-bin relative error ~1e-5 (fp32 FFT), d = mean(log-ratio^2)
         assert np.all(np.abs(got - want) <= dist_tol(want, 3e-5) * 2), (got, want)
     else:
-        assert np.all(np.abs(got - want) <= dist_tol(want, 2e-5)), (got, want)
+        assert np.all(np.abs(got - want) <= dist_tol(want)), (got, want)
 
 
 def test_accept_and_sequential_stop(pkg, ctx):
@@ -269,9 +269,9 @@ def test_oscillation_with_missing_model(pkg, ctx):
             g = gm.gpu_model(ctx)
         assert g.kernel_info()[0] == ("k_abc_acf_tc" if tc == 1 else "k_abc_acf")
         d, stats = g.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
-        assert np.max(np.abs(stats - want)) <= 2e-5, (tc, np.max(np.abs(stats - want)))
+        assert np.max(np.abs(stats - want)) <= ACF_TOL, (tc, np.max(np.abs(stats - want)))
         d_ref = np.mean((want - om.data_sum_stats) ** 2, axis=1)
-        assert np.all(np.abs(d - d_ref) <= dist_tol(d_ref, 2e-5))
+        assert np.all(np.abs(d - d_ref) <= dist_tol(d_ref))
 
 
 def test_distance_combined_acf_branch(pkg, ctx):
@@ -328,8 +328,8 @@ def test_oscillation_with_missing_model_many_long_trials(pkg, ctx):
     theta = np.array([[0.05, 10.0, 0.9], [0.1, 12.0, 0.5], [0.02, 8.0, 0.3], [0.2, 11.0, 0.7]])
     want, s_want = cport.abc_distances(om, theta, seed=4, generation=2, return_stats=True)
     got, s_got = gm.gpu_model(ctx).distances(theta, seed=4, generation=2, return_stats=True)
-    assert np.max(np.abs(s_got - s_want)) <= 2e-5, np.max(np.abs(s_got - s_want))
-    assert np.all(np.abs(got - want) <= dist_tol(want, 2e-5))
+    assert np.max(np.abs(s_got - s_want)) <= ACF_TOL, np.max(np.abs(s_got - s_want))
+    assert np.all(np.abs(got - want) <= dist_tol(want))
 
 
 def test_psd_model_with_more_selected_bins_than_fit_in_shared_memory(pkg, ctx):

@@ -61,10 +61,10 @@ def test_generate_ou_with_oscillation(pkg, ctx, coeff):
                                             phases=ph, n_t=n_t)
     got = pkg.generate_ou_with_oscillation(th, dt, n_t * dt, n_trials, 0.7, 2.5, u0=u0, noise=noise,
                                            phases=ph, ctx=ctx)
-    assert np.max(np.abs(got - want)) <= 2e-5 * np.abs(want).max()
+    assert np.max(np.abs(got - want)) <= 1e-5 * np.abs(want).max()
     want2 = oou.generate_ou_with_oscillation(th, dt, n_t * dt, n_trials, 0.7, 2.5, seed=9, n_t=n_t)
     got2 = pkg.generate_ou_with_oscillation(th, dt, n_t * dt, n_trials, 0.7, 2.5, seed=9, ctx=ctx)
-    assert np.max(np.abs(got2 - want2)) <= 2e-5 * np.abs(want2).max()
+    assert np.max(np.abs(got2 - want2)) <= 1e-5 * np.abs(want2).max()
 
 
 # --------------------------------------------------------------- summary stats ----

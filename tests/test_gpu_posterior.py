@@ -73,3 +73,17 @@ def test_posterior_predictive_statistics(pkg, ctx):
     # same numbers as scoring the same draws directly
     _, stats = model.gpu_model(ctx).distances(pp["theta_samples"], seed=5, generation=0, return_stats=True)
     assert np.array_equal(stats, pp["predictions"])
+    # against the oracle: the reference's loop (generate_data -> summary_stats per draw, IntPlottingExt.jl:114-124) on the
+    # same draws and Philox streams, for the ACF model and for the periodogram (PSD) model
+    from oracle import models as omodels
+    for summary_method in ("acf", "psd"):
+        om = omodels.one_timescale_model(data, t, summary_method=summary_method, prior=[omodels.Uniform(0.05, 5.0)])
+        gm = pkg.one_timescale_model(data, t, "abc", summary_method=summary_method, prior=[pkg.Uniform(0.05, 5.0)])
+        pq = pkg.posterior_predictive(post, gm, n_samples=16, rng=np.random.default_rng(3), seed=8, ctx=ctx)
+        want = np.stack([omodels.summary_stats(om, omodels.generate_data(om, th, seed=8, generation=0, particle=i))
+                         for i, th in enumerate(pq["theta_samples"])])
+        scale = 1.0 if summary_method == "acf" else want.max()
+        assert np.max(np.abs(pq["predictions"] - want)) <= 1e-5 * scale
+        assert np.max(np.abs(pq["pred_mean"] - want.mean(axis=0))) <= 1e-5 * scale
+        assert np.max(np.abs(pq["pred_lower"] - np.quantile(want, 0.025, axis=0))) <= 1e-5 * scale
+        assert np.max(np.abs(pq["pred_upper"] - np.quantile(want, 0.975, axis=0))) <= 1e-5 * scale

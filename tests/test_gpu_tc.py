@@ -287,8 +287,8 @@ def test_tc_kernel_oscillation_acf_variant(pkg, ctx):
     d_ff, s_ff = g_ff.distances(theta, u0=u0, noise=noise, phases=phases, return_stats=True)
     for i in range(3):
         ac = omodels.summary_stats(om, omodels.generate_data(om, theta[i], u0=u0[i], noise=noise[i], phases=phases[i]))
-        assert np.max(np.abs(s_tc[i] - ac)) <= 2e-5        # same tolerance as test_gpu_abc's oscillation ACF case
-    assert np.max(np.abs(s_tc - s_ff)) <= 2e-5
+        assert np.max(np.abs(s_tc[i] - ac)) <= 1e-5
+    assert np.max(np.abs(s_tc - s_ff)) <= 1e-5
 
 
 def e_shared(n_trials):
