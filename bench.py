@@ -275,6 +275,35 @@ def sub_c2(pkg, ctx, torch, stream, hbm_peak, hbm_src, cpu):
     return rec
 
 
+def sub_knee(pkg, ctx, cpu):
+    """f3: acw(data, fs; acwtypes = :knee) - periodogram of every slice + FOOOF-style knee fit, 2000 x 5000."""
+    fs, n = 100.0, 2000
+    d = np.asfortranarray(ou_rows(np.random.default_rng(8), n, 5000, 0.3, 1.0 / fs))
+    pkg.acw(d[:64], fs, acwtypes="knee", ctx=ctx)
+    n0 = ctx.launch_count
+    t0 = time.perf_counter()
+    r = pkg.acw(d, fs, acwtypes="knee", ctx=ctx)
+    s = time.perf_counter() - t0
+    tau = np.asarray(r.acw_results)
+    rec = {"metric": "acw_knee_slices_per_sec", "unit": "slices/s", "value": n / s,
+           "config": {"workload": "acw(OU tau = 0.3 s, 2000 x 5000, fs = 100; acwtypes = :knee, oscillation_peak = true, max_peaks = 1)",
+                      "n_freq": int(r.freqs.size), "median_tau": float(np.median(tau)), "kernels": "k_pgram_data + k_transpose + k_knee_fit",
+                      "launches": int(ctx.launch_count - n0)},
+           "e2e": {"value": n / s, "unit": "slices/s", "ms_per_call": 1e3 * s, "h2d_bytes_per_step": int(d.nbytes),
+                   "d2h_bytes_per_step": int(8 * n + 8 * n * r.freqs.size)},
+           "roofline": None}
+    if cpu:
+        from oracle import knee as oknee, summary as osum
+        t0 = time.perf_counter()
+        psd, fr = osum.comp_psd_periodogram(d[:3], fs)
+        for p_ in psd:
+            oknee.fooof_fit(p_, fr, fr[0], fr[-1], True, 1, True)
+        s1 = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 3 / s1, "unit": "slices/s", "cores": 1, "kind": "port",
+                               "sample": f"3 slices, NumPy / SciPy oracle (pocketfft periodogram + Nelder-Mead L1 fits), {s1:.1f} s"}
+    return rec
+
+
 def time_model(pkg, ctx, torch, stream, gm, theta, seed):
     """(resident ms per launch from CUDA events on the context stream, e2e seconds per call with host buffers)."""
     P, p = theta.shape
@@ -307,17 +336,32 @@ def sub_model(pkg, ctx, torch, stream, name, model, om_fn, theta, fp32_peak, ten
     if kname == "k_abc_acf_tc":
         roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "peak_source": tensor_src, "flops_per_sample": flops,
-                "executed_tensor_flops_per_sample": tflops_exec, "traffic": None}
+                "executed_tensor_flops_per_sample": tflops_exec, "traffic": None,
+                "traffic_note": "compute bound: theta in, one distance out per particle; the trajectories stay in shared memory"}
     else:
         roof = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp32_peak, "peak_source": "itjl_fp32_peak microbenchmark of this run",
-                "flops_per_sample": flops, "traffic": ncu_traffic("r02_k_abc_psd_ncu_summary.txt") if kname == "k_abc_psd" else None}
+                "flops_per_sample": flops,
+                # per launch of the profiled run (profiles/README.md names its particle count), parsed from the committed summary
+                "traffic": ncu_traffic({"k_abc_psd2": "r02_k_abc_psd2_ncu_summary.txt", "k_abc_psd": "r01_k_abc_psd_v5_ncu_summary.txt",
+                                        "k_abc_pgram": "r02_k_abc_pgram_ncu_summary.txt"}.get(kname, "none")),
+                "traffic_note": "compute bound (simulate + FFT in shared memory); DRAM traffic = theta, the bin table and the window"}
     rec = {"metric": METRIC, "unit": UNIT, "value": samples / (ms * 1e-3), "ms_per_launch": ms,
            "config": {"workload": name, "particles_per_launch": P, "n_trials": int(model.numTrials), "n_t": int(model.n_t),
                       "n_stats": int(gm.n_stats)},
            "roofline": roof,
            "e2e": {"value": samples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(theta.nbytes), "d2h_bytes_per_step": int(8 * P)}}
-    if cpu:
+    if cpu and kname == "k_abc_pgram":
+        # the C port has no mixed-radix periodogram: NumPy oracle (pocketfft), one thread, two particles
+        from oracle import models as omodels
+        om = om_fn()
+        t0 = time.perf_counter()
+        for i in range(2):
+            omodels.generate_data_and_reduce(om, theta[i], seed=seed, generation=1, particle=i)
+        s1 = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 2 * spp / s1, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"2 particles of the same model, NumPy oracle (exact OU transition + pocketfft periodogram), {s1:.1f} s"}
+    elif cpu:
         from oracle import cport
         om = om_fn()
         cores = cport.max_threads()
@@ -585,6 +629,19 @@ def run_gpu(args):
         th4 = np.stack([np.abs(r4.normal(.1, .1, 2000)) + 0.005, r4.normal(10, 5, 2000), r4.uniform(0, 1, 2000)], axis=1)
         sub["c4_osc_psd"] = sub_model(pkg, ctx, torch, stream, "C4 one_timescale_and_osc_model, PSD summary, 100 trials x 10000",
                                       m4, om4, th4, fp32_peak, tensor_peak, tensor_src, want_cpu)
+        # f1: one_timescale_model(summary_method = :psd), DSP periodogram (nfft = 5000), 20 trials x 5000
+        d1, t1 = observed_c3()
+        d1 = np.nan_to_num(d1[:20])                                  # complete data (the C3 gaps filled with zeros)
+        mp = pkg.one_timescale_model(d1, t1, "abc", summary_method="psd", prior=[pkg.Uniform(0.0, 5.0)])
+
+        def omp():
+            from oracle import models as omodels
+            return omodels.one_timescale_model(d1, t1, summary_method="psd", prior=[omodels.Uniform(0.0, 5.0)])
+        sub["f1_psd_periodogram"] = sub_model(pkg, ctx, torch, stream,
+                                              "one_timescale_model(:psd): DSP periodogram summary, 20 trials x 5000, nfft = 5000",
+                                              mp, omp, np.random.default_rng(6).uniform(0.05, 5.0, size=(20000, 1)), fp32_peak,
+                                              tensor_peak, tensor_src, want_cpu)
+        sub["f3_acw_knee"] = sub_knee(pkg, ctx, want_cpu)
     if sweep is not None:
         sub = sub or {}
         sub["c5_sweep"] = sweep

@@ -765,8 +765,6 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
     ITJL_LOCK(ctx);
     ctx = primary(ctx);
     ITJL_LOCK(ctx);
-    int micro = 0;                                   // tuning: negative iters select a microbenchmark
-    if (iters < 0) { micro = -iters; iters = 5; }
     if (iters < 1) iters = 1;
     ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8;
@@ -779,8 +777,7 @@ int itjl_fp32_peak(itjl_ctx* ctx, int32_t iters, double* tflops_out) {
     double best = 0.0;
     for (int i = 0; i < iters; ++i) {
         ITJL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        e = micro ? fp32_micro_launch((float*)ctx->scratch.p, blocks, inner, micro, ctx->stream)
-                  : fp32_peak_launch((float*)ctx->scratch.p, blocks, inner, ctx->stream);
+        e = fp32_peak_launch((float*)ctx->scratch.p, blocks, inner, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_fp32_peak: %s", cudaGetErrorString(e));
         ctx->launches++;
         ITJL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

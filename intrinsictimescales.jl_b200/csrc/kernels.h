@@ -258,6 +258,5 @@ cudaError_t wcov_launch(const double* x, const double* w, int64_t n, int p, int 
 // ---- peak_kernels.cu -----------------------------------------------------------------
 cudaError_t fp32_peak_launch(float* sink, int blocks, int iters, cudaStream_t st);
 double fp32_peak_flops_per_launch(int blocks, int iters);
-cudaError_t fp32_micro_launch(float* sink, int blocks, int iters, int mode, cudaStream_t st);
 
 }  // namespace itjl
