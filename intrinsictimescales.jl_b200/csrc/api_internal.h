@@ -23,7 +23,7 @@ struct itjl_model {
     int psd_round0_bins = 0;
     // DSP-convention periodogram (ITJL_SUMMARY_PGRAM)
     itjl::FftPlan pg_plan{};
-    int pg_chunk = 0;
+    int pg_chunk = 0, pg_bufb = 0;
     size_t pg_smem = 0;
     // multi-GPU parent model: one model per device of the parent context (itjl_api_multi.cu)
     std::vector<itjl_model*> subs;

@@ -292,7 +292,7 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         if (d.n_t > 65536 || !fft_plan_make(nfft, &m->pg_plan)) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "periodogram: n_t too large"); }
         for (int64_t i = 0; i < d.n_stats; ++i)
             if (d.freq_bins[i] < 0 || d.freq_bins[i] >= nfft / 2) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
-        m->pg_smem = abc_pgram_smem_bytes((int)d.n_t, nfft, (int)d.n_stats, &m->pg_chunk);
+        m->pg_smem = abc_pgram_smem_bytes((int)d.n_t, nfft, (int)d.n_stats, &m->pg_chunk, &m->pg_bufb);
         if ((int64_t)m->pg_smem > ctx->max_smem_optin || m->pg_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "periodogram FFT does not fit in shared memory (n_t too large)"); }
         std::vector<float> win((size_t)d.n_t);
         std::vector<float2> roots((size_t)roots_two_level_entries(nfft));
@@ -444,7 +444,7 @@ int itjl::launch_distances(itjl_model* m, const double* theta_dev, int64_t n_par
         AbcPgramParams P{};
         P.theta = theta_dev; P.n_particles = n_particles; P.theta_ld = theta_ld > 0 ? theta_ld : n_particles; P.n_theta = n_theta;
         P.n_t = (int)d.n_t; P.n_trials = (int)d.n_trials; P.n_stats = (int)d.n_stats;
-        P.chunk = m->pg_chunk; P.plan = m->pg_plan;
+        P.chunk = m->pg_chunk; P.bufb_len = m->pg_bufb; P.plan = m->pg_plan;
         P.dt = d.dt; P.data_mean = d.data_mean; P.data_sd = d.data_sd;
         P.update = d.update; P.kind = d.kind; P.distance = d.distance;
         P.keys = philox_keys(seed);

@@ -94,6 +94,7 @@ struct AbcPgramParams {
     int n_theta;
     int n_t, n_trials, n_stats;
     int chunk;                  // simulate chunk (samples per thread)
+    int bufb_len;               // float2 entries of the second transform buffer (it also holds the simulated trial)
     FftPlan plan;               // nfft = nextfastfft(n_t) and its radices
     double dt, data_mean, data_sd;
     int update, kind, distance;
@@ -111,7 +112,7 @@ struct AbcPgramParams {
     double* dist_out;
     double* stats_out;
 };
-size_t abc_pgram_smem_bytes(int n_t, int nfft, int n_stats, int* chunk_out);
+size_t abc_pgram_smem_bytes(int n_t, int nfft, int n_stats, int* chunk_out, int* bufb_len_out);
 void pgram_make_tables(int n_t, int nfft, float* window_f, double* window_d, float2* roots2_f, double2* roots_d, double* win_ss);
 cudaError_t abc_pgram_launch(const AbcPgramParams& P, bool osc, size_t smem, cudaStream_t st);
 // stored data (n_slices x n_t col-major double), fp64: all nfft/2 bins of every slice; scratch = grid * 2 * nfft double2

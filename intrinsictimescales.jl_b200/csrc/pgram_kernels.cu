@@ -14,6 +14,7 @@
 //                      global scratch area that stays in L2), all nfft / 2 bins out.
 //   k_lomb_scargle   : generalised Lomb-Scargle periodogram of stored data with NaN gaps (summary.jl:254-356)
 #include <math.h>
+#include <algorithm>
 
 #include "fft_mixed.cuh"
 #include "kernels.h"
@@ -23,14 +24,16 @@ namespace itjl {
 
 constexpr int kPgramThreads = 512;
 
+// Two CTAs per SM (the trial buffer lives in the second transform buffer, which is idle while a trial is simulated):
+// one CTA's simulate phase runs under the other's transform.
 template <bool OSC>
-__global__ void __launch_bounds__(kPgramThreads, 1) k_abc_pgram(const __grid_constant__ AbcPgramParams P) {
+__global__ void __launch_bounds__(kPgramThreads, 2) k_abc_pgram(const __grid_constant__ AbcPgramParams P) {
     constexpr int NT = kPgramThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* xs = reinterpret_cast<float*>(smem_raw);                          // chunk * NT floats: one simulated trial
-    Cx<float>* bufa = reinterpret_cast<Cx<float>*>(xs + P.chunk * NT);        // nfft complex points
-    Cx<float>* bufb = bufa + P.plan.n;
-    float* accb = reinterpret_cast<float*>(bufb + P.plan.n);                 // n_stats bin sums (padded to 4)
+    Cx<float>* bufa = reinterpret_cast<Cx<float>*>(smem_raw);                // nfft complex points
+    Cx<float>* bufb = bufa + ((P.plan.n + 1) & ~1);                          // second transform buffer, 16-byte aligned (bufb_len entries) ...
+    float* xs = reinterpret_cast<float*>(bufb);                              // ... = chunk * NT floats: one simulated trial
+    float* accb = reinterpret_cast<float*>(bufb + P.bufb_len);               // n_stats bin sums (padded to 4)
     SimShared<NT>* sh = reinterpret_cast<SimShared<NT>*>(accb + ((P.n_stats + 3) & ~3));
     Cx<float>* rtab = reinterpret_cast<Cx<float>*>(sh + 1);                  // two-level roots of unity
     __shared__ double red[NT / 32];
@@ -115,11 +118,14 @@ __global__ void __launch_bounds__(kPgramThreads, 1) k_abc_pgram(const __grid_con
     }
 }
 
-size_t abc_pgram_smem_bytes(int n_t, int nfft, int n_stats, int* chunk_out) {
+size_t abc_pgram_smem_bytes(int n_t, int nfft, int n_stats, int* chunk_out, int* bufb_len_out) {
     int c = (n_t + kPgramThreads - 1) / kPgramThreads;
     c = (c + 3) & ~3;
     *chunk_out = c;
-    return (size_t)c * kPgramThreads * sizeof(float) + (size_t)2 * nfft * sizeof(float2) +
+    // the second buffer also holds the simulated trial: max(nfft float2, chunk * NT floats)
+    const int bufb = (std::max(nfft, (c * kPgramThreads + 1) / 2) + 1) & ~1;
+    *bufb_len_out = bufb;
+    return (size_t)(((nfft + 1) & ~1) + bufb) * sizeof(float2) +
            (size_t)((n_stats + 3) & ~3) * sizeof(float) + sizeof(SimShared<kPgramThreads>) +
            (size_t)roots_two_level_entries(nfft) * sizeof(float2);
 }
