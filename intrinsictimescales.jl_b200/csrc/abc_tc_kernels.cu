@@ -297,6 +297,44 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                     tc::mbar_wait_warp(&bar_acc_empty, (seg_it & 1u) ^ 1u);   // previous segment drained
                     tc::fence_after_thread_sync();
                     const int seg1 = min(seg0 + P.seg_trials, P.n_trials);
+#ifdef ITJL_V_HOIST
+                    // this warp's ops and the per-group trial counters, kept in registers across the segment: the
+                    // issue loop is 8 % of the kernel's instructions when it re-derives them per MMA
+                    uint32_t my_a[2], my_b[2], my_t[2], my_i[2];
+                    int n_my = 0;
+                    for (int o = e_warp; o < P.n_ops && n_my < 2; o += 4, ++n_my) {
+                        my_a[n_my] = P.op_a_off[o]; my_b[n_my] = P.op_b_off[o];
+                        my_t[n_my] = tmem_base + P.op_taddr[o]; my_i[n_my] = P.op_idesc[o];
+                    }
+                    int g = seg0 % G;
+                    uint32_t kq = (uint32_t)(seg0 / G);
+                    for (int trial = seg0; trial < seg1; ++trial) {
+                        const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
+                        const uint32_t k = it * n_g + kq;
+                        const uint32_t buf = k & 1u;
+                        tc::mbar_wait_warp(&bar_full[g][buf], (k >> 1) & 1u);
+                        tc::fence_after_thread_sync();
+                        const uint32_t hi_addr = opnd_addr + (uint32_t)((g * 2 + (int)buf) * 2 * op_bytes);
+                        const uint64_t d_hi = tc::make_smem_desc(hi_addr, 128u, (uint32_t)P.sbo_bytes);
+                        const uint64_t d_lo = tc::make_smem_desc(hi_addr + (uint32_t)op_bytes, 128u, (uint32_t)P.sbo_bytes);
+                        const int n_ks = (P.debug & 1) ? 0 : P.ksteps;
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            const uint32_t first = (trial == seg0 && ks == 0) ? 0u : 1u;
+#pragma unroll
+                            for (int m = 0; m < 2; ++m) {
+                                if (m < n_my) {
+                                    const uint64_t a_off = (uint64_t)(ks * 16 + my_a[m]);
+                                    const uint64_t b_off = (uint64_t)(ks * 16 + my_b[m]);
+                                    tc::mma_f16_ss_elect(my_t[m], d_hi + a_off, d_hi + b_off, my_i[m], first);
+                                    if (P.n_terms >= 2) tc::mma_f16_ss_elect(my_t[m], d_hi + a_off, d_lo + b_off, my_i[m], 1u);
+                                    if (P.n_terms == 3) tc::mma_f16_ss_elect(my_t[m], d_lo + a_off, d_hi + b_off, my_i[m], 1u);
+                                }
+                            }
+                        }
+                        tc::mma_commit_elect(&bar_empty[g][buf]); // this warp's reads of the buffer have retired
+                        if (++g == G) { g = 0; ++kq; }
+                    }
+#else
                     for (int trial = seg0; trial < seg1; ++trial) {
                         const int g = trial % G;
                         const uint32_t n_g = (uint32_t)((P.n_trials - g + G - 1) / G);
@@ -322,6 +360,7 @@ __global__ void __launch_bounds__(kTcMaxThreads, 1) k_abc_acf_tc(const __grid_co
                         }
                         tc::mma_commit_elect(&bar_empty[g][buf]); // this warp's reads of the buffer have retired
                     }
+#endif
                     tc::mma_commit_elect(&bar_acc_full);          // this warp's accumulators of the segment complete
                 }
                 __syncwarp();

@@ -242,7 +242,11 @@ __device__ __forceinline__ void simulate_trial(const SimArgs& g, const OuConsts&
     const double* nz = g.noise ? g.noise + (size_t)trial * g.n_t : nullptr;
     const uint32_t* mrow = MISSING ? g.mask_bits + (size_t)trial * g.mask_words : nullptr;
     const float* qt = sh->qtab;
+#ifdef ITJL_V_SIMSLEEP
+    if (TC) { while (!tc::mbar_try_wait(sink->wait_bar, sink->wait_parity)) __nanosleep(ITJL_V_SIMSLEEP); }
+#else
     if (TC) tc::mbar_wait(sink->wait_bar, sink->wait_parity);
+#endif
     if (j0 < g.n_t) {
         // recurrence + partial sums + store of the four samples j .. j+3 driven by z[0..3]; u = q of these samples
         auto advance4 = [&](const int j, const float (&z)[4], const float4 u4, const bool full, const uint32_t mbits) {

@@ -50,7 +50,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 // warp does not take issue slots from the simulate warps of its scheduler (a test_wait poll loop
 // measured 6 % of all issued instructions).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#ifdef ITJL_V_EPISLEEP
+    while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) __nanosleep(ITJL_V_EPISLEEP);
+#else
     while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) { }
+#endif
 }
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)

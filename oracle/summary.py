@@ -96,7 +96,8 @@ def comp_psd_adfriendly_vec(x, fs, demean=True):
     scale = 1.0 / (fs * np.sum(w ** 2))
     xf = np.fft.fft(xp)
     psd = np.abs(xf[:n2 // 2]) ** 2 * scale
-    freqs = np.fft.fftfreq(n2, 1.0 / fs)[:n2 // 2]
+    # AbstractFFTs.fftfreq(n2, fs)[1 : n2 / 2] = (0 : n2 / 2 - 1) * (fs / n2)
+    freqs = np.arange(n2 // 2, dtype=np.float64) * (fs / n2)
     return psd[1:], freqs[1:]
 
 
@@ -138,7 +139,8 @@ def comp_psd_periodogram_vec(x, fs):
         p[1:-1] *= 2.0
     else:
         p[1:] *= 2.0
-    freqs = np.fft.rfftfreq(nfft, 1.0 / fs)
+    # AbstractFFTs.rfftfreq(nfft, fs) = (0 : nfft / 2) * (fs / nfft): the multiplier is formed first
+    freqs = np.arange(nfft // 2 + 1, dtype=np.float64) * (fs / nfft)
     return p[1:], freqs[1:]
 
 
