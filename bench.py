@@ -388,7 +388,8 @@ def run_sweep(pkg, ctx, model, gm, P, seed, barrier, n_gen=3):
         if g == 1:
             theta = rng.uniform(*PRIOR, size=(P, 1))
         else:
-            theta = pkg.draw_theta_pmc(model, theta_prev, w_prev, tau_sq, rng, P)
+            # PMC proposals on the device (itjl_pmc_propose): every rank draws the same matrix from the Philox stream
+            theta = pkg.draw_theta_pmc_device(theta_prev, w_prev, tau_sq, P, seed=seed, generation=g, ctx=ctx)
         t1 = time.perf_counter()
         d, isacc, n_total, n_acc = gm.generation(theta, eps, P + 1, seed=seed, generation=g)
         t2 = time.perf_counter()
@@ -543,8 +544,9 @@ def run_gpu(args):
                  "host_ms_total": sum(g["propose_host_ms"] + g["accept_epsilon_host_ms"] for g in gens),
                  "score_ms_total": sum(g["score_ms"] for g in gens),
                  "weights_cov_ms_total": sum(g["weights_cov_ms"] for g in gens),
-                 "note": "wall clock of the whole host-driven loop (max over ranks); proposals, epsilon quantiles and the accept "
-                         "compaction run on the host of every rank, scoring and weights are sharded over the GPUs"}
+                 "note": "wall clock of the whole host-driven loop (max over ranks); PMC proposals are drawn on the device "
+                         "(k_pmc_propose, every rank the same matrix), epsilon quantiles and the accept compaction run on the host "
+                         "of every rank, scoring and weights are sharded over the GPUs"}
 
     samples_per_step = P * samples_per_particle
     value = args.steps * samples_per_step / (ms * 1e-3)

@@ -186,6 +186,15 @@ int itjl_abc_distances_dev(itjl_model* model, const double* theta_dev, int64_t n
 int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, const double* theta, int64_t n,
                      int32_t n_theta, const double* tau_squared, const double* weights_prev,
                      const double* prior_pdf, int32_t normalize, double* weights_out);
+/* n i.i.d. draws of draw_theta_pmc(model, theta_prev, weights, tau_squared; jitter)  (src/core/abc.jl:101-117):
+ * theta* resampled from theta_prev (n_prev x n_theta, column-major) with probabilities weights_prev, then
+ * MvNormal(theta*, tau_squared + jitter I), redrawn around the same theta* while any component is negative.
+ * Philox stream (seed, generation, first + i): proposal i does not depend on n or on the number of GPUs (every
+ * rank of a communicator draws the same matrix).  theta_out: (n x n_theta) column-major.  StatsBase's and
+ * Distributions' own streams are not reproduced - the draws are i.i.d. from the same distribution. */
+int itjl_pmc_propose(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, int32_t n_theta, const double* weights_prev,
+                     const double* tau_squared, double jitter, int64_t n, uint64_t seed, uint64_t generation,
+                     int64_t first, double* theta_out);
 /* weighted_covar(x, w)  (src/core/abc.jl:582-613): x (n x n_theta) column-major, cov_out (n_theta x n_theta). */
 int itjl_weighted_covar(itjl_ctx* ctx, const double* x, int64_t n, int32_t n_theta, const double* w, double* cov_out);
 

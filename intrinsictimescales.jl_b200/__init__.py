@@ -11,7 +11,7 @@ there is no CPU fallback.
 from . import _lib
 from ._lib import Context, ItjlError, default_context, library_path
 from .abc import (ABCResults, abc_results, basic_abc, calc_weights, compute_adaptive_alpha,
-                  draw_theta_pmc, effective_sample_size, find_MAP, get_param_dict_abc, int_fit,
+                  draw_theta_pmc, draw_theta_pmc_device, effective_sample_size, find_MAP, get_param_dict_abc, int_fit,
                   pmc_abc, posterior_predictive, select_epsilon, weighted_covar)
 from .acw import ACWResults, DeviceData, acw, possible_acwtypes, upload
 from .models import (Normal, Uniform, TimescaleModel, check_model_inputs, distance_function,

@@ -192,4 +192,44 @@ int itjl_weighted_covar(itjl_ctx* ctx, const double* x, int64_t n, int32_t n_the
     return ITJL_OK;
 }
 
+
+int itjl_pmc_propose(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, int32_t n_theta, const double* weights_prev,
+                     const double* tau_squared, double jitter, int64_t n, uint64_t seed, uint64_t generation,
+                     int64_t first, double* theta_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_pmc_propose: null context");
+    if (!theta_prev || !weights_prev || !tau_squared || !theta_out) return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_propose: null argument");
+    if (n < 1 || n_prev < 1 || n_theta < 1 || n_theta > 4 || !(jitter >= 0.0) || first < 0)
+        return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_propose: need n, n_prev >= 1, 1 <= n_theta <= 4, jitter >= 0, first >= 0");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);                                  // every rank / device draws the same proposals: nothing to shard
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_pmc_propose");
+    const int p = n_theta;
+    double cov[16], L[16];
+    for (int i = 0; i < p * p; ++i) cov[i] = tau_squared[i];
+    for (int d = 0; d < p; ++d) cov[d + d * p] += jitter;                     // abc.jl:106-108
+    if (!cholesky(cov, p, L)) return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_propose: tau_squared + jitter I is not positive definite");
+    std::vector<double> cdf((size_t)n_prev);
+    double run = 0.0;
+    for (int64_t j = 0; j < n_prev; ++j) {
+        if (!(weights_prev[j] >= 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_propose: weights must be non-negative and finite");
+        run += weights_prev[j];
+        cdf[(size_t)j] = run;
+    }
+    if (!(run > 0.0) || !isfinite(run)) return fail(ctx, ITJL_ERR_ARG, "itjl_pmc_propose: weights sum to zero");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    ITJL_CUDA(ctx, ctx->raw.reserve((size_t)n_prev * p * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->scratch.reserve((size_t)n_prev * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->theta.reserve((size_t)n * p * sizeof(double)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, theta_prev, (size_t)n_prev * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, cdf.data(), (size_t)n_prev * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = pmc_propose_launch((const double*)ctx->raw.p, (const double*)ctx->scratch.p, n_prev, p, L, n, seed, generation, first,
+                                       (double*)ctx->theta.p, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_propose: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(theta_out, ctx->theta.p, (size_t)n * p * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));              // cdf stays alive until here
+    return ITJL_OK;
+}
+
 }  // extern "C"

@@ -253,6 +253,8 @@ cudaError_t pmc_mixture_launch(bool fp32, const void* z, const void* zp, const v
 cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const double* prior_pdf, double norm,
                               double* w_out, double* block_sums, bool normalize, cudaStream_t st);
 cudaError_t pmc_normalize_launch(double* w, int64_t n, double* block_sums, cudaStream_t st);
+cudaError_t pmc_propose_launch(const double* theta_prev, const double* cdf, int64_t n_prev, int p, const double* L, int64_t n,
+                               uint64_t seed, uint64_t generation, int64_t first, double* out, cudaStream_t st);
 cudaError_t wcov_launch(const double* x, const double* w, int64_t n, int p, int pass, double wsum, const double* xbar,
                         double* out, int blocks, cudaStream_t st);
 

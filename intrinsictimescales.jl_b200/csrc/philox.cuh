@@ -16,6 +16,7 @@ constexpr int kPhiloxRounds = 7;
 
 constexpr uint32_t kStreamNoise = 0u;
 constexpr uint32_t kStreamInit = 1u;
+constexpr uint32_t kStreamPropose = 2u;    // PMC proposals (itjl_pmc_propose): counter = (attempt, 0, proposal index, c3)
 
 __host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t stream, uint64_t generation) {
     return ((stream & 0xFu) << 28) | (uint32_t)(generation & 0x0FFFFFFFull);

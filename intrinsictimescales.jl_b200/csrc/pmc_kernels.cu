@@ -16,6 +16,7 @@
 //     exponent argument is an O(1) whitened distance, so fp32 costs ~1e-6 relative on a weight, and the pair
 //     rate is the MUFU rate (one ex2 per pair: 148 SMs x 16 / clk) instead of the fp64 exp() rate.
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace itjl {
 
@@ -226,6 +227,68 @@ cudaError_t wcov_launch(const double* x, const double* w, int64_t n, int p, int 
                         double* out, int blocks, cudaStream_t st) {
     if (p < 1 || p > kWcovMaxP) return cudaErrorInvalidValue;
     k_wcov<<<blocks, 256, 0, st>>>(x, w, n, p, pass, wsum, xbar, out);
+    return cudaGetLastError();
+}
+
+
+// ---- PMC proposals (draw_theta_pmc, reference src/core/abc.jl:101-117), one thread per proposal ----------------
+// theta* = theta_prev[sample(pweights(weights))] by inverse-cdf look-up (53-bit uniform against the running sum of
+// the weights), theta = theta* + L z with L the Cholesky factor of tau_squared + jitter I and z ~ N(0, I) (Box-Muller
+// on Philox block `attempt`), redrawn around the SAME theta* while any component is negative (:112-115).
+// Counter-based: proposal i of (seed, generation) does not depend on n, on the launch geometry or on the GPU count.
+struct PmcProposeParams {
+    const double* theta_prev;    // (n_prev x p) column-major
+    const double* cdf;           // running sum of the weights, n_prev
+    int64_t n_prev, n;
+    int p;
+    double L[16];                // lower Cholesky factor, column-major p x p
+    PhiloxKeys keys;
+    uint32_t c3;
+    int64_t first;               // global index of proposal 0 of this launch
+    double* out;                 // (n x p) column-major
+};
+
+__global__ void __launch_bounds__(256) k_pmc_propose(const __grid_constant__ PmcProposeParams P) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t gi = (uint32_t)(P.first + i), gh = (uint32_t)((uint64_t)(P.first + i) >> 32);
+    uint32_t r[4];
+    philox4x32(0u, gh, gi, P.c3, P.keys, r);
+    const double u = ((double)(((uint64_t)r[0] << 21) ^ (uint64_t)(r[1] >> 11)) + 0.5) * 1.1102230246251565e-16;   // (0, 1), 53 bits
+    const double target = u * P.cdf[P.n_prev - 1];
+    int64_t lo = 0, hi = P.n_prev - 1;                   // first index with cdf > target
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(P.cdf + mid) > target) hi = mid; else lo = mid + 1;
+    }
+    double star[4], th[4];
+    for (int d = 0; d < P.p; ++d) star[d] = P.theta_prev[lo + (int64_t)d * P.n_prev];
+    for (uint32_t attempt = 1u;; ++attempt) {
+        philox4x32(attempt, gh, gi, P.c3, P.keys, r);
+        float z[4];
+        box_muller(r[0], r[1], z[0], z[1]);
+        box_muller(r[2], r[3], z[2], z[3]);
+        bool neg = false;
+        for (int d = 0; d < P.p; ++d) {
+            double v = star[d];
+            for (int k = 0; k <= d; ++k) v = fma(P.L[d + k * P.p], (double)z[k], v);
+            th[d] = v;
+            neg |= v < 0.0;
+        }
+        if (!neg || attempt == 0xFFFFu) break;           // (65535 redraws: theta* itself is far below zero - give up as is)
+    }
+    for (int d = 0; d < P.p; ++d) P.out[i + (int64_t)d * P.n] = th[d];
+}
+
+cudaError_t pmc_propose_launch(const double* theta_prev, const double* cdf, int64_t n_prev, int p, const double* L, int64_t n,
+                               uint64_t seed, uint64_t generation, int64_t first, double* out, cudaStream_t st) {
+    PmcProposeParams P{};
+    P.theta_prev = theta_prev; P.cdf = cdf; P.n_prev = n_prev; P.n = n; P.p = p;
+    for (int i = 0; i < p * p; ++i) P.L[i] = L[i];
+    P.keys = philox_keys(seed);
+    P.c3 = philox_c3(kStreamPropose, generation);
+    P.first = first; P.out = out;
+    k_pmc_propose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
     return cudaGetLastError();
 }
 

@@ -94,3 +94,53 @@ def test_pmc_abc_end_to_end_uses_the_device_weights(pkg, ctx):
     assert len(a.epsilon_history) == len(b.epsilon_history) >= 2
     assert np.array_equal(a.theta_history[1], b.theta_history[1])
     assert np.allclose(a.weights_history[1], b.weights_history[1], rtol=1e-9)
+
+
+def test_device_pmc_proposals_have_the_reference_distribution(pkg, ctx):
+    """itjl_pmc_propose against draw_theta_pmc's definition (abc.jl:101-117): resampling frequencies follow the weights,
+    the perturbation has covariance tau_squared + jitter I, nothing negative comes out, and proposal i depends only on
+    (seed, generation, first + i)."""
+    rng = np.random.default_rng(0)
+    n_prev, n = 500, 400000
+    theta_prev = np.stack([rng.uniform(0.5, 3.0, n_prev), rng.uniform(5.0, 15.0, n_prev)], axis=1)
+    w = rng.random(n_prev) ** 3
+    w /= w.sum()
+    tsq = np.array([[0.04, 0.03], [0.03, 0.25]])
+    th = pkg.draw_theta_pmc_device(theta_prev, w, tsq, n, seed=11, generation=2, ctx=ctx)
+    assert th.shape == (n, 2) and np.all(th >= 0) and np.all(np.isfinite(th))
+    # batching invariance
+    a = pkg.draw_theta_pmc_device(theta_prev, w, tsq, 1000, seed=11, generation=2, first=0, ctx=ctx)
+    b = pkg.draw_theta_pmc_device(theta_prev, w, tsq, 600, seed=11, generation=2, first=400, ctx=ctx)
+    assert np.array_equal(a, th[:1000]) and np.array_equal(b, th[400:1000])
+    assert not np.array_equal(pkg.draw_theta_pmc_device(theta_prev, w, tsq, 1000, seed=11, generation=3, ctx=ctx), a)
+    # moments of the mixture sum_j w_j N(theta_j, C) (nothing is near zero here, so no draw was rejected):
+    # mean = sum w theta, covariance = C + weighted covariance of theta_prev
+    mu = w @ theta_prev
+    cov = tsq + 1e-5 * np.eye(2) + (theta_prev - mu).T @ ((theta_prev - mu) * w[:, None])
+    se = np.sqrt(np.diag(cov) / n)
+    assert np.all(np.abs(th.mean(axis=0) - mu) < 5 * se)
+    assert np.allclose(np.cov(th, rowvar=False), cov, rtol=0.02)
+    # resampling frequencies: nearest theta_prev after removing the perturbation is not identifiable, so test through a
+    # degenerate covariance instead
+    t0 = pkg.draw_theta_pmc_device(theta_prev, w, 1e-12 * np.eye(2), 200000, seed=5, generation=1, jitter=0.0, ctx=ctx)
+    idx = np.argmin(np.abs(t0[:, :1] - theta_prev[:, 0][None, :]), axis=1)
+    freq = np.bincount(idx, minlength=n_prev) / 200000
+    assert np.max(np.abs(freq - w) / np.sqrt(w * (1 - w) / 200000 + 1e-12)) < 5.5
+    # redraw-while-negative: theta* close to zero, wide proposal - the accepted draws are the positive part of the Gaussian
+    t1 = pkg.draw_theta_pmc_device(np.array([[0.05]]), np.array([1.0]), np.array([[1.0]]), 100000, seed=3, ctx=ctx)
+    assert t1.min() >= 0 and abs(t1.mean() - (0.05 + np.exp(-0.05 ** 2 / 2) / np.sqrt(2 * np.pi) / 0.5199388)) < 0.01
+    with pytest.raises(pkg.ItjlError):
+        pkg.draw_theta_pmc_device(theta_prev, w, -tsq, 10, ctx=ctx)
+
+
+def test_pmc_abc_with_device_proposals(pkg, ctx):
+    """pmc_abc(device_proposals = True) recovers the timescale like the host-proposal run does."""
+    from oracle import ou as oou
+    dt, n_t = 0.002, 2500
+    t = dt * np.arange(1, n_t + 1)
+    data = oou.generate_ou_process(0.1, 1.0, dt, n_t * dt, 20, seed=4, n_t=n_t)
+    model = pkg.one_timescale_model(data, t, "abc", prior=[pkg.Uniform(0.01, 1.0)])
+    res = [pkg.pmc_abc(model, epsilon_0=1.0, max_iter=4000, min_accepted=300, steps=6, rng=np.random.default_rng(1), seed=2,
+                       ctx=ctx, device_proposals=dp) for dp in (False, True)]
+    m = [float(np.average(r.final_theta[:, 0], weights=r.final_weights)) for r in res]
+    assert abs(m[0] - 0.1) < 0.03 and abs(m[1] - 0.1) < 0.03 and abs(m[0] - m[1]) < 0.03
