@@ -395,7 +395,7 @@ def run_sweep(pkg, ctx, model, gm, P, seed, barrier, n_gen=3):
         t2 = time.perf_counter()
         acc = isacc[:n_total]
         theta_acc = theta[:n_total][acc]
-        new_eps = pkg.select_epsilon(d[:n_total], eps, current_acc_rate=n_acc / n_total, iteration=g, total_iterations=n_gen)
+        new_eps = pkg.select_epsilon(d[:n_total], eps, current_acc_rate=n_acc / n_total, iteration=g, total_iterations=n_gen, ctx=ctx)
         t3 = time.perf_counter()
         if g == 1:
             w = np.full(theta_acc.shape[0], 1.0 / theta_acc.shape[0])

@@ -195,6 +195,13 @@ int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, co
 int itjl_pmc_propose(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, int32_t n_theta, const double* weights_prev,
                      const double* tau_squared, double jitter, int64_t n, uint64_t seed, uint64_t generation,
                      int64_t first, double* theta_out);
+/* Order statistics for select_epsilon (src/core/abc.jl:700-760: percentiles of the valid distances).  The values
+ * that are not NaN and < upper are sorted ascending on the device; *n_valid_out = their count m, and for every
+ * probability probs[i] in [0, 1] out[2i], out[2i+1] = the order statistics of 0-based ranks floor(probs[i] (m - 1)) and
+ * that + 1 (clamped): the two numbers quantile type 7 (StatsBase.percentile) interpolates between - the caller does
+ * the interpolation with its own rounding.  k <= 32; nothing is written to `out` when m = 0. */
+int itjl_order_stats(itjl_ctx* ctx, const double* values, int64_t n, double upper, const double* probs, int32_t k,
+                     double* out, int64_t* n_valid_out);
 /* weighted_covar(x, w)  (src/core/abc.jl:582-613): x (n x n_theta) column-major, cov_out (n_theta x n_theta). */
 int itjl_weighted_covar(itjl_ctx* ctx, const double* x, int64_t n, int32_t n_theta, const double* w, double* cov_out);
 

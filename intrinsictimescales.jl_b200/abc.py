@@ -182,15 +182,37 @@ def compute_adaptive_alpha(iteration, current_acc_rate, target_acc_rate, alpha_m
 def select_epsilon(distances, current_epsilon, target_acc_rate=0.01, current_acc_rate=0.0, iteration=1,
                    total_iterations=100, distance_max=10.0, quantile_lower=25.0, quantile_upper=75.0,
                    quantile_init=50.0, acc_rate_buffer=0.1, alpha_max=0.9, alpha_min=0.1,
-                   acc_rate_far=2.0, acc_rate_close=0.2, alpha_far_mult=1.5, alpha_close_mult=0.5):
-    d = np.asarray(distances, dtype=np.float64)
-    valid = d[~np.isnan(d)]
-    valid = valid[valid < distance_max]
-    if valid.size == 0:
-        return current_epsilon
-    # one selection pass for the three order statistics (StatsBase.percentile = quantile type 7)
-    q_lower, q_init, q_upper = (float(q) for q in np.percentile(valid, [quantile_lower, quantile_init, quantile_upper],
-                                                               method="linear"))
+                   acc_rate_far=2.0, acc_rate_close=0.2, alpha_far_mult=1.5, alpha_close_mult=0.5, ctx=None):
+    d = np.ascontiguousarray(distances, dtype=np.float64)
+    if ctx is not None and d.size >= 65536:
+        # large generations: the order statistics come from a device sort (itjl_order_stats); same numbers - the
+        # interpolation below is NumPy's own (quantile type 7 = StatsBase.percentile)
+        import ctypes
+        probs = np.array([quantile_lower, quantile_init, quantile_upper], dtype=np.float64) / 100.0
+        pairs = np.empty(6, dtype=np.float64)
+        nv = ctypes.c_int64(0)
+        ctx.check(_lib.lib().itjl_order_stats(ctx.handle, _lib.ptr(d), d.size, float(distance_max), _lib.ptr(probs), 3,
+                                              _lib.ptr(pairs), ctypes.byref(nv)))
+        if nv.value == 0:
+            return current_epsilon
+        qs = []
+        for i, p in enumerate(probs):
+            pos = p * (nv.value - 1)
+            t = pos - math.floor(pos)
+            a, b = pairs[2 * i], pairs[2 * i + 1]
+            v = a + (b - a) * t
+            if t >= 0.5:                                  # numpy's _lerp
+                v = b - (b - a) * (1.0 - t)
+            qs.append(float(v))
+        q_lower, q_init, q_upper = qs
+    else:
+        valid = d[~np.isnan(d)]
+        valid = valid[valid < distance_max]
+        if valid.size == 0:
+            return current_epsilon
+        # one selection pass for the three order statistics (StatsBase.percentile = quantile type 7)
+        q_lower, q_init, q_upper = (float(q) for q in np.percentile(valid, [quantile_lower, quantile_init, quantile_upper],
+                                                                   method="linear"))
     alpha = compute_adaptive_alpha(iteration, current_acc_rate, target_acc_rate, alpha_max=alpha_max,
                                    alpha_min=alpha_min, total_iterations=total_iterations,
                                    acc_rate_far=acc_rate_far, acc_rate_close=acc_rate_close,

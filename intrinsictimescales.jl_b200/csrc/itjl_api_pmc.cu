@@ -232,4 +232,55 @@ int itjl_pmc_propose(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, in
     return ITJL_OK;
 }
 
+
+int itjl_order_stats(itjl_ctx* ctx, const double* values, int64_t n, double upper, const double* probs, int32_t k,
+                     double* out, int64_t* n_valid_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_order_stats: null context");
+    if (!values || !n_valid_out || n < 1 || n > 0x7fffffffll || k < 0 || k > 32 || (k > 0 && (!probs || !out)))
+        return fail(ctx, ITJL_ERR_ARG, "itjl_order_stats: invalid argument (1 <= n < 2^31, 0 <= k <= 32)");
+    for (int i = 0; i < k; ++i)
+        if (!(probs[i] >= 0.0 && probs[i] <= 1.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_order_stats: probabilities must lie in [0, 1]");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_order_stats");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n * sizeof(double), tb = sort_temp_bytes(n);
+    ITJL_CUDA(ctx, ctx->raw.reserve(bytes));
+    ITJL_CUDA(ctx, ctx->out.reserve(bytes));
+    ITJL_CUDA(ctx, ctx->out2.reserve(bytes));
+    ITJL_CUDA(ctx, ctx->part.reserve(tb));
+    ITJL_CUDA(ctx, ctx->scratch.reserve(64 * sizeof(int64_t) + 64 * sizeof(double) + 16));
+    unsigned long long* nv = (unsigned long long*)ctx->scratch.p;
+    int64_t* idx_dev = (int64_t*)((char*)ctx->scratch.p + 16);
+    double* got_dev = (double*)((char*)ctx->scratch.p + 16 + 64 * sizeof(int64_t));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, values, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ITJL_CUDA(ctx, cudaMemsetAsync(nv, 0, sizeof(unsigned long long), ctx->stream));
+    cudaError_t e = mask_invalid_launch((const double*)ctx->raw.p, n, upper, (double*)ctx->out.p, nv, ctx->stream);
+    if (e == cudaSuccess) e = sort_doubles_launch(ctx->part.p, tb, (const double*)ctx->out.p, (double*)ctx->out2.p, n, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "itjl_order_stats: %s", cudaGetErrorString(e));
+    ctx->launches += 2;
+    unsigned long long n_valid = 0;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(&n_valid, nv, sizeof(n_valid), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_valid_out = (int64_t)n_valid;
+    if (k > 0 && n_valid > 0) {
+        // quantile type 7: position p (n_valid - 1) between the order statistics floor and floor + 1
+        int64_t idx[64];
+        for (int i = 0; i < k; ++i) {
+            const double pos = probs[i] * (double)(n_valid - 1);
+            const int64_t lo = (int64_t)floor(pos);
+            idx[2 * i] = lo;
+            idx[2 * i + 1] = lo + 1 < (int64_t)n_valid ? lo + 1 : lo;
+        }
+        ITJL_CUDA(ctx, cudaMemcpyAsync(idx_dev, idx, (size_t)2 * k * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        e = gather_launch((const double*)ctx->out2.p, idx_dev, 2 * k, got_dev, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_gather: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(out, got_dev, (size_t)2 * k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return ITJL_OK;
+}
+
 }  // extern "C"

@@ -253,6 +253,10 @@ cudaError_t pmc_mixture_launch(bool fp32, const void* z, const void* zp, const v
 cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const double* prior_pdf, double norm,
                               double* w_out, double* block_sums, bool normalize, cudaStream_t st);
 cudaError_t pmc_normalize_launch(double* w, int64_t n, double* block_sums, cudaStream_t st);
+size_t sort_temp_bytes(int64_t n);
+cudaError_t mask_invalid_launch(const double* v, int64_t n, double upper, double* out, unsigned long long* n_valid, cudaStream_t st);
+cudaError_t sort_doubles_launch(void* temp, size_t temp_bytes, const double* in, double* out, int64_t n, cudaStream_t st);
+cudaError_t gather_launch(const double* sorted, const int64_t* idx, int k, double* out, cudaStream_t st);
 cudaError_t pmc_propose_launch(const double* theta_prev, const double* cdf, int64_t n_prev, int p, const double* L, int64_t n,
                                uint64_t seed, uint64_t generation, int64_t first, double* out, cudaStream_t st);
 cudaError_t wcov_launch(const double* x, const double* w, int64_t n, int p, int pass, double wsum, const double* xbar,

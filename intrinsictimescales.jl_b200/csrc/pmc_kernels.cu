@@ -15,6 +15,8 @@
 //   - T = double for up to ~10^8 pairs (the reference's arithmetic, exp() in fp64), T = float above: the
 //     exponent argument is an O(1) whitened distance, so fp32 costs ~1e-6 relative on a weight, and the pair
 //     rate is the MUFU rate (one ex2 per pair: 148 SMs x 16 / clk) instead of the fp64 exp() rate.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kernels.h"
 #include "philox.cuh"
 
@@ -289,6 +291,44 @@ cudaError_t pmc_propose_launch(const double* theta_prev, const double* cdf, int6
     P.c3 = philox_c3(kStreamPropose, generation);
     P.first = first; P.out = out;
     k_pmc_propose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+
+// ---- order statistics of the distances (select_epsilon, reference src/core/abc.jl:700-760) ------------------------
+// values that are NaN or >= upper are moved to +inf (they sort last) and counted out; the sort itself is CUB's radix
+// sort - a library call, once per generation on <= 10^6 doubles, not a hot kernel.
+__global__ void __launch_bounds__(256) k_mask_invalid(const double* __restrict__ v, int64_t n, double upper, double* __restrict__ out,
+                                                      unsigned long long* __restrict__ n_valid) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        const double x = v[i];
+        ok = (x == x) && x < upper;
+        out[i] = ok ? x : INFINITY;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned long long)__popc(m));
+}
+__global__ void k_gather(const double* __restrict__ sorted, const int64_t* __restrict__ idx, int k, double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i < k) out[i] = sorted[idx[i]];
+}
+
+size_t sort_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const double*)nullptr, (double*)nullptr, (int)n);
+    return bytes;
+}
+cudaError_t mask_invalid_launch(const double* v, int64_t n, double upper, double* out, unsigned long long* n_valid, cudaStream_t st) {
+    k_mask_invalid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, n, upper, out, n_valid);
+    return cudaGetLastError();
+}
+cudaError_t sort_doubles_launch(void* temp, size_t temp_bytes, const double* in, double* out, int64_t n, cudaStream_t st) {
+    return cub::DeviceRadixSort::SortKeys(temp, temp_bytes, in, out, (int)n, 0, 64, st);
+}
+cudaError_t gather_launch(const double* sorted, const int64_t* idx, int k, double* out, cudaStream_t st) {
+    k_gather<<<1, 64, 0, st>>>(sorted, idx, k, out);
     return cudaGetLastError();
 }
 

@@ -144,3 +144,18 @@ def test_pmc_abc_with_device_proposals(pkg, ctx):
                        ctx=ctx, device_proposals=dp) for dp in (False, True)]
     m = [float(np.average(r.final_theta[:, 0], weights=r.final_weights)) for r in res]
     assert abs(m[0] - 0.1) < 0.03 and abs(m[1] - 0.1) < 0.03 and abs(m[0] - m[1]) < 0.03
+
+
+def test_select_epsilon_device_order_statistics_match_numpy(pkg, ctx):
+    """select_epsilon(..., ctx): the percentiles of a large generation come from a device sort and are the same
+    floats np.percentile (quantile type 7 = StatsBase.percentile) gives, NaN and >= distance_max removed first."""
+    rng = np.random.default_rng(9)
+    d = rng.gamma(2.0, 0.3, size=300001)
+    d[rng.integers(0, d.size, 5000)] = np.nan
+    d[rng.integers(0, d.size, 3000)] = 25.0                    # >= distance_max: dropped
+    for it, rate, eps in [(1, 0.0, 1.0), (3, 0.5, 0.6), (3, 0.001, 0.05), (4, 0.0101, 0.3)]:
+        want = pkg.select_epsilon(d, eps, current_acc_rate=rate, iteration=it, total_iterations=10)
+        got = pkg.select_epsilon(d, eps, current_acc_rate=rate, iteration=it, total_iterations=10, ctx=ctx)
+        assert got == want, (it, rate, got, want)
+    allbad = np.full(70000, np.nan)
+    assert pkg.select_epsilon(allbad, 0.7, iteration=2, current_acc_rate=0.5, ctx=ctx) == 0.7
