@@ -494,7 +494,8 @@ struct AcwFinishParams {
 // CTA = 32 slices: the segment partials, the first 32 and the last 64 samples of every slice are
 // staged coalesced in shared memory ([row][slice] tiles), then one warp per slice (lane = lag)
 // derives the ACF and the crossings
-__global__ void __launch_bounds__(256) k_acw_finish(const AcwFinishParams P) {
+constexpr int kFinishWarps = 16;       // 512 threads: all CTAs of C2 (313) in one wave of 4 per SM; 8 warps: 25 us, 32 warps (two waves): 21.6 us
+__global__ void __launch_bounds__(32 * kFinishWarps) k_acw_finish(const AcwFinishParams P) {
     __shared__ double tile[SPART][33];
     __shared__ double head[SREF][33];          // samples 0 .. 31
     __shared__ double tail[2 * SK][33];        // samples n_t - 64 .. n_t - 1
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(256) k_acw_finish(const AcwFinishParams P) {
     const int64_t s0 = (int64_t)blockIdx.x * 32;
     const size_t ld = (size_t)P.n_slices;
     const bool col_ok = s0 + lane < P.n_slices;
-    for (int r = warp; r < SPART; r += 8) {
+    for (int r = warp; r < SPART; r += kFinishWarps) {
         double v = 0.0;
         if (col_ok) {
             const float* src = P.part + (size_t)r * ld + s0 + lane;
@@ -517,14 +518,14 @@ __global__ void __launch_bounds__(256) k_acw_finish(const AcwFinishParams P) {
         }
         tile[r][lane] = v;
     }
-    for (int r = warp; r < SREF; r += 8) head[r][lane] = (col_ok && r < P.n_t) ? P.data[s0 + lane + (size_t)r * ld] : 0.0;
+    for (int r = warp; r < SREF; r += kFinishWarps) head[r][lane] = (col_ok && r < P.n_t) ? P.data[s0 + lane + (size_t)r * ld] : 0.0;
     const int t_tail = P.n_t - 2 * SK;         // time index of tail row 0 (may be negative)
-    for (int r = warp; r < 2 * SK; r += 8) {
+    for (int r = warp; r < 2 * SK; r += kFinishWarps) {
         const int t = t_tail + r;
         tail[r][lane] = (col_ok && t >= 0) ? P.data[s0 + lane + (size_t)t * ld] : 0.0;
     }
     __syncthreads();
-    for (int w = warp; w < 32; w += 8) {
+    for (int w = warp; w < 32; w += kFinishWarps) {
         const int64_t s = s0 + w;
         if (s >= P.n_slices) break;
         const int k = lane;
@@ -623,7 +624,7 @@ cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, dou
     F.data = data; F.n_slices = n_slices; F.n_t = n_t; F.n_seg = n_seg; F.part = reinterpret_cast<const float*>(part);
     F.acf_work = acf_work; F.cap = cap; F.n_done = n_done; F.k0 = k0; F.k50 = k50; F.ke = ke;
     F.redo = redo;
-    k_acw_finish<<<(unsigned)((n_slices + 31) / 32), 256, 0, st>>>(F);
+    k_acw_finish<<<(unsigned)((n_slices + 31) / 32), 32 * kFinishWarps, 0, st>>>(F);
     return cudaGetLastError();
 }
 int acw_stream_lags() { return SK; }
