@@ -153,6 +153,17 @@ int itjl_abc_distances(itjl_model* model, const double* theta, int64_t n_particl
                        const double* u0, const double* noise, const double* phases,
                        double* dist_out, double* stats_out);
 
+/* d[i] = distance_function(model, summary_stats(model, generate_data(model, theta[i, :])), data_sum_stats) with
+ * distance_combined = true (one_timescale.jl:306-320 + combined_distance :278-290; one_timescale_and_osc.jl:368-385 +
+ * :324-347), the whole batch on the device: fused kernel -> statistics (kept on the device) -> batched fit (ACF:
+ * fit_expdecay over lags = (0 : n_stats - 1) dt; PSD: find_knee_frequency of every particle's spectrum over lags_freqs,
+ * and for the oscillation model find_oscillation_peak of its residual) -> weights[0] d + weights[1] (data_tau - tau)^2
+ * [+ weights[2] (data_osc - peak)^2].  n_weights = 2, or 3 for the PSD summary of the oscillation model.  A particle
+ * whose statistics are not finite gets NaN. */
+int itjl_abc_distances_combined(itjl_model* model, const double* theta, int64_t n_particles, int32_t n_theta,
+                                uint64_t seed, uint64_t generation, int64_t particle_offset, const double* lags_freqs,
+                                const double* weights, int32_t n_weights, double data_tau, double data_osc, double* dist_out);
+
 /* Same, fused with the bookkeeping of src/core/abc.jl:182-199: applies `d <= epsilon`
  * (NaN -> rejected) and the sequential stopping rule (stop right after the
  * min_accepted-th acceptance, in particle order).  isaccepted (n_particles bytes) is only

@@ -106,6 +106,7 @@ SIGNATURES = {
     "itjl_fit_knee": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _vp]),
     "itjl_acw_knee": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _f64, _f64, _u32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "itjl_acw_knee_nfreq": (_i64, [_i64, _i32]),
+    "itjl_abc_distances_combined": (ctypes.c_int, [_vp, _vp, _i64, _i32, _u64, _u64, _i64, _vp, _vp, _i32, _f64, _f64, _vp]),
     "itjl_pmc_propose": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _f64, _i64, _u64, _u64, _i64, _vp]),
     "itjl_order_stats": (ctypes.c_int, [_vp, _vp, _i64, _f64, _vp, _i32, _vp, _vp]),
     "itjl_generate_ou_two": (ctypes.c_int, [_vp, _f64, _f64, _f64, _f64, _i64, _i64, _f64, _i32, _u64, _vp]),

@@ -297,11 +297,11 @@ int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, in
 // knee fit of the rows in `rows_dev` (row-major, ld doubles apart) on columns [i0, i0 + n); results in ctx->stats as
 // three consecutive arrays of n_rows doubles: knee, amp, peak
 static int knee_fit_dev(itjl_ctx* ctx, const double* rows_dev, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs_dev,
-                        double min_freq, double max_freq, int mode, int max_peaks) {
+                        double min_freq, double max_freq, int mode, int max_peaks, double* out3 = nullptr) {
     const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->sm_count * 4);
     ITJL_CUDA(ctx, ctx->part.reserve((size_t)grid * 3 * n * sizeof(double)));
-    ITJL_CUDA(ctx, ctx->stats.reserve((size_t)n_rows * 3 * sizeof(double)));
-    double* k = (double*)ctx->stats.p;
+    if (!out3) ITJL_CUDA(ctx, ctx->stats.reserve((size_t)n_rows * 3 * sizeof(double)));
+    double* k = out3 ? out3 : (double*)ctx->stats.p;
     cudaError_t e = knee_fit_launch(rows_dev, n_rows, ld, i0, n, freqs_dev, min_freq, max_freq, mode, max_peaks, k, k + n_rows,
                                     k + 2 * n_rows, (double*)ctx->part.p, grid, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_knee_fit: %s", cudaGetErrorString(e));
@@ -468,6 +468,64 @@ int itjl_acw_knee(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n
     if (rc != ITJL_OK) return rc;
     ITJL_CUDA(ctx, cudaMemcpyAsync(knee_out, ctx->stats.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // freqs stays alive until here
+    return ITJL_OK;
+}
+
+int itjl_abc_distances_combined(itjl_model* m, const double* theta, int64_t n_particles, int32_t n_theta,
+                                uint64_t seed, uint64_t generation, int64_t particle_offset, const double* lags_freqs,
+                                const double* weights, int32_t n_weights, double data_tau, double data_osc, double* dist_out) {
+    if (!m) return fail(nullptr, ITJL_ERR_ARG, "null model");
+    if (!theta || !dist_out || !weights || n_particles < 1 || n_theta < 1) return fail(m->ctx, ITJL_ERR_ARG, "itjl_abc_distances_combined: null / empty argument");
+    ITJL_LOCK(m->ctx);
+    m = primary(m);
+    itjl_ctx* ctx = m->ctx;
+    ITJL_LOCK(ctx);
+    NvtxRange nvtx("itjl_abc_distances_combined");
+    const itjl_model_desc& d = m->d;
+    const bool psd = d.summary == ITJL_SUMMARY_PSD || d.summary == ITJL_SUMMARY_PGRAM;
+    const bool osc_psd = psd && d.kind == ITJL_KIND_OU_OSC;
+    if (n_weights != (osc_psd ? 3 : 2)) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances_combined: two weights (three for the PSD summary of the oscillation model)");
+    if (psd && !lags_freqs) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances_combined: lags_freqs (the model's frequencies) required for a PSD summary");
+    if (psd && d.n_stats < 3) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances_combined: fewer than three frequencies");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t ns = d.n_stats;
+    if (psd) {
+        for (int64_t i = 1; i < ns; ++i)
+            if (!(lags_freqs[i] > lags_freqs[i - 1])) return fail(ctx, ITJL_ERR_ARG, "itjl_abc_distances_combined: lags_freqs must be strictly ascending");
+        ITJL_CUDA(ctx, ctx->out3.reserve((size_t)ns * sizeof(double)));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out3.p, lags_freqs, (size_t)ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = upload(ctx, ctx->theta, theta, (size_t)n_particles * n_theta * sizeof(double));
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, ctx->dist.reserve((size_t)n_particles * sizeof(double)));
+    // the statistics stay on the device: batches of at most 16384 particles (n_stats doubles each)
+    const int64_t batch = std::min<int64_t>(n_particles, 16384);
+    ITJL_CUDA(ctx, ctx->stats.reserve((size_t)batch * ns * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->gather.reserve((size_t)batch * 3 * sizeof(double)));
+    for (int64_t lo = 0; lo < n_particles; lo += batch) {
+        const int64_t nb = std::min<int64_t>(batch, n_particles - lo);
+        rc = launch_distances(m, (const double*)ctx->theta.p + lo, nb, n_theta, seed, generation, particle_offset + lo,
+                              nullptr, nullptr, nullptr, (double*)ctx->dist.p + lo, (double*)ctx->stats.p, n_particles);
+        if (rc != ITJL_OK) return rc;
+        double* fit = (double*)ctx->gather.p;                 // [knee or tau | amp | peak] x nb
+        if (psd) {
+            // find_knee_frequency defaults (min_freq = freqs[1], max_freq = freqs[end]); the peak search window of the
+            // oscillation model is its freqlims, an open interval around every selected frequency: the whole axis
+            rc = knee_fit_dev(ctx, (const double*)ctx->stats.p, nb, ns, 0, (int)ns, (const double*)ctx->out3.p, lags_freqs[0],
+                              lags_freqs[ns - 1], 0, 0, fit);
+            if (rc != ITJL_OK) return rc;
+        } else {
+            cudaError_t e = acw_tau_launch((const double*)ctx->stats.p, nb, ns, (int)ns, d.dt, fit, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_tau: %s", cudaGetErrorString(e));
+            ctx->launches++;
+        }
+        cudaError_t e = combine_launch((double*)ctx->dist.p + lo, nb, fit, psd ? 1 : 0, osc_psd ? fit + 2 * nb : nullptr, weights[0],
+                                       weights[1], osc_psd ? weights[2] : 0.0, data_tau, data_osc, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_combine: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    }
+    ITJL_CUDA(ctx, cudaMemcpyAsync(dist_out, ctx->dist.p, (size_t)n_particles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ITJL_OK;
 }
 

@@ -126,6 +126,8 @@ cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, d
 cudaError_t knee_fit_launch(const double* rows, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs, double min_freq,
                             double max_freq, int mode, int max_peaks, double* knee_out, double* amp_out, double* peak_out,
                             double* work, int grid, cudaStream_t st);
+cudaError_t combine_launch(double* dist, int64_t n, const double* fit, int is_knee, const double* peak, double w0, double w1, double w2,
+                           double data_tau, double data_osc, cudaStream_t st);
 cudaError_t transpose_launch(const double* in, int64_t n_rows, int64_t n_cols, double* out, cudaStream_t st);
 cudaError_t col_mean_launch(const double* in, int64_t n_rows, int64_t n_cols, double* out, cudaStream_t st);
 

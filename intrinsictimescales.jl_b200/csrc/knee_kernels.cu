@@ -338,4 +338,24 @@ cudaError_t col_mean_launch(const double* in, int64_t n_rows, int64_t n_cols, do
     return cudaGetLastError();
 }
 
+
+// combined_distance (one_timescale.jl:278-290, one_timescale_and_osc.jl:324-347):
+// d <- w0 d + w1 (data_tau - tau)^2 [+ w2 (data_osc - peak)^2]; fit = tau (ACF) or the knee frequency (PSD: tau = 1 / 2 pi knee)
+__global__ void __launch_bounds__(256) k_combine(double* __restrict__ dist, int64_t n, const double* __restrict__ fit, int is_knee,
+                                                 const double* __restrict__ peak, double w0, double w1, double w2, double data_tau,
+                                                 double data_osc) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double tau = is_knee ? 1.0 / (6.283185307179586 * fit[i]) : fit[i];
+    const double e = data_tau - tau;
+    double d = w0 * dist[i] + w1 * (e * e);
+    if (peak) { const double o = data_osc - peak[i]; d += w2 * (o * o); }
+    dist[i] = d;
+}
+cudaError_t combine_launch(double* dist, int64_t n, const double* fit, int is_knee, const double* peak, double w0, double w1, double w2,
+                           double data_tau, double data_osc, cudaStream_t st) {
+    k_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, n, fit, is_knee, peak, w0, w1, w2, data_tau, data_osc);
+    return cudaGetLastError();
+}
+
 }  // namespace itjl

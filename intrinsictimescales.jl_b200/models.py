@@ -175,6 +175,15 @@ class GpuModel:
         cast = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         u0, noise, phases = cast(u0), cast(noise), cast(phases)
         combined = bool(self.model.distance_combined)
+        if combined and stats is None and u0 is None and noise is None and phases is None:
+            # the whole combined distance on the device (itjl_abc_distances_combined): the statistics never leave it
+            m = self.model
+            w = np.ascontiguousarray(m.weights, dtype=np.float64)
+            lf = np.ascontiguousarray(m.lags_freqs, dtype=np.float64) if m.summary_method == "psd" else None
+            self.ctx.check(_lib.lib().itjl_abc_distances_combined(
+                self._h, _lib.ptr(th), n, p, int(seed), int(generation), int(particle_offset), _lib.ptr(lf), _lib.ptr(w),
+                int(w.size), float(m.data_tau), float(m.data_osc) if m.data_osc is not None else 0.0, _lib.ptr(out)))
+            return out
         if combined and stats is None:
             stats = np.empty((n, self.n_stats), dtype=np.float64)
         self.ctx.check(_lib.lib().itjl_abc_distances(

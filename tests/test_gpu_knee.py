@@ -158,3 +158,27 @@ def test_combined_psd_distances(pkg, ctx):
         x = omodels.generate_data(om, theta[i], seed=5, generation=3, particle=i)
         want = omodels.distance_function(om, omodels.summary_stats(om, x), om.data_sum_stats)
         assert (np.isnan(want) and np.isnan(got[i])) or abs(got[i] - want) <= 1e-3 * want, (i, got[i], want)
+
+
+def test_combined_distance_on_the_device_equals_the_host_combination(pkg, ctx):
+    """itjl_abc_distances_combined (statistics stay on the device) against the step-by-step path (statistics to the
+    host, itjl_fit_knee / itjl_fit_expdecay, NumPy combination) for the three combined distances."""
+    dt, n_t, n_trials = 1 / 500, 5000, 4
+    t = dt * np.arange(1, n_t + 1)
+    rng = np.random.default_rng(3)
+    d1 = oou.generate_ou_process(0.05, 1.0, dt, n_t * dt, n_trials, seed=3, n_t=n_t)
+    d2 = oou.generate_ou_with_oscillation([0.05, 10.0, 0.7], dt, n_t * dt, n_trials, 0.0, 1.0, seed=11, n_t=n_t)
+    models = [
+        (pkg.one_timescale_model(d1, t, "abc", summary_method="psd", distance_combined=True, weights=[0.7, 0.3], ctx=ctx),
+         rng.uniform(0.01, 0.5, size=(40, 1))),
+        (pkg.one_timescale_model(d1, t, "abc", distance_combined=True, weights=[0.4, 0.6], ctx=ctx), rng.uniform(0.01, 0.5, size=(40, 1))),
+        (pkg.one_timescale_and_osc_model(d2, t, "abc", summary_method="psd", distance_combined=True, weights=[0.5, 0.3, 0.2], ctx=ctx),
+         np.stack([rng.uniform(0.02, 0.2, 40), rng.uniform(5, 20, 40), rng.uniform(0.1, 0.95, 40)], axis=1)),
+    ]
+    for gm, theta in models:
+        g = gm.gpu_model(ctx)
+        fused = g.distances(theta, seed=7, generation=2)
+        plain, stats = g.distances(theta, seed=7, generation=2, return_stats=True)     # host combination of the same statistics
+        assert np.allclose(fused, plain, rtol=1e-12, atol=0.0, equal_nan=True), np.nanmax(np.abs(fused - plain) / plain)
+        d, isacc, n_total, n_acc = g.generation(theta, float(np.nanmedian(fused)), 10, seed=7, generation=2)
+        assert np.array_equal(d[:n_total], fused[:n_total], equal_nan=True) and n_acc == 10
