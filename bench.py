@@ -628,7 +628,8 @@ def run_gpu(args):
             from oracle import models as omodels
             return omodels.one_timescale_and_osc_model(d4, t4, prior=[omodels.Normal(.1, .1), omodels.Normal(10, 5), omodels.Uniform(0, 1)])
         r4 = np.random.default_rng(4)
-        th4 = np.stack([np.abs(r4.normal(.1, .1, 2000)) + 0.005, r4.normal(10, 5, 2000), r4.uniform(0, 1, 2000)], axis=1)
+        n4 = 14 * ctx.sm_count                      # one CTA per particle, one CTA per SM: whole waves (2072 on a B200)
+        th4 = np.stack([np.abs(r4.normal(.1, .1, n4)) + 0.005, r4.normal(10, 5, n4), r4.uniform(0, 1, n4)], axis=1)
         sub["c4_osc_psd"] = sub_model(pkg, ctx, torch, stream, "C4 one_timescale_and_osc_model, PSD summary, 100 trials x 10000",
                                       m4, om4, th4, fp32_peak, tensor_peak, tensor_src, want_cpu)
         # f1: one_timescale_model(summary_method = :psd), DSP periodogram (nfft = 5000), 20 trials x 5000
