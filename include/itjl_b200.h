@@ -54,7 +54,8 @@ enum { ITJL_DIST_LINEAR = 0, ITJL_DIST_LOG = 1 };
 enum { ITJL_UPDATE_EXACT = 0, ITJL_UPDATE_EM = 1 };
 
 /* acw type mask bits (src/core/acw.jl:132, acf_acwtypes) */
-enum { ITJL_ACW0 = 1, ITJL_ACW50 = 2, ITJL_ACWEULER = 4, ITJL_AUC = 8, ITJL_TAU = 16 };
+enum { ITJL_ACW0 = 1, ITJL_ACW50 = 2, ITJL_ACWEULER = 4, ITJL_AUC = 8, ITJL_TAU = 16,
+       ITJL_TAU3 = 32 };   /* tau by fit_expdecay_3_parameters (skip_zero_lag = true, acw.jl:212-216) instead of fit_expdecay */
 
 /* ---- tuning ------------------------------------------------------------------------ */
 /* Per-context knobs (itjl_tuning_default gives the values below).  They replace the ITJL_* environment
@@ -339,7 +340,9 @@ int64_t itjl_acw_knee_nfreq(int64_t n_t, int32_t has_nan);
  *   k0 / k50 / ke : 0-based first lag index with acf <= 0 / 0.5 / 1/e, -1 if never
  *                   (the caller indexes its own `lags` range; NaN for -1);
  *   auc           : acw_romberg(dt, acf[1:k0_first]) per slice (NaN when k0_first < 2);
- *   tau           : fit_expdecay(lags[1:n_lags], acf[.., 1:n_lags]) per slice;
+ *   tau           : fit_expdecay(lags[1:n_lags], acf[.., 1:n_lags]) per slice (ITJL_TAU), or the tau of
+ *                   fit_expdecay_3_parameters - A (exp(-t / tau) + B) over lags[2:end], src/utils/utils.jl:159-179 -
+ *                   with ITJL_TAU3 (argmin of its mean-squared-error objective; LM's stopping point is not reproduced);
  *   n_lags_io     : in: user n_lags or 0 for the reference default ceil(1.1*max k0);
  *                   out: the value used;
  *   acf_out       : NULL, or capacity acf_capacity doubles; receives (n_out x n_lags)

@@ -46,7 +46,7 @@ KIND_OU, KIND_OU_OSC = 0, 1
 SUMMARY_ACF, SUMMARY_ACF_MISSING, SUMMARY_PSD, SUMMARY_PGRAM = 0, 1, 2, 3
 DIST_LINEAR, DIST_LOG = 0, 1
 UPDATE_EXACT, UPDATE_EM = 0, 1
-ACW0, ACW50, ACWEULER, AUC, TAU = 1, 2, 4, 8, 16
+ACW0, ACW50, ACWEULER, AUC, TAU, TAU3 = 1, 2, 4, 8, 16, 32
 
 _vp, _i32, _i64, _u32, _u64, _f64 = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64,
                                       ctypes.c_uint32, ctypes.c_uint64, ctypes.c_double)

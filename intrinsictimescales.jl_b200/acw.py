@@ -116,7 +116,7 @@ def _acw_knee(data, dims, fs, freqlims, average_over_trials, oscillation_peak, m
 
 def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
         average_over_trials=False, ctx=None, freqlims=None, return_psd=True, oscillation_peak=True, max_peaks=1,
-        allow_variable_exponent=False, constrained=False):
+        allow_variable_exponent=False, constrained=False, skip_zero_lag=False):
     """Compute ACW measures of every slice of `data` along its time dimension.
 
     `dims` is the time dimension in the reference's convention: 1-based, default = the last one
@@ -166,6 +166,8 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     mask = 0
     for t in acwtypes:
         mask |= _BITS.get(t, 0)
+    if skip_zero_lag and (mask & _lib.TAU):
+        mask = (mask & ~_lib.TAU) | _lib.TAU3              # fit_expdecay_3_parameters over lags[2:end] (acw.jl:212-216)
     n_out = 1 if average_over_trials else n_slices
     k0 = np.empty(n_out, dtype=np.int32)
     k50 = np.empty(n_out, dtype=np.int32)

@@ -560,9 +560,10 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
     int rc = ITJL_OK;
     if (!n_lags_io) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags_io is required");
     if (!(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: fs must be positive");
-    if ((typemask & ~31u) || typemask == 0) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: No ACW types specified / unknown type bit");
+    if ((typemask & ~63u) || typemask == 0) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: No ACW types specified / unknown type bit");
+    if ((typemask & ITJL_TAU) && (typemask & ITJL_TAU3)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: ITJL_TAU and ITJL_TAU3 share the tau output: request one");
     if (((typemask & ITJL_ACW0) && !k0) || ((typemask & ITJL_ACW50) && !k50) || ((typemask & ITJL_ACWEULER) && !ke) ||
-        ((typemask & ITJL_AUC) && !auc) || ((typemask & ITJL_TAU) && !tau))
+        ((typemask & ITJL_AUC) && !auc) || ((typemask & (ITJL_TAU | ITJL_TAU3)) && !tau))
         return fail(ctx, ITJL_ERR_ARG, "itjl_acw: output pointer missing for a requested acwtype");
     const int64_t user_lags = *n_lags_io;
     if (user_lags < 0 || user_lags > n_t) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags out of range");
@@ -753,6 +754,19 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
     if (typemask & ITJL_TAU) {
         e = acw_tau_launch(acf_rows, n_out, acf_ld, (int)n_lags, dt, d_tau, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_tau: %s", cudaGetErrorString(e));
+        ctx->launches++;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    std::vector<double> lag_axis;                  // must outlive the async copy
+    if (typemask & ITJL_TAU3) {
+        // skip_zero_lag = true (acw.jl:212-216): fit_expdecay_3_parameters over lags[2:end]
+        lag_axis.resize((size_t)n_lags);
+        for (int64_t k = 0; k < n_lags; ++k) lag_axis[(size_t)k] = (double)k * dt;
+        ITJL_CUDA(ctx, ctx->gather.reserve((size_t)n_lags * sizeof(double)));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->gather.p, lag_axis.data(), (size_t)n_lags * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        e = expdecay3_launch(acf_rows, n_out, acf_ld, (int)n_lags, (const double*)ctx->gather.p, d_tau,
+                             (int)std::min<int64_t>(n_out, (int64_t)ctx->sm_count * 8), ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_expdecay3_fit: %s", cudaGetErrorString(e));
         ctx->launches++;
         ITJL_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }

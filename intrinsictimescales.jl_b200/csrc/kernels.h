@@ -128,6 +128,8 @@ cudaError_t knee_fit_launch(const double* rows, int64_t n_rows, int64_t ld, int 
                             double* work, int grid, cudaStream_t st);
 cudaError_t combine_launch(double* dist, int64_t n, const double* fit, int is_knee, const double* peak, double w0, double w1, double w2,
                            double data_tau, double data_osc, cudaStream_t st);
+cudaError_t expdecay3_launch(const double* rows, int64_t n_rows, int64_t ld, int n_lags, const double* lags, double* tau_out, int grid,
+                             cudaStream_t st);
 cudaError_t transpose_launch(const double* in, int64_t n_rows, int64_t n_cols, double* out, cudaStream_t st);
 cudaError_t col_mean_launch(const double* in, int64_t n_rows, int64_t n_cols, double* out, cudaStream_t st);
 

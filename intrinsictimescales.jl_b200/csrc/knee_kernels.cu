@@ -358,4 +358,85 @@ cudaError_t combine_launch(double* dist, int64_t n, const double* fit, int is_kn
     return cudaGetLastError();
 }
 
+
+// ---- fit_expdecay_3_parameters (reference src/utils/utils.jl:85-91, 159-179) ------------------------------------------
+// A (exp(-t / tau) + B) fitted to acf[2:end] over lags[2:end] (the zero lag is skipped: acw(...; skip_zero_lag = true)),
+// residual = mean squared error.  For a given tau the model is linear in (A, A B), so the best pair is the closed-form
+// 2 x 2 least-squares solution and the objective becomes a function of log tau alone, minimised by the same
+// deterministic Nelder-Mead (one dimension) from the reference's initial guess tau0 = tau_from_acw50(acw50(lags, acf))
+// (1.0 when the ACF never falls to 0.5).  Returns the argmin of the reference's objective; its LM may stop elsewhere
+// (unpinned) and returns NaN for a negative tau, which the log parametrisation cannot produce.
+struct Exp3Sums { double se, see, sy, sey, syy; };
+
+__device__ __forceinline__ double exp3_objective(const double* __restrict__ y, const double* __restrict__ t, int n, double log_tau,
+                                                 KneeShared* sh, double* a_out = nullptr, double* c_out = nullptr) {
+    const double it = exp(-log_tau);
+    double se = 0.0, see = 0.0, sy = 0.0, sey = 0.0, syy = 0.0;
+    for (int i = threadIdx.x; i < n; i += kKneeThreads) {
+        const double e = exp(-t[i] * it), v = y[i];
+        se += e; see = fma(e, e, see); sy += v; sey = fma(e, v, sey); syy = fma(v, v, syy);
+    }
+    se = block_sum(se, sh); see = block_sum(see, sh); sy = block_sum(sy, sh); sey = block_sum(sey, sh); syy = block_sum(syy, sh);
+    // minimise sum (a e_i + c - y_i)^2: [see se; se n] [a; c] = [sey; sy]
+    const double nn = (double)n, det = see * nn - se * se;
+    double a, c;
+    if (fabs(det) > 1e-300 * (see * nn + 1e-300)) { a = (sey * nn - se * sy) / det; c = (see * sy - se * sey) / det; }
+    else { a = 0.0; c = sy / nn; }
+    if (a_out) { *a_out = a; *c_out = c; }
+    const double sse = syy - a * sey - c * sy;
+    return fmax(sse, 0.0) / nn;
+}
+
+// rows: [n_rows][ld] (lag index fastest); lags: n_lags values; uses entries 1 .. n_lags - 1
+__global__ void __launch_bounds__(kKneeThreads) k_expdecay3_fit(const double* __restrict__ rows, int64_t n_rows, int64_t ld, int n_lags,
+                                                                const double* __restrict__ lags, double* __restrict__ tau_out) {
+    __shared__ KneeShared sh;
+    const int tid = threadIdx.x;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const double* acf = rows + r * ld;
+        // acw50: first lag with acf <= 0.5 (NaN values never compare true)
+        int first = 0x7fffffff;
+        double bad = 0.0;
+        for (int i = tid; i < n_lags; i += kKneeThreads) {
+            if (acf[i] <= 0.5) first = min(first, i);
+            if (i >= 1 && !isfinite(acf[i])) bad = 1.0;
+        }
+        first = block_min_int(first, &sh);
+        bad = block_sum(bad, &sh);
+        const double tau0 = first == 0x7fffffff ? 1.0 : lags[first] / 0.6931471805599453;       // tau_from_acw50
+        double tau = NAN;
+        if (bad == 0.0 && n_lags >= 4 && tau0 > 0.0) {
+            // one-dimensional Nelder-Mead = interval halving with reflection / expansion; three rounds as for the knee
+            double x = log(tau0), fx = exp3_objective(acf + 1, lags + 1, n_lags - 1, x, &sh);
+            for (int round = 0; round < 3; ++round) {
+                double h = round == 0 ? 0.25 : (round == 1 ? 0.025 : 0.0025);
+                double x1 = x + h, f1 = exp3_objective(acf + 1, lags + 1, n_lags - 1, x1, &sh);
+                for (int it = 0; it < 400; ++it) {
+                    // (x, fx) best, (x1, f1) other
+                    if (f1 < fx) { const double tx = x, tf = fx; x = x1; fx = f1; x1 = tx; f1 = tf; }
+                    if (fabs(x1 - x) < 1e-12) break;
+                    const double xr = x + (x - x1), fr = exp3_objective(acf + 1, lags + 1, n_lags - 1, xr, &sh);
+                    if (fr < fx) {
+                        const double xe = x + 2.0 * (x - x1), fe = exp3_objective(acf + 1, lags + 1, n_lags - 1, xe, &sh);
+                        if (fe < fr) { x1 = x; f1 = fx; x = xe; fx = fe; } else { x1 = x; f1 = fx; x = xr; fx = fr; }
+                    } else {
+                        const double xc = x + 0.5 * (x1 - x), fc = exp3_objective(acf + 1, lags + 1, n_lags - 1, xc, &sh);
+                        x1 = xc; f1 = fc;
+                    }
+                }
+                if (f1 < fx) { x = x1; fx = f1; }
+            }
+            tau = exp(x);
+        }
+        if (tid == 0) tau_out[r] = tau;
+        __syncthreads();
+    }
+}
+
+cudaError_t expdecay3_launch(const double* rows, int64_t n_rows, int64_t ld, int n_lags, const double* lags, double* tau_out, int grid,
+                             cudaStream_t st) {
+    k_expdecay3_fit<<<grid, kKneeThreads, 0, st>>>(rows, n_rows, ld, n_lags, lags, tau_out);
+    return cudaGetLastError();
+}
+
 }  // namespace itjl

@@ -20,7 +20,7 @@ from . import acwred, summary
 ACF_ACWTYPES = ("acw0", "acw50", "acweuler", "auc", "tau")
 
 
-def acw(data, fs, acwtypes=ACF_ACWTYPES, n_lags=None, average_over_trials=False):
+def acw(data, fs, acwtypes=ACF_ACWTYPES, n_lags=None, average_over_trials=False, skip_zero_lag=False):
     data = np.asarray(data, dtype=np.float64)
     if data.ndim == 1:
         data = data.reshape(1, -1)                      # acw.jl:122-125
@@ -69,7 +69,8 @@ def acw(data, fs, acwtypes=ACF_ACWTYPES, n_lags=None, average_over_trials=False)
     acf = acf[:, :n_lags]
     lags = lags[:n_lags]
     if "tau" in acwtypes:
-        out["tau"] = np.array([acwred.fit_expdecay(lags, a) for a in acf])
+        fit = acwred.fit_expdecay_3_parameters if skip_zero_lag else acwred.fit_expdecay       # acw.jl:212-220
+        out["tau"] = np.array([fit(lags, a) for a in acf])
     out["n_lags"] = n_lags
     out["acf"] = acf
     out["lags"] = lags

@@ -221,3 +221,37 @@ def fit_expdecay(lags, acf):
                 gb *= 0.5
             side = 1
     return math.exp(u)
+
+
+def fit_expdecay_3_parameters(lags, acf):
+    """utils.jl:159-179: A (exp(-t / tau) + B) fitted to acf[2:end] over lags[2:end] with the scalar residual mean(abs2(.)),
+    from u0 = [0.5, tau_from_acw50(acw50(lags, acf)), 0] ([0.5, 1, 0] when the ACF never falls to 0.5); tau < 0 -> NaN.
+    NonlinearSolve's LM is not restated: this returns the argmin of the same objective (for a fixed tau the best
+    (A, A B) is a closed-form linear least-squares pair; the remaining 1-D problem in log tau is minimised by SciPy's
+    bounded Brent search around the initial guess and polished by least_squares).  PARITY UNPINNED."""
+    from scipy import optimize
+    lags = np.asarray(lags, dtype=np.float64); acf = np.asarray(acf, dtype=np.float64)
+    a50 = acw50(lags, acf)
+    tau0 = 1.0 if math.isnan(a50) else tau_from_acw50(a50)
+    t, y = lags[1:], acf[1:]
+    if t.size < 3 or not np.all(np.isfinite(y)) or not tau0 > 0:
+        return float("nan")
+
+    def reduced(lt):
+        e = np.exp(-t * math.exp(-lt))
+        A = np.stack([e, np.ones_like(e)], axis=1)
+        coef, *_ = np.linalg.lstsq(A, y, rcond=None)
+        r = A @ coef - y
+        return float(np.mean(r * r))
+    # local search from the initial guess, widening the bracket while the minimum sits on its edge
+    x = math.log(tau0)
+    h = 0.25
+    for _ in range(60):
+        r = optimize.minimize_scalar(reduced, bounds=(x - h, x + h), method="bounded", options={"xatol": 1e-12})
+        moved = abs(r.x - x)
+        x = r.x
+        if moved < 0.9 * h:
+            h *= 0.25
+            if h < 1e-9:
+                break
+    return float(math.exp(x))

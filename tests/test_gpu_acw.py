@@ -238,3 +238,25 @@ def test_acw_random_inputs_against_oracle(pkg, ctx, case, n_slices, n_t, fs, gen
     assert a.shape == want["acf"].shape and np.array_equal(np.isnan(a), np.isnan(want["acf"]))
     assert np.nanmax(np.abs(a - want["acf"]), initial=0.0) < 1e-5
     assert np.allclose(np.atleast_1d(res["tau"]), want["tau"], rtol=1e-2, atol=0, equal_nan=True)
+
+
+def test_acw_skip_zero_lag_three_parameter_fit(pkg, ctx):
+    """acw(...; acwtypes = :tau, skip_zero_lag = true) -> fit_expdecay_3_parameters (utils.jl:159-179): A (exp(-t / tau) + B)
+    over lags[2:end].  White measurement noise on top of an OU signal puts a delta at lag 0 that the one-parameter fit
+    cannot absorb - the case the option exists for."""
+    fs, n_t, tau = 100.0, 6000, 0.25
+    sig = oou.generate_ou_process(tau, 1.0, 1 / fs, n_t / fs, 9, seed=21, n_t=n_t)
+    data = sig + 0.8 * np.random.default_rng(4).standard_normal(sig.shape)
+    want = oacw.acw(data, fs, acwtypes=["tau"], skip_zero_lag=True)
+    got = pkg.acw(data, fs, acwtypes=["tau"], skip_zero_lag=True, ctx=ctx)
+    assert got.n_lags == want["n_lags"]
+    assert np.allclose(got.acw_results, want["tau"], rtol=1e-6), (got.acw_results, want["tau"])
+    plain = pkg.acw(data, fs, acwtypes=["tau"], ctx=ctx)
+    # the three-parameter fit recovers the OU timescale, the one-parameter fit is dragged down by the lag-0 delta
+    assert np.all(np.abs(np.log(np.asarray(got.acw_results) / tau)) < np.log(2.2)) and abs(np.median(got.acw_results) / tau - 1.0) < 0.25
+    assert np.median(plain.acw_results) < 0.8 * np.median(got.acw_results)
+    # a perfect A (exp(-t / tau) + B) row comes back exactly
+    lags = np.arange(60) / fs
+    row = 0.7 * (np.exp(-lags / 0.11) + 0.05)
+    from oracle import acwred
+    assert acwred.fit_expdecay_3_parameters(lags, row) == pytest.approx(0.11, rel=1e-8)
