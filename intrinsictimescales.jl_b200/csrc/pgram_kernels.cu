@@ -277,7 +277,11 @@ __global__ void __launch_bounds__(kLsThreads) k_lomb_scargle(const double* __res
     const double SS = (1.0 - CC) - S * S;
     CC -= C * C; CS -= C * S;
     const double D = CC * SS - CS * CS;
-    out[s + (size_t)k * n_slices] = (SS * YC * YC + CC * YS * YS - 2.0 * CS * YC * YS) / (YY * D);
+    double pw = (SS * YC * YC + CC * YS * YS - 2.0 * CS * YC * YS) / (YY * D);
+    // degenerate frequencies (exactly Nyquist on the regular grid: every sin(omega t) vanishes, D = 0 / 0): the model
+    // has one basis function left - the power is the projection on it
+    if (!(D > 1e-12 * (CC + SS) * (CC + SS))) pw = SS < CC ? YC * YC / (YY * CC) : YS * YS / (YY * SS);
+    out[s + (size_t)k * n_slices] = pw;
 }
 
 cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq,

@@ -183,7 +183,13 @@ def lombscargle_vec(times, signal, freqs):
         CCh, CSh = w * np.sum(c * c, axis=1), w * np.sum(c * s_, axis=1)
         CC, SS, CS = CCh - C * C, (1.0 - CCh) - S * S, CSh - C * S
         D = CC * SS - CS * CS
-        out[lo:lo + 256] = (SS * YC * YC + CC * YS * YS - 2.0 * CS * YC * YS) / (YY * D)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pw = (SS * YC * YC + CC * YS * YS - 2.0 * CS * YC * YS) / (YY * D)
+            # degenerate frequencies (exactly Nyquist on a regular grid: every sin(omega t) vanishes, D = 0 / 0): one basis
+            # function is left - the power is the projection on it
+            deg = ~(D > 1e-12 * (CC + SS) ** 2)
+            one = np.where(SS < CC, YC * YC / (YY * CC), YS * YS / (YY * SS))
+        out[lo:lo + 256] = np.where(deg, one, pw)
     return out
 
 
