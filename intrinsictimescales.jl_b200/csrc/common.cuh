@@ -85,6 +85,10 @@ extern char g_err[512];
 inline int fail(itjl_ctx* ctx, int code, const char* fmt, const char* a = "", const char* b = "") {
     char* dst = ctx ? ctx->err : g_err;
     snprintf(dst, 512, fmt, a, b);
+    // a failed runtime call stays recorded as the thread's "last error" until it is fetched: clear it here, or the next
+    // successful launch's cudaGetLastError() reports it (found by benchmarks/psd_fuzz.py: a refused configuration made
+    // the following, unrelated call fail with "invalid argument")
+    if (code == ITJL_ERR_CUDA) (void)cudaGetLastError();
     return code;
 }
 

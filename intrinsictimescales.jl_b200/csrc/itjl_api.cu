@@ -236,16 +236,17 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         // shared memory; tuning.psd_v2 = 0 keeps the first kernel
         if (ctx->tuning.psd_v2 != 0 && abc_psd2_supported((int)d.n_t, m->n2)) {
             const size_t sm2 = abc_psd2_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
-            if ((int64_t)sm2 <= ctx->max_smem_optin && m->psd_chunk <= kQtab) { m->psd_v2 = true; m->psd_smem = sm2; }
+            // (+ 2 KB: the kernel's static shared memory and the 1 KB the system reserves per CTA count against the same limit)
+            if ((int64_t)sm2 + 2048 <= ctx->max_smem_optin && m->psd_chunk <= kQtab) { m->psd_v2 = true; m->psd_smem = sm2; }
         }
         if (!m->psd_v2) {
             m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len);
-            if ((int64_t)m->psd_smem > ctx->max_smem_optin) {
+            if ((int64_t)m->psd_smem + 2048 > ctx->max_smem_optin) {
                 // many selected bins (e.g. fs = 250 Hz: 80 % of 16 384): keep the per-particle bin sums in global memory
                 m->psd_smem = abc_psd_smem_bytes((int)d.n_t, m->n2, (int)d.n_stats, &m->psd_chunk, &m->psd_xs_len, false);
                 m->psd_accb_global = true;
             }
-            if ((int64_t)m->psd_smem > ctx->max_smem_optin || m->psd_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
+            if ((int64_t)m->psd_smem + 2048 > ctx->max_smem_optin || m->psd_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "PSD FFT does not fit in shared memory (n_t too large)"); }
         }
         // window padded with zeros to the simulate buffer (k_abc_psd2 multiplies inside the simulator, 16 bytes at a time)
         std::vector<float> win((size_t)std::max<int64_t>(d.n_t + 1, m->psd_xs_len) + 4, 0.0f);
@@ -293,7 +294,7 @@ int itjl_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** m
         for (int64_t i = 0; i < d.n_stats; ++i)
             if (d.freq_bins[i] < 0 || d.freq_bins[i] >= nfft / 2) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "freq_bins out of range"); }
         m->pg_smem = abc_pgram_smem_bytes((int)d.n_t, nfft, (int)d.n_stats, &m->pg_chunk, &m->pg_bufb);
-        if ((int64_t)m->pg_smem > ctx->max_smem_optin || m->pg_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "periodogram FFT does not fit in shared memory (n_t too large)"); }
+        if ((int64_t)m->pg_smem + 2048 > ctx->max_smem_optin || m->pg_chunk > kQtab) { itjl_model_destroy(m); return fail(ctx, ITJL_ERR_ARG, "periodogram FFT does not fit in shared memory (n_t too large)"); }
         std::vector<float> win((size_t)d.n_t);
         std::vector<float2> roots((size_t)roots_two_level_entries(nfft));
         std::vector<int32_t> bins((size_t)d.n_stats);

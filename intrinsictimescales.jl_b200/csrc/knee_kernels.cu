@@ -72,13 +72,14 @@ __device__ __forceinline__ double l1_objective(const double* __restrict__ y, con
 }
 
 // Nelder-Mead (reflection 1, expansion 2, contraction 1/2, shrink 1/2), run redundantly by every thread of the CTA on
-// identical values; three rounds with initial simplex steps step, step / 10, step / 100 from the best point so far.
+// identical values; five rounds with initial simplex steps step, step / 10, ... step / 10^4 from the best point so far
+// (a kinked L1 objective can stall a simplex: restarts from the best point get it moving again).
 template <int MODEL, int ND>
 __device__ void nelder_mead(const double* y, const double* f, int n, double* x, const double* step, double f_hi, KneeShared* sh) {
     double best[ND], fbest = 0.0;
     for (int d = 0; d < ND; ++d) best[d] = x[d];
-    for (int round = 0; round < 3; ++round) {
-        const double sc = round == 0 ? 1.0 : (round == 1 ? 0.1 : 0.01);
+    for (int round = 0; round < 5; ++round) {
+        const double sc = round == 0 ? 1.0 : (round == 1 ? 0.1 : (round == 2 ? 0.01 : (round == 3 ? 1e-3 : 1e-4)));
         double P[ND + 1][ND], F[ND + 1];
         for (int v = 0; v <= ND; ++v) {
             for (int d = 0; d < ND; ++d) P[v][d] = best[d] + ((v == d + 1) ? sc * step[d] : 0.0);

@@ -83,3 +83,27 @@ def test_psd2_plain_ou_kind_and_many_trials(pkg, ctx):
         ws = omodels.summary_stats(om, x)
         assert np.max(np.abs(stats[i] - ws)) <= 1e-5 * ws.max()
         assert abs(got[i] - omodels.distance_function(om, ws, om.data_sum_stats)) <= 3e-4 * got[i]
+
+
+@pytest.mark.parametrize("n_t,hi", [(15642, 0.49), (16384, 0.49), (9000, 0.49)])
+def test_large_trials_with_a_wide_band_fit_or_fall_back(pkg, ctx, n_t, hi):
+    """Shapes at the shared-memory limit (found by benchmarks/psd_fuzz.py: n_t = 15642 with 16 040 selected bins was
+    accepted by itjl_model_create and then refused by the launch - the static shared memory and the per-CTA reserve were
+    not counted): the model either runs k_abc_psd2 or falls back to k_abc_psd with its bin sums in global memory, and a
+    refused launch must not poison the next call."""
+    from oracle import cport
+    fs = 1000.0
+    dt = 1 / fs
+    t = dt * np.arange(1, n_t + 1)
+    data = oou.generate_ou_with_oscillation([0.05, 10.0, 0.9], dt, n_t * dt, 2, 0.0, 1.0, seed=1, n_t=n_t)
+    po = [omodels.Normal(.1, .1), omodels.Normal(10, 5), omodels.Uniform(0, 1)]
+    pp = [pkg.Normal(.1, .1), pkg.Normal(10, 5), pkg.Uniform(0, 1)]
+    om = omodels.one_timescale_and_osc_model(data, t, prior=po, summary_method="psd", freqlims=(0.5, hi * fs))
+    gm = pkg.one_timescale_and_osc_model(data, t, "abc", prior=pp, summary_method="psd", freqlims=(0.5, hi * fs))
+    theta = np.array([[0.05, 10.0, 0.9], [0.1, 12.0, 0.5]])
+    want, ws = cport.abc_distances(om, theta, seed=1, generation=1, return_stats=True)
+    got, gs = gm.gpu_model(ctx).distances(theta, seed=1, generation=1, return_stats=True)
+    assert np.max(np.abs(gs - ws) / ws.max(axis=1, keepdims=True)) <= 1e-5
+    assert np.all(np.abs(got - want) <= 1e-3 * want)
+    x = np.random.default_rng(0).standard_normal((2, 500))
+    assert np.all(np.isfinite(pkg.summary.comp_psd(x, fs, ctx=ctx)[0]))          # the context is still healthy
