@@ -363,9 +363,10 @@ cudaError_t combine_launch(double* dist, int64_t n, const double* fit, int is_kn
 // ---- fit_expdecay_3_parameters (reference src/utils/utils.jl:85-91, 159-179) ------------------------------------------
 // A (exp(-t / tau) + B) fitted to acf[2:end] over lags[2:end] (the zero lag is skipped: acw(...; skip_zero_lag = true)),
 // residual = mean squared error.  For a given tau the model is linear in (A, A B), so the best pair is the closed-form
-// 2 x 2 least-squares solution and the objective becomes a function of log tau alone, minimised by the same
-// deterministic Nelder-Mead (one dimension) from the reference's initial guess tau0 = tau_from_acw50(acw50(lags, acf))
-// (1.0 when the ACF never falls to 0.5).  Returns the argmin of the reference's objective; its LM may stop elsewhere
+// 2 x 2 least-squares solution and the objective becomes a function of log tau alone, minimised around the reference's
+// initial guess tau0 = tau_from_acw50(acw50(lags, acf)) (1.0 when the ACF never falls to 0.5) by a 65-point log scan of
+// tau0 / 32 .. 32 tau0 and a golden-section search (a noisy ACF gives this function more than one dip: a local 1-D
+// simplex and SciPy's Brent stopped in different ones, benchmarks/api_fuzz.py).  Returns the argmin of the reference's objective; its LM may stop elsewhere
 // (unpinned) and returns NaN for a negative tau, which the log parametrisation cannot produce.
 struct Exp3Sums { double se, see, sy, sey, syy; };
 
@@ -407,26 +408,24 @@ __global__ void __launch_bounds__(kKneeThreads) k_expdecay3_fit(const double* __
         const double tau0 = first == 0x7fffffff ? 1.0 : lags[first] / 0.6931471805599453;       // tau_from_acw50
         double tau = NAN;
         if (bad == 0.0 && n_lags >= 4 && tau0 > 0.0) {
-            // one-dimensional Nelder-Mead = interval halving with reflection / expansion; three rounds as for the knee
-            double x = log(tau0), fx = exp3_objective(acf + 1, lags + 1, n_lags - 1, x, &sh);
-            for (int round = 0; round < 3; ++round) {
-                double h = round == 0 ? 0.25 : (round == 1 ? 0.025 : 0.0025);
-                double x1 = x + h, f1 = exp3_objective(acf + 1, lags + 1, n_lags - 1, x1, &sh);
-                for (int it = 0; it < 400; ++it) {
-                    // (x, fx) best, (x1, f1) other
-                    if (f1 < fx) { const double tx = x, tf = fx; x = x1; fx = f1; x1 = tx; f1 = tf; }
-                    if (fabs(x1 - x) < 1e-12) break;
-                    const double xr = x + (x - x1), fr = exp3_objective(acf + 1, lags + 1, n_lags - 1, xr, &sh);
-                    if (fr < fx) {
-                        const double xe = x + 2.0 * (x - x1), fe = exp3_objective(acf + 1, lags + 1, n_lags - 1, xe, &sh);
-                        if (fe < fr) { x1 = x; f1 = fx; x = xe; fx = fe; } else { x1 = x; f1 = fx; x = xr; fx = fr; }
-                    } else {
-                        const double xc = x + 0.5 * (x1 - x), fc = exp3_objective(acf + 1, lags + 1, n_lags - 1, xc, &sh);
-                        x1 = xc; f1 = fc;
-                    }
-                }
-                if (f1 < fx) { x = x1; fx = f1; }
+            // the objective in log tau can have more than one dip: scan tau0 / 32 .. 32 tau0 on 65 log-spaced points
+            // (first minimum on ties), then golden-section search between the neighbours of the best one
+            const double* yy = acf + 1; const double* tt = lags + 1; const int m = n_lags - 1;
+            const double x0 = log(tau0), span = log(32.0), dx = span / 32.0;
+            int bi = 0; double bf = INFINITY;
+            for (int i = 0; i < 65; ++i) {
+                const double fv = exp3_objective(yy, tt, m, x0 - span + i * dx, &sh);
+                if (fv < bf) { bf = fv; bi = i; }
             }
+            double lo = x0 - span + (bi - 1) * dx, hi = x0 - span + (bi + 1) * dx;
+            const double gr = 0.6180339887498949;
+            double c1 = hi - gr * (hi - lo), c2 = lo + gr * (hi - lo);
+            double f1 = exp3_objective(yy, tt, m, c1, &sh), f2 = exp3_objective(yy, tt, m, c2, &sh);
+            for (int it = 0; it < 70; ++it) {
+                if (f1 < f2) { hi = c2; c2 = c1; f2 = f1; c1 = hi - gr * (hi - lo); f1 = exp3_objective(yy, tt, m, c1, &sh); }
+                else { lo = c1; c1 = c2; f1 = f2; c2 = lo + gr * (hi - lo); f2 = exp3_objective(yy, tt, m, c2, &sh); }
+            }
+            const double x = 0.5 * (lo + hi);
             tau = exp(x);
         }
         if (tid == 0) tau_out[r] = tau;

@@ -227,8 +227,8 @@ def fit_expdecay_3_parameters(lags, acf):
     """utils.jl:159-179: A (exp(-t / tau) + B) fitted to acf[2:end] over lags[2:end] with the scalar residual mean(abs2(.)),
     from u0 = [0.5, tau_from_acw50(acw50(lags, acf)), 0] ([0.5, 1, 0] when the ACF never falls to 0.5); tau < 0 -> NaN.
     NonlinearSolve's LM is not restated: this returns the argmin of the same objective (for a fixed tau the best
-    (A, A B) is a closed-form linear least-squares pair; the remaining 1-D problem in log tau is minimised by SciPy's
-    bounded Brent search around the initial guess and polished by least_squares).  PARITY UNPINNED."""
+    (A, A B) is a closed-form linear least-squares pair; the remaining 1-D problem in log tau is minimised over
+    tau0 / 32 .. 32 tau0 by a 65-point log scan + golden section).  PARITY UNPINNED."""
     from scipy import optimize
     lags = np.asarray(lags, dtype=np.float64); acf = np.asarray(acf, dtype=np.float64)
     a50 = acw50(lags, acf)
@@ -243,15 +243,21 @@ def fit_expdecay_3_parameters(lags, acf):
         coef, *_ = np.linalg.lstsq(A, y, rcond=None)
         r = A @ coef - y
         return float(np.mean(r * r))
-    # local search from the initial guess, widening the bracket while the minimum sits on its edge
-    x = math.log(tau0)
-    h = 0.25
-    for _ in range(60):
-        r = optimize.minimize_scalar(reduced, bounds=(x - h, x + h), method="bounded", options={"xatol": 1e-12})
-        moved = abs(r.x - x)
-        x = r.x
-        if moved < 0.9 * h:
-            h *= 0.25
-            if h < 1e-9:
-                break
-    return float(math.exp(x))
+    # the objective in log tau can have more than one dip: scan tau0 / 32 .. 32 tau0 on 65 log-spaced points, then
+    # golden-section search between the neighbours of the best one (the same procedure as csrc/knee_kernels.cu)
+    x0, span = math.log(tau0), math.log(32.0)
+    grid = [x0 - span + i * (span / 32.0) for i in range(65)]
+    vals = [reduced(g) for g in grid]
+    i = int(np.argmin(vals))
+    lo, hi = x0 - span + (i - 1) * (span / 32.0), x0 - span + (i + 1) * (span / 32.0)
+    gr = 0.6180339887498949
+    c1, c2 = hi - gr * (hi - lo), lo + gr * (hi - lo)
+    f1, f2 = reduced(c1), reduced(c2)
+    for _ in range(70):
+        if f1 < f2:
+            hi, c2, f2 = c2, c1, f1
+            c1 = hi - gr * (hi - lo); f1 = reduced(c1)
+        else:
+            lo, c1, f1 = c1, c2, f2
+            c2 = lo + gr * (hi - lo); f2 = reduced(c2)
+    return float(math.exp(0.5 * (lo + hi)))

@@ -66,6 +66,64 @@ def lorentzian_objective(psd, freqs, u):
     return float(np.mean(np.abs(lorentzian(freqs, u) - psd)))
 
 
+def _nelder_mead_spec(fun, x0, step, rounds=5, max_iter=600):
+    """The deterministic Nelder-Mead search the device kernel runs (csrc/knee_kernels.cu::nelder_mead), restated step by
+    step: reflection 1, expansion 2, contraction 1/2, shrink 1/2; `rounds` restarts from the best point with start
+    simplices step, step / 10, ...; stops when the simplex is smaller than 1e-9 with a flat objective or smaller than
+    1e-13.  Used where the objective is multimodal (the Gaussian fit of a noisy residual): there "the argmin reached from
+    the initial guess" is only defined together with the search that reaches it."""
+    nd = len(x0)
+    best = np.array(x0, dtype=np.float64)
+    fbest = None
+    for rnd in range(rounds):
+        sc = 10.0 ** (-rnd)
+        P = np.array([best + (sc * step[v - 1] * np.eye(nd)[v - 1] if v else 0.0) for v in range(nd + 1)])
+        F = np.array([fun(p) for p in P])
+        if rnd == 0:
+            fbest = F[0]
+        for _ in range(max_iter):
+            lo = hi = 0
+            for v in range(1, nd + 1):
+                if F[v] < F[lo]:
+                    lo = v
+                if F[v] > F[hi]:
+                    hi = v
+            nh = lo
+            for v in range(nd + 1):
+                if v != hi and F[v] > F[nh]:
+                    nh = v
+            size = float(np.max(np.abs(P - P[lo])))
+            if (not (F[hi] - F[lo] > 1e-15 * abs(F[lo])) and size < 1e-9) or size < 1e-13:
+                break
+            c = (P.sum(axis=0) - P[hi]) / nd
+            xr = c + (c - P[hi])
+            fr = fun(xr)
+            if fr < F[lo]:
+                xe = c + 2.0 * (c - P[hi])
+                fe = fun(xe)
+                if fe < fr:
+                    P[hi], F[hi] = xe, fe
+                else:
+                    P[hi], F[hi] = xr, fr
+            elif fr < F[nh]:
+                P[hi], F[hi] = xr, fr
+            else:
+                outside = fr < F[hi]
+                xc = c + 0.5 * (xr - c) if outside else c + 0.5 * (P[hi] - c)
+                fc = fun(xc)
+                if fc < (fr if outside else F[hi]):
+                    P[hi], F[hi] = xc, fc
+                else:
+                    for v in range(nd + 1):
+                        if v != lo:
+                            P[v] = P[lo] + 0.5 * (P[v] - P[lo])
+                            F[v] = fun(P[v])
+        lo = int(np.argmin(F))
+        if F[lo] <= fbest:
+            fbest, best = F[lo], P[lo].copy()
+    return best, fbest
+
+
 def _nelder_mead(fun, x0, step):
     best = None
     x = np.asarray(x0, dtype=np.float64)
@@ -94,7 +152,10 @@ def find_knee_frequency(psd, freqs, min_freq=None, max_freq=None):
     fhi = float(freqs.max())
     fun = lambda x: lorentzian_objective(psd, freqs, [math.exp(x[0]), min(math.exp(x[1]), fhi)])
     x, fx = _nelder_mead(fun, [math.log(u0[0]), math.log(u0[1])], [0.1, 0.1])
-    x = [x[0], min(x[1], math.log(fhi))]
+    if x[1] >= math.log(fhi):
+        # the search ended on the clamp: "when the knee frequency is not detected, the algorithm just returns the maximum
+        # frequency" (test_utils.jl:69-73) - no polish back into the band
+        return [math.exp(x[0]), fhi]
     # polish: exact amplitude for the knee found, then a bounded 1-D search over log knee around it
     def inner(lk):
         g = 1.0 / (1.0 + (freqs / math.exp(lk)) ** 2)
@@ -138,8 +199,11 @@ def gaussian_initial_guess(psd, freqs, initial_peak, min_freq, max_freq):
     return [float(amp), float(initial_peak), float(sd)]
 
 
-def fit_gaussian(psd, freqs, initial_peak, min_freq=None, max_freq=None):
-    """utils.jl:813-838 -> [amplitude, centre, sd]: argmin of mean |gaussian - psd| from the reference's initial guess."""
+def fit_gaussian(psd, freqs, initial_peak, min_freq=None, max_freq=None, independent=False):
+    """utils.jl:813-838 -> [amplitude, centre, sd]: argmin of mean |gaussian - psd| from the reference's initial guess.
+    The residual of a noisy spectrum makes this objective multimodal, so the search is part of the definition: by default
+    the specified Nelder-Mead (_nelder_mead_spec, what the device runs); `independent = True` uses SciPy's instead (the
+    two agree on clean peaks, tests/test_oracle_knee_kats.py)."""
     psd = np.asarray(psd, dtype=np.float64); freqs = np.asarray(freqs, dtype=np.float64)
     min_freq = freqs[0] if min_freq is None else min_freq
     max_freq = freqs[-1] if max_freq is None else max_freq
@@ -147,14 +211,22 @@ def fit_gaussian(psd, freqs, initial_peak, min_freq=None, max_freq=None):
     if not (u0[2] > 0 and np.isfinite(u0[0])):
         return [float("nan")] * 3
     fun = lambda x: float(np.mean(np.abs(gaussian(freqs, [x[0], x[1], math.exp(x[2])]) - psd)))
-    x, _ = _nelder_mead(fun, [u0[0], u0[1], math.log(u0[2])], [0.1 * abs(u0[0]) + 1e-300, 0.5 * u0[2], 0.1])
+    start, step = [u0[0], u0[1], math.log(u0[2])], [0.1 * abs(u0[0]) + 1e-300, 0.5 * u0[2], 0.1]
+    if independent:
+        x, _ = _nelder_mead(fun, start, step)
+    else:
+        x, _ = _nelder_mead_spec(fun, start, step)
     return [float(x[0]), float(x[1]), float(math.exp(x[2]))]
 
 
 def fooof_fit(psd, freqs, min_freq=None, max_freq=None, oscillation_peak=True, max_peaks=3, return_only_knee=True):
     """utils.jl:598-675 (return_only_knee = true is what acw uses, acw.jl:258-266).
-    Deviation: with oscillation_peak = true and NO peak found the reference hits `return knee, ...` with `knee`
-    undefined (UndefVarError, :651); the knee of the first fit is returned here."""
+    Deviations: (1) with oscillation_peak = true and NO peak found the reference hits `return knee, ...` with `knee`
+    undefined (UndefVarError, :651); the knee of the first fit is returned here.  (2) A residual peak that lies below
+    zero gives fit_gaussian a zero-width initial guess (utils.jl:821-830: the peak bin itself is <= half its negative
+    height), whose Gaussian is 0/0 at the peak bin - the reference hands NaN residuals to the solver and what comes
+    back depends on the solver; here (and on the device) such a peak ends the peak loop and the peaks found so far are
+    used."""
     psd = np.asarray(psd, dtype=np.float64); freqs = np.asarray(freqs, dtype=np.float64)
     min_freq = freqs[0] if min_freq is None else min_freq
     max_freq = freqs[-1] if max_freq is None else max_freq
@@ -170,6 +242,8 @@ def fooof_fit(psd, freqs, min_freq=None, max_freq=None, oscillation_peak=True, m
         if math.isnan(pf):
             break
         g = fit_gaussian(resid, f, pf, min_freq, max_freq)
+        if math.isnan(g[0]):
+            break
         peaks.append(g)
         resid = resid - gaussian(f, g)
     if not peaks:
