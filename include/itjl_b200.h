@@ -371,6 +371,11 @@ int itjl_acw_resident(itjl_ctx* ctx, double fs, uint32_t typemask, int32_t avera
  * acf is (n_rows x n_lags) column-major; tau_out has n_rows entries. */
 int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt,
                       double* tau_out);
+/* fit_expdecay_3_parameters(lags, acf; dims = 2) (reference src/utils/utils.jl:159-192; what
+ * acw(...; skip_zero_lag = true) runs, acw.jl:212-216): A (exp(-t / tau) + B) fitted to acf[:, 2:end] over
+ * lags[2:end] = dt, 2 dt, ...; same layout as itjl_fit_expdecay; NaN for a row holding a non-finite value. */
+int itjl_fit_expdecay_3_parameters(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt,
+                                   double* tau_out);
 
 /* ---- measurement helpers ---------------------------------------------------------- */
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator of the fused simulate+ACF

@@ -19,7 +19,10 @@ from .models import (Normal, Uniform, TimescaleModel, check_model_inputs, distan
                      one_timescale_and_osc_with_missing_model,
                      one_timescale_model, one_timescale_with_missing_model, summary_stats)
 from .ou import generate_ou_process, generate_ou_with_oscillation, generate_two_timescale
-from .summary import comp_ac_fft, comp_ac_time_missing, comp_psd_adfriendly
-from .utils import acw0, acw50, acweuler, expdecay, fit_expdecay, tau_from_acw50
+from .summary import (comp_ac_fft, comp_ac_time_missing, comp_psd, comp_psd_adfriendly, comp_psd_lombscargle,
+                      lombscargle_autofrequency, nextfastfft)
+from .utils import (acw0, acw50, acw50_analytical, acweuler, expdecay, find_knee_frequency, find_oscillation_peak,
+                    fit_expdecay, fit_expdecay_3_parameters, fooof_fit, knee_from_tau, lorentzian,
+                    lorentzian_initial_guess, tau_from_acw50, tau_from_knee)
 
 __version__ = "0.1.0"

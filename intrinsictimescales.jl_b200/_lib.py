@@ -78,6 +78,7 @@ SIGNATURES = {
     "itjl_psd_hamming": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
     "itjl_acw": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "itjl_fit_expdecay": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
+    "itjl_fit_expdecay_3_parameters": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
     "itjl_model_kernel_info": (ctypes.c_int, [_vp, _vp, _vp]),
     "itjl_tc_plan": (ctypes.c_int, [_i64, _i64, _i64, _i32, _i32, _vp]),
     "itjl_fp32_peak": (ctypes.c_int, [_vp, _i32, _vp]),

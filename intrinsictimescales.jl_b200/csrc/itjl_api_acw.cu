@@ -551,6 +551,32 @@ int itjl_fit_expdecay(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t 
     return ITJL_OK;
 }
 
+int itjl_fit_expdecay_3_parameters(itjl_ctx* ctx, const double* acf, int64_t n_rows, int64_t n_lags, double dt, double* tau_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_fit_expdecay_3_parameters: null context");
+    if (!acf || !tau_out || n_rows < 1 || n_lags < 1 || n_lags > INT32_MAX || !(dt > 0.0))
+        return fail(ctx, ITJL_ERR_ARG, "itjl_fit_expdecay_3_parameters: invalid argument");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // device layout: [n_rows][n_lags] rows, then the lag axis
+    std::vector<double> rows((size_t)(n_rows + 1) * n_lags);
+    for (int64_t r = 0; r < n_rows; ++r)
+        for (int64_t k = 0; k < n_lags; ++k) rows[(size_t)r * n_lags + k] = acf[r + k * n_rows];
+    for (int64_t k = 0; k < n_lags; ++k) rows[(size_t)n_rows * n_lags + k] = (double)k * dt;
+    ITJL_CUDA(ctx, ctx->out.reserve(rows.size() * sizeof(double)));
+    ITJL_CUDA(ctx, ctx->out3.reserve((size_t)n_rows * sizeof(double)));
+    ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out.p, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const double* d_rows = (const double*)ctx->out.p;
+    cudaError_t e = expdecay3_launch(d_rows, n_rows, n_lags, (int)n_lags, d_rows + (size_t)n_rows * n_lags, (double*)ctx->out3.p,
+                                     (int)std::min<int64_t>(n_rows, (int64_t)ctx->sm_count * 8), ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_expdecay3_fit: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ITJL_CUDA(ctx, cudaMemcpyAsync(tau_out, ctx->out3.p, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
+
 }  // extern "C"
 
 // acw() on the matrix in ctx->data (n_slices x n_t, slice index fastest); `data` != null: upload it first

@@ -53,7 +53,7 @@ def expdecay(tau, lags):
     return np.exp(-(1.0 / tau) * np.asarray(lags, dtype=np.float64))
 
 
-def fit_expdecay(lags, acf, ctx=None):
+def fit_expdecay(lags, acf, ctx=None, _entry="itjl_fit_expdecay"):
     """utils.jl:113-138: timescale of exp(-lags/tau) fitted to `acf` (vector -> scalar,
     (rows, lags) matrix -> vector).  `lags` must be uniformly spaced from 0."""
     lags = np.asarray(lags, dtype=np.float64)
@@ -68,8 +68,14 @@ def fit_expdecay(lags, acf, ctx=None):
         raise ValueError("fit_expdecay on the GPU path needs lags = (0:n-1)*dt")
     ctx = ctx or _lib.default_context()
     out = np.empty(n_rows, dtype=np.float64)
-    ctx.check(_lib.lib().itjl_fit_expdecay(ctx.handle, _lib.ptr(rows), n_rows, n_lags, dt, _lib.ptr(out)))
+    ctx.check(getattr(_lib.lib(), _entry)(ctx.handle, _lib.ptr(rows), n_rows, n_lags, dt, _lib.ptr(out)))
     return float(out[0]) if vec else out
+
+
+def fit_expdecay_3_parameters(lags, acf, ctx=None):
+    """utils.jl:159-192: tau of A (exp(-t / tau) + B) fitted to acf[2:end] over lags[2:end] (what
+    acw(...; skip_zero_lag = true) uses); vector -> scalar, (rows, lags) matrix -> vector."""
+    return fit_expdecay(lags, acf, ctx=ctx, _entry="itjl_fit_expdecay_3_parameters")
 
 
 # ---- PSD-side reducers (utils.jl:197-198, 359-361, 423-765) ------------------------------------------

@@ -1,4 +1,4 @@
-"""Oracle: the `acw()` front end on (trials, time) data, ACF-based acwtypes only.
+"""Oracle: the `acw()` front end on (trials, time) data.
 
 Follows /root/reference/src/core/acw.jl:109-307 (dims = last, trial_dims = 1):
   complete data -> comp_ac_fft, all n lags           :145-146
@@ -9,26 +9,53 @@ Follows /root/reference/src/core/acw.jl:109-307 (dims = last, trial_dims = 1):
   :auc window = floor(Int, acw0_sample[1]) of the FIRST slice   :192-201
   n_lags = ceil(Int, 1.1 * nanmaximum(acw0_sample)) or n        :203-210
   :tau on acf[:, 1:n_lags]                           :212-231
-`:knee` (FOOOF) is out of scope.
+  :knee: comp_psd (complete) / comp_psd_lombscargle on dt:dt:n dt (NaN data), mean over trials,
+         tau_from_knee(fooof_fit(...; min_freq, max_freq = freqlims, return_only_knee = true))   :242-270
 """
 import math
 
 import numpy as np
 
-from . import acwred, summary
+from . import acwred, knee, summary
 
 ACF_ACWTYPES = ("acw0", "acw50", "acweuler", "auc", "tau")
 
 
-def acw(data, fs, acwtypes=ACF_ACWTYPES, n_lags=None, average_over_trials=False, skip_zero_lag=False):
+def acw_knee(data, fs, freqlims=None, average_over_trials=False, oscillation_peak=True, max_peaks=1):
+    """acw.jl:242-270 on (trials, time) data -> (tau per slice, psd, freqs)."""
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        data = data.reshape(1, -1)
+    dt = 1.0 / fs
+    mask = np.isnan(data)
+    if mask.any():
+        psd, freqs = summary.comp_psd_lombscargle(dt * np.arange(1, data.shape[1] + 1), data, mask, dt)
+    else:
+        psd, freqs = summary.comp_psd_periodogram(data, fs)
+    if average_over_trials:
+        psd = psd.mean(axis=0, keepdims=True)
+    lo, hi = (freqs[0], freqs[-1]) if freqlims is None else freqlims
+    tau = np.array([knee.tau_from_knee(knee.fooof_fit(p, freqs, lo, hi, oscillation_peak, max_peaks, True)) for p in psd])
+    return tau, psd, freqs
+
+
+def acw(data, fs, acwtypes=ACF_ACWTYPES, n_lags=None, average_over_trials=False, skip_zero_lag=False, freqlims=None,
+        oscillation_peak=True, max_peaks=1):
     data = np.asarray(data, dtype=np.float64)
     if data.ndim == 1:
         data = data.reshape(1, -1)                      # acw.jl:122-125
     if isinstance(acwtypes, str):
         acwtypes = (acwtypes,)
     for t in acwtypes:
-        if t not in ACF_ACWTYPES:
+        if t not in ACF_ACWTYPES + ("knee",):
             raise ValueError(f"unsupported acwtype {t!r}")
+    if "knee" in acwtypes:
+        tau, psd, freqs = acw_knee(data, fs, freqlims, average_over_trials, oscillation_peak, max_peaks)
+        if tuple(acwtypes) == ("knee",):
+            return {"knee": tau, "psd": psd, "freqs": freqs}
+        rest = acw(data, fs, [t for t in acwtypes if t != "knee"], n_lags, average_over_trials, skip_zero_lag)
+        rest.update(knee=tau, psd=psd, freqs=freqs)
+        return rest
     dt = 1.0 / fs
     n = data.shape[1]
     iscomplete = not np.isnan(data).any()

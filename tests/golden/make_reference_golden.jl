@@ -24,11 +24,18 @@
 #   weighted_covar           src/core/abc.jl:582-613
 #   effective_sample_size    src/core/abc.jl:632-642
 #   linear_distance / logarithmic_distance  src/stats/distances.jl:29-53
+#   comp_psd_lombscargle     src/stats/summary.jl:315-360       (LombScargle.jl, autofrequency grid)
+#   lorentzian_initial_guess / find_knee_frequency / find_oscillation_peak / fooof_fit
+#                            src/utils/utils.jl:423-445, 479-538, 721-765, 598-675
+#   tau_from_knee / knee_from_tau            src/utils/utils.jl:197-198
+#   fit_expdecay_3_parameters                src/utils/utils.jl:159-192
+#   acw(:knee) / acw(:tau; skip_zero_lag)    src/core/acw.jl:212-216, 242-270
 
 using IntrinsicTimescales
 import IntrinsicTimescales.ABC as ABCmod
 import Distributions
 import StatsBase
+import Statistics
 
 const HERE = @__DIR__
 const INDIR = joinpath(HERE, "reference_inputs_v1")
@@ -70,6 +77,7 @@ function emit(key::String, value)
 end
 
 nan_if_nothing(x) = x === nothing ? NaN : x
+as_array(v) = v isa Number ? [Float64(v)] : Float64.(collect(v))
 
 function main()
     inp = load_inputs()
@@ -128,6 +136,37 @@ function main()
     emit("calc_weights_2param", w_new)
     emit("weighted_covar", weighted_covar(inp["theta_new"], w_new))
     emit("effective_sample_size", effective_sample_size(w_new))
+
+    # ---- PSD side: Lomb-Scargle, knee / peak / FOOOF fits, knee-based acw, 3-parameter decay ----
+    times = collect(DT:DT:(size(xm, 2) * DT))
+    ls_power, ls_freqs = comp_psd_lombscargle(times, xm, isnan.(xm), DT)
+    emit("comp_psd_lombscargle_power", ls_power)
+    emit("comp_psd_lombscargle_freqs", collect(ls_freqs))
+    pc, fc = comp_psd(x, FS)
+    mean_c = vec(Statistics.mean(pc, dims=1))
+    mean_o = vec(Statistics.mean(psd2, dims=1))
+    fo = collect(freqs2)
+    fc = collect(fc)
+    for (ptag, m, f) in (("ou", mean_c, fc), ("osc", mean_o, fo))
+        emit("lorentzian_initial_guess_$(ptag)", lorentzian_initial_guess(m, f; min_freq=f[1], max_freq=f[end]))
+        emit("find_knee_frequency_$(ptag)", find_knee_frequency(m, f; min_freq=f[1], max_freq=f[end]))
+        emit("find_knee_frequency_band_$(ptag)", find_knee_frequency(m, f; min_freq=1.0, max_freq=100.0))
+    end
+    emit("find_oscillation_peak_osc", find_oscillation_peak(mean_o, fo; min_freq=2.0, max_freq=40.0))
+    emit("find_oscillation_peak_none", find_oscillation_peak(collect(1.0 ./ (1.0 .+ (fc ./ 3.0) .^ 2)), fc; min_freq=2.0, max_freq=40.0))
+    emit("fooof_fit_osc_knee", fooof_fit(mean_o, fo; min_freq=1.0, max_freq=100.0, oscillation_peak=true, max_peaks=2,
+                                         return_only_knee=true))
+    emit("fooof_fit_ou_knee_only", fooof_fit(mean_c, fc; min_freq=1.0, max_freq=100.0, oscillation_peak=false,
+                                             return_only_knee=true))
+    emit("tau_from_knee", tau_from_knee([0.5, 3.0, 40.0]))
+    emit("knee_from_tau", knee_from_tau([0.004, 0.05, 0.3]))
+    emit("acw_knee_ou_avg", as_array(acw(copy(x), FS; acwtypes=:knee, average_over_trials=true, oscillation_peak=false).acw_results))
+    emit("acw_knee_osc_avg", acw(copy(xo), FS; acwtypes=:knee, average_over_trials=true, freqlims=(1.0, 100.0),
+                                 oscillation_peak=true, max_peaks=2).acw_results |> as_array)
+    emit("acw_knee_missing_avg", acw(copy(xm), FS; acwtypes=:knee, average_over_trials=true, freqlims=(1.0, 100.0),
+                                     oscillation_peak=false).acw_results |> as_array)
+    emit("fit_expdecay_3_parameters", Float64.(fit_expdecay_3_parameters(lags, acf_rows)))
+    emit("acw_tau_skip_zero_lag", as_array(acw(copy(x), FS; acwtypes=:tau, skip_zero_lag=true).acw_results))
 
     # ---- distances ----
     emit("linear_distance", linear_distance(inp["dist_a"][:], inp["dist_b"][:]))
