@@ -72,7 +72,9 @@ typedef struct {
     int32_t tc_bias;         /* 1 (default): undo the accumulator's round-toward-zero to first order; 0 off */
     int32_t abc_threads;     /* 0 automatic; 128 / 256 threads per CTA of k_abc_acf */
     int32_t abc_bufs;        /* 0 automatic; 1 / 2 trial buffers of k_abc_acf */
-    int32_t acw_stream;      /* 1 (default): acw() starts with the one-read streaming pass; 0: shared-memory kernel only */
+    int32_t acw_stream;      /* 1 (default): acw() starts with the one-read streaming pass over 32 lags; 0: shared-memory
+                                kernel only; 8 / 16 / 32: lags that pass keeps (slices that do not cross zero inside the
+                                window go to the fp64 kernel: a narrower window pays only on short-memory data) */
     int32_t acw_waves;       /* 0 automatic; time segments of the streaming pass sized for this many waves of CTAs */
     int32_t pinned_upload;   /* 1 (default): large host <-> device copies go through the pinned staging ring */
     int32_t copy_threads;    /* 0 automatic (half the hardware threads, at most 8); host threads feeding that ring */
@@ -366,6 +368,12 @@ int itjl_data_upload(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_
 int itjl_acw_resident(itjl_ctx* ctx, double fs, uint32_t typemask, int32_t average_over_trials,
                       int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke, double* auc, double* tau,
                       double* acf_out, int64_t acf_capacity);
+/* ACF matrix of the most recent itjl_acw / _strided / _resident call on this context (the reference's
+ * ACWResults.acf, acw.jl:275-307): n_rows x n_lags, column-major, kept on the device until the next acw call.
+ * n_lags is only known after the call (ceil(1.1 max acw0), acw.jl:203-210): pass acf_out = NULL to those calls,
+ * read the shape here (acf_out = NULL: shape query only), then fetch into an array of exactly that size - a
+ * worst-case n_slices x n_t host buffer costs a first-touch page fault per 4 KB the library writes. */
+int itjl_acw_acf(itjl_ctx* ctx, double* acf_out, int64_t acf_capacity, int64_t* n_rows_out, int64_t* n_lags_out);
 
 /* fit_expdecay(lags, acf; dims = 2) with lags = (0:n_lags-1)*dt  (src/utils/utils.jl:113-138):
  * acf is (n_rows x n_lags) column-major; tau_out has n_rows entries. */

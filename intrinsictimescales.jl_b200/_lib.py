@@ -100,6 +100,7 @@ SIGNATURES = {
                                         _vp, _vp, _i64]),
     "itjl_data_upload": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64]),
     "itjl_acw_resident": (ctypes.c_int, [_vp, _f64, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "itjl_acw_acf": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "itjl_ctx_timing_stop": (ctypes.c_int, [_vp]),
     "itjl_psd_periodogram": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f64, _vp]),
     "itjl_nextfastfft": (_i64, [_i64]),

@@ -175,13 +175,10 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     auc = np.empty(n_out, dtype=np.float64)
     tau = np.empty(n_out, dtype=np.float64)
     nl = ctypes.c_int64(0 if n_lags is None else int(n_lags))
-    # n_lags is only known after the call: reserve the worst case (np.empty only maps
-    # virtual memory; the library writes the first n_out * n_lags entries)
+    # n_lags is only known after the call: the ACF stays on the device and is fetched below into an array of
+    # exactly (n_out, n_lags) (itjl_acw_acf) - a worst-case (n_out x n_t) buffer costs a page fault per 4 KB written
     acf_buf = None
     cap = 0
-    if return_acf:
-        cap = n_out * (int(n_lags) if n_lags is not None else n_t)
-        acf_buf = np.empty(cap, dtype=np.float64)
     # always request acw0: the AUC window and the default n_lags derive from it
     if resident:
         rc = _lib.lib().itjl_acw_resident(ctx.handle, float(fs), mask | _lib.ACW0, int(bool(average_over_trials)),
@@ -195,6 +192,9 @@ def acw(data, fs, acwtypes=None, n_lags=None, dims=None, return_acf=True,
     ctx.check(rc)
     n_lags_used = int(nl.value)
     dt = 1.0 / float(fs)
+    if return_acf:
+        acf_buf = np.empty(n_out * n_lags_used, dtype=np.float64)
+        ctx.check(_lib.lib().itjl_acw_acf(ctx.handle, _lib.ptr(acf_buf), acf_buf.size, None, None))
 
     def as_lag(k):
         return np.where(k >= 0, k.astype(np.float64) * dt, np.nan)

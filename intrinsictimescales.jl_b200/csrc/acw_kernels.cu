@@ -399,7 +399,12 @@ __device__ __forceinline__ double slice_ref(const double* __restrict__ data, int
     return r / (double)m;
 }
 
-__global__ void __launch_bounds__(STREAM_THREADS, 4) k_acw_stream(const AcwStreamParams P) {
+// SKT = lags kept by the pass (8 / 16 / 32): the window, the accumulators and so the registers and the FFMA per
+// sample scale with it - 32 lags: 128 registers, 4 CTAs per SM, 38 instructions per sample; 16 lags: 6 CTAs, 22; 8 lags:
+// 8 CTAs, 14.  Blocks stay 32 samples long for every SKT (k_acw_finish adds the n_t % 32 tail in fp64).
+template <int SKT> struct StreamCfg { static constexpr int kCtas = SKT == 32 ? 4 : (SKT == 16 ? 6 : 8); };
+template <int SKT>
+__global__ void __launch_bounds__(STREAM_THREADS, StreamCfg<SKT>::kCtas) k_acw_stream(const AcwStreamParams P) {
     const int64_t s = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if (s >= P.n_slices) return;
     const int seg = blockIdx.y;
@@ -410,30 +415,31 @@ __global__ void __launch_bounds__(STREAM_THREADS, 4) k_acw_stream(const AcwStrea
     const double ref = slice_ref(P.data, s, P.n_slices, P.n_t);
 
     // fp64 running sums live in shared memory ([lag][thread]: conflict-free), touched every SFLUSH samples
-    __shared__ double acc64[SPART][STREAM_THREADS];
-    float acc[SK], C[SK];
+    __shared__ double acc64[SKT + 1][STREAM_THREADS];
+    float acc[SKT], C[SKT];
 #pragma unroll
-    for (int j = 0; j < SK; ++j) { acc[j] = 0.f; acc64[j][threadIdx.x] = 0.0; }
-    acc64[SK][threadIdx.x] = 0.0;
+    for (int j = 0; j < SKT; ++j) { acc[j] = 0.f; acc64[j][threadIdx.x] = 0.0; }
+    acc64[SKT][threadIdx.x] = 0.0;
     float S = 0.f;
 
-    // window warm-up: C[i] = y_{tb - 32 + i} (zero before the series starts)
+    // window warm-up: C[i] = y_{tb - SKT + i} (zero before the series starts)
+    constexpr int HB = SKT < 16 ? SKT : 16;
 #pragma unroll
-    for (int h = 0; h < SK; h += 16) {
-        double x[16];
+    for (int h = 0; h < SKT; h += HB) {
+        double x[HB];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int t = tb - SK + h + i;
+        for (int i = 0; i < HB; ++i) {
+            const int t = tb - SKT + h + i;
             x[i] = (t >= 0) ? col[(size_t)t * ld] : ref;
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) C[h + i] = (float)(x[i] - ref);       // t < 0: ref - ref = 0
+        for (int i = 0; i < HB; ++i) C[h + i] = (float)(x[i] - ref);       // t < 0: ref - ref = 0
         asm volatile("" ::: "memory");
     }
 
     // whole 32-sample blocks only: the host makes every segment a multiple of 32 samples and
     // k_acw_finish adds the n_t % 32 samples at the end of the series in fp64.
-    // (Tried and dropped, B200: loads issued half a block ahead of the math - 162 registers, 3 CTAs/SM,
+    // (Tried and dropped, B200, SKT = 32: loads issued half a block ahead of the math - 162 registers, 3 CTAs/SM,
     // 116 us - and an extra prefetch.global.L2 96 steps ahead - 122 us - against 111 us for this loop:
     // 38 instructions per sample fill 65 % of the issue slots and 16 resident warps per SM (128 registers per
     // thread) leave DRAM latency exposed - trading registers for load depth loses on both counts.)
@@ -448,25 +454,25 @@ __global__ void __launch_bounds__(STREAM_THREADS, 4) k_acw_stream(const AcwStrea
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float z = (float)(x[i] - ref);
-                C[h + i] = z;                              // (t - tb) & 31 == h + i
+                C[(h + i) & (SKT - 1)] = z;                // (t - tb) mod SKT
                 S += z;
 #pragma unroll
-                for (int j = 0; j < SK; ++j) acc[j] = fmaf(z, C[(h + i - j) & (SK - 1)], acc[j]);
+                for (int j = 0; j < SKT; ++j) acc[j] = fmaf(z, C[(h + i - j) & (SKT - 1)], acc[j]);
             }
             asm volatile("" ::: "memory");                 // keep the next 16 loads behind this half's math
         }
         since_flush += SK;
         if (since_flush >= SFLUSH) {
 #pragma unroll
-            for (int j = 0; j < SK; ++j) { acc64[j][threadIdx.x] += (double)acc[j]; acc[j] = 0.f; }
-            acc64[SK][threadIdx.x] += (double)S; S = 0.f;
+            for (int j = 0; j < SKT; ++j) { acc64[j][threadIdx.x] += (double)acc[j]; acc[j] = 0.f; }
+            acc64[SKT][threadIdx.x] += (double)S; S = 0.f;
             since_flush = 0;
         }
     }
     float* out = P.part + (size_t)seg * SPART * ld + s;
 #pragma unroll
-    for (int j = 0; j < SK; ++j) out[(size_t)j * ld] = (float)(acc64[j][threadIdx.x] + (double)acc[j]);
-    out[(size_t)SK * ld] = (float)(acc64[SK][threadIdx.x] + (double)S);
+    for (int j = 0; j < SKT; ++j) out[(size_t)j * ld] = (float)(acc64[j][threadIdx.x] + (double)acc[j]);
+    out[(size_t)SK * ld] = (float)(acc64[SKT][threadIdx.x] + (double)S);
 }
 
 // Measured and not kept (B200, C2 = randn 10000 x 5000; this kernel: 102 us, 55 % of the measured HBM rate):
@@ -489,6 +495,7 @@ struct AcwFinishParams {
     double* acf_work; int64_t cap;
     int32_t* n_done; int32_t* k0; int32_t* k50; int32_t* ke;
     int32_t* redo;               // [n_slices] 1 = needs the fp64 kernel
+    int w;                       // lags the streaming pass kept (8 / 16 / 32)
 };
 
 // CTA = 32 slices: the segment partials, the first 32 and the last 64 samples of every slice are
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(32 * kFinishWarps) k_acw_finish(const AcwFinis
     const bool col_ok = s0 + lane < P.n_slices;
     for (int r = warp; r < SPART; r += kFinishWarps) {
         double v = 0.0;
-        if (col_ok) {
+        if (col_ok && (r < P.w || r == SK)) {
             const float* src = P.part + (size_t)r * ld + s0 + lane;
             const size_t gs = (size_t)SPART * ld;
             int g = 0;
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(32 * kFinishWarps) k_acw_finish(const AcwFinis
         }
         const double ck = pk - m * (2.0 * S - a - b) + (n - (double)k) * m * m;
         const double c0 = __shfl_sync(0xffffffffu, ck, 0);
-        const bool in_range = k < P.n_t;
+        const bool in_range = k < P.n_t && k < P.w;
         const double v = (k == 0) ? (c0 / c0) : ck / c0;
         if (in_range) P.acf_work[(size_t)s * P.cap + k] = v;
         const unsigned b0 = __ballot_sync(0xffffffffu, in_range && v <= 0.0);
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(32 * kFinishWarps) k_acw_finish(const AcwFinis
         const bool close = fabs(v) < kStreamTol || fabs(v - 0.5) < kStreamTol || fabs(v - kInvE) < kStreamTol;
         const unsigned unsure = __ballot_sync(0xffffffffu, matters && close);
         if (k == 0) {
-            const int kmax = min(SK, P.n_t);
+            const int kmax = min(P.w, P.n_t);
             const bool ill = !(n * m * m <= c0);             // shifted mean still dominates: cancellation
             const bool redo = ill || bad || unsure || (f0 < 0 && kmax < P.n_t);
             P.redo[s] = redo ? 1 : 0;
@@ -611,32 +618,36 @@ static cudaError_t launch_slices(AcfSliceParams& P, int reach, int max_smem, int
 
 cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                              int32_t* ke, int32_t* redo, cudaStream_t st) {
+                              int32_t* ke, int32_t* redo, int w, cudaStream_t st) {
     AcwStreamParams S{};
     S.data = data; S.n_slices = n_slices; S.n_t = n_t; S.n_seg = n_seg; S.seg_len = seg_len;
     S.part = reinterpret_cast<float*>(part);
     dim3 grid((unsigned)((n_slices + STREAM_THREADS - 1) / STREAM_THREADS), (unsigned)n_seg);
     cudaError_t e;
-    k_acw_stream<<<grid, STREAM_THREADS, 0, st>>>(S);
+    if (w == 8) k_acw_stream<8><<<grid, STREAM_THREADS, 0, st>>>(S);
+    else if (w == 16) k_acw_stream<16><<<grid, STREAM_THREADS, 0, st>>>(S);
+    else if (w == 32) k_acw_stream<32><<<grid, STREAM_THREADS, 0, st>>>(S);
+    else return cudaErrorInvalidValue;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AcwFinishParams F{};
     F.data = data; F.n_slices = n_slices; F.n_t = n_t; F.n_seg = n_seg; F.part = reinterpret_cast<const float*>(part);
     F.acf_work = acf_work; F.cap = cap; F.n_done = n_done; F.k0 = k0; F.k50 = k50; F.ke = ke;
-    F.redo = redo;
+    F.redo = redo; F.w = w;
     k_acw_finish<<<(unsigned)((n_slices + 31) / 32), 32 * kFinishWarps, 0, st>>>(F);
     return cudaGetLastError();
 }
 int acw_stream_lags() { return SK; }
 // fp32 partials, counted in doubles for the caller's reserve()
 size_t acw_stream_part_doubles(int64_t n_slices, int n_seg) { return ((size_t)n_seg * SPART * (size_t)n_slices + 1) / 2; }
-void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves) {
+int acw_stream_ctas_per_sm(int w) { return w == 32 ? StreamCfg<32>::kCtas : (w == 16 ? StreamCfg<16>::kCtas : StreamCfg<8>::kCtas); }
+void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves, int w) {
     // The grid is (blocks of 128 slices) x (time segments); 4 CTAs of 128 threads are resident per SM
     // (128 registers per thread).  Pick the segment count whose grid fills whole waves of those slots:
     // cost = waves x (segment length + 32-sample halo); segments are multiples of 32 samples and at least
     // 256 long (each one also writes 33 partial sums per slice).  C2 (10 000 x 5000): 7 segments of 736
     // samples, 553 of 592 slots, one wave (16 segments were 2.13 waves, i.e. three rounds).
-    const long long slots = 4LL * sm_count;
+    const long long slots = (long long)acw_stream_ctas_per_sm(w) * sm_count;
     const long long blocks = (n_slices + 127) / 128;
     const int max_g = n_t / 256 > 0 ? n_t / 256 : 1;
     long long best_cost = -1;

@@ -73,9 +73,16 @@ struct itjl_ctx {
     double timed_ms = 0.0;
     itjl::DevBuf theta, dist, stats, u0, noise, phases, flags, scratch, data, out, out2, out3, part, raw;
     int64_t res_slices = 0, res_nt = 0;   // shape of the matrix itjl_data_upload left in `data` (0: none)
+    itjl::DevBuf acf_keep;                // ACF matrix (rows x lags, column-major) of the last acw call (itjl_acw_acf)
+    int64_t keep_rows = 0, keep_lags = 0;
     // pinned staging ring of the large host -> device uploads (itjl_api_acw.cu)
     void* pin[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pin_ev[3] = {nullptr, nullptr, nullptr};
+    // small device -> host results staged through pinned memory (itjl_api_acw.cu: d2h_queue / d2h_flush)
+    struct PendingCopy { void* dst; size_t off, bytes; };
+    void* pin_small = nullptr;
+    size_t pin_small_used = 0;
+    std::vector<PendingCopy> pending;
 };
 
 namespace itjl {

@@ -43,7 +43,8 @@ int itjl_ctx_set_tuning(itjl_ctx* ctx, const itjl_tuning* t) {
     ITJL_LOCK(ctx);
     if (t->abc_tc < -1 || t->abc_tc > 1 || t->tc_terms < 0 || t->tc_terms > 3 || t->tc_tail_max > 60 || t->tc_groups < 0 ||
         t->tc_groups > 4 || t->tc_seg_trials < 0 || (t->abc_threads != 0 && t->abc_threads != 128 && t->abc_threads != 256) ||
-        t->abc_bufs < 0 || t->abc_bufs > 2 || t->copy_threads < 0 || t->pmc_fp32 < -1 || t->pmc_fp32 > 1 || !(t->tc_error_bound > 0.0))
+        t->abc_bufs < 0 || t->abc_bufs > 2 || t->copy_threads < 0 || t->pmc_fp32 < -1 || t->pmc_fp32 > 1 || !(t->tc_error_bound > 0.0) ||
+        (t->acw_stream != 0 && t->acw_stream != 1 && t->acw_stream != 8 && t->acw_stream != 16 && t->acw_stream != 32))
         return fail(ctx, ITJL_ERR_ARG, "itjl_ctx_set_tuning: value out of range");
     ctx->tuning = *t;
     for (itjl_ctx* sub : ctx->subs) sub->tuning = *t;
@@ -96,13 +97,14 @@ int itjl_ctx_destroy(itjl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->theta, &ctx->dist, &ctx->stats, &ctx->u0, &ctx->noise, &ctx->phases,
-                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3, &ctx->part, &ctx->gather, &ctx->raw};
+                      &ctx->flags, &ctx->scratch, &ctx->data, &ctx->out, &ctx->out2, &ctx->out3, &ctx->part, &ctx->gather, &ctx->raw, &ctx->acf_keep};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 3; ++i) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
         if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]);
     }
+    if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ITJL_OK;

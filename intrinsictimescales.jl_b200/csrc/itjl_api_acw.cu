@@ -83,7 +83,9 @@ static int upload_data(itjl_ctx* ctx, const double* data, int64_t n_slices, int6
 // Device -> host download of a large result (the exported ACF matrix) through the same pinned ring:
 // DMA of chunk c + 1 runs while the host threads copy chunk c out to the caller's pageable array.
 static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
-    if (bytes < 4 * kPinChunk || ctx->tuning.pinned_upload == 0) {
+    // below 256 KB the driver's own pageable path is as quick; above it a pageable cudaMemcpy crawls (the 1.3 MB ACF of
+    // acw() on 10 000 slices: 0.6 ms against 0.1 ms through the pinned ring + one memcpy)
+    if (bytes < ((size_t)256 << 10) || ctx->tuning.pinned_upload == 0) {
         ITJL_CUDA(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         return ITJL_OK;
     }
@@ -101,7 +103,7 @@ static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, si
         return e != cudaSuccess ? e : cudaEventRecord(ctx->pin_ev[c % 3], ctx->stream);
     };
     for (size_t c = 0; c < 2 && c < n_chunks; ++c) ITJL_CUDA(ctx, issue(c));
-    const int n_threads = copy_threads(ctx);
+    const int n_threads = bytes < ((size_t)8 << 20) ? 1 : copy_threads(ctx);      // thread start-up costs more than a small copy
     for (size_t c = 0; c < n_chunks; ++c) {
         if (c + 2 < n_chunks) ITJL_CUDA(ctx, issue(c + 2));      // buffer (c + 2) % 3 was emptied at chunk c - 1
         ITJL_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[c % 3]));
@@ -117,6 +119,30 @@ static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, si
         memcpy(dst + off, stage, part < n ? part : n);
         for (int t = 1; t < n_threads; ++t) workers[t - 1].join();
     }
+    return ITJL_OK;
+}
+
+// Small results (crossing indices, flags, per-slice values): a cudaMemcpyAsync into pageable memory blocks the host
+// for every copy (10-20 us each; acw() makes seven).  d2h_queue copies into a pinned scratch area instead - truly
+// asynchronous - and d2h_flush synchronises the stream once and moves the bytes to their destinations.
+static const size_t kPinSmall = (size_t)2 << 20;
+static int d2h_queue(itjl_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!ctx->pin_small) ITJL_CUDA(ctx, cudaHostAlloc(&ctx->pin_small, kPinSmall, cudaHostAllocDefault));
+    const size_t off = (ctx->pin_small_used + 63) & ~(size_t)63;
+    if (off + bytes > kPinSmall) {
+        ITJL_CUDA(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return ITJL_OK;
+    }
+    ITJL_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(ctx->pin_small) + off, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending.push_back({host_dst, off, bytes});
+    ctx->pin_small_used = off + bytes;
+    return ITJL_OK;
+}
+static int d2h_flush(itjl_ctx* ctx) {
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (const auto& c : ctx->pending) memcpy(c.dst, reinterpret_cast<const char*>(ctx->pin_small) + c.off, c.bytes);
+    ctx->pending.clear();
+    ctx->pin_small_used = 0;
     return ITJL_OK;
 }
 
@@ -584,6 +610,7 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
                     uint32_t typemask, int32_t average_over_trials, int64_t* n_lags_io, int32_t* k0, int32_t* k50,
                     int32_t* ke, double* auc, double* tau, double* acf_out, int64_t acf_capacity) {
     int rc = ITJL_OK;
+    ctx->pending.clear(); ctx->pin_small_used = 0;        // leftovers of a call that failed half way
     if (!n_lags_io) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: n_lags_io is required");
     if (!(fs > 0.0)) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: fs must be positive");
     if ((typemask & ~63u) || typemask == 0) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: No ACW types specified / unknown type bit");
@@ -621,6 +648,7 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
     bool all_streamed = false;       // every slice holds the streaming pass's 32 lags
     int64_t n_redo = 0;              // slices redone by the fp64 kernel (their indices stay in d_list)
     int32_t has_nan = 0;             // some slice has a NaN (the reference then takes comp_ac_time_missing)
+    int stream_w = 0;                // lags kept by the streaming pass of this call (0: not used)
     cudaError_t e;
 
     if (!average_over_trials) {
@@ -633,18 +661,19 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
         const bool use_stream = ctx->tuning.acw_stream != 0 && nt >= 256 && acw_stream_lags() <= reach;
         std::vector<int32_t> h_redo;
         if (use_stream) {
-            // one streaming read of the data: raw lagged products of the first 32 lags
+            // one streaming read of the data: raw lagged products of the first stream_w lags
+            stream_w = ctx->tuning.acw_stream == 8 ? 8 : (ctx->tuning.acw_stream == 16 ? 16 : 32);
             int n_seg = 1, seg_len = nt;
-            acw_stream_segments(nt, n_slices, ctx->sm_count, &n_seg, &seg_len, ctx->tuning.acw_waves);
+            acw_stream_segments(nt, n_slices, ctx->sm_count, &n_seg, &seg_len, ctx->tuning.acw_waves, stream_w);
             ITJL_CUDA(ctx, ctx->part.reserve(acw_stream_part_doubles(n_slices, n_seg) * sizeof(double)));
             e = acw_stream_launch((const double*)ctx->data.p, n_slices, nt, (double*)ctx->part.p, n_seg, seg_len,
-                                  (double*)ctx->out.p, cap, d_done, d_k0, d_k50, d_ke, d_redo, ctx->stream);
+                                  (double*)ctx->out.p, cap, d_done, d_k0, d_k50, d_ke, d_redo, stream_w, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_stream: %s", cudaGetErrorString(e));
             ctx->launches += 2;
             if (ctx->timing) cudaEventRecord(ctx->ev1, ctx->stream);     // the streaming pass (k_acw_stream + k_acw_finish) alone
             h_redo.resize((size_t)n_slices);
-            ITJL_CUDA(ctx, cudaMemcpyAsync(h_redo.data(), d_redo, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            { const int rq = d2h_queue(ctx, h_redo.data(), d_redo, (size_t)n_slices * 4); if (rq != ITJL_OK) return rq; }
+            { const int rq = d2h_flush(ctx); if (rq != ITJL_OK) return rq; }
             std::vector<int32_t> list;
             for (int64_t i = 0; i < n_slices; ++i) if (h_redo[i]) list.push_back((int32_t)i);
             all_streamed = list.empty();
@@ -672,11 +701,14 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
             ctx->timed_ms += ms; ctx->timed_launches++;
         }
-        ITJL_CUDA(ctx, cudaMemcpyAsync(h_k0.data(), d_k0, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ITJL_CUDA(ctx, cudaMemcpyAsync(h_k50.data(), d_k50, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ITJL_CUDA(ctx, cudaMemcpyAsync(h_ke.data(), d_ke, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ITJL_CUDA(ctx, cudaMemcpyAsync(&has_nan, d_nan, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        {
+            int rq = d2h_queue(ctx, h_k0.data(), d_k0, (size_t)n_slices * 4);
+            if (rq == ITJL_OK) rq = d2h_queue(ctx, h_k50.data(), d_k50, (size_t)n_slices * 4);
+            if (rq == ITJL_OK) rq = d2h_queue(ctx, h_ke.data(), d_ke, (size_t)n_slices * 4);
+            if (rq == ITJL_OK) rq = d2h_queue(ctx, &has_nan, d_nan, sizeof(int32_t));
+            if (rq == ITJL_OK) rq = d2h_flush(ctx);
+            if (rq != ITJL_OK) return rq;
+        }
         if (has_nan && user_lags > 0) {
             // NaN data + user n_lags: the reference only computes n_lags lags (acw.jl:151-152)
             for (int64_t i = 0; i < n_slices; ++i) {
@@ -737,9 +769,9 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
     int64_t fill_lags = n_lags;
     if ((typemask & ITJL_AUC) && !has_nan && h_k0[0] > fill_lags) fill_lags = h_k0[0];
     if (!average_over_trials) {
-        if (!(all_streamed && fill_lags <= acw_stream_lags())) {
-            // streamed slices already hold 32 lags: when that is enough only the redone ones need filling
-            const bool only_list = n_redo > 0 && fill_lags <= acw_stream_lags();
+        if (!(all_streamed && fill_lags <= stream_w)) {
+            // streamed slices already hold stream_w lags: when that is enough only the redone ones need filling
+            const bool only_list = n_redo > 0 && fill_lags <= stream_w;
             e = acf_fill_launch((const double*)ctx->data.p, n_slices, nt, 1, (int)fill_lags, (double*)ctx->out.p, cap,
                                 d_done, only_list ? d_list : nullptr, only_list ? n_redo : 0,
                                 ctx->max_smem_optin, ctx->stream);
@@ -774,14 +806,14 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
             e = acw_auc_launch(acf_rows, n_out, acf_ld, w, dt, d_strides, (int)strides.size(), d_auc, ctx->stream);
             if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_auc: %s", cudaGetErrorString(e));
             ctx->launches++;
-            ITJL_CUDA(ctx, cudaMemcpyAsync(auc, d_auc, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            { const int rq = d2h_queue(ctx, auc, d_auc, (size_t)n_out * sizeof(double)); if (rq != ITJL_OK) return rq; }
         }
     }
     if (typemask & ITJL_TAU) {
         e = acw_tau_launch(acf_rows, n_out, acf_ld, (int)n_lags, dt, d_tau, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acw_tau: %s", cudaGetErrorString(e));
         ctx->launches++;
-        ITJL_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        { const int rq = d2h_queue(ctx, tau, d_tau, (size_t)n_out * sizeof(double)); if (rq != ITJL_OK) return rq; }
     }
     std::vector<double> lag_axis;                  // must outlive the async copy
     if (typemask & ITJL_TAU3) {
@@ -794,22 +826,41 @@ static int acw_core(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t
                              (int)std::min<int64_t>(n_out, (int64_t)ctx->sm_count * 8), ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_expdecay3_fit: %s", cudaGetErrorString(e));
         ctx->launches++;
-        ITJL_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        { const int rq = d2h_queue(ctx, tau, d_tau, (size_t)n_out * sizeof(double)); if (rq != ITJL_OK) return rq; }
     }
-    if (acf_out) {
-        if (acf_capacity < n_out * n_lags) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: acf_out capacity too small");
+    // the ACF matrix (n_out x n_lags, column-major) stays on the device for itjl_acw_acf(); acf_out fetches it right away
+    {
+        if (acf_out && acf_capacity < n_out * n_lags) return fail(ctx, ITJL_ERR_ARG, "itjl_acw: acf_out capacity too small");
         const size_t obytes = (size_t)n_out * n_lags * sizeof(double);
-        ITJL_CUDA(ctx, ctx->stats.reserve(obytes));
-        e = acf_export_launch(acf_rows, n_out, acf_ld, (int)n_lags, (double*)ctx->stats.p, ctx->stream);
+        ctx->keep_rows = ctx->keep_lags = 0;
+        ITJL_CUDA(ctx, ctx->acf_keep.reserve(obytes));
+        e = acf_export_launch(acf_rows, n_out, acf_ld, (int)n_lags, (double*)ctx->acf_keep.p, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_acf_export: %s", cudaGetErrorString(e));
         ctx->launches++;
-        { const int rcd = download_large(ctx, acf_out, ctx->stats.p, obytes); if (rcd != ITJL_OK) return rcd; }
+        ctx->keep_rows = n_out; ctx->keep_lags = n_lags;
+        if (acf_out) { const int rcd = download_large(ctx, acf_out, ctx->acf_keep.p, obytes); if (rcd != ITJL_OK) return rcd; }
     }
-    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return ITJL_OK;
+    return d2h_flush(ctx);
 }
 
 extern "C" {
+
+int itjl_acw_acf(itjl_ctx* ctx, double* acf_out, int64_t acf_capacity, int64_t* n_rows_out, int64_t* n_lags_out) {
+    if (!ctx) return fail(nullptr, ITJL_ERR_ARG, "itjl_acw_acf: null context");
+    ITJL_LOCK(ctx);
+    ctx = primary(ctx);
+    ITJL_LOCK(ctx);
+    if (ctx->keep_rows < 1 || ctx->keep_lags < 1) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_acf: no acw result on this context");
+    if (n_rows_out) *n_rows_out = ctx->keep_rows;
+    if (n_lags_out) *n_lags_out = ctx->keep_lags;
+    if (!acf_out) return ITJL_OK;                          // shape query
+    if (acf_capacity < ctx->keep_rows * ctx->keep_lags) return fail(ctx, ITJL_ERR_ARG, "itjl_acw_acf: acf_out capacity too small");
+    ITJL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rc = download_large(ctx, acf_out, ctx->acf_keep.p, (size_t)ctx->keep_rows * ctx->keep_lags * sizeof(double));
+    if (rc != ITJL_OK) return rc;
+    ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ITJL_OK;
+}
 
 int itjl_acw(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double fs, uint32_t typemask,
              int32_t average_over_trials, int64_t* n_lags_io, int32_t* k0, int32_t* k50, int32_t* ke,

@@ -157,10 +157,10 @@ cudaError_t acw_scan_launch(const double* data, int64_t n_slices, int n_t, int m
 // streaming first pass (raw lagged products of the first acw_stream_lags() lags, one read of the data)
 cudaError_t acw_stream_launch(const double* data, int64_t n_slices, int n_t, double* part, int n_seg, int seg_len,
                               double* acf_work, int64_t cap, int32_t* n_done, int32_t* k0, int32_t* k50,
-                              int32_t* ke, int32_t* redo, cudaStream_t st);
+                              int32_t* ke, int32_t* redo, int w, cudaStream_t st);
 int acw_stream_lags();
 size_t acw_stream_part_doubles(int64_t n_slices, int n_seg);
-void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves = 0);
+void acw_stream_segments(int n_t, int64_t n_slices, int sm_count, int* n_seg, int* seg_len, int force_waves = 0, int w = 32);
 cudaError_t acf_fill_launch(const double* data, int64_t n_slices, int n_t, int missing, int need,
                             double* acf_work, int64_t cap, int32_t* n_done, const int32_t* slice_list,
                             int64_t n_list, int max_smem, cudaStream_t st, int32_t* nan_flag = nullptr);

@@ -19,7 +19,7 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ["itjl_ctx_create", "itjl_model_create", "itjl_abc_distances", "itjl_abc_generation",
                  "itjl_abc_accept", "itjl_generate_ou", "itjl_generate_ou_osc", "itjl_acf",
-                 "itjl_acf_missing", "itjl_psd_hamming", "itjl_acw", "itjl_fit_expdecay", "itjl_fit_expdecay_3_parameters",
+                 "itjl_acf_missing", "itjl_psd_hamming", "itjl_acw", "itjl_acw_acf", "itjl_fit_expdecay", "itjl_fit_expdecay_3_parameters",
                  "itjl_last_error", "itjl_fp32_peak"]:
         assert must in syms
 

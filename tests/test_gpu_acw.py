@@ -13,7 +13,7 @@ TYPES = ["acw0", "acw50", "acweuler", "auc", "tau"]
 ACF_VALUE_TOL = 2e-7
 
 
-def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=False, tau_rtol=1e-5):
+def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=False, tau_rtol=1e-5, acf_tol=ACF_VALUE_TOL):
     want = oacw.acw(data, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average)
     got = pkg.acw(data, fs, acwtypes=types, n_lags=n_lags, average_over_trials=average, ctx=ctx)
     res = dict(zip(types, got.acw_results if len(types) > 1 else [got.acw_results]))
@@ -30,7 +30,7 @@ def check_against_oracle(pkg, ctx, data, fs, types=TYPES, n_lags=None, average=F
     if "tau" in types:
         assert np.allclose(np.atleast_1d(res["tau"]), want["tau"], rtol=tau_rtol, atol=0)
     assert got.acf.shape == want["acf"].shape or got.acf.shape == want["acf"][0].shape
-    assert np.max(np.abs(np.atleast_2d(got.acf) - want["acf"])) < ACF_VALUE_TOL
+    assert np.max(np.abs(np.atleast_2d(got.acf) - want["acf"])) < acf_tol
     assert np.array_equal(got.lags, want["lags"])
     return got, want
 
@@ -260,3 +260,29 @@ def test_acw_skip_zero_lag_three_parameter_fit(pkg, ctx):
     row = 0.7 * (np.exp(-lags / 0.11) + 0.05)
     from oracle import acwred
     assert acwred.fit_expdecay_3_parameters(lags, row) == pytest.approx(0.11, rel=1e-8)
+
+
+@pytest.mark.parametrize("window", [8, 16, 32])
+def test_acw_streaming_window_choices(pkg, ctx, window):
+    """tuning.acw_stream = 8 / 16 / 32 keeps that many lags in the one-read streaming pass (fewer lags: fewer registers
+    and FFMA per sample); slices that have not crossed zero inside the window are redone by the fp64 kernel, so every
+    choice must give the oracle's indices bit for bit - on white noise (nothing redone at 32), on an AR(1) mix whose
+    zero crossings straddle 8 and 16 lags, and with NaN gaps."""
+    rng = np.random.default_rng(11)
+    n_slices, n_t = 96, 1500
+    white = rng.standard_normal((n_slices, n_t))
+    phi = np.linspace(0.0, 0.85, n_slices)[:, None]                     # AR(1): crossings from lag 1 to beyond 16
+    ar = np.empty((n_slices, n_t)); prev = rng.standard_normal((n_slices, 1))
+    for k in range(n_t):
+        prev = phi * prev + np.sqrt(1 - phi ** 2) * rng.standard_normal((n_slices, 1))
+        ar[:, k] = prev[:, 0]
+    gaps = ar.copy(); gaps[::7, 200:260] = np.nan
+    ctx.set_tuning(acw_stream=window)
+    try:
+        for d in (white, ar, gaps):
+            d = d.copy()
+            first = next(i for i in range(n_slices) if oacw.acw(d[i], 100.0, acwtypes=["acw0"])["k0"][0] >= 2)
+            d[[0, first]] = d[[first, 0]]                               # AUC window of the first slice needs >= 2 points
+            check_against_oracle(pkg, ctx, d, 100.0, acf_tol=5e-7)       # fp32 products over 1500 samples
+    finally:
+        ctx.reset_tuning()
