@@ -374,7 +374,7 @@ int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, in
 // three consecutive arrays of n_rows doubles: knee, amp, peak
 static int knee_fit_dev(itjl_ctx* ctx, const double* rows_dev, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs_dev,
                         double min_freq, double max_freq, int mode, int max_peaks, double* out3 = nullptr) {
-    const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->sm_count * 4);
+    const int grid = knee_fit_grid(ctx->sm_count, n_rows);
     ITJL_CUDA(ctx, ctx->part.reserve((size_t)grid * 3 * n * sizeof(double)));
     if (!out3) ITJL_CUDA(ctx, ctx->stats.reserve((size_t)n_rows * 3 * sizeof(double)));
     double* k = out3 ? out3 : (double*)ctx->stats.p;

@@ -123,6 +123,7 @@ cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, d
                                 double* out, cudaStream_t st);
 
 // ---- knee_kernels.cu -----------------------------------------------------------------
+int knee_fit_grid(int sm_count, int64_t n_rows);
 cudaError_t knee_fit_launch(const double* rows, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs, double min_freq,
                             double max_freq, int mode, int max_peaks, double* knee_out, double* amp_out, double* peak_out,
                             double* work, int grid, cudaStream_t st);

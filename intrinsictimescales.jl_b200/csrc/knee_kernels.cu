@@ -295,6 +295,12 @@ __global__ void __launch_bounds__(kKneeThreads) k_knee_fit(const double* __restr
     }
 }
 
+// CTAs that fill the machine once: 128 registers per thread bound the resident CTAs per SM
+int knee_fit_grid(int sm_count, int64_t n_rows) {
+    const int64_t per_sm = 65536 / (128 * kKneeThreads);
+    const int64_t g = (int64_t)sm_count * (per_sm < 1 ? 1 : (per_sm > 32 ? 32 : per_sm));
+    return (int)(n_rows < g ? n_rows : g);
+}
 cudaError_t knee_fit_launch(const double* rows, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs, double min_freq,
                             double max_freq, int mode, int max_peaks, double* knee_out, double* amp_out, double* peak_out,
                             double* work, int grid, cudaStream_t st) {

@@ -286,3 +286,35 @@ def test_acw_streaming_window_choices(pkg, ctx, window):
             check_against_oracle(pkg, ctx, d, 100.0, acf_tol=5e-7)       # fp32 products over 1500 samples
     finally:
         ctx.reset_tuning()
+
+
+def test_acw_acf_fetch_matches_inline_output(pkg, ctx):
+    """C ABI: the ACF matrix through acf_out of itjl_acw (as a C / Julia caller may pass it) and through
+    itjl_acw_acf after a call made with acf_out = NULL are the same bytes; the shape query reports (rows, lags)."""
+    import ctypes
+    lib, L = pkg._lib.lib(), pkg._lib
+    rng = np.random.default_rng(5)
+    d = np.asfortranarray(rng.standard_normal((300, 900)))
+    n_s, n_t = d.shape
+
+    def call(acf_buf):
+        k = [np.empty(n_s, dtype=np.int32) for _ in range(3)]
+        auc, tau = np.empty(n_s), np.empty(n_s)
+        nl = ctypes.c_int64(0)
+        ctx.check(lib.itjl_acw(ctx.handle, L.ptr(d), n_s, n_t, 100.0, L.ACW0 | L.ACW50 | L.TAU, 0, ctypes.byref(nl),
+                               L.ptr(k[0]), L.ptr(k[1]), L.ptr(k[2]), L.ptr(auc), L.ptr(tau), L.ptr(acf_buf),
+                               0 if acf_buf is None else acf_buf.size))
+        return int(nl.value), tau
+    big = np.full(n_s * n_t, np.nan)
+    n_lags, tau_a = call(big)
+    n_lags_b, tau_b = call(None)
+    assert n_lags == n_lags_b and np.array_equal(tau_a, tau_b)
+    rows, lags = ctypes.c_int64(0), ctypes.c_int64(0)
+    ctx.check(lib.itjl_acw_acf(ctx.handle, None, 0, ctypes.byref(rows), ctypes.byref(lags)))
+    assert (rows.value, lags.value) == (n_s, n_lags)
+    exact = np.empty(n_s * n_lags)
+    ctx.check(lib.itjl_acw_acf(ctx.handle, L.ptr(exact), exact.size, None, None))
+    assert np.array_equal(exact, big[: n_s * n_lags]) and np.all(np.isnan(big[n_s * n_lags:]))
+    assert np.allclose(exact.reshape((n_s, n_lags), order="F")[:, 0], 1.0)
+    small = np.empty(n_s * n_lags - 1)
+    assert lib.itjl_acw_acf(ctx.handle, L.ptr(small), small.size, None, None) != 0          # capacity too small: refused
