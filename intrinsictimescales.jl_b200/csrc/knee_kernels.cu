@@ -15,7 +15,11 @@
 
 namespace itjl {
 
-constexpr int kKneeThreads = 256;
+// 64 threads per row, 16 CTAs per SM (64 registers): an objective evaluation is a short latency-bound loop + reduction,
+// so many small CTAs beat few wide ones - 20 000 spectra x 994 bins, knee only: 119 ms (256 threads, 2 CTAs per SM, one
+// partial sum per thread) -> 66 ms (64 threads, four independent partial sums) -> 53 ms (16 CTAs per SM);
+// benchmarks/knee_time.py
+constexpr int kKneeThreads = 64;
 
 struct KneeShared {
     double red[kKneeThreads / 32];
@@ -54,21 +58,41 @@ __device__ __forceinline__ int block_min_int(int v, KneeShared* sh) { return (in
 template <int MODEL>
 __device__ __forceinline__ double l1_objective(const double* __restrict__ y, const double* __restrict__ f, int n, const double* x,
                                                double f_hi, KneeShared* sh) {
-    double acc = 0.0;
+    // four independent partial sums per thread: the divisions (exps) of four elements overlap instead of queueing behind
+    // one another's ~100-cycle dependent chains
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    constexpr int T = kKneeThreads;
+    int i = threadIdx.x;
     if (MODEL == 0) {
         const double amp = exp(x[0]), ik = 1.0 / fmin(exp(x[1]), f_hi);
-        for (int i = threadIdx.x; i < n; i += kKneeThreads) {
+        for (; i + 3 * T < n; i += 4 * T) {
+            const double t0 = f[i] * ik, t1 = f[i + T] * ik, t2 = f[i + 2 * T] * ik, t3 = f[i + 3 * T] * ik;
+            const double y0 = y[i], y1 = y[i + T], y2 = y[i + 2 * T], y3 = y[i + 3 * T];
+            a0 += fabs(amp / fma(t0, t0, 1.0) - y0);
+            a1 += fabs(amp / fma(t1, t1, 1.0) - y1);
+            a2 += fabs(amp / fma(t2, t2, 1.0) - y2);
+            a3 += fabs(amp / fma(t3, t3, 1.0) - y3);
+        }
+        for (; i < n; i += T) {
             const double t = f[i] * ik;
-            acc += fabs(amp / fma(t, t, 1.0) - y[i]);
+            a0 += fabs(amp / fma(t, t, 1.0) - y[i]);
         }
     } else {
         const double amp = x[0], c = x[1], h = -0.5 * exp(-2.0 * x[2]);
-        for (int i = threadIdx.x; i < n; i += kKneeThreads) {
+        for (; i + 3 * T < n; i += 4 * T) {
+            const double d0 = f[i] - c, d1 = f[i + T] - c, d2 = f[i + 2 * T] - c, d3 = f[i + 3 * T] - c;
+            const double y0 = y[i], y1 = y[i + T], y2 = y[i + 2 * T], y3 = y[i + 3 * T];
+            a0 += fabs(amp * exp(h * d0 * d0) - y0);
+            a1 += fabs(amp * exp(h * d1 * d1) - y1);
+            a2 += fabs(amp * exp(h * d2 * d2) - y2);
+            a3 += fabs(amp * exp(h * d3 * d3) - y3);
+        }
+        for (; i < n; i += T) {
             const double d = f[i] - c;
-            acc += fabs(amp * exp(h * d * d) - y[i]);
+            a0 += fabs(amp * exp(h * d * d) - y[i]);
         }
     }
-    return block_sum(acc, sh) / (double)n;
+    return block_sum((a0 + a1) + (a2 + a3), sh) / (double)n;
 }
 
 // Nelder-Mead (reflection 1, expansion 2, contraction 1/2, shrink 1/2), run redundantly by every thread of the CTA on
@@ -237,7 +261,7 @@ __device__ void gaussian_fit_row(const double* y, const double* f, int n, double
 // with lorentzian_initial_guess in place of the fit (the oscillation models' informed prior,
 // one_timescale_and_osc.jl:16-28); mode 3: find_oscillation_peak of the row itself.
 // work: gridDim.x * 3 * n doubles.
-__global__ void __launch_bounds__(kKneeThreads) k_knee_fit(const double* __restrict__ rows, int64_t n_rows, int64_t ld, int i0, int n,
+__global__ void __launch_bounds__(kKneeThreads, 16) k_knee_fit(const double* __restrict__ rows, int64_t n_rows, int64_t ld, int i0, int n,
                                                            const double* __restrict__ freqs, double min_freq, double max_freq,
                                                            int mode, int max_peaks, double* __restrict__ knee_out,
                                                            double* __restrict__ amp_out, double* __restrict__ peak_out,
@@ -295,10 +319,11 @@ __global__ void __launch_bounds__(kKneeThreads) k_knee_fit(const double* __restr
     }
 }
 
-// CTAs that fill the machine once: 128 registers per thread bound the resident CTAs per SM
+// CTAs that fill the machine once (the registers per thread bound the resident CTAs per SM)
 int knee_fit_grid(int sm_count, int64_t n_rows) {
-    const int64_t per_sm = 65536 / (128 * kKneeThreads);
-    const int64_t g = (int64_t)sm_count * (per_sm < 1 ? 1 : (per_sm > 32 ? 32 : per_sm));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_knee_fit, kKneeThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t g = (int64_t)sm_count * per_sm;
     return (int)(n_rows < g ? n_rows : g);
 }
 cudaError_t knee_fit_launch(const double* rows, int64_t n_rows, int64_t ld, int i0, int n, const double* freqs, double min_freq,
