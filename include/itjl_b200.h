@@ -78,7 +78,10 @@ typedef struct {
     int32_t acw_waves;       /* 0 automatic; time segments of the streaming pass sized for this many waves of CTAs */
     int32_t pinned_upload;   /* 1 (default): large host <-> device copies go through the pinned staging ring */
     int32_t copy_threads;    /* 0 automatic (half the hardware threads, at most 8); host threads feeding that ring */
-    int32_t pmc_fp32;        /* -1 automatic (fp32 pair sums above 1e8 pairs); 0 always fp64; 1 always fp32 */
+    int32_t pmc_fp32;        /* PMC weights: -1 automatic (fp64 pair sums up to 1e8 pairs, fp32 pair sums above; one-parameter
+                                models above 1e8 pairs with >= 32768 new particles: exact fp64 mixture density on an
+                                8192-point grid + 4-point interpolation, ~1e-12); 0 always fp64 pair sums; 1 always fp32
+                                pair sums; 2 always the grid (n_theta = 1) */
     int32_t psd_v2;          /* 1 (default): PSD models with 4096 < n_t <= 16384 run the warp-specialised kernel k_abc_psd2;
                                 0: always k_abc_psd */
     double tc_error_bound;   /* 5e-6: bound on the predicted |error| of a trial-mean ACF value of k_abc_acf_tc */

@@ -43,7 +43,7 @@ int itjl_ctx_set_tuning(itjl_ctx* ctx, const itjl_tuning* t) {
     ITJL_LOCK(ctx);
     if (t->abc_tc < -1 || t->abc_tc > 1 || t->tc_terms < 0 || t->tc_terms > 3 || t->tc_tail_max > 60 || t->tc_groups < 0 ||
         t->tc_groups > 4 || t->tc_seg_trials < 0 || (t->abc_threads != 0 && t->abc_threads != 128 && t->abc_threads != 256) ||
-        t->abc_bufs < 0 || t->abc_bufs > 2 || t->copy_threads < 0 || t->pmc_fp32 < -1 || t->pmc_fp32 > 1 || !(t->tc_error_bound > 0.0) ||
+        t->abc_bufs < 0 || t->abc_bufs > 2 || t->copy_threads < 0 || t->pmc_fp32 < -1 || t->pmc_fp32 > 2 || !(t->tc_error_bound > 0.0) ||
         (t->acw_stream != 0 && t->acw_stream != 1 && t->acw_stream != 8 && t->acw_stream != 16 && t->acw_stream != 32))
         return fail(ctx, ITJL_ERR_ARG, "itjl_ctx_set_tuning: value out of range");
     ctx->tuning = *t;

@@ -65,7 +65,10 @@ int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, co
         for (int64_t j = 0; j < n_prev; ++j) s += theta_prev[j + (int64_t)d * n_prev];
         mu[d] = s / (double)n_prev;
     }
-    const bool fp32 = ctx->tuning.pmc_fp32 == 1 || (ctx->tuning.pmc_fp32 == -1 && (double)n * (double)n_prev > 1e8);
+    // one parameter and a large population: exact fp64 density on a grid + interpolation (k_pmc_grid_weights)
+    const bool grid1d = p == 1 && n >= 16 && (ctx->tuning.pmc_fp32 == 2 || (ctx->tuning.pmc_fp32 == -1 && (double)n * (double)n_prev > 1e8 && n >= 4 * 8192));
+    const int n_grid = 8192;
+    const bool fp32 = !grid1d && (ctx->tuning.pmc_fp32 == 1 || (ctx->tuning.pmc_fp32 == -1 && (double)n * (double)n_prev > 1e8));
     const double scale = pmc_coord_scale(fp32);
     const size_t el = fp32 ? sizeof(float) : sizeof(double);
 
@@ -83,7 +86,62 @@ int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, co
         memcpy(wp.data(), weights_prev, (size_t)n_prev * sizeof(double));
     }
     std::vector<std::vector<unsigned char>> zs(mem.size());
-    for (size_t i = 0; i < mem.size(); ++i) {
+    // grid path: whitened coordinate of every new particle (range of the grid), the grid itself
+    std::vector<double> z_all, grid;
+    double z_lo = 0.0, h = 1.0;
+    bool use_grid = grid1d;
+    if (use_grid) {
+        z_all.resize((size_t)n);
+        whiten<double>(theta, n, 1, L, mu, scale, 0, n, z_all.data());
+        double lo = z_all[0], hi = z_all[0];
+        bool finite = true;
+        for (int64_t i = 0; i < n; ++i) {
+            const double v = z_all[(size_t)i];
+            if (!(v == v) || std::isinf(v)) finite = false;
+            lo = v < lo ? v : lo; hi = v > hi ? v : hi;
+        }
+        if (!finite || !(hi > lo)) use_grid = false;                // degenerate population: the exact pair sums handle it
+        else {
+            z_lo = lo; h = (hi - lo) / (double)(n_grid - 3);        // points lie in [g_1, g_{n_grid - 2}]
+            grid.resize((size_t)n_grid);
+            for (int m = 0; m < n_grid; ++m) grid[(size_t)m] = z_lo + (double)(m - 1) * h;
+        }
+    }
+    for (size_t i = 0; use_grid && i < mem.size(); ++i) {
+        itjl_ctx* c = mem[i].c;
+        ITJL_LOCK(c);
+        int64_t lo, hi;
+        shard_bounds(n, world, mem[i].rank, &lo, &hi);
+        ITJL_CUDA(ctx, cudaSetDevice(c->device));
+        ITJL_CUDA(ctx, c->gather.reserve((size_t)world * width * sizeof(double)));
+        if (hi <= lo) continue;
+        const int64_t nl = hi - lo;
+        int n_split = 1;
+        int64_t j_per = n_prev;
+        pmc_mixture_split(n_grid, n_prev, c->sm_count, &n_split, &j_per);
+        // device layout in c->data: [zp | wp | grid | z of this shard], partial sums + density in c->part
+        const size_t off_wp = (size_t)n_prev * sizeof(double), off_g = off_wp + (size_t)n_prev * sizeof(double);
+        const size_t off_z = off_g + (size_t)n_grid * sizeof(double);
+        ITJL_CUDA(ctx, c->data.reserve(off_z + (size_t)nl * sizeof(double)));
+        ITJL_CUDA(ctx, c->part.reserve(((size_t)n_split + 1) * n_grid * sizeof(double)));
+        ITJL_CUDA(ctx, c->out2.reserve((size_t)nl * sizeof(double)));
+        ITJL_CUDA(ctx, c->out3.reserve((size_t)((nl + 255) / 256) * sizeof(double)));
+        unsigned char* base = (unsigned char*)c->data.p;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base, zp.data(), zp.size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_wp, wp.data(), wp.size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_g, grid.data(), (size_t)n_grid * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_z, z_all.data() + lo, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(c->out2.p, prior_pdf + lo, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = pmc_mixture_launch(false, base + off_g, base, base + off_wp, n_grid, n_prev, 1, n_split, j_per,
+                                           (double*)c->part.p, c->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_mixture(grid): %s", cudaGetErrorString(e));
+        e = pmc_grid_weights_launch((const double*)c->part.p, n_split, n_grid, (double*)c->part.p + (size_t)n_split * n_grid, z_lo, h,
+                                    (const double*)(base + off_z), nl, (const double*)c->out2.p, norm,
+                                    (double*)c->gather.p + (int64_t)mem[i].rank * width, (double*)c->out3.p, c->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_grid_weights: %s", cudaGetErrorString(e));
+        c->launches += 3;
+    }
+    for (size_t i = 0; !use_grid && i < mem.size(); ++i) {
         itjl_ctx* c = mem[i].c;
         ITJL_LOCK(c);
         int64_t lo, hi;

@@ -109,6 +109,53 @@ __global__ void __launch_bounds__(256) k_pmc_finish(const double* __restrict__ p
     }
 }
 
+// One-parameter models with large populations: the mixture density f(z) = sum_j w_j exp(-(z - z_j)^2) is a smooth function
+// of ONE whitened coordinate (every term has width 1 in z), so it is evaluated exactly (fp64 pair sums, k_pmc_mixture)
+// on a uniform grid of n_grid points spanning the new particles and read off by 4-point Lagrange interpolation:
+// error <= (3/128) h^4 max|d^4 f / dz^4| ~ 0.3 h^4 f_max with h = range / n_grid ~ 1e-3, i.e. ~1e-12 of the density's
+// scale (below 1e-9 relative out to the tails) - tighter than the fp32 pair sums it replaces, at n_grid x n_prev
+// instead of n x n_prev pairs.  dens[m] = sum over the j splits of part[split][m] (fixed order).
+__global__ void __launch_bounds__(256) k_pmc_grid_density(const double* __restrict__ part, int n_split, int n_grid,
+                                                          double* __restrict__ dens) {
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    if (m >= n_grid) return;
+    double d = 0.0;
+    for (int s = 0; s < n_split; ++s) d += part[(int64_t)s * n_grid + m];
+    dens[m] = d;
+}
+// grid point m sits at z_lo + (m - 1) h; w_i = prior_i / (norm * f(z_i)); block sums of w for the normalisation
+__global__ void __launch_bounds__(256) k_pmc_grid_weights(const double* __restrict__ dens, int n_grid, double z_lo, double inv_h,
+                                                          const double* __restrict__ z, int64_t n,
+                                                          const double* __restrict__ prior_pdf, double norm,
+                                                          double* __restrict__ w_out, double* __restrict__ block_sums) {
+    __shared__ double red[8];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double w = 0.0;
+    if (i < n) {
+        const double u = (z[i] - z_lo) * inv_h + 1.0;
+        int m0 = (int)floor(u);
+        m0 = m0 < 1 ? 1 : (m0 > n_grid - 3 ? n_grid - 3 : m0);
+        const double t = u - (double)m0;                               // in [0, 1] (up to rounding at the ends)
+        const double fm = dens[m0 - 1], f0 = dens[m0], f1 = dens[m0 + 1], f2 = dens[m0 + 2];
+        // Lagrange basis on nodes -1, 0, 1, 2
+        const double lm = -t * (t - 1.0) * (t - 2.0) * (1.0 / 6.0);
+        const double l0 = (t + 1.0) * (t - 1.0) * (t - 2.0) * 0.5;
+        const double l1 = -(t + 1.0) * t * (t - 2.0) * 0.5;
+        const double l2 = (t + 1.0) * t * (t - 1.0) * (1.0 / 6.0);
+        const double den = fma(lm, fm, fma(l0, f0, fma(l1, f1, l2 * f2)));
+        w = prior_pdf[i] / (norm * den);
+        w_out[i] = w;
+    }
+    w = warp_sum(w);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_scale(double* __restrict__ w, int64_t n, const double* __restrict__ block_sums, int n_blocks) {
     __shared__ double total;
     if (threadIdx.x == 0) {
@@ -165,6 +212,16 @@ cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !normalize) return e;
     k_scale<<<blocks, 256, 0, st>>>(w_out, n, block_sums, blocks);
+    return cudaGetLastError();
+}
+
+cudaError_t pmc_grid_weights_launch(const double* part, int n_split, int n_grid, double* dens, double z_lo, double h,
+                                    const double* z, int64_t n, const double* prior_pdf, double norm, double* w_out,
+                                    double* block_sums, cudaStream_t st) {
+    k_pmc_grid_density<<<(n_grid + 255) / 256, 256, 0, st>>>(part, n_split, n_grid, dens);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_pmc_grid_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dens, n_grid, z_lo, 1.0 / h, z, n, prior_pdf, norm, w_out, block_sums);
     return cudaGetLastError();
 }
 

@@ -62,6 +62,38 @@ def test_calc_weights_fp32_pair_sums_above_1e8_pairs(pkg, ctx, p):
     assert np.isclose(got.sum(), 1.0, rtol=1e-12) and np.allclose(got, raw64 / raw64.sum(), rtol=1e-5)
 
 
+def test_calc_weights_one_parameter_grid_path(pkg, ctx):
+    """One-parameter models above 4e9 pairs (C5: 4.4e11): the mixture density is evaluated exactly in fp64 on an
+    8192-point grid of the whitened coordinate and read off by 4-point interpolation - tuning.pmc_fp32 = 2 forces that
+    path here at a size the oracle can check.  Interpolation error ~1e-12 of the density's scale: every weight within
+    1e-8 of the fp64 pair sums, including proposals far out in the tails and a duplicated particle."""
+    rng = np.random.default_rng(21)
+    th_prev, th, w, cov = _case(rng, 6000, 20000, 1)
+    th[:40, 0] = th_prev[:, 0].mean() + np.linspace(-9, 9, 40) * th_prev[:, 0].std()      # tails (most have prior 0)
+    th[41] = th[40]
+    po, pp = _priors(pkg, 1)
+    want = oabc.calc_weights(th_prev, th, cov, w, po)
+    with ctx.tuned(pmc_fp32=0):
+        exact = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx, normalize=False)
+    with ctx.tuned(pmc_fp32=2):
+        n0 = ctx.launch_count
+        raw = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx, normalize=False)
+        assert ctx.launch_count - n0 == 3                    # mixture on the grid, density, interpolation
+        got = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx)
+        again = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx)
+    ok = exact > 0
+    rel = np.abs(raw[ok] - exact[ok]) / exact[ok]
+    print(f"grid path: max relative error of a weight {rel.max():.3g} over {ok.sum()} particles")
+    assert rel.max() < 1e-8 and np.array_equal(raw == 0, exact == 0)
+    assert np.isclose(got.sum(), 1.0, rtol=1e-12) and np.allclose(got, want, rtol=1e-8, atol=0)
+    assert np.array_equal(got, again) and got[40] == got[41]
+    # a degenerate new population (all particles equal) has no grid: the pair sums take over
+    same = np.full((64, 1), th[100, 0])
+    with ctx.tuned(pmc_fp32=2):
+        d = pkg.calc_weights(th_prev, same, cov, w, pp, ctx=ctx)
+    assert np.allclose(d, 1.0 / 64, rtol=1e-12)
+
+
 def test_weighted_covar_and_reference_kats(pkg, ctx):
     rng = np.random.default_rng(3)
     x = rng.normal(size=(5000, 3)) * np.array([1.0, 5.0, 0.1]) + np.array([0.3, 10.0, -2.0])
