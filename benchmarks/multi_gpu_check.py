@@ -52,6 +52,12 @@ def compare(model, sharded_ctx, tag):
     w_sh = pkg.calc_weights(th_prev, th, cov, w, [pkg.Uniform(0, 5)], ctx=sharded_ctx)
     w_si = pkg.calc_weights(th_prev, th, cov, w, [pkg.Uniform(0, 5)], ctx=solo)
     same_w = np.array_equal(w_sh, w_si)
+    # the one-parameter grid path (>= 32768 new particles): every rank builds the same density grid and interpolates
+    # its own rows
+    th_big = rg.gamma(4.0, 0.1, (40001, 1))
+    g_sh = pkg.calc_weights(th_prev, th_big, cov, w, [pkg.Uniform(0, 5)], ctx=sharded_ctx)
+    g_si = pkg.calc_weights(th_prev, th_big, cov, w, [pkg.Uniform(0, 5)], ctx=solo)
+    same_w = same_w and np.array_equal(g_sh, g_si)
     print(f"[{tag}] rank {rank}/{world}: n_lags={model.n_lags}: basic_abc identical={same} (n_total {sharded['n_total']}, accepted "
           f"{sharded['n_accepted']}); pmc_abc identical={same_pmc} (eps history {[round(e, 5) for e in r_sh.epsilon_history]}); "
           f"calc_weights identical={same_w}", flush=True)
