@@ -61,6 +61,7 @@ int sharded_distances(itjl_model* m, const double* theta, int64_t n_particles, i
 struct ShardMember { itjl_ctx* c; int rank; };
 void shard_members(itjl_ctx* ctx, std::vector<ShardMember>* out, int* world);
 int shard_allgather_compact(itjl_ctx* ctx, int64_t n, double** out_dev);
+int shard_allgather_inplace(itjl_ctx* ctx, const std::vector<double*>& bases, int64_t width);
 int multi_model_create(itjl_ctx* ctx, const itjl_model_desc* desc, itjl_model** model_out);
 void comm_destroy(itjl_ctx* ctx);
 

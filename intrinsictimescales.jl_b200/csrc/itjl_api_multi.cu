@@ -86,6 +86,28 @@ void shard_members(itjl_ctx* ctx, std::vector<ShardMember>* out, int* world) {
 
 // After every member has written its rows [lo_r, hi_r) at gather + rank * width: all-gather in place and, on
 // the primary context, compact the padded [world][width] layout into ctx->dist (n doubles).
+// in-place all-gather of `width` doubles per rank: member i holds its slice at bases[i] + rank * width and ends up
+// with all world * width values at bases[i] (one ncclAllGather per member, stream-ordered; no-op on one GPU)
+int shard_allgather_inplace(itjl_ctx* ctx, const std::vector<double*>& bases, int64_t width) {
+    std::vector<ShardMember> mem;
+    int world = 1;
+    shard_members(ctx, &mem, &world);
+    if (world <= 1) return ITJL_OK;
+    NcclApi* nc = nccl_api();
+    if (!nc->ok) return fail(ctx, ITJL_ERR_ARG, "libnccl.so.2 could not be loaded");
+    ncclResult_t r = nc->GroupStart();
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclGroupStart", r);
+    for (size_t i = 0; i < mem.size(); ++i) {
+        cudaSetDevice(mem[i].c->device);
+        r = nc->AllGather(bases[i] + (int64_t)mem[i].rank * width, bases[i], (size_t)width, ncclDouble, (ncclComm_t)mem[i].c->comm, mem[i].c->stream);
+        if (r != ncclSuccess) { nc->GroupEnd(); return nccl_fail(ctx, "ncclAllGather", r); }
+        mem[i].c->launches++;
+    }
+    r = nc->GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclGroupEnd", r);
+    return ITJL_OK;
+}
+
 int shard_allgather_compact(itjl_ctx* ctx, int64_t n, double** out_dev) {
     std::vector<ShardMember> mem;
     int world = 1;

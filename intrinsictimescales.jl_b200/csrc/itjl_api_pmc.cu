@@ -107,6 +107,43 @@ int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, co
             for (int m = 0; m < n_grid; ++m) grid[(size_t)m] = z_lo + (double)(m - 1) * h;
         }
     }
+    // grid rows are sharded over the members too: each one sums its slice of the density, an in-place all-gather
+    // (n_grid doubles) gives every member the whole grid, then each interpolates its own particles
+    const int64_t g_width = (n_grid + world - 1) / world;
+    const int n_grid_pad = (int)(g_width * world);
+    std::vector<double*> dens_bases(mem.size(), nullptr);
+    for (size_t i = 0; use_grid && i < mem.size(); ++i) {
+        itjl_ctx* c = mem[i].c;
+        ITJL_LOCK(c);
+        ITJL_CUDA(ctx, cudaSetDevice(c->device));
+        const int64_t g_lo = std::min<int64_t>((int64_t)mem[i].rank * g_width, n_grid), g_hi = std::min<int64_t>(g_lo + g_width, n_grid);
+        const int64_t ng = g_hi - g_lo;
+        // the split of the previous particles is a function of n_prev alone, so every grid point's sum has the same
+        // grouping on any number of GPUs (results identical to one GPU's)
+        int64_t j_per = 8192;
+        if ((n_prev + j_per - 1) / j_per > 1024) j_per = (((n_prev + 1023) / 1024 + 1023) / 1024) * 1024;
+        const int n_split = (int)((n_prev + j_per - 1) / j_per);
+        // device layout in c->data: [zp | wp | grid slice]; c->part: [density of all grid points (padded) | partial sums]
+        const size_t off_wp = (size_t)n_prev * sizeof(double), off_g = off_wp + (size_t)n_prev * sizeof(double);
+        ITJL_CUDA(ctx, c->data.reserve(off_g + (size_t)g_width * sizeof(double)));
+        ITJL_CUDA(ctx, c->part.reserve(((size_t)n_grid_pad + (size_t)n_split * g_width) * sizeof(double)));
+        dens_bases[i] = (double*)c->part.p;
+        if (ng <= 0) continue;
+        unsigned char* base = (unsigned char*)c->data.p;
+        double* part = dens_bases[i] + n_grid_pad;
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base, zp.data(), zp.size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_wp, wp.data(), wp.size(), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_g, grid.data() + g_lo, (size_t)ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = pmc_mixture_launch(false, base + off_g, base, base + off_wp, ng, n_prev, 1, n_split, j_per, part, c->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_mixture(grid): %s", cudaGetErrorString(e));
+        e = pmc_grid_density_launch(part, n_split, (int)ng, dens_bases[i] + g_lo, c->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_grid_density: %s", cudaGetErrorString(e));
+        c->launches += 2;
+    }
+    if (use_grid) {
+        const int rcg = shard_allgather_inplace(ctx, dens_bases, g_width);
+        if (rcg != ITJL_OK) return rcg;
+    }
     for (size_t i = 0; use_grid && i < mem.size(); ++i) {
         itjl_ctx* c = mem[i].c;
         ITJL_LOCK(c);
@@ -116,30 +153,15 @@ int itjl_pmc_weights(itjl_ctx* ctx, const double* theta_prev, int64_t n_prev, co
         ITJL_CUDA(ctx, c->gather.reserve((size_t)world * width * sizeof(double)));
         if (hi <= lo) continue;
         const int64_t nl = hi - lo;
-        int n_split = 1;
-        int64_t j_per = n_prev;
-        pmc_mixture_split(n_grid, n_prev, c->sm_count, &n_split, &j_per);
-        // device layout in c->data: [zp | wp | grid | z of this shard], partial sums + density in c->part
-        const size_t off_wp = (size_t)n_prev * sizeof(double), off_g = off_wp + (size_t)n_prev * sizeof(double);
-        const size_t off_z = off_g + (size_t)n_grid * sizeof(double);
-        ITJL_CUDA(ctx, c->data.reserve(off_z + (size_t)nl * sizeof(double)));
-        ITJL_CUDA(ctx, c->part.reserve(((size_t)n_split + 1) * n_grid * sizeof(double)));
+        ITJL_CUDA(ctx, c->out.reserve((size_t)nl * sizeof(double)));
         ITJL_CUDA(ctx, c->out2.reserve((size_t)nl * sizeof(double)));
         ITJL_CUDA(ctx, c->out3.reserve((size_t)((nl + 255) / 256) * sizeof(double)));
-        unsigned char* base = (unsigned char*)c->data.p;
-        ITJL_CUDA(ctx, cudaMemcpyAsync(base, zp.data(), zp.size(), cudaMemcpyHostToDevice, c->stream));
-        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_wp, wp.data(), wp.size(), cudaMemcpyHostToDevice, c->stream));
-        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_g, grid.data(), (size_t)n_grid * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        ITJL_CUDA(ctx, cudaMemcpyAsync(base + off_z, z_all.data() + lo, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ITJL_CUDA(ctx, cudaMemcpyAsync(c->out.p, z_all.data() + lo, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         ITJL_CUDA(ctx, cudaMemcpyAsync(c->out2.p, prior_pdf + lo, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        cudaError_t e = pmc_mixture_launch(false, base + off_g, base, base + off_wp, n_grid, n_prev, 1, n_split, j_per,
-                                           (double*)c->part.p, c->stream);
-        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_mixture(grid): %s", cudaGetErrorString(e));
-        e = pmc_grid_weights_launch((const double*)c->part.p, n_split, n_grid, (double*)c->part.p + (size_t)n_split * n_grid, z_lo, h,
-                                    (const double*)(base + off_z), nl, (const double*)c->out2.p, norm,
-                                    (double*)c->gather.p + (int64_t)mem[i].rank * width, (double*)c->out3.p, c->stream);
+        cudaError_t e = pmc_grid_weights_launch(dens_bases[i], n_grid, z_lo, h, (const double*)c->out.p, nl, (const double*)c->out2.p, norm,
+                                                (double*)c->gather.p + (int64_t)mem[i].rank * width, (double*)c->out3.p, c->stream);
         if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_pmc_grid_weights: %s", cudaGetErrorString(e));
-        c->launches += 3;
+        c->launches++;
     }
     for (size_t i = 0; !use_grid && i < mem.size(); ++i) {
         itjl_ctx* c = mem[i].c;

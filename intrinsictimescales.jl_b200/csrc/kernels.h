@@ -255,9 +255,9 @@ double pmc_coord_scale(bool fp32);
 void pmc_mixture_split(int64_t n, int64_t n_prev, int sm_count, int* n_split, int64_t* j_per_split);
 cudaError_t pmc_mixture_launch(bool fp32, const void* z, const void* zp, const void* wp, int64_t n, int64_t n_prev, int p,
                                int n_split, int64_t j_per_split, double* part, cudaStream_t st);
-cudaError_t pmc_grid_weights_launch(const double* part, int n_split, int n_grid, double* dens, double z_lo, double h,
-                                    const double* z, int64_t n, const double* prior_pdf, double norm, double* w_out,
-                                    double* block_sums, cudaStream_t st);
+cudaError_t pmc_grid_density_launch(const double* part, int n_split, int n_rows, double* dens, cudaStream_t st);
+cudaError_t pmc_grid_weights_launch(const double* dens, int n_grid, double z_lo, double h, const double* z, int64_t n,
+                                    const double* prior_pdf, double norm, double* w_out, double* block_sums, cudaStream_t st);
 cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const double* prior_pdf, double norm,
                               double* w_out, double* block_sums, bool normalize, cudaStream_t st);
 cudaError_t pmc_normalize_launch(double* w, int64_t n, double* block_sums, cudaStream_t st);

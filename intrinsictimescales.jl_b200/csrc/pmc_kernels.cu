@@ -215,12 +215,12 @@ cudaError_t pmc_finish_launch(const double* part, int n_split, int64_t n, const 
     return cudaGetLastError();
 }
 
-cudaError_t pmc_grid_weights_launch(const double* part, int n_split, int n_grid, double* dens, double z_lo, double h,
-                                    const double* z, int64_t n, const double* prior_pdf, double norm, double* w_out,
-                                    double* block_sums, cudaStream_t st) {
-    k_pmc_grid_density<<<(n_grid + 255) / 256, 256, 0, st>>>(part, n_split, n_grid, dens);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+cudaError_t pmc_grid_density_launch(const double* part, int n_split, int n_rows, double* dens, cudaStream_t st) {
+    k_pmc_grid_density<<<(n_rows + 255) / 256, 256, 0, st>>>(part, n_split, n_rows, dens);
+    return cudaGetLastError();
+}
+cudaError_t pmc_grid_weights_launch(const double* dens, int n_grid, double z_lo, double h, const double* z, int64_t n,
+                                    const double* prior_pdf, double norm, double* w_out, double* block_sums, cudaStream_t st) {
     k_pmc_grid_weights<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dens, n_grid, z_lo, 1.0 / h, z, n, prior_pdf, norm, w_out, block_sums);
     return cudaGetLastError();
 }

@@ -78,7 +78,7 @@ def test_calc_weights_one_parameter_grid_path(pkg, ctx):
     with ctx.tuned(pmc_fp32=2):
         n0 = ctx.launch_count
         raw = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx, normalize=False)
-        assert ctx.launch_count - n0 == 3                    # mixture on the grid, density, interpolation
+        assert ctx.launch_count - n0 == 3                    # mixture on the grid, density, interpolation (one GPU)
         got = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx)
         again = pkg.calc_weights(th_prev, th, cov, w, pp, ctx=ctx)
     ok = exact > 0
