@@ -318,3 +318,25 @@ def test_acw_acf_fetch_matches_inline_output(pkg, ctx):
     assert np.allclose(exact.reshape((n_s, n_lags), order="F")[:, 0], 1.0)
     small = np.empty(n_s * n_lags - 1)
     assert lib.itjl_acw_acf(ctx.handle, L.ptr(small), small.size, None, None) != 0          # capacity too small: refused
+
+
+def test_acw_many_slices_overflow_the_pinned_scratch(pkg, ctx):
+    """170 000 short slices: the crossing indices (3 x 680 KB) no longer fit the 2 MB pinned scratch the small
+    device -> host results are staged through, so part of them takes the direct copy - every index must still be
+    the oracle's, and the fetched ACF must be the right shape."""
+    rng = np.random.default_rng(8)
+    n_slices, n_t = 170_000, 300
+    phi = rng.uniform(0.0, 0.6, (n_slices, 1))
+    d = np.empty((n_slices, n_t)); prev = rng.standard_normal((n_slices, 1))
+    for k in range(n_t):
+        prev = phi * prev + np.sqrt(1 - phi ** 2) * rng.standard_normal((n_slices, 1))
+        d[:, k] = prev[:, 0]
+    types = ["acw0", "acw50", "acweuler"]
+    want = oacw.acw(d, 50.0, acwtypes=types)
+    got = pkg.acw(d, 50.0, acwtypes=types, ctx=ctx)
+    assert got.n_lags == want["n_lags"] and got.acf.shape == (n_slices, want["n_lags"])
+    dt = 1.0 / 50.0
+    for name, key, res in zip(types, ("k0", "k50", "ke"), got.acw_results):
+        w = np.where(want[key] >= 0, want[key] * dt, np.nan)
+        assert np.array_equal(res, w, equal_nan=True), name
+    assert np.max(np.abs(got.acf - want["acf"])) < 5e-6      # fp32 products of the streaming pass, max over 1.7e7 values (north_star: 1e-5)
