@@ -78,19 +78,32 @@ __device__ __forceinline__ double l1_objective(const double* __restrict__ y, con
             a0 += fabs(amp / fma(t, t, 1.0) - y[i]);
         }
     } else {
-        const double amp = x[0], c = x[1], h = -0.5 * exp(-2.0 * x[2]);
-        for (; i + 3 * T < n; i += 4 * T) {
+        // Gaussian: beyond 10 sd of the centre the model is < 2e-22 of its amplitude and |model - y| == |y| to the last
+        // bit, so only the bins inside that window are visited; the rest is known: f_hi carries sum |y| of the row
+        // (freqs ascending - checked by the callers - so the window is an index range found by bisection)
+        const double amp = x[0], c = x[1], sd = exp(x[2]), h = -0.5 / (sd * sd), r = 10.0 * sd;
+        int lo = 0, hi = n;
+        if (r == r && c == c) {
+            int a = 0, b = n;                                   // first index with f >= c - r
+            while (a < b) { const int m = (a + b) >> 1; if (f[m] < c - r) a = m + 1; else b = m; }
+            lo = a; b = n;                                      // first index with f > c + r
+            while (a < b) { const int m = (a + b) >> 1; if (f[m] <= c + r) a = m + 1; else b = m; }
+            hi = a;
+        }
+        i = lo + (int)threadIdx.x;
+        for (; i + 3 * T < hi; i += 4 * T) {
             const double d0 = f[i] - c, d1 = f[i + T] - c, d2 = f[i + 2 * T] - c, d3 = f[i + 3 * T] - c;
             const double y0 = y[i], y1 = y[i + T], y2 = y[i + 2 * T], y3 = y[i + 3 * T];
-            a0 += fabs(amp * exp(h * d0 * d0) - y0);
-            a1 += fabs(amp * exp(h * d1 * d1) - y1);
-            a2 += fabs(amp * exp(h * d2 * d2) - y2);
-            a3 += fabs(amp * exp(h * d3 * d3) - y3);
+            a0 += fabs(amp * exp(h * d0 * d0) - y0) - fabs(y0);
+            a1 += fabs(amp * exp(h * d1 * d1) - y1) - fabs(y1);
+            a2 += fabs(amp * exp(h * d2 * d2) - y2) - fabs(y2);
+            a3 += fabs(amp * exp(h * d3 * d3) - y3) - fabs(y3);
         }
-        for (; i < n; i += T) {
-            const double d = f[i] - c;
-            a0 += fabs(amp * exp(h * d * d) - y[i]);
+        for (; i < hi; i += T) {
+            const double d = f[i] - c, yi = y[i];
+            a0 += fabs(amp * exp(h * d * d) - yi) - fabs(yi);
         }
+        return (f_hi + block_sum((a0 + a1) + (a2 + a3), sh)) / (double)n;
     }
     return block_sum((a0 + a1) + (a2 + a3), sh) / (double)n;
 }
@@ -251,7 +264,10 @@ __device__ void gaussian_fit_row(const double* y, const double* f, int n, double
     if (!(sd0 > 0.0) || !isfinite(amp0)) { g[0] = g[1] = g[2] = NAN; return; }
     double x[3] = {amp0, peak, log(sd0)};
     const double step[3] = {0.1 * fabs(amp0) + 1e-300, 0.5 * sd0, 0.1};
-    nelder_mead<1, 3>(y, f, n, x, step, 0.0, sh);
+    double sabs = 0.0;
+    for (int i = tid; i < n; i += kKneeThreads) sabs += fabs(y[i]);
+    sabs = block_sum(sabs, sh);
+    nelder_mead<1, 3>(y, f, n, x, step, sabs, sh);
     g[0] = x[0]; g[1] = x[1]; g[2] = exp(x[2]);
 }
 
