@@ -121,9 +121,12 @@ def comp_psd_lombscargle(times, data, nanmask=None, dt=None, ctx=None):
     samples on LombScargle.autofrequency(times; maximum_frequency = 1 / 2dt); returns (power, frequency_grid).
     `times` must be the regular grid dt:dt:n*dt the reference's callers pass (acw.jl:247)."""
     vec = np.ndim(data) == 1
-    d = np.array(_as_slices(data), order="F", copy=True)
+    d = _as_slices(data)                                   # no copy when the matrix already has the slice index fastest
     if nanmask is not None:
-        d[np.asarray(nanmask, dtype=bool).reshape(d.shape)] = np.nan
+        m = np.asarray(nanmask, dtype=bool).reshape(d.shape)
+        if not np.all(np.isnan(d[m])):                     # the reference's callers pass isnan.(data): nothing to mark then
+            d = np.array(d, order="F", copy=True)
+            d[m] = np.nan
     times = np.asarray(times, dtype=np.float64)
     dt = float(times[1] - times[0]) if dt is None else float(dt)
     if times.shape[0] != d.shape[1] or not np.allclose(np.diff(times), dt, rtol=1e-9, atol=0.0):
