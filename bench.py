@@ -395,6 +395,7 @@ def run_sweep(pkg, ctx, model, gm, P, seed, barrier, n_gen=3):
         t2 = time.perf_counter()
         acc = isacc[:n_total]
         theta_acc = theta[:n_total][acc]
+        t2a = time.perf_counter()
         new_eps = pkg.select_epsilon(d[:n_total], eps, current_acc_rate=n_acc / n_total, iteration=g, total_iterations=n_gen, ctx=ctx)
         t3 = time.perf_counter()
         if g == 1:
@@ -405,7 +406,7 @@ def run_sweep(pkg, ctx, model, gm, P, seed, barrier, n_gen=3):
             tsq = 2.0 * pkg.weighted_covar(theta_acc, w, ctx=ctx)
         t4 = time.perf_counter()
         gens.append({"generation": g, "epsilon": eps, "n_accepted": int(n_acc), "propose_host_ms": 1e3 * (t1 - t0),
-                     "score_ms": 1e3 * (t2 - t1), "accept_epsilon_host_ms": 1e3 * (t3 - t2), "weights_cov_ms": 1e3 * (t4 - t3),
+                     "score_ms": 1e3 * (t2 - t1), "accept_epsilon_host_ms": 1e3 * (t3 - t2), "accept_compaction_ms": 1e3 * (t2a - t2), "weights_cov_ms": 1e3 * (t4 - t3),
                      "weight_pairs": 0 if g == 1 else int(theta_acc.shape[0]) * int(theta_prev.shape[0]),
                      "posterior_mean": float(np.average(theta_acc[:, 0], weights=w))})
         theta_prev, w_prev, tau_sq, eps = theta_acc, w, tsq, new_eps
@@ -529,7 +530,7 @@ def run_gpu(args):
     # ---- the 3-generation sweep (every rank: its host steps are redundant, its device steps sharded) ---------
     sweep = None
     if not args.no_sub or sweep_mode:
-        run_sweep(pkg, ctx, model, gm, min(P, 20000), args.seed, barrier)               # warm-up on a small population
+        run_sweep(pkg, ctx, model, gm, P, args.seed, barrier, n_gen=2)     # warm-up: two generations at full size (every buffer the sweep grows is allocated here, not inside the timed loop)
         sweep_s, gens = run_sweep(pkg, ctx, model, gm, P, args.seed, barrier)
         if distributed:
             tms = torch.tensor([sweep_s], dtype=torch.float64, device=dev)
