@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <stdlib.h>
 #include <condition_variable>
+#include <pthread.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -30,15 +31,16 @@ static int copy_threads(const itjl_ctx* ctx) {
 
 // Persistent fork-join pool for those copies: starting std::threads per 16 MB chunk cost as much as a third of the
 // chunk's copy time (7 thread starts ~ 0.1-0.15 ms against ~0.25 ms of memcpy).  One copy at a time (run_mu); workers
-// sleep on a condition variable between jobs and are joined when the library is unloaded.
+// are detached threads that sleep on a condition variable between jobs.  The pool lives on the heap and is never
+// destroyed (nothing to join when the process exits); a forked child starts with a fresh, empty pool (the parent's
+// workers do not exist there).
 namespace {
 class CopyPool {
     std::mutex run_mu, mu;
     std::condition_variable cv_start, cv_done;
-    std::vector<std::thread> workers;
+    int n_workers = 0;
     uint64_t gen = 0;
     int pending = 0, n_parts = 0;
-    bool stop = false;
     char* dst = nullptr; const char* src = nullptr; size_t n = 0, part = 0;
 
     void copy_part(int t) const {
@@ -46,12 +48,10 @@ class CopyPool {
         const size_t hi = (size_t)(t + 1) * part < n ? (size_t)(t + 1) * part : n;
         if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
     }
-    void worker(int t) {
-        uint64_t seen = 0;
+    void worker(int t, uint64_t seen) {
         for (;;) {
             std::unique_lock<std::mutex> lk(mu);
-            cv_start.wait(lk, [&] { return stop || gen != seen; });
-            if (stop) return;
+            cv_start.wait(lk, [&] { return gen != seen; });
             seen = gen;
             const bool mine = t < n_parts;
             lk.unlock();
@@ -67,14 +67,15 @@ class CopyPool {
         std::lock_guard<std::mutex> run(run_mu);
         {
             std::lock_guard<std::mutex> lk(mu);
-            while ((int)workers.size() < n_threads - 1) {
-                const int t = (int)workers.size() + 1;
-                workers.emplace_back([this, t] { worker(t); });
+            while (n_workers < n_threads - 1) {
+                const int t = ++n_workers;
+                const uint64_t seen = gen;
+                std::thread([this, t, seen] { worker(t, seen); }).detach();
             }
             dst = reinterpret_cast<char*>(d); src = reinterpret_cast<const char*>(s); n = bytes;
             part = ((bytes / n_threads) + 4095) & ~(size_t)4095;
             n_parts = n_threads;
-            pending = (int)workers.size();
+            pending = n_workers;
             ++gen;
         }
         cv_start.notify_all();
@@ -82,13 +83,17 @@ class CopyPool {
         std::unique_lock<std::mutex> lk(mu);
         cv_done.wait(lk, [&] { return pending == 0; });
     }
-    ~CopyPool() {
-        { std::lock_guard<std::mutex> lk(mu); stop = true; }
-        cv_start.notify_all();
-        for (auto& w : workers) if (w.joinable()) w.join();
-    }
 };
-CopyPool g_copy_pool;
+CopyPool* g_copy_pool_ptr = nullptr;
+std::once_flag g_copy_pool_once;
+void copy_pool_after_fork() { g_copy_pool_ptr = new CopyPool(); }      // the parent's pool (and its locks) are left behind
+CopyPool& copy_pool() {
+    std::call_once(g_copy_pool_once, [] {
+        g_copy_pool_ptr = new CopyPool();
+        pthread_atfork(nullptr, nullptr, copy_pool_after_fork);
+    });
+    return *g_copy_pool_ptr;
+}
 }  // namespace
 
 // `bytes` from the caller's array to the device buffer `dst_dev`
@@ -110,7 +115,7 @@ static int upload_bytes(itjl_ctx* ctx, void* dst_dev, const void* data, size_t b
         const size_t n = bytes - off < kPinChunk ? bytes - off : kPinChunk;
         if (c >= 3) ITJL_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[b]));       // the DMA out of this buffer is done
         char* stage = reinterpret_cast<char*>(ctx->pin[b]);
-        g_copy_pool.copy(stage, src + off, n, n_threads);
+        copy_pool().copy(stage, src + off, n, n_threads);
         ITJL_CUDA(ctx, cudaMemcpyAsync(dst + off, stage, n, cudaMemcpyHostToDevice, ctx->stream));
         ITJL_CUDA(ctx, cudaEventRecord(ctx->pin_ev[b], ctx->stream));
     }
@@ -167,7 +172,7 @@ static int download_large(itjl_ctx* ctx, void* host_dst, const void* dev_src, si
         ITJL_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[c % 3]));
         const char* stage = reinterpret_cast<const char*>(ctx->pin[c % 3]);
         const size_t n = chunk_len(c), off = c * kPinChunk;
-        g_copy_pool.copy(dst + off, stage, n, n_threads);
+        copy_pool().copy(dst + off, stage, n, n_threads);
     }
     return ITJL_OK;
 }
