@@ -82,8 +82,9 @@ typedef struct {
                                 models above 1e8 pairs with >= 32768 new particles: exact fp64 mixture density on an
                                 8192-point grid + 4-point interpolation, ~1e-12); 0 always fp64 pair sums; 1 always fp32
                                 pair sums; 2 always the grid (n_theta = 1) */
-    int32_t psd_v2;          /* 1 (default): PSD models with 4096 < n_t <= 16384 run the warp-specialised kernel k_abc_psd2;
-                                0: always k_abc_psd */
+    int32_t psd_v2;          /* bit 0 (default 1): PSD models with 4096 < n_t <= 16384 run the warp-specialised kernel
+                                k_abc_psd2 (0: always k_abc_psd); bit 1 (default 0): Lomb-Scargle by the direct
+                                O(n_t n_freq) sums instead of the chirp-z transforms */
     double tc_error_bound;   /* 5e-6: bound on the predicted |error| of a trial-mean ACF value of k_abc_acf_tc */
 } itjl_tuning;
 int itjl_tuning_default(itjl_tuning* out);

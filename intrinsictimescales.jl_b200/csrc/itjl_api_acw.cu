@@ -351,6 +351,37 @@ int itjl_psd_periodogram(itjl_ctx* ctx, const double* data, int64_t n_slices, in
     return ITJL_OK;
 }
 
+}  // extern "C"
+
+// Lomb-Scargle spectra of the matrix in ctx->data into out_dev: chirp-z transforms where a 7-smooth length
+// >= n_t + n_freq <= 65536 exists (tuning.psd_v2 bit 1 forces the direct O(n_t n_freq) sums), the direct kernel otherwise
+static int lomb_scargle_dev(itjl_ctx* ctx, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq, double* out_dev) {
+    const int M = (ctx->tuning.psd_v2 & 2) ? 0 : lomb_czt_length(n_t, n_freq);
+    if (M > 0) {
+        const int grid = (int)std::min<int64_t>(n_slices, (int64_t)ctx->sm_count * 2);
+        ITJL_CUDA(ctx, ctx->out3.reserve(lomb_czt_table_elems(n_t, n_freq, M) * sizeof(double2)));
+        ITJL_CUDA(ctx, ctx->out2.reserve(lomb_czt_scratch_elems(n_freq, M, grid) * sizeof(double2)));
+        std::vector<double2> roots((size_t)M);
+        for (int k = 0; k < M; ++k) {
+            const double ang = -2.0 * M_PI * (double)k / (double)M;
+            roots[(size_t)k] = make_double2(cos(ang), sin(ang));
+        }
+        ITJL_CUDA(ctx, cudaMemcpyAsync(ctx->out3.p, roots.data(), roots.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        cudaError_t e = lomb_czt_launch((const double*)ctx->data.p, n_slices, n_t, dt, f0, df, n_freq, M, (double2*)ctx->out3.p,
+                                        (double2*)ctx->out2.p, grid, out_dev, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_lomb_czt: %s", cudaGetErrorString(e));
+        ctx->launches += 2;
+        ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // roots stays alive until here
+        return ITJL_OK;
+    }
+    cudaError_t e = lomb_scargle_launch((const double*)ctx->data.p, n_slices, n_t, dt, f0, df, n_freq, out_dev, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_lomb_scargle: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return ITJL_OK;
+}
+
+extern "C" {
+
 int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n_t, double dt,
                          double f0, double df, int64_t n_freq, double* out) {
     int rc = check_data_args(ctx, data, n_slices, n_t, "itjl_psd_lombscargle");
@@ -366,9 +397,8 @@ int itjl_psd_lombscargle(itjl_ctx* ctx, const double* data, int64_t n_slices, in
     if (rc != ITJL_OK) return rc;
     const size_t obytes = (size_t)n_slices * n_freq * sizeof(double);
     ITJL_CUDA(ctx, ctx->out.reserve(obytes));
-    cudaError_t e = lomb_scargle_launch((const double*)ctx->data.p, n_slices, (int)n_t, dt, f0, df, (int)n_freq, (double*)ctx->out.p, ctx->stream);
-    if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_lomb_scargle: %s", cudaGetErrorString(e));
-    ctx->launches++;
+    rc = lomb_scargle_dev(ctx, n_slices, (int)n_t, dt, f0, df, (int)n_freq, (double*)ctx->out.p);
+    if (rc != ITJL_OK) return rc;
     rc = download_large(ctx, out, ctx->out.p, obytes);
     if (rc != ITJL_OK) return rc;
     ITJL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -504,9 +534,7 @@ int itjl_acw_knee(itjl_ctx* ctx, const double* data, int64_t n_slices, int64_t n
         double f0, df;
         ls_grid(n_t, dt, &f0, &df, &nb);
         ITJL_CUDA(ctx, ctx->out.reserve((size_t)n_slices * nb * sizeof(double)));
-        cudaError_t e = lomb_scargle_launch((const double*)ctx->data.p, n_slices, (int)n_t, dt, f0, df, (int)nb, (double*)ctx->out.p, ctx->stream);
-        if (e != cudaSuccess) return fail(ctx, ITJL_ERR_CUDA, "launch k_lomb_scargle: %s", cudaGetErrorString(e));
-        ctx->launches++;
+        { const int rcl = lomb_scargle_dev(ctx, n_slices, (int)n_t, dt, f0, df, (int)nb, (double*)ctx->out.p); if (rcl != ITJL_OK) return rcl; }
         freqs.resize((size_t)nb);
         for (int64_t k = 0; k < nb; ++k) freqs[(size_t)k] = f0 + df * (double)k;
     }

@@ -119,6 +119,11 @@ cudaError_t abc_pgram_launch(const AbcPgramParams& P, bool osc, size_t smem, cud
 cudaError_t pgram_data_launch(const double* data, int64_t n_slices, int n_t, const FftPlan& plan, const double* window,
                               const double2* roots, double psd_scale, double2* scratch, int grid, double* out, cudaStream_t st);
 // generalised Lomb-Scargle periodogram of stored data with NaN gaps on the grid f0 + k df, k < n_freq
+int lomb_czt_length(int n_t, int n_freq);
+size_t lomb_czt_table_elems(int n_t, int n_freq, int M);
+size_t lomb_czt_scratch_elems(int n_freq, int M, int grid);
+cudaError_t lomb_czt_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq, int M,
+                            double2* tables, double2* scratch, int grid, double* out, cudaStream_t st);
 cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq,
                                 double* out, cudaStream_t st);
 

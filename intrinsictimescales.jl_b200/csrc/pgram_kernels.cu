@@ -291,4 +291,182 @@ cudaError_t lomb_scargle_launch(const double* data, int64_t n_slices, int n_t, d
     return cudaGetLastError();
 }
 
+
+// ---- Lomb-Scargle by chirp-z transforms --------------------------------------------------------------------------
+// The samples sit on the regular grid t = (k + 1) dt with gaps, so the five sums of the periodogram are values of
+//   A_j = sum_k c_k e^{-i w_j t_k},   B_j = sum_k m_k e^{-i w_j t_k},   C_j = sum_k m_k e^{-2 i w_j t_k}
+// (c = centred data with zeros in the gaps, m = the mask of valid samples, w_j = 2 pi (f0 + j df)): three chirp-z
+// (Bluestein) transforms of length-n_t sequences to n_freq equispaced frequencies.  With p = k + 1 and
+// a = f0 dt, b = df dt (in turns):  phase(p, j) = a p + b j p = a p + b (p^2 + j^2 - (j - p)^2) / 2, so
+//   A_j = e^{-2 pi i b j^2 / 2} * sum_p [c_p e^{-2 pi i (a p + b p^2 / 2)}] * e^{+2 pi i b (j - p)^2 / 2}
+// - a convolution, done with two FFTs of a 7-smooth length M >= n_t + n_freq per transform (mixed-radix Stockham,
+// fft_mixed.cuh, fp64, buffers in a per-CTA global scratch area) against the precomputed transform of the chirp
+// filter.  O(M log M) per slice instead of O(n_t n_freq): 2000 x 5000 samples x 12 498 frequencies: 94 -> ~10 ms.
+constexpr int kCztThreads = 256;
+
+struct LsCztParams {
+    const double* data; int64_t n_slices; int n_t, n_freq;
+    double a_turn, b_turn;                // f0 dt, df dt
+    FftPlan plan;                         // length M
+    const double2* roots;                 // M-th roots of unity e^{-2 pi i k / M}
+    double2* chirp_in;                    // [2][n_t]   e^{-2 pi i (a p + b p^2 / 2)} and the same for (2a, 2b), p = k + 1
+    double2* filt;                        // [2][M]     FFT of v1[l] = e^{+2 pi i b l^2 / 2}, v2[l] = e^{+2 pi i b l^2} (l = -n_t .. n_freq - 1, circular)
+    double2* chirp_out;                   // [2][n_freq] e^{-2 pi i b j^2 / 2}, e^{-2 pi i b j^2}
+    double2* scratch;                     // per CTA: 2 M (transform buffers) + 2 n_freq (A, B)
+    double* out;                          // (n_slices x n_freq) column-major
+};
+
+// e^{2 pi i t} for a phase of t turns (|t| up to ~1e5: reduced before sincospi)
+__device__ __forceinline__ Cx<double> cis_turns(double t) {
+    t -= floor(t);
+    double s, c;
+    sincospi(2.0 * t, &s, &c);
+    return {c, s};
+}
+
+// one CTA: the chirps and the transformed filters
+__global__ void __launch_bounds__(kCztThreads) k_lomb_czt_prepare(const __grid_constant__ LsCztParams P) {
+    const int tid = threadIdx.x, M = P.plan.n, n = P.n_t, J = P.n_freq;
+    const double a = P.a_turn, b = P.b_turn;
+    for (int k = tid; k < n; k += kCztThreads) {
+        const double p = (double)(k + 1);
+        const Cx<double> c1 = cis_turns(-(a * p + 0.5 * b * p * p)), c2 = cis_turns(-(2.0 * a * p + b * p * p));
+        P.chirp_in[k] = make_double2(c1.x, c1.y);
+        P.chirp_in[n + k] = make_double2(c2.x, c2.y);
+    }
+    for (int j = tid; j < J; j += kCztThreads) {
+        const double q = (double)j;
+        const Cx<double> c1 = cis_turns(-0.5 * b * q * q), c2 = cis_turns(-b * q * q);
+        P.chirp_out[j] = make_double2(c1.x, c1.y);
+        P.chirp_out[J + j] = make_double2(c2.x, c2.y);
+    }
+    Cx<double>* x = reinterpret_cast<Cx<double>*>(P.scratch);
+    Cx<double>* y = x + M;
+    const RootsTable<double> roots{reinterpret_cast<const Cx<double>*>(P.roots)};
+    for (int which = 0; which < 2; ++which) {
+        const double bb = which == 0 ? 0.5 * b : b;
+        __syncthreads();
+        for (int i = tid; i < M; i += kCztThreads) {
+            // circular index i <-> lag l: l = i for i < n_freq, l = i - M for i >= M - n_t, nothing in between
+            Cx<double> v = {0.0, 0.0};
+            if (i < J) { const double l = (double)i; v = cis_turns(bb * l * l); }
+            else if (i >= M - n) { const double l = (double)(i - M); v = cis_turns(bb * l * l); }
+            x[i] = v;
+        }
+        __syncthreads();
+        const Cx<double>* z = fft_mixed_cta<double>(P.plan, x, y, roots);
+        for (int i = tid; i < M; i += kCztThreads) P.filt[(size_t)which * M + i] = make_double2(z[i].x, z[i].y);
+    }
+}
+
+__global__ void __launch_bounds__(kCztThreads) k_lomb_czt(const __grid_constant__ LsCztParams P) {
+    __shared__ double red[3][kCztThreads / 32];
+    const int tid = threadIdx.x, M = P.plan.n, n = P.n_t, J = P.n_freq;
+    Cx<double>* buf0 = reinterpret_cast<Cx<double>*>(P.scratch) + (size_t)blockIdx.x * (2 * (size_t)M + 2 * (size_t)J);
+    Cx<double>* buf1 = buf0 + M;
+    Cx<double>* SA = buf1 + M;
+    Cx<double>* SB = SA + J;
+    const RootsTable<double> roots{reinterpret_cast<const Cx<double>*>(P.roots)};
+    const double inv_m = 1.0 / (double)M;
+    for (int64_t s = blockIdx.x; s < P.n_slices; s += gridDim.x) {
+        const double* col = P.data + s;
+        const size_t ld = (size_t)P.n_slices;
+        // mean over the valid samples (center_data), their count, and sum c^2
+        double sum = 0.0, cnt = 0.0;
+        for (int k = tid; k < n; k += kCztThreads) { const double v = col[(size_t)k * ld]; if (v == v) { sum += v; cnt += 1.0; } }
+        sum = warp_sum(sum); cnt = warp_sum(cnt);
+        __syncthreads();
+        if ((tid & 31) == 0) { red[0][tid >> 5] = sum; red[1][tid >> 5] = cnt; }
+        __syncthreads();
+        sum = 0.0; cnt = 0.0;
+#pragma unroll
+        for (int w = 0; w < kCztThreads / 32; ++w) { sum += red[0][w]; cnt += red[1][w]; }
+        const double mean = sum / cnt;
+        double yy = 0.0;
+        for (int k = tid; k < n; k += kCztThreads) { const double v = col[(size_t)k * ld]; if (v == v) yy = fma(v - mean, v - mean, yy); }
+        yy = warp_sum(yy);
+        if ((tid & 31) == 0) red[2][tid >> 5] = yy;
+        __syncthreads();
+        yy = 0.0;
+#pragma unroll
+        for (int w = 0; w < kCztThreads / 32; ++w) yy += red[2][w];
+
+        for (int tr = 0; tr < 3; ++tr) {
+            const double2* cin = P.chirp_in + (tr == 2 ? n : 0);
+            const double2* flt = P.filt + (tr == 2 ? (size_t)M : 0);
+            const double2* cout = P.chirp_out + (tr == 2 ? J : 0);
+            // u[p] = value_{p-1} * chirp_in[p-1] at index p = 1 .. n_t, zero elsewhere
+            for (int i = tid; i < M; i += kCztThreads) {
+                Cx<double> u = {0.0, 0.0};
+                if (i >= 1 && i <= n) {
+                    const double v = col[(size_t)(i - 1) * ld];
+                    if (v == v) {
+                        const double val = tr == 0 ? v - mean : 1.0;
+                        const double2 c = cin[i - 1];
+                        u = {val * c.x, val * c.y};
+                    }
+                }
+                buf0[i] = u;
+            }
+            __syncthreads();
+            Cx<double>* z = fft_mixed_cta<double>(P.plan, buf0, buf1, roots);
+            Cx<double>* other = z == buf0 ? buf1 : buf0;
+            // inverse transform of z * filt by conjugation: ifft(x) = conj(fft(conj(x))) / M
+            for (int i = tid; i < M; i += kCztThreads) {
+                const double2 f = flt[i];
+                const Cx<double> pz = z[i];
+                z[i] = {pz.x * f.x - pz.y * f.y, -(pz.x * f.y + pz.y * f.x)};
+            }
+            __syncthreads();
+            const Cx<double>* w = fft_mixed_cta<double>(P.plan, z, other, roots);
+            for (int j = tid; j < J; j += kCztThreads) {
+                const double wr = w[j].x * inv_m, wi = -w[j].y * inv_m;
+                const double2 c = cout[j];
+                const Cx<double> r = {wr * c.x - wi * c.y, wr * c.y + wi * c.x};
+                if (tr == 0) SA[j] = r;
+                else if (tr == 1) SB[j] = r;
+                else {
+                    // sums of the periodogram (weights 1 / n_valid, Y = 0 after centring): cos <-> Re, sin <-> -Im
+                    const double wgt = 1.0 / cnt;
+                    const Cx<double> A = SA[j], B = SB[j];
+                    const double C = B.x * wgt, S = -B.y * wgt, YC = A.x * wgt, YS = -A.y * wgt, YY = yy * wgt;
+                    double CC = 0.5 * (cnt + r.x) * wgt, CS = -0.5 * r.y * wgt;
+                    const double SS = (1.0 - CC) - S * S;
+                    CC -= C * C; CS -= C * S;
+                    const double D = CC * SS - CS * CS;
+                    double pw = (SS * YC * YC + CC * YS * YS - 2.0 * CS * YC * YS) / (YY * D);
+                    if (!(D > 1e-12 * (CC + SS) * (CC + SS))) pw = SS < CC ? YC * YC / (YY * CC) : YS * YS / (YY * SS);
+                    P.out[s + (size_t)j * ld] = pw;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// chirp-z plan: transform length (0 when the direct kernel has to be used), device memory needs in double2 units
+int lomb_czt_length(int n_t, int n_freq) {
+    if (n_freq < 64 || (long long)n_t + n_freq > 65536) return 0;
+    const int M = next_fast_len(n_t + n_freq);
+    FftPlan plan;
+    return (M <= 65536 && fft_plan_make(M, &plan)) ? M : 0;
+}
+size_t lomb_czt_table_elems(int n_t, int n_freq, int M) { return (size_t)M + 2 * (size_t)n_t + 2 * (size_t)M + 2 * (size_t)n_freq; }
+size_t lomb_czt_scratch_elems(int n_freq, int M, int grid) { return (size_t)grid * (2 * (size_t)M + 2 * (size_t)n_freq); }
+
+// tables: [roots M | chirp_in 2 n_t | filt 2 M | chirp_out 2 n_freq] (roots are written by the caller)
+cudaError_t lomb_czt_launch(const double* data, int64_t n_slices, int n_t, double dt, double f0, double df, int n_freq, int M,
+                            double2* tables, double2* scratch, int grid, double* out, cudaStream_t st) {
+    LsCztParams P{};
+    P.data = data; P.n_slices = n_slices; P.n_t = n_t; P.n_freq = n_freq; P.a_turn = f0 * dt; P.b_turn = df * dt;
+    if (!fft_plan_make(M, &P.plan)) return cudaErrorInvalidValue;
+    P.roots = tables; P.chirp_in = tables + M; P.filt = P.chirp_in + 2 * (size_t)n_t; P.chirp_out = P.filt + 2 * (size_t)M;
+    P.scratch = scratch; P.out = out;
+    k_lomb_czt_prepare<<<1, kCztThreads, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_lomb_czt<<<grid, kCztThreads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
 }  // namespace itjl

@@ -108,3 +108,28 @@ def test_lombscargle_on_data_with_gaps(pkg, ctx, n_slices, n_t, dt):
     assert np.all(np.isfinite(got))
     assert np.max(np.abs(got - want)) < 1e-9
     assert np.all(got >= -1e-12) and np.all(got <= 1.0 + 1e-12)
+
+
+@pytest.mark.parametrize("n_slices,n_t,dt", [(5, 1000, 0.01), (3, 777, 0.002), (4, 5000, 0.01), (3, 18000, 0.001)])
+def test_lombscargle_chirp_z_matches_direct_sums(pkg, ctx, n_slices, n_t, dt):
+    """The default path evaluates the Lomb-Scargle sums as chirp-z transforms (k_lomb_czt, O(M log M) per slice);
+    tuning.psd_v2 bit 1 forces the direct O(n_t n_freq) sums (k_lomb_scargle): both must agree to rounding, and with the
+    oracle, on even / odd / long records, with gaps at the edges and a slice that is nearly all missing."""
+    rng = np.random.default_rng(n_t + 1)
+    t = dt * np.arange(1, n_t + 1)
+    data = np.sin(2 * np.pi * (0.07 / dt) * t)[None, :] + rng.standard_normal((n_slices, n_t)).cumsum(axis=1) * 0.05 + 3.0
+    data[0, : n_t // 7] = np.nan                       # gap at the start
+    data[1, -n_t // 9:] = np.nan                       # gap at the end
+    data[2, rng.random(n_t) < 0.8] = np.nan            # mostly missing
+    mask = np.isnan(data)
+    n0 = ctx.launch_count
+    got, gf = pkg.comp_psd_lombscargle(t, data, mask, dt, ctx=ctx)
+    assert ctx.launch_count - n0 == 2                  # prepare + transform kernel (no relayout: slice-fastest input)
+    with ctx.tuned(psd_v2=3):
+        direct, df_ = pkg.comp_psd_lombscargle(t, data, mask, dt, ctx=ctx)
+    assert np.array_equal(gf, df_) and got.shape == direct.shape
+    print(f"n_t={n_t}: chirp-z vs direct max abs diff {np.max(np.abs(got - direct)):.2e}")
+    assert np.max(np.abs(got - direct)) < 1e-10
+    if n_t <= 5000:
+        want, _ = osum.comp_psd_lombscargle(t, data, mask, dt)
+        assert np.max(np.abs(got - want)) < 1e-9
