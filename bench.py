@@ -279,7 +279,7 @@ def sub_knee(pkg, ctx, cpu):
     """f3: acw(data, fs; acwtypes = :knee) - periodogram of every slice + FOOOF-style knee fit, 2000 x 5000."""
     fs, n = 100.0, 2000
     d = np.asfortranarray(ou_rows(np.random.default_rng(8), n, 5000, 0.3, 1.0 / fs))
-    pkg.acw(d[:64], fs, acwtypes="knee", ctx=ctx)
+    pkg.acw(d, fs, acwtypes="knee", ctx=ctx)                 # warm-up at full size: the context's buffers grow here
     n0 = ctx.launch_count
     t0 = time.perf_counter()
     r = pkg.acw(d, fs, acwtypes="knee", ctx=ctx)
