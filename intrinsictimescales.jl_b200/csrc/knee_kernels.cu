@@ -53,6 +53,17 @@ __device__ __forceinline__ double block_max(double v, KneeShared* sh) { return -
 __device__ __forceinline__ int block_max_int(int v, KneeShared* sh) { return (int)block_max((double)v, sh); }
 __device__ __forceinline__ int block_min_int(int v, KneeShared* sh) { return (int)block_min((double)v, sh); }
 
+// 1 / d for d >= 1 (finite): hardware seed (~20 bits) + two Newton steps, within ~1 ulp of the correctly rounded
+// quotient - the objective loop is bound by the FP64 pipe and a full-precision division costs about twice as many
+// DP operations (no special cases can occur here: d = 1 + (f / knee)^2)
+__device__ __forceinline__ double rcp_ge1(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+}
+
 // mean |model(f_i; x) - y_i| over the row; MODEL 0: Lorentzian x = (log amp, log knee), knee clamped to fmax;
 // MODEL 1: Gaussian x = (amp, centre, log sd)
 template <int MODEL>
@@ -68,14 +79,14 @@ __device__ __forceinline__ double l1_objective(const double* __restrict__ y, con
         for (; i + 3 * T < n; i += 4 * T) {
             const double t0 = f[i] * ik, t1 = f[i + T] * ik, t2 = f[i + 2 * T] * ik, t3 = f[i + 3 * T] * ik;
             const double y0 = y[i], y1 = y[i + T], y2 = y[i + 2 * T], y3 = y[i + 3 * T];
-            a0 += fabs(amp / fma(t0, t0, 1.0) - y0);
-            a1 += fabs(amp / fma(t1, t1, 1.0) - y1);
-            a2 += fabs(amp / fma(t2, t2, 1.0) - y2);
-            a3 += fabs(amp / fma(t3, t3, 1.0) - y3);
+            a0 += fabs(fma(amp, rcp_ge1(fma(t0, t0, 1.0)), -y0));
+            a1 += fabs(fma(amp, rcp_ge1(fma(t1, t1, 1.0)), -y1));
+            a2 += fabs(fma(amp, rcp_ge1(fma(t2, t2, 1.0)), -y2));
+            a3 += fabs(fma(amp, rcp_ge1(fma(t3, t3, 1.0)), -y3));
         }
         for (; i < n; i += T) {
             const double t = f[i] * ik;
-            a0 += fabs(amp / fma(t, t, 1.0) - y[i]);
+            a0 += fabs(fma(amp, rcp_ge1(fma(t, t, 1.0)), -y[i]));
         }
     } else {
         // Gaussian: beyond 10 sd of the centre the model is < 2e-22 of its amplitude and |model - y| == |y| to the last
