@@ -165,3 +165,30 @@ def test_tensor_core_plan_selection_is_host_logic(pkg):
     rc, p = plan(10000, 430, 100)                     # longer trials: fewer simulate groups fit
     assert rc == 0 and 1 <= p["groups"] < 4 and p["ksteps"] == 5
     assert plan(8, 4, 2)[0] == -1 and plan(5000, 6000, 2)[0] == -1
+
+
+def test_spectrum_grid_helpers_match_the_oracle(pkg):
+    """Host-side helpers of the PSD side (no device work): nextfastfft, the Lomb-Scargle autofrequency grid, knee <-> tau,
+    the Lorentzian - against the oracle's restatements and closed forms."""
+    from oracle import knee as oknee
+    from oracle import summary as osum
+    for n in list(range(1, 400)) + [4999, 5000, 5001, 9973, 10000, 16385, 65536]:
+        m = pkg.nextfastfft(n)
+        assert m == osum.nextfastfft(n) and m >= n
+        r = m
+        for p in (2, 3, 5, 7):
+            while r % p == 0:
+                r //= p
+        assert r == 1                                         # 7-smooth
+    for n_t, dt in ((1000, 0.01), (777, 0.002), (5000, 0.002)):
+        t = dt * np.arange(1, n_t + 1)
+        f0, df, n = pkg.lombscargle_autofrequency(t, 1.0 / (2 * dt))
+        want = osum.lombscargle_autofrequency(t, 1.0 / (2 * dt))
+        grid = f0 + df * np.arange(n)
+        assert np.allclose(grid, want, rtol=1e-13, atol=0) and grid[-1] <= 1.0 / (2 * dt) * (1 + 1e-12)
+        assert np.isclose(df, 1.0 / (5 * (t[-1] - t[0])), rtol=1e-14) and np.isclose(f0, df / 2, rtol=1e-14)
+    k = np.array([0.5, 3.0, 40.0])
+    assert np.allclose(pkg.tau_from_knee(k), 1.0 / (2 * np.pi * k)) and np.allclose(pkg.knee_from_tau(pkg.tau_from_knee(k)), k)
+    f = np.linspace(0.1, 50, 200)
+    assert np.allclose(pkg.lorentzian(f, [3.0, 7.0]), oknee.lorentzian(f, [3.0, 7.0]), rtol=1e-15)
+    assert np.isclose(pkg.lorentzian(np.array([7.0]), [3.0, 7.0])[0], 1.5)          # half power at the knee
