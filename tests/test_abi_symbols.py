@@ -51,3 +51,36 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "itjl_oracle" not in src, f
+
+
+def _declarations():
+    """name -> list of C parameter types, parsed from the header (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "itjl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(itjl_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        params = [p.strip() for p in m.group(2).split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        out[m.group(1)] = params
+    return out
+
+
+def test_ctypes_signatures_agree_with_the_header(pkg):
+    """Arity and type class of every parameter: a pointer in the header is a void pointer in the table, an integer /
+    floating type the ctypes type of the same width."""
+    decl = _declarations()
+    assert set(decl) == set(pkg._lib.SIGNATURES)
+    scalar = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32,
+              "uint64_t": ctypes.c_uint64, "double": ctypes.c_double}
+    for name, params in decl.items():
+        _, argtypes = pkg._lib.SIGNATURES[name]
+        assert len(argtypes) == len(params), f"{name}: {len(params)} parameters in the header, {len(argtypes)} in the ctypes table"
+        for p, a in zip(params, argtypes):
+            if "*" in p:
+                assert a in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(a, ctypes._Pointer), f"{name}: `{p}` is a pointer"
+            else:
+                ctype = re.sub(r"\bconst\b", "", p).split()[0]
+                assert ctype in scalar, f"{name}: unrecognised scalar type in `{p}`"
+                assert ctypes.sizeof(a) == ctypes.sizeof(scalar[ctype]) and (a is ctypes.c_double) == (ctype == "double"), \
+                    f"{name}: `{p}` bound as {a.__name__}"
