@@ -84,3 +84,12 @@ def test_ctypes_signatures_agree_with_the_header(pkg):
                 assert ctype in scalar, f"{name}: unrecognised scalar type in `{p}`"
                 assert ctypes.sizeof(a) == ctypes.sizeof(scalar[ctype]) and (a is ctypes.c_double) == (ctype == "double"), \
                     f"{name}: `{p}` bound as {a.__name__}"
+
+
+def test_documents_name_only_symbols_the_header_declares():
+    """INTEGRATION.md (the Julia-side binding), DESIGN.md and README.md may only cite itjl_* names that exist."""
+    header = open(os.path.join(ROOT, "include", "itjl_b200.h")).read()
+    known = set(re.findall(r"\bitjl_[a-z0-9_]+", header)) | {"itjl_oracle", "itjl_b200"}
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        cited = set(re.findall(r"\bitjl_[a-z0-9_]+", open(os.path.join(ROOT, doc)).read()))
+        assert cited <= known, f"{doc} cites names the header does not declare: {sorted(cited - known)}"
